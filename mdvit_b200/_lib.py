@@ -1,0 +1,62 @@
+"""ctypes binding of libmdvit_b200.so (the C ABI declared in include/mdvit_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmdvit_b200.so")
+
+c_void_p, c_int, c_float, c_uint32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint32
+
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_HSWISH = 0, 1, 2, 3
+
+
+class GemmEpi(ctypes.Structure):
+    _fields_ = [
+        ("bias", c_void_p), ("residual", c_void_p), ("mul_gelu_grad", c_void_p), ("out_preact", c_void_p),
+        ("out", c_void_p), ("rowscale", c_void_p), ("rng", c_void_p),
+        ("ld_res", c_int), ("ld_mul", c_int), ("ld_preact", c_int), ("ldc", c_int),
+        ("rows_per_scale", c_int), ("out_bf16", c_int), ("act", c_int), ("accumulate", c_int),
+        ("dropout_p", c_float), ("drop_stream", c_uint32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(mdvit_b200 has no CPU or PyTorch fallback path)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name in dir(_lib):
+            pass
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class MdvError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc > 0:
+            msg = f"CUDA error {rc}"
+        else:
+            msg = {-1: "invalid argument", -2: "unsupported shape", -3: "driver entry point unavailable"}.get(rc, str(rc))
+        raise MdvError(f"{what} failed: {msg}")

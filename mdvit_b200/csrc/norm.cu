@@ -1,0 +1,393 @@
+// LayerNorm (token-wise) and BatchNorm (channel-wise, train + eval) kernels — HBM-bound, warp-shuffle reduced.
+// LayerNorm: reference mdvit.py:349,357 (nn.LayerNorm eps=1e-6).  BatchNorm2d (+Hardswish/ReLU): mpvit.py:119-122,
+// mdvit.py:120-121,559-563, Decoders.py:60-61,306-307.
+#include "../../include/mdvit_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_MAXV = 8;  // float2 per lane -> C <= 512
+
+// ---------------------------------------------------------------------------------- LayerNorm forward
+// one warp per row; the row lives in registers (C/32 values per lane).
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, bf16* __restrict__ y,
+                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nv = C >> 6;
+    const float* xr = x + (size_t)row * C;
+    float2 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float2*>(xr + i * 64 + lane * 2);
+            s += v[i].x + v[i].y;
+        }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (i < nv) {
+            float a = v[i].x - mean, b = v[i].y - mean;
+            q += a * a + b * b;
+        }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    bf16* yr = y + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (i < nv) {
+            const int c = i * 64 + lane * 2;
+            float2 g = *reinterpret_cast<const float2*>(gamma + c), b = *reinterpret_cast<const float2*>(beta + c);
+            *reinterpret_cast<uint32_t*>(yr + c) = f2_to_bf2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+        }
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
+// ---------------------------------------------------------------------------------- LayerNorm backward
+// dx = dres + rstd * (gy - mean(gy) - xhat * mean(gy*xhat)),  gy = dy*gamma;  dgamma += sum dy*xhat; dbeta += sum dy.
+// Optional dx_masked = bf16(dx * rowscale[row / rows_per_scale] * dropout_mask) feeds the previous Linear's dgrad/wgrad.
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
+                                                      float* __restrict__ dx, bf16* __restrict__ dx_masked,
+                                                      const float* __restrict__ rowscale, int rows_per_scale, float drop_p,
+                                                      const unsigned long long* __restrict__ rng, uint32_t drop_stream,
+                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C) {
+    __shared__ float red[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nv = C >> 6;
+    float2 ag[LN_MAXV], ab[LN_MAXV], gm[LN_MAXV];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        ag[i] = make_float2(0.f, 0.f);
+        ab[i] = make_float2(0.f, 0.f);
+        if (i < nv) gm[i] = *reinterpret_cast<const float2*>(gamma + i * 64 + lane * 2);
+    }
+    uint32_t dthr = 0, dkey = 0;
+    float dinv = 1.f;
+    if (dx_masked && drop_p > 0.f) {
+        dthr = drop_thresh(drop_p);
+        dinv = 1.f / (1.f - drop_p);
+        dkey = rng_key(rng, drop_stream);
+    }
+    for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const size_t off = (size_t)row * C;
+        float2 d[LN_MAXV], xh[LN_MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i)
+            if (i < nv) {
+                const int c = i * 64 + lane * 2;
+                d[i] = *reinterpret_cast<const float2*>(dy + off + c);
+                float2 xv = *reinterpret_cast<const float2*>(x + off + c);
+                xh[i] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
+                ag[i].x += d[i].x * xh[i].x;
+                ag[i].y += d[i].y * xh[i].y;
+                ab[i].x += d[i].x;
+                ab[i].y += d[i].y;
+                d[i].x *= gm[i].x;
+                d[i].y *= gm[i].y;
+                s1 += d[i].x + d[i].y;
+                s2 += d[i].x * xh[i].x + d[i].y * xh[i].y;
+            }
+        s1 = warp_sum(s1) / C;
+        s2 = warp_sum(s2) / C;
+        const float rs = rowscale ? rowscale[row / rows_per_scale] : 1.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i)
+            if (i < nv) {
+                const int c = i * 64 + lane * 2;
+                float o0 = rstd * (d[i].x - s1 - xh[i].x * s2), o1 = rstd * (d[i].y - s1 - xh[i].y * s2);
+                if (dres) {
+                    float2 r = *reinterpret_cast<const float2*>(dres + off + c);
+                    o0 += r.x;
+                    o1 += r.y;
+                }
+                *reinterpret_cast<float2*>(dx + off + c) = make_float2(o0, o1);
+                if (dx_masked) {
+                    float m0 = rs, m1 = rs;
+                    if (dthr) {
+                        m0 *= drop_scale(dkey, off + c, dthr, dinv);
+                        m1 *= drop_scale(dkey, off + c + 1, dthr, dinv);
+                    }
+                    *reinterpret_cast<uint32_t*>(dx_masked + off + c) = f2_to_bf2(o0 * m0, o1 * m1);
+                }
+            }
+    }
+    // column reductions across the block's warps, then one atomic per column per block
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+        if (i < nv) {
+            for (int pass = 0; pass < 2; ++pass) {
+                float2 val = pass == 0 ? ag[i] : ab[i];
+                __syncthreads();
+                red[warp][lane * 2] = val.x;
+                red[warp][lane * 2 + 1] = val.y;
+                __syncthreads();
+                if (warp == 0) {
+                    float t0 = 0.f, t1 = 0.f;
+                    for (int w = 0; w < nwarp; ++w) {
+                        t0 += red[w][lane * 2];
+                        t1 += red[w][lane * 2 + 1];
+                    }
+                    float* dst = (pass == 0 ? dgamma : dbeta) + i * 64 + lane * 2;
+                    atomicAdd(dst, t0);
+                    atomicAdd(dst + 1, t1);
+                }
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------- BatchNorm
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == MDV_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == MDV_ACT_HSWISH) return hardswish_f(v);
+    return v;
+}
+__device__ __forceinline__ float act_bwd(float v, int act) {
+    if (act == MDV_ACT_RELU) return v > 0.f ? 1.f : 0.f;
+    if (act == MDV_ACT_HSWISH) return hardswish_grad(v);
+    return 1.f;
+}
+
+// sums[c] += sum_m z[m,c]; sums[C+c] += sum_m z[m,c]^2   (double accumulators; block = 32 channels x 8 row lanes)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, double* __restrict__ sums, int M, int C,
+                                                        int rows_per_block) {
+    __shared__ float sh[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f, q = 0.f;
+    if (c < C)
+        for (int r = r0 + ty; r < r1; r += 8) {
+            float v = __ldg(z + (size_t)r * C + c);
+            s += v;
+            q += v * v;
+        }
+    sh[0][ty][tx] = s;
+    sh[1][ty][tx] = q;
+    __syncthreads();
+    if (ty < 2 && c < C) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sh[ty][i][tx];
+        atomicAdd(sums + ty * C + c, (double)t);
+    }
+}
+
+// train: mean/rstd from batch sums + running-stat update (unbiased var), eval: from running stats.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int M, int C, float eps, float momentum, int training,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches, float* __restrict__ mean, float* __restrict__ rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && num_batches) *num_batches += 1;
+    if (c >= C) return;
+    if (training) {
+        double mu = sums[c] / M;
+        double var = sums[C + c] / M - mu * mu;
+        if (var < 0) var = 0;
+        mean[c] = (float)mu;
+        rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+            double unb = M > 1 ? var * M / (M - 1) : var;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    } else {
+        mean[c] = running_mean[c];
+        rstd[c] = rsqrtf(running_var[c] + eps);
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int act, TO* __restrict__ y,
+                                                          long long total, int C) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    float4 v = *reinterpret_cast<const float4*>(z + i);
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cc = c + j;
+        o[j] = act_fwd((o[j] - __ldg(mean + cc)) * __ldg(rstd + cc) * __ldg(gamma + cc) + __ldg(beta + cc), act);
+    }
+    if (sizeof(TO) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + i) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        uint2 pk = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + i) = pk;
+    }
+}
+
+// sums[c] += sum g, sums[C+c] += sum g*xhat with g = dy * act'(bn(z))
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             int act, double* __restrict__ sums, int M, int C, int rows_per_block) {
+    __shared__ float sh[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f, q = 0.f;
+    if (c < C) {
+        const float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
+        for (int r = r0 + ty; r < r1; r += 8) {
+            const size_t o = (size_t)r * C + c;
+            const float xh = (__ldg(z + o) - mu) * rs;
+            const float gg = __ldg(dy + o) * act_bwd(xh * g + b, act);
+            s += gg;
+            q += gg * xh;
+        }
+    }
+    sh[0][ty][tx] = s;
+    sh[1][ty][tx] = q;
+    __syncthreads();
+    if (ty < 2 && c < C) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sh[ty][i][tx];
+        atomicAdd(sums + ty * C + c, (double)t);
+    }
+}
+
+// coef[c] = sum_g / M, coef[C+c] = sum_gxhat / M;  dgamma += sum_gxhat; dbeta += sum_g
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int M, int C, float* __restrict__ coef,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    coef[c] = (float)(sums[c] / M);
+    coef[C + c] = (float)(sums[C + c] / M);
+    if (dbeta) atomicAdd(dbeta + c, (float)sums[c]);
+    if (dgamma) atomicAdd(dgamma + c, (float)sums[C + c]);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            int act, const float* __restrict__ coef, TO* __restrict__ dz,
+                                                            long long total, int C) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    float4 zv = *reinterpret_cast<const float4*>(z + i);
+    float4 dv = *reinterpret_cast<const float4*>(dy + i);
+    float zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cc = c + j;
+        const float rs = __ldg(rstd + cc), g = __ldg(gamma + cc);
+        const float xh = (zz[j] - __ldg(mean + cc)) * rs;
+        const float gg = dd[j] * act_bwd(xh * g + __ldg(beta + cc), act);
+        o[j] = g * rs * (gg - __ldg(coef + cc) - xh * __ldg(coef + C + cc));
+    }
+    if (sizeof(TO) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dz) + i) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dz) + i) = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
+    }
+}
+
+int stats_rows_per_block(int M, int C) {
+    // aim at ~4 waves of 148 SMs
+    int col_blocks = mdv_cdiv(C, 32);
+    int want = (8 * MDV_NUM_SMS) / col_blocks;
+    if (want < 1) want = 1;
+    int rpb = mdv_cdiv(M, want);
+    if (rpb < 64) rpb = 64;
+    return rpb;
+}
+
+}  // namespace
+
+extern "C" int mdv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16, float* mean,
+                                 float* rstd, int M, int C, void* stream) {
+    if (!x || !y_bf16 || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
+    ln_fwd_kernel<<<mdv_cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, (bf16*)y_bf16, mean, rstd, M, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                 const float* dres, float* dx, void* dx_masked_bf16, const float* rowscale,
+                                 int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* dgamma,
+                                 float* dbeta, int M, int C, void* stream) {
+    if (!dy || !x || !dx || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
+    int blocks = mdv_cdiv(M, 8);
+    if (blocks > 4 * MDV_NUM_SMS) blocks = 4 * MDV_NUM_SMS;
+    ln_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, mean, rstd, gamma, dres, dx, (bf16*)dx_masked_bf16, rowscale,
+                                                             rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
+                                                             (const unsigned long long*)rng, drop_stream, dgamma, dbeta, M, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+// ws: >= 2*C doubles (zeroed here).  Writes mean[C], rstd[C]; in training also updates the running buffers.
+extern "C" int mdv_bn_stats(const float* z, int M, int C, float eps, float momentum, int training, float* running_mean,
+                            float* running_var, long long* num_batches_tracked, float* mean, float* rstd, void* ws,
+                            void* stream) {
+    if (!mean || !rstd || M <= 0 || C <= 0) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (training) {
+        if (!z || !ws) return MDV_ERR_ARG;
+        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+        if (e != cudaSuccess) return (int)e;
+        const int rpb = stats_rows_per_block(M, C);
+        dim3 grid(mdv_cdiv(C, 32), mdv_cdiv(M, rpb));
+        bn_stats_kernel<<<grid, 256, 0, st>>>(z, (double*)ws, M, C, rpb);
+        MDV_CHECK_LAUNCH();
+    } else if (!running_mean || !running_var) {
+        return MDV_ERR_ARG;
+    }
+    bn_finalize_kernel<<<mdv_cdiv(C, 128), 128, 0, st>>>((const double*)ws, M, C, eps, momentum, training, running_mean,
+                                                         running_var, num_batches_tracked, mean, rstd);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                              int act, void* y, int y_bf16, int M, int C, void* stream) {
+    if (!z || !y || M <= 0 || (C & 3)) return MDV_ERR_ARG;
+    const long long total = (long long)M * C;
+    const int blocks = mdv_cdiv(total / 4, 256);
+    if (y_bf16)
+        bn_act_fwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(z, mean, rstd, gamma, beta, act, (bf16*)y, total, C);
+    else
+        bn_act_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(z, mean, rstd, gamma, beta, act, (float*)y, total, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+// ws: >= 2*C doubles + 2*C floats.  dz = d(loss)/dz for y = act(BN_train(z)); dgamma/dbeta accumulate.
+extern "C" int mdv_bn_act_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C,
+                              void* ws, void* stream) {
+    if (!dy || !z || !dz || !ws || M <= 0 || (C & 3)) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sums = (double*)ws;
+    float* coef = (float*)(sums + 2 * C);
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+    if (e != cudaSuccess) return (int)e;
+    const int rpb = stats_rows_per_block(M, C);
+    dim3 grid(mdv_cdiv(C, 32), mdv_cdiv(M, rpb));
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, act, sums, M, C, rpb);
+    MDV_CHECK_LAUNCH();
+    bn_bwd_finalize_kernel<<<mdv_cdiv(C, 128), 128, 0, st>>>(sums, M, C, coef, dgamma, dbeta);
+    MDV_CHECK_LAUNCH();
+    const long long total = (long long)M * C;
+    const int blocks = mdv_cdiv(total / 4, 256);
+    if (dz_bf16)
+        bn_bwd_apply_kernel<bf16><<<blocks, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C);
+    else
+        bn_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, act, coef, (float*)dz, total, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
