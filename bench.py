@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""MDViT training-throughput benchmark (BASELINE.json metric: MDViT train images/sec at 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch-per-domain B] [--impl reference]
+
+One *step* = the reference's optimizer step (multi_train_MDViT.py:121-213): 4 single-domain mini-batches forward,
+BCE+Dice / MKD losses, the two-pass backward, AdamW — on synthetic 256x256 data, random-init weights, dropout 0.1 /
+DropPath 0.1 as in the trainer (multi_train_MDViT.py:59).  N>1 is launched by torchrun (one rank per GPU, NCCL).
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference (oracle/) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mdvit_train_images_per_sec"
+UNIT = "images/s"
+IMG = 256
+F_TRAIN_GFLOP_PER_IMG = 62.3     # 3 x 20.77 GFLOP algorithmic fwd+bwd per image
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch-per-domain", type=int, default=32)
+    ap.add_argument("--impl", default="mdvit_b200")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch-per-domain", type=int, default=1)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_step_time(batch_per_domain, steps, warmup, threads=None):
+    """The reference algorithm on host cores: oracle/mdvit_oracle.py train step (+AdamW) on a bounded sample."""
+    import torch
+    from mdvit_b200 import synth
+    from mdvit_b200.model import MDViT
+    from oracle import mdvit_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    holder = MDViT(img_size=IMG, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")   # parameter container: reference init
+    sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    for k in list(sd):
+        ck = synth.canonical_key(k)
+        if ck != k:
+            sd[k] = sd[ck]
+    names = [k for k, v in sd.items() if v.requires_grad and synth.canonical_key(k) == k]
+    m = {k: torch.zeros_like(sd[k]) for k in names}
+    v = {k: torch.zeros_like(sd[k]) for k in names}
+    times = []
+    for it in range(warmup + steps):
+        batches = [synth.synth_batch(1234 + it, d, batch_per_domain, IMG, IMG) + (d,) for d in range(4)]
+        t0 = time.perf_counter()
+        _, grads = O.train_step_grads(sd, batches, drop=0.1, dpr=0.1, drop2d=0.1)
+        with torch.no_grad():
+            for k in names:
+                if grads[k] is not None:
+                    O.adamw_step(sd[k], grads[k], m[k], v[k], it + 1)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bpd = args.cpu_batch_per_domain
+    sec, cores = cpu_oracle_step_time(bpd, args.steps, min(args.warmup, 1))
+    val = 4 * bpd / sec
+    sample = f"{4 * bpd} images/step ({bpd}/domain x 4 domains) at {IMG}x{IMG}, fp32, dropout on, {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MDViT(Sup, MLPFM) MKD train step, CPU restatement of the reference (oracle port), {sample}"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def kernel_roofline(peaks, device):
+    """Dominant kernel = the tcgen05 GEMM at the MLPDecoderFM.linear_fuse shape (42.7% of forward FLOPs):
+    M = 32*4096 tokens, K = 2112, N = 512.  Timed alone with CUDA events on the launching stream, L2 flushed between launches."""
+    import ctypes
+    import torch
+    from mdvit_b200 import _lib as L
+    lib = L.lib()
+    M, N, K = 32 * 4096, 512, 2112
+    A = torch.randn(M, K, device=device).bfloat16()
+    W = (torch.randn(N, K, device=device) / K ** 0.5).bfloat16()
+    bias = torch.zeros(N, device=device)
+    out = torch.empty(M, N, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    e = L.GemmEpi()
+    e.out, e.ldc, e.out_bf16, e.bias = L.ptr(out), N, 0, L.ptr(bias)
+    st = torch.cuda.current_stream(device)
+    times = []
+    for i in range(8):
+        flush.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
+        t.record(st)
+        t.synchronize()
+        if i >= 3:
+            times.append(s.elapsed_time(t))
+    ms = sum(times) / len(times)
+    achieved = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops"]
+    return {"bound": "tensor", "kernel": "gemm_kernel<BN,NT> (tcgen05) @ linear_fuse M=131072 N=512 K=2112", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (burst)",
+            "ms_per_launch": ms}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from mdvit_b200 import _lib as L
+    from mdvit_b200 import ops, synth
+    from mdvit_b200.model import MDViT
+    from mdvit_b200.train_step import MKDTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — mdvit_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()   # fail loudly if the extension is missing
+    peaks = load_peaks()
+    B = args.batch_per_domain
+
+    torch.manual_seed(0)
+    model = MDViT(img_size=IMG, drop_rate=0.1, drop_path_rate=0.1, adapt_method="Sup", num_domains=4, decoder_name="MLPFM").to(dev).train()
+    ops.manual_seed(1234 + rank, dev)
+    trainer = MKDTrainer(model, lr=1e-4, weight_decay=0.05)
+    # synthetic inputs: per-rank slice of each domain batch, staged in pinned host memory for the e2e arm
+    host = []
+    for d in range(4):
+        img, lab = synth.synth_batch(1234 + 17 * rank, d, B, IMG, IMG)
+        host.append((img.pin_memory(), lab.pin_memory(), d))
+    dev_batches = [(i.to(dev), l.to(dev), d) for i, l, d in host]
+    h2d = sum(i.numel() * 4 + l.numel() * 4 for i, l, _ in host)
+
+    use_graph = not args.no_graph
+    if use_graph:
+        trainer.capture(dev_batches, warmup=1)
+        step_resident = lambda: trainer.step_graph(None)          # noqa: E731  inputs already in the static HBM buffers
+        step_e2e = lambda: trainer.step_graph(host)               # noqa: E731  H2D of this step's inputs inside the timed region
+    else:
+        step_resident = lambda: trainer.step(dev_batches)         # noqa: E731
+        step_e2e = lambda: trainer.step([(i.to(dev, non_blocking=True), l.to(dev, non_blocking=True), d) for i, l, d in host])  # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, read_back):
+        barrier()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss_host = None
+        for _ in range(steps):
+            losses = fn()
+            if read_back:
+                loss_host = losses.to("cpu", non_blocking=False)   # device->host read of the step's result, every step
+        t.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(t)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, loss_host
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    lib = L.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.mdv_launch_count()
+    ms_res, _ = timed(step_resident, args.steps, False)
+    n1 = lib.mdv_launch_count()
+    ms_e2e, loss_host = timed(step_e2e, args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = trainer.launches_per_step if use_graph else (n1 - n0) // max(args.steps, 1)
+
+    imgs_per_step = 4 * B * world
+    value = imgs_per_step / (ms_res * 1e-3)
+    e2e = imgs_per_step / (ms_e2e * 1e-3)
+    if rank == 0:
+        roof = kernel_roofline(peaks, dev)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, cores = cpu_oracle_step_time(args.cpu_batch_per_domain, 2, 1)
+            cpu = {"value": 4 * args.cpu_batch_per_domain / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"oracle (torch fp32 restatement of the reference) train step, {4 * args.cpu_batch_per_domain} images/step "
+                             f"at {IMG}x{IMG}, 1 warm-up + 2 timed steps"}
+        model_tflops = value * F_TRAIN_GFLOP_PER_IMG / 1e3
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"MDViT(adapt_method=Sup, decoder=MLPFM) MKD train step: 4 domains x {B} images/GPU at {IMG}x{IMG}, "
+                                   "dropout 0.1, DropPath 0.1, two-pass backward, AdamW; bf16 tensor-core operands, fp32 accumulate/residual",
+                       "batch_per_domain_per_gpu": B, "images_per_step": imgs_per_step, "parallelism": f"dp{world}",
+                       "cuda_graph": use_graph, "l2": "per-step working set (>10 GB) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * 3 * 4},
+            "gpu_launches": int(launches_per_step * args.steps * 2),
+            "launches_per_step": int(launches_per_step),
+            "model_algorithmic_tflops": model_tflops,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "final_losses_seg_aux_kt_per_domain": loss_host.tolist() if loss_host is not None else None,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ extern "C" {
 #define MDV_ACT_HSWISH 3
 
 int mdv_version(void);
+long long mdv_launch_count(void); /* kernels launched by this library so far (host-side counter) */
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA) */
 /* Epilogue applied to acc = A.W^T, in this order:
@@ -58,6 +59,97 @@ int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, in
 
 /* Debug/tuning knob (0 = automatic): force tile N, pipeline stages, TN split count. */
 int mdv_gemm_tune(int force_bn, int force_stages, int force_split);
+
+/* ------------------------------------------------------------------ LayerNorm (mdvit.py:349,357; eps 1e-6) */
+/* y = bf16(LN(x)); mean/rstd [M] are saved for backward.  C % 64 == 0, C <= 512. */
+int mdv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16, float* mean,
+                      float* rstd, int M, int C, void* stream);
+/* dx = dres + LN'(dy); optional dx_masked = bf16(dx * rowscale[m/rows_per_scale] * dropout_mask) (the gradient of the
+ * preceding Linear's output when proj_drop/DropPath sit between it and the residual add, mdvit.py:311,354);
+ * dgamma/dbeta accumulate (+=). */
+int mdv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* dres, float* dx, void* dx_masked_bf16, const float* rowscale, int rows_per_scale,
+                      float drop_p, const void* rng, uint32_t drop_stream, float* dgamma, float* dbeta, int M, int C,
+                      void* stream);
+
+/* ------------------------------------------------------------------ BatchNorm2d (+act) on [M=B*H*W, C] (mpvit.py:119-122 ...) */
+/* training: batch mean / biased var -> mean,rstd; running stats updated with momentum (unbiased var) and
+ * *num_batches_tracked += 1.  eval: mean,rstd from the running buffers.  ws >= 2*C doubles. */
+int mdv_bn_stats(const float* z, int M, int C, float eps, float momentum, int training, float* running_mean,
+                 float* running_var, long long* num_batches_tracked, float* mean, float* rstd, void* ws, void* stream);
+int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta, int act,
+                   void* y, int y_bf16, int M, int C, void* stream);
+/* dz for y = act(BN_train(z)); ws >= 2*C doubles + 2*C floats; dgamma/dbeta accumulate. */
+int mdv_bn_act_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
+                   void* stream);
+
+/* ------------------------------------------------------------------ stencils (token-major / NHWC) */
+/* depthwise 3x3, pad 1 (ConvPosEnc mpvit.py:244-246 with residual=1; patch-embed dwconv mdvit.py:118).
+ * transposed=1 computes the input gradient of the same conv (in = output gradient on the Ho x Wo grid). */
+int mdv_dwconv3(const float* in, const float* w, const float* bias, void* out, int out_bf16, int B, int Hi, int Wi, int Ho,
+                int Wo, int C, int stride, int transposed, int residual, void* stream);
+int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                      int stride, void* stream);
+/* decoder conv_after.dwconv: 3x3, groups=C over cat(skip, up) (2 inputs per group), Decoders.py:30-38,198-205 */
+int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out_bf16, int B, int H, int W, int C, void* stream);
+int mdv_gconv2_bwd(const float* dout, const float* skip, const float* up, const float* w, float* dskip, float* dup, float* dw,
+                   int B, int H, int W, int C, void* stream);
+/* im2col for dense 3x3 convs (stem mdvit.py:509-526, bridge :557-564): col[(b,yo,xo), (i*3+j)*C + c] */
+int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc,
+                void* stream);
+int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int Hi, int Wi, void* stream);
+int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc, void* stream);
+/* bilinear resize, align_corners=False (mdvit.py:699; Decoders.py:196,319-336) and its exact transpose */
+int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* out, int out_bf16, int ld_out, int B, int Hi, int Wi, int Ho,
+                     int Wo, int C, void* stream);
+int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, float* din, int ld_in, int B, int Hi, int Wi, int Ho, int Wo,
+                     int C, void* stream);
+
+/* ------------------------------------------------------------------ factorized attention + CRPE + DA gate */
+long long mdv_attn_stats_floats(int B, int C, int heads);
+/* qkv bf16 [B,N,3C]; gate fp32 [B,C] or NULL (non-'Sup' attention, mpvit.py:347-373); stats = saved workspace. */
+int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float* crpe_w3, const float* crpe_b3, const float* crpe_w5,
+                 const float* crpe_b5, const float* crpe_w7, const float* crpe_b7, float* stats, void* out_bf16, int B, int H,
+                 int W, int C, int heads, void* stream);
+/* ws: B*C*(2*Ch+1) floats.  dqkv overwritten; dgate and the CRPE gradients accumulate. */
+int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, const float* gate, const float* crpe_w3,
+                 const float* crpe_b3, const float* crpe_w5, const float* crpe_b5, const float* crpe_w7, const float* crpe_b7,
+                 const float* stats, void* dqkv_bf16, float* dgate, float* dcrpe_w3, float* dcrpe_b3, float* dcrpe_w5,
+                 float* dcrpe_b5, float* dcrpe_w7, float* dcrpe_b7, float* ws, int B, int H, int W, int C, int heads,
+                 void* stream);
+/* DA: gate[b,h,v] = softmax_h( W2 relu(W1 label_b + b1) + b2 )  (mdvit.py:272-276,301-303) */
+int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,
+                    float* gate, int B, int nd, int hid, int C, int heads, void* stream);
+int mdv_da_gate_bwd(const float* label, const float* w2, const float* hid_in, const float* gate, const float* dgate, float* dw1,
+                    float* db1, float* dw2, float* db2, int B, int nd, int hid, int C, int heads, void* stream);
+
+/* ------------------------------------------------------------------ heads, reductions, casts */
+/* logits[m] = sum_c x[m,c] w[c] dropout2d(b,c) + bias  — the C->1 1x1 conv commuted in front of the final resize */
+int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const float* bias, float* out, int M, int C, int rows_per_sample,
+                   float drop_p, const void* rng, uint32_t drop_stream, void* stream);
+int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, const float* w, float* dx, float* dw, float* db, int M, int C,
+                   int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream);
+int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, int C, void* stream);  /* out[c] += sum_m x[m,c] */
+int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
+                  int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, void* stream);
+int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate, void* stream);
+/* fp32 master weight -> bf16 GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2 */
+int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream);
+int mdv_unperm_conv_grad(const float* g, int ld, float* dw, int R, int cin, void* stream);
+
+/* ------------------------------------------------------------------ losses (multi_train_MDViT.py:147-169, Utils/losses.py:8-16) */
+/* sums: 8 doubles {bce(p,y), bce(q,y), p.y, p.p, y.y, q.y, q.q, q.p}; all-reduce them across ranks for the global Dice. */
+int mdv_loss_sums(const float* out, const float* aux, const float* label, void* sums, long long n, void* stream);
+int mdv_loss_finalize(const void* sums, double n_total, float* losses /* seg, aux, kt */, void* stream);
+int mdv_loss_bwd(const float* out, const float* aux, const float* label, const void* sums, double n_total, const float* coef,
+                 float* dout, float* daux, long long n, void* stream);
+
+/* ------------------------------------------------------------------ optimizer / RNG */
+/* hyper (device fp32[8]): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale */
+int mdv_adamw(float* p, const float* g, float* m, float* v, const float* hyper, long long n, void* stream);
+int mdv_rng_bump(void* rng /* device uint64[2] {seed, step} */, void* stream);
+int mdv_droppath_scale(float* scale, int B, float p, const void* rng, uint32_t drop_stream, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,9 +35,36 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(mdvit_b200 has no CPU or PyTorch fallback path)")
         _lib = ctypes.CDLL(LIB_PATH)
-        for name in dir(_lib):
-            pass
+        for name, (restype, argtypes) in header_signatures().items():
+            fn = getattr(_lib, name)          # AttributeError here == header/library mismatch
+            fn.restype, fn.argtypes = restype, argtypes
     return _lib
+
+
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mdvit_b200.h")
+_CTYPES = {"int": c_int, "float": c_float, "double": ctypes.c_double, "long long": ctypes.c_longlong,
+           "uint32_t": c_uint32, "void": None}
+
+
+def header_signatures(path=HEADER_PATH):
+    """Parse include/mdvit_b200.h -> {name: (restype, [argtypes])}; every pointer is passed as void*."""
+    import re
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\b(int|long long)\s+(mdv_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(c_void_p)
+                else:
+                    base = a.replace("const ", "").rsplit(" ", 1)[0].strip()
+                    argtypes.append(_CTYPES[base])
+        sigs[name] = (_CTYPES[ret], argtypes)
+    return sigs
 
 
 def ptr(t):
@@ -53,7 +80,15 @@ class MdvError(RuntimeError):
     pass
 
 
+_DEBUG_SYNC = bool(int(os.environ.get("MDV_DEBUG_SYNC", "0")))
+
+
 def check(rc, what):
+    if _DEBUG_SYNC and rc == 0:
+        try:
+            torch.cuda.synchronize()
+        except Exception as ex:  # pragma: no cover - debug aid
+            raise MdvError(f"{what}: asynchronous CUDA failure: {ex}") from ex
     if rc != 0:
         if rc > 0:
             msg = f"CUDA error {rc}"

@@ -11,8 +11,11 @@ typedef __nv_bfloat16 bf16;
 #define MDV_ERR_UNSUPPORTED (-2)
 #define MDV_ERR_DRIVER (-3)
 
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+extern long long g_mdv_launches;
 #define MDV_CHECK_LAUNCH()                          \
     do {                                            \
+        ++g_mdv_launches;                           \
         cudaError_t e__ = cudaGetLastError();       \
         if (e__ != cudaSuccess) return (int)e__;    \
     } while (0)

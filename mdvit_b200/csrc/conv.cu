@@ -1,0 +1,580 @@
+// Token-major (NHWC) stencil kernels: depthwise 3x3 (ConvPosEnc / patch-embed), the decoder's 2-in-per-group 3x3,
+// im2col / col2im for the dense 3x3 convs (stem, bridge -> tcgen05 GEMM), bilinear resize (align_corners=False).
+// All HBM/L2-bound; one thread owns 4 consecutive channels of one pixel so every access is a coalesced 16-byte vector.
+// Reference: mpvit.py:239-248 (ConvPosEnc), mdvit.py:114-123 (DWConv2d_BN), Decoders.py:54-63,194-199,315-336,
+// mdvit.py:509-526,557-564,699.
+#include "../../include/mdvit_b200.h"
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(f2_to_bf2(v.x, v.y), f2_to_bf2(v.z, v.w));
+}
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = bf2_to_f2(u.x), b = bf2_to_f2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void fma4(float4& a, const float4& w, const float4& x) {
+    a.x += w.x * x.x; a.y += w.y * x.y; a.z += w.z * x.z; a.w += w.w * x.w;
+}
+
+// ---------------------------------------------------------------------------------- depthwise 3x3
+// forward:    out[b,yo,xo,c] = bias[c] + sum_ij w[c,i,j] * in[b, yo*s-1+i, xo*s-1+j, c]   (+ in[b,yo,xo,c] if residual)
+// transposed: out[b,y,x,c]   = sum_ij w[c,i,j] * in[b, (y+1-i)/s, (x+1-j)/s, c]           (+ in[b,y,x,c] if residual)
+//             (input-gradient of the forward; `in` is then the output-gradient on the Ho x Wo grid)
+// Weights are staged in shared memory as [9][C].
+template <typename TO>
+__global__ void __launch_bounds__(256) dwconv3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, TO* __restrict__ out, int B, int Hi,
+                                                       int Wi, int Ho, int Wo, int C, int stride, int transposed, int residual) {
+    extern __shared__ float sw[];  // [9][C] then bias [C]
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[(i % 9) * C + i / 9] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[9 * C + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int c4n = C >> 2;
+    const long long total = (long long)B * Ho * Wo * c4n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4n) * 4;
+        long long pix = idx / c4n;
+        const int xo = (int)(pix % Wo);
+        pix /= Wo;
+        const int yo = (int)(pix % Ho);
+        const int b = (int)(pix / Ho);
+        float4 acc = transposed ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(sw + 9 * C + c);
+        const float* inb = in + (size_t)b * Hi * Wi * C;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int yi;
+            if (!transposed) {
+                yi = yo * stride - 1 + i;
+            } else {
+                int t = yo + 1 - i;
+                if (t < 0 || (t % stride)) continue;
+                yi = t / stride;
+            }
+            if (yi < 0 || yi >= Hi) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                int xi;
+                if (!transposed) {
+                    xi = xo * stride - 1 + j;
+                } else {
+                    int t = xo + 1 - j;
+                    if (t < 0 || (t % stride)) continue;
+                    xi = t / stride;
+                }
+                if (xi < 0 || xi >= Wi) continue;
+                fma4(acc, ld4(sw + (i * 3 + j) * C + c), ld4(inb + ((size_t)yi * Wi + xi) * C + c));
+            }
+        }
+        if (residual) {
+            float4 r = ld4(inb + ((size_t)yo * Wi + xo) * C + c);
+            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+        }
+        st4(out + ((size_t)(b * Ho + yo) * Wo + xo) * C + c, acc);
+    }
+}
+
+// weight / bias gradient of the forward above: dw[c,i,j] += sum dy[b,yo,xo,c] * x[b,yo*s-1+i,xo*s-1+j,c]; db[c] += sum dy
+// block = 32 channels x 8 pixel lanes over a chunk of output pixels.
+__global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             float* __restrict__ dw, float* __restrict__ db, int B, int Hi, int Wi,
+                                                             int Ho, int Wo, int C, int stride, int pix_per_block) {
+    __shared__ float sh[8][32][11];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const long long npix = (long long)B * Ho * Wo;
+    const long long p0 = (long long)blockIdx.y * pix_per_block;
+    const long long p1 = min(npix, p0 + pix_per_block);
+    float acc[10];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[t] = 0.f;
+    if (c < C)
+        for (long long p = p0 + ty; p < p1; p += 8) {
+            const int xo = (int)(p % Wo);
+            const int yo = (int)((p / Wo) % Ho);
+            const int b = (int)(p / ((long long)Wo * Ho));
+            const float g = __ldg(dy + (size_t)p * C + c);
+            acc[9] += g;
+            const float* xb = x + (size_t)b * Hi * Wi * C + c;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int yi = yo * stride - 1 + i;
+                if (yi < 0 || yi >= Hi) continue;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int xi = xo * stride - 1 + j;
+                    if (xi < 0 || xi >= Wi) continue;
+                    acc[i * 3 + j] += g * __ldg(xb + ((size_t)yi * Wi + xi) * C);
+                }
+            }
+        }
+#pragma unroll
+    for (int t = 0; t < 10; ++t) sh[ty][tx][t] = acc[t];
+    __syncthreads();
+    // 320 (channel, tap) sums per block, reduced over the 8 pixel lanes
+    for (int o = threadIdx.x; o < 320; o += 256) {
+        const int cc = o / 10, t = o % 10;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += sh[k][cc][t];
+        const int cg = blockIdx.x * 32 + cc;
+        if (cg < C) {
+            if (t < 9) atomicAdd(dw + cg * 9 + t, s);
+            else if (db) atomicAdd(db + cg, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- decoder grouped 3x3 (2 inputs / group)
+// cat = concat(skip[C], up[C]) along channels; out[g] = sum_{t<2} sum_ij w[g,t,i,j] * cat[2g+t] shifted.  Decoders.py:30-38,198-205.
+// cat channel k lives in skip if k < C else in up (k - C).  One thread = one pixel x 2 output groups (= 4 cat channels).
+__global__ void __launch_bounds__(256) gconv2_fwd_kernel(const float* __restrict__ skip, const float* __restrict__ up,
+                                                          const float* __restrict__ w, bf16* __restrict__ out, int B, int H, int W,
+                                                          int C) {
+    const int g2n = C >> 1;
+    const long long total = (long long)B * H * W * g2n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % g2n) * 2;
+        long long pix = idx / g2n;
+        const int x0 = (int)(pix % W);
+        const int y0 = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long long)W * H));
+        const int k = 2 * g;  // first of 4 cat channels
+        const float* src = (k < C ? skip + k : up + (k - C)) + (size_t)b * H * W * C;
+        const float* wg = w + (size_t)g * 18;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int yi = y0 - 1 + i;
+            if (yi < 0 || yi >= H) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int xi = x0 - 1 + j;
+                if (xi < 0 || xi >= W) continue;
+                const float4 v = ld4(src + ((size_t)yi * W + xi) * C);
+                const int t = i * 3 + j;
+                a0 += __ldg(wg + t) * v.x + __ldg(wg + 9 + t) * v.y;
+                a1 += __ldg(wg + 18 + t) * v.z + __ldg(wg + 27 + t) * v.w;
+            }
+        }
+        *reinterpret_cast<uint32_t*>(out + (size_t)pix * C + g) = f2_to_bf2(a0, a1);
+    }
+}
+
+// input gradient: dcat[k=2g+t] [y,x] = sum_ij w[g,t,i,j] * dout[g][y+1-i, x+1-j]; written to dskip / dup (both fp32 [.,C]).
+__global__ void __launch_bounds__(256) gconv2_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                            float* __restrict__ dskip, float* __restrict__ dup, int B, int H, int W,
+                                                            int C) {
+    const int g2n = C >> 1;
+    const long long total = (long long)B * H * W * g2n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % g2n) * 2;
+        long long pix = idx / g2n;
+        const int x0 = (int)(pix % W);
+        const int y0 = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long long)W * H));
+        const float* wg = w + (size_t)g * 18;
+        const float* db_ = dout + (size_t)b * H * W * C + g;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int yi = y0 + 1 - i;
+            if (yi < 0 || yi >= H) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int xi = x0 + 1 - j;
+                if (xi < 0 || xi >= W) continue;
+                const float2 d = *reinterpret_cast<const float2*>(db_ + ((size_t)yi * W + xi) * C);
+                const int t = i * 3 + j;
+                a.x += __ldg(wg + t) * d.x;
+                a.y += __ldg(wg + 9 + t) * d.x;
+                a.z += __ldg(wg + 18 + t) * d.y;
+                a.w += __ldg(wg + 27 + t) * d.y;
+            }
+        }
+        const int k = 2 * g;
+        float* dst = (k < C ? dskip + k : dup + (k - C)) + (size_t)pix * C;
+        st4(dst, a);
+    }
+}
+
+// weight gradient: dw[g,t,i,j] += sum dout[p,g] * cat[p shifted, 2g+t].  block = 32 groups x 8 pixel lanes.
+__global__ void __launch_bounds__(256) gconv2_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ skip,
+                                                            const float* __restrict__ up, float* __restrict__ dw, int B, int H, int W,
+                                                            int C, int pix_per_block) {
+    __shared__ float sh[8][32][19];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int g = blockIdx.x * 32 + tx;
+    const long long npix = (long long)B * H * W;
+    const long long p0 = (long long)blockIdx.y * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+    float acc[18];
+#pragma unroll
+    for (int t = 0; t < 18; ++t) acc[t] = 0.f;
+    if (g < C) {
+        const int k = 2 * g;
+        const float* srcbase = (k < C ? skip + k : up + (k - C));
+        for (long long p = p0 + ty; p < p1; p += 8) {
+            const int x0 = (int)(p % W);
+            const int y0 = (int)((p / W) % H);
+            const int b = (int)(p / ((long long)W * H));
+            const float d = __ldg(dout + (size_t)p * C + g);
+            const float* src = srcbase + (size_t)b * H * W * C;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int yi = y0 - 1 + i;
+                if (yi < 0 || yi >= H) continue;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int xi = x0 - 1 + j;
+                    if (xi < 0 || xi >= W) continue;
+                    const float2 v = *reinterpret_cast<const float2*>(src + ((size_t)yi * W + xi) * C);
+                    acc[i * 3 + j] += d * v.x;
+                    acc[9 + i * 3 + j] += d * v.y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 18; ++t) sh[ty][tx][t] = acc[t];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 32 * 18; o += 256) {
+        const int gg = o / 18, t = o % 18;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += sh[k][gg][t];
+        const int gi = blockIdx.x * 32 + gg;
+        if (gi < C) atomicAdd(dw + (size_t)gi * 18 + t, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------- im2col / col2im (3x3, pad 1)
+// col[(b,yo,xo), (i*3+j)*C + c] = in[b, yo*s-1+i, xo*s-1+j, c]  (0 outside); row pitch ldc >= 9*C (extra columns zeroed).
+template <typename TI>
+__global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in, bf16* __restrict__ col, int B, int Hi, int Wi,
+                                                       int Ho, int Wo, int C, int stride, int ldc) {
+    const int c4n = C >> 2;
+    const int per_row = 9 * c4n;
+    const long long total = (long long)B * Ho * Wo * per_row;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx % per_row);
+        const long long pix = idx / per_row;
+        const int t = r / c4n, c = (r % c4n) * 4;
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long long)Wo * Ho));
+        const int yi = yo * stride - 1 + t / 3, xi = xo * stride - 1 + t % 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v = ld4(in + (((size_t)b * Hi + yi) * Wi + xi) * C + c);
+        st4(col + (size_t)pix * ldc + t * C + c, v);
+    }
+}
+
+// first stem conv: NCHW fp32 image [B,3,H,W] -> col [B*Ho*Wo, 64] bf16, column = (i*3+j)*3 + ci for < 27, zero elsewhere.
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, bf16* __restrict__ col, int B, int Hi,
+                                                           int Wi, int Ho, int Wo) {
+    const long long total = (long long)B * Ho * Wo * 32;  // one thread = 2 columns
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % 32) * 2;
+        const long long pix = idx / 32;
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long long)Wo * Ho));
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int kk = k + u;
+            if (kk < 27) {
+                const int t = kk / 3, ci = kk % 3;
+                const int yi = yo * 2 - 1 + t / 3, xi = xo * 2 - 1 + t % 3;
+                if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v[u] = __ldg(img + (((size_t)b * 3 + ci) * Hi + yi) * Wi + xi);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(col + (size_t)pix * 64 + k) = f2_to_bf2(v[0], v[1]);
+    }
+}
+
+// dx[b,y,x,c] = sum_ij dcol[(b,(y+1-i)/s,(x+1-j)/s), (i*3+j)*C + c]   (gather form of the im2col transpose)
+__global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B, int Hi, int Wi,
+                                                       int Ho, int Wo, int C, int stride, int ldc) {
+    const int c4n = C >> 2;
+    const long long total = (long long)B * Hi * Wi * c4n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4n) * 4;
+        const long long pix = idx / c4n;
+        const int x = (int)(pix % Wi);
+        const int y = (int)((pix / Wi) % Hi);
+        const int b = (int)(pix / ((long long)Wi * Hi));
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int t = y + 1 - i;
+            if (t < 0 || (t % stride)) continue;
+            const int yo = t / stride;
+            if (yo >= Ho) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                int u = x + 1 - j;
+                if (u < 0 || (u % stride)) continue;
+                const int xo = u / stride;
+                if (xo >= Wo) continue;
+                const float4 v = ld4(dcol + (((size_t)b * Ho + yo) * Wo + xo) * ldc + (i * 3 + j) * C + c);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+        }
+        st4(dx + (size_t)pix * C + c, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------- bilinear resize, align_corners=False
+__device__ __forceinline__ void bil_src(int d, float scale, int n_in, int& i0, int& i1, float& lam) {
+    float s = ((float)d + 0.5f) * scale - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    lam = s - (float)i0;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const TI* __restrict__ in, int ld_in, TO* __restrict__ out, int ld_out,
+                                                            int B, int Hi, int Wi, int Ho, int Wo, int C) {
+    const int c4n = C >> 2;
+    const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
+    const long long total = (long long)B * Ho * Wo * c4n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4n) * 4;
+        const long long pix = idx / c4n;
+        const int x = (int)(pix % Wo);
+        const int y = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long long)Wo * Ho));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bil_src(y, sy, Hi, y0, y1, ly);
+        bil_src(x, sx, Wi, x0, x1, lx);
+        const TI* base = in + (size_t)b * Hi * Wi * ld_in + c;
+        const float4 v00 = ld4(base + ((size_t)y0 * Wi + x0) * ld_in), v01 = ld4(base + ((size_t)y0 * Wi + x1) * ld_in);
+        const float4 v10 = ld4(base + ((size_t)y1 * Wi + x0) * ld_in), v11 = ld4(base + ((size_t)y1 * Wi + x1) * ld_in);
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        float4 o;
+        o.x = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+        o.y = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+        o.z = w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+        o.w = w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+        st4(out + (size_t)pix * ld_out + c, o);
+    }
+}
+
+// single-channel variant (the commuted segmentation heads): in [B,Hi,Wi] fp32 -> out [B,Ho,Wo] fp32
+__global__ void __launch_bounds__(256) upsample1_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int Hi,
+                                                             int Wi, int Ho, int Wo) {
+    const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
+    const long long total = (long long)B * Ho * Wo;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % Wo);
+        const int y = (int)((idx / Wo) % Ho);
+        const int b = (int)(idx / ((long long)Wo * Ho));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bil_src(y, sy, Hi, y0, y1, ly);
+        bil_src(x, sx, Wi, x0, x1, lx);
+        const float* base = in + (size_t)b * Hi * Wi;
+        out[idx] = (1.f - ly) * ((1.f - lx) * __ldg(base + y0 * Wi + x0) + lx * __ldg(base + y0 * Wi + x1)) +
+                   ly * ((1.f - lx) * __ldg(base + y1 * Wi + x0) + lx * __ldg(base + y1 * Wi + x1));
+    }
+}
+
+// Transposed resize in gather form.  For input pixel (yi,xi) the contributing output rows are found by scanning the
+// candidate window [ (yi-1)/scale , (yi+2)/scale ) and re-evaluating the forward's (i0,i1,lam) — an exact mirror.
+template <typename TI, int VEC>
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const TI* __restrict__ dout, int ld_out, float* __restrict__ din,
+                                                            int ld_in, int B, int Hi, int Wi, int Ho, int Wo, int C) {
+    const int cvn = C / VEC;
+    const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
+    const float iy = (float)Ho / Hi, ix = (float)Wo / Wi;
+    const long long total = (long long)B * Hi * Wi * cvn;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cvn) * VEC;
+        const long long pix = idx / cvn;
+        const int xi = (int)(pix % Wi);
+        const int yi = (int)((pix / Wi) % Hi);
+        const int b = (int)(pix / ((long long)Wi * Hi));
+        int ya = (int)floorf(((float)yi - 1.f) * iy) - 1, yb = (int)ceilf(((float)yi + 2.f) * iy) + 1;
+        int xa = (int)floorf(((float)xi - 1.f) * ix) - 1, xb = (int)ceilf(((float)xi + 2.f) * ix) + 1;
+        ya = max(ya, 0); xa = max(xa, 0); yb = min(yb, Ho); xb = min(xb, Wo);
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int y = ya; y < yb; ++y) {
+            int y0, y1;
+            float ly;
+            bil_src(y, sy, Hi, y0, y1, ly);
+            const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+            if (wy == 0.f) continue;
+            for (int x = xa; x < xb; ++x) {
+                int x0, x1;
+                float lx;
+                bil_src(x, sx, Wi, x0, x1, lx);
+                const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+                if (wx == 0.f) continue;
+                const TI* p = dout + (((size_t)b * Ho + y) * Wo + x) * ld_out + c;
+                const float wgt = wy * wx;
+                if (VEC == 4) {
+                    const float4 v = ld4(p);
+                    acc[0] += wgt * v.x; acc[1] += wgt * v.y; acc[2] += wgt * v.z; acc[3] += wgt * v.w;
+                } else {
+                    acc[0] += wgt * ldf(p);
+                }
+            }
+        }
+        float* o = din + (size_t)pix * ld_in + c;
+        if (VEC == 4) st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        else *o = acc[0];
+    }
+}
+
+inline int grid_for(long long total_threads) {
+    long long b = (total_threads + 255) / 256;
+    const long long cap = (long long)MDV_NUM_SMS * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+inline int pix_per_block_for(long long npix, int col_blocks) {
+    int want = (8 * MDV_NUM_SMS) / (col_blocks > 0 ? col_blocks : 1);
+    if (want < 1) want = 1;
+    long long ppb = (npix + want - 1) / want;
+    if (ppb < 64) ppb = 64;
+    return (int)ppb;
+}
+
+}  // namespace
+
+extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, void* out, int out_bf16, int B, int Hi, int Wi,
+                           int Ho, int Wo, int C, int stride, int transposed, int residual, void* stream) {
+    if (!in || !w || !out || (C & 3) || B <= 0) return MDV_ERR_ARG;
+    const long long total = (long long)B * Ho * Wo * (C / 4);
+    const size_t smem = (size_t)10 * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_bf16)
+        dwconv3_kernel<bf16><<<grid_for(total), 256, smem, st>>>(in, w, bias, (bf16*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
+    else
+        dwconv3_kernel<float><<<grid_for(total), 256, smem, st>>>(in, w, bias, (float*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int Hi, int Wi, int Ho, int Wo,
+                                 int C, int stride, void* stream) {
+    if (!dy || !x || !dw || B <= 0) return MDV_ERR_ARG;
+    const long long npix = (long long)B * Ho * Wo;
+    const int cb = mdv_cdiv(C, 32);
+    const int ppb = pix_per_block_for(npix, cb);
+    dim3 grid(cb, mdv_cdiv(npix, ppb));
+    dwconv3_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, dw, db, B, Hi, Wi, Ho, Wo, C, stride, ppb);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out_bf16, int B, int H, int W, int C,
+                              void* stream) {
+    if (!skip || !up || !w || !out_bf16 || (C & 3)) return MDV_ERR_ARG;
+    gconv2_fwd_kernel<<<grid_for((long long)B * H * W * (C / 2)), 256, 0, (cudaStream_t)stream>>>(skip, up, w, (bf16*)out_bf16, B, H, W, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float* up, const float* w, float* dskip, float* dup,
+                              float* dw, int B, int H, int W, int C, void* stream) {
+    if (!dout || !skip || !up || !w || !dskip || !dup || !dw || (C & 3)) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    gconv2_dgrad_kernel<<<grid_for((long long)B * H * W * (C / 2)), 256, 0, st>>>(dout, w, dskip, dup, B, H, W, C);
+    MDV_CHECK_LAUNCH();
+    const long long npix = (long long)B * H * W;
+    const int cb = mdv_cdiv(C, 32);
+    const int ppb = pix_per_block_for(npix, cb);
+    dim3 grid(cb, mdv_cdiv(npix, ppb));
+    gconv2_wgrad_kernel<<<grid, 256, 0, st>>>(dout, skip, up, dw, B, H, W, C, ppb);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride,
+                           int ldc, void* stream) {
+    if (!in || !col_bf16 || (C & 3) || ldc < 9 * C || (ldc & 7)) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ldc > 9 * C) {
+        cudaError_t e = cudaMemsetAsync(col_bf16, 0, (size_t)B * Ho * Wo * ldc * 2, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const long long total = (long long)B * Ho * Wo * 9 * (C / 4);
+    if (in_bf16)
+        im2col3_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    else
+        im2col3_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int Hi, int Wi, void* stream) {
+    if (!img_nchw || !col_bf16 || (Hi & 1) || (Wi & 1)) return MDV_ERR_ARG;
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    im2col_stem_kernel<<<grid_for((long long)B * Ho * Wo * 32), 256, 0, (cudaStream_t)stream>>>(img_nchw, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc,
+                           void* stream) {
+    if (!dcol || !dx || (C & 3)) return MDV_ERR_ARG;
+    col2im3_kernel<<<grid_for((long long)B * Hi * Wi * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dcol, dx, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* out, int out_bf16, int ld_out, int B, int Hi, int Wi,
+                                int Ho, int Wo, int C, void* stream) {
+    if (!in || !out || B <= 0) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 1) {
+        if (in_bf16 || out_bf16) return MDV_ERR_UNSUPPORTED;
+        upsample1_fwd_kernel<<<grid_for((long long)B * Ho * Wo), 256, 0, st>>>((const float*)in, (float*)out, B, Hi, Wi, Ho, Wo);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
+    if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
+    const int g = grid_for((long long)B * Ho * Wo * (C / 4));
+    if (in_bf16 && out_bf16)
+        upsample_fwd_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
+    else if (!in_bf16 && out_bf16)
+        upsample_fwd_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)in, ld_in, (bf16*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
+    else if (!in_bf16 && !out_bf16)
+        upsample_fwd_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, ld_in, (float*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
+    else
+        return MDV_ERR_UNSUPPORTED;
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+// din[B,Hi,Wi,C] (fp32, overwritten) = resize^T(dout[B,Ho,Wo,C])
+extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, float* din, int ld_in, int B, int Hi, int Wi, int Ho,
+                                int Wo, int C, void* stream) {
+    if (!dout || !din || B <= 0) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 1) {
+        if (dout_bf16) return MDV_ERR_UNSUPPORTED;
+        upsample_bwd_kernel<float, 1><<<grid_for((long long)B * Hi * Wi), 256, 0, st>>>((const float*)dout, 1, din, 1, B, Hi, Wi, Ho, Wo, 1);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
+    if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
+    const int g = grid_for((long long)B * Hi * Wi * (C / 4));
+    if (dout_bf16)
+        upsample_bwd_kernel<bf16, 4><<<g, 256, 0, st>>>((const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
+    else
+        upsample_bwd_kernel<float, 4><<<g, 256, 0, st>>>((const float*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}

@@ -1,0 +1,432 @@
+// Small HBM-bound kernels: 1-channel heads (commuted 1x1 conv), bias-gradient column sums, casts / weight
+// preparation, the fused segmentation + MKD losses, fused AdamW.
+#include "../../include/mdvit_b200.h"
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------- rowdot: logits[m] = sum_c x[m,c] w[c] m(b,c) + bias
+// The reference applies the C->1 1x1 conv AFTER a bilinear upsample (mdvit.py:699-700, Decoders.py:336-337); bilinear
+// weights sum to 1 per channel so conv and resize commute exactly and the conv runs at 1/16 of the pixels.
+// Optional Dropout2d (Decoders.py:334): whole (sample, channel) planes are dropped, mask = f(rng, stream, b*C+c).
+template <typename TI>
+__global__ void __launch_bounds__(256) rowdot_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int M, int C,
+                                                          int rows_per_sample, float drop_p, const unsigned long long* __restrict__ rng,
+                                                          uint32_t stream) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    uint32_t thr = 0, key = 0;
+    float inv = 1.f;
+    if (drop_p > 0.f) {
+        thr = drop_thresh(drop_p);
+        inv = 1.f / (1.f - drop_p);
+        key = rng_key(rng, stream);
+    }
+    const int b = row / rows_per_sample;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float wv = __ldg(w + c);
+        if (thr) wv *= drop_scale(key, (unsigned long long)b * C + c, thr, inv);
+        s += ldf(x + (size_t)row * C + c) * wv;
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s + (bias ? bias[0] : 0.f);
+}
+
+// dx[m,c] = dlog[m] w[c] mask;  dw[c] += sum_m dlog[m] x[m,c] mask;  db += sum_m dlog[m]
+template <typename TI>
+__global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict__ dlog, const TI* __restrict__ x,
+                                                          const float* __restrict__ w, float* __restrict__ dx, float* __restrict__ dw,
+                                                          float* __restrict__ db, int M, int C, int rows_per_sample, float drop_p,
+                                                          const unsigned long long* __restrict__ rng, uint32_t stream, int rows_per_block) {
+    // thread = channel (strided), block = chunk of rows of ONE sample
+    uint32_t thr = 0, key = 0;
+    float inv = 1.f;
+    if (drop_p > 0.f) {
+        thr = drop_thresh(drop_p);
+        inv = 1.f / (1.f - drop_p);
+        key = rng_key(rng, stream);
+    }
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float dbacc = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        const float wv = __ldg(w + c);
+        for (int r = r0; r < r1; ++r) {
+            const int b = r / rows_per_sample;
+            const float m = thr ? drop_scale(key, (unsigned long long)b * C + c, thr, inv) : 1.f;
+            const float d = __ldg(dlog + r);
+            dx[(size_t)r * C + c] = d * wv * m;
+            acc += d * ldf(x + (size_t)r * C + c) * m;
+        }
+        atomicAdd(dw + c, acc);
+    }
+    if (db && threadIdx.x == 0) {
+        for (int r = r0; r < r1; ++r) dbacc += dlog[r];
+        atomicAdd(db, dbacc);
+    }
+}
+
+// ---------------------------------------------------------------------------------- column sums (bias gradients)
+template <typename TI>
+__global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ x, int ld, float* __restrict__ out, int M, int C,
+                                                      int rows_per_block) {
+    __shared__ float sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < C)
+        for (int r = r0 + ty; r < r1; r += 8) s += ldf(x + (size_t)r * ld + c);
+    sh[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sh[i][tx];
+        atomicAdd(out + c, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------- casts
+// out[m, c] (bf16, pitch ld_out) = in[m, c] (fp32, pitch ld_in) * rowscale[m / rps] * dropout_mask(m*C + c)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
+                                                         long long M, int C, const float* __restrict__ rowscale, int rps, float drop_p,
+                                                         const unsigned long long* __restrict__ rng, uint32_t stream) {
+    const int c4n = C >> 2;
+    const long long total = M * c4n;
+    uint32_t thr = 0, key = 0;
+    float inv = 1.f;
+    if (drop_p > 0.f) {
+        thr = drop_thresh(drop_p);
+        inv = 1.f / (1.f - drop_p);
+        key = rng_key(rng, stream);
+    }
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4n) * 4;
+        const long long m = idx / c4n;
+        float4 v = *reinterpret_cast<const float4*>(in + m * ld_in + c);
+        float s = rowscale ? __ldg(rowscale + m / rps) : 1.f;
+        float s0 = s, s1 = s, s2 = s, s3 = s;
+        if (thr) {
+            const unsigned long long e = (unsigned long long)m * C + c;
+            s0 *= drop_scale(key, e, thr, inv);
+            s1 *= drop_scale(key, e + 1, thr, inv);
+            s2 *= drop_scale(key, e + 2, thr, inv);
+            s3 *= drop_scale(key, e + 3, thr, inv);
+        }
+        *reinterpret_cast<uint2*>(out + m * ld_out + c) = make_uint2(f2_to_bf2(v.x * s0, v.y * s1), f2_to_bf2(v.z * s2, v.w * s3));
+    }
+}
+
+// out fp32 [M,C] (pitch ld_out) (+)= bf16/fp32 in (pitch ld_in)
+template <typename TI>
+__global__ void __launch_bounds__(256) add_f32_kernel(const TI* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out,
+                                                       long long M, int C, int accumulate) {
+    const long long total = M * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const long long m = idx / C;
+        const float v = ldf(in + m * ld_in + c);
+        float* o = out + m * ld_out + c;
+        *o = accumulate ? *o + v : v;
+    }
+}
+
+// Weight preparation: dst[r, c] = bf16(src[...]) with optional transpose / 3x3-conv permutation.
+//  mode 0: src [R, Cc] row-major                       -> dst [R, ld]        (Linear / 1x1 conv weight)
+//  mode 1: src [R, Cc] row-major                       -> dst [Cc, ld] = src^T (for input gradients)
+//  mode 2: src [R, Cin, 3, 3] (PyTorch conv)           -> dst [R, ld], column (i*3+j)*Cin + ci    (im2col order)
+//  mode 3: src [R, Cin, 3, 3]                          -> dst [9*Cin (pad to rows), ld] transposed of mode 2
+__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int Cc,
+                                                           int ld, int mode, int cin) {
+    const long long total = (long long)R * Cc;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / Cc), c = (int)(idx % Cc);
+        const bf16 v = __float2bfloat16_rn(src[idx]);
+        if (mode == 0) {
+            dst[(size_t)r * ld + c] = v;
+        } else if (mode == 1) {
+            dst[(size_t)c * ld + r] = v;
+        } else {
+            const int ci = c / 9, t = c % 9;
+            const int col = t * cin + ci;
+            if (mode == 2) dst[(size_t)r * ld + col] = v;
+            else dst[(size_t)col * ld + r] = v;
+        }
+    }
+}
+
+// d(conv weight [R,Cin,3,3]) += dW_im2col[R, ld] (column (i*3+j)*Cin+ci)
+__global__ void __launch_bounds__(256) unperm_conv_grad_kernel(const float* __restrict__ g, int ld, float* __restrict__ dw, int R,
+                                                                int cin) {
+    const long long total = (long long)R * cin * 9;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / (cin * 9)), c = (int)(idx % (cin * 9));
+        const int ci = c / 9, t = c % 9;
+        dw[idx] += g[(size_t)r * ld + t * cin + ci];
+    }
+}
+
+// ---------------------------------------------------------------------------------- losses
+// multi_train_MDViT.py:147-169 + Utils/losses.py:8-16.  p = sigmoid(out), q = sigmoid(aux), y = label.
+// sums[0..7] = sum bce(p,y), sum bce(q,y), sum p*y, sum p*p, sum y*y, sum q*y, sum q*q, sum q*p     (double)
+__device__ __forceinline__ float bce_term(float p, float y) {
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+    return -(y * lp + (1.f - y) * l1p);
+}
+
+__global__ void __launch_bounds__(256) loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ aux,
+                                                         const float* __restrict__ label, double* __restrict__ sums, long long n) {
+    __shared__ float red[32];
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float y = label[i];
+        const float p = 1.f / (1.f + expf(-out[i]));
+        const float q = aux ? 1.f / (1.f + expf(-aux[i])) : 0.f;
+        a[0] += bce_term(p, y);
+        a[2] += p * y;
+        a[3] += p * p;
+        a[4] += y * y;
+        if (aux) {
+            a[1] += bce_term(q, y);
+            a[5] += q * y;
+            a[6] += q * q;
+            a[7] += q * p;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float t = block_sum(a[k], red);
+        if (threadIdx.x == 0) atomicAdd(sums + k, (double)t);
+    }
+}
+
+// losses[0..2] = L_seg, L_aux, L_kt  (fp32), from (possibly all-reduced) sums;  n_total = global element count.
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, double n_total, float* __restrict__ losses) {
+    const double eps = 1e-5;
+    const double bce_p = sums[0] / n_total, bce_q = sums[1] / n_total;
+    const double dice_p = 1.0 - (2.0 * sums[2] + eps) / (sums[3] + sums[4] + eps);
+    const double dice_q = 1.0 - (2.0 * sums[5] + eps) / (sums[6] + sums[4] + eps);
+    const double dice_kt = 1.0 - (2.0 * sums[7] + eps) / (sums[6] + sums[3] + eps);
+    losses[0] = (float)(bce_p + dice_p);
+    losses[1] = (float)(bce_q + dice_q);
+    losses[2] = (float)dice_kt;
+}
+
+// Gradients w.r.t. the logits for  L = c_seg*L_seg + c_aux*L_aux + c_kt*L_kt  (coef[0..2]); see SURVEY.md App. E.
+// PyTorch's BCELoss backward: (p - y) / max(p(1-p), 1e-12) / n, times sigmoid' = p(1-p).
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ aux,
+                                                        const float* __restrict__ label, const double* __restrict__ sums,
+                                                        double n_total, const float* __restrict__ coef, float* __restrict__ dout,
+                                                        float* __restrict__ daux, long long n) {
+    const double eps = 1e-5;
+    const float c_seg = coef[0], c_aux = coef[1], c_kt = coef[2];
+    const float inv_n = (float)(1.0 / n_total);
+    // dice(s,t): dD/ds_i = -(2 t_i den - 2 s_i num) / den^2, num = 2I+eps, den = Z+Y+eps
+    const double den_p = sums[3] + sums[4] + eps, num_p = 2.0 * sums[2] + eps;
+    const double den_q = sums[6] + sums[4] + eps, num_q = 2.0 * sums[5] + eps;
+    const double den_k = sums[6] + sums[3] + eps, num_k = 2.0 * sums[7] + eps;
+    const float ap = (float)(2.0 / den_p), bp = (float)(2.0 * num_p / (den_p * den_p));
+    const float aq = (float)(2.0 / den_q), bq = (float)(2.0 * num_q / (den_q * den_q));
+    const float ak = (float)(2.0 / den_k), bk = (float)(2.0 * num_k / (den_k * den_k));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float y = label[i];
+        const float p = 1.f / (1.f + expf(-out[i]));
+        const float sp = p * (1.f - p);
+        float gp = c_seg * ((p - y) / fmaxf(sp, 1e-12f) * inv_n + (-ap * y + bp * p));
+        if (aux) {
+            const float q = 1.f / (1.f + expf(-aux[i]));
+            const float sq = q * (1.f - q);
+            float gq = c_aux * ((q - y) / fmaxf(sq, 1e-12f) * inv_n + (-aq * y + bq * q));
+            gq += c_kt * (-ak * p + bk * q);
+            gp += c_kt * (-ak * q + bk * p);
+            daux[i] = gq * sq;
+        }
+        dout[i] = gp * sp;
+    }
+}
+
+// ---------------------------------------------------------------------------------- AdamW (torch.optim.AdamW semantics)
+// hyper (device fp32[8]): lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, grad_scale
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ v, const float* __restrict__ hyper, long long n) {
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6],
+                gs = hyper[7];
+    const float step = lr / bc1, isb2 = rsqrtf(bc2);
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < n) {
+            float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+            float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+            float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w},
+                  va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gk = ga[k] * gs;
+                pa[k] *= 1.f - lr * wd;
+                ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+                va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+                pa[k] -= step * ma[k] / (sqrtf(va[k]) * isb2 + eps);
+            }
+            *reinterpret_cast<float4*>(p + i) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+            *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+            *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
+        } else {
+            for (long long j = i; j < n; ++j) {
+                const float gk = g[j] * gs;
+                float pj = p[j] * (1.f - lr * wd);
+                const float mj = b1 * m[j] + (1.f - b1) * gk, vj = b2 * v[j] + (1.f - b2) * gk * gk;
+                pj -= step * mj / (sqrtf(vj) * isb2 + eps);
+                p[j] = pj; m[j] = mj; v[j] = vj;
+            }
+        }
+    }
+}
+
+__global__ void rng_bump_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+
+// DropPath per-sample scale: scale[b] = Bernoulli(1-p)/(1-p)   (timm DropPath, mdvit.py:339)
+__global__ void droppath_scale_kernel(float* __restrict__ scale, int B, float p, const unsigned long long* __restrict__ rng,
+                                      uint32_t stream) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    scale[b] = drop_scale(rng_key(rng, stream), (unsigned long long)b, drop_thresh(p), 1.f / (1.f - p));
+}
+
+inline int grid_for(long long total_threads) {
+    long long b = (total_threads + 255) / 256;
+    const long long cap = (long long)MDV_NUM_SMS * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+long long g_mdv_launches = 0;
+
+extern "C" int mdv_version(void) { return 100; }
+
+extern "C" long long mdv_launch_count(void) { return g_mdv_launches; }
+
+extern "C" int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const float* bias, float* out, int M, int C,
+                              int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
+    if (!x || !w || !out || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
+    const int blocks = mdv_cdiv(M, 8);
+    if (x_bf16)
+        rowdot_fwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
+    else
+        rowdot_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, const float* w, float* dx, float* dw, float* db, int M,
+                              int C, int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
+    if (!dlog || !x || !w || !dx || !dw || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
+    int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);
+    if (rpb < 8) rpb = 8;
+    const int blocks = mdv_cdiv(M, rpb);
+    const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+    if (x_bf16)
+        rowdot_bwd_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>(dlog, (const bf16*)x, w, dx, dw, db, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream, rpb);
+    else
+        rowdot_bwd_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(dlog, (const float*)x, w, dx, dw, db, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream, rpb);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, int C, void* stream) {
+    if (!x || !out || M <= 0 || C <= 0) return MDV_ERR_ARG;
+    const int cb = mdv_cdiv(C, 32);
+    int want = (8 * MDV_NUM_SMS) / cb;
+    if (want < 1) want = 1;
+    int rpb = mdv_cdiv(M, want);
+    if (rpb < 64) rpb = 64;
+    dim3 grid(cb, mdv_cdiv(M, rpb));
+    if (x_bf16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, C, rpb);
+    else colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, out, M, C, rpb);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
+                             int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
+    if (!in || !out_bf16 || (C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
+    cast_bf16_kernel<<<grid_for(M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(in, ld_in, (bf16*)out_bf16, ld_out, M, C, rowscale,
+                                                                               rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
+                                                                               (const unsigned long long*)rng, drop_stream);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate,
+                           void* stream) {
+    if (!in || !out) return MDV_ERR_ARG;
+    if (in_bf16) add_f32_kernel<bf16><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ld_in, out, ld_out, M, C, accumulate);
+    else add_f32_kernel<float><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, out, ld_out, M, C, accumulate);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream) {
+    if (!src || !dst_bf16 || mode < 0 || mode > 3) return MDV_ERR_ARG;
+    prep_weight_kernel<<<grid_for((long long)R * Cc), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst_bf16, R, Cc, ld, mode, cin);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_unperm_conv_grad(const float* g, int ld, float* dw, int R, int cin, void* stream) {
+    if (!g || !dw) return MDV_ERR_ARG;
+    unperm_conv_grad_kernel<<<grid_for((long long)R * cin * 9), 256, 0, (cudaStream_t)stream>>>(g, ld, dw, R, cin);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+// sums: 8 doubles (zeroed here).  aux may be NULL (BASE model: only L_seg is meaningful).
+extern "C" int mdv_loss_sums(const float* out, const float* aux, const float* label, void* sums, long long n, void* stream) {
+    if (!out || !label || !sums || n <= 0) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sums, 0, 8 * sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+    loss_sums_kernel<<<grid_for(n), 256, 0, st>>>(out, aux, label, (double*)sums, n);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_loss_finalize(const void* sums, double n_total, float* losses, void* stream) {
+    if (!sums || !losses) return MDV_ERR_ARG;
+    loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const double*)sums, n_total, losses);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_loss_bwd(const float* out, const float* aux, const float* label, const void* sums, double n_total,
+                            const float* coef, float* dout, float* daux, long long n, void* stream) {
+    if (!out || !label || !sums || !coef || !dout || (aux && !daux)) return MDV_ERR_ARG;
+    loss_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(out, aux, label, (const double*)sums, n_total, coef, dout, daux, n);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_adamw(float* p, const float* g, float* m, float* v, const float* hyper, long long n, void* stream) {
+    if (!p || !g || !m || !v || !hyper || n <= 0) return MDV_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15)
+        return MDV_ERR_ARG;
+    adamw_kernel<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, hyper, n);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_rng_bump(void* rng, void* stream) {
+    if (!rng) return MDV_ERR_ARG;
+    rng_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)rng);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_droppath_scale(float* scale, int B, float p, const void* rng, uint32_t drop_stream, void* stream) {
+    if (!scale || B <= 0 || p < 0.f || p >= 1.f) return MDV_ERR_ARG;
+    droppath_scale_kernel<<<mdv_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(scale, B, p, (const unsigned long long*)rng, drop_stream);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}

@@ -1,0 +1,388 @@
+"""MDViT / BASE nn.Modules with the reference's constructor, forward signature, parameter names and state_dict layout
+(Models/Transformer/mdvit.py:474-730, Models/Transformer/base.py:340-512), executing on the sm_100a kernels of
+libmdvit_b200.so.  The torch.nn layers instantiated here (Conv2d, Linear, LayerNorm, BatchNorm2d) are parameter
+CONTAINERS only — their own forward is never called; all arithmetic goes through mdvit_b200.ops.
+
+Drop-in use with the unmodified trainer: put `<repo>/dropin` in front of the reference root on PYTHONPATH so that
+`from Models.Transformer.mdvit import MDViT` (multi_train_MDViT.py:58) resolves to this class.  See INTEGRATION.md.
+"""
+import math
+from functools import partial
+
+import torch
+from torch import nn
+
+from . import ops
+
+CRPE_WINDOW = {3: 2, 5: 3, 7: 3}
+
+
+# ----------------------------------------------------------------------------------------------- parameter containers
+class Conv2d_BN(nn.Module):
+    """mpvit.py:81-124 (conv no bias + BN + act)."""
+
+    def __init__(self, in_ch, out_ch, kernel_size=1, stride=1, pad=0, act_layer=None):
+        super().__init__()
+        self.conv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, pad, bias=False)
+        self.bn = nn.BatchNorm2d(out_ch)
+        self.act_layer = act_layer() if act_layer is not None else nn.Identity()
+
+
+class DWConv2d_BN(nn.Module):
+    """mdvit.py:74-123: depthwise (groups=in_ch) + pointwise in->out + BN + Hardswish."""
+
+    def __init__(self, in_ch, out_ch, kernel_size=3, stride=1):
+        super().__init__()
+        self.dwconv = nn.Conv2d(in_ch, in_ch, kernel_size, stride, (kernel_size - 1) // 2, groups=in_ch, bias=False)
+        self.pwconv = nn.Conv2d(in_ch, out_ch, 1, 1, 0, bias=False)
+        self.bn = nn.BatchNorm2d(out_ch)
+        self.act = nn.Hardswish()
+        self.stride = stride
+
+
+class DWCPatchEmbed(nn.Module):
+    """mdvit.py:183-208."""
+
+    def __init__(self, in_chans, embed_dim, patch_size=3, stride=1):
+        super().__init__()
+        self.patch_conv = DWConv2d_BN(in_chans, embed_dim, patch_size, stride)
+
+    def forward(self, x, H, W):
+        pc = self.patch_conv
+        bn = pc.bn
+        y = ops.PatchEmbedFn.apply(x, pc.dwconv.weight, pc.pwconv.weight, bn.weight, bn.bias,
+                                   (bn.running_mean, bn.running_var, bn.num_batches_tracked), H, W, pc.stride,
+                                   self.training)
+        s = pc.stride
+        return y, (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
+
+
+class DecoderDWConv2d_BN(nn.Module):
+    """Decoders.py:15-63: 3x3 conv groups=out_ch over 2*out_ch inputs, pointwise out->out, BN, Hardswish."""
+
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.dwconv = nn.Conv2d(in_ch, out_ch, 3, 1, 1, groups=out_ch, bias=False)
+        self.pwconv = nn.Conv2d(out_ch, out_ch, 1, 1, 0, bias=False)
+        self.bn = nn.BatchNorm2d(out_ch)
+        self.act = nn.Hardswish()
+
+
+class ConvPosEnc(nn.Module):
+    """mpvit.py:229-248."""
+
+    def __init__(self, dim, k=3):
+        super().__init__()
+        self.proj = nn.Conv2d(dim, dim, k, 1, k // 2, groups=dim)
+
+
+class ConvRelPosEnc(nn.Module):
+    """mpvit.py:251-318."""
+
+    def __init__(self, Ch, h, window):
+        super().__init__()
+        self.conv_list = nn.ModuleList()
+        self.head_splits = []
+        for cur_window, cur_head_split in window.items():
+            self.conv_list.append(nn.Conv2d(cur_head_split * Ch, cur_head_split * Ch, cur_window, padding=cur_window // 2,
+                                            groups=cur_head_split * Ch))
+            self.head_splits.append(cur_head_split)
+
+
+class FactorAtt_ConvRelPosEnc(nn.Module):
+    """mpvit.py:321-373 (no domain adapter)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, shared_crpe=None):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)  # constructed but never applied by the reference either
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.crpe = shared_crpe
+        self.domain_layer = None
+
+
+class FactorAtt_ConvRelPosEnc_Sup(nn.Module):
+    """mdvit.py:243-313 (DA: domain_layer MLP -> softmax over heads gate)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, shared_crpe=None, r=2, num_domains=4):
+        super().__init__()
+        self.num_heads = num_heads
+        hidden_dim = max(dim // r, 4)
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.domain_layer = nn.Sequential(nn.Linear(num_domains, hidden_dim), nn.ReLU(inplace=True), nn.Linear(hidden_dim, dim))
+        self.crpe = shared_crpe
+
+
+class Mlp(nn.Module):
+    """mpvit.py:51-78."""
+
+    def __init__(self, in_features, hidden_features, drop=0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, in_features)
+        self.drop = nn.Dropout(drop)
+
+
+class SerialBlock_adapt(nn.Module):
+    """mdvit.py:316-361."""
+
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, drop, attn_drop, drop_path, norm_layer, shared_cpe, shared_crpe,
+                 adapt_method, num_domains, label_only_guard=False):
+        super().__init__()
+        self.label_only_guard = label_only_guard   # base.py:216 tests only `domain_label != None`
+        if num_heads != ops.HEADS:
+            raise ValueError("mdvit_b200 kernels are specialised for 8 attention heads (the reference's only setting)")
+        self.cpe = shared_cpe
+        self.norm1 = norm_layer(dim)
+        self.adapt_method = adapt_method
+        if adapt_method == 'Sup':
+            self.factoratt_crpe = FactorAtt_ConvRelPosEnc_Sup(dim, num_heads, qkv_bias, attn_drop, drop, shared_crpe,
+                                                              num_domains=num_domains)
+        else:
+            self.factoratt_crpe = FactorAtt_ConvRelPosEnc(dim, num_heads, qkv_bias, attn_drop, drop, shared_crpe)
+        self.drop_path = nn.Identity()
+        self.drop_path_rate = float(drop_path)
+        self.drop_rate = float(drop)
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio), drop)
+
+    def forward(self, x, size, domain_label=None):
+        H, W = size
+        att = self.factoratt_crpe
+        # dispatch quirks of mdvit.py:350-353 preserved: Sup attention needs a label, plain attention rejects one
+        use_label = domain_label is not None and (self.label_only_guard or self.adapt_method is not None)
+        if att.domain_layer is not None and not use_label:
+            raise TypeError("FactorAtt_ConvRelPosEnc_Sup.forward() missing 1 required positional argument: 'domain_label'")
+        if att.domain_layer is None and use_label:
+            raise TypeError("FactorAtt_ConvRelPosEnc.forward() takes 3 positional arguments but 4 were given")
+        dl = att.domain_layer
+        da = (dl[0].weight, dl[0].bias, dl[2].weight, dl[2].bias) if dl is not None else (None, None, None, None)
+        cl = att.crpe.conv_list
+        if not (isinstance(self.norm1, nn.LayerNorm) and abs(self.norm1.eps - 1e-6) < 1e-12):
+            raise ValueError("mdvit_b200 supports norm_layer=LayerNorm(eps=1e-6) (the reference default)")
+        return ops.BlockFn.apply(
+            x, domain_label if use_label else None, self.cpe.proj.weight, self.cpe.proj.bias,
+            cl[0].weight, cl[0].bias, cl[1].weight, cl[1].bias, cl[2].weight, cl[2].bias,
+            self.norm1.weight, self.norm1.bias, att.qkv.weight, att.qkv.bias, att.proj.weight, att.proj.bias,
+            da[0], da[1], da[2], da[3], self.norm2.weight, self.norm2.bias,
+            self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
+            H, W, self.drop_rate, self.drop_path_rate, self.training)
+
+
+class MHSA_stage_adapt(nn.Module):
+    """mdvit.py:415-440: one shared ConvPosEnc + ConvRelPosEnc, `num_layers` serial blocks."""
+
+    def __init__(self, dim, num_layers, num_heads, mlp_ratio, qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
+                 num_domains=4, norm_layer=nn.LayerNorm, adapt_method=None, label_only_guard=False):
+        super().__init__()
+        self.cpe = ConvPosEnc(dim, k=3)
+        self.crpe = ConvRelPosEnc(Ch=dim // num_heads, h=num_heads, window=CRPE_WINDOW)
+        self.mhca_blks = nn.ModuleList([
+            SerialBlock_adapt(dim, num_heads, mlp_ratio, qkv_bias, drop_rate, attn_drop_rate, drop_path_rate, norm_layer,
+                              self.cpe, self.crpe, adapt_method, num_domains, label_only_guard) for _ in range(num_layers)])
+
+    def forward(self, x, H, W, domain_label=None):
+        for blk in self.mhca_blks:
+            x = blk(x, (H, W), domain_label)
+        return x
+
+
+class UnetDecodingBlockTransformer(nn.Module):
+    """Decoders.py:174-214 (use_res=False)."""
+
+    def __init__(self, in_channel, out_channel, mhsa_block):
+        super().__init__()
+        self.conv_before = nn.Conv2d(in_channel, out_channel, kernel_size=1)
+        self.conv_after = DecoderDWConv2d_BN(out_channel * 2, out_channel)
+        self.mhsa_block = mhsa_block
+
+    def forward(self, x, h, w, skip, H, W, domain_label=None):
+        ca = self.conv_after
+        out = ops.DecoderConvFn.apply(x, skip, self.conv_before.weight, self.conv_before.bias, ca.dwconv.weight, ca.pwconv.weight,
+                                      ca.bn.weight, ca.bn.bias, (ca.bn.running_mean, ca.bn.running_var, ca.bn.num_batches_tracked),
+                                      h, w, H, W, self.training)
+        return self.mhsa_block(out, H, W, domain_label)
+
+
+class MLPDecoderFM(nn.Module):
+    """Decoders.py:289-339."""
+
+    def __init__(self, in_channels, out_channel, hidden_channel=256, outfeature_channel=64, dropout_ratio=0.1):
+        super().__init__()
+        if out_channel != 1:
+            raise ValueError("mdvit_b200 implements the single-class head used by the reference trainers")
+        self.linear1 = nn.Conv2d(in_channels[0], hidden_channel, 1)
+        self.linear2 = nn.Conv2d(in_channels[1], hidden_channel, 1)
+        self.linear3 = nn.Conv2d(in_channels[2], hidden_channel, 1)
+        self.linear4 = nn.Conv2d(in_channels[3], hidden_channel, 1)
+        self.linear_fuse = nn.Sequential(nn.Conv2d(hidden_channel * 4 + outfeature_channel, hidden_channel, 1),
+                                         nn.BatchNorm2d(hidden_channel), nn.ReLU(inplace=True))
+        self.dropout = nn.Dropout2d(dropout_ratio)
+        self.linear_out = nn.Conv2d(hidden_channel, out_channel, 1)
+        self.avg_pool = nn.AdaptiveAvgPool2d((1, 1))
+
+    def forward(self, feats, sizes, img_size):
+        x1, x2, x3, x4, x5 = feats
+        bn = self.linear_fuse[1]
+        return ops.AuxFn.apply(x1, x2, x3, x4, x5, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                               self.linear3.weight, self.linear3.bias, self.linear4.weight, self.linear4.bias,
+                               self.linear_fuse[0].weight, self.linear_fuse[0].bias, bn.weight, bn.bias, self.linear_out.weight,
+                               self.linear_out.bias, (bn.running_mean, bn.running_var, bn.num_batches_tracked), tuple(sizes),
+                               int(img_size[0]), int(img_size[1]), float(self.dropout.p), self.training)
+
+
+# ----------------------------------------------------------------------------------------------- models
+class _Trunk(nn.Module):
+    """Shared encoder / bridge / decoder of MDViT and BASE."""
+
+    def _build_trunk(self, in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, drop_rate, attn_drop_rate,
+                     drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains, label_only_guard=False):
+        if num_stages != 4 or in_chans != 3:
+            raise ValueError("mdvit_b200 implements the 4-stage, 3-channel configuration of the reference trainers")
+        if conv_norm is not nn.BatchNorm2d:
+            raise ValueError("mdvit_b200 implements conv_norm=nn.BatchNorm2d (the reference trainers' setting)")
+        self.num_stages = num_stages
+        self.embed_dims = list(embed_dims)
+        self.stem = nn.Sequential(
+            Conv2d_BN(in_chans, embed_dims[0] // 2, 3, 2, 1, act_layer=nn.Hardswish),
+            Conv2d_BN(embed_dims[0] // 2, embed_dims[0], 3, 2, 1, act_layer=nn.Hardswish))
+        self.patch_embed_stages = nn.ModuleList([
+            DWCPatchEmbed(embed_dims[idx] if idx == 0 else embed_dims[idx - 1], embed_dims[idx], 3, 1 if idx == 0 else 2)
+            for idx in range(num_stages)])
+
+        def stage(idx):
+            return MHSA_stage_adapt(embed_dims[idx], num_layers[idx], num_heads[idx], mlp_ratios[idx], qkv_bias, drop_rate,
+                                    attn_drop_rate, drop_path_rate, num_domains, norm_layer, adapt_method, label_only_guard)
+
+        self.mhsa_stages = nn.ModuleList([stage(idx) for idx in range(num_stages)])
+        self.bridge = nn.Sequential(
+            nn.Conv2d(embed_dims[3], embed_dims[3], 3, 1, 1), nn.BatchNorm2d(embed_dims[3]), nn.ReLU(inplace=True),
+            nn.Conv2d(embed_dims[3], embed_dims[3] * 2, 3, 1, 1), nn.BatchNorm2d(embed_dims[3] * 2), nn.ReLU(inplace=True))
+        self.mhsa_list = [stage(idx) for idx in range(num_stages)]   # plain list, as in mdvit.py:568
+        self.decoder1 = UnetDecodingBlockTransformer(embed_dims[3] * 2, embed_dims[3], self.mhsa_list[3])
+        self.decoder2 = UnetDecodingBlockTransformer(embed_dims[3], embed_dims[2], self.mhsa_list[2])
+        self.decoder3 = UnetDecodingBlockTransformer(embed_dims[2], embed_dims[1], self.mhsa_list[1])
+        self.decoder4 = UnetDecodingBlockTransformer(embed_dims[1], embed_dims[0], self.mhsa_list[0])
+        self.finalconv = nn.Sequential(nn.Conv2d(embed_dims[0], 1, kernel_size=1))
+
+    def _init_weights(self, m):
+        """mdvit.py:648-664."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+        elif isinstance(m, nn.Conv2d):
+            fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+            fan_out //= m.groups
+            m.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
+
+    def _trunk_forward(self, x, domain_label):
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError("input must be [B,3,H,W] with H and W divisible by 32")
+        if not x.is_cuda:
+            raise RuntimeError("mdvit_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        s0, s1 = self.stem[0], self.stem[1]
+        H, W = x.shape[2] // 4, x.shape[3] // 4
+        t = ops.StemFn.apply(x, s0.conv.weight, s0.bn.weight, s0.bn.bias, s1.conv.weight, s1.bn.weight, s1.bn.bias,
+                             (s0.bn.running_mean, s0.bn.running_var, s0.bn.num_batches_tracked,
+                              s1.bn.running_mean, s1.bn.running_var, s1.bn.num_batches_tracked), self.training)
+        enc = []
+        for idx in range(self.num_stages):
+            t, H, W = self.patch_embed_stages[idx](t, H, W)
+            t = self.mhsa_stages[idx](t, H, W, domain_label)
+            enc.append((t, H, W))
+        return enc
+
+    def _decode(self, enc, domain_label):
+        t3, H3, W3 = enc[3]
+        b = self.bridge
+        out = ops.BridgeFn.apply(t3, b[0].weight, b[0].bias, b[1].weight, b[1].bias, b[3].weight, b[3].bias, b[4].weight, b[4].bias,
+                                 (b[1].running_mean, b[1].running_var, b[1].num_batches_tracked,
+                                  b[4].running_mean, b[4].running_var, b[4].num_batches_tracked), H3, W3, self.training)
+        h, w = H3, W3
+        for dec, (skip, H, W) in zip((self.decoder1, self.decoder2, self.decoder3, self.decoder4), (enc[3], enc[2], enc[1], enc[0])):
+            out = dec(out, h, w, skip, H, W, domain_label)
+            h, w = H, W
+        return out, h, w
+
+    def _head(self, dec4, h, w, img_size):
+        fc = self.finalconv[0]
+        return ops.HeadFn.apply(dec4, fc.weight, fc.bias, h, w, int(img_size[0]), int(img_size[1]))
+
+
+class MDViT(_Trunk):
+    """Drop-in for Models.Transformer.mdvit.MDViT (decoder_name='MLPFM')."""
+
+    def __init__(self, img_size=512, in_chans=3, num_stages=4, num_layers=[2, 2, 2, 2], embed_dims=[64, 128, 320, 512],
+                 mlp_ratios=[8, 8, 4, 4], num_heads=[8, 8, 8, 8], qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), conv_norm=nn.BatchNorm2d, adapt_method=None,
+                 num_domains=4, decoder_name='MLPFM', **kwargs):
+        super().__init__()
+        if qk_scale is not None:
+            raise ValueError("mdvit_b200 implements qk_scale=None (head_dim**-0.5), the reference trainers' setting")
+        if decoder_name != 'MLPFM':
+            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' (hard-coded by multi_train_MDViT.py:60)")
+        self.decoder_name = decoder_name
+        self._build_trunk(in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, drop_rate, attn_drop_rate,
+                          drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains)
+        self.debranch1 = MLPDecoderFM(embed_dims, 1, 512)
+        self.debranch2 = MLPDecoderFM(embed_dims, 1, 512)
+        self.debranch3 = MLPDecoderFM(embed_dims, 1, 512)
+        self.debranch4 = MLPDecoderFM(embed_dims, 1, 512)
+        self.apply(self._init_weights)
+
+    def forward(self, x, domain_label=None, d=None, out_feat=False, out_seg=True):
+        img_size = x.shape[2:]
+        enc = self._trunk_forward(x, domain_label)
+        if not out_seg:
+            return {'seg': None, 'feat': enc[3][0].mean(dim=1)}
+        dec4, h, w = self._decode(enc, domain_label)
+        out = self._head(dec4, h, w, img_size)
+        aux_out = None
+        if d in ('0', '1', '2', '3'):
+            branch = getattr(self, f'debranch{int(d) + 1}')
+            feats = [e[0] for e in enc] + [dec4]
+            aux_out = branch(feats, [(e[1], e[2]) for e in enc], img_size)
+        if out_feat:
+            return {'seg': [out, aux_out], 'feat': enc[3][0].mean(dim=1)}
+        return [out, aux_out]
+
+
+class BASE(_Trunk):
+    """Drop-in for Models.Transformer.base.BASE (base.py:340-512): MDViT without auxiliary branches."""
+
+    def __init__(self, img_size=512, in_chans=3, num_stages=4, num_layers=[2, 2, 2, 2], embed_dims=[64, 128, 320, 512],
+                 mlp_ratios=[8, 8, 4, 4], num_heads=[8, 8, 8, 8], qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), conv_norm=nn.BatchNorm2d, adapt_method=None,
+                 num_domains=4, **kwargs):
+        super().__init__()
+        if qk_scale is not None:
+            raise ValueError("mdvit_b200 implements qk_scale=None")
+        self._build_trunk(in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, drop_rate, attn_drop_rate,
+                          drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains, label_only_guard=True)
+        self.apply(self._init_weights)
+
+    def forward(self, x, domain_label=None, out_feat=False, out_seg=True):
+        img_size = x.shape[2:]
+        enc = self._trunk_forward(x, domain_label)
+        if not out_seg:
+            return {'seg': None, 'feat': enc[3][0].mean(dim=1)}
+        dec4, h, w = self._decode(enc, domain_label)
+        out = self._head(dec4, h, w, img_size)
+        if out_feat:
+            return {'seg': out, 'feat': enc[3][0].mean(dim=1)}
+        return out

@@ -1,0 +1,687 @@
+"""Host-side operators of the MDViT hot path: torch.autograd.Functions whose forward/backward are sequences of
+C-ABI kernel launches (include/mdvit_b200.h).  torch supplies device memory, the current stream and the autograd
+tape; all arithmetic runs in libmdvit_b200.so.  Activations are token-major fp32/bf16 ([B, H*W, C] == NHWC).
+
+Every Function tolerates being back-propagated twice over one graph (multi_train_MDViT.py:201,207 call backward
+with retain_graph=True and then again): saved tensors are never written in backward, all backward scratch is
+freshly allocated, and parameter gradients are returned (autograd does the accumulation and honours the
+requires_grad flips on `domain_layer` between the two passes).
+"""
+import ctypes
+import itertools
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_GELU, ACT_HSWISH, ACT_NONE, ACT_RELU, GemmEpi, check, ptr
+
+BF16, F32 = torch.bfloat16, torch.float32
+HEADS = 8
+
+# ------------------------------------------------------------------------------------------------- RNG state
+_rng_state = {}
+_stream_counter = itertools.count(1)
+
+
+def rng_tensor(device):
+    """Device uint64[2] {seed, step}: dropout masks are hash(seed, step, stream-id, element)."""
+    t = _rng_state.get(device)
+    if t is None:
+        t = torch.tensor([0x5EED, 0], dtype=torch.int64, device=device)
+        _rng_state[device] = t
+    return t
+
+
+def manual_seed(seed, device):
+    rng_tensor(torch.device(device))[0] = int(seed)
+
+
+def rng_bump(device):
+    check(L.lib().mdv_rng_bump(ptr(rng_tensor(device)), L.stream()), "mdv_rng_bump")
+
+
+def reset_stream_ids():
+    """Call at the start of every training step so mask stream ids are reproducible (CUDA-graph friendly)."""
+    global _stream_counter
+    _stream_counter = itertools.count(1)
+
+
+def new_stream_id():
+    return next(_stream_counter) & 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------- weight cache
+WEIGHT_EPOCH = 0
+_wcache = {}
+
+
+def bump_weight_epoch():
+    """Invalidate cached bf16 operand copies (called by the fused optimizer, which updates params by pointer)."""
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+    _wcache.clear()
+
+
+def prep_weight(w, mode, rows, cols, ld=None, cin=0):
+    """bf16 GEMM operand of fp32 parameter `w` (mode: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order)."""
+    key = (w.data_ptr(), w._version, mode, ld, WEIGHT_EPOCH)
+    hit = _wcache.get(key)
+    if hit is not None:
+        return hit
+    R, Cc = rows, cols
+    if mode == 0 or mode == 2:
+        out_rows, out_ld = R, (ld or Cc)
+    else:
+        out_rows, out_ld = Cc, (ld or R)
+    with torch.no_grad():
+        need_zero = mode >= 2 and out_ld != (Cc if mode == 2 else R)
+        dst = (torch.zeros if need_zero or mode >= 2 else torch.empty)((out_rows, out_ld), dtype=BF16, device=w.device)
+        check(L.lib().mdv_prep_weight(ptr(w), ptr(dst), R, Cc, out_ld, mode, cin, L.stream()), "mdv_prep_weight")
+    _wcache[key] = dst
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------- thin wrappers
+def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, residual=None, act=ACT_NONE, out_preact=None,
+            mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False):
+    e = GemmEpi()
+    e.bias, e.residual, e.mul_gelu_grad, e.out_preact = ptr(bias), ptr(residual), ptr(mul_gelu_grad), ptr(out_preact)
+    e.out, e.rowscale = ptr(out), ptr(rowscale)
+    e.rng = ptr(rng_tensor(out.device)) if drop_p > 0 else None
+    e.ld_res = N if residual is not None else 0
+    e.ld_mul = N if mul_gelu_grad is not None else 0
+    e.ld_preact = N if out_preact is not None else 0
+    e.ldc = ldc or N
+    e.rows_per_scale = rows_per_scale
+    e.out_bf16 = 1 if out.dtype == BF16 else 0
+    e.act = act
+    e.accumulate = 1 if accumulate else 0
+    e.dropout_p = float(drop_p)
+    e.drop_stream = drop_stream
+    check(L.lib().mdv_gemm_nt(ptr(A), lda or K, ptr(W), ldw or K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
+    return out
+
+
+def gemm_tn(A, B, R, P, Q, C, *, lda=None, ldb=None, ldc=None):
+    """C[P,Q] += A[R,P]^T B[R,Q]"""
+    check(L.lib().mdv_gemm_tn(ptr(A), lda or P, ptr(B), ldb or Q, R, P, Q, ptr(C), ldc or Q, L.stream()), "mdv_gemm_tn")
+    return C
+
+
+def colsum(x, M, C, out, ld=None):
+    check(L.lib().mdv_colsum(ptr(x), int(x.dtype == BF16), ld or C, ptr(out), M, C, L.stream()), "mdv_colsum")
+    return out
+
+
+def cast_bf16(x, M, C, out=None, ld_in=None, ld_out=None, rowscale=None, rows_per_scale=1, drop_p=0.0, drop_stream=0):
+    if out is None:
+        out = torch.empty((M, C), dtype=BF16, device=x.device)
+    check(L.lib().mdv_cast_bf16(ptr(x), ld_in or C, ptr(out), ld_out or C, M, C, ptr(rowscale), rows_per_scale, float(drop_p),
+                                ptr(rng_tensor(x.device)) if drop_p > 0 else None, drop_stream, L.stream()), "mdv_cast_bf16")
+    return out
+
+
+def layernorm_fwd(x, w, b, M, C, eps=1e-6):
+    y = torch.empty((M, C), dtype=BF16, device=x.device)
+    mean = torch.empty(M, dtype=F32, device=x.device)
+    rstd = torch.empty(M, dtype=F32, device=x.device)
+    check(L.lib().mdv_layernorm_fwd(ptr(x), ptr(w), ptr(b), ctypes.c_float(eps), ptr(y), ptr(mean), ptr(rstd), M, C, L.stream()),
+          "mdv_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, w, dres, M, C, *, masked=False, rowscale=None, rows_per_scale=1, drop_p=0.0, drop_stream=0):
+    dx = torch.empty((M, C), dtype=F32, device=x.device)
+    dxm = torch.empty((M, C), dtype=BF16, device=x.device) if masked else None
+    dg = torch.zeros(C, dtype=F32, device=x.device)
+    db = torch.zeros(C, dtype=F32, device=x.device)
+    check(L.lib().mdv_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(w), ptr(dres), ptr(dx), ptr(dxm), ptr(rowscale),
+                                    rows_per_scale, ctypes.c_float(drop_p), ptr(rng_tensor(x.device)) if drop_p > 0 else None,
+                                    drop_stream, ptr(dg), ptr(db), M, C, L.stream()), "mdv_layernorm_bwd")
+    return dx, dxm, dg, db
+
+
+def dwconv3(x, w, bias, B, Hi, Wi, Ho, Wo, C, stride, *, out_bf16=False, transposed=False, residual=False):
+    out = torch.empty((B, Ho * Wo, C), dtype=BF16 if out_bf16 else F32, device=x.device)
+    check(L.lib().mdv_dwconv3(ptr(x), ptr(w), ptr(bias), ptr(out), int(out_bf16), B, Hi, Wi, Ho, Wo, C, stride, int(transposed),
+                              int(residual), L.stream()), "mdv_dwconv3")
+    return out
+
+
+def dwconv3_wgrad(dy, x, w, bias, B, Hi, Wi, Ho, Wo, C, stride):
+    dw = torch.zeros_like(w)
+    db = torch.zeros_like(bias) if bias is not None else None
+    check(L.lib().mdv_dwconv3_wgrad(ptr(dy), ptr(x), ptr(dw), ptr(db), B, Hi, Wi, Ho, Wo, C, stride, L.stream()), "mdv_dwconv3_wgrad")
+    return dw, db
+
+
+class BNState:
+    """mean/rstd of one BatchNorm application (+ the buffers it updates)."""
+
+    def __init__(self, bn, C):
+        self.bn, self.C = bn, C
+
+
+def bn_forward(z, M, C, weight, bias, running_mean, running_var, nbt, training, act, out_bf16, eps=1e-5, momentum=0.1):
+    dev = z.device
+    mean = torch.empty(C, dtype=F32, device=dev)
+    rstd = torch.empty(C, dtype=F32, device=dev)
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev) if training else None
+    check(L.lib().mdv_bn_stats(ptr(z), M, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(training), ptr(running_mean),
+                               ptr(running_var), ptr(nbt), ptr(mean), ptr(rstd), ptr(ws), L.stream()), "mdv_bn_stats")
+    y = torch.empty((M, C), dtype=BF16 if out_bf16 else F32, device=dev)
+    check(L.lib().mdv_bn_act_fwd(ptr(z), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), act, ptr(y), int(out_bf16), M, C, L.stream()),
+          "mdv_bn_act_fwd")
+    return y, mean, rstd
+
+
+def bn_backward(dy, z, mean, rstd, weight, bias, act, M, C, dz_bf16=True):
+    dev = z.device
+    ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
+    dz = torch.empty((M, C), dtype=BF16 if dz_bf16 else F32, device=dev)
+    dg = torch.zeros(C, dtype=F32, device=dev)
+    db = torch.zeros(C, dtype=F32, device=dev)
+    check(L.lib().mdv_bn_act_bwd(ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), act, ptr(dz), int(dz_bf16), ptr(dg),
+                                 ptr(db), M, C, ptr(ws), L.stream()), "mdv_bn_act_bwd")
+    return dz, dg, db
+
+
+def upsample_fwd(x, out, B, Hi, Wi, Ho, Wo, C, ld_in=None, ld_out=None):
+    check(L.lib().mdv_upsample_fwd(ptr(x), int(x.dtype == BF16), ld_in or C, ptr(out), int(out.dtype == BF16), ld_out or C, B, Hi, Wi,
+                                   Ho, Wo, C, L.stream()), "mdv_upsample_fwd")
+    return out
+
+
+def upsample_bwd(dout, B, Hi, Wi, Ho, Wo, C, ld_out=None):
+    din = torch.empty((B * Hi * Wi, C), dtype=F32, device=dout.device)
+    check(L.lib().mdv_upsample_bwd(ptr(dout), int(dout.dtype == BF16), ld_out or C, ptr(din), C, B, Hi, Wi, Ho, Wo, C, L.stream()),
+          "mdv_upsample_bwd")
+    return din
+
+
+def _contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _dev_ctx(t):
+    return torch.cuda.device(t.device)
+
+
+# ------------------------------------------------------------------------------------------------- SerialBlock
+class BlockFn(torch.autograd.Function):
+    """SerialBlock_adapt.forward (mdvit.py:346-361) incl. ConvPosEnc, FactorAtt_ConvRelPosEnc(_Sup) and Mlp."""
+
+    NP = 24  # number of parameter tensors passed after (x, label)
+
+    @staticmethod
+    def forward(ctx, x, label, cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b,
+                da_w1, da_b1, da_w2, da_b2, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, H, W, drop, dpr, training):
+        B, N, C = x.shape
+        M, dev = B * N, x.device
+        hidden = fc1_w.shape[0]
+        x = _contig(x)
+        lib = L.lib()
+        with _dev_ctx(x):
+            x1 = dwconv3(x, cpe_w, cpe_b, B, H, W, H, W, C, 1, residual=True)
+            ln1, mean1, rstd1 = layernorm_fwd(x1, n1w, n1b, M, C)
+            qkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
+            gemm_nt(ln1, prep_weight(qkv_w, 0, 3 * C, C), M, 3 * C, C, qkv, bias=qkv_b)
+            gate = hid = None
+            if label is not None and da_w1 is not None:
+                label = _contig(label.float())
+                nd, hd = da_w1.shape[1], da_w1.shape[0]
+                gate = torch.empty((B, C), dtype=F32, device=dev)
+                hid = torch.empty((B, hd), dtype=F32, device=dev)
+                check(lib.mdv_da_gate_fwd(ptr(label), ptr(da_w1), ptr(da_b1), ptr(da_w2), ptr(da_b2), ptr(hid), ptr(gate), B, nd, hd,
+                                          C, HEADS, L.stream()), "mdv_da_gate_fwd")
+            stats = torch.empty(lib.mdv_attn_stats_floats(B, C, HEADS), dtype=F32, device=dev)
+            y = torch.empty((M, C), dtype=BF16, device=dev)
+            check(lib.mdv_attn_fwd(ptr(qkv), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b), ptr(stats), ptr(y),
+                                   B, H, W, C, HEADS, L.stream()), "mdv_attn_fwd")
+            p_drop = drop if training else 0.0
+            sid = [new_stream_id() for _ in range(5)] if training and (drop > 0 or dpr > 0) else [0] * 5
+            dp1 = dp2 = None
+            if training and dpr > 0:
+                dp1 = torch.empty(B, dtype=F32, device=dev)
+                dp2 = torch.empty(B, dtype=F32, device=dev)
+                rng = rng_tensor(dev)
+                check(lib.mdv_droppath_scale(ptr(dp1), B, ctypes.c_float(dpr), ptr(rng), sid[3], L.stream()), "mdv_droppath_scale")
+                check(lib.mdv_droppath_scale(ptr(dp2), B, ctypes.c_float(dpr), ptr(rng), sid[4], L.stream()), "mdv_droppath_scale")
+            x2 = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(y, prep_weight(proj_w, 0, C, C), M, C, C, x2, bias=proj_b, residual=x1, drop_p=p_drop, drop_stream=sid[0],
+                    rowscale=dp1, rows_per_scale=N)
+            ln2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, M, C)
+            u = torch.empty((M, hidden), dtype=BF16, device=dev)
+            hact = torch.empty((M, hidden), dtype=BF16, device=dev)
+            gemm_nt(ln2, prep_weight(fc1_w, 0, hidden, C), M, hidden, C, hact, bias=fc1_b, act=ACT_GELU, out_preact=u, drop_p=p_drop,
+                    drop_stream=sid[1])
+            x3 = torch.empty((B, N, C), dtype=F32, device=dev)
+            gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2, drop_p=p_drop,
+                    drop_stream=sid[2], rowscale=dp2, rows_per_scale=N)
+        ctx.save_for_backward(x, label, cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, qkv_w, proj_w, da_w1, da_w2, n2w, fc1_w,
+                              fc2_w, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2)
+        ctx.meta = (B, N, C, H, W, hidden, p_drop, sid)
+        return x3
+
+    @staticmethod
+    def backward(ctx, dx3):
+        (x, label, cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, qkv_w, proj_w, da_w1, da_w2, n2w, fc1_w, fc2_w, x1, mean1, rstd1,
+         ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2) = ctx.saved_tensors
+        B, N, C, H, W, hidden, p_drop, sid = ctx.meta
+        M, dev = B * N, x.device
+        lib = L.lib()
+        dx3 = _contig(dx3.float())
+        z = lambda *s: torch.zeros(s, dtype=F32, device=dev)  # noqa: E731
+        with _dev_ctx(x):
+            # ---- MLP
+            d_fc2 = cast_bf16(dx3, M, C, rowscale=dp2, rows_per_scale=N, drop_p=p_drop, drop_stream=sid[2])
+            g_fc2_w = gemm_tn(d_fc2, hact, M, C, hidden, z(C, hidden))
+            g_fc2_b = colsum(d_fc2, M, C, z(C))
+            du = torch.empty((M, hidden), dtype=BF16, device=dev)
+            gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, drop_p=p_drop, drop_stream=sid[1])
+            g_fc1_w = gemm_tn(du, ln2, M, hidden, C, z(hidden, C))
+            g_fc1_b = colsum(du, M, hidden, z(hidden))
+            dln2 = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(du, prep_weight(fc1_w, 1, hidden, C), M, C, hidden, dln2)
+            dx2, d_proj, g_n2w, g_n2b = layernorm_bwd(dln2, x2, mean2, rstd2, n2w, dx3, M, C, masked=True, rowscale=dp1,
+                                                      rows_per_scale=N, drop_p=p_drop, drop_stream=sid[0])
+            # ---- attention
+            g_proj_w = gemm_tn(d_proj, y, M, C, C, z(C, C))
+            g_proj_b = colsum(d_proj, M, C, z(C))
+            dy = torch.empty((M, C), dtype=BF16, device=dev)
+            gemm_nt(d_proj, prep_weight(proj_w, 1, C, C), M, C, C, dy)
+            dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
+            Ch = C // HEADS
+            dgate = z(B, C) if gate is not None else None
+            g3w, g3b, g5w, g5b, g7w, g7b = (torch.zeros_like(t) for t in (c3w, c3b, c5w, c5b, c7w, c7b))
+            ws = torch.empty(B * C * (2 * Ch + 1), dtype=F32, device=dev)
+            check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
+                                   ptr(stats), ptr(dqkv), ptr(dgate), ptr(g3w), ptr(g3b), ptr(g5w), ptr(g5b), ptr(g7w), ptr(g7b),
+                                   ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")
+            g_da = (None, None, None, None)
+            if gate is not None:
+                nd, hd = da_w1.shape[1], da_w1.shape[0]
+                g_da = (z(hd, nd), z(hd), z(C, hd), z(C))
+                check(lib.mdv_da_gate_bwd(ptr(label), ptr(da_w2), ptr(hid), ptr(gate), ptr(dgate), ptr(g_da[0]), ptr(g_da[1]),
+                                          ptr(g_da[2]), ptr(g_da[3]), B, nd, hd, C, HEADS, L.stream()), "mdv_da_gate_bwd")
+            g_qkv_w = gemm_tn(dqkv, ln1, M, 3 * C, C, z(3 * C, C))
+            g_qkv_b = colsum(dqkv, M, 3 * C, z(3 * C))
+            dln1 = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(dqkv, prep_weight(qkv_w, 1, 3 * C, C), M, C, 3 * C, dln1)
+            dx1, _, g_n1w, g_n1b = layernorm_bwd(dln1, x1, mean1, rstd1, n1w, dx2, M, C)
+            # ---- ConvPosEnc
+            dx = dwconv3(dx1, cpe_w, None, B, H, W, H, W, C, 1, transposed=True, residual=True)
+            g_cpe_w, g_cpe_b = dwconv3_wgrad(dx1, x, cpe_w, cpe_b, B, H, W, H, W, C, 1)
+        return (dx.view(B, N, C), None, g_cpe_w, g_cpe_b, g3w, g3b, g5w, g5b, g7w, g7b, g_n1w, g_n1b, g_qkv_w, g_qkv_b, g_proj_w,
+                g_proj_b, g_da[0], g_da[1], g_da[2], g_da[3], g_n2w, g_n2b, g_fc1_w, g_fc1_b, g_fc2_w, g_fc2_b, None, None, None, None,
+                None)
+
+
+# ------------------------------------------------------------------------------------------------- conv pieces
+def _bn_args(bn):
+    return bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked
+
+
+class StemFn(torch.autograd.Function):
+    """stem = 2x (Conv3x3 s2 no-bias -> BN -> Hardswish), mdvit.py:509-526.  im2col (bf16) + tcgen05 GEMM."""
+
+    @staticmethod
+    def forward(ctx, img, w0, g0, b0, w1, g1, b1, bufs, training):
+        B, _, H, W = img.shape
+        dev = img.device
+        img = _contig(img.float())
+        H1, W1, H2, W2 = H // 2, W // 2, H // 4, W // 4
+        M0, M1 = B * H1 * W1, B * H2 * W2
+        rm0, rv0, nb0, rm1, rv1, nb1 = bufs
+        lib = L.lib()
+        with _dev_ctx(img):
+            col0 = torch.empty((M0, 64), dtype=BF16, device=dev)
+            check(lib.mdv_im2col_stem(ptr(img), ptr(col0), B, H, W, L.stream()), "mdv_im2col_stem")
+            z0 = torch.empty((M0, 32), dtype=F32, device=dev)
+            gemm_nt(col0, prep_weight(w0, 2, 32, 27, ld=64, cin=3), M0, 32, 64, z0)
+            a0, mean0, rstd0 = bn_forward(z0, M0, 32, g0, b0, rm0, rv0, nb0, training, ACT_HSWISH, True)
+            col1 = torch.empty((M1, 288), dtype=BF16, device=dev)
+            check(lib.mdv_im2col3(ptr(a0), 1, ptr(col1), B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_im2col3")
+            z1 = torch.empty((M1, 64), dtype=F32, device=dev)
+            gemm_nt(col1, prep_weight(w1, 2, 64, 288, cin=32), M1, 64, 288, z1)
+            y, mean1, rstd1 = bn_forward(z1, M1, 64, g1, b1, rm1, rv1, nb1, training, ACT_HSWISH, False)
+        ctx.save_for_backward(w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
+        ctx.meta = (B, H1, W1, H2, W2, training)
+        return y.view(B, H2 * W2, 64)
+
+    @staticmethod
+    def backward(ctx, dy):
+        w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        B, H1, W1, H2, W2, training = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        M0, M1, dev = B * H1 * W1, B * H2 * W2, dy.device
+        lib = L.lib()
+        dy = _contig(dy.float())
+        with _dev_ctx(dy):
+            dz1, dg1, db1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_HSWISH, M1, 64)
+            gw1p = gemm_tn(dz1, col1, M1, 64, 288, torch.zeros((64, 288), dtype=F32, device=dev))
+            gw1 = torch.zeros_like(w1)
+            check(lib.mdv_unperm_conv_grad(ptr(gw1p), 288, ptr(gw1), 64, 32, L.stream()), "mdv_unperm_conv_grad")
+            dcol1 = torch.empty((M1, 288), dtype=F32, device=dev)
+            gemm_nt(dz1, prep_weight(w1, 3, 64, 288, cin=32), M1, 288, 64, dcol1)
+            da0 = torch.empty((M0, 32), dtype=F32, device=dev)
+            check(lib.mdv_col2im3(ptr(dcol1), ptr(da0), B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_col2im3")
+            dz0, dg0, db0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_HSWISH, M0, 32)
+            gw0p = gemm_tn(dz0, col0, M0, 32, 64, torch.zeros((32, 64), dtype=F32, device=dev))
+            gw0 = torch.zeros_like(w0)
+            check(lib.mdv_unperm_conv_grad(ptr(gw0p), 64, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
+        return None, gw0, dg0, db0, gw1, dg1, db1, None, None
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """DWCPatchEmbed: depthwise 3x3 (stride s) -> 1x1 conv -> BN -> Hardswish, mdvit.py:114-123."""
+
+    @staticmethod
+    def forward(ctx, x, dw_w, pw_w, g, b, bufs, Hi, Wi, stride, training):
+        B, _, Cin = x.shape
+        C = pw_w.shape[0]
+        Ho, Wo = (Hi + 2 - 3) // stride + 1, (Wi + 2 - 3) // stride + 1
+        M, dev = B * Ho * Wo, x.device
+        x = _contig(x)
+        rm, rv, nb = bufs
+        with _dev_ctx(x):
+            t = dwconv3(x, dw_w, None, B, Hi, Wi, Ho, Wo, Cin, stride, out_bf16=True)
+            z = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(t, prep_weight(pw_w, 0, C, Cin), M, C, Cin, z)
+            y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
+        ctx.save_for_backward(x, dw_w, pw_w, g, b, t, z, mean, rstd)
+        ctx.meta = (B, Hi, Wi, Ho, Wo, Cin, C, stride, training)
+        return y.view(B, Ho * Wo, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, dw_w, pw_w, g, b, t, z, mean, rstd = ctx.saved_tensors
+        B, Hi, Wi, Ho, Wo, Cin, C, stride, training = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        M, dev = B * Ho * Wo, dy.device
+        dy = _contig(dy.float())
+        with _dev_ctx(dy):
+            dz, dg, db = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
+            g_pw = gemm_tn(dz, t, M, C, Cin, torch.zeros((C, Cin), dtype=F32, device=dev)).view_as(pw_w)
+            dt = torch.empty((M, Cin), dtype=F32, device=dev)
+            gemm_nt(dz, prep_weight(pw_w, 1, C, Cin), M, Cin, C, dt)
+            dx = dwconv3(dt, dw_w, None, B, Ho, Wo, Hi, Wi, Cin, stride, transposed=True)
+            g_dw, _ = dwconv3_wgrad(dt, x, dw_w, None, B, Hi, Wi, Ho, Wo, Cin, stride)
+        return dx.view(B, Hi * Wi, Cin), g_dw, g_pw, dg, db, None, None, None, None, None
+
+
+class BridgeFn(torch.autograd.Function):
+    """bridge = 2x (Conv3x3 + bias -> BN -> ReLU), mdvit.py:557-564."""
+
+    @staticmethod
+    def forward(ctx, x, w0, c0, g0, b0, w1, c1, g1, b1, bufs, H, W, training):
+        B, _, C = x.shape
+        C0, C1 = w0.shape[0], w1.shape[0]
+        M, dev = B * H * W, x.device
+        x = _contig(x)
+        rm0, rv0, nb0, rm1, rv1, nb1 = bufs
+        lib = L.lib()
+        with _dev_ctx(x):
+            col0 = torch.empty((M, 9 * C), dtype=BF16, device=dev)
+            check(lib.mdv_im2col3(ptr(x), 0, ptr(col0), B, H, W, H, W, C, 1, 9 * C, L.stream()), "mdv_im2col3")
+            z0 = torch.empty((M, C0), dtype=F32, device=dev)
+            gemm_nt(col0, prep_weight(w0, 2, C0, 9 * C, cin=C), M, C0, 9 * C, z0, bias=c0)
+            a0, mean0, rstd0 = bn_forward(z0, M, C0, g0, b0, rm0, rv0, nb0, training, ACT_RELU, True)
+            col1 = torch.empty((M, 9 * C0), dtype=BF16, device=dev)
+            check(lib.mdv_im2col3(ptr(a0), 1, ptr(col1), B, H, W, H, W, C0, 1, 9 * C0, L.stream()), "mdv_im2col3")
+            z1 = torch.empty((M, C1), dtype=F32, device=dev)
+            gemm_nt(col1, prep_weight(w1, 2, C1, 9 * C0, cin=C0), M, C1, 9 * C0, z1, bias=c1)
+            y, mean1, rstd1 = bn_forward(z1, M, C1, g1, b1, rm1, rv1, nb1, training, ACT_RELU, False)
+        ctx.save_for_backward(w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
+        ctx.meta = (B, H, W, C, C0, C1, training)
+        return y.view(B, H * W, C1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        B, H, W, C, C0, C1, training = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        M, dev = B * H * W, dy.device
+        lib = L.lib()
+        dy = _contig(dy.float())
+
+        def conv_bwd(dz, col, w, Cout, Cin):
+            gwp = gemm_tn(dz, col, M, Cout, 9 * Cin, torch.zeros((Cout, 9 * Cin), dtype=F32, device=dev))
+            gw = torch.zeros_like(w)
+            check(lib.mdv_unperm_conv_grad(ptr(gwp), 9 * Cin, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
+            gb = colsum(dz, M, Cout, torch.zeros(Cout, dtype=F32, device=dev))
+            dcol = torch.empty((M, 9 * Cin), dtype=F32, device=dev)
+            gemm_nt(dz, prep_weight(w, 3, Cout, 9 * Cin, cin=Cin), M, 9 * Cin, Cout, dcol)
+            dx = torch.empty((M, Cin), dtype=F32, device=dev)
+            check(lib.mdv_col2im3(ptr(dcol), ptr(dx), B, H, W, H, W, Cin, 1, 9 * Cin, L.stream()), "mdv_col2im3")
+            return gw, gb, dx
+
+        with _dev_ctx(dy):
+            dz1, dg1, db1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_RELU, M, C1)
+            gw1, gc1, da0 = conv_bwd(dz1, col1, w1, C1, C0)
+            dz0, dg0, db0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_RELU, M, C0)
+            gw0, gc0, dx = conv_bwd(dz0, col0, w0, C0, C)
+        return dx.view(B, H * W, C), gw0, gc0, dg0, db0, gw1, gc1, dg1, db1, None, None, None, None
+
+
+class DecoderConvFn(torch.autograd.Function):
+    """Conv part of UnetDecodingBlockTransformer.forward (Decoders.py:194-205): bilinear up -> 1x1 conv_before -> cat(skip, .) ->
+    grouped 3x3 (2 in/group) -> 1x1 -> BN -> Hardswish.  conv_before is commuted in front of the resize (exact)."""
+
+    @staticmethod
+    def forward(ctx, inp, skip, cb_w, cb_b, dw_w, pw_w, g, b, bufs, h, w, H, W, training):
+        B, _, Cin = inp.shape
+        C = cb_w.shape[0]
+        m, M, dev = B * h * w, B * H * W, inp.device
+        inp, skip = _contig(inp), _contig(skip)
+        rm, rv, nb = bufs
+        lib = L.lib()
+        with _dev_ctx(inp):
+            a = cast_bf16(inp, m, Cin)
+            t = torch.empty((m, C), dtype=F32, device=dev)
+            gemm_nt(a, prep_weight(cb_w, 0, C, Cin), m, C, Cin, t, bias=cb_b)
+            up = upsample_fwd(t, torch.empty((M, C), dtype=F32, device=dev), B, h, w, H, W, C)
+            gc = torch.empty((M, C), dtype=BF16, device=dev)
+            check(lib.mdv_gconv2_fwd(ptr(skip), ptr(up), ptr(dw_w), ptr(gc), B, H, W, C, L.stream()), "mdv_gconv2_fwd")
+            z = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(gc, prep_weight(pw_w, 0, C, C), M, C, C, z)
+            y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
+        ctx.save_for_backward(skip, cb_w, dw_w, pw_w, g, b, a, up, gc, z, mean, rstd)
+        ctx.meta = (B, h, w, H, W, Cin, C, training)
+        return y.view(B, H * W, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        skip, cb_w, dw_w, pw_w, g, b, a, up, gc, z, mean, rstd = ctx.saved_tensors
+        B, h, w, H, W, Cin, C, training = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        m, M, dev = B * h * w, B * H * W, dy.device
+        lib = L.lib()
+        dy = _contig(dy.float())
+        with _dev_ctx(dy):
+            dz, dg, db = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
+            g_pw = gemm_tn(dz, gc, M, C, C, torch.zeros((C, C), dtype=F32, device=dev)).view_as(pw_w)
+            dgc = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(dz, prep_weight(pw_w, 1, C, C), M, C, C, dgc)
+            dskip = torch.empty((M, C), dtype=F32, device=dev)
+            dup = torch.empty((M, C), dtype=F32, device=dev)
+            g_dw = torch.zeros_like(dw_w)
+            check(lib.mdv_gconv2_bwd(ptr(dgc), ptr(skip), ptr(up), ptr(dw_w), ptr(dskip), ptr(dup), ptr(g_dw), B, H, W, C, L.stream()),
+                  "mdv_gconv2_bwd")
+            dt = upsample_bwd(dup, B, h, w, H, W, C)
+            dtb = cast_bf16(dt, m, C)
+            g_cb = gemm_tn(dtb, a, m, C, Cin, torch.zeros((C, Cin), dtype=F32, device=dev)).view_as(cb_w)
+            g_cbb = colsum(dt, m, C, torch.zeros(C, dtype=F32, device=dev))
+            dinp = torch.empty((m, Cin), dtype=F32, device=dev)
+            gemm_nt(dtb, prep_weight(cb_w, 1, C, Cin), m, Cin, C, dinp)
+        return (dinp.view(B, h * w, Cin), dskip.view(B, H * W, C), g_cb, g_cbb, g_dw, g_pw, dg, db, None, None, None, None, None, None)
+
+
+class HeadFn(torch.autograd.Function):
+    """bilinear up to the image size -> 1x1 conv C->1 (mdvit.py:699-700), evaluated as conv-then-resize (exact)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, H, W, Ho, Wo):
+        B, _, C = x.shape
+        dev = x.device
+        x = _contig(x)
+        lib = L.lib()
+        with _dev_ctx(x):
+            lo = torch.empty(B * H * W, dtype=F32, device=dev)
+            check(lib.mdv_rowdot_fwd(ptr(x), 0, ptr(w), ptr(b), ptr(lo), B * H * W, C, H * W, ctypes.c_float(0.0), None, 0, L.stream()),
+                  "mdv_rowdot_fwd")
+            out = upsample_fwd(lo, torch.empty((B, 1, Ho, Wo), dtype=F32, device=dev), B, H, W, Ho, Wo, 1)
+        ctx.save_for_backward(x, w)
+        ctx.meta = (B, C, H, W, Ho, Wo)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        B, C, H, W, Ho, Wo = ctx.meta
+        dev = x.device
+        lib = L.lib()
+        dout = _contig(dout.float())
+        with _dev_ctx(x):
+            dlo = upsample_bwd(dout, B, H, W, Ho, Wo, 1)
+            dx = torch.empty((B, H * W, C), dtype=F32, device=dev)
+            dw = torch.zeros_like(w)
+            db = torch.zeros(1, dtype=F32, device=dev)
+            check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(x), 0, ptr(w), ptr(dx), ptr(dw), ptr(db), B * H * W, C, H * W, ctypes.c_float(0.0),
+                                     None, 0, L.stream()), "mdv_rowdot_bwd")
+        return dx, dw, db, None, None, None, None
+
+
+class AuxFn(torch.autograd.Function):
+    """MLPDecoderFM.forward (Decoders.py:315-339): the MKD auxiliary 'peer' decoder."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, x3, x4, x5, l1w, l1b, l2w, l2b, l3w, l3b, l4w, l4b, fw, fb, g, b, ow, ob, bufs, sizes, Ho, Wo, drop2d,
+                training):
+        B = x1.shape[0]
+        dev = x1.device
+        xs = [_contig(t) for t in (x1, x2, x3, x4)]
+        x5 = _contig(x5)
+        (H, W) = sizes[0]
+        M0 = B * H * W
+        hc = fw.shape[0]               # 512
+        K = fw.shape[1]                # 2112
+        C5 = x5.shape[2]
+        rm, rv, nb = bufs
+        lib = L.lib()
+        lw, lb = (l1w, l2w, l3w, l4w), (l1b, l2b, l3b, l4b)
+        with _dev_ctx(x1):
+            cat = torch.empty((M0, K), dtype=BF16, device=dev)
+            acts = []
+            for i in range(4):
+                Hi, Wi = sizes[i]
+                Mi, Ci = B * Hi * Wi, xs[i].shape[2]
+                a = cast_bf16(xs[i], Mi, Ci)
+                acts.append(a)
+                wb = prep_weight(lw[i], 0, hc, Ci)
+                if i == 0:
+                    gemm_nt(a, wb, Mi, hc, Ci, cat, ldc=K, bias=lb[i])
+                else:
+                    t = torch.empty((Mi, hc), dtype=BF16, device=dev)
+                    gemm_nt(a, wb, Mi, hc, Ci, t, bias=lb[i])
+                    upsample_fwd(t, cat[:, i * hc:], B, Hi, Wi, H, W, hc, ld_out=K)
+            cast_bf16(x5, M0, C5, out=cat[:, 4 * hc:], ld_out=K)
+            z = torch.empty((M0, hc), dtype=F32, device=dev)
+            gemm_nt(cat, prep_weight(fw, 0, hc, K), M0, hc, K, z, bias=fb)
+            a5, mean, rstd = bn_forward(z, M0, hc, g, b, rm, rv, nb, training, ACT_RELU, True)
+            p2 = drop2d if training else 0.0
+            sid = new_stream_id() if p2 > 0 else 0
+            lo = torch.empty(M0, dtype=F32, device=dev)
+            check(lib.mdv_rowdot_fwd(ptr(a5), 1, ptr(ow), ptr(ob), ptr(lo), M0, hc, H * W, ctypes.c_float(p2),
+                                     ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_fwd")
+            out = upsample_fwd(lo, torch.empty((B, 1, Ho, Wo), dtype=F32, device=dev), B, H, W, Ho, Wo, 1)
+        ctx.save_for_backward(l1w, l2w, l3w, l4w, fw, g, b, ow, cat, z, mean, rstd, a5, *acts)
+        ctx.meta = (B, sizes, Ho, Wo, hc, K, C5, p2, sid, training, [t.shape[2] for t in xs])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        l1w, l2w, l3w, l4w, fw, g, b, ow, cat, z, mean, rstd, a5, *acts = ctx.saved_tensors
+        B, sizes, Ho, Wo, hc, K, C5, p2, sid, training, Cs = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        (H, W) = sizes[0]
+        M0, dev = B * H * W, dout.device
+        lib = L.lib()
+        dout = _contig(dout.float())
+        lw = (l1w, l2w, l3w, l4w)
+        zf = lambda *s: torch.zeros(s, dtype=F32, device=dev)  # noqa: E731
+        with _dev_ctx(dout):
+            dlo = upsample_bwd(dout, B, H, W, Ho, Wo, 1)
+            da5 = torch.empty((M0, hc), dtype=F32, device=dev)
+            g_ow, g_ob = torch.zeros_like(ow), zf(1)
+            check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(a5), 1, ptr(ow), ptr(da5), ptr(g_ow), ptr(g_ob), M0, hc, H * W, ctypes.c_float(p2),
+                                     ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_bwd")
+            dz, dg, db = bn_backward(da5, z, mean, rstd, g, b, ACT_RELU, M0, hc)
+            g_fw = gemm_tn(dz, cat, M0, hc, K, zf(hc, K)).view_as(fw)
+            g_fb = colsum(dz, M0, hc, zf(hc))
+            dcat = torch.empty((M0, K), dtype=BF16, device=dev)
+            gemm_nt(dz, prep_weight(fw, 1, hc, K), M0, K, hc, dcat)
+            gx, gw, gb = [], [], []
+            for i in range(4):
+                Hi, Wi = sizes[i]
+                Mi, Ci = B * Hi * Wi, Cs[i]
+                sl = dcat[:, i * hc:]
+                if i == 0:
+                    dtb, lda = sl, K
+                    gb.append(colsum(sl, Mi, hc, zf(hc), ld=K))
+                else:
+                    dt = upsample_bwd(sl, B, Hi, Wi, H, W, hc, ld_out=K)
+                    dtb, lda = cast_bf16(dt, Mi, hc), hc
+                    gb.append(colsum(dt, Mi, hc, zf(hc)))
+                gw.append(gemm_tn(dtb, acts[i], Mi, hc, Ci, zf(hc, Ci), lda=lda).view_as(lw[i]))
+                dxi = torch.empty((B, Hi * Wi, Ci), dtype=F32, device=dev)
+                gemm_nt(dtb, prep_weight(lw[i], 1, hc, Ci), Mi, Ci, hc, dxi, lda=lda)
+                gx.append(dxi)
+            dx5 = torch.empty((B, H * W, C5), dtype=F32, device=dev)
+            check(lib.mdv_add_f32(ptr(dcat[:, 4 * hc:]), 1, K, ptr(dx5), C5, M0, C5, 0, L.stream()), "mdv_add_f32")
+        return (gx[0], gx[1], gx[2], gx[3], dx5, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2], gw[3], gb[3], g_fw, g_fb, dg, db, g_ow, g_ob,
+                None, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------- fused losses
+class SegLossFn(torch.autograd.Function):
+    """(L_seg, L_aux, L_kt) of multi_train_MDViT.py:147-169 in one pass over (out, aux, label); `reduce_sums` (optional
+    callable) all-reduces the 8 partial sums across data-parallel ranks so Dice is the global-batch Dice."""
+
+    @staticmethod
+    def forward(ctx, out, aux, label, n_total, reduce_sums):
+        out, label = _contig(out.float()), _contig(label.float())
+        aux = _contig(aux.float()) if aux is not None else None
+        dev, n = out.device, out.numel()
+        lib = L.lib()
+        with _dev_ctx(out):
+            sums = torch.empty(8, dtype=torch.float64, device=dev)
+            check(lib.mdv_loss_sums(ptr(out), ptr(aux), ptr(label), ptr(sums), n, L.stream()), "mdv_loss_sums")
+            if reduce_sums is not None:
+                reduce_sums(sums)
+            losses = torch.empty(3, dtype=F32, device=dev)
+            check(lib.mdv_loss_finalize(ptr(sums), ctypes.c_double(n_total or n), ptr(losses), L.stream()), "mdv_loss_finalize")
+        ctx.save_for_backward(out, aux, label, sums)
+        ctx.n_total = float(n_total or n)
+        return losses
+
+    @staticmethod
+    def backward(ctx, dl):
+        out, aux, label, sums = ctx.saved_tensors
+        lib = L.lib()
+        dl = _contig(dl.float())
+        with _dev_ctx(out):
+            dout = torch.empty_like(out)
+            daux = torch.empty_like(aux) if aux is not None else None
+            check(lib.mdv_loss_bwd(ptr(out), ptr(aux), ptr(label), ptr(sums), ctypes.c_double(ctx.n_total), ptr(dl), ptr(dout), ptr(daux),
+                                   out.numel(), L.stream()), "mdv_loss_bwd")
+        return dout, daux, None, None, None
+
+
+def seg_losses(out, aux, label, n_total=None, reduce_sums=None):
+    return SegLossFn.apply(out, aux, label, n_total, reduce_sums)

@@ -1,0 +1,159 @@
+"""The MDViT training step (multi_train_MDViT.py:121-213) on the B200 kernels, single- or multi-GPU.
+
+One step = 4 domain forwards (each a single-domain mini-batch) -> fused BCE+Dice / MKD losses -> the reference's
+two-pass backward (aux loss with `domain_layer` frozen, then 0.5*kt + 0.5*seg) -> gradient all-reduce -> fused AdamW.
+
+Data parallelism (replaces nn.DataParallel, multi_train_MDViT.py:73-74): one process per GPU; every rank runs all four
+domain forwards on its own slice of each domain batch.  The 8 loss partial sums are all-reduced so BCE/Dice are those
+of the gathered global batch (what DataParallel computes on GPU0); gradients are then a plain SUM over ranks, all-reduced
+in one flat fp32 buffer that the fused AdamW consumes in place.  BatchNorm statistics stay per-replica, as in DataParallel.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from ._lib import check, ptr
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class MKDTrainer:
+    def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, process_group=None,
+                 num_domains=4, with_aux=True):
+        self.model = model
+        self.alpha = alpha
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.num_domains = num_domains
+        self.with_aux = with_aux
+        self.t = 0
+        params, seen = [], set()
+        for p in model.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        self.params = params
+        dev = params[0].device
+        self.device = dev
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += _align(p.numel())
+        self.total = total
+        with torch.no_grad():
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            for p, o in zip(params, offs):
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.da_params = [p for n, p in model.named_parameters() if "domain_layer" in n]
+        ops.bump_weight_epoch()
+        self._graph = None
+
+    # ------------------------------------------------------------------ pieces
+    def _reduce_sums(self, sums):
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def forward_losses(self, batches):
+        """batches: list of (img [B,3,H,W], label [B,1,H,W], domain index).  Returns [n_dom, 3] losses (seg, aux, kt)."""
+        out = []
+        for img, label, d in batches:
+            B = img.shape[0]
+            dl = torch.zeros((B, self.num_domains), dtype=torch.float32, device=img.device)
+            dl[:, int(d)] = 1.0
+            if self.with_aux:
+                o, a = self.model(img, dl, str(d))
+            else:
+                o, a = self.model(img), None
+            n_total = o.numel() * self.world
+            out.append(ops.seg_losses(o, a, label, n_total=n_total, reduce_sums=self._reduce_sums if self.world > 1 else None))
+        return torch.stack(out)
+
+    def backward(self, losses):
+        """multi_train_MDViT.py:195-207: aux pass with DA frozen (retain_graph), then alpha*kt + (1-alpha)*seg."""
+        seg, aux, kt = losses[:, 0].sum(), losses[:, 1].sum(), losses[:, 2].sum()
+        if self.with_aux:
+            for p in self.da_params:
+                p.requires_grad = False
+            aux.backward(retain_graph=True)
+            for p in self.da_params:
+                p.requires_grad = True
+            (self.alpha * kt + (1.0 - self.alpha) * seg).backward()
+        else:
+            seg.backward()
+
+    def _set_hyper(self):
+        self.t += 1
+        b1, b2 = self.betas
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3], h[4] = self.lr, b1, b2, self.eps, self.wd
+        h[5], h[6], h[7] = 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, 1.0
+        self.hyper.copy_(h, non_blocking=True)
+
+    def optimizer_step(self):
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        with torch.cuda.device(self.device):
+            check(L.lib().mdv_adamw(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.hyper), self.total, L.stream()),
+                  "mdv_adamw")
+            ops.rng_bump(self.device)
+
+    def _step_body(self, batches):
+        ops.reset_stream_ids()
+        self.grad.zero_()
+        # autograd accumulates into the flat views (p.grad is never None, so `+=` lands in self.grad)
+        losses = self.forward_losses(batches)
+        self.backward(losses)
+        self.optimizer_step()
+        return losses.detach()
+
+    # ------------------------------------------------------------------ eager step
+    def step(self, batches):
+        self._set_hyper()
+        ops.bump_weight_epoch()
+        return self._step_body(batches)
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def capture(self, example_batches, warmup=2):
+        """Capture the whole step into one CUDA graph over static input buffers (launch-bound otherwise: ~3k kernels)."""
+        self.static = [(img.clone(), lab.clone(), d) for img, lab, d in example_batches]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._set_hyper()
+                ops.bump_weight_epoch()
+                self._step_body(self.static)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        self._set_hyper()
+        ops.bump_weight_epoch()
+        n0 = L.lib().mdv_launch_count()
+        with torch.cuda.graph(self._graph):
+            self._static_losses = self._step_body(self.static)
+        self.launches_per_step = L.lib().mdv_launch_count() - n0   # kernels of this library captured per step
+        return self
+
+    def step_graph(self, batches=None):
+        """Replay; `batches` (host or device tensors) are copied into the static buffers first."""
+        if batches is not None:
+            for (s_img, s_lab, _), (img, lab, _) in zip(self.static, batches):
+                s_img.copy_(img, non_blocking=True)
+                s_lab.copy_(lab, non_blocking=True)
+        self._set_hyper()
+        self._graph.replay()
+        return self._static_losses

