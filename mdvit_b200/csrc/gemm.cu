@@ -1,14 +1,17 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a.
+// Persistent, warp-specialised tcgen05 / TMEM / TMA GEMM for sm_100a.
 //
 //   mdv_gemm_nt : C[M,N] = epilogue( A[M,K] . W[N,K]^T )      (both operands K-major; Linear / 1x1 conv fwd + dgrad)
-//   mdv_gemm_tn : C[P,Q] += A[R,P]^T . B[R,Q]                 (both operands MN-major; weight gradients, split over R,
-//                                                              fp32 atomics into the gradient buffer)
+//   mdv_gemm_tn : C[P,Q] += A[R,P]^T . B[R,Q]                 (both operands MN-major; weight gradients; the reduction
+//                                                              is split over CTAs and summed with TMA reduce-add)
 //
-// One CTA computes one 128 x BN output tile.  Warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
-// tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> smem transpose -> coalesced global stores).
-// Operand tiles are staged in 128B-swizzled shared memory by TMA through an mbarrier ring; the fp32 accumulator
-// lives in TMEM.  Replaces the aten::addmm / cudnn 1x1-conv calls behind nn.Linear / nn.Conv2d(k=1) in
-// reference Models/Transformer/mdvit.py:288,310, mpvit.py:72-76, Decoders.py:197,59,317-333.
+// One CTA per SM loops over 128 x BN output tiles (tile = blockIdx.x, += gridDim.x; BN is a runtime multiple of 32).
+//   warp 0      TMA producer: 128B-swizzled operand tiles into an mbarrier ring of `stages` buffers; runs ahead across tiles
+//   warp 1      single-thread tcgen05.mma issuer; fp32 accumulators live in TMEM, double-buffered (2 x 256 columns)
+//   warp 2      TMEM allocator
+//   warps 4..11 epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / dropout / DropPath / residual in registers ->
+//               swizzled shared-memory slab -> TMA store (bf16 or fp32), overlapping the next tile's loads and MMAs
+// Replaces the aten::addmm / cudnn 1x1-conv calls behind nn.Linear / nn.Conv2d(k=1) in the reference
+// (Models/Transformer/mdvit.py:288,310, mpvit.py:72-76, Decoders.py:197,59,317-333) and their backward passes.
 #include <cuda.h>
 
 #include "../../include/mdvit_b200.h"
@@ -18,17 +21,20 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int MAX_STAGES = 6;
-constexpr int EPI_ROW_F = 68;                       // padded fp32 row of the 32x64 staging tile
-constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_F * 4;  // 8704
-constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;       // 34816
+constexpr int MAX_STAGES = 8;
+constexpr int A_BYTES = BM * BK * 2;       // 16 KB
+constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
 
 struct GemmParams {
     int M, N, K;          // NT: output M x N, reduce K.  TN: output P(=M) x Q(=N), reduce R(=K)
+    int BN;               // tile width (multiple of 32, <= 256; TN: multiple of 64)
     int stages;
-    int kb_per_split;     // TN: k-blocks per blockIdx.z
+    int n_tiles, m_tiles, splits, kb_per_split;
+    int has_preact;
+    int nbuf;             // staging buffers per epilogue warp (2 or 4)
+    int out_slab, buf_bytes;   // bytes of the output slab (2 KB bf16 / 4 KB fp32) and of one buffer (out [+ 2 KB preact])
     MdvGemmEpi epi;
-    int atomic;           // TN: atomicAdd into fp32 out
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -38,6 +44,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
@@ -60,6 +69,26 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -114,96 +143,65 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool mn_major) {
     return d;
 }
 
-__device__ __forceinline__ void epilogue_pair(const GemmParams& p, float v0, float v1, int row, int col, uint32_t dkey,
-                                              uint32_t dthr, float dinv) {
-    const MdvGemmEpi& e = p.epi;
-    if (e.bias) {
-        v0 += __ldg(e.bias + col);
-        v1 += __ldg(e.bias + col + 1);
-    }
-    if (e.out_preact) *reinterpret_cast<uint32_t*>((bf16*)e.out_preact + (size_t)row * e.ld_preact + col) = f2_to_bf2(v0, v1);
-    if (e.act == MDV_ACT_GELU) {
-        v0 = gelu_erf(v0);
-        v1 = gelu_erf(v1);
-    }
-    if (e.mul_gelu_grad) {
-        float2 u = bf2_to_f2(*reinterpret_cast<const uint32_t*>((const bf16*)e.mul_gelu_grad + (size_t)row * e.ld_mul + col));
-        v0 *= gelu_erf_grad(u.x);
-        v1 *= gelu_erf_grad(u.y);
-    }
-    if (dthr) {
-        unsigned long long idx = (unsigned long long)row * (unsigned)p.N + (unsigned)col;
-        v0 *= drop_scale(dkey, idx, dthr, dinv);
-        v1 *= drop_scale(dkey, idx + 1, dthr, dinv);
-    }
-    if (e.rowscale) {
-        float s = __ldg(e.rowscale + row / e.rows_per_scale);
-        v0 *= s;
-        v1 *= s;
-    }
-    if (e.residual) {
-        float2 r = *reinterpret_cast<const float2*>(e.residual + (size_t)row * e.ld_res + col);
-        v0 += r.x;
-        v1 += r.y;
-    }
-    if (p.atomic) {
-        float* o = (float*)e.out + (size_t)row * e.ldc + col;
-        atomicAdd(o, v0);
-        atomicAdd(o + 1, v1);
-    } else if (e.out_bf16) {
-        *reinterpret_cast<uint32_t*>((bf16*)e.out + (size_t)row * e.ldc + col) = f2_to_bf2(v0, v1);
+struct TileCoord {
+    int m_tile, n_tile, kb0, num_kb;
+};
+template <bool TN>
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
+    TileCoord c;
+    c.n_tile = t % p.n_tiles;
+    const int r = t / p.n_tiles;
+    c.m_tile = r % p.m_tiles;
+    const int total_kb = (p.K + BK - 1) / BK;
+    if (TN) {
+        c.kb0 = (r / p.m_tiles) * p.kb_per_split;
+        c.num_kb = min(p.kb_per_split, total_kb - c.kb0);
     } else {
-        float2* o = reinterpret_cast<float2*>((float*)e.out + (size_t)row * e.ldc + col);
-        if (e.accumulate) {
-            float2 old = *o;
-            v0 += old.x;
-            v1 += old.y;
-        }
-        *o = make_float2(v0, v1);
+        c.kb0 = 0;
+        c.num_kb = total_kb;
     }
+    return c;
 }
 
-template <int BN, bool TN>
-__global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+template <bool TN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
 
-    constexpr uint32_t A_BYTES = BM * BK * 2;
-    constexpr uint32_t B_BYTES = BN * BK * 2;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-    const int total_kb = (p.K + BK - 1) / BK;
-    int kb0 = 0, num_kb = total_kb;
-    if (TN) {
-        kb0 = blockIdx.z * p.kb_per_split;
-        num_kb = min(p.kb_per_split, total_kb - kb0);
-    }
+    const int BN = p.BN;
     const int stages = p.stages;
+    const uint32_t b_bytes = (uint32_t)BN * BK * 2;
+    const uint32_t stage_bytes = A_BYTES + b_bytes;
+    uint8_t* slabs = smem + (size_t)stages * stage_bytes;          // [8 warps][nbuf][out (+ preact)]
+    const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+        if (p.has_preact) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmP)) : "memory");
     }
-    if (warp == 1) {
-        if (lane == 0) {
-            for (int i = 0; i < stages; ++i) {
-                mbar_init(&full_bar[i], 1);
-                mbar_init(&empty_bar[i], 1);
-            }
-            mbar_init(&tmem_full_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
         }
-        __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "r"(TMEM_COLS)
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -212,37 +210,47 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ CUten
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (num_kb > 0) {
-        if (warp == 0) {
-            if (lane == 0) {
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int s = kb % stages;
-                    const uint32_t ph = (kb / stages) & 1;
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord<TN>(p, t);
+                for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                    uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], stage_bytes);
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
-                    const int kc = (kb0 + kb) * BK;
+                    const int kc = (tc.kb0 + kb) * BK;
                     if (!TN) {
-                        tma_load_2d(sa, &tmA, kc, m_tile * BM, &full_bar[s]);
-                        tma_load_2d(sb, &tmB, kc, n_tile * BN, &full_bar[s]);
+                        tma_load_2d(sa, &tmA, kc, tc.m_tile * BM, &full_bar[s]);
+                        tma_load_2d(sb, &tmB, kc, tc.n_tile * BN, &full_bar[s]);
                     } else {
-#pragma unroll
-                        for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m_tile * BM + c * 64, kc, &full_bar[s]);
-#pragma unroll
-                        for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n_tile * BN + c * 64, kc, &full_bar[s]);
+                        for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, tc.m_tile * BM + c * 64, kc, &full_bar[s]);
+                        for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, tc.n_tile * BN + c * 64, kc, &full_bar[s]);
                     }
                 }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc(BM, BN, TN);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int s = kb % stages;
-                    const uint32_t ph = (kb / stages) & 1;
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BM, BN, TN);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+                const TileCoord tc = tile_coord<TN>(p, t);
+                const int as = lt & 1;
+                mbar_wait(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
+                for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
@@ -254,57 +262,166 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ CUten
                             ad = make_desc(sa + k * 2048, 8192, 1024);
                             bd = make_desc(sb + k * 2048, 8192, 1024);
                         }
-                        tc_mma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_bf16(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[s]);
                 }
-                tc_commit(&tmem_full_bar);
-            }
-        } else {
-            mbar_wait(&tmem_full_bar, 0);
-            tc_fence_after();
-            const int q = warp & 3;
-            const int row_base = m_tile * BM + q * 32;
-            float* stg = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * EPI_WARP_BYTES);
-            const int n0 = n_tile * BN;
-            uint32_t dthr = 0, dkey = 0;
-            float dinv = 1.0f;
-            if (p.epi.dropout_p > 0.0f) {
-                dthr = drop_thresh(p.epi.dropout_p);
-                dinv = 1.0f / (1.0f - p.epi.dropout_p);
-                dkey = rng_key((const unsigned long long*)p.epi.rng, p.epi.drop_stream);
-            }
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 64) {
-                if (n0 + c0 >= p.N) break;
-                uint32_t v[64];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                tc_ld32(taddr, v);
-                tc_ld32(taddr + 32, v + 32);
-                tc_wait_ld();
-                float4* dst = reinterpret_cast<float4*>(stg + lane * EPI_ROW_F);
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                         __uint_as_float(v[4 * j + 3]));
-                __syncwarp();
-                const int col = n0 + c0 + 2 * lane;
-                if (col < p.N) {
-                    const int rmax = min(32, p.M - row_base);
-                    for (int r = 0; r < rmax; ++r) {
-                        float2 a = *reinterpret_cast<const float2*>(stg + r * EPI_ROW_F + 2 * lane);
-                        epilogue_pair(p, a.x, a.y, row_base + r, col, dkey, dthr, dinv);
-                    }
-                }
-                __syncwarp();
+                tc_commit(&tfull_bar[as]);
             }
         }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const MdvGemmEpi& e = p.epi;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;       // which alternate 32-column chunks it owns
+        uint8_t* myslab = slabs + (size_t)(warp - 4) * (p.nbuf * p.buf_bytes);
+        const int nbuf_mask = p.nbuf - 1;
+        uint32_t dthr = 0, dkey = 0;
+        float dinv = 1.0f;
+        if (e.dropout_p > 0.0f) {
+            dthr = drop_thresh(e.dropout_p);
+            dinv = 1.0f / (1.0f - e.dropout_p);
+            dkey = rng_key((const unsigned long long*)e.rng, e.drop_stream);
+        }
+        const bool out_bf16 = e.out_bf16 != 0;
+        int lt = 0, nstore = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const TileCoord tc = tile_coord<TN>(p, t);
+            const int as = lt & 1;
+            mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
+            tc_fence_after();
+            const int row0 = tc.m_tile * BM + q * 32;     // first row of this warp's slab
+            const int row = row0 + lane;
+            const bool row_ok = row < p.M;
+            const int n0 = tc.n_tile * BN;
+            float rs = 1.0f;
+            if (e.rowscale && row_ok) rs = __ldg(e.rowscale + row / e.rows_per_scale);
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                const int col0 = n0 + c0;
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + c0), v);
+                tc_wait_ld();
+                if (col0 >= p.N || row0 >= p.M) continue;   // tile overhang: nothing to store (warp-uniform)
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                const bool full_cols = col0 + 32 <= p.N;
+                if (e.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (full_cols) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+                            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (col0 + j + u < p.N) f[j + u] += __ldg(e.bias + col0 + j + u);
+                        }
+                    }
+                }
+                const int buf = nstore & nbuf_mask;
+                // make sure the TMA store that last read this buffer has drained (one bulk group per chunk)
+                if (lane == 0) {
+                    if (p.nbuf == 4) tma_wait_read<3>();
+                    else if (p.nbuf == 2) tma_wait_read<1>();
+                    else tma_wait_read<0>();
+                }
+                __syncwarp();
+                uint8_t* s_out = myslab + (size_t)buf * p.buf_bytes;
+                uint8_t* s_pre = s_out + p.out_slab;
+                if (p.has_preact) {
+                    // bf16 rows of 64 B, SWIZZLE_64B: 16B-chunk index ^= (row >> 1) & 3
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk = make_uint4(f2_to_bf2(f[8 * j], f[8 * j + 1]), f2_to_bf2(f[8 * j + 2], f[8 * j + 3]),
+                                              f2_to_bf2(f[8 * j + 4], f[8 * j + 5]), f2_to_bf2(f[8 * j + 6], f[8 * j + 7]));
+                        *reinterpret_cast<uint4*>(s_pre + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+                    }
+                }
+                if (e.act == MDV_ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                }
+                if (e.mul_gelu_grad && row_ok) {
+                    const bf16* up = (const bf16*)e.mul_gelu_grad + (size_t)row * e.ld_mul + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (full_cols) {
+                            const uint4 u4 = *reinterpret_cast<const uint4*>(up + j);
+                            const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 g = bf2_to_f2(uu[u]);
+                                f[j + 2 * u] *= gelu_erf_grad(g.x);
+                                f[j + 2 * u + 1] *= gelu_erf_grad(g.y);
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (col0 + j + u < p.N) f[j + u] *= gelu_erf_grad(__bfloat162float(up[j + u]));
+                        }
+                    }
+                }
+                if (dthr) {
+                    const unsigned long long base = (unsigned long long)row * (unsigned)p.N + (unsigned)col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] *= drop_scale(dkey, base + j, dthr, dinv);
+                }
+                if (e.rowscale) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] *= rs;
+                }
+                if (e.residual && row_ok) {
+                    const float* rp = e.residual + (size_t)row * e.ld_res + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (full_cols) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                            f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (col0 + j + u < p.N) f[j + u] += rp[j + u];
+                        }
+                    }
+                }
+                if (out_bf16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk = make_uint4(f2_to_bf2(f[8 * j], f[8 * j + 1]), f2_to_bf2(f[8 * j + 2], f[8 * j + 3]),
+                                              f2_to_bf2(f[8 * j + 4], f[8 * j + 5]), f2_to_bf2(f[8 * j + 6], f[8 * j + 7]));
+                        *reinterpret_cast<uint4*>(s_out + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+                    }
+                } else {
+                    // fp32 rows of 128 B, SWIZZLE_128B: 16B-chunk index ^= row & 7
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(s_out + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (TN) tma_reduce_add_2d(&tmC, s_out, col0, row0);
+                    else tma_store_2d(&tmC, s_out, col0, row0);
+                    if (p.has_preact) tma_store_2d(&tmP, s_pre, col0, row0);
+                    tma_commit();
+                }
+                ++nstore;
+            }
+            // all of this warp's tcgen05.ld for the tile have completed -> hand the accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (lane == 0) tma_wait_all();
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -326,59 +443,65 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch `ld` elements.
-int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+// 2-D tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch `ld` elements of `esize` bytes.
+int make_map(CUtensorMap* m, const void* ptr, int esize, long long inner, long long outer, long long ld, int box_inner,
+             int box_outer, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return MDV_ERR_DRIVER;
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return MDV_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esize) & 15)) return MDV_ERR_ARG;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? MDV_OK : MDV_ERR_DRIVER;
 }
 
-int g_force_bn = 0, g_force_stages = 0, g_force_split = 0;
+int g_force_bn = 0, g_force_stages = 0, g_force_split = 0, g_force_grid = 0;
 
-int pick_bn(int N, long long m_tiles) {
+// widest tile (multiple of `step`, <= 256) that wastes the least of N; ties go to the wider tile
+int pick_bn(int N, int step) {
     if (g_force_bn) return g_force_bn;
-    const int cands[3] = {256, 128, 64};
-    int best = 64;
+    int best = step;
     double best_w = 1e9;
-    for (int i = 0; i < 3; ++i) {
-        int bn = cands[i];
-        double w = (double)mdv_cdiv(N, bn) * bn / N;
-        if (w <= 1.07) {
-            best = bn;
-            best_w = w;
-            break;
-        }
+    for (int bn = 256; bn >= step; bn -= step) {
+        const double w = (double)mdv_cdiv(N, bn) * bn / N;
         if (w < best_w - 1e-9) {
             best_w = w;
             best = bn;
         }
     }
-    // small grids: prefer more, narrower tiles so that all 148 SMs get work
-    while (best > 64 && m_tiles * mdv_cdiv(N, best) < MDV_NUM_SMS) best >>= 1;
     return best;
 }
 
-template <int BN, bool TN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t st) {
-    const size_t stage_bytes = (size_t)(BM * BK * 2 + BN * BK * 2);
-    size_t smem = (size_t)p.stages * stage_bytes;
-    if (smem < (size_t)EPI_BYTES) smem = EPI_BYTES;
-    smem += 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+template <bool TN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, GemmParams& p, cudaStream_t st) {
+    const size_t stage_bytes = (size_t)A_BYTES + (size_t)p.BN * BK * 2;
+    p.out_slab = (TN || !p.epi.out_bf16) ? 4096 : 2048;
+    p.buf_bytes = p.out_slab + (p.has_preact ? 2048 : 0);
+    // short-K tiles are epilogue-bound (deep store buffering); long-K tiles are MMA-bound (spend smem on operand stages)
+    const int kbt = TN ? p.kb_per_split : mdv_cdiv(p.K, BK);
+    p.nbuf = kbt <= 2 ? 4 : (kbt <= 8 ? 2 : 1);
+    const size_t slab_bytes = (size_t)NUM_EPI_WARPS * p.nbuf * p.buf_bytes;
+    const size_t budget = 226 * 1024 - 1024 - 512;
+    int stages = (int)((budget - slab_bytes) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (g_force_stages && g_force_stages < stages) stages = g_force_stages;
+    if (stages < 2) return MDV_ERR_UNSUPPORTED;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + slab_bytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
         if (e != cudaSuccess) return (int)e;
-        configured = 200 * 1024;
+        configured = true;
     }
-    gemm_kernel<BN, TN><<<grid, 192, smem, st>>>(ta, tb, p);
+    const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
+    int grid = total_tiles < MDV_NUM_SMS ? total_tiles : MDV_NUM_SMS;
+    if (g_force_grid && g_force_grid < grid) grid = g_force_grid;
+    gemm_kernel<TN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, tp, p);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -395,70 +518,60 @@ extern "C" int mdv_gemm_tune(int force_bn, int force_stages, int force_split) {
 extern "C" int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi,
                            void* stream) {
     if (!A || !W || !epi || !epi->out || M <= 0 || N <= 0 || K <= 0) return MDV_ERR_ARG;
-    if ((N & 1) || (K & 7) || (epi->ldc & 1)) return MDV_ERR_ARG;
-    const long long m_tiles = mdv_cdiv(M, BM);
-    if (m_tiles > 65535) return MDV_ERR_UNSUPPORTED;
-    const int bn = pick_bn(N, m_tiles);
-    GemmParams p;
+    if ((N & 3) || (K & 7) || epi->accumulate) return MDV_ERR_ARG;
+    GemmParams p = {};
     p.M = M; p.N = N; p.K = K;
     p.epi = *epi;
-    p.atomic = 0;
-    p.kb_per_split = 0;
-    const int kb = mdv_cdiv(K, BK);
-    int stages = bn == 256 ? 4 : (bn == 128 ? 4 : 6);
-    if (g_force_stages) stages = g_force_stages;
-    p.stages = stages < kb ? stages : kb;
-    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, K, M, lda, BK, BM);
+    p.BN = pick_bn(N, 32);
+    p.n_tiles = mdv_cdiv(N, p.BN);
+    p.m_tiles = mdv_cdiv(M, BM);
+    p.splits = 1;
+    p.kb_per_split = mdv_cdiv(K, BK);
+    p.has_preact = epi->out_preact != nullptr;
+    CUtensorMap ta, tb, tc, tp;
+    int rc = make_map(&ta, A, 2, K, M, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, W, K, N, ldw, BK, bn);
+    rc = make_map(&tb, W, 2, K, N, ldw, BK, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    dim3 grid(mdv_cdiv(N, bn), (unsigned)m_tiles, 1);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (bn) {
-        case 256: return launch<256, false>(ta, tb, p, grid, st);
-        case 128: return launch<128, false>(ta, tb, p, grid, st);
-        default: return launch<64, false>(ta, tb, p, grid, st);
+    if (epi->out_bf16) rc = make_map(&tc, epi->out, 2, N, M, epi->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    else rc = make_map(&tc, epi->out, 4, N, M, epi->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    tp = tc;
+    if (p.has_preact) {
+        rc = make_map(&tp, epi->out_preact, 2, N, M, epi->ld_preact, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
     }
+    return launch<false>(ta, tb, tc, tp, p, (cudaStream_t)stream);
 }
 
 extern "C" int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc,
                            void* stream) {
     if (!A || !B || !C || R <= 0 || P <= 0 || Q <= 0) return MDV_ERR_ARG;
-    if ((P & 7) || (Q & 7) || (ldc & 1)) return MDV_ERR_ARG;
-    const long long p_tiles = mdv_cdiv(P, BM);
-    int bn = g_force_bn ? g_force_bn : (Q % 256 == 0 || Q > 512 ? 256 : (Q % 128 == 0 ? 128 : 64));
-    if (Q <= 64) bn = 64;
-    const int q_tiles = mdv_cdiv(Q, bn);
+    if ((P & 7) || (Q & 7) || (ldc & 3)) return MDV_ERR_ARG;
+    GemmParams p = {};
+    p.M = P; p.N = Q; p.K = R;
+    p.BN = pick_bn(Q, 64);
+    p.n_tiles = mdv_cdiv(Q, p.BN);
+    p.m_tiles = mdv_cdiv(P, BM);
     const int kb = mdv_cdiv(R, BK);
-    // split the reduction so that the grid is a few waves of the 148 SMs; >= 4 k-blocks per CTA
-    int want = (4 * MDV_NUM_SMS) / (int)(p_tiles * q_tiles);
+    // split the reduction so that every SM gets ~2 tiles; at least 4 k-blocks per split
+    int want = (2 * MDV_NUM_SMS) / (p.n_tiles * p.m_tiles);
     if (want < 1) want = 1;
     int splits = kb / 4 < want ? (kb / 4 > 0 ? kb / 4 : 1) : want;
     if (g_force_split) splits = g_force_split;
     if (splits > kb) splits = kb;
-    GemmParams p;
-    p.M = P; p.N = Q; p.K = R;
     p.kb_per_split = mdv_cdiv(kb, splits);
-    splits = mdv_cdiv(kb, p.kb_per_split);
+    p.splits = mdv_cdiv(kb, p.kb_per_split);
     MdvGemmEpi e = {};
     e.out = C;
     e.ldc = ldc;
     p.epi = e;
-    p.atomic = 1;
-    int stages = g_force_stages ? g_force_stages : 4;
-    p.stages = stages < p.kb_per_split ? stages : p.kb_per_split;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, P, R, lda, 64, BK);
+    CUtensorMap ta, tb, tc;
+    int rc = make_map(&ta, A, 2, P, R, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, B, Q, R, ldb, 64, BK);
+    rc = make_map(&tb, B, 2, Q, R, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    dim3 grid(q_tiles, (unsigned)p_tiles, splits);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (bn) {
-        case 256: return launch<256, true>(ta, tb, p, grid, st);
-        case 128: return launch<128, true>(ta, tb, p, grid, st);
-        default: return launch<64, true>(ta, tb, p, grid, st);
-    }
+    rc = make_map(&tc, C, 4, Q, P, ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return launch<true>(ta, tb, tc, tc, p, (cudaStream_t)stream);
 }

@@ -38,7 +38,8 @@ def run_tn(R, P, Q):
 
 ok = True
 for (M, N, K) in [(128, 64, 64), (256, 128, 64), (1000, 192, 64), (4096, 384, 128), (300, 320, 320), (2048, 512, 2112),
-                  (8, 512, 512), (8192, 1280, 320), (2048, 1024, 4608), (131072, 192, 64), (131072, 64, 512)]:
+                  (8, 512, 512), (8192, 1280, 320), (2048, 1024, 4608), (131072, 192, 64), (131072, 64, 512), (5000, 32, 64),
+                  (3000, 288, 64), (70000, 960, 320)]:
     for kw in [dict(), dict(res=True, out_bf16=False), dict(act=1, bias=True)]:
         try:
             rc, err = run_nt(M, N, K, **kw)
@@ -48,7 +49,7 @@ for (M, N, K) in [(128, 64, 64), (256, 128, 64), (1000, 192, 64), (4096, 384, 12
         ok &= flag == "OK "
         print(f"NT {flag} M={M} N={N} K={K} {kw} rc={rc} relerr={err:.3e}", flush=True)
 for (R, P, Q) in [(64, 128, 64), (256, 128, 64), (4096, 192, 64), (1000, 64, 64), (8192, 512, 64), (8192, 320, 1280),
-                  (131072, 192, 64), (16384, 512, 2112), (2048, 1024, 4608)]:
+                  (131072, 192, 64), (16384, 512, 2112), (2048, 1024, 4608), (9000, 32, 64), (9000, 64, 288), (8, 512, 4608)]:
     try:
         rc, err = run_tn(R, P, Q)
     except Exception as ex:
@@ -73,7 +74,7 @@ for (M, N, K) in [(131072, 192, 64), (131072, 512, 64), (131072, 64, 512), (3276
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     e = L.GemmEpi(); e.out = L.ptr(out); e.ldc = N; e.out_bf16 = 1
     st = L.stream()
-    for bn, stg in [(0, 0), (64, 0), (128, 0), (256, 0), (256, 2), (128, 2), (128, 3)]:
+    for bn, stg in [(0, 0), (64, 0), (128, 0), (256, 0), (256, 2), (128, 3)]:
         lib.mdv_gemm_tune(bn, stg, 0)
         t = bench(lambda: lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), st))
         fl = 2.0 * M * N * K / t / 1e9
