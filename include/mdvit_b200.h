@@ -122,7 +122,8 @@ int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, 
 int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,
                     float* gate, int B, int nd, int hid, int C, int heads, void* stream);
 int mdv_da_gate_bwd(const float* label, const float* w2, const float* hid_in, const float* gate, const float* dgate, float* dw1,
-                    float* db1, float* dw2, float* db2, int B, int nd, int hid, int C, int heads, void* stream);
+                    float* db1, float* dw2, float* db2, float* ws /* B*(C+hid) floats */, int B, int nd, int hid, int C, int heads,
+                    void* stream);
 
 /* ------------------------------------------------------------------ heads, reductions, casts */
 /* logits[m] = sum_c x[m,c] w[c] dropout2d(b,c) + bias  — the C->1 1x1 conv commuted in front of the final resize */

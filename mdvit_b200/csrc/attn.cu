@@ -9,19 +9,9 @@
 //     Y[n,v] = g[v] * ( s * sum_k Q[n,k] A[k,v] + Q[n,v] * (dwconv(V)[n,v] + b[v]) )                         (phase 2)
 // Everything here is HBM/L2-bound (matmul FLOPs < 1% of the model); the cross-token quantities are
 // (2+Ch)*C floats per image.  Backward follows SURVEY.md App. E.
-#include "../../include/mdvit_b200.h"
-#include "common.cuh"
+#include "attn_internal.cuh"
 
 namespace {
-
-struct CrpeW {               // three depthwise filters: heads [0,2) 3x3, [2,5) 5x5, [5,8) 7x7  (mdvit.py:423)
-    const float* w[3];
-    const float* b[3];
-};
-struct CrpeG {
-    float* w[3];
-    float* b[3];
-};
 
 __device__ __forceinline__ void crpe_lookup(int c, int Ch, int& grp, int& cl, int& win) {
     const int h = c / Ch;
@@ -140,126 +130,6 @@ __global__ void attn_normalize_kernel(float* __restrict__ A, float* __restrict__
     At[(bc - k + v) * Ch + k] = a;
 }
 
-// ---------------------------------------------------------------------------------- phase 2: output
-__device__ __forceinline__ float crpe_conv(const bf16* __restrict__ vbase /* V[b, 0, c] */, int ld, int y, int x, int H, int Wd,
-                                           const float* __restrict__ w, int win) {
-    const int r = win >> 1;
-    float e = 0.f;
-    for (int i = 0; i < win; ++i) {
-        const int yy = y + i - r;
-        if (yy < 0 || yy >= H) continue;
-        for (int j = 0; j < win; ++j) {
-            const int xx = x + j - r;
-            if (xx < 0 || xx >= Wd) continue;
-            e += __ldg(w + i * win + j) * __bfloat162float(vbase[(size_t)(yy * Wd + xx) * ld]);
-        }
-    }
-    return e;
-}
-
-template <int CH>
-__global__ void __launch_bounds__(256) attn_out_kernel(const bf16* __restrict__ qkv, const float* __restrict__ A,
-                                                        const float* __restrict__ gate, CrpeW cw, bf16* __restrict__ out, float scale,
-                                                        int B, int H, int Wd, int C) {
-    const int N = H * Wd;
-    const long long total = (long long)B * N * C;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % C);
-    const long long tok = idx / C;
-    const int n = (int)(tok % N), b = (int)(tok / N);
-    const int h = c / CH, v = c % CH;
-    const bf16* qrow = qkv + (size_t)tok * 3 * C + h * CH;
-    const float* Ab = A + ((size_t)b * C + h * CH) * CH + v;
-    float fa = 0.f;
-#pragma unroll
-    for (int k8 = 0; k8 < CH / 8; ++k8) {
-        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + k8 * 8);
-        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float2 f = bf2_to_f2(qq[u]);
-            fa += f.x * __ldg(Ab + (k8 * 8 + 2 * u) * CH) + f.y * __ldg(Ab + (k8 * 8 + 2 * u + 1) * CH);
-        }
-    }
-    int grp, cl, win;
-    crpe_lookup(c, CH, grp, cl, win);
-    const float e = crpe_conv(qkv + (size_t)b * N * 3 * C + 2 * C + c, 3 * C, n / Wd, n % Wd, H, Wd, cw.w[grp] + (size_t)cl * win * win, win) +
-                    __ldg(cw.b[grp] + cl);
-    const float q = __bfloat162float(qrow[v]);
-    const float g = gate ? __ldg(gate + (size_t)b * C + c) : 1.f;
-    out[idx] = __float2bfloat16_rn(g * (scale * fa + q * e));
-}
-
-// ---------------------------------------------------------------------------------- backward: per-channel reductions
-// dE[n,c] = g*dY*Q;  dWconv[c,tap] += dE[n,c] * V[n+tap,c];  dbconv[c] += dE;  dg[b,c] += dY[n,c]*y[n,c]/g[b,c]
-// block = 32 channels x 8 token lanes over a token chunk of one image; grid = (C/32, chunks, B).
-__global__ void __launch_bounds__(256) attn_bwd_chan_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
-                                                             const bf16* __restrict__ yout, const float* __restrict__ gate, CrpeG cg,
-                                                             float* __restrict__ dgate, int H, int Wd, int C, int Ch,
-                                                             int rows_per_block) {
-    extern __shared__ float sh[];  // [8][32][52]
-    const int N = H * Wd;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + tx, b = blockIdx.z;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(N, r0 + rows_per_block);
-    float acc[49];
-#pragma unroll
-    for (int t = 0; t < 49; ++t) acc[t] = 0.f;
-    float accb = 0.f, accg = 0.f;
-    int grp = 0, cl = 0, win = 3;
-    if (c < C) {
-        crpe_lookup(c, Ch, grp, cl, win);
-        const int r = win >> 1;
-        const float g = gate ? gate[(size_t)b * C + c] : 1.f;
-        const bf16* base = qkv + (size_t)b * N * 3 * C;
-        for (int n = r0 + ty; n < r1; n += 8) {
-            const float d = __bfloat162float(dy[((size_t)b * N + n) * C + c]);
-            const float q = __bfloat162float(base[(size_t)n * 3 * C + c]);
-            const float de = g * d * q;
-            accb += de;
-            if (gate) accg += d * __bfloat162float(yout[((size_t)b * N + n) * C + c]);
-            const int y = n / Wd, x = n % Wd;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const int yy = y + i - r;
-                if (i >= win || yy < 0 || yy >= H) continue;
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const int xx = x + j - r;
-                    if (j >= win || xx < 0 || xx >= Wd) continue;
-                    acc[i * 7 + j] += de * __bfloat162float(base[(size_t)(yy * Wd + xx) * 3 * C + 2 * C + c]);
-                }
-            }
-        }
-        if (gate) accg /= g;
-    }
-    float* mine = sh + ((size_t)ty * 32 + tx) * 52;
-#pragma unroll
-    for (int t = 0; t < 49; ++t) mine[t] = acc[t];
-    mine[49] = accb;
-    mine[50] = accg;
-    __syncthreads();
-    for (int o = threadIdx.x; o < 32 * 51; o += 256) {
-        const int cc = o / 51, t = o % 51;
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += sh[((size_t)k * 32 + cc) * 52 + t];
-        const int cgl = blockIdx.x * 32 + cc;
-        if (cgl >= C) continue;
-        int g2, cl2, win2;
-        crpe_lookup(cgl, Ch, g2, cl2, win2);
-        if (t < 49) {
-            const int i = t / 7, j = t % 7;
-            if (i < win2 && j < win2) atomicAdd(cg.w[g2] + (size_t)cl2 * win2 * win2 + i * win2 + j, s);
-        } else if (t == 49) {
-            atomicAdd(cg.b[g2] + cl2, s);
-        } else if (dgate) {
-            atomicAdd(dgate + (size_t)b * C + cgl, s);
-        }
-    }
-}
-
 // dAt[b,h,v,k] = dA[b,h,k,v];  r[b,c=(h,k)] = sum_v A[b,c,v] * dA[b,c,v]      one block per (b, head)
 __global__ void attn_bwd_mid_kernel(const float* __restrict__ A, const float* __restrict__ dA, float* __restrict__ dAt,
                                     float* __restrict__ rk, int C, int Ch) {
@@ -274,72 +144,6 @@ __global__ void attn_bwd_mid_kernel(const float* __restrict__ A, const float* __
         for (int v = 0; v < Ch; ++v) s += A[base + (size_t)k * Ch + v] * dA[base + (size_t)k * Ch + v];
         rk[(size_t)b * C + h * Ch + k] = s;
     }
-}
-
-// ---------------------------------------------------------------------------------- backward: dQ, dK, dV per (token, channel)
-template <int CH>
-__global__ void __launch_bounds__(256) attn_bwd_qkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
-                                                            const float* __restrict__ gate, const float* __restrict__ At,
-                                                            const float* __restrict__ dA, const float* __restrict__ dAt,
-                                                            const float* __restrict__ rk, const float* __restrict__ kmax,
-                                                            const float* __restrict__ zsum, CrpeW cw, bf16* __restrict__ dqkv,
-                                                            float scale, int B, int H, int Wd, int C) {
-    const int N = H * Wd;
-    const long long total = (long long)B * N * C;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % C);
-    const long long tok = idx / C;
-    const int n = (int)(tok % N), b = (int)(tok / N);
-    const int h = c / CH, v = c % CH;          // this thread's channel plays k for dQ/dK and v for dV
-    const size_t bc0 = (size_t)b * C + h * CH;
-    const bf16* row = qkv + (size_t)tok * 3 * C;
-    const bf16* dyrow = dy + (size_t)tok * C + h * CH;
-    const float* gb = gate ? gate + bc0 : nullptr;
-    // sums over the head dimension
-    float sq = 0.f;   // sum_v' dF[v'] * A[k=v][v']      -> dQ
-    float sv = 0.f;   // sum_k  S[n,k] * dA[k][v]        -> dV
-    float sk = 0.f;   // sum_v' V[n,v'] * dA[k=v][v']    -> dK
-    const float* Atb = At + bc0 * CH + v;     // At[v'][k=v] = A[k][v'] : stride CH over v', lanes contiguous in k
-    const float* dAb = dA + bc0 * CH + v;     // dA[k][v]               : stride CH over k,  lanes contiguous in v
-    const float* dAtb = dAt + bc0 * CH + v;   // dAt[v'][k=v] = dA[k][v']
-#pragma unroll 4
-    for (int j = 0; j < CH; ++j) {
-        const float dF = (gb ? __ldg(gb + j) : 1.f) * __bfloat162float(dyrow[j]);
-        sq += dF * __ldg(Atb + (size_t)j * CH);
-        const float S = __expf(__bfloat162float(row[C + h * CH + j]) - __ldg(kmax + bc0 + j)) / __ldg(zsum + bc0 + j);
-        sv += S * __ldg(dAb + (size_t)j * CH);
-        sk += __bfloat162float(row[2 * C + h * CH + j]) * __ldg(dAtb + (size_t)j * CH);
-    }
-    int grp, cl, win;
-    crpe_lookup(c, CH, grp, cl, win);
-    const float* w = cw.w[grp] + (size_t)cl * win * win;
-    const int y = n / Wd, x = n % Wd, r = win >> 1;
-    const bf16* imgb = qkv + (size_t)b * N * 3 * C;
-    const bf16* dyb = dy + (size_t)b * N * C;
-    const float g = gb ? __ldg(gb + v) : 1.f;
-    // E[n,c] (forward conv of V) and the transposed conv of dE
-    float e = __ldg(cw.b[grp] + cl), tconv = 0.f;
-    for (int i = 0; i < win; ++i) {
-        for (int j = 0; j < win; ++j) {
-            const float wt = __ldg(w + i * win + j);
-            const int yy = y + i - r, xx = x + j - r;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < Wd) e += wt * __bfloat162float(imgb[(size_t)(yy * Wd + xx) * 3 * C + 2 * C + c]);
-            const int y2 = y - i + r, x2 = x - j + r;   // token n' with n' + (i-r, j-r) == n
-            if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < Wd) {
-                const size_t n2 = (size_t)(y2 * Wd + x2);
-                tconv += wt * g * __bfloat162float(dyb[n2 * C + c]) * __bfloat162float(imgb[n2 * 3 * C + c]);
-            }
-        }
-    }
-    const float dFc = g * __bfloat162float(dyrow[v]);
-    const float Sc = __expf(__bfloat162float(row[C + c]) - __ldg(kmax + bc0 + v)) / __ldg(zsum + bc0 + v);
-    const float dk = Sc * (sk - __ldg(rk + bc0 + v));
-    const float dv = sv + tconv;
-    bf16* drow = dqkv + (size_t)tok * 3 * C;
-    drow[c] = __float2bfloat16_rn(scale * sq + dFc * e);
-    drow[C + c] = __float2bfloat16_rn(dk);
-    drow[2 * C + c] = __float2bfloat16_rn(dv);
 }
 
 // ---------------------------------------------------------------------------------- DA gate
@@ -377,36 +181,58 @@ __global__ void da_gate_fwd_kernel(const float* __restrict__ label, const float*
     }
 }
 
-// dz = g * (dg - sum_h g*dg);  dW2 += dz hid^T; db2 += dz; dhid = W2^T dz * (hid>0); dW1 += dhid label^T; db1 += dhid
-__global__ void da_gate_bwd_kernel(const float* __restrict__ label, const float* __restrict__ w2, const float* __restrict__ hid_in,
-                                   const float* __restrict__ gate, const float* __restrict__ dgate, float* __restrict__ dw1,
-                                   float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2, int nd, int hid, int C,
-                                   int heads) {
-    extern __shared__ float s[];   // dz[C] + hid[hid]
+// DA gate backward, step 1 (one block per sample): dz = g * (dg - sum_h g*dg);  dhid = W2^T dz * (hid > 0)
+__global__ void da_gate_bwd1_kernel(const float* __restrict__ w2, const float* __restrict__ hid_in, const float* __restrict__ gate,
+                                    const float* __restrict__ dgate, float* __restrict__ dz_out, float* __restrict__ dhid_out, int hid,
+                                    int C, int heads) {
+    extern __shared__ float s[];   // dz[C]
     float* dz = s;
-    float* sh = s + C;
     const int b = blockIdx.x;
     const int Ch = C / heads;
-    for (int j = threadIdx.x; j < hid; j += blockDim.x) sh[j] = hid_in[(size_t)b * hid + j];
     for (int v = threadIdx.x; v < Ch; v += blockDim.x) {
         float dot = 0.f;
         for (int h = 0; h < heads; ++h) dot += gate[(size_t)b * C + h * Ch + v] * dgate[(size_t)b * C + h * Ch + v];
         for (int h = 0; h < heads; ++h) {
             const size_t i = (size_t)b * C + h * Ch + v;
-            dz[h * Ch + v] = gate[i] * (dgate[i] - dot);
+            const float d = gate[i] * (dgate[i] - dot);
+            dz[h * Ch + v] = d;
+            dz_out[i] = d;
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(db2 + c, dz[c]);
-        for (int j = 0; j < hid; ++j) atomicAdd(dw2 + (size_t)c * hid + j, dz[c] * sh[j]);
-    }
     for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-        if (sh[j] <= 0.f) continue;
         float a = 0.f;
-        for (int c = 0; c < C; ++c) a += w2[(size_t)c * hid + j] * dz[c];
-        atomicAdd(db1 + j, a);
-        for (int d = 0; d < nd; ++d) atomicAdd(dw1 + j * nd + d, a * label[b * nd + d]);
+        if (hid_in[(size_t)b * hid + j] > 0.f)
+            for (int c = 0; c < C; ++c) a += __ldg(w2 + (size_t)c * hid + j) * dz[c];
+        dhid_out[(size_t)b * hid + j] = a;
+    }
+}
+// step 2: dW2[c,j] += sum_b dz[b,c] hid[b,j]; db2[c] += sum_b dz[b,c]; dW1[j,d] += sum_b dhid[b,j] label[b,d]; db1[j] += sum_b dhid[b,j]
+__global__ void da_gate_bwd2_kernel(const float* __restrict__ label, const float* __restrict__ hid_in, const float* __restrict__ dz,
+                                    const float* __restrict__ dhid, float* __restrict__ dw1, float* __restrict__ db1,
+                                    float* __restrict__ dw2, float* __restrict__ db2, int B, int nd, int hid, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n2 = C * hid;
+    if (i < n2) {
+        const int c = i / hid, j = i % hid;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += dz[(size_t)b * C + c] * hid_in[(size_t)b * hid + j];
+        dw2[i] += a;
+    } else if (i < n2 + C) {
+        const int c = i - n2;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += dz[(size_t)b * C + c];
+        db2[c] += a;
+    } else if (i < n2 + C + hid * nd) {
+        const int k = i - n2 - C, j = k / nd, d = k % nd;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += dhid[(size_t)b * hid + j] * label[b * nd + d];
+        dw1[k] += a;
+    } else if (i < n2 + C + hid * nd + hid) {
+        const int j = i - n2 - C - hid * nd;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += dhid[(size_t)b * hid + j];
+        db1[j] += a;
     }
 }
 
@@ -465,18 +291,7 @@ extern "C" int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float
     MDV_CHECK_LAUNCH();
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
     const float scale = 1.0f / sqrtf((float)Ch);
-    const long long total = (long long)B * N * C;
-    const int blocks = mdv_cdiv(total, 256);
-    bf16* out = (bf16*)out_bf16;
-    switch (Ch) {
-        case 8: attn_out_kernel<8><<<blocks, 256, 0, st>>>(qkv, A, gate, cw, out, scale, B, H, W, C); break;
-        case 16: attn_out_kernel<16><<<blocks, 256, 0, st>>>(qkv, A, gate, cw, out, scale, B, H, W, C); break;
-        case 40: attn_out_kernel<40><<<blocks, 256, 0, st>>>(qkv, A, gate, cw, out, scale, B, H, W, C); break;
-        case 64: attn_out_kernel<64><<<blocks, 256, 0, st>>>(qkv, A, gate, cw, out, scale, B, H, W, C); break;
-        default: return MDV_ERR_UNSUPPORTED;
-    }
-    MDV_CHECK_LAUNCH();
-    return MDV_OK;
+    return attn_tile_fwd(qkv, A, gate, cw, (bf16*)out_bf16, scale, B, H, W, C, Ch, st);
 }
 
 // ws: fp32 scratch of B*C*(2*Ch+1) floats.  dqkv bf16 [B,N,3C] is overwritten; crpe grads, dgate accumulate (+=).
@@ -505,33 +320,10 @@ extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const voi
     if (rc) return rc;
     attn_bwd_mid_kernel<<<dim3(heads, B), 256, 0, st>>>(A, dA, dAt, rk, C, Ch);
     MDV_CHECK_LAUNCH();
-    {
-        static bool attr_set = false;
-        const int smem = 8 * 32 * 52 * (int)sizeof(float);
-        if (!attr_set) {
-            e = cudaFuncSetAttribute(attn_bwd_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return (int)e;
-            attr_set = true;
-        }
-        int rpb = mdv_cdiv((long long)N * B * (C / 32), 6 * MDV_NUM_SMS);
-        if (rpb < 64) rpb = 64;
-        CrpeG cg = {{dcrpe_w3, dcrpe_w5, dcrpe_w7}, {dcrpe_b3, dcrpe_b5, dcrpe_b7}};
-        attn_bwd_chan_kernel<<<dim3(C / 32, mdv_cdiv(N, rpb), B), 256, smem, st>>>(qkv, dy, (const bf16*)y_bf16, gate, cg, dgate, H, W, C, Ch, rpb);
-        MDV_CHECK_LAUNCH();
-    }
+    CrpeG cg = {{dcrpe_w3, dcrpe_w5, dcrpe_w7}, {dcrpe_b3, dcrpe_b5, dcrpe_b7}};
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
-    const long long total = (long long)B * N * C;
-    const int blocks = mdv_cdiv(total, 256);
-    bf16* dqkv = (bf16*)dqkv_bf16;
-    switch (Ch) {
-        case 8: attn_bwd_qkv_kernel<8><<<blocks, 256, 0, st>>>(qkv, dy, gate, At, dA, dAt, rk, kmax, zsum, cw, dqkv, scale, B, H, W, C); break;
-        case 16: attn_bwd_qkv_kernel<16><<<blocks, 256, 0, st>>>(qkv, dy, gate, At, dA, dAt, rk, kmax, zsum, cw, dqkv, scale, B, H, W, C); break;
-        case 40: attn_bwd_qkv_kernel<40><<<blocks, 256, 0, st>>>(qkv, dy, gate, At, dA, dAt, rk, kmax, zsum, cw, dqkv, scale, B, H, W, C); break;
-        case 64: attn_bwd_qkv_kernel<64><<<blocks, 256, 0, st>>>(qkv, dy, gate, At, dA, dAt, rk, kmax, zsum, cw, dqkv, scale, B, H, W, C); break;
-        default: return MDV_ERR_UNSUPPORTED;
-    }
-    MDV_CHECK_LAUNCH();
-    return MDV_OK;
+    return attn_tile_bwd(qkv, dy, (const bf16*)y_bf16, gate, A, At, dA, dAt, rk, kmax, zsum, cw, cg, (bf16*)dqkv_bf16, dgate, scale, B, H, W,
+                         C, Ch, st);
 }
 
 extern "C" int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,
@@ -542,10 +334,18 @@ extern "C" int mdv_da_gate_fwd(const float* label, const float* w1, const float*
     return MDV_OK;
 }
 
+// ws: B*(C+hid) floats of scratch.  Gradients accumulate (+=).
 extern "C" int mdv_da_gate_bwd(const float* label, const float* w2, const float* hid_in, const float* gate, const float* dgate,
-                               float* dw1, float* db1, float* dw2, float* db2, int B, int nd, int hid, int C, int heads, void* stream) {
-    if (!label || !w2 || !hid_in || !gate || !dgate) return MDV_ERR_ARG;
-    da_gate_bwd_kernel<<<B, 128, (hid + C) * sizeof(float), (cudaStream_t)stream>>>(label, w2, hid_in, gate, dgate, dw1, db1, dw2, db2, nd, hid, C, heads);
+                               float* dw1, float* db1, float* dw2, float* db2, float* ws, int B, int nd, int hid, int C, int heads,
+                               void* stream) {
+    if (!label || !w2 || !hid_in || !gate || !dgate || !ws || !dw1 || !db1 || !dw2 || !db2) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dz = ws;
+    float* dhid = ws + (size_t)B * C;
+    da_gate_bwd1_kernel<<<B, 128, C * sizeof(float), st>>>(w2, hid_in, gate, dgate, dz, dhid, hid, C, heads);
+    MDV_CHECK_LAUNCH();
+    const int total = C * hid + C + hid * nd + hid;
+    da_gate_bwd2_kernel<<<mdv_cdiv(total, 256), 256, 0, st>>>(label, hid_in, dz, dhid, dw1, db1, dw2, db2, B, nd, hid, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

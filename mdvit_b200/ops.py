@@ -4,8 +4,9 @@ tape; all arithmetic runs in libmdvit_b200.so.  Activations are token-major fp32
 
 Every Function tolerates being back-propagated twice over one graph (multi_train_MDViT.py:201,207 call backward
 with retain_graph=True and then again): saved tensors are never written in backward, all backward scratch is
-freshly allocated, and parameter gradients are returned (autograd does the accumulation and honours the
-requires_grad flips on `domain_layer` between the two passes).
+freshly allocated, and parameter gradients are accumulated into `.grad` in place when it already exists (see
+gtarget) or returned for autograd to install; the requires_grad flips on `domain_layer` between the two passes are
+honoured at backward time.
 """
 import ctypes
 import itertools
@@ -130,15 +131,14 @@ def layernorm_fwd(x, w, b, M, C, eps=1e-6):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, w, dres, M, C, *, masked=False, rowscale=None, rows_per_scale=1, drop_p=0.0, drop_stream=0):
+def layernorm_bwd(dy, x, mean, rstd, w, dres, M, C, dg, db, *, masked=False, rowscale=None, rows_per_scale=1, drop_p=0.0,
+                  drop_stream=0):
     dx = torch.empty((M, C), dtype=F32, device=x.device)
     dxm = torch.empty((M, C), dtype=BF16, device=x.device) if masked else None
-    dg = torch.zeros(C, dtype=F32, device=x.device)
-    db = torch.zeros(C, dtype=F32, device=x.device)
     check(L.lib().mdv_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(w), ptr(dres), ptr(dx), ptr(dxm), ptr(rowscale),
                                     rows_per_scale, ctypes.c_float(drop_p), ptr(rng_tensor(x.device)) if drop_p > 0 else None,
                                     drop_stream, ptr(dg), ptr(db), M, C, L.stream()), "mdv_layernorm_bwd")
-    return dx, dxm, dg, db
+    return dx, dxm
 
 
 def dwconv3(x, w, bias, B, Hi, Wi, Ho, Wo, C, stride, *, out_bf16=False, transposed=False, residual=False):
@@ -148,11 +148,8 @@ def dwconv3(x, w, bias, B, Hi, Wi, Ho, Wo, C, stride, *, out_bf16=False, transpo
     return out
 
 
-def dwconv3_wgrad(dy, x, w, bias, B, Hi, Wi, Ho, Wo, C, stride):
-    dw = torch.zeros_like(w)
-    db = torch.zeros_like(bias) if bias is not None else None
+def dwconv3_wgrad(dy, x, dw, db, B, Hi, Wi, Ho, Wo, C, stride):
     check(L.lib().mdv_dwconv3_wgrad(ptr(dy), ptr(x), ptr(dw), ptr(db), B, Hi, Wi, Ho, Wo, C, stride, L.stream()), "mdv_dwconv3_wgrad")
-    return dw, db
 
 
 class BNState:
@@ -176,14 +173,15 @@ def bn_forward(z, M, C, weight, bias, running_mean, running_var, nbt, training, 
 
 
 def bn_backward(dy, z, mean, rstd, weight, bias, act, M, C, dz_bf16=True):
+    """Returns dz and the values to return from backward for (gamma, beta)."""
     dev = z.device
     ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
     dz = torch.empty((M, C), dtype=BF16 if dz_bf16 else F32, device=dev)
-    dg = torch.zeros(C, dtype=F32, device=dev)
-    db = torch.zeros(C, dtype=F32, device=dev)
+    dg, rg = gtarget(weight)
+    db, rb = gtarget(bias)
     check(L.lib().mdv_bn_act_bwd(ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), act, ptr(dz), int(dz_bf16), ptr(dg),
                                  ptr(db), M, C, ptr(ws), L.stream()), "mdv_bn_act_bwd")
-    return dz, dg, db
+    return dz, rg, rb
 
 
 def upsample_fwd(x, out, B, Hi, Wi, Ho, Wo, C, ld_in=None, ld_out=None):
@@ -201,6 +199,25 @@ def upsample_bwd(dout, B, Hi, Wi, Ho, Wo, C, ld_out=None):
 
 def _contig(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+def gtarget(p, shape=None):
+    """Where a parameter gradient is accumulated.  Returns (buffer, value_to_return_from_backward).
+
+    All parameter-gradient kernels ACCUMULATE (+=).  If the parameter already owns a contiguous fp32 .grad (the fused
+    trainer's flat buffer, or a second backward pass) the kernels add straight into it and backward returns None for it;
+    otherwise a zero buffer is returned for autograd to install.  A parameter whose requires_grad was switched off after
+    the forward (multi_train_MDViT.py:198-200 freezes `domain_layer`) gets a scratch buffer and nothing is returned."""
+    if p is None:
+        return None, None
+    if not p.requires_grad:      # frozen after the forward: compute into scratch, hand nothing to autograd
+        z = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return (z if shape is None else z.view(shape)), None
+    g = p.grad
+    if g is not None and g.dtype == F32 and g.is_contiguous() and g.device == p.device and g.data_ptr() % 16 == 0:
+        return (g if shape is None else g.view(shape)), None
+    z = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return (z if shape is None else z.view(shape)), z
 
 
 def _dev_ctx(t):
@@ -258,63 +275,67 @@ class BlockFn(torch.autograd.Function):
             x3 = torch.empty((B, N, C), dtype=F32, device=dev)
             gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2, drop_p=p_drop,
                     drop_stream=sid[2], rowscale=dp2, rows_per_scale=N)
-        ctx.save_for_backward(x, label, cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, qkv_w, proj_w, da_w1, da_w2, n2w, fc1_w,
-                              fc2_w, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2)
+        ctx.save_for_backward(x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2)
+        ctx.params = (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2,
+                      n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         ctx.meta = (B, N, C, H, W, hidden, p_drop, sid)
         return x3
 
     @staticmethod
     def backward(ctx, dx3):
-        (x, label, cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, qkv_w, proj_w, da_w1, da_w2, n2w, fc1_w, fc2_w, x1, mean1, rstd1,
-         ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2) = ctx.saved_tensors
+        (x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2) = ctx.saved_tensors
+        (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2, n2w, n2b,
+         fc1_w, fc1_b, fc2_w, fc2_b) = ctx.params
         B, N, C, H, W, hidden, p_drop, sid = ctx.meta
         M, dev = B * N, x.device
         lib = L.lib()
         dx3 = _contig(dx3.float())
-        z = lambda *s: torch.zeros(s, dtype=F32, device=dev)  # noqa: E731
+        T = {n: gtarget(p) for n, p in zip(("cpe_w", "cpe_b", "c3w", "c3b", "c5w", "c5b", "c7w", "c7b", "n1w", "n1b", "qkv_w", "qkv_b",
+                                            "proj_w", "proj_b", "da_w1", "da_b1", "da_w2", "da_b2", "n2w", "n2b", "fc1_w", "fc1_b",
+                                            "fc2_w", "fc2_b"), ctx.params)}
+        G = {k: v[0] for k, v in T.items()}
         with _dev_ctx(x):
             # ---- MLP
             d_fc2 = cast_bf16(dx3, M, C, rowscale=dp2, rows_per_scale=N, drop_p=p_drop, drop_stream=sid[2])
-            g_fc2_w = gemm_tn(d_fc2, hact, M, C, hidden, z(C, hidden))
-            g_fc2_b = colsum(d_fc2, M, C, z(C))
+            gemm_tn(d_fc2, hact, M, C, hidden, G["fc2_w"])
+            colsum(d_fc2, M, C, G["fc2_b"])
             du = torch.empty((M, hidden), dtype=BF16, device=dev)
             gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, drop_p=p_drop, drop_stream=sid[1])
-            g_fc1_w = gemm_tn(du, ln2, M, hidden, C, z(hidden, C))
-            g_fc1_b = colsum(du, M, hidden, z(hidden))
+            gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
+            colsum(du, M, hidden, G["fc1_b"])
             dln2 = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(du, prep_weight(fc1_w, 1, hidden, C), M, C, hidden, dln2)
-            dx2, d_proj, g_n2w, g_n2b = layernorm_bwd(dln2, x2, mean2, rstd2, n2w, dx3, M, C, masked=True, rowscale=dp1,
-                                                      rows_per_scale=N, drop_p=p_drop, drop_stream=sid[0])
+            dx2, d_proj = layernorm_bwd(dln2, x2, mean2, rstd2, n2w, dx3, M, C, G["n2w"], G["n2b"], masked=True, rowscale=dp1,
+                                        rows_per_scale=N, drop_p=p_drop, drop_stream=sid[0])
             # ---- attention
-            g_proj_w = gemm_tn(d_proj, y, M, C, C, z(C, C))
-            g_proj_b = colsum(d_proj, M, C, z(C))
+            gemm_tn(d_proj, y, M, C, C, G["proj_w"])
+            colsum(d_proj, M, C, G["proj_b"])
             dy = torch.empty((M, C), dtype=BF16, device=dev)
             gemm_nt(d_proj, prep_weight(proj_w, 1, C, C), M, C, C, dy)
             dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
             Ch = C // HEADS
-            dgate = z(B, C) if gate is not None else None
-            g3w, g3b, g5w, g5b, g7w, g7b = (torch.zeros_like(t) for t in (c3w, c3b, c5w, c5b, c7w, c7b))
+            da_live = gate is not None and da_w1.requires_grad and da_w2.requires_grad
+            dgate = torch.zeros((B, C), dtype=F32, device=dev) if gate is not None else None
             ws = torch.empty(B * C * (2 * Ch + 1), dtype=F32, device=dev)
             check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
-                                   ptr(stats), ptr(dqkv), ptr(dgate), ptr(g3w), ptr(g3b), ptr(g5w), ptr(g5b), ptr(g7w), ptr(g7b),
-                                   ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")
-            g_da = (None, None, None, None)
-            if gate is not None:
+                                   ptr(stats), ptr(dqkv), ptr(dgate), ptr(G["c3w"]), ptr(G["c3b"]), ptr(G["c5w"]), ptr(G["c5b"]),
+                                   ptr(G["c7w"]), ptr(G["c7b"]), ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")
+            if da_live:
                 nd, hd = da_w1.shape[1], da_w1.shape[0]
-                g_da = (z(hd, nd), z(hd), z(C, hd), z(C))
-                check(lib.mdv_da_gate_bwd(ptr(label), ptr(da_w2), ptr(hid), ptr(gate), ptr(dgate), ptr(g_da[0]), ptr(g_da[1]),
-                                          ptr(g_da[2]), ptr(g_da[3]), B, nd, hd, C, HEADS, L.stream()), "mdv_da_gate_bwd")
-            g_qkv_w = gemm_tn(dqkv, ln1, M, 3 * C, C, z(3 * C, C))
-            g_qkv_b = colsum(dqkv, M, 3 * C, z(3 * C))
+                ws2 = torch.empty(B * (C + hd), dtype=F32, device=dev)
+                check(lib.mdv_da_gate_bwd(ptr(label), ptr(da_w2), ptr(hid), ptr(gate), ptr(dgate), ptr(G["da_w1"]), ptr(G["da_b1"]),
+                                          ptr(G["da_w2"]), ptr(G["da_b2"]), ptr(ws2), B, nd, hd, C, HEADS, L.stream()), "mdv_da_gate_bwd")
+            gemm_tn(dqkv, ln1, M, 3 * C, C, G["qkv_w"])
+            colsum(dqkv, M, 3 * C, G["qkv_b"])
             dln1 = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(dqkv, prep_weight(qkv_w, 1, 3 * C, C), M, C, 3 * C, dln1)
-            dx1, _, g_n1w, g_n1b = layernorm_bwd(dln1, x1, mean1, rstd1, n1w, dx2, M, C)
+            dx1, _ = layernorm_bwd(dln1, x1, mean1, rstd1, n1w, dx2, M, C, G["n1w"], G["n1b"])
             # ---- ConvPosEnc
             dx = dwconv3(dx1, cpe_w, None, B, H, W, H, W, C, 1, transposed=True, residual=True)
-            g_cpe_w, g_cpe_b = dwconv3_wgrad(dx1, x, cpe_w, cpe_b, B, H, W, H, W, C, 1)
-        return (dx.view(B, N, C), None, g_cpe_w, g_cpe_b, g3w, g3b, g5w, g5b, g7w, g7b, g_n1w, g_n1b, g_qkv_w, g_qkv_b, g_proj_w,
-                g_proj_b, g_da[0], g_da[1], g_da[2], g_da[3], g_n2w, g_n2b, g_fc1_w, g_fc1_b, g_fc2_w, g_fc2_b, None, None, None, None,
-                None)
+            dwconv3_wgrad(dx1, x, G["cpe_w"], G["cpe_b"], B, H, W, H, W, C, 1)
+        R = [T[n][1] for n in ("cpe_w", "cpe_b", "c3w", "c3b", "c5w", "c5b", "c7w", "c7b", "n1w", "n1b", "qkv_w", "qkv_b", "proj_w",
+                               "proj_b", "da_w1", "da_b1", "da_w2", "da_b2", "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+        return (dx.view(B, N, C), None, *R, None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------- conv pieces
@@ -345,13 +366,15 @@ class StemFn(torch.autograd.Function):
             z1 = torch.empty((M1, 64), dtype=F32, device=dev)
             gemm_nt(col1, prep_weight(w1, 2, 64, 288, cin=32), M1, 64, 288, z1)
             y, mean1, rstd1 = bn_forward(z1, M1, 64, g1, b1, rm1, rv1, nb1, training, ACT_HSWISH, False)
-        ctx.save_for_backward(w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
+        ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
+        ctx.params = (w0, g0, b0, w1, g1, b1)
         ctx.meta = (B, H1, W1, H2, W2, training)
         return y.view(B, H2 * W2, 64)
 
     @staticmethod
     def backward(ctx, dy):
-        w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        w0, g0, b0, w1, g1, b1 = ctx.params
         B, H1, W1, H2, W2, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
@@ -359,19 +382,19 @@ class StemFn(torch.autograd.Function):
         lib = L.lib()
         dy = _contig(dy.float())
         with _dev_ctx(dy):
-            dz1, dg1, db1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_HSWISH, M1, 64)
+            dz1, rg1, rb1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_HSWISH, M1, 64)
             gw1p = gemm_tn(dz1, col1, M1, 64, 288, torch.zeros((64, 288), dtype=F32, device=dev))
-            gw1 = torch.zeros_like(w1)
+            gw1, rw1 = gtarget(w1)
             check(lib.mdv_unperm_conv_grad(ptr(gw1p), 288, ptr(gw1), 64, 32, L.stream()), "mdv_unperm_conv_grad")
             dcol1 = torch.empty((M1, 288), dtype=F32, device=dev)
             gemm_nt(dz1, prep_weight(w1, 3, 64, 288, cin=32), M1, 288, 64, dcol1)
             da0 = torch.empty((M0, 32), dtype=F32, device=dev)
             check(lib.mdv_col2im3(ptr(dcol1), ptr(da0), B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_col2im3")
-            dz0, dg0, db0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_HSWISH, M0, 32)
+            dz0, rg0, rb0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_HSWISH, M0, 32)
             gw0p = gemm_tn(dz0, col0, M0, 32, 64, torch.zeros((32, 64), dtype=F32, device=dev))
-            gw0 = torch.zeros_like(w0)
+            gw0, rw0 = gtarget(w0)
             check(lib.mdv_unperm_conv_grad(ptr(gw0p), 64, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
-        return None, gw0, dg0, db0, gw1, dg1, db1, None, None
+        return None, rw0, rg0, rb0, rw1, rg1, rb1, None, None
 
 
 class PatchEmbedFn(torch.autograd.Function):
@@ -390,26 +413,30 @@ class PatchEmbedFn(torch.autograd.Function):
             z = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(t, prep_weight(pw_w, 0, C, Cin), M, C, Cin, z)
             y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
-        ctx.save_for_backward(x, dw_w, pw_w, g, b, t, z, mean, rstd)
+        ctx.save_for_backward(x, t, z, mean, rstd)
+        ctx.params = (dw_w, pw_w, g, b)
         ctx.meta = (B, Hi, Wi, Ho, Wo, Cin, C, stride, training)
         return y.view(B, Ho * Wo, C)
 
     @staticmethod
     def backward(ctx, dy):
-        x, dw_w, pw_w, g, b, t, z, mean, rstd = ctx.saved_tensors
+        x, t, z, mean, rstd = ctx.saved_tensors
+        dw_w, pw_w, g, b = ctx.params
         B, Hi, Wi, Ho, Wo, Cin, C, stride, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
         M, dev = B * Ho * Wo, dy.device
         dy = _contig(dy.float())
         with _dev_ctx(dy):
-            dz, dg, db = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
-            g_pw = gemm_tn(dz, t, M, C, Cin, torch.zeros((C, Cin), dtype=F32, device=dev)).view_as(pw_w)
+            dz, rg, rb = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
+            g_pw, r_pw = gtarget(pw_w, (C, Cin))
+            gemm_tn(dz, t, M, C, Cin, g_pw)
             dt = torch.empty((M, Cin), dtype=F32, device=dev)
             gemm_nt(dz, prep_weight(pw_w, 1, C, Cin), M, Cin, C, dt)
             dx = dwconv3(dt, dw_w, None, B, Ho, Wo, Hi, Wi, Cin, stride, transposed=True)
-            g_dw, _ = dwconv3_wgrad(dt, x, dw_w, None, B, Hi, Wi, Ho, Wo, Cin, stride)
-        return dx.view(B, Hi * Wi, Cin), g_dw, g_pw, dg, db, None, None, None, None, None
+            g_dw, r_dw = gtarget(dw_w)
+            dwconv3_wgrad(dt, x, g_dw, None, B, Hi, Wi, Ho, Wo, Cin, stride)
+        return dx.view(B, Hi * Wi, Cin), r_dw, r_pw, rg, rb, None, None, None, None, None
 
 
 class BridgeFn(torch.autograd.Function):
@@ -434,13 +461,15 @@ class BridgeFn(torch.autograd.Function):
             z1 = torch.empty((M, C1), dtype=F32, device=dev)
             gemm_nt(col1, prep_weight(w1, 2, C1, 9 * C0, cin=C0), M, C1, 9 * C0, z1, bias=c1)
             y, mean1, rstd1 = bn_forward(z1, M, C1, g1, b1, rm1, rv1, nb1, training, ACT_RELU, False)
-        ctx.save_for_backward(w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
+        ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
+        ctx.params = (w0, c0, g0, b0, w1, c1, g1, b1)
         ctx.meta = (B, H, W, C, C0, C1, training)
         return y.view(B, H * W, C1)
 
     @staticmethod
     def backward(ctx, dy):
-        w0, g0, b0, w1, g1, b1, col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        w0, c0, g0, b0, w1, c1, g1, b1 = ctx.params
         B, H, W, C, C0, C1, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
@@ -448,23 +477,24 @@ class BridgeFn(torch.autograd.Function):
         lib = L.lib()
         dy = _contig(dy.float())
 
-        def conv_bwd(dz, col, w, Cout, Cin):
+        def conv_bwd(dz, col, w, cb, Cout, Cin):
             gwp = gemm_tn(dz, col, M, Cout, 9 * Cin, torch.zeros((Cout, 9 * Cin), dtype=F32, device=dev))
-            gw = torch.zeros_like(w)
+            gw, rw = gtarget(w)
             check(lib.mdv_unperm_conv_grad(ptr(gwp), 9 * Cin, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
-            gb = colsum(dz, M, Cout, torch.zeros(Cout, dtype=F32, device=dev))
+            gb, rb = gtarget(cb)
+            colsum(dz, M, Cout, gb)
             dcol = torch.empty((M, 9 * Cin), dtype=F32, device=dev)
             gemm_nt(dz, prep_weight(w, 3, Cout, 9 * Cin, cin=Cin), M, 9 * Cin, Cout, dcol)
             dx = torch.empty((M, Cin), dtype=F32, device=dev)
             check(lib.mdv_col2im3(ptr(dcol), ptr(dx), B, H, W, H, W, Cin, 1, 9 * Cin, L.stream()), "mdv_col2im3")
-            return gw, gb, dx
+            return rw, rb, dx
 
         with _dev_ctx(dy):
-            dz1, dg1, db1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_RELU, M, C1)
-            gw1, gc1, da0 = conv_bwd(dz1, col1, w1, C1, C0)
-            dz0, dg0, db0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_RELU, M, C0)
-            gw0, gc0, dx = conv_bwd(dz0, col0, w0, C0, C)
-        return dx.view(B, H * W, C), gw0, gc0, dg0, db0, gw1, gc1, dg1, db1, None, None, None, None
+            dz1, rg1, rb1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_RELU, M, C1)
+            rw1, rc1, da0 = conv_bwd(dz1, col1, w1, c1, C1, C0)
+            dz0, rg0, rb0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_RELU, M, C0)
+            rw0, rc0, dx = conv_bwd(dz0, col0, w0, c0, C0, C)
+        return dx.view(B, H * W, C), rw0, rc0, rg0, rb0, rw1, rc1, rg1, rb1, None, None, None, None
 
 
 class DecoderConvFn(torch.autograd.Function):
@@ -489,13 +519,15 @@ class DecoderConvFn(torch.autograd.Function):
             z = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(gc, prep_weight(pw_w, 0, C, C), M, C, C, z)
             y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
-        ctx.save_for_backward(skip, cb_w, dw_w, pw_w, g, b, a, up, gc, z, mean, rstd)
+        ctx.save_for_backward(skip, a, up, gc, z, mean, rstd)
+        ctx.params = (cb_w, cb_b, dw_w, pw_w, g, b)
         ctx.meta = (B, h, w, H, W, Cin, C, training)
         return y.view(B, H * W, C)
 
     @staticmethod
     def backward(ctx, dy):
-        skip, cb_w, dw_w, pw_w, g, b, a, up, gc, z, mean, rstd = ctx.saved_tensors
+        skip, a, up, gc, z, mean, rstd = ctx.saved_tensors
+        cb_w, cb_b, dw_w, pw_w, g, b = ctx.params
         B, h, w, H, W, Cin, C, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
@@ -503,22 +535,25 @@ class DecoderConvFn(torch.autograd.Function):
         lib = L.lib()
         dy = _contig(dy.float())
         with _dev_ctx(dy):
-            dz, dg, db = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
-            g_pw = gemm_tn(dz, gc, M, C, C, torch.zeros((C, C), dtype=F32, device=dev)).view_as(pw_w)
+            dz, rg, rb = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
+            g_pw, r_pw = gtarget(pw_w, (C, C))
+            gemm_tn(dz, gc, M, C, C, g_pw)
             dgc = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(dz, prep_weight(pw_w, 1, C, C), M, C, C, dgc)
             dskip = torch.empty((M, C), dtype=F32, device=dev)
             dup = torch.empty((M, C), dtype=F32, device=dev)
-            g_dw = torch.zeros_like(dw_w)
+            g_dw, r_dw = gtarget(dw_w)
             check(lib.mdv_gconv2_bwd(ptr(dgc), ptr(skip), ptr(up), ptr(dw_w), ptr(dskip), ptr(dup), ptr(g_dw), B, H, W, C, L.stream()),
                   "mdv_gconv2_bwd")
             dt = upsample_bwd(dup, B, h, w, H, W, C)
             dtb = cast_bf16(dt, m, C)
-            g_cb = gemm_tn(dtb, a, m, C, Cin, torch.zeros((C, Cin), dtype=F32, device=dev)).view_as(cb_w)
-            g_cbb = colsum(dt, m, C, torch.zeros(C, dtype=F32, device=dev))
+            g_cb, r_cb = gtarget(cb_w, (C, Cin))
+            gemm_tn(dtb, a, m, C, Cin, g_cb)
+            g_cbb, r_cbb = gtarget(cb_b)
+            colsum(dt, m, C, g_cbb)
             dinp = torch.empty((m, Cin), dtype=F32, device=dev)
             gemm_nt(dtb, prep_weight(cb_w, 1, C, Cin), m, Cin, C, dinp)
-        return (dinp.view(B, h * w, Cin), dskip.view(B, H * W, C), g_cb, g_cbb, g_dw, g_pw, dg, db, None, None, None, None, None, None)
+        return (dinp.view(B, h * w, Cin), dskip.view(B, H * W, C), r_cb, r_cbb, r_dw, r_pw, rg, rb, None, None, None, None, None, None)
 
 
 class HeadFn(torch.autograd.Function):
@@ -535,13 +570,15 @@ class HeadFn(torch.autograd.Function):
             check(lib.mdv_rowdot_fwd(ptr(x), 0, ptr(w), ptr(b), ptr(lo), B * H * W, C, H * W, ctypes.c_float(0.0), None, 0, L.stream()),
                   "mdv_rowdot_fwd")
             out = upsample_fwd(lo, torch.empty((B, 1, Ho, Wo), dtype=F32, device=dev), B, H, W, Ho, Wo, 1)
-        ctx.save_for_backward(x, w)
+        ctx.save_for_backward(x)
+        ctx.params = (w, b)
         ctx.meta = (B, C, H, W, Ho, Wo)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w = ctx.saved_tensors
+        (x,) = ctx.saved_tensors
+        w, b = ctx.params
         B, C, H, W, Ho, Wo = ctx.meta
         dev = x.device
         lib = L.lib()
@@ -549,11 +586,11 @@ class HeadFn(torch.autograd.Function):
         with _dev_ctx(x):
             dlo = upsample_bwd(dout, B, H, W, Ho, Wo, 1)
             dx = torch.empty((B, H * W, C), dtype=F32, device=dev)
-            dw = torch.zeros_like(w)
-            db = torch.zeros(1, dtype=F32, device=dev)
+            dw, rw = gtarget(w)
+            db, rb = gtarget(b)
             check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(x), 0, ptr(w), ptr(dx), ptr(dw), ptr(db), B * H * W, C, H * W, ctypes.c_float(0.0),
                                      None, 0, L.stream()), "mdv_rowdot_bwd")
-        return dx, dw, db, None, None, None, None
+        return dx, rw, rb, None, None, None, None
 
 
 class AuxFn(torch.autograd.Function):
@@ -599,13 +636,15 @@ class AuxFn(torch.autograd.Function):
             check(lib.mdv_rowdot_fwd(ptr(a5), 1, ptr(ow), ptr(ob), ptr(lo), M0, hc, H * W, ctypes.c_float(p2),
                                      ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_fwd")
             out = upsample_fwd(lo, torch.empty((B, 1, Ho, Wo), dtype=F32, device=dev), B, H, W, Ho, Wo, 1)
-        ctx.save_for_backward(l1w, l2w, l3w, l4w, fw, g, b, ow, cat, z, mean, rstd, a5, *acts)
+        ctx.save_for_backward(cat, z, mean, rstd, a5, *acts)
+        ctx.params = (l1w, l1b, l2w, l2b, l3w, l3b, l4w, l4b, fw, fb, g, b, ow, ob)
         ctx.meta = (B, sizes, Ho, Wo, hc, K, C5, p2, sid, training, [t.shape[2] for t in xs])
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        l1w, l2w, l3w, l4w, fw, g, b, ow, cat, z, mean, rstd, a5, *acts = ctx.saved_tensors
+        cat, z, mean, rstd, a5, *acts = ctx.saved_tensors
+        l1w, l1b, l2w, l2b, l3w, l3b, l4w, l4b, fw, fb, g, b, ow, ob = ctx.params
         B, sizes, Ho, Wo, hc, K, C5, p2, sid, training, Cs = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
@@ -613,39 +652,45 @@ class AuxFn(torch.autograd.Function):
         M0, dev = B * H * W, dout.device
         lib = L.lib()
         dout = _contig(dout.float())
-        lw = (l1w, l2w, l3w, l4w)
-        zf = lambda *s: torch.zeros(s, dtype=F32, device=dev)  # noqa: E731
+        lw, lb = (l1w, l2w, l3w, l4w), (l1b, l2b, l3b, l4b)
         with _dev_ctx(dout):
             dlo = upsample_bwd(dout, B, H, W, Ho, Wo, 1)
             da5 = torch.empty((M0, hc), dtype=F32, device=dev)
-            g_ow, g_ob = torch.zeros_like(ow), zf(1)
+            g_ow, r_ow = gtarget(ow)
+            g_ob, r_ob = gtarget(ob)
             check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(a5), 1, ptr(ow), ptr(da5), ptr(g_ow), ptr(g_ob), M0, hc, H * W, ctypes.c_float(p2),
                                      ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_bwd")
-            dz, dg, db = bn_backward(da5, z, mean, rstd, g, b, ACT_RELU, M0, hc)
-            g_fw = gemm_tn(dz, cat, M0, hc, K, zf(hc, K)).view_as(fw)
-            g_fb = colsum(dz, M0, hc, zf(hc))
+            dz, rg, rb = bn_backward(da5, z, mean, rstd, g, b, ACT_RELU, M0, hc)
+            g_fw, r_fw = gtarget(fw, (hc, K))
+            gemm_tn(dz, cat, M0, hc, K, g_fw)
+            g_fb, r_fb = gtarget(fb)
+            colsum(dz, M0, hc, g_fb)
             dcat = torch.empty((M0, K), dtype=BF16, device=dev)
             gemm_nt(dz, prep_weight(fw, 1, hc, K), M0, K, hc, dcat)
-            gx, gw, gb = [], [], []
+            gx, rw, rbs = [], [], []
             for i in range(4):
                 Hi, Wi = sizes[i]
                 Mi, Ci = B * Hi * Wi, Cs[i]
                 sl = dcat[:, i * hc:]
+                g_b, r_b = gtarget(lb[i])
                 if i == 0:
                     dtb, lda = sl, K
-                    gb.append(colsum(sl, Mi, hc, zf(hc), ld=K))
+                    colsum(sl, Mi, hc, g_b, ld=K)
                 else:
                     dt = upsample_bwd(sl, B, Hi, Wi, H, W, hc, ld_out=K)
                     dtb, lda = cast_bf16(dt, Mi, hc), hc
-                    gb.append(colsum(dt, Mi, hc, zf(hc)))
-                gw.append(gemm_tn(dtb, acts[i], Mi, hc, Ci, zf(hc, Ci), lda=lda).view_as(lw[i]))
+                    colsum(dt, Mi, hc, g_b)
+                g_w, r_w = gtarget(lw[i], (hc, Ci))
+                gemm_tn(dtb, acts[i], Mi, hc, Ci, g_w, lda=lda)
                 dxi = torch.empty((B, Hi * Wi, Ci), dtype=F32, device=dev)
                 gemm_nt(dtb, prep_weight(lw[i], 1, hc, Ci), Mi, Ci, hc, dxi, lda=lda)
                 gx.append(dxi)
+                rw.append(r_w)
+                rbs.append(r_b)
             dx5 = torch.empty((B, H * W, C5), dtype=F32, device=dev)
             check(lib.mdv_add_f32(ptr(dcat[:, 4 * hc:]), 1, K, ptr(dx5), C5, M0, C5, 0, L.stream()), "mdv_add_f32")
-        return (gx[0], gx[1], gx[2], gx[3], dx5, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2], gw[3], gb[3], g_fw, g_fb, dg, db, g_ow, g_ob,
-                None, None, None, None, None, None)
+        return (gx[0], gx[1], gx[2], gx[3], dx5, rw[0], rbs[0], rw[1], rbs[1], rw[2], rbs[2], rw[3], rbs[3], r_fw, r_fb, rg, rb, r_ow,
+                r_ob, None, None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------- fused losses
