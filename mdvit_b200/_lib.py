@@ -38,7 +38,64 @@ def lib():
         for name, (restype, argtypes) in header_signatures().items():
             fn = getattr(_lib, name)          # AttributeError here == header/library mismatch
             fn.restype, fn.argtypes = restype, argtypes
+        if _PROFILE:
+            _lib = _ProfiledLib(_lib)
     return _lib
+
+
+_PROFILE = bool(int(os.environ.get("MDV_PROFILE", "0")))
+PROFILE_LOG = []     # (key, start_event, end_event) per C-ABI call when MDV_PROFILE=1 (development aid only)
+
+
+class _ProfiledLib:
+    """Wraps every mdv_* entry point with CUDA events on the launching stream; keys calls by their integer arguments."""
+
+    def __init__(self, raw):
+        self._raw = raw
+
+    def __getattr__(self, name):
+        fn = getattr(self._raw, name)
+        if not name.startswith("mdv_") or name in ("mdv_launch_count", "mdv_version", "mdv_attn_stats_floats", "mdv_gemm_tune"):
+            return fn
+
+        def wrapped(*args):
+            key = [name]
+            for a in args:
+                if isinstance(a, bool) or isinstance(a, int):
+                    key.append(int(a))
+                elif isinstance(a, float):
+                    key.append(round(a, 4))
+                elif hasattr(a, "_obj") and isinstance(a._obj, GemmEpi):
+                    e = a._obj
+                    key.append("epi[" + ",".join(k for k, v in (("bias", e.bias), ("res", e.residual), ("mulg", e.mul_gelu_grad),
+                                                                ("pre", e.out_preact), ("rs", e.rowscale), ("drop", e.dropout_p > 0),
+                                                                ("bf16" if e.out_bf16 else "f32", True), ("act%d" % e.act, e.act)) if v) + "]")
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            t.record()
+            PROFILE_LOG.append((tuple(key), s, t))
+            return rc
+
+        setattr(self, name, wrapped)
+        return wrapped
+
+
+def profile_report(top=80, clear=True):
+    """Aggregate PROFILE_LOG by (entry point, integer args): total ms, calls, average us."""
+    torch.cuda.synchronize()
+    agg = {}
+    for key, s, t in PROFILE_LOG:
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += s.elapsed_time(t)
+    if clear:
+        PROFILE_LOG.clear()
+    tot = sum(v[1] for v in agg.values())
+    lines = [f"total {tot:.2f} ms over {sum(v[0] for v in agg.values())} calls"]
+    for key, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        lines.append(f"{ms:9.3f} ms {100 * ms / tot:5.1f}%  n={n:4d}  avg {ms / n * 1e3:8.1f} us  {key[0]} {' '.join(map(str, key[1:]))}")
+    return "\n".join(lines)
 
 
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mdvit_b200.h")

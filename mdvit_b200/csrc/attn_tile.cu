@@ -363,6 +363,7 @@ __device__ __forceinline__ void wgrad_tile_body(const bf16* __restrict__ qkv, co
         const float de = gt * d * q;
         accb += de;
         if (gate) accg += d * __bfloat162float(yout[((size_t)b * N + n) * C + c]);
+        if (!cg.w[0]) continue;   // dgate-only pass (weight gradients off)
         const bf16* spv = sV + (py * g.PW + px) * 32 + lane;
 #pragma unroll
         for (int i = 0; i < WIN; ++i)
@@ -386,6 +387,7 @@ __device__ __forceinline__ void wgrad_tile_body(const bf16* __restrict__ qkv, co
         const int grp = h < 2 ? 0 : (h < 5 ? 1 : 2);
         const int cl = cgl - (grp == 0 ? 0 : (grp == 1 ? 2 * CH : 5 * CH));
         const int wc = 3 + 2 * grp;
+        if (t <= WIN * WIN && !cg.w[0]) continue;
         if (t < WIN * WIN) {
             const int o2 = (WIN - wc) >> 1;
             const int ii = t / WIN - o2, jj = t % WIN - o2;
@@ -475,8 +477,10 @@ static int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const flo
     }
     attn_bwd_tile_kernel<CH><<<tile_grid(B, H, W, C), 256, 2 * HALO_BYTES, st>>>(qkv, dy, gate, A, dA, rk, kmax, zsum, cw, dqkv, scale, H, W, C);
     MDV_CHECK_LAUNCH();
-    attn_wgrad_tile_kernel<CH><<<tile_grid(B, H, W, C), 256, RED_BYTES, st>>>(qkv, dy, yout, gate, cg, dgate, H, W, C);
-    MDV_CHECK_LAUNCH();
+    if (cg.w[0] || dgate) {
+        attn_wgrad_tile_kernel<CH><<<tile_grid(B, H, W, C), 256, RED_BYTES, st>>>(qkv, dy, yout, gate, cg, dgate, H, W, C);
+        MDV_CHECK_LAUNCH();
+    }
     return MDV_OK;
 }
 

@@ -488,10 +488,11 @@ extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w
 
 extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float* up, const float* w, float* dskip, float* dup,
                               float* dw, int B, int H, int W, int C, void* stream) {
-    if (!dout || !skip || !up || !w || !dskip || !dup || !dw || (C & 3)) return MDV_ERR_ARG;
+    if (!dout || !skip || !up || !w || !dskip || !dup || (C & 3)) return MDV_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     gconv2_dgrad_kernel<<<grid_for((long long)B * H * W * (C / 2)), 256, 0, st>>>(dout, w, dskip, dup, B, H, W, C);
     MDV_CHECK_LAUNCH();
+    if (!dw) return MDV_OK;   // weight gradient not wanted in this pass
     const long long npix = (long long)B * H * W;
     const int cb = mdv_cdiv(C, 32);
     const int ppb = pix_per_block_for(npix, cb);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
             dx[(size_t)r * C + c] = d * wv * m;
             acc += d * ldf(x + (size_t)r * C + c) * m;
         }
-        atomicAdd(dw + c, acc);
+        if (dw) atomicAdd(dw + c, acc);
     }
     if (db && threadIdx.x == 0) {
         for (int r = r0; r < r1; ++r) dbacc += dlog[r];
@@ -322,7 +322,7 @@ extern "C" int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const f
 
 extern "C" int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, const float* w, float* dx, float* dw, float* db, int M,
                               int C, int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
-    if (!dlog || !x || !w || !dx || !dw || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
+    if (!dlog || !x || !w || !dx || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
     int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);
     if (rpb < 8) rpb = 8;
     const int blocks = mdv_cdiv(M, rpb);

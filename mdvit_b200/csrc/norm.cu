@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
             }
     }
     // column reductions across the block's warps, then one atomic per column per block
+    if (!dgamma) return;   // weight gradients switched off for this pass (block-uniform)
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i)
         if (i < nv) {

@@ -47,12 +47,12 @@ class DWCPatchEmbed(nn.Module):
         super().__init__()
         self.patch_conv = DWConv2d_BN(in_chans, embed_dim, patch_size, stride)
 
-    def forward(self, x, H, W):
+    def forward(self, x, H, W, after_stem=False):
         pc = self.patch_conv
         bn = pc.bn
         y = ops.PatchEmbedFn.apply(x, pc.dwconv.weight, pc.pwconv.weight, bn.weight, bn.bias,
                                    (bn.running_mean, bn.running_var, bn.num_batches_tracked), H, W, pc.stride,
-                                   self.training)
+                                   self.training, after_stem)
         s = pc.stride
         return y, (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
 
@@ -302,7 +302,7 @@ class _Trunk(nn.Module):
                               s1.bn.running_mean, s1.bn.running_var, s1.bn.num_batches_tracked), self.training)
         enc = []
         for idx in range(self.num_stages):
-            t, H, W = self.patch_embed_stages[idx](t, H, W)
+            t, H, W = self.patch_embed_stages[idx](t, H, W, after_stem=(idx == 0))
             t = self.mhsa_stages[idx](t, H, W, domain_label)
             enc.append((t, H, W))
         return enc

@@ -10,6 +10,7 @@ honoured at backward time.
 """
 import ctypes
 import itertools
+import weakref
 
 import torch
 
@@ -65,10 +66,10 @@ def bump_weight_epoch():
 
 def prep_weight(w, mode, rows, cols, ld=None, cin=0):
     """bf16 GEMM operand of fp32 parameter `w` (mode: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order)."""
-    key = (w.data_ptr(), w._version, mode, ld, WEIGHT_EPOCH)
+    key = (id(w), w.data_ptr(), w._version, mode, ld, WEIGHT_EPOCH)
     hit = _wcache.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is w:      # id()/data_ptr() are recycled once a model is freed: check liveness
+        return hit[1]
     R, Cc = rows, cols
     if mode == 0 or mode == 2:
         out_rows, out_ld = R, (ld or Cc)
@@ -78,7 +79,9 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
         need_zero = mode >= 2 and out_ld != (Cc if mode == 2 else R)
         dst = (torch.zeros if need_zero or mode >= 2 else torch.empty)((out_rows, out_ld), dtype=BF16, device=w.device)
         check(L.lib().mdv_prep_weight(ptr(w), ptr(dst), R, Cc, out_ld, mode, cin, L.stream()), "mdv_prep_weight")
-    _wcache[key] = dst
+    if len(_wcache) > 4096:
+        _wcache.clear()
+    _wcache[key] = (weakref.ref(w), dst)
     return dst
 
 
@@ -104,12 +107,16 @@ def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, resi
 
 
 def gemm_tn(A, B, R, P, Q, C, *, lda=None, ldb=None, ldc=None):
-    """C[P,Q] += A[R,P]^T B[R,Q]"""
+    """C[P,Q] += A[R,P]^T B[R,Q]   (skipped when C is None: weight gradients are off in this backward mode)"""
+    if C is None:
+        return None
     check(L.lib().mdv_gemm_tn(ptr(A), lda or P, ptr(B), ldb or Q, R, P, Q, ptr(C), ldc or Q, L.stream()), "mdv_gemm_tn")
     return C
 
 
 def colsum(x, M, C, out, ld=None):
+    if out is None:
+        return None
     check(L.lib().mdv_colsum(ptr(x), int(x.dtype == BF16), ld or C, ptr(out), M, C, L.stream()), "mdv_colsum")
     return out
 
@@ -149,6 +156,8 @@ def dwconv3(x, w, bias, B, Hi, Wi, Ho, Wo, C, stride, *, out_bf16=False, transpo
 
 
 def dwconv3_wgrad(dy, x, dw, db, B, Hi, Wi, Ho, Wo, C, stride):
+    if dw is None:
+        return
     check(L.lib().mdv_dwconv3_wgrad(ptr(dy), ptr(x), ptr(dw), ptr(db), B, Hi, Wi, Ho, Wo, C, stride, L.stream()), "mdv_dwconv3_wgrad")
 
 
@@ -201,14 +210,38 @@ def _contig(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def gtarget(p, shape=None):
+# Backward mode.  "all": every gradient (the default; what autograd expects).  "da_only": only the activation-gradient
+# chain and the domain-adapter (`domain_layer`) gradients are computed — all other weight-gradient kernels are skipped.
+# MKDTrainer's single-sweep schedule uses it for the aux-loss pass (train_step.py); see DESIGN.md "MKD backward schedule".
+_BWD_MODE = "all"
+
+
+class backward_mode:
+    def __init__(self, mode):
+        assert mode in ("all", "da_only")
+        self.mode = mode
+
+    def __enter__(self):
+        global _BWD_MODE
+        self.prev, _BWD_MODE = _BWD_MODE, self.mode
+
+    def __exit__(self, *exc):
+        global _BWD_MODE
+        _BWD_MODE = self.prev
+
+
+def wgrad_on():
+    return _BWD_MODE == "all"
+
+
+def gtarget(p, shape=None, da=False):
     """Where a parameter gradient is accumulated.  Returns (buffer, value_to_return_from_backward).
 
     All parameter-gradient kernels ACCUMULATE (+=).  If the parameter already owns a contiguous fp32 .grad (the fused
     trainer's flat buffer, or a second backward pass) the kernels add straight into it and backward returns None for it;
     otherwise a zero buffer is returned for autograd to install.  A parameter whose requires_grad was switched off after
     the forward (multi_train_MDViT.py:198-200 freezes `domain_layer`) gets a scratch buffer and nothing is returned."""
-    if p is None:
+    if p is None or (_BWD_MODE == "da_only" and not da):
         return None, None
     if not p.requires_grad:      # frozen after the forward: compute into scratch, hand nothing to autograd
         z = torch.zeros_like(p, memory_format=torch.contiguous_format)
@@ -290,7 +323,7 @@ class BlockFn(torch.autograd.Function):
         M, dev = B * N, x.device
         lib = L.lib()
         dx3 = _contig(dx3.float())
-        T = {n: gtarget(p) for n, p in zip(("cpe_w", "cpe_b", "c3w", "c3b", "c5w", "c5b", "c7w", "c7b", "n1w", "n1b", "qkv_w", "qkv_b",
+        T = {n: gtarget(p, da=n.startswith("da_")) for n, p in zip(("cpe_w", "cpe_b", "c3w", "c3b", "c5w", "c5b", "c7w", "c7b", "n1w", "n1b", "qkv_w", "qkv_b",
                                             "proj_w", "proj_b", "da_w1", "da_b1", "da_w2", "da_b2", "n2w", "n2b", "fc1_w", "fc1_b",
                                             "fc2_w", "fc2_b"), ctx.params)}
         G = {k: v[0] for k, v in T.items()}
@@ -369,10 +402,13 @@ class StemFn(torch.autograd.Function):
         ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
         ctx.params = (w0, g0, b0, w1, g1, b1)
         ctx.meta = (B, H1, W1, H2, W2, training)
+        ctx.set_materialize_grads(False)
         return y.view(B, H2 * W2, 64)
 
     @staticmethod
     def backward(ctx, dy):
+        if dy is None:       # the da_only pass stops at the first patch embedding
+            return (None,) * 9
         col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
         w0, g0, b0, w1, g1, b1 = ctx.params
         B, H1, W1, H2, W2, training = ctx.meta
@@ -383,17 +419,19 @@ class StemFn(torch.autograd.Function):
         dy = _contig(dy.float())
         with _dev_ctx(dy):
             dz1, rg1, rb1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_HSWISH, M1, 64)
-            gw1p = gemm_tn(dz1, col1, M1, 64, 288, torch.zeros((64, 288), dtype=F32, device=dev))
             gw1, rw1 = gtarget(w1)
-            check(lib.mdv_unperm_conv_grad(ptr(gw1p), 288, ptr(gw1), 64, 32, L.stream()), "mdv_unperm_conv_grad")
+            if gw1 is not None:
+                gw1p = gemm_tn(dz1, col1, M1, 64, 288, torch.zeros((64, 288), dtype=F32, device=dev))
+                check(lib.mdv_unperm_conv_grad(ptr(gw1p), 288, ptr(gw1), 64, 32, L.stream()), "mdv_unperm_conv_grad")
             dcol1 = torch.empty((M1, 288), dtype=F32, device=dev)
             gemm_nt(dz1, prep_weight(w1, 3, 64, 288, cin=32), M1, 288, 64, dcol1)
             da0 = torch.empty((M0, 32), dtype=F32, device=dev)
             check(lib.mdv_col2im3(ptr(dcol1), ptr(da0), B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_col2im3")
             dz0, rg0, rb0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_HSWISH, M0, 32)
-            gw0p = gemm_tn(dz0, col0, M0, 32, 64, torch.zeros((32, 64), dtype=F32, device=dev))
             gw0, rw0 = gtarget(w0)
-            check(lib.mdv_unperm_conv_grad(ptr(gw0p), 64, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
+            if gw0 is not None:
+                gw0p = gemm_tn(dz0, col0, M0, 32, 64, torch.zeros((32, 64), dtype=F32, device=dev))
+                check(lib.mdv_unperm_conv_grad(ptr(gw0p), 64, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
         return None, rw0, rg0, rb0, rw1, rg1, rb1, None, None
 
 
@@ -401,7 +439,7 @@ class PatchEmbedFn(torch.autograd.Function):
     """DWCPatchEmbed: depthwise 3x3 (stride s) -> 1x1 conv -> BN -> Hardswish, mdvit.py:114-123."""
 
     @staticmethod
-    def forward(ctx, x, dw_w, pw_w, g, b, bufs, Hi, Wi, stride, training):
+    def forward(ctx, x, dw_w, pw_w, g, b, bufs, Hi, Wi, stride, training, after_stem=False):
         B, _, Cin = x.shape
         C = pw_w.shape[0]
         Ho, Wo = (Hi + 2 - 3) // stride + 1, (Wi + 2 - 3) // stride + 1
@@ -416,6 +454,7 @@ class PatchEmbedFn(torch.autograd.Function):
         ctx.save_for_backward(x, t, z, mean, rstd)
         ctx.params = (dw_w, pw_w, g, b)
         ctx.meta = (B, Hi, Wi, Ho, Wo, Cin, C, stride, training)
+        ctx.after_stem = after_stem
         return y.view(B, Ho * Wo, C)
 
     @staticmethod
@@ -425,6 +464,9 @@ class PatchEmbedFn(torch.autograd.Function):
         B, Hi, Wi, Ho, Wo, Cin, C, stride, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        if ctx.after_stem and not wgrad_on():
+            # nothing upstream of the first patch embedding owns a domain adapter: the da_only pass stops here
+            return (None,) * 11
         M, dev = B * Ho * Wo, dy.device
         dy = _contig(dy.float())
         with _dev_ctx(dy):
@@ -436,7 +478,7 @@ class PatchEmbedFn(torch.autograd.Function):
             dx = dwconv3(dt, dw_w, None, B, Ho, Wo, Hi, Wi, Cin, stride, transposed=True)
             g_dw, r_dw = gtarget(dw_w)
             dwconv3_wgrad(dt, x, g_dw, None, B, Hi, Wi, Ho, Wo, Cin, stride)
-        return dx.view(B, Hi * Wi, Cin), r_dw, r_pw, rg, rb, None, None, None, None, None
+        return dx.view(B, Hi * Wi, Cin), r_dw, r_pw, rg, rb, None, None, None, None, None, None
 
 
 class BridgeFn(torch.autograd.Function):
@@ -478,9 +520,10 @@ class BridgeFn(torch.autograd.Function):
         dy = _contig(dy.float())
 
         def conv_bwd(dz, col, w, cb, Cout, Cin):
-            gwp = gemm_tn(dz, col, M, Cout, 9 * Cin, torch.zeros((Cout, 9 * Cin), dtype=F32, device=dev))
             gw, rw = gtarget(w)
-            check(lib.mdv_unperm_conv_grad(ptr(gwp), 9 * Cin, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
+            if gw is not None:
+                gwp = gemm_tn(dz, col, M, Cout, 9 * Cin, torch.zeros((Cout, 9 * Cin), dtype=F32, device=dev))
+                check(lib.mdv_unperm_conv_grad(ptr(gwp), 9 * Cin, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
             gb, rb = gtarget(cb)
             colsum(dz, M, Cout, gb)
             dcol = torch.empty((M, 9 * Cin), dtype=F32, device=dev)

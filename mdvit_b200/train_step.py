@@ -1,7 +1,15 @@
 """The MDViT training step (multi_train_MDViT.py:121-213) on the B200 kernels, single- or multi-GPU.
 
-One step = 4 domain forwards (each a single-domain mini-batch) -> fused BCE+Dice / MKD losses -> the reference's
-two-pass backward (aux loss with `domain_layer` frozen, then 0.5*kt + 0.5*seg) -> gradient all-reduce -> fused AdamW.
+One step = 4 domain forwards (each a single-domain mini-batch) -> fused BCE+Dice / MKD losses -> the MKD backward ->
+gradient all-reduce -> fused AdamW.
+
+MKD backward schedules (both produce the reference's gradients; tests compare them):
+  "reference"     multi_train_MDViT.py:195-207 verbatim: aux.backward(retain_graph) with `domain_layer` frozen, then
+                  (alpha*kt + (1-alpha)*seg).backward() — every weight gradient kernel runs twice.
+  "single_sweep"  gradients are linear in the loss cotangent, so  grad(non-DA) = d(aux + a*kt + (1-a)*seg)  and
+                  grad(DA) = d(aux + a*kt + (1-a)*seg) - d(aux).  Pass 1 back-propagates -aux in ops.backward_mode("da_only")
+                  (activation-gradient chain + DA gradients only, no other wgrad kernel), pass 2 back-propagates the total
+                  loss once with all weight gradients.  Same result, ~1 trunk wgrad sweep cheaper.
 
 Data parallelism (replaces nn.DataParallel, multi_train_MDViT.py:73-74): one process per GPU; every rank runs all four
 domain forwards on its own slice of each domain batch.  The 8 loss partial sums are all-reduced so BCE/Dice are those
@@ -25,7 +33,10 @@ def _align(n, a=4):
 
 class MKDTrainer:
     def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, process_group=None,
-                 num_domains=4, with_aux=True):
+                 num_domains=4, with_aux=True, schedule="single_sweep"):
+        if schedule not in ("single_sweep", "reference"):
+            raise ValueError("schedule must be 'single_sweep' or 'reference'")
+        self.schedule = schedule
         self.model = model
         self.alpha = alpha
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -85,13 +96,19 @@ class MKDTrainer:
     def backward(self, losses):
         """multi_train_MDViT.py:195-207: aux pass with DA frozen (retain_graph), then alpha*kt + (1-alpha)*seg."""
         seg, aux, kt = losses[:, 0].sum(), losses[:, 1].sum(), losses[:, 2].sum()
-        if self.with_aux:
+        if self.with_aux and self.schedule == "reference":
             for p in self.da_params:
                 p.requires_grad = False
             aux.backward(retain_graph=True)
             for p in self.da_params:
                 p.requires_grad = True
             (self.alpha * kt + (1.0 - self.alpha) * seg).backward()
+        elif self.with_aux:
+            main = self.alpha * kt + (1.0 - self.alpha) * seg
+            if self.da_params:
+                with ops.backward_mode("da_only"):
+                    (-aux).backward(retain_graph=True)
+            (aux + main).backward()
         else:
             seg.backward()
 

@@ -92,7 +92,7 @@ def main():
     bn_keys = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
     out["train64_bn_names"] = np.asarray(bn_keys)
     out["train64_bn_fp"] = fingerprint([(k, sd[k]) for k in bn_keys])
-    out["train64_bn/stem.0.bn.running_var"] = sd["stem.0.bn.running_var"].numpy()
+    out["train64_bn/stem.0.bn.running_var"] = sd["stem.0.bn.running_var"].clone().numpy()   # clone: the buffer is updated in place later
     opt.step()
     out["train64_param_fp_after_adamw"] = fingerprint(list(m.named_parameters()))
     # train-mode logits of domain 1 after the step (BN batch stats, updated weights)

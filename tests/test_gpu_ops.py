@@ -292,7 +292,12 @@ def test_fused_losses_match_reference_formulas(env):
     for a, b in zip(losses, ref):
         assert abs(a.item() - b.item()) < 2e-5 * max(1.0, abs(b.item()))
     coef = torch.tensor([0.5, 1.0, 0.5], device=dev)
-    (0.5 * ref[0] + ref[1] + 0.5 * ref[2]).backward()
+    # gradient reference: nn.BCELoss's own backward (the oracle's log().clamp() formula gives 0*inf = nan at saturated
+    # sigmoids, where PyTorch's BCELoss backward — and the reference trainer — give 0)
+    p, q = torch.sigmoid(out), torch.sigmoid(aux)
+    bce = torch.nn.BCELoss()
+    l_seg, l_aux, l_kt = bce(p, y) + O.dice_loss(p, y), bce(q, y) + O.dice_loss(q, y), O.dice_loss(q, p)
+    (0.5 * l_seg + l_aux + 0.5 * l_kt).backward()
     dout, daux = torch.empty(n, device=dev), torch.empty(n, device=dev)
     L.check(lib.mdv_loss_bwd(L.ptr(out), L.ptr(aux), L.ptr(y), L.ptr(sums), float(n), L.ptr(coef), L.ptr(dout), L.ptr(daux), n, L.stream()), "lb")
     assert rel(dout, out.grad) < 1e-4 and rel(daux, aux.grad) < 1e-4
