@@ -31,7 +31,7 @@ long long mdv_launch_count(void); /* kernels launched by this library so far (ho
 /* Epilogue applied to acc = A.W^T, in this order:
  *   v = acc + bias[n];  out_preact[m,n] = bf16(v);  v = act(v);  v *= gelu'(mul_gelu_grad[m,n]);
  *   v *= dropout_mask(rng, drop_stream, m*N+n)/(1-p);  v *= rowscale[m / rows_per_scale];
- *   v += residual[m,n];  out[m,n] (=|+=) v                                                   */
+ *   v += residual[m,n];  out[m,n] = v;  colsum[n] += sum_m v   (bias gradient of the producing layer) */
 typedef struct MdvGemmEpi {
     const float* bias;          /* [N] fp32 or NULL */
     const float* residual;      /* [M, ld_res] fp32 or NULL */
@@ -40,6 +40,7 @@ typedef struct MdvGemmEpi {
     void* out;                  /* [M, ldc] bf16 or fp32 */
     const float* rowscale;      /* [ceil(M / rows_per_scale)] fp32 or NULL (DropPath per-sample scale) */
     const void* rng;            /* device uint64[2] {seed, step}; may be NULL when dropout_p == 0 */
+    float* colsum;              /* [N] fp32 or NULL: column sums of the stored values are ADDED here (atomics) */
     int ld_res, ld_mul, ld_preact, ldc;
     int rows_per_scale;
     int out_bf16;               /* 1: out is bf16, 0: fp32 */
@@ -69,8 +70,8 @@ int mdv_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
  * dgamma/dbeta accumulate (+=). */
 int mdv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* dres, float* dx, void* dx_masked_bf16, const float* rowscale, int rows_per_scale,
-                      float drop_p, const void* rng, uint32_t drop_stream, float* dgamma, float* dbeta, int M, int C,
-                      void* stream);
+                      float drop_p, const void* rng, uint32_t drop_stream, float* dgamma, float* dbeta,
+                      float* dbias_masked /* [C] += column sums of dx_masked, or NULL */, int M, int C, void* stream);
 
 /* ------------------------------------------------------------------ BatchNorm2d (+act) on [M=B*H*W, C] (mpvit.py:119-122 ...) */
 /* training: batch mean / biased var -> mean,rstd; running stats updated with momentum (unbiased var) and
@@ -132,8 +133,9 @@ int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const float* bias,
 int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, const float* w, float* dx, float* dw, float* db, int M, int C,
                    int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream);
 int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, int C, void* stream);  /* out[c] += sum_m x[m,c] */
+/* out = bf16(in * rowscale[m / rows_per_scale] * dropout_mask(m*C + c)); colsum (optional, C <= 1024): [C] += column sums of out */
 int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
-                  int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, void* stream);
+                  int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* colsum, void* stream);
 int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate, void* stream);
 /* fp32 master weight -> bf16 GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2 */
 int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream);

@@ -147,64 +147,77 @@ __global__ void attn_bwd_mid_kernel(const float* __restrict__ A, const float* __
 }
 
 // ---------------------------------------------------------------------------------- DA gate
-// z = W2 relu(W1[:,dom] + b1) + b2  (one-hot input => a column lookup);  g[h,v] = softmax over heads of z[h*Ch+v].
-// One block per sample; label is the general [B, nd] fp32 vector so soft labels also work.
-__global__ void da_gate_fwd_kernel(const float* __restrict__ label, const float* __restrict__ w1, const float* __restrict__ b1,
-                                   const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ hid_out,
-                                   float* __restrict__ gate, int nd, int hid, int C, int heads) {
-    extern __shared__ float s[];   // hid + C
-    float* sh = s;
-    float* sz = s + hid;
-    const int b = blockIdx.x;
+// z = W2 relu(W1 label + b1) + b2  (mdvit.py:272-276; a one-hot label makes the first layer a column lookup);
+// g[h,v] = softmax over heads of z[h*Ch+v] (mdvit.py:301-303).  label is the general [B, nd] fp32 vector (soft labels work).
+// Kernel 1: one warp per (sample, output channel): the W2 row is read coalesced and warp-reduced.
+__global__ void __launch_bounds__(256) da_gate_z_kernel(const float* __restrict__ label, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ hid_out,
+                                                         float* __restrict__ z_out, int nd, int hid, int C) {
+    extern __shared__ float sh[];   // hid
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = threadIdx.x; j < hid; j += blockDim.x) {
         float a = b1[j];
         for (int d = 0; d < nd; ++d) a += w1[j * nd + d] * label[b * nd + d];
         a = fmaxf(a, 0.f);
         sh[j] = a;
-        hid_out[(size_t)b * hid + j] = a;
+        if (blockIdx.x == 0) hid_out[(size_t)b * hid + j] = a;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = b2[c];
-        const float* wr = w2 + (size_t)c * hid;
-        for (int j = 0; j < hid; ++j) a += wr[j] * sh[j];
-        sz[c] = a;
-    }
-    __syncthreads();
+    const int c = blockIdx.x * 8 + warp;
+    if (c >= C) return;
+    const float* wr = w2 + (size_t)c * hid;
+    float a = 0.f;
+    for (int j = lane; j < hid; j += 32) a += __ldg(wr + j) * sh[j];
+    a = warp_sum(a);
+    if (lane == 0) z_out[(size_t)b * C + c] = a + b2[c];
+}
+// Kernel 2: softmax over the heads, one thread per (sample, v); in place on the z buffer.
+__global__ void da_gate_softmax_kernel(float* __restrict__ gate, int B, int C, int heads) {
     const int Ch = C / heads;
-    for (int v = threadIdx.x; v < Ch; v += blockDim.x) {
-        float m = -INFINITY;
-        for (int h = 0; h < heads; ++h) m = fmaxf(m, sz[h * Ch + v]);
-        float z = 0.f;
-        for (int h = 0; h < heads; ++h) z += __expf(sz[h * Ch + v] - m);
-        for (int h = 0; h < heads; ++h) gate[(size_t)b * C + h * Ch + v] = __expf(sz[h * Ch + v] - m) / z;
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Ch) return;
+    const int b = i / Ch, v = i % Ch;
+    float* g = gate + (size_t)b * C + v;
+    float m = -INFINITY;
+    for (int h = 0; h < heads; ++h) m = fmaxf(m, g[h * Ch]);
+    float z = 0.f;
+    for (int h = 0; h < heads; ++h) z += __expf(g[h * Ch] - m);
+    const float inv = 1.f / z;
+    for (int h = 0; h < heads; ++h) g[h * Ch] = __expf(g[h * Ch] - m) * inv;
 }
 
-// DA gate backward, step 1 (one block per sample): dz = g * (dg - sum_h g*dg);  dhid = W2^T dz * (hid > 0)
-__global__ void da_gate_bwd1_kernel(const float* __restrict__ w2, const float* __restrict__ hid_in, const float* __restrict__ gate,
-                                    const float* __restrict__ dgate, float* __restrict__ dz_out, float* __restrict__ dhid_out, int hid,
-                                    int C, int heads) {
-    extern __shared__ float s[];   // dz[C]
-    float* dz = s;
-    const int b = blockIdx.x;
+// DA gate backward, step 1a (thread per (sample, v)): dz = g * (dg - sum_h g*dg)
+__global__ void da_gate_bwd_dz_kernel(const float* __restrict__ gate, const float* __restrict__ dgate, float* __restrict__ dz_out,
+                                      int B, int C, int heads) {
     const int Ch = C / heads;
-    for (int v = threadIdx.x; v < Ch; v += blockDim.x) {
-        float dot = 0.f;
-        for (int h = 0; h < heads; ++h) dot += gate[(size_t)b * C + h * Ch + v] * dgate[(size_t)b * C + h * Ch + v];
-        for (int h = 0; h < heads; ++h) {
-            const size_t i = (size_t)b * C + h * Ch + v;
-            const float d = gate[i] * (dgate[i] - dot);
-            dz[h * Ch + v] = d;
-            dz_out[i] = d;
-        }
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Ch) return;
+    const int b = i / Ch, v = i % Ch;
+    const size_t o = (size_t)b * C + v;
+    float dot = 0.f;
+    for (int h = 0; h < heads; ++h) dot += gate[o + h * Ch] * dgate[o + h * Ch];
+    for (int h = 0; h < heads; ++h) dz_out[o + h * Ch] = gate[o + h * Ch] * (dgate[o + h * Ch] - dot);
+}
+// step 1b: dhid[b,j] = (hid > 0) * sum_c W2[c,j] dz[b,c].  block = 32 hidden units x 8 channel lanes, grid (hid/32, B).
+__global__ void __launch_bounds__(256) da_gate_bwd_dhid_kernel(const float* __restrict__ w2, const float* __restrict__ hid_in,
+                                                                const float* __restrict__ dz, float* __restrict__ dhid_out, int hid,
+                                                                int C) {
+    __shared__ float red[8][33];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    float a = 0.f;
+    if (j < hid)
+        for (int c = warp; c < C; c += 8) a += __ldg(w2 + (size_t)c * hid + j) * __ldg(dz + (size_t)b * C + c);
+    red[warp][lane] = a;
     __syncthreads();
-    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-        float a = 0.f;
-        if (hid_in[(size_t)b * hid + j] > 0.f)
-            for (int c = 0; c < C; ++c) a += __ldg(w2 + (size_t)c * hid + j) * dz[c];
-        dhid_out[(size_t)b * hid + j] = a;
+    if (warp == 0 && j < hid) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        dhid_out[(size_t)b * hid + j] = hid_in[(size_t)b * hid + j] > 0.f ? t : 0.f;
     }
 }
 // step 2: dW2[c,j] += sum_b dz[b,c] hid[b,j]; db2[c] += sum_b dz[b,c]; dW1[j,d] += sum_b dhid[b,j] label[b,d]; db1[j] += sum_b dhid[b,j]
@@ -329,7 +342,10 @@ extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const voi
 extern "C" int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,
                                float* gate, int B, int nd, int hid, int C, int heads, void* stream) {
     if (!label || !w1 || !w2 || !hid_out || !gate || C % heads) return MDV_ERR_ARG;
-    da_gate_fwd_kernel<<<B, 128, (hid + C) * sizeof(float), (cudaStream_t)stream>>>(label, w1, b1, w2, b2, hid_out, gate, nd, hid, C, heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    da_gate_z_kernel<<<dim3(mdv_cdiv(C, 8), B), 256, hid * sizeof(float), st>>>(label, w1, b1, w2, b2, hid_out, gate, nd, hid, C);
+    MDV_CHECK_LAUNCH();
+    da_gate_softmax_kernel<<<mdv_cdiv(B * (C / heads), 128), 128, 0, st>>>(gate, B, C, heads);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -342,7 +358,9 @@ extern "C" int mdv_da_gate_bwd(const float* label, const float* w2, const float*
     cudaStream_t st = (cudaStream_t)stream;
     float* dz = ws;
     float* dhid = ws + (size_t)B * C;
-    da_gate_bwd1_kernel<<<B, 128, C * sizeof(float), st>>>(w2, hid_in, gate, dgate, dz, dhid, hid, C, heads);
+    da_gate_bwd_dz_kernel<<<mdv_cdiv(B * (C / heads), 128), 128, 0, st>>>(gate, dgate, dz, B, C, heads);
+    MDV_CHECK_LAUNCH();
+    da_gate_bwd_dhid_kernel<<<dim3(mdv_cdiv(hid, 32), B), 256, 0, st>>>(w2, hid_in, dz, dhid, hid, C);
     MDV_CHECK_LAUNCH();
     const int total = C * hid + C + hid * nd + hid;
     da_gate_bwd2_kernel<<<mdv_cdiv(total, 256), 256, 0, st>>>(label, hid_in, dz, dhid, dw1, db1, dw2, db2, B, nd, hid, C);

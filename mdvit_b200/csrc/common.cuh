@@ -25,9 +25,30 @@ extern long long g_mdv_launches;
 static inline int mdv_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------- math
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default, mpvit.py:61).  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32
+// round-off level) on the MUFU units: one ex2 + one rcp + 7 FMAs, a third of libdevice erff's instruction count — the
+// GEMM epilogues that apply it are issue-bound (8 warps/SM), see DESIGN.md.
+// Returns Phi(x) = 0.5 (1 + erf(x / sqrt 2)); *e_out = exp(-x^2 / 2).
+__device__ __forceinline__ float gauss_cdf(float x, float* e_out) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    const float e = __expf(-z * z);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float h = 0.5f * poly * t * e;          // 0.5 * erfc(|z|)
+    *e_out = e;
+    return x >= 0.0f ? 1.0f - h : h;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+    float e;
+    return x * gauss_cdf(x, &e);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    float e;
+    const float phi = gauss_cdf(x, &e);
+    return fmaf(x * 0.3989422804014327f, e, phi);
 }
 __device__ __forceinline__ float hardswish_f(float x) { return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f); }
 __device__ __forceinline__ float hardswish_grad(float x) {
@@ -74,15 +95,19 @@ __device__ __forceinline__ uint32_t rng_key(const unsigned long long* rng, uint3
     k = mix32(k ^ stream * 0x165667B1u);
     return k;
 }
-// keep-scale for element `idx`: 0 if dropped, 1/(1-p) if kept. thresh = p * 2^32.
-__device__ __forceinline__ float drop_scale(uint32_t key, unsigned long long idx, uint32_t thresh, float inv_keep) {
-    uint32_t h = mix32((uint32_t)idx * 0x9E3779B1u ^ key);
-    h = mix32(h ^ (uint32_t)(idx >> 32) ^ 0x632BE5ABu);
-    return h >= thresh ? inv_keep : 0.0f;
+// One 32-bit hash decides TWO consecutive elements (16 bits each): element idx is kept iff the (idx & 1)-th half of
+// hash(idx >> 1) is >= thresh16 = round(p * 65536).  Kernels that walk consecutive elements hash once per pair.
+__device__ __forceinline__ uint32_t drop_hash(uint32_t key, uint32_t pair) { return mix32(pair * 0x9E3779B1u ^ key); }
+__device__ __forceinline__ float drop_lo(uint32_t h, uint32_t thresh16, float inv_keep) { return (h & 0xFFFFu) >= thresh16 ? inv_keep : 0.0f; }
+__device__ __forceinline__ float drop_hi(uint32_t h, uint32_t thresh16, float inv_keep) { return (h >> 16) >= thresh16 ? inv_keep : 0.0f; }
+// keep-scale for element `idx`: 0 if dropped, 1/(1-p) if kept.
+__device__ __forceinline__ float drop_scale(uint32_t key, unsigned long long idx, uint32_t thresh16, float inv_keep) {
+    const uint32_t h = drop_hash(key, (uint32_t)(idx >> 1));
+    return (idx & 1ull) ? drop_hi(h, thresh16, inv_keep) : drop_lo(h, thresh16, inv_keep);
 }
 __host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
-    double t = (double)p * 4294967296.0;
-    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    const float t = p * 65536.0f + 0.5f;
+    return t >= 65535.0f ? 65535u : (uint32_t)t;
 }
 
 // ----------------------------------------------------------------------------- vector io

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t b_bytes = (uint32_t)BN * BK * 2;
     const uint32_t stage_bytes = A_BYTES + b_bytes;
     uint8_t* slabs = smem + (size_t)stages * stage_bytes;          // [8 warps][nbuf][out (+ preact)]
+    float* cs_all = reinterpret_cast<float*>(slabs + (size_t)NUM_EPI_WARPS * p.nbuf * p.buf_bytes);   // [8 warps][4 chunks][32]
     const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
 
     if (warp == 0 && lane == 0) {
@@ -284,10 +285,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             dkey = rng_key((const unsigned long long*)e.rng, e.drop_stream);
         }
         const bool out_bf16 = e.out_bf16 != 0;
+        // bias-gradient by-product: per-lane column sums of the stored tile, kept in shared memory across this CTA's
+        // tiles while they share an n_tile and flushed with one atomic per column when it changes / at the end
+        float* cs = cs_all + (warp - 4) * 128;
+        int cs_n0 = -1;
+        if (e.colsum) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cs[i * 32 + lane] = 0.f;
+        }
         int lt = 0, nstore = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const TileCoord tc = tile_coord<TN>(p, t);
             const int as = lt & 1;
+            if (e.colsum && tc.n_tile * BN != cs_n0) {
+                if (cs_n0 >= 0) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int col = cs_n0 + half * 32 + 64 * i + lane;
+                        if (half * 32 + 64 * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
+                        cs[i * 32 + lane] = 0.f;
+                    }
+                }
+                cs_n0 = tc.n_tile * BN;
+            }
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
             const int row0 = tc.m_tile * BM + q * 32;     // first row of this warp's slab
@@ -363,9 +382,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     }
                 }
                 if (dthr) {
-                    const unsigned long long base = (unsigned long long)row * (unsigned)p.N + (unsigned)col0;
+                    // N and col0 are even: elements (2j, 2j+1) of this chunk share one hash
+                    const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned)p.N + (unsigned)col0) >> 1);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] *= drop_scale(dkey, base + j, dthr, dinv);
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t h = drop_hash(dkey, pbase + j);
+                        f[2 * j] *= drop_lo(h, dthr, dinv);
+                        f[2 * j + 1] *= drop_hi(h, dthr, dinv);
+                    }
                 }
                 if (e.rowscale) {
 #pragma unroll
@@ -385,6 +409,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                         }
                     }
                 }
+                if (e.colsum && !row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.f;      // rows past M are clipped by the TMA store; keep them out of the sums
+                }
                 if (out_bf16) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -401,6 +429,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
                 fence_async_smem();
                 __syncwarp();
+                if (e.colsum) {
+                    // lane = column: walk the 32 rows of the staged (swizzled) tile
+                    float s = 0.f;
+                    if (out_bf16) {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            s += __bfloat162float(*reinterpret_cast<const bf16*>(s_out + r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4) + (lane & 7) * 2));
+                    } else {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            s += *reinterpret_cast<const float*>(s_out + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                    }
+                    cs[((c0 - half * 32) >> 6) * 32 + lane] += s;
+                }
                 if (lane == 0) {
                     if (TN) tma_reduce_add_2d(&tmC, s_out, col0, row0);
                     else tma_store_2d(&tmC, s_out, col0, row0);
@@ -413,6 +455,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (e.colsum && cs_n0 >= 0) {
+            for (int i = 0; i < 4; ++i) {
+                const int col = cs_n0 + half * 32 + 64 * i + lane;
+                if (half * 32 + 64 * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
+            }
         }
         if (lane == 0) tma_wait_all();
         __syncwarp();
@@ -484,9 +532,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     // short-K tiles are epilogue-bound (deep store buffering); long-K tiles are MMA-bound (spend smem on operand stages)
     const int kbt = TN ? p.kb_per_split : mdv_cdiv(p.K, BK);
     p.nbuf = kbt <= 2 ? 4 : (kbt <= 8 ? 2 : 1);
-    const size_t slab_bytes = (size_t)NUM_EPI_WARPS * p.nbuf * p.buf_bytes;
+    const size_t cs_bytes = p.epi.colsum ? NUM_EPI_WARPS * 128 * sizeof(float) : 0;
     const size_t budget = 226 * 1024 - 1024 - 512;
-    int stages = (int)((budget - slab_bytes) / stage_bytes);
+    size_t slab_bytes;
+    int stages;
+    for (;;) {
+        slab_bytes = (size_t)NUM_EPI_WARPS * p.nbuf * p.buf_bytes + cs_bytes;
+        stages = (int)((budget - slab_bytes) / stage_bytes);
+        if (stages >= 2 || p.nbuf == 1) break;
+        p.nbuf >>= 1;      // trade store buffering for operand stages
+    }
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (g_force_stages && g_force_stages < stages) stages = g_force_stages;
     if (stages < 2) return MDV_ERR_UNSUPPORTED;

@@ -110,13 +110,67 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
         float s = rowscale ? __ldg(rowscale + m / rps) : 1.f;
         float s0 = s, s1 = s, s2 = s, s3 = s;
         if (thr) {
-            const unsigned long long e = (unsigned long long)m * C + c;
-            s0 *= drop_scale(key, e, thr, inv);
-            s1 *= drop_scale(key, e + 1, thr, inv);
-            s2 *= drop_scale(key, e + 2, thr, inv);
-            s3 *= drop_scale(key, e + 3, thr, inv);
+            const uint32_t pr = (uint32_t)(((unsigned long long)m * C + c) >> 1);    // C, c multiples of 4: even index
+            const uint32_t h0 = drop_hash(key, pr), h1 = drop_hash(key, pr + 1);
+            s0 *= drop_lo(h0, thr, inv);
+            s1 *= drop_hi(h0, thr, inv);
+            s2 *= drop_lo(h1, thr, inv);
+            s3 *= drop_hi(h1, thr, inv);
         }
         *reinterpret_cast<uint2*>(out + m * ld_out + c) = make_uint2(f2_to_bf2(v.x * s0, v.y * s1), f2_to_bf2(v.z * s2, v.w * s3));
+    }
+}
+
+// Same cast, plus column sums of the values written (the bias gradient of the Linear whose output gradient this is).
+// block = (C/4 column groups) x (256 / (C/4) row lanes) over a chunk of rows; one atomic per column per block.
+__global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __restrict__ in, int ld_in, bf16* __restrict__ out,
+                                                                int ld_out, int M, int C, const float* __restrict__ rowscale, int rps,
+                                                                float drop_p, const unsigned long long* __restrict__ rng,
+                                                                uint32_t stream, float* __restrict__ colsum, int rows_per_block) {
+    __shared__ float4 sh[256];
+    const int cg = C >> 2;
+    const int nty = 256 / cg;
+    const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+    uint32_t thr = 0, key = 0;
+    float inv = 1.f;
+    if (drop_p > 0.f) {
+        thr = drop_thresh(drop_p);
+        inv = 1.f / (1.f - drop_p);
+        key = rng_key(rng, stream);
+    }
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    const int c = tx * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ty < nty) {
+#pragma unroll 4
+        for (int m = r0 + ty; m < r1; m += nty) {
+            const float4 v = *reinterpret_cast<const float4*>(in + (size_t)m * ld_in + c);
+            const float s = rowscale ? __ldg(rowscale + m / rps) : 1.f;
+            float s0 = s, s1 = s, s2 = s, s3 = s;
+            if (thr) {
+                const uint32_t pr = (uint32_t)(((unsigned long long)m * C + c) >> 1);
+                const uint32_t h0 = drop_hash(key, pr), h1 = drop_hash(key, pr + 1);
+                s0 *= drop_lo(h0, thr, inv);
+                s1 *= drop_hi(h0, thr, inv);
+                s2 *= drop_lo(h1, thr, inv);
+                s3 *= drop_hi(h1, thr, inv);
+            }
+            const float o0 = v.x * s0, o1 = v.y * s1, o2 = v.z * s2, o3 = v.w * s3;
+            acc.x += o0; acc.y += o1; acc.z += o2; acc.w += o3;
+            *reinterpret_cast<uint2*>(out + (size_t)m * ld_out + c) = make_uint2(f2_to_bf2(o0, o1), f2_to_bf2(o2, o3));
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0) {
+        for (int k = 1; k < nty; ++k) {
+            const float4 o = sh[k * cg + tx];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        atomicAdd(colsum + c, acc.x);
+        atomicAdd(colsum + c + 1, acc.y);
+        atomicAdd(colsum + c + 2, acc.z);
+        atomicAdd(colsum + c + 3, acc.w);
     }
 }
 
@@ -350,8 +404,19 @@ extern "C" int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, 
 }
 
 extern "C" int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
-                             int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
+                             int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* colsum, void* stream) {
     if (!in || !out_bf16 || (C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
+    if (colsum) {
+        if (C > 1024 || M > 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
+        int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);
+        const int nty = 256 / (C / 4);
+        if (rpb < 4 * nty) rpb = 4 * nty;
+        cast_bf16_colsum_kernel<<<mdv_cdiv(M, rpb), 256, 0, (cudaStream_t)stream>>>(in, ld_in, (bf16*)out_bf16, ld_out, (int)M, C, rowscale,
+                                                                                    rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
+                                                                                    (const unsigned long long*)rng, drop_stream, colsum, rpb);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     cast_bf16_kernel<<<grid_for(M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(in, ld_in, (bf16*)out_bf16, ld_out, M, C, rowscale,
                                                                                rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
                                                                                (const unsigned long long*)rng, drop_stream);

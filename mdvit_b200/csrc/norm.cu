@@ -51,23 +51,29 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 
 // ---------------------------------------------------------------------------------- LayerNorm backward
 // dx = dres + rstd * (gy - mean(gy) - xhat * mean(gy*xhat)),  gy = dy*gamma;  dgamma += sum dy*xhat; dbeta += sum dy.
-// Optional dx_masked = bf16(dx * rowscale[row / rows_per_scale] * dropout_mask) feeds the previous Linear's dgrad/wgrad.
+// Optional dx_masked = bf16(dx * rowscale[row / rows_per_scale] * dropout_mask) feeds the previous Linear's dgrad/wgrad,
+// and its column sums (that Linear's bias gradient) are accumulated into dbias_masked.
+// One warp owns R rows per iteration (all of their loads are issued before any arithmetic: with C = 64 a row is only
+// 256 B, so a single row per warp leaves HBM latency exposed); a row lives in registers, NV float2 per lane.
+template <int NV, int R>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                       const float* __restrict__ gamma, const float* __restrict__ dres,
                                                       float* __restrict__ dx, bf16* __restrict__ dx_masked,
                                                       const float* __restrict__ rowscale, int rows_per_scale, float drop_p,
                                                       const unsigned long long* __restrict__ rng, uint32_t drop_stream,
-                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C) {
+                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                      float* __restrict__ dbias_masked, int M) {
+    constexpr int C = NV * 64;
     __shared__ float red[8][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int nv = C >> 6;
-    float2 ag[LN_MAXV], ab[LN_MAXV], gm[LN_MAXV];
+    float2 ag[NV], ab[NV], am[NV], gm[NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         ag[i] = make_float2(0.f, 0.f);
         ab[i] = make_float2(0.f, 0.f);
-        if (i < nv) gm[i] = *reinterpret_cast<const float2*>(gamma + i * 64 + lane * 2);
+        am[i] = make_float2(0.f, 0.f);
+        gm[i] = *reinterpret_cast<const float2*>(gamma + i * 64 + lane * 2);
     }
     uint32_t dthr = 0, dkey = 0;
     float dinv = 1.f;
@@ -76,74 +82,90 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         dinv = 1.f / (1.f - drop_p);
         dkey = rng_key(rng, drop_stream);
     }
-    for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
-        const size_t off = (size_t)row * C;
-        float2 d[LN_MAXV], xh[LN_MAXV];
-        float s1 = 0.f, s2 = 0.f;
+    for (int row0 = (blockIdx.x * nwarp + warp) * R; row0 < M; row0 += gridDim.x * nwarp * R) {
+        float2 d[R][NV], xh[R][NV], rr[R][NV];
+        float mean[R], rstd[R];
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i)
-            if (i < nv) {
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r;
+            const bool ok = row < M;
+            const size_t off = (size_t)(ok ? row : 0) * C;
+            mean[r] = ok ? mean_in[row] : 0.f;
+            rstd[r] = ok ? rstd_in[row] : 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
                 const int c = i * 64 + lane * 2;
-                d[i] = *reinterpret_cast<const float2*>(dy + off + c);
-                float2 xv = *reinterpret_cast<const float2*>(x + off + c);
-                xh[i] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
-                ag[i].x += d[i].x * xh[i].x;
-                ag[i].y += d[i].y * xh[i].y;
-                ab[i].x += d[i].x;
-                ab[i].y += d[i].y;
-                d[i].x *= gm[i].x;
-                d[i].y *= gm[i].y;
-                s1 += d[i].x + d[i].y;
-                s2 += d[i].x * xh[i].x + d[i].y * xh[i].y;
+                d[r][i] = ok ? *reinterpret_cast<const float2*>(dy + off + c) : make_float2(0.f, 0.f);
+                xh[r][i] = ok ? *reinterpret_cast<const float2*>(x + off + c) : make_float2(0.f, 0.f);
+                rr[r][i] = (ok && dres) ? *reinterpret_cast<const float2*>(dres + off + c) : make_float2(0.f, 0.f);
             }
-        s1 = warp_sum(s1) / C;
-        s2 = warp_sum(s2) / C;
-        const float rs = rowscale ? rowscale[row / rows_per_scale] : 1.f;
+        }
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i)
-            if (i < nv) {
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r;
+            if (row >= M) break;
+            const size_t off = (size_t)row * C;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                xh[r][i] = make_float2((xh[r][i].x - mean[r]) * rstd[r], (xh[r][i].y - mean[r]) * rstd[r]);
+                ag[i].x += d[r][i].x * xh[r][i].x;
+                ag[i].y += d[r][i].y * xh[r][i].y;
+                ab[i].x += d[r][i].x;
+                ab[i].y += d[r][i].y;
+                d[r][i].x *= gm[i].x;
+                d[r][i].y *= gm[i].y;
+                s1 += d[r][i].x + d[r][i].y;
+                s2 += d[r][i].x * xh[r][i].x + d[r][i].y * xh[r][i].y;
+            }
+            s1 = warp_sum(s1) * (1.f / C);
+            s2 = warp_sum(s2) * (1.f / C);
+            const float rs = rowscale ? rowscale[row / rows_per_scale] : 1.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
                 const int c = i * 64 + lane * 2;
-                float o0 = rstd * (d[i].x - s1 - xh[i].x * s2), o1 = rstd * (d[i].y - s1 - xh[i].y * s2);
-                if (dres) {
-                    float2 r = *reinterpret_cast<const float2*>(dres + off + c);
-                    o0 += r.x;
-                    o1 += r.y;
-                }
+                const float o0 = rstd[r] * (d[r][i].x - s1 - xh[r][i].x * s2) + rr[r][i].x;
+                const float o1 = rstd[r] * (d[r][i].y - s1 - xh[r][i].y * s2) + rr[r][i].y;
                 *reinterpret_cast<float2*>(dx + off + c) = make_float2(o0, o1);
                 if (dx_masked) {
                     float m0 = rs, m1 = rs;
                     if (dthr) {
-                        m0 *= drop_scale(dkey, off + c, dthr, dinv);
-                        m1 *= drop_scale(dkey, off + c + 1, dthr, dinv);
+                        const uint32_t h = drop_hash(dkey, (uint32_t)((off + c) >> 1));   // off + c is even
+                        m0 *= drop_lo(h, dthr, dinv);
+                        m1 *= drop_hi(h, dthr, dinv);
                     }
-                    *reinterpret_cast<uint32_t*>(dx_masked + off + c) = f2_to_bf2(o0 * m0, o1 * m1);
-                }
-            }
-    }
-    // column reductions across the block's warps, then one atomic per column per block
-    if (!dgamma) return;   // weight gradients switched off for this pass (block-uniform)
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-        if (i < nv) {
-            for (int pass = 0; pass < 2; ++pass) {
-                float2 val = pass == 0 ? ag[i] : ab[i];
-                __syncthreads();
-                red[warp][lane * 2] = val.x;
-                red[warp][lane * 2 + 1] = val.y;
-                __syncthreads();
-                if (warp == 0) {
-                    float t0 = 0.f, t1 = 0.f;
-                    for (int w = 0; w < nwarp; ++w) {
-                        t0 += red[w][lane * 2];
-                        t1 += red[w][lane * 2 + 1];
-                    }
-                    float* dst = (pass == 0 ? dgamma : dbeta) + i * 64 + lane * 2;
-                    atomicAdd(dst, t0);
-                    atomicAdd(dst + 1, t1);
+                    m0 *= o0;
+                    m1 *= o1;
+                    am[i].x += m0;
+                    am[i].y += m1;
+                    *reinterpret_cast<uint32_t*>(dx_masked + off + c) = f2_to_bf2(m0, m1);
                 }
             }
         }
+    }
+    // column reductions across the block's warps, then one atomic per column per block
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        for (int pass = 0; pass < 3; ++pass) {
+            float* base = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias_masked);
+            if (!base) continue;   // block-uniform
+            const float2 val = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : am[i]);
+            __syncthreads();
+            red[warp][lane * 2] = val.x;
+            red[warp][lane * 2 + 1] = val.y;
+            __syncthreads();
+            if (warp == 0) {
+                float t0 = 0.f, t1 = 0.f;
+                for (int w = 0; w < nwarp; ++w) {
+                    t0 += red[w][lane * 2];
+                    t1 += red[w][lane * 2 + 1];
+                }
+                float* dst = base + i * 64 + lane * 2;
+                atomicAdd(dst, t0);
+                atomicAdd(dst + 1, t1);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------- BatchNorm
@@ -320,13 +342,31 @@ extern "C" int mdv_layernorm_fwd(const float* x, const float* gamma, const float
 extern "C" int mdv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                  const float* dres, float* dx, void* dx_masked_bf16, const float* rowscale,
                                  int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* dgamma,
-                                 float* dbeta, int M, int C, void* stream) {
-    if (!dy || !x || !dx || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
-    int blocks = mdv_cdiv(M, 8);
-    if (blocks > 4 * MDV_NUM_SMS) blocks = 4 * MDV_NUM_SMS;
-    ln_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x, mean, rstd, gamma, dres, dx, (bf16*)dx_masked_bf16, rowscale,
-                                                             rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
-                                                             (const unsigned long long*)rng, drop_stream, dgamma, dbeta, M, C);
+                                 float* dbeta, float* dbias_masked, int M, int C, void* stream) {
+    if (!dy || !x || !dx || !gamma || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
+    if (dbias_masked && !dx_masked_bf16) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
+#define MDV_LN_BWD(NV, R)                                                                                                        \
+    {                                                                                                                            \
+        int blocks = mdv_cdiv(M, 8 * R);                                                                                         \
+        if (blocks > 4 * MDV_NUM_SMS) blocks = 4 * MDV_NUM_SMS;                                                                  \
+        ln_bwd_kernel<NV, R><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, (bf16*)dx_masked_bf16, rowscale, rps,   \
+                                                     drop_p, (const unsigned long long*)rng, drop_stream, dgamma, dbeta,         \
+                                                     dbias_masked, M);                                                           \
+    }                                                                                                                            \
+    break;
+    switch (C >> 6) {
+        case 1: MDV_LN_BWD(1, 4)
+        case 2: MDV_LN_BWD(2, 4)
+        case 3: MDV_LN_BWD(3, 2)
+        case 4: MDV_LN_BWD(4, 2)
+        case 5: MDV_LN_BWD(5, 2)
+        case 6: MDV_LN_BWD(6, 1)
+        case 7: MDV_LN_BWD(7, 1)
+        default: MDV_LN_BWD(8, 1)
+    }
+#undef MDV_LN_BWD
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

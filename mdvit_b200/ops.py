@@ -87,10 +87,10 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
 
 # ------------------------------------------------------------------------------------------------- thin wrappers
 def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, residual=None, act=ACT_NONE, out_preact=None,
-            mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False):
+            mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False, colsum=None):
     e = GemmEpi()
     e.bias, e.residual, e.mul_gelu_grad, e.out_preact = ptr(bias), ptr(residual), ptr(mul_gelu_grad), ptr(out_preact)
-    e.out, e.rowscale = ptr(out), ptr(rowscale)
+    e.out, e.rowscale, e.colsum = ptr(out), ptr(rowscale), ptr(colsum)
     e.rng = ptr(rng_tensor(out.device)) if drop_p > 0 else None
     e.ld_res = N if residual is not None else 0
     e.ld_mul = N if mul_gelu_grad is not None else 0
@@ -121,11 +121,12 @@ def colsum(x, M, C, out, ld=None):
     return out
 
 
-def cast_bf16(x, M, C, out=None, ld_in=None, ld_out=None, rowscale=None, rows_per_scale=1, drop_p=0.0, drop_stream=0):
+def cast_bf16(x, M, C, out=None, ld_in=None, ld_out=None, rowscale=None, rows_per_scale=1, drop_p=0.0, drop_stream=0, colsum=None):
     if out is None:
         out = torch.empty((M, C), dtype=BF16, device=x.device)
     check(L.lib().mdv_cast_bf16(ptr(x), ld_in or C, ptr(out), ld_out or C, M, C, ptr(rowscale), rows_per_scale, float(drop_p),
-                                ptr(rng_tensor(x.device)) if drop_p > 0 else None, drop_stream, L.stream()), "mdv_cast_bf16")
+                                ptr(rng_tensor(x.device)) if drop_p > 0 else None, drop_stream, ptr(colsum), L.stream()),
+          "mdv_cast_bf16")
     return out
 
 
@@ -139,12 +140,12 @@ def layernorm_fwd(x, w, b, M, C, eps=1e-6):
 
 
 def layernorm_bwd(dy, x, mean, rstd, w, dres, M, C, dg, db, *, masked=False, rowscale=None, rows_per_scale=1, drop_p=0.0,
-                  drop_stream=0):
+                  drop_stream=0, dbias_masked=None):
     dx = torch.empty((M, C), dtype=F32, device=x.device)
     dxm = torch.empty((M, C), dtype=BF16, device=x.device) if masked else None
     check(L.lib().mdv_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(w), ptr(dres), ptr(dx), ptr(dxm), ptr(rowscale),
                                     rows_per_scale, ctypes.c_float(drop_p), ptr(rng_tensor(x.device)) if drop_p > 0 else None,
-                                    drop_stream, ptr(dg), ptr(db), M, C, L.stream()), "mdv_layernorm_bwd")
+                                    drop_stream, ptr(dg), ptr(db), ptr(dbias_masked), M, C, L.stream()), "mdv_layernorm_bwd")
     return dx, dxm
 
 
@@ -329,20 +330,19 @@ class BlockFn(torch.autograd.Function):
         G = {k: v[0] for k, v in T.items()}
         with _dev_ctx(x):
             # ---- MLP
-            d_fc2 = cast_bf16(dx3, M, C, rowscale=dp2, rows_per_scale=N, drop_p=p_drop, drop_stream=sid[2])
+            # bias gradients (column sums) are by-products of the kernels that produce each output gradient
+            d_fc2 = cast_bf16(dx3, M, C, rowscale=dp2, rows_per_scale=N, drop_p=p_drop, drop_stream=sid[2], colsum=G["fc2_b"])
             gemm_tn(d_fc2, hact, M, C, hidden, G["fc2_w"])
-            colsum(d_fc2, M, C, G["fc2_b"])
             du = torch.empty((M, hidden), dtype=BF16, device=dev)
-            gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, drop_p=p_drop, drop_stream=sid[1])
+            gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, drop_p=p_drop, drop_stream=sid[1],
+                    colsum=G["fc1_b"])
             gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
-            colsum(du, M, hidden, G["fc1_b"])
             dln2 = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(du, prep_weight(fc1_w, 1, hidden, C), M, C, hidden, dln2)
             dx2, d_proj = layernorm_bwd(dln2, x2, mean2, rstd2, n2w, dx3, M, C, G["n2w"], G["n2b"], masked=True, rowscale=dp1,
-                                        rows_per_scale=N, drop_p=p_drop, drop_stream=sid[0])
+                                        rows_per_scale=N, drop_p=p_drop, drop_stream=sid[0], dbias_masked=G["proj_b"])
             # ---- attention
             gemm_tn(d_proj, y, M, C, C, G["proj_w"])
-            colsum(d_proj, M, C, G["proj_b"])
             dy = torch.empty((M, C), dtype=BF16, device=dev)
             gemm_nt(d_proj, prep_weight(proj_w, 1, C, C), M, C, C, dy)
             dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)

@@ -99,8 +99,55 @@ def test_gemm_nt_dropout_mask_is_reproducible_and_unbiased(env):
     # the standalone cast kernel regenerates the identical mask (used by the backward pass)
     ones = torch.ones(M, N, device=dev)
     m2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    L.check(lib.mdv_cast_bf16(L.ptr(ones), N, L.ptr(m2), N, M, N, None, 1, p, L.ptr(rng), 5, L.stream()), "cast")
+    L.check(lib.mdv_cast_bf16(L.ptr(ones), N, L.ptr(m2), N, M, N, None, 1, p, L.ptr(rng), 5, None, L.stream()), "cast")
     assert torch.equal(m2.float() == 0, outs[0] == 0)
+    # ... and so does the cast+column-sum variant, whose sums are the bias gradient
+    m3 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=dev)
+    L.check(lib.mdv_cast_bf16(L.ptr(ones), N, L.ptr(m3), N, M, N, None, 1, p, L.ptr(rng), 5, L.ptr(cs), L.stream()), "cast")
+    assert torch.equal(m3, m2) and rel(cs, m2.float().sum(0)) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 64), (5000, 512, 64), (300, 320, 1280), (40000, 1024, 128)])
+def test_gemm_nt_colsum_byproduct(env, M, N, K):
+    """epi.colsum accumulates the column sums of the stored tile (bias gradient of the producing Linear)."""
+    L, lib, dev = env
+    torch.manual_seed(N)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    for dt in (torch.bfloat16, torch.float32):
+        out = torch.empty(M, N, device=dev, dtype=dt)
+        cs = torch.ones(N, device=dev)
+        e = L.GemmEpi()
+        e.out, e.ldc, e.out_bf16, e.colsum = L.ptr(out), N, int(dt == torch.bfloat16), L.ptr(cs)
+        L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "gemm_nt")
+        ref = A.float() @ W.float().t()
+        assert rel(out, ref) < BF16_TOL
+        want = 1.0 + out.double().sum(0)
+        assert ((cs.double() - want).abs().max() / want.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("M,C", [(1000, 64), (777, 128), (500, 320), (300, 512)])
+def test_layernorm_bwd_masked_output_and_bias_colsum(env, M, C):
+    L, lib, dev = env
+    torch.manual_seed(C + 1)
+    x, dy, dres = torch.randn(M, C, device=dev), torch.randn(M, C, device=dev), torch.randn(M, C, device=dev)
+    g, b = 1 + 0.1 * torch.randn(C, device=dev), torch.zeros(C, device=dev)
+    y = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    L.check(lib.mdv_layernorm_fwd(L.ptr(x), L.ptr(g), L.ptr(b), 1e-6, L.ptr(y), L.ptr(mean), L.ptr(rstd), M, C, L.stream()), "ln")
+    rows_per = 100
+    rs = torch.rand((M + rows_per - 1) // rows_per, device=dev) + 0.5
+    rng = torch.tensor([9, 3], dtype=torch.int64, device=dev)
+    dx, dxm = torch.empty(M, C, device=dev), torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    dg, db, dbm = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    L.check(lib.mdv_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), L.ptr(dres), L.ptr(dx), L.ptr(dxm), L.ptr(rs),
+                                  rows_per, 0.1, L.ptr(rng), 11, L.ptr(dg), L.ptr(db), L.ptr(dbm), M, C, L.stream()), "ln_bwd")
+    mask = torch.empty(M, C, device=dev, dtype=torch.bfloat16)      # the same mask from the standalone cast kernel
+    L.check(lib.mdv_cast_bf16(L.ptr(torch.ones(M, C, device=dev)), C, L.ptr(mask), C, M, C, None, 1, 0.1, L.ptr(rng), 11, None, L.stream()), "cast")
+    want = dx * rs.repeat_interleave(rows_per)[:M, None] * (mask.float() != 0) / 0.9
+    assert rel(dxm, want) < BF16_TOL
+    assert rel(dbm, want.sum(0)) < 1e-4
 
 
 @pytest.mark.parametrize("R,P,Q", [(64, 128, 64), (1000, 64, 64), (8192, 320, 1280), (9000, 32, 64), (9000, 64, 288), (8, 512, 4608),
@@ -133,7 +180,7 @@ def test_layernorm_fwd_bwd(env, M, C):
     (ref * dy).sum().backward()
     dx, dg, db = torch.empty(M, C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     L.check(lib.mdv_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), L.ptr(dres), L.ptr(dx), None, None, 1, 0.0, None,
-                                  0, L.ptr(dg), L.ptr(db), M, C, L.stream()), "ln_bwd")
+                                  0, L.ptr(dg), L.ptr(db), None, M, C, L.stream()), "ln_bwd")
     assert rel(dx, x.grad + dres) < F32_TOL and rel(dg, g.grad) < F32_TOL and rel(db, b.grad) < F32_TOL
 
 
