@@ -1,4 +1,4 @@
-// Internal interface between attn.cu (cross-token statistics, C ABI) and attn_tile.cu (token-parallel tiled kernels).
+// Internal interface between attn.cu (C ABI, column max, DA gate) and attn_strip.cu (cross-token sums + strip kernels).
 #pragma once
 #include "../../include/mdvit_b200.h"
 #include "common.cuh"
@@ -12,8 +12,9 @@ struct CrpeG {
     float* b[3];
 };
 
-int attn_tile_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& cw, bf16* out, float scale, int B, int H, int W, int C,
-                  int Ch, cudaStream_t st);
-int attn_tile_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* A, const float* At, const float* dA,
-                  const float* dAt, const float* rk, const float* kmax, const float* zsum, const CrpeW& cw, const CrpeG& cg, bf16* dqkv,
-                  float* dgate, float scale, int B, int H, int W, int C, int Ch, cudaStream_t st);
+long long attn_strip_ws_floats(int B, int C, int Ch);
+int attn_strip_fwd(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out,
+                   float scale, int B, int H, int W, int C, int Ch, cudaStream_t st);
+int attn_strip_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum,
+                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B, int H, int W,
+                   int C, int Ch, cudaStream_t st);

@@ -1,0 +1,771 @@
+// Factorized attention, second generation: "strip" kernels.
+//
+// lane == one PAIR of adjacent channels (one bf16x2 word), so a warp spans 64 channels with 128-byte coalesced global
+// accesses and conflict-free 128-byte shared-memory rows, and every fp32 multiply-add is a packed FFMA2 over the pair.
+// A thread owns a horizontal strip of TX = 8 pixels: each staged input value is reused for up to WIN taps x TX outputs
+// from registers, so the 3x3 / 5x5 / 7x7 depthwise relative-position convolution (mpvit.py:296-318) costs ~0.2 shared
+// loads per multiply-add instead of 1.  The per-head Ch x Ch matrix products (Q.A, and in backward dF.A^T, S.dA, V.dA^T)
+// are done with warp shuffles inside the lanes of a head.  Cross-token reductions (K^T V and Q^T dF) write per-chunk
+// partials that a second tiny kernel sums in a fixed order: no atomics, bit-reproducible forward.
+//
+// Channel groups: a warp handles CPW = 64 channels (8 heads at Ch=8, 4 at Ch=16, 1 at Ch=64) or one 40-channel head
+// (20 active lanes) at Ch=40.  The convolution window of a group is that of its last head (windows grow with the head).
+#include "attn_internal.cuh"
+
+namespace {
+
+constexpr int TX = 8;        // pixels per strip
+constexpr int TILE_W = 16;   // spatial tile (pixels) handled by one block
+constexpr int TILE_H = 16;
+
+template <int CH>
+struct Cfg {
+    static constexpr int LPH = CH / 2;                        // lanes per head
+    static constexpr int HPW = CH <= 16 ? 32 / LPH : 1;       // heads per warp
+    static constexpr int ACT = LPH * HPW;                     // active lanes (32, 32, 20, 32)
+    static constexpr int CPW = 2 * ACT;                       // channels per warp / group
+    static constexpr int KR = CH <= 16 ? CH : CH / 2;         // k-range per block of the outer-product kernel
+    static constexpr int KSPLIT = CH / KR;
+};
+
+__host__ __device__ inline int win_of_head(int h) { return h < 2 ? 3 : (h < 5 ? 5 : 7); }
+
+__device__ __forceinline__ float2 up2(uint32_t v) { return bf2_to_f2(v); }
+__device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// per-lane view of the filter bank: (window, pointer to this channel's taps, pointer to its bias)
+__device__ __forceinline__ void crpe_of_channel(const CrpeW& cw, int c, int CH, const float*& w, const float*& b, int& win) {
+    const int h = c / CH;
+    const int grp = h < 2 ? 0 : (h < 5 ? 1 : 2);
+    const int cl = c - (grp == 0 ? 0 : (grp == 1 ? 2 * CH : 5 * CH));
+    win = 3 + 2 * grp;
+    w = cw.w[grp] + (size_t)cl * win * win;
+    b = cw.b[grp] + cl;
+}
+
+// ------------------------------------------------------------------------------------------------ cross-token sums
+// MODE 0:  part[k,v] = sum_n exp(K[n,k]-kmax[k]) V[n,v];  zpart[k] = sum_n exp(K[n,k]-kmax[k])      (forward, App. E)
+// MODE 1:  part[k,v] = sum_n Q[n,k] (g[v] dY[n,v])                                                  (backward dA / scale)
+// grid = (token chunk, group * KSPLIT + ksplit, B).  A warp walks its tokens 4 at a time; lane (pair v) accumulates
+// acc[k] for the KR values of k of this split, fetching P[n,k] from the lane that owns k with shuffles.
+template <int CH, int MODE>
+__global__ void __launch_bounds__(256) attn_outer_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+                                                          const float* __restrict__ gate, const float* __restrict__ kmax,
+                                                          float* __restrict__ part, float* __restrict__ zpart, int N, int C,
+                                                          int rows_per_block, int nchunk) {
+    using G = Cfg<CH>;
+    constexpr int KR = G::KR;
+    __shared__ float2 red[KR][32];
+    __shared__ float2 zred[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, chunk = blockIdx.x;
+    const int grp = blockIdx.y / G::KSPLIT, ks = blockIdx.y % G::KSPLIT;
+    const bool act = lane < G::ACT;
+    const int c0 = grp * G::CPW + 2 * (act ? lane : 0);            // this lane's channel pair
+    const int hb = (lane / G::LPH) * G::LPH;                        // first lane of this lane's head
+    const int r0 = chunk * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    const bf16* base = qkv + (size_t)b * N * 3 * C;
+    float2 km = make_float2(0.f, 0.f), gt = make_float2(1.f, 1.f);
+    if (MODE == 0) km = *reinterpret_cast<const float2*>(kmax + (size_t)b * C + c0);
+    if (MODE == 1 && gate) gt = *reinterpret_cast<const float2*>(gate + (size_t)b * C + c0);
+    float2 acc[KR];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) acc[k] = make_float2(0.f, 0.f);
+    float2 zacc = make_float2(0.f, 0.f);
+    constexpr int U = 4;
+    for (int n0 = r0 + warp * U; n0 < r1; n0 += 8 * U) {
+        uint32_t pw[U], vw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = n0 + u;
+            const bool ok = act && n < r1;
+            const size_t row = (size_t)n * 3 * C;
+            if (MODE == 0) {
+                pw[u] = ok ? *reinterpret_cast<const uint32_t*>(base + row + C + c0) : 0u;
+                vw[u] = ok ? *reinterpret_cast<const uint32_t*>(base + row + 2 * C + c0) : 0u;
+            } else {
+                pw[u] = ok ? *reinterpret_cast<const uint32_t*>(base + row + c0) : 0u;
+                vw[u] = ok ? *reinterpret_cast<const uint32_t*>(dy + ((size_t)b * N + n) * C + c0) : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = act && (n0 + u) < r1;
+            float2 p = up2(pw[u]);
+            float2 v = up2(vw[u]);
+            if (MODE == 0) {
+                p = ok ? make_float2(__expf(p.x - km.x), __expf(p.y - km.y)) : make_float2(0.f, 0.f);
+                zacc.x += p.x;
+                zacc.y += p.y;
+            } else {
+                v = mul2(v, gt);
+            }
+#pragma unroll
+            for (int kk = 0; kk < KR / 2; ++kk) {
+                const float2 pp = shfl2(p, hb + ks * (KR / 2) + kk);
+                acc[2 * kk] = fma2(splat(pp.x), v, acc[2 * kk]);
+                acc[2 * kk + 1] = fma2(splat(pp.y), v, acc[2 * kk + 1]);
+            }
+        }
+    }
+    // deterministic block reduction: warps add in order
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                float2 t = w == 0 ? make_float2(0.f, 0.f) : red[k][lane];
+                red[k][lane] = make_float2(t.x + acc[k].x, t.y + acc[k].y);
+            }
+            if (MODE == 0) {
+                float2 t = w == 0 ? make_float2(0.f, 0.f) : zred[lane];
+                zred[lane] = make_float2(t.x + zacc.x, t.y + zacc.y);
+            }
+        }
+        __syncthreads();
+    }
+    // part[b][chunk][c = h*CH + k][v]  (v pair of this lane)
+    for (int idx = threadIdx.x; idx < KR * 32; idx += 256) {
+        const int k = idx >> 5, l = idx & 31;
+        if (l >= G::ACT) continue;
+        const int cc = grp * G::CPW + 2 * l;
+        const int h = cc / CH, v = cc % CH;
+        const int kg = ks * KR + k;
+        float* dst = part + (((size_t)(b * nchunk + chunk) * C) + h * CH + kg) * CH + v;
+        *reinterpret_cast<float2*>(dst) = red[k][l];
+    }
+    if (MODE == 0 && ks == 0 && threadIdx.x < G::ACT)
+        *reinterpret_cast<float2*>(zpart + (size_t)(b * nchunk + chunk) * C + grp * G::CPW + 2 * threadIdx.x) = zred[threadIdx.x];
+}
+
+// A[b,c,v] = sum_chunks part / sum_chunks zpart ; zsum[b,c]
+__global__ void attn_combine_fwd_kernel(const float* __restrict__ part, const float* __restrict__ zpart, float* __restrict__ A,
+                                        float* __restrict__ zsum, int C, int Ch, int nchunk, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long bc = i / Ch;
+    const int b = (int)(bc / C), c = (int)(bc % C);
+    float s = 0.f, z = 0.f;
+    for (int k = 0; k < nchunk; ++k) {
+        s += part[((size_t)(b * nchunk + k) * C + c) * Ch + (i % Ch)];
+        z += zpart[(size_t)(b * nchunk + k) * C + c];
+    }
+    A[i] = s / z;
+    if ((i % Ch) == 0) zsum[bc] = z;
+}
+
+// dA[b,c,v] = scale * sum_chunks part ;  rk[b,c] = sum_v A[b,c,v] dA[b,c,v]      (one warp per (b,c) row)
+__global__ void attn_combine_bwd_kernel(const float* __restrict__ part, const float* __restrict__ A, float* __restrict__ dA,
+                                        float* __restrict__ rk, float scale, int C, int Ch, int nchunk, int rows) {
+    const int lane = threadIdx.x & 31;
+    const int bc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bc >= rows) return;
+    const int b = bc / C, c = bc % C;
+    float r = 0.f;
+    for (int v = lane; v < Ch; v += 32) {
+        float s = 0.f;
+        for (int k = 0; k < nchunk; ++k) s += part[((size_t)(b * nchunk + k) * C + c) * Ch + v];
+        s *= scale;
+        dA[(size_t)bc * Ch + v] = s;
+        r += s * A[(size_t)bc * Ch + v];
+    }
+    r = warp_sum(r);
+    if (lane == 0) rk[bc] = r;
+}
+
+// ------------------------------------------------------------------------------------------------ tile helpers
+struct TileGeom {
+    int ty0, tx0, th, tw, R, PW, PH, nsx;   // PW: padded row pitch (strips rounded up + halo); nsx strips per row
+};
+__device__ __forceinline__ TileGeom tile_geom(int H, int Wd, int WIN) {
+    TileGeom g;
+    const int TH = min(H, TILE_H), TW = min(Wd, TILE_W);
+    const int tiles_x = (Wd + TW - 1) / TW;
+    g.ty0 = (blockIdx.x / tiles_x) * TH;
+    g.tx0 = (blockIdx.x % tiles_x) * TW;
+    g.th = min(TH, H - g.ty0);
+    g.tw = min(TW, Wd - g.tx0);
+    g.R = WIN >> 1;
+    g.nsx = (g.tw + TX - 1) / TX;
+    g.PW = g.nsx * TX + 2 * g.R;
+    g.PH = g.th + 2 * g.R;
+    return g;
+}
+__host__ __device__ constexpr int tile_words(int WIN) {   // uint32 words of one halo tile (worst case geometry)
+    return (TILE_H + WIN - 1) * (((TILE_W + TX - 1) / TX) * TX + WIN - 1) * 32;
+}
+
+// stage src[b, pos, c0 + 2*lane .. +1] (bf16x2 words) for all halo positions; zero outside the image / for idle lanes
+template <int ACT>
+__device__ __forceinline__ void load_halo(uint32_t* dst, const bf16* __restrict__ src_b, int ld, int cg0, const TileGeom& g, int H, int Wd) {
+    const int total = g.PH * g.PW * 8;                               // 8 x 16-byte parts per 128-byte position
+    constexpr int UB = 8;                                            // loads in flight per thread
+    for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * UB) {
+        uint4 v[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * blockDim.x;
+            const int pos = e >> 3, part = e & 7;
+            const int py = pos / g.PW, px = pos - py * g.PW;
+            const int y = g.ty0 - g.R + py, x = g.tx0 - g.R + px;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (e < total && part * 4 < ACT && y >= 0 && y < H && x >= 0 && x < Wd && px < g.tw + 2 * g.R)
+                v[u] = *reinterpret_cast<const uint4*>(src_b + (size_t)(y * Wd + x) * ld + cg0 + part * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < total) *reinterpret_cast<uint4*>(dst + (e >> 3) * 32 + (e & 7) * 4) = v[u];
+        }
+    }
+}
+
+// zero-padded WIN x WIN taps of every lane's channel pair: sW[tap][lane] (float2)
+template <int CH, int WIN>
+__device__ __forceinline__ void load_taps(float2* sW, const CrpeW& cw, int cg0, int nact) {
+    for (int e = threadIdx.x; e < WIN * WIN * 32; e += blockDim.x) {
+        const int tap = e >> 5, l = e & 31;
+        float2 w = make_float2(0.f, 0.f);
+        if (l < nact) {
+            const int i = tap / WIN, j = tap % WIN;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float* wp; const float* bp; int wc;
+                crpe_of_channel(cw, cg0 + 2 * l + u, CH, wp, bp, wc);
+                const int o = (WIN - wc) >> 1, ii = i - o, jj = j - o;
+                const float t = (ii >= 0 && ii < wc && jj >= 0 && jj < wc) ? __ldg(wp + ii * wc + jj) : 0.f;
+                if (u == 0) w.x = t; else w.y = t;
+            }
+        }
+        sW[e] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// Y[n,v] = g[v] * ( s * sum_k Q[n,k] A[k,v] + Q[n,v] * (dwconv(V)[n,v] + b[v]) )         (mdvit.py:293-304)
+template <int CH, int WIN>
+__device__ __forceinline__ void attn_fwd_strip_body(const bf16* __restrict__ qkv, const float* __restrict__ A,
+                                                    const float* __restrict__ gate, const CrpeW& cw, bf16* __restrict__ out,
+                                                    float scale, int H, int Wd, int C, uint8_t* smem_s) {
+    using G = Cfg<CH>;
+    const int grp0 = 0;
+    uint32_t* sV = reinterpret_cast<uint32_t*>(smem_s);
+    float2* sW = reinterpret_cast<float2*>(sV + tile_words(WIN));
+    float4* sA = reinterpret_cast<float4*>(sW + WIN * WIN * 32);      // [CH/2][32]: (A[2kk][v0], A[2kk+1][v0], A[2kk][v1], A[2kk+1][v1])
+    const int N = H * Wd;
+    const int b = blockIdx.z, cg0 = (blockIdx.y + grp0) * G::CPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileGeom g = tile_geom(H, Wd, WIN);
+    const bf16* qkv_b = qkv + (size_t)b * N * 3 * C;
+    load_halo<G::ACT>(sV, qkv_b + 2 * C, 3 * C, cg0, g, H, Wd);
+    load_taps<CH, WIN>(sW, cw, cg0, G::ACT);
+    for (int e = threadIdx.x; e < (CH / 2) * 32; e += blockDim.x) {
+        const int kk = e >> 5, l = e & 31;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < G::ACT) {
+            const int c = cg0 + 2 * l, h = c / CH, v = c % CH;
+            const float* src = A + ((size_t)b * C + h * CH + 2 * kk) * CH + v;
+            const float2 r0 = *reinterpret_cast<const float2*>(src), r1 = *reinterpret_cast<const float2*>(src + CH);
+            a = make_float4(r0.x, r1.x, r0.y, r1.y);
+        }
+        sA[e] = a;
+    }
+    const bool act = lane < G::ACT;
+    const int c0 = cg0 + 2 * (act ? lane : 0);
+    const int hb = (lane / G::LPH) * G::LPH;
+    float2 bias = make_float2(0.f, 0.f), gt = make_float2(1.f, 1.f);
+    if (act) {
+        const float* wp; const float* bp; int wc;
+        crpe_of_channel(cw, c0, CH, wp, bp, wc);
+        bias.x = __ldg(bp);
+        crpe_of_channel(cw, c0 + 1, CH, wp, bp, wc);
+        bias.y = __ldg(bp);
+        if (gate) gt = *reinterpret_cast<const float2*>(gate + (size_t)b * C + c0);
+    }
+    __syncthreads();
+    const int nstrips = g.th * g.nsx;
+    for (int s = warp; s < nstrips; s += 8) {
+        const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
+        const size_t n0 = (size_t)(g.ty0 + py) * Wd + g.tx0 + px0;
+        uint32_t qw[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) qw[t] = (act && px0 + t < g.tw) ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + c0) : 0u;
+        float2 e[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) e[t] = bias;
+#pragma unroll 1
+        for (int i = 0; i < WIN; ++i) {
+            const uint32_t* row = sV + ((py + i) * g.PW + px0) * 32 + lane;
+            float2 in[TX + WIN - 1];
+#pragma unroll
+            for (int t = 0; t < TX + WIN - 1; ++t) in[t] = up2(row[t * 32]);
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) {
+                const float2 w = sW[(i * WIN + j) * 32 + lane];
+#pragma unroll
+                for (int t = 0; t < TX; ++t) e[t] = fma2(w, in[t + j], e[t]);
+            }
+        }
+        // Q.A per head: the (even k, odd k) halves of a packed accumulator are summed at the end, so the shuffled
+        // bf16x2 word (Q[2kk], Q[2kk+1]) is used as a packed operand directly
+        float2 f0[TX], f1[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) f0[t] = f1[t] = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int kk = 0; kk < CH / 2; ++kk) {
+            const float4 a = sA[kk * 32 + lane];
+            const float2 a0 = make_float2(a.x, a.y), a1 = make_float2(a.z, a.w);
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+                const float2 qq = up2(__shfl_sync(0xffffffffu, qw[t], hb + kk));
+                f0[t] = fma2(qq, a0, f0[t]);
+                f1[t] = fma2(qq, a1, f1[t]);
+            }
+        }
+        float2 fa[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) fa[t] = make_float2(f0[t].x + f0[t].y, f1[t].x + f1[t].y);
+        if (act) {
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+                if (px0 + t >= g.tw) break;
+                const float2 q = up2(qw[t]);
+                const float2 y = mul2(gt, fma2(splat(scale), fa[t], mul2(q, e[t])));
+                *reinterpret_cast<uint32_t*>(out + ((size_t)b * N + n0 + t) * C + c0) = f2_to_bf2(y.x, y.y);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// dQ = s dF.A^T + dF*E ; dK = S*(V.dA^T - r) ; dV = S.dA + convT(dE) ; dE = g dY Q ; dF = g dY            
+// dgate[b,c] += sum_n dY Y / g ;  dWconv[c,tap] += sum_n dE[n,c] V[n+tap,c] ;  dbconv[c] += sum_n dE[n,c]
+template <int CH, int WIN>
+__device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+                                                    const bf16* __restrict__ yout, const float* __restrict__ gate,
+                                                    const float* __restrict__ A, const float* __restrict__ dA,
+                                                    const float* __restrict__ rk, const float* __restrict__ kmax,
+                                                    const float* __restrict__ zsum, const CrpeW& cw, const CrpeG& cg,
+                                                    bf16* __restrict__ dqkv, float* __restrict__ dgate, float scale, int H,
+                                                    int Wd, int C, uint8_t* smem_s) {
+    using G = Cfg<CH>;
+    const int grp0 = 0;
+    uint32_t* sV = reinterpret_cast<uint32_t*>(smem_s);
+    uint32_t* sE = sV + tile_words(WIN);
+    float2* sW = reinterpret_cast<float2*>(sE + tile_words(WIN));
+    // per (j pair, lane): the two j-values of a matrix entry for each of the lane's two channels v0, v1
+    float4* sAt = reinterpret_cast<float4*>(sW + WIN * WIN * 32);   // (A[v0][2jj],  A[v0][2jj+1],  A[v1][2jj],  A[v1][2jj+1])
+    float4* sdA = sAt + (CH / 2) * 32;                               // (dA[2jj][v0], dA[2jj+1][v0], dA[2jj][v1], dA[2jj+1][v1])
+    float4* sdAt = sdA + (CH / 2) * 32;                              // (dA[v0][2jj], dA[v0][2jj+1], dA[v1][2jj], dA[v1][2jj+1])
+    float* sG = reinterpret_cast<float*>(sdAt + (CH / 2) * 32);      // [WIN*WIN + 1][64] conv weight / bias gradient accumulators
+    const int N = H * Wd;
+    const int b = blockIdx.z, cg0 = (blockIdx.y + grp0) * G::CPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TileGeom g = tile_geom(H, Wd, WIN);
+    const bf16* qkv_b = qkv + (size_t)b * N * 3 * C;
+    const bf16* dy_b = dy + (size_t)b * N * C;
+    const bool want_w = cg.w[0] != nullptr;
+    load_halo<G::ACT>(sV, qkv_b + 2 * C, 3 * C, cg0, g, H, Wd);
+    {   // dE = g * dY * Q at every halo position (loads batched: 2 x UB requests in flight per thread)
+        const int total = g.PH * g.PW * 8;
+        constexpr int UB = 4;
+        for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * UB) {
+            uint4 dv[UB], qv[UB];
+            bool ok[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int e = e0 + u * blockDim.x;
+                const int pos = e >> 3, part = e & 7;
+                const int py = pos / g.PW, px = pos - py * g.PW;
+                const int y = g.ty0 - g.R + py, x = g.tx0 - g.R + px;
+                ok[u] = e < total && part * 4 < G::ACT && y >= 0 && y < H && x >= 0 && x < Wd && px < g.tw + 2 * g.R;
+                dv[u] = qv[u] = make_uint4(0, 0, 0, 0);
+                if (ok[u]) {
+                    const size_t n = (size_t)y * Wd + x;
+                    dv[u] = *reinterpret_cast<const uint4*>(dy_b + n * C + cg0 + part * 8);
+                    qv[u] = *reinterpret_cast<const uint4*>(qkv_b + n * 3 * C + cg0 + part * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e >= total) continue;
+                const int cc = cg0 + (e & 7) * 8;
+                uint4 r = make_uint4(0, 0, 0, 0);
+                if (ok[u]) {
+                    const uint32_t d4[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, q4[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+                    uint32_t o4[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const float2 d = up2(d4[w]), q = up2(q4[w]);
+                        float2 gg = make_float2(1.f, 1.f);
+                        if (gate) gg = *reinterpret_cast<const float2*>(gate + (size_t)b * C + cc + 2 * w);
+                        o4[w] = f2_to_bf2(gg.x * d.x * q.x, gg.y * d.y * q.y);
+                    }
+                    r = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                }
+                *reinterpret_cast<uint4*>(sE + (e >> 3) * 32 + (e & 7) * 4) = r;
+            }
+        }
+    }
+    load_taps<CH, WIN>(sW, cw, cg0, G::ACT);
+    for (int e = threadIdx.x; e < (CH / 2) * 32; e += blockDim.x) {
+        const int jj = e >> 5, l = e & 31;
+        float4 at = make_float4(0.f, 0.f, 0.f, 0.f), da = at, dat = at;
+        if (l < G::ACT) {
+            const int c = cg0 + 2 * l, h = c / CH, v = c % CH;
+            const size_t hbase = ((size_t)b * C + h * CH) * CH;
+            const float2 a0 = *reinterpret_cast<const float2*>(A + hbase + (size_t)v * CH + 2 * jj);
+            const float2 a1 = *reinterpret_cast<const float2*>(A + hbase + (size_t)(v + 1) * CH + 2 * jj);
+            at = make_float4(a0.x, a0.y, a1.x, a1.y);
+            const float2 d0 = *reinterpret_cast<const float2*>(dA + hbase + (size_t)(2 * jj) * CH + v);
+            const float2 d1 = *reinterpret_cast<const float2*>(dA + hbase + (size_t)(2 * jj + 1) * CH + v);
+            da = make_float4(d0.x, d1.x, d0.y, d1.y);
+            const float2 t0 = *reinterpret_cast<const float2*>(dA + hbase + (size_t)v * CH + 2 * jj);
+            const float2 t1 = *reinterpret_cast<const float2*>(dA + hbase + (size_t)(v + 1) * CH + 2 * jj);
+            dat = make_float4(t0.x, t0.y, t1.x, t1.y);
+        }
+        sAt[e] = at;
+        sdA[e] = da;
+        sdAt[e] = dat;
+    }
+    if (want_w)
+        for (int e = threadIdx.x; e < (WIN * WIN + 1) * 64; e += blockDim.x) sG[e] = 0.f;
+    const bool act = lane < G::ACT;
+    const int c0 = cg0 + 2 * (act ? lane : 0);
+    const int hb = (lane / G::LPH) * G::LPH;
+    float2 bias = make_float2(0.f, 0.f), gt = make_float2(1.f, 1.f), km = make_float2(0.f, 0.f), zi = make_float2(0.f, 0.f),
+           rr = make_float2(0.f, 0.f);
+    if (act) {
+        const float* wp; const float* bp; int wc;
+        crpe_of_channel(cw, c0, CH, wp, bp, wc);
+        bias.x = __ldg(bp);
+        crpe_of_channel(cw, c0 + 1, CH, wp, bp, wc);
+        bias.y = __ldg(bp);
+        const size_t bc = (size_t)b * C + c0;
+        if (gate) gt = *reinterpret_cast<const float2*>(gate + bc);
+        km = *reinterpret_cast<const float2*>(kmax + bc);
+        const float2 z = *reinterpret_cast<const float2*>(zsum + bc);
+        zi = make_float2(1.f / z.x, 1.f / z.y);
+        rr = *reinterpret_cast<const float2*>(rk + bc);
+    }
+    __syncthreads();
+    const int nstrips = g.th * g.nsx;
+    float2 gacc = make_float2(0.f, 0.f);
+    // ---- pass A: activation gradients
+    for (int s = warp; s < nstrips; s += 8) {
+        const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
+        const size_t n0 = (size_t)(g.ty0 + py) * Wd + g.tx0 + px0;
+        // this strip's own pixels: issued before the convolution loops so their latency hides behind the math
+        uint32_t qw[TX], kw[TX], dw[TX], yw[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+            const bool ok = act && px0 + t < g.tw;
+            qw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + c0) : 0u;
+            kw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + C + c0) : 0u;
+            dw[t] = ok ? *reinterpret_cast<const uint32_t*>(dy_b + (n0 + t) * C + c0) : 0u;
+            yw[t] = (ok && gate) ? *reinterpret_cast<const uint32_t*>(yout + ((size_t)b * N + n0 + t) * C + c0) : 0u;
+        }
+        float2 e[TX], tc[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+            e[t] = bias;
+            tc[t] = make_float2(0.f, 0.f);
+        }
+#pragma unroll 1
+        for (int i = 0; i < WIN; ++i) {
+            const uint32_t* rowv = sV + ((py + i) * g.PW + px0) * 32 + lane;
+            const uint32_t* rowe = sE + ((py + i) * g.PW + px0) * 32 + lane;
+            float2 inv[TX + WIN - 1], ine[TX + WIN - 1];
+#pragma unroll
+            for (int t = 0; t < TX + WIN - 1; ++t) {
+                inv[t] = up2(rowv[t * 32]);
+                ine[t] = up2(rowe[t * 32]);
+            }
+#pragma unroll
+            for (int j = 0; j < WIN; ++j) {
+                const float2 w = sW[(i * WIN + j) * 32 + lane];
+                const float2 wf = sW[(WIN * WIN - 1 - (i * WIN + j)) * 32 + lane];   // transposed convolution: flipped taps
+#pragma unroll
+                for (int t = 0; t < TX; ++t) {
+                    e[t] = fma2(w, inv[t + j], e[t]);
+                    tc[t] = fma2(wf, ine[t + j], tc[t]);
+                }
+            }
+        }
+        uint32_t vw[TX];
+        float2 dF[TX], S[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+            const bool ok = act && px0 + t < g.tw;
+            vw[t] = sV[((py + g.R) * g.PW + px0 + g.R + t) * 32 + lane];
+            const float2 kk = up2(kw[t]), d = up2(dw[t]);
+            dF[t] = mul2(gt, d);
+            S[t] = ok ? make_float2(__expf(kk.x - km.x) * zi.x, __expf(kk.y - km.y) * zi.y) : make_float2(0.f, 0.f);
+            gacc = fma2(d, up2(yw[t]), gacc);
+        }
+        // three per-head mat-vecs, 4 pixels at a time (register pressure); packed accumulators hold the (even j, odd j)
+        // partial sums, so the shuffled pairs are used as packed operands without splatting
+#pragma unroll
+        for (int half = 0; half < TX / 4; ++half) {
+            float2 q0[4], q1[4], v0[4], v1[4], k0[4], k1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q0[u] = q1[u] = v0[u] = v1[u] = k0[u] = k1[u] = make_float2(0.f, 0.f);
+#pragma unroll 2
+            for (int jj = 0; jj < CH / 2; ++jj) {
+                const float4 at = sAt[jj * 32 + lane], da = sdA[jj * 32 + lane], dt = sdAt[jj * 32 + lane];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = half * 4 + u;
+                    const float2 f = shfl2(dF[t], hb + jj);
+                    const float2 ss = shfl2(S[t], hb + jj);
+                    const float2 vv = up2(__shfl_sync(0xffffffffu, vw[t], hb + jj));
+                    q0[u] = fma2(f, make_float2(at.x, at.y), q0[u]);
+                    q1[u] = fma2(f, make_float2(at.z, at.w), q1[u]);
+                    v0[u] = fma2(ss, make_float2(da.x, da.y), v0[u]);
+                    v1[u] = fma2(ss, make_float2(da.z, da.w), v1[u]);
+                    k0[u] = fma2(vv, make_float2(dt.x, dt.y), k0[u]);
+                    k1[u] = fma2(vv, make_float2(dt.z, dt.w), k1[u]);
+                }
+            }
+            if (act) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = half * 4 + u;
+                    if (px0 + t >= g.tw) break;
+                    const float2 sq = make_float2(q0[u].x + q0[u].y, q1[u].x + q1[u].y);
+                    const float2 sv = make_float2(v0[u].x + v0[u].y, v1[u].x + v1[u].y);
+                    const float2 sk = make_float2(k0[u].x + k0[u].y, k1[u].x + k1[u].y);
+                    const float2 dq = fma2(splat(scale), sq, mul2(dF[t], e[t]));
+                    const float2 dk = mul2(S[t], make_float2(sk.x - rr.x, sk.y - rr.y));
+                    const float2 dv = make_float2(sv.x + tc[t].x, sv.y + tc[t].y);
+                    bf16* drow = dqkv + ((size_t)b * N + n0 + t) * 3 * C + c0;
+                    *reinterpret_cast<uint32_t*>(drow) = f2_to_bf2(dq.x, dq.y);
+                    *reinterpret_cast<uint32_t*>(drow + C) = f2_to_bf2(dk.x, dk.y);
+                    *reinterpret_cast<uint32_t*>(drow + 2 * C) = f2_to_bf2(dv.x, dv.y);
+                }
+            }
+        }
+    }
+    if (gate && dgate && act) {
+        atomicAdd(dgate + (size_t)b * C + c0, gacc.x / gt.x);
+        atomicAdd(dgate + (size_t)b * C + c0 + 1, gacc.y / gt.y);
+    }
+    if (!want_w) return;   // block-uniform
+    // ---- pass B: convolution weight / bias gradients, one kernel row at a time (7 float2 accumulators live)
+#pragma unroll 1
+    for (int i = 0; i < WIN; ++i) {
+        float2 gw[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) gw[j] = make_float2(0.f, 0.f);
+        float2 gb = make_float2(0.f, 0.f);
+        for (int s = warp; s < nstrips; s += 8) {
+            const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
+            const uint32_t* rowv = sV + ((py + i) * g.PW + px0) * 32 + lane;
+            const uint32_t* ce = sE + ((py + g.R) * g.PW + px0 + g.R) * 32 + lane;
+            float2 inv[TX + WIN - 1], de[TX];
+#pragma unroll
+            for (int t = 0; t < TX + WIN - 1; ++t) inv[t] = up2(rowv[t * 32]);
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+                de[t] = (px0 + t < g.tw) ? up2(ce[t * 32]) : make_float2(0.f, 0.f);   // halo columns past the tile hold neighbours' dE
+                if (i == 0) {
+                    gb.x += de[t].x;
+                    gb.y += de[t].y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < WIN; ++j)
+#pragma unroll
+                for (int t = 0; t < TX; ++t) gw[j] = fma2(de[t], inv[t + j], gw[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+            atomicAdd(sG + (i * WIN + j) * 64 + 2 * lane, gw[j].x);
+            atomicAdd(sG + (i * WIN + j) * 64 + 2 * lane + 1, gw[j].y);
+        }
+        if (i == 0) {
+            atomicAdd(sG + WIN * WIN * 64 + 2 * lane, gb.x);
+            atomicAdd(sG + WIN * WIN * 64 + 2 * lane + 1, gb.y);
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < (WIN * WIN + 1) * G::CPW; o += blockDim.x) {
+        const int t = o / G::CPW, cl_ = o % G::CPW;
+        const float sum = sG[t * 64 + cl_];
+        const int c = cg0 + cl_;
+        const int h = c / CH;
+        const int grp = h < 2 ? 0 : (h < 5 ? 1 : 2);
+        const int cl = c - (grp == 0 ? 0 : (grp == 1 ? 2 * CH : 5 * CH));
+        const int wc = 3 + 2 * grp;
+        if (t < WIN * WIN) {
+            const int o2 = (WIN - wc) >> 1;
+            const int ii = t / WIN - o2, jj = t % WIN - o2;
+            if (ii >= 0 && ii < wc && jj >= 0 && jj < wc) atomicAdd(cg.w[grp] + (size_t)cl * wc * wc + ii * wc + jj, sum);
+        } else {
+            atomicAdd(cg.b[grp] + cl, sum);
+        }
+    }
+}
+
+// One launch covers every channel group; the window of a group (that of its last head) selects the instantiation.
+template <int CH>
+__device__ __forceinline__ int win_of_group(int grp) { return win_of_head(((grp + 1) * Cfg<CH>::CPW - 1) / CH); }
+
+template <int CH>
+__global__ void __launch_bounds__(256) attn_fwd_strip_kernel(const bf16* __restrict__ qkv, const float* __restrict__ A,
+                                                              const float* __restrict__ gate, CrpeW cw, bf16* __restrict__ out,
+                                                              float scale, int H, int Wd, int C) {
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    const int win = win_of_group<CH>(blockIdx.y);
+    if (win == 3) attn_fwd_strip_body<CH, 3>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_fwd_strip_body<CH, 5>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
+    else attn_fwd_strip_body<CH, 7>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) attn_bwd_strip_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+                                                              const bf16* __restrict__ yout, const float* __restrict__ gate,
+                                                              const float* __restrict__ A, const float* __restrict__ dA,
+                                                              const float* __restrict__ rk, const float* __restrict__ kmax,
+                                                              const float* __restrict__ zsum, CrpeW cw, CrpeG cg,
+                                                              bf16* __restrict__ dqkv, float* __restrict__ dgate, float scale, int H,
+                                                              int Wd, int C) {
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    const int win = win_of_group<CH>(blockIdx.y);
+    if (win == 3) attn_bwd_strip_body<CH, 3>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_bwd_strip_body<CH, 5>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    else attn_bwd_strip_body<CH, 7>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <typename K>
+int set_smem(K kernel, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e == cudaSuccess ? MDV_OK : (int)e;
+}
+
+inline dim3 tile_grid(int B, int H, int W, int groups) {
+    const int TH = H < TILE_H ? H : TILE_H, TW = W < TILE_W ? W : TILE_W;
+    return dim3(mdv_cdiv(H, TH) * mdv_cdiv(W, TW), groups, B);
+}
+
+template <int CH>
+int launch_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& cw, bf16* out, float scale, int B, int H, int W, int C,
+               cudaStream_t st) {
+    const int smem = tile_words(7) * 4 + 49 * 32 * 8 + CH * 32 * 8;     // sized for the widest window
+    static bool configured = false;
+    if (!configured) {
+        int rc = set_smem(attn_fwd_strip_kernel<CH>, smem);
+        if (rc) return rc;
+        configured = true;
+    }
+    attn_fwd_strip_kernel<CH><<<tile_grid(B, H, W, C / Cfg<CH>::CPW), 256, smem, st>>>(qkv, A, gate, cw, out, scale, H, W, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+template <int CH>
+int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* A, const float* dA, const float* rk,
+               const float* kmax, const float* zsum, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B,
+               int H, int W, int C, cudaStream_t st) {
+    const int smem = 2 * tile_words(7) * 4 + 49 * 32 * 8 + 3 * CH * 32 * 8 + 50 * 64 * 4;
+    static bool configured = false;
+    if (!configured) {
+        int rc = set_smem(attn_bwd_strip_kernel<CH>, smem);
+        if (rc) return rc;
+        configured = true;
+    }
+    attn_bwd_strip_kernel<CH><<<tile_grid(B, H, W, C / Cfg<CH>::CPW), 256, smem, st>>>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv,
+                                                                                       dgate, scale, H, W, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+int chunks_for(int B, int N, int blocks_y) {
+    int want = mdv_cdiv(4 * MDV_NUM_SMS, B * blocks_y);
+    const int maxc = N / 64 > 0 ? N / 64 : 1;
+    if (want > maxc) want = maxc;
+    if (want > 64) want = 64;
+    return want < 1 ? 1 : want;
+}
+
+template <int CH, int MODE>
+int launch_outer(const bf16* qkv, const bf16* dy, const float* gate, const float* kmax, float* part, float* zpart, int B, int N, int C,
+                 int& nchunk, cudaStream_t st) {
+    using G = Cfg<CH>;
+    const int by = (C / G::CPW) * G::KSPLIT;
+    nchunk = chunks_for(B, N, by);
+    int rpb = mdv_cdiv(N, nchunk);
+    rpb = ((rpb + 31) / 32) * 32;
+    nchunk = mdv_cdiv(N, rpb);
+    attn_outer_kernel<CH, MODE><<<dim3(nchunk, by, B), 256, 0, st>>>(qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+template <int CH>
+int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out, float scale,
+             int B, int H, int W, int C, cudaStream_t st) {
+    const int N = H * W;
+    int nchunk = 0;
+    float* part = ws;
+    // zpart sits behind the largest possible partial buffer of this shape
+    float* zpart = ws + (size_t)B * 64 * C * CH;
+    int rc = launch_outer<CH, 0>(qkv, nullptr, nullptr, kmax, part, zpart, B, N, C, nchunk, st);
+    if (rc) return rc;
+    const long long tot = (long long)B * C * CH;
+    attn_combine_fwd_kernel<<<mdv_cdiv(tot, 256), 256, 0, st>>>(part, zpart, A, zsum, C, CH, nchunk, tot);
+    MDV_CHECK_LAUNCH();
+    return launch_fwd<CH>(qkv, A, gate, cw, out, scale, B, H, W, C, st);
+}
+
+template <int CH>
+int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum, const float* A,
+             float* ws, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B, int H, int W, int C,
+             cudaStream_t st) {
+    const int N = H * W;
+    int nchunk = 0;
+    float* part = ws;
+    float* dA = ws + (size_t)B * 64 * C * CH + (size_t)B * 64 * C;
+    float* rk = dA + (size_t)B * C * CH;
+    int rc = launch_outer<CH, 1>(qkv, dy, gate, nullptr, part, nullptr, B, N, C, nchunk, st);
+    if (rc) return rc;
+    attn_combine_bwd_kernel<<<mdv_cdiv(B * C, 8), 256, 0, st>>>(part, A, dA, rk, scale, C, CH, nchunk, B * C);
+    MDV_CHECK_LAUNCH();
+    return launch_bwd<CH>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+}
+
+}  // namespace
+
+// scratch floats needed by attn_strip_fwd / attn_strip_bwd: partial sums (<= 64 chunks) + zpart + dA + rk
+long long attn_strip_ws_floats(int B, int C, int Ch) {
+    return (long long)B * 64 * C * Ch + (long long)B * 64 * C + (long long)B * C * Ch + (long long)B * C;
+}
+
+int attn_strip_fwd(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out,
+                   float scale, int B, int H, int W, int C, int Ch, cudaStream_t st) {
+    switch (Ch) {
+        case 8: return fwd_impl<8>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
+        case 16: return fwd_impl<16>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
+        case 40: return fwd_impl<40>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
+        case 64: return fwd_impl<64>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
+        default: return MDV_ERR_UNSUPPORTED;
+    }
+}
+
+int attn_strip_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum,
+                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B, int H, int W,
+                   int C, int Ch, cudaStream_t st) {
+    switch (Ch) {
+        case 8: return bwd_impl<8>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+        case 16: return bwd_impl<16>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+        case 40: return bwd_impl<40>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+        case 64: return bwd_impl<64>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+        default: return MDV_ERR_UNSUPPORTED;
+    }
+}

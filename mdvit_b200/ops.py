@@ -286,9 +286,10 @@ class BlockFn(torch.autograd.Function):
                 check(lib.mdv_da_gate_fwd(ptr(label), ptr(da_w1), ptr(da_b1), ptr(da_w2), ptr(da_b2), ptr(hid), ptr(gate), B, nd, hd,
                                           C, HEADS, L.stream()), "mdv_da_gate_fwd")
             stats = torch.empty(lib.mdv_attn_stats_floats(B, C, HEADS), dtype=F32, device=dev)
+            ws = torch.empty(lib.mdv_attn_ws_floats(B, C, HEADS), dtype=F32, device=dev)
             y = torch.empty((M, C), dtype=BF16, device=dev)
-            check(lib.mdv_attn_fwd(ptr(qkv), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b), ptr(stats), ptr(y),
-                                   B, H, W, C, HEADS, L.stream()), "mdv_attn_fwd")
+            check(lib.mdv_attn_fwd(ptr(qkv), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b), ptr(stats), ptr(ws),
+                                   ptr(y), B, H, W, C, HEADS, L.stream()), "mdv_attn_fwd")
             p_drop = drop if training else 0.0
             sid = [new_stream_id() for _ in range(5)] if training and (drop > 0 or dpr > 0) else [0] * 5
             dp1 = dp2 = None
@@ -349,7 +350,7 @@ class BlockFn(torch.autograd.Function):
             Ch = C // HEADS
             da_live = gate is not None and da_w1.requires_grad and da_w2.requires_grad
             dgate = torch.zeros((B, C), dtype=F32, device=dev) if gate is not None else None
-            ws = torch.empty(B * C * (2 * Ch + 1), dtype=F32, device=dev)
+            ws = torch.empty(lib.mdv_attn_ws_floats(B, C, HEADS), dtype=F32, device=dev)
             check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
                                    ptr(stats), ptr(dqkv), ptr(dgate), ptr(G["c3w"]), ptr(G["c3b"]), ptr(G["c5w"]), ptr(G["c5b"]),
                                    ptr(G["c7w"]), ptr(G["c7b"]), ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")

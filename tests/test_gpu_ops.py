@@ -394,7 +394,8 @@ def test_da_gate_fwd_bwd(env):
 
 # ------------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,H,W,C,sup", [(2, 16, 16, 64, True), (2, 8, 8, 128, True), (2, 4, 4, 320, True), (2, 2, 2, 512, True),
-                                         (3, 12, 20, 64, True), (1, 40, 24, 128, False), (2, 16, 16, 320, True), (2, 8, 8, 512, False)])
+                                         (3, 12, 20, 64, True), (1, 40, 24, 128, False), (2, 16, 16, 320, True), (2, 8, 8, 512, False),
+                                         (2, 64, 64, 64, True), (1, 32, 32, 128, True), (1, 20, 36, 320, True), (1, 17, 9, 512, True)])
 def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
     L, lib, dev = env
     from oracle import mdvit_oracle as O
@@ -416,16 +417,19 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
         fa = gref.reshape(B, 8, 1, Ch) * fa                                           # mdvit.py:304
     yref = fa.transpose(1, 2).reshape(B, N, C)
     stats = torch.empty(lib.mdv_attn_stats_floats(B, C, 8), device=dev)
+    ws = torch.empty(lib.mdv_attn_ws_floats(B, C, 8), device=dev)
     y = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
     cw = [sd[f"crpe.conv_list.{i}.{n}"].detach() for i in range(3) for n in ("weight", "bias")]
-    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(y), B, H, W, C, 8, L.stream()), "attn_fwd")
+    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(ws), P(y), B, H, W, C, 8, L.stream()), "attn_fwd")
     assert rel(y, yref) < BF16_TOL
+    y2 = torch.empty_like(y)                       # no atomics in the forward: bit-reproducible
+    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(ws), P(y2), B, H, W, C, 8, L.stream()), "attn_fwd")
+    assert torch.equal(y, y2)
     dy = torch.randn(B, N, C, device=dev).bfloat16()
     yref.backward(dy.float())
     dqkv = torch.empty_like(qkv)
     dgate = torch.zeros(B, C, device=dev) if sup else None
     gcw = [torch.zeros_like(t_) for t_ in cw]
-    ws = torch.empty(B * C * (2 * Ch + 1), device=dev)
     L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv), P(dgate), *[P(t_) for t_ in gcw], P(ws),
                              B, H, W, C, 8, L.stream()), "attn_bwd")
     g = q32.grad
@@ -436,3 +440,8 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
         assert rel(gcw[2 * i + 1], sd[f"crpe.conv_list.{i}.bias"].grad) < BF16_TOL
     if sup:
         assert rel(dgate, gref.grad) < BF16_TOL
+        # activation-gradient-only mode (CRPE gradient pointers NULL): same dqkv, dgate still accumulated
+        dqkv2, dgate2 = torch.empty_like(qkv), torch.zeros(B, C, device=dev)
+        L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv2), P(dgate2), None, None, None, None,
+                                 None, None, P(ws), B, H, W, C, 8, L.stream()), "attn_bwd")
+        assert torch.equal(dqkv2, dqkv) and rel(dgate2, gref.grad) < BF16_TOL
