@@ -235,6 +235,40 @@ def wgrad_on():
     return _BWD_MODE == "all"
 
 
+# Data-parallel bookkeeping hooks (train_step.GradBucketer).  Every Function remembers the tag that was current during
+# its forward (the trainer tags each domain's forward) and reports the parameters it has just finished accumulating
+# gradients for at the end of its backward, so the trainer can all-reduce a gradient bucket as soon as it is final.
+_FWD_TAG = None
+_FWD_USE_CB = None
+_GRAD_READY_CB = None
+
+
+def set_forward_tag(tag):
+    global _FWD_TAG
+    _FWD_TAG = tag
+
+
+def set_forward_use_cb(cb):
+    global _FWD_USE_CB
+    _FWD_USE_CB = cb
+
+
+def set_grad_ready_cb(cb):
+    global _GRAD_READY_CB
+    _GRAD_READY_CB = cb
+
+
+def _fwd_mark(ctx):
+    ctx.tag = _FWD_TAG
+    if _FWD_USE_CB is not None:
+        _FWD_USE_CB(_FWD_TAG, ctx.params)
+
+
+def _grads_done(ctx):
+    if _GRAD_READY_CB is not None:
+        _GRAD_READY_CB(ctx.tag, ctx.params)
+
+
 def gtarget(p, shape=None, da=False):
     """Where a parameter gradient is accumulated.  Returns (buffer, value_to_return_from_backward).
 
@@ -314,6 +348,7 @@ class BlockFn(torch.autograd.Function):
         ctx.params = (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2,
                       n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         ctx.meta = (B, N, C, H, W, hidden, p_drop, sid)
+        _fwd_mark(ctx)
         return x3
 
     @staticmethod
@@ -367,6 +402,7 @@ class BlockFn(torch.autograd.Function):
             # ---- ConvPosEnc
             dx = dwconv3(dx1, cpe_w, None, B, H, W, H, W, C, 1, transposed=True, residual=True)
             dwconv3_wgrad(dx1, x, G["cpe_w"], G["cpe_b"], B, H, W, H, W, C, 1)
+        _grads_done(ctx)
         R = [T[n][1] for n in ("cpe_w", "cpe_b", "c3w", "c3b", "c5w", "c5b", "c7w", "c7b", "n1w", "n1b", "qkv_w", "qkv_b", "proj_w",
                                "proj_b", "da_w1", "da_b1", "da_w2", "da_b2", "n2w", "n2b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
         return (dx.view(B, N, C), None, *R, None, None, None, None, None)
@@ -403,6 +439,7 @@ class StemFn(torch.autograd.Function):
         ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
         ctx.params = (w0, g0, b0, w1, g1, b1)
         ctx.meta = (B, H1, W1, H2, W2, training)
+        _fwd_mark(ctx)
         ctx.set_materialize_grads(False)
         return y.view(B, H2 * W2, 64)
 
@@ -433,6 +470,7 @@ class StemFn(torch.autograd.Function):
             if gw0 is not None:
                 gw0p = gemm_tn(dz0, col0, M0, 32, 64, torch.zeros((32, 64), dtype=F32, device=dev))
                 check(lib.mdv_unperm_conv_grad(ptr(gw0p), 64, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
+        _grads_done(ctx)
         return None, rw0, rg0, rb0, rw1, rg1, rb1, None, None
 
 
@@ -455,6 +493,7 @@ class PatchEmbedFn(torch.autograd.Function):
         ctx.save_for_backward(x, t, z, mean, rstd)
         ctx.params = (dw_w, pw_w, g, b)
         ctx.meta = (B, Hi, Wi, Ho, Wo, Cin, C, stride, training)
+        _fwd_mark(ctx)
         ctx.after_stem = after_stem
         return y.view(B, Ho * Wo, C)
 
@@ -479,6 +518,7 @@ class PatchEmbedFn(torch.autograd.Function):
             dx = dwconv3(dt, dw_w, None, B, Ho, Wo, Hi, Wi, Cin, stride, transposed=True)
             g_dw, r_dw = gtarget(dw_w)
             dwconv3_wgrad(dt, x, g_dw, None, B, Hi, Wi, Ho, Wo, Cin, stride)
+        _grads_done(ctx)
         return dx.view(B, Hi * Wi, Cin), r_dw, r_pw, rg, rb, None, None, None, None, None, None
 
 
@@ -507,6 +547,7 @@ class BridgeFn(torch.autograd.Function):
         ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
         ctx.params = (w0, c0, g0, b0, w1, c1, g1, b1)
         ctx.meta = (B, H, W, C, C0, C1, training)
+        _fwd_mark(ctx)
         return y.view(B, H * W, C1)
 
     @staticmethod
@@ -538,6 +579,7 @@ class BridgeFn(torch.autograd.Function):
             rw1, rc1, da0 = conv_bwd(dz1, col1, w1, c1, C1, C0)
             dz0, rg0, rb0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_RELU, M, C0)
             rw0, rc0, dx = conv_bwd(dz0, col0, w0, c0, C0, C)
+        _grads_done(ctx)
         return dx.view(B, H * W, C), rw0, rc0, rg0, rb0, rw1, rc1, rg1, rb1, None, None, None, None
 
 
@@ -566,6 +608,7 @@ class DecoderConvFn(torch.autograd.Function):
         ctx.save_for_backward(skip, a, up, gc, z, mean, rstd)
         ctx.params = (cb_w, cb_b, dw_w, pw_w, g, b)
         ctx.meta = (B, h, w, H, W, Cin, C, training)
+        _fwd_mark(ctx)
         return y.view(B, H * W, C)
 
     @staticmethod
@@ -597,6 +640,7 @@ class DecoderConvFn(torch.autograd.Function):
             colsum(dt, m, C, g_cbb)
             dinp = torch.empty((m, Cin), dtype=F32, device=dev)
             gemm_nt(dtb, prep_weight(cb_w, 1, C, Cin), m, Cin, C, dinp)
+        _grads_done(ctx)
         return (dinp.view(B, h * w, Cin), dskip.view(B, H * W, C), r_cb, r_cbb, r_dw, r_pw, rg, rb, None, None, None, None, None, None)
 
 
@@ -617,6 +661,7 @@ class HeadFn(torch.autograd.Function):
         ctx.save_for_backward(x)
         ctx.params = (w, b)
         ctx.meta = (B, C, H, W, Ho, Wo)
+        _fwd_mark(ctx)
         return out
 
     @staticmethod
@@ -634,6 +679,7 @@ class HeadFn(torch.autograd.Function):
             db, rb = gtarget(b)
             check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(x), 0, ptr(w), ptr(dx), ptr(dw), ptr(db), B * H * W, C, H * W, ctypes.c_float(0.0),
                                      None, 0, L.stream()), "mdv_rowdot_bwd")
+        _grads_done(ctx)
         return dx, rw, rb, None, None, None, None
 
 
@@ -683,6 +729,7 @@ class AuxFn(torch.autograd.Function):
         ctx.save_for_backward(cat, z, mean, rstd, a5, *acts)
         ctx.params = (l1w, l1b, l2w, l2b, l3w, l3b, l4w, l4b, fw, fb, g, b, ow, ob)
         ctx.meta = (B, sizes, Ho, Wo, hc, K, C5, p2, sid, training, [t.shape[2] for t in xs])
+        _fwd_mark(ctx)
         return out
 
     @staticmethod
@@ -733,6 +780,7 @@ class AuxFn(torch.autograd.Function):
                 rbs.append(r_b)
             dx5 = torch.empty((B, H * W, C5), dtype=F32, device=dev)
             check(lib.mdv_add_f32(ptr(dcat[:, 4 * hc:]), 1, K, ptr(dx5), C5, M0, C5, 0, L.stream()), "mdv_add_f32")
+        _grads_done(ctx)
         return (gx[0], gx[1], gx[2], gx[3], dx5, rw[0], rbs[0], rw[1], rbs[1], rw[2], rbs[2], rw[3], rbs[3], r_fw, r_fb, rg, rb, r_ow,
                 r_ob, None, None, None, None, None, None)
 

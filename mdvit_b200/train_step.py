@@ -31,9 +31,101 @@ def _align(n, a=4):
     return (n + a - 1) // a * a
 
 
+class GradBucketer:
+    """Overlaps the data-parallel gradient all-reduce with the backward pass (replaces nn.DataParallel's gather/reduce,
+    multi_train_MDViT.py:73-74; the stock DDP reducer cannot be used because the MKD step back-propagates one graph twice).
+
+    The flat fp32 gradient buffer is cut into `n_buckets` contiguous ranges.  Every parameter receives contributions
+    from all domain graphs; autograd runs the graph of the domain that was forwarded FIRST last, so a parameter is final
+    once the Functions of that domain (tag `last_tag`) have reported it as many times as they use it (`uses`, recorded
+    during one forward: 2 for the CPE/CRPE shared by a stage's two blocks, 0 for the other domains' aux decoders).  When
+    the last parameter of a bucket is final the bucket is all-reduced on a side stream behind an event, so NCCL runs
+    under the remaining backward kernels.  Device-agnostic (CPU tensors + gloo in the tests)."""
+
+    def __init__(self, flat_grad, param_ranges, n_buckets=8, group=None, comm_stream=None):
+        self.flat, self.group, self.comm = flat_grad, group, comm_stream
+        total = flat_grad.numel()
+        n_buckets = max(1, min(n_buckets, len(param_ranges)))
+        target = (total + n_buckets - 1) // n_buckets
+        self.bucket_of, self.bounds = {}, []
+        lo, cur = 0, 0
+        for i, (key, (o, n)) in enumerate(param_ranges.items()):
+            self.bucket_of[key] = len(self.bounds)
+            cur = o + n
+            if cur - lo >= target or i == len(param_ranges) - 1:
+                hi = total if i == len(param_ranges) - 1 else _align(cur)
+                self.bounds.append((lo, hi))
+                lo = hi
+        self.uses = None            # key -> number of reports expected from the last-run domain graph
+        self.reduced = []           # bucket ids in the order they were reduced (inspected by the tests)
+
+    # -- one-time recording of how often each parameter is used by the first-forwarded domain
+    def record_use(self, keys):
+        if self.uses is None:
+            self.uses = {}
+        for k in keys:
+            if k in self.bucket_of:
+                self.uses[k] = self.uses.get(k, 0) + 1
+
+    def begin(self):
+        assert self.uses is not None, "record_use() must run during one forward first"
+        self._left = {k: self.uses.get(k, 0) for k in self.bucket_of}
+        self._bucket_left = [0] * len(self.bounds)
+        for k, b in self.bucket_of.items():
+            if self._left[k] > 0:
+                self._bucket_left[b] += 1
+        self._started = False
+        self.reduced = []
+
+    def _start(self):
+        self._started = True
+        for b, left in enumerate(self._bucket_left):      # buckets owned entirely by other domains' graphs: already final
+            if left == 0:
+                self._reduce(b)
+
+    def report(self, keys):
+        """Parameters `keys` have received their gradient from one Function of the last-run domain graph."""
+        if not self._started:
+            self._start()
+        for k in keys:
+            left = self._left.get(k, 0)
+            if left <= 0:
+                continue
+            self._left[k] = left - 1
+            if left == 1:
+                b = self.bucket_of[k]
+                self._bucket_left[b] -= 1
+                if self._bucket_left[b] == 0:
+                    self._reduce(b)
+
+    def _reduce(self, b):
+        if b in self.reduced:
+            return
+        self.reduced.append(b)
+        lo, hi = self.bounds[b]
+        view = self.flat[lo:hi]
+        if self.comm is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self):
+        """Reduce whatever has not been reported final (defensive) and join the side stream."""
+        if not self._started:
+            self._start()
+        for b in range(len(self.bounds)):
+            self._reduce(b)
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+
+
 class MKDTrainer:
     def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, process_group=None,
-                 num_domains=4, with_aux=True, schedule="single_sweep"):
+                 num_domains=4, with_aux=True, schedule="single_sweep", n_buckets=8):
         if schedule not in ("single_sweep", "reference"):
             raise ValueError("schedule must be 'single_sweep' or 'reference'")
         self.schedule = schedule
@@ -73,6 +165,11 @@ class MKDTrainer:
         self.da_params = [p for n, p in model.named_parameters() if "domain_layer" in n]
         ops.bump_weight_epoch()
         self._graph = None
+        self.bucketer = None
+        if self.world > 1:
+            ranges = {id(p): (o, p.numel()) for p, o in zip(params, offs)}
+            self.comm_stream = torch.cuda.Stream(device=dev)
+            self.bucketer = GradBucketer(self.grad, ranges, n_buckets=n_buckets, group=process_group, comm_stream=self.comm_stream)
 
     # ------------------------------------------------------------------ pieces
     def _reduce_sums(self, sums):
@@ -81,7 +178,13 @@ class MKDTrainer:
     def forward_losses(self, batches):
         """batches: list of (img [B,3,H,W], label [B,1,H,W], domain index).  Returns [n_dom, 3] losses (seg, aux, kt)."""
         out = []
-        for img, label, d in batches:
+        recording = self.bucketer is not None and self.bucketer.uses is None
+        for i, (img, label, d) in enumerate(batches):
+            ops.set_forward_tag(i)
+            if recording and i == 0:
+                ops.set_forward_use_cb(lambda tag, params: self.bucketer.record_use([id(p) for p in params if p is not None]))
+            elif recording:
+                ops.set_forward_use_cb(None)
             B = img.shape[0]
             dl = torch.zeros((B, self.num_domains), dtype=torch.float32, device=img.device)
             dl[:, int(d)] = 1.0
@@ -91,7 +194,23 @@ class MKDTrainer:
                 o, a = self.model(img), None
             n_total = o.numel() * self.world
             out.append(ops.seg_losses(o, a, label, n_total=n_total, reduce_sums=self._reduce_sums if self.world > 1 else None))
+        ops.set_forward_use_cb(None)
+        ops.set_forward_tag(None)
         return torch.stack(out)
+
+    def _final_backward(self, loss):
+        """The last backward call of the step: gradients become final bucket by bucket and are all-reduced as they do."""
+        if self.bucketer is None:
+            loss.backward()
+            return
+        bk = self.bucketer
+        bk.begin()
+        ops.set_grad_ready_cb(lambda tag, params: bk.report([id(p) for p in params if p is not None]) if tag == 0 else None)
+        try:
+            loss.backward()
+        finally:
+            ops.set_grad_ready_cb(None)
+        bk.finish()
 
     def backward(self, losses):
         """multi_train_MDViT.py:195-207: aux pass with DA frozen (retain_graph), then alpha*kt + (1-alpha)*seg."""
@@ -102,15 +221,15 @@ class MKDTrainer:
             aux.backward(retain_graph=True)
             for p in self.da_params:
                 p.requires_grad = True
-            (self.alpha * kt + (1.0 - self.alpha) * seg).backward()
+            self._final_backward(self.alpha * kt + (1.0 - self.alpha) * seg)
         elif self.with_aux:
             main = self.alpha * kt + (1.0 - self.alpha) * seg
             if self.da_params:
                 with ops.backward_mode("da_only"):
                     (-aux).backward(retain_graph=True)
-            (aux + main).backward()
+            self._final_backward(aux + main)
         else:
-            seg.backward()
+            self._final_backward(seg)
 
     def _set_hyper(self):
         self.t += 1
@@ -121,8 +240,7 @@ class MKDTrainer:
         self.hyper.copy_(h, non_blocking=True)
 
     def optimizer_step(self):
-        if self.world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        # (gradients were all-reduced bucket by bucket during the last backward call, see GradBucketer)
         with torch.cuda.device(self.device):
             check(L.lib().mdv_adamw(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.hyper), self.total, L.stream()),
                   "mdv_adamw")

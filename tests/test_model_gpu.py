@@ -246,3 +246,17 @@ def test_base_model_without_adapter(dev):
     l = ops.seg_losses(out, None, lab.to(dev))
     l[0].backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all().item() for p in m.parameters())
+
+
+def test_data_parallel_two_gpus_nccl(dev):
+    """One process per GPU over NCCL (skipped on a 1-GPU box): scripts/dp_check.py asserts overlapped == single all-reduce,
+    global-batch losses identical on all ranks, replicas in sync after AdamW, and the graph-captured step with NCCL inside."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "scripts", "dp_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("DP_OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]

@@ -63,3 +63,23 @@ def test_unsupported_configs_fail_loudly():
         MDViT(decoder_name="DeepLabV3")
     with pytest.raises(ValueError):
         MDViT(num_heads=[4, 4, 4, 4])
+
+
+def test_dropin_package_resolves_reference_import_paths():
+    """`from Models.Transformer.mdvit import MDViT` (multi_train_MDViT.py:58) / `...base import BASE` (multi_train_BASE.py:67)
+    resolve to this implementation when <repo>/dropin precedes the reference checkout on sys.path."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        for name in [m for m in sys.modules if m == "Models" or m.startswith("Models.")]:
+            del sys.modules[name]
+        mod = importlib.import_module("Models.Transformer.mdvit")
+        assert mod.MDViT is MDViT
+        assert importlib.import_module("Models.Transformer.base").BASE is BASE
+    finally:
+        sys.path.remove(os.path.join(root, "dropin"))
+        for name in [m for m in sys.modules if m == "Models" or m.startswith("Models.")]:
+            del sys.modules[name]
