@@ -24,6 +24,7 @@ METRIC = "mdvit_train_images_per_sec"
 UNIT = "images/s"
 IMG = 256
 F_TRAIN_GFLOP_PER_IMG = 62.3     # 3 x 20.77 GFLOP algorithmic fwd+bwd per image
+LINEAR_FUSE_DRAM_BYTES = 789904384    # 556.36 MB read + 233.54 MB write per launch (profiles/r1_ncu_gemm_linear_fuse.txt)
 
 
 def parse():
@@ -133,9 +134,11 @@ def run_reference(args):
     if rank != 0:
         return
     bpd = args.cpu_batch_per_domain
-    sec, cores = cpu_oracle_step_time(bpd, args.steps, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 12))          # ~6 s of CPU work per 4-image step: keep the whole arm within ~2 minutes
+    sec, cores = cpu_oracle_step_time(bpd, steps, min(args.warmup, 1))
     val = 4 * bpd / sec
-    sample = f"{4 * bpd} images/step ({bpd}/domain x 4 domains) at {IMG}x{IMG}, fp32, dropout on, {args.steps} steps"
+    sample = f"{4 * bpd} images/step ({bpd}/domain x 4 domains) at {IMG}x{IMG}, fp32, dropout on, {steps} timed steps"
+    args.steps = steps
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -176,8 +179,10 @@ def kernel_roofline(peaks, device):
     achieved = 2.0 * M * N * K / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
     return {"bound": "tensor", "kernel": "gemm_kernel<BN,NT> (tcgen05) @ linear_fuse M=131072 N=512 K=2112", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (burst)",
-            "ms_per_launch": ms}
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": LINEAR_FUSE_DRAM_BYTES,
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_gemm_linear_fuse.txt",
+            "algorithmic_flops_per_launch": 2.0 * M * N * K, "algorithmic_bytes_per_launch": (M * K + N * K) * 2 + M * N * 4,
+            "peak_source": peaks["source"] + " (burst)", "ms_per_launch": ms}
 
 
 def main():
@@ -253,7 +258,12 @@ def main():
     if rank == 0:
         sampler.start()
     n0 = lib.mdv_launch_count()
+    ncu_range = bool(int(os.environ.get("MDV_NCU_RANGE", "0")))     # `ncu --profile-from-start off`: capture exactly the timed steps
+    if ncu_range:
+        torch.cuda.profiler.start()
     ms_res, _ = timed(step_resident, args.steps, False)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     n1 = lib.mdv_launch_count()
     ms_e2e, loss_host = timed(step_e2e, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None

@@ -29,6 +29,8 @@ def make(M, N, K, kind):
         e.out, e.ldc, e.out_bf16, e.mul_gelu_grad, e.ld_mul, e.colsum = L.ptr(out), N, 1, L.ptr(u), N, L.ptr(cs)
         e.dropout_p, e.rng, e.drop_stream = 0.1, L.ptr(rng), 3
         keep += [u, cs]
+    elif kind == "lf":     # MLPDecoderFM.linear_fuse forward: bias, fp32 out
+        out = torch.empty(M, N, device=dev); e.out, e.ldc, e.out_bf16, e.bias = L.ptr(out), N, 0, L.ptr(bias)
     elif kind == "res":
         out = torch.empty(M, N, device=dev); res = torch.randn(M, N, device=dev)
         e.out, e.ldc, e.out_bf16, e.bias, e.residual, e.ld_res = L.ptr(out), N, 0, L.ptr(bias), L.ptr(res), N
@@ -47,7 +49,7 @@ def bench(fn, n=20):
     t.record(); torch.cuda.synchronize()
     return s.elapsed_time(t) / n * 1e3
 
-cases = [(131072, 512, 64, k) for k in ("plain", "fc1_nodrop", "fc1", "fc2d")] + [(131072, 64, 512, "res"), (32768, 1024, 128, "fc1"), (32768, 1024, 128, "fc2d")]
+cases = [(131072, 512, 64, k) for k in ("plain", "fc1_nodrop", "fc1", "fc2d")] + [(131072, 64, 512, "res"), (32768, 1024, 128, "fc1"), (32768, 1024, 128, "fc2d"), (131072, 512, 2112, "lf")]
 if os.environ.get("ONE"):
     M, N, K, kind = cases[int(os.environ["ONE"])]
     fn, keep = make(M, N, K, kind)
