@@ -79,6 +79,111 @@ __global__ void __launch_bounds__(256) dwconv3_kernel(const float* __restrict__ 
     }
 }
 
+// Stride-1 fast path (ConvPosEnc forward and backward, first patch embedding).  An image row of an NHWC tensor is one
+// contiguous vector of W*C floats and a horizontal shift is +-C floats, so a thread owns 4 consecutive floats of the row
+// (4 channels of one pixel) and walks down a segment of rows with a 3-row sliding window in registers: 3 coalesced
+// 16-byte loads per output instead of 9, weights in registers, no per-element index arithmetic.
+// flip = 1 gives the transposed convolution (input gradient): same stencil with the taps reversed.
+struct Row3 {
+    float4 l, m, r;
+};
+__device__ __forceinline__ Row3 load_row3(const float* __restrict__ row, int p, int C, bool ok, bool left_ok, bool right_ok) {
+    Row3 t;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    t.m = ok ? ld4(row + p) : z;
+    t.l = (ok && left_ok) ? ld4(row + p - C) : z;
+    t.r = (ok && right_ok) ? ld4(row + p + C) : z;
+    return t;
+}
+template <typename TO>
+__global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, TO* __restrict__ out, int H, int W, int C,
+                                                          int flip, int residual, int seg) {
+    const int L = W * C;
+    const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (p >= L) return;
+    const int c = p % C, x = p / C;
+    const bool left_ok = x > 0, right_ok = x < W - 1;
+    float4 wv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int tt = flip ? 8 - t : t;
+        wv[t] = make_float4(__ldg(w + (c + 0) * 9 + tt), __ldg(w + (c + 1) * 9 + tt), __ldg(w + (c + 2) * 9 + tt), __ldg(w + (c + 3) * 9 + tt));
+    }
+    const float4 bv = bias ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int y0 = blockIdx.y * seg, y1 = min(H, y0 + seg);
+    const float* img = in + (size_t)blockIdx.z * H * L;
+    TO* oimg = out + (size_t)blockIdx.z * H * L;
+    Row3 r0 = load_row3(img + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
+    Row3 r1 = load_row3(img + (size_t)y0 * L, p, C, true, left_ok, right_ok);
+    for (int y = y0; y < y1; ++y) {
+        const Row3 r2 = load_row3(img + (size_t)(y + 1) * L, p, C, y + 1 < H, left_ok, right_ok);
+        float4 acc = bv;
+        fma4(acc, wv[0], r0.l); fma4(acc, wv[1], r0.m); fma4(acc, wv[2], r0.r);
+        fma4(acc, wv[3], r1.l); fma4(acc, wv[4], r1.m); fma4(acc, wv[5], r1.r);
+        fma4(acc, wv[6], r2.l); fma4(acc, wv[7], r2.m); fma4(acc, wv[8], r2.r);
+        if (residual) {
+            acc.x += r1.m.x; acc.y += r1.m.y; acc.z += r1.m.z; acc.w += r1.m.w;
+        }
+        st4(oimg + (size_t)y * L + p, acc);
+        r0 = r1;
+        r1 = r2;
+    }
+}
+
+// weight / bias gradient, stride 1: dw[c,i,j] += sum dy[y,x,c] * x[y-1+i, x-1+j, c];  db[c] += sum dy.  Same thread
+// mapping; 10 float4 accumulators per thread, summed per block in shared memory, one global atomic per (channel, tap).
+__global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                float* __restrict__ dw, float* __restrict__ db, int H, int W, int C,
+                                                                int seg) {
+    extern __shared__ float sacc[];     // [C][10]
+    for (int i = threadIdx.x; i < C * 10; i += 256) sacc[i] = 0.f;
+    __syncthreads();
+    const int L = W * C;
+    const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (p < L) {
+        const int c = p % C, xx = p / C;
+        const bool left_ok = xx > 0, right_ok = xx < W - 1;
+        const int y0 = blockIdx.y * seg, y1 = min(H, y0 + seg);
+        const float* img = x + (size_t)blockIdx.z * H * L;
+        const float* gimg = dy + (size_t)blockIdx.z * H * L;
+        float4 acc[10];
+#pragma unroll
+        for (int t = 0; t < 10; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        Row3 r0 = load_row3(img + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
+        Row3 r1 = load_row3(img + (size_t)y0 * L, p, C, true, left_ok, right_ok);
+        for (int y = y0; y < y1; ++y) {
+            const Row3 r2 = load_row3(img + (size_t)(y + 1) * L, p, C, y + 1 < H, left_ok, right_ok);
+            const float4 g = ld4(gimg + (size_t)y * L + p);
+            fma4(acc[0], g, r0.l); fma4(acc[1], g, r0.m); fma4(acc[2], g, r0.r);
+            fma4(acc[3], g, r1.l); fma4(acc[4], g, r1.m); fma4(acc[5], g, r1.r);
+            fma4(acc[6], g, r2.l); fma4(acc[7], g, r2.m); fma4(acc[8], g, r2.r);
+            acc[9].x += g.x; acc[9].y += g.y; acc[9].z += g.z; acc[9].w += g.w;
+            r0 = r1;
+            r1 = r2;
+        }
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            atomicAdd(sacc + (c + 0) * 10 + t, acc[t].x);
+            atomicAdd(sacc + (c + 1) * 10 + t, acc[t].y);
+            atomicAdd(sacc + (c + 2) * 10 + t, acc[t].z);
+            atomicAdd(sacc + (c + 3) * 10 + t, acc[t].w);
+        }
+    }
+    __syncthreads();
+    // channels this block touched: the 1024-float span [blockIdx.x*1024, +1024) modulo C
+    const int span = min(C, 1024);
+    const int cfirst = (blockIdx.x * 1024) % C;
+    for (int o = threadIdx.x; o < span * 10; o += 256) {
+        const int cc = (cfirst + o / 10) % C, t = o % 10;
+        const float v = sacc[cc * 10 + t];
+        if (v != 0.f) {
+            if (t < 9) atomicAdd(dw + cc * 9 + t, v);
+            else if (db) atomicAdd(db + cc, v);
+        }
+    }
+}
+
 // weight / bias gradient of the forward above: dw[c,i,j] += sum dy[b,yo,xo,c] * x[b,yo*s-1+i,xo*s-1+j,c]; db[c] += sum dy
 // block = 32 channels x 8 pixel lanes over a chunk of output pixels.
 __global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
@@ -403,37 +508,90 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const TI* __restrict_
         const int xi = (int)(pix % Wi);
         const int yi = (int)((pix / Wi) % Hi);
         const int b = (int)(pix / ((long long)Wi * Hi));
-        int ya = (int)floorf(((float)yi - 1.f) * iy) - 1, yb = (int)ceilf(((float)yi + 2.f) * iy) + 1;
-        int xa = (int)floorf(((float)xi - 1.f) * ix) - 1, xb = (int)ceilf(((float)xi + 2.f) * ix) + 1;
+        // outputs whose source coordinate falls in (i-1, i+1):  x in ((i-0.5)*inv - 0.5, (i+1.5)*inv - 0.5), padded by one
+        int ya = (int)floorf(((float)yi - 0.5f) * iy - 0.5f) - 1, yb = (int)ceilf(((float)yi + 1.5f) * iy - 0.5f) + 2;
+        int xa = (int)floorf(((float)xi - 0.5f) * ix - 0.5f) - 1, xb = (int)ceilf(((float)xi + 1.5f) * ix - 0.5f) + 2;
         ya = max(ya, 0); xa = max(xa, 0); yb = min(yb, Ho); xb = min(xb, Wo);
         float acc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        for (int y = ya; y < yb; ++y) {
-            int y0, y1;
-            float ly;
-            bil_src(y, sy, Hi, y0, y1, ly);
-            const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
-            if (wy == 0.f) continue;
-            for (int x = xa; x < xb; ++x) {
-                int x0, x1;
-                float lx;
-                bil_src(x, sx, Wi, x0, x1, lx);
-                const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
-                if (wx == 0.f) continue;
-                const TI* p = dout + (((size_t)b * Ho + y) * Wo + x) * ld_out + c;
-                const float wgt = wy * wx;
-                if (VEC == 4) {
-                    const float4 v = ld4(p);
-                    acc[0] += wgt * v.x; acc[1] += wgt * v.y; acc[2] += wgt * v.z; acc[3] += wgt * v.w;
-                } else {
-                    acc[0] += wgt * ldf(p);
+        {
+            for (int y = ya; y < yb; ++y) {
+                int y0, y1;
+                float ly;
+                bil_src(y, sy, Hi, y0, y1, ly);
+                const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+                if (wy == 0.f) continue;
+                for (int x = xa; x < xb; ++x) {
+                    int x0, x1;
+                    float lx;
+                    bil_src(x, sx, Wi, x0, x1, lx);
+                    const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+                    if (wx == 0.f) continue;
+                    const TI* p = dout + (((size_t)b * Ho + y) * Wo + x) * ld_out + c;
+                    const float wgt = wy * wx;
+                    if (VEC == 4) {
+                        const float4 v = ld4(p);
+                        acc[0] += wgt * v.x; acc[1] += wgt * v.y; acc[2] += wgt * v.z; acc[3] += wgt * v.w;
+                    } else {
+                        acc[0] += wgt * ldf(p);
+                    }
                 }
             }
         }
         float* o = din + (size_t)pix * ld_in + c;
         if (VEC == 4) st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
         else *o = acc[0];
+    }
+}
+
+// Integer scale factors S (every resize of the 256x256 configuration: 2, 4, 8): input pixel i receives exactly the 2S
+// outputs [S*i - S/2, S*i + 3S/2), so the window is a compile-time constant: no scanning, fully unrolled loads.  The
+// weights are still evaluated with the forward's own index/lambda arithmetic (bil_src), which keeps the edge clamping
+// (src < 0, i1 == i0 at the far edge) an exact mirror of F.interpolate(align_corners=False).
+template <typename TI, int S>
+__global__ void __launch_bounds__(256) upsample_bwd_int_kernel(const TI* __restrict__ dout, int ld_out, float* __restrict__ din,
+                                                                int ld_in, int B, int Hi, int Wi, int C) {
+    const int Ho = Hi * S, Wo = Wi * S;
+    const int cvn = C >> 2;
+    const float sc = 1.f / S;
+    const int total = B * Hi * Wi * cvn;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = (idx % cvn) * 4;
+        const int pix = idx / cvn;
+        const int xi = pix % Wi;
+        const int yi = (pix / Wi) % Hi;
+        const int b = pix / (Wi * Hi);
+        const int xa = S * xi - S / 2, ya = S * yi - S / 2;
+        float wx[2 * S];
+#pragma unroll
+        for (int k = 0; k < 2 * S; ++k) {
+            const int x = xa + k;
+            int x0, x1;
+            float lx;
+            bil_src(x, sc, Wi, x0, x1, lx);
+            wx[k] = (x >= 0 && x < Wo) ? (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f) : 0.f;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 2 * S; ++r) {
+            const int y = ya + r;
+            if (y < 0 || y >= Ho) continue;
+            int y0, y1;
+            float ly;
+            bil_src(y, sc, Hi, y0, y1, ly);
+            const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+            const TI* prow = dout + ((size_t)(b * Ho + y) * Wo) * ld_out + c;
+#pragma unroll
+            for (int k = 0; k < 2 * S; ++k) {
+                const int x = xa + k;
+                if (x < 0 || x >= Wo) continue;
+                const float4 v = ld4(prow + (size_t)x * ld_out);
+                const float wgt = wy * wx[k];
+                acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+            }
+        }
+        st4(din + (size_t)pix * ld_in + c, acc);
     }
 }
 
@@ -458,6 +616,14 @@ extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, v
     const long long total = (long long)B * Ho * Wo * (C / 4);
     const size_t smem = (size_t)10 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1 && Hi == Ho && Wi == Wo) {
+        const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
+        dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
+        if (out_bf16) dwconv3_s1_kernel<bf16><<<grid, 256, 0, st>>>(in, w, bias, (bf16*)out, Hi, Wi, C, transposed, residual, seg);
+        else dwconv3_s1_kernel<float><<<grid, 256, 0, st>>>(in, w, bias, (float*)out, Hi, Wi, C, transposed, residual, seg);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     if (out_bf16)
         dwconv3_kernel<bf16><<<grid_for(total), 256, smem, st>>>(in, w, bias, (bf16*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
     else
@@ -469,6 +635,13 @@ extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, v
 extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int Hi, int Wi, int Ho, int Wo,
                                  int C, int stride, void* stream) {
     if (!dy || !x || !dw || B <= 0) return MDV_ERR_ARG;
+    if (stride == 1 && Hi == Ho && Wi == Wo && !(C & 3) && C * 40 <= 48 * 1024) {
+        const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
+        dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
+        dwconv3_s1_wgrad_kernel<<<grid, 256, (size_t)C * 10 * sizeof(float), (cudaStream_t)stream>>>(dy, x, dw, db, Hi, Wi, C, seg);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     const long long npix = (long long)B * Ho * Wo;
     const int cb = mdv_cdiv(C, 32);
     const int ppb = pix_per_block_for(npix, cb);
@@ -572,6 +745,16 @@ extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, flo
     }
     if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
     const int g = grid_for((long long)B * Hi * Wi * (C / 4));
+    const int S = (Ho % Hi == 0 && Wo % Wi == 0 && Ho / Hi == Wo / Wi) ? Ho / Hi : 0;
+    if ((S == 2 || S == 4 || S == 8) && (long long)B * Hi * Wi * (C / 4) < 0x7fffffffLL) {
+#define MDV_UPB(SS)                                                                                                              \
+    if (dout_bf16) upsample_bwd_int_kernel<bf16, SS><<<g, 256, 0, st>>>((const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, C);     \
+    else upsample_bwd_int_kernel<float, SS><<<g, 256, 0, st>>>((const float*)dout, ld_out, din, ld_in, B, Hi, Wi, C);
+        if (S == 2) { MDV_UPB(2) } else if (S == 4) { MDV_UPB(4) } else { MDV_UPB(8) }
+#undef MDV_UPB
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     if (dout_bf16)
         upsample_bwd_kernel<bf16, 4><<<g, 256, 0, st>>>((const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
     else

@@ -54,14 +54,21 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float acc = 0.f;
         const float wv = __ldg(w + c);
-        for (int r = r0; r < r1; ++r) {
+        int r = r0;
+        while (r < r1) {       // rows of one sample share the Dropout2d mask of (sample, channel): hash once per segment
             const int b = r / rows_per_sample;
+            const int rend = min(r1, (b + 1) * rows_per_sample);
             const float m = thr ? drop_scale(key, (unsigned long long)b * C + c, thr, inv) : 1.f;
-            const float d = __ldg(dlog + r);
-            dx[(size_t)r * C + c] = d * wv * m;
-            acc += d * ldf(x + (size_t)r * C + c) * m;
+            const float wm = wv * m;
+#pragma unroll 4
+            for (; r < rend; ++r) {
+                const float d = __ldg(dlog + r);
+                dx[(size_t)r * C + c] = d * wm;
+                acc += d * ldf(x + (size_t)r * C + c);
+            }
+            if (dw) atomicAdd(dw + c, acc * m);      // dw[c] += sum_m dlog[m] x[m,c] mask(b,c)
+            acc = 0.f;
         }
-        if (dw) atomicAdd(dw + c, acc);
     }
     if (db && threadIdx.x == 0) {
         for (int r = r0; r < r1; ++r) dbacc += dlog[r];

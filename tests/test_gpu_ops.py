@@ -215,7 +215,8 @@ def test_batchnorm_train_fwd_bwd_and_running_stats(env, M, C, act):
 
 
 # ------------------------------------------------------------------------------------------------- stencils
-@pytest.mark.parametrize("B,H,W,C,stride", [(2, 16, 16, 64, 1), (2, 16, 16, 64, 2), (1, 8, 12, 320, 2), (3, 4, 4, 512, 1)])
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 16, 16, 64, 1), (2, 16, 16, 64, 2), (1, 8, 12, 320, 2), (3, 4, 4, 512, 1),
+                                            (2, 64, 64, 64, 1), (1, 24, 40, 128, 1), (2, 16, 20, 320, 1), (1, 70, 9, 64, 1)])
 def test_dwconv3_fwd_transposed_wgrad(env, B, H, W, C, stride):
     L, lib, dev = env
     torch.manual_seed(C + stride)
@@ -234,6 +235,16 @@ def test_dwconv3_fwd_transposed_wgrad(env, B, H, W, C, stride):
     dw, db = torch.zeros_like(w), torch.zeros_like(bias)
     L.check(lib.mdv_dwconv3_wgrad(L.ptr(dy), L.ptr(x), L.ptr(dw), L.ptr(db), B, H, W, Ho, Wo, C, stride, L.stream()), "dwconv_w")
     assert rel(dx, x.grad) < F32_TOL and rel(dw, w.grad) < F32_TOL and rel(db, bias.grad) < F32_TOL
+    if stride == 1:      # ConvPosEnc form (mpvit.py:239-248): + identity, and the bf16-output variant
+        out2 = torch.empty(B, H, W, C, device=dev)
+        L.check(lib.mdv_dwconv3(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(out2), 0, B, H, W, H, W, C, 1, 0, 1, L.stream()), "dwconv_res")
+        assert rel(out2, ref + x) < F32_TOL
+        out3 = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+        L.check(lib.mdv_dwconv3(L.ptr(x), L.ptr(w), None, L.ptr(out3), 1, B, H, W, H, W, C, 1, 0, 0, L.stream()), "dwconv_bf16")
+        assert rel(out3, ref - bias) < BF16_TOL
+        dx2 = torch.empty(B, H, W, C, device=dev)
+        L.check(lib.mdv_dwconv3(L.ptr(dy), L.ptr(w), None, L.ptr(dx2), 0, B, H, W, H, W, C, 1, 1, 1, L.stream()), "dwconv_t_res")
+        assert rel(dx2, x.grad + dy) < F32_TOL
 
 
 def test_gconv2_matches_grouped_conv_over_concat(env):
@@ -279,7 +290,8 @@ def test_im2col_col2im_are_transposes_of_conv3x3(env, stride, C):
     assert rel(dx, x.grad) < F32_TOL
 
 
-@pytest.mark.parametrize("hi,ho,C", [(8, 16, 64), (4, 16, 512), (2, 16, 64), (16, 64, 1), (5, 13, 8)])
+@pytest.mark.parametrize("hi,ho,C", [(8, 16, 64), (4, 16, 512), (2, 16, 64), (16, 64, 1), (5, 13, 8), (8, 64, 64), (3, 40, 16), (64, 256, 1),
+                                     (7, 64, 4)])
 def test_bilinear_resize_and_transpose(env, hi, ho, C):
     L, lib, dev = env
     torch.manual_seed(hi * ho)
