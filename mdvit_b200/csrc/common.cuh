@@ -50,6 +50,38 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float phi = gauss_cdf(x, &e);
     return fmaf(x * 0.3989422804014327f, e, phi);
 }
+// Packed (two elements per instruction, Blackwell FFMA2/FMUL2/FADD2) versions for the issue-bound GEMM epilogues.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 gauss_cdf2(float2 x, float2* e_out) {
+    const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+    const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y));
+    const float2 w = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    const float2 e = make_float2(ex2_approx(w.x), ex2_approx(w.y));                       // exp(-z^2)
+    float2 poly = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    poly = __ffma2_rn(poly, t, make_float2(1.421413741f, 1.421413741f));
+    poly = __ffma2_rn(poly, t, make_float2(-0.284496736f, -0.284496736f));
+    poly = __ffma2_rn(poly, t, make_float2(0.254829592f, 0.254829592f));
+    // g = 0.5 - 0.5 erfc(|z|) >= 0;  Phi = 0.5 + copysign(g, x)
+    const float2 h = __fmul2_rn(__fmul2_rn(poly, t), e);
+    const float2 g = __ffma2_rn(h, make_float2(-0.5f, -0.5f), make_float2(0.5f, 0.5f));
+    *e_out = e;
+    return __fadd2_rn(make_float2(copysignf(g.x, x.x), copysignf(g.y, x.y)), make_float2(0.5f, 0.5f));
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    float2 e;
+    return __fmul2_rn(x, gauss_cdf2(x, &e));
+}
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
+    float2 e;
+    const float2 phi = gauss_cdf2(x, &e);
+    return __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), e, phi);
+}
+
 __device__ __forceinline__ float hardswish_f(float x) { return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f); }
 __device__ __forceinline__ float hardswish_grad(float x) {
     return x <= -3.0f ? 0.0f : (x >= 3.0f ? 1.0f : (2.0f * x + 3.0f) * (1.0f / 6.0f));

@@ -23,8 +23,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2;       // 16 KB
-constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, alternating 32-column chunks
-constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
+// NEPI epilogue warps (template parameter): NEPI/4 warps per TMEM lane quarter, interleaving 32-column chunks.  8 for
+// MMA-bound shapes; 16 when the epilogue does real arithmetic (GELU / gelu' / dropout): those epilogues are issue-bound
+// and 2 warps per scheduler cannot hide the ALU/MUFU latencies (profiles/r1_ncu_gemm_fc1_epilogue.txt: IPC 2.0).
 
 struct GemmParams {
     int M, N, K;          // NT: output M x N, reduce K.  TN: output P(=M) x Q(=N), reduce R(=K)
@@ -163,8 +164,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
     return c;
 }
 
-template <bool TN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool TN, int NEPI>
+__global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t b_bytes = (uint32_t)BN * BK * 2;
     const uint32_t stage_bytes = A_BYTES + b_bytes;
     uint8_t* slabs = smem + (size_t)stages * stage_bytes;          // [8 warps][nbuf][out (+ preact)]
-    float* cs_all = reinterpret_cast<float*>(slabs + (size_t)NUM_EPI_WARPS * p.nbuf * p.buf_bytes);   // [8 warps][4 chunks][32]
+    float* cs_all = reinterpret_cast<float*>(slabs + (size_t)NEPI * p.nbuf * p.buf_bytes);   // [NEPI warps][4 chunks][32]
     const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
 
     if (warp == 0 && lane == 0) {
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+            mbar_init(&tempty_bar[i], NEPI);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // ------------------------------------------------------------------ epilogue
         const MdvGemmEpi& e = p.epi;
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;       // which alternate 32-column chunks it owns
+        const int half = (warp - 4) >> 2;       // which interleaved 32-column chunks it owns (0 .. NEPI/4-1)
+        constexpr int CSTEP = 8 * NEPI;         // column distance between two chunks of one warp
         uint8_t* myslab = slabs + (size_t)(warp - 4) * (p.nbuf * p.buf_bytes);
         const int nbuf_mask = p.nbuf - 1;
         uint32_t dthr = 0, dkey = 0;
@@ -300,8 +302,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (e.colsum && tc.n_tile * BN != cs_n0) {
                 if (cs_n0 >= 0) {
                     for (int i = 0; i < 4; ++i) {
-                        const int col = cs_n0 + half * 32 + 64 * i + lane;
-                        if (half * 32 + 64 * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
+                        const int col = cs_n0 + half * 32 + CSTEP * i + lane;
+                        if (half * 32 + CSTEP * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
                         cs[i * 32 + lane] = 0.f;
                     }
                 }
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const int n0 = tc.n_tile * BN;
             float rs = 1.0f;
             if (e.rowscale && row_ok) rs = __ldg(e.rowscale + row / e.rows_per_scale);
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            for (int c0 = half * 32; c0 < BN; c0 += CSTEP) {
                 const int col0 = n0 + c0;
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + c0), v);
@@ -359,7 +361,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
                 if (e.act == MDV_ACT_GELU) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    for (int j = 0; j < 32; j += 2) {
+                        const float2 r = gelu_erf2(make_float2(f[j], f[j + 1]));
+                        f[j] = r.x;
+                        f[j + 1] = r.y;
+                    }
                 }
                 if (e.mul_gelu_grad && row_ok) {
                     const bf16* up = (const bf16*)e.mul_gelu_grad + (size_t)row * e.ld_mul + col0;
@@ -370,9 +376,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                             const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float2 g = bf2_to_f2(uu[u]);
-                                f[j + 2 * u] *= gelu_erf_grad(g.x);
-                                f[j + 2 * u + 1] *= gelu_erf_grad(g.y);
+                                const float2 r = __fmul2_rn(make_float2(f[j + 2 * u], f[j + 2 * u + 1]), gelu_erf_grad2(bf2_to_f2(uu[u])));
+                                f[j + 2 * u] = r.x;
+                                f[j + 2 * u + 1] = r.y;
                             }
                         } else {
 #pragma unroll
@@ -387,8 +393,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const uint32_t h = drop_hash(dkey, pbase + j);
-                        f[2 * j] *= drop_lo(h, dthr, dinv);
-                        f[2 * j + 1] *= drop_hi(h, dthr, dinv);
+                        const float2 r = __fmul2_rn(make_float2(f[2 * j], f[2 * j + 1]), make_float2(drop_lo(h, dthr, dinv), drop_hi(h, dthr, dinv)));
+                        f[2 * j] = r.x;
+                        f[2 * j + 1] = r.y;
                     }
                 }
                 if (e.rowscale) {
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                         for (int r = 0; r < 32; ++r)
                             s += *reinterpret_cast<const float*>(s_out + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
                     }
-                    cs[((c0 - half * 32) >> 6) * 32 + lane] += s;
+                    cs[((c0 - half * 32) / CSTEP) * 32 + lane] += s;
                 }
                 if (lane == 0) {
                     if (TN) tma_reduce_add_2d(&tmC, s_out, col0, row0);
@@ -458,8 +465,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         if (e.colsum && cs_n0 >= 0) {
             for (int i = 0; i < 4; ++i) {
-                const int col = cs_n0 + half * 32 + 64 * i + lane;
-                if (half * 32 + 64 * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
+                const int col = cs_n0 + half * 32 + CSTEP * i + lane;
+                if (half * 32 + CSTEP * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
             }
         }
         if (lane == 0) tma_wait_all();
@@ -524,20 +531,21 @@ int pick_bn(int N, int step) {
     return best;
 }
 
-template <bool TN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, GemmParams& p, cudaStream_t st) {
+template <bool TN, int NEPI>
+int launch_n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, GemmParams& p, cudaStream_t st) {
     const size_t stage_bytes = (size_t)A_BYTES + (size_t)p.BN * BK * 2;
     p.out_slab = (TN || !p.epi.out_bf16) ? 4096 : 2048;
     p.buf_bytes = p.out_slab + (p.has_preact ? 2048 : 0);
     // short-K tiles are epilogue-bound (deep store buffering); long-K tiles are MMA-bound (spend smem on operand stages)
     const int kbt = TN ? p.kb_per_split : mdv_cdiv(p.K, BK);
     p.nbuf = kbt <= 2 ? 4 : (kbt <= 8 ? 2 : 1);
-    const size_t cs_bytes = p.epi.colsum ? NUM_EPI_WARPS * 128 * sizeof(float) : 0;
+    if (NEPI > 8 && p.nbuf > 2) p.nbuf = 2;      // twice the warps: the same number of stores in flight
+    const size_t cs_bytes = p.epi.colsum ? NEPI * 128 * sizeof(float) : 0;
     const size_t budget = 226 * 1024 - 1024 - 512;
     size_t slab_bytes;
     int stages;
     for (;;) {
-        slab_bytes = (size_t)NUM_EPI_WARPS * p.nbuf * p.buf_bytes + cs_bytes;
+        slab_bytes = (size_t)NEPI * p.nbuf * p.buf_bytes + cs_bytes;
         stages = (int)((budget - slab_bytes) / stage_bytes);
         if (stages >= 2 || p.nbuf == 1) break;
         p.nbuf >>= 1;      // trade store buffering for operand stages
@@ -549,23 +557,38 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     const size_t smem = stages * stage_bytes + slab_bytes + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<TN, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
     int grid = total_tiles < MDV_NUM_SMS ? total_tiles : MDV_NUM_SMS;
     if (g_force_grid && g_force_grid < grid) grid = g_force_grid;
-    gemm_kernel<TN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, tp, p);
+    gemm_kernel<TN, NEPI><<<grid, 32 * (4 + NEPI), smem, st>>>(ta, tb, tc, tp, p);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
+}
+
+int g_force_nepi = 0;
+
+template <bool TN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, GemmParams& p, cudaStream_t st) {
+    const MdvGemmEpi& e = p.epi;
+    bool heavy = !TN && (e.act != MDV_ACT_NONE || e.mul_gelu_grad != nullptr || e.dropout_p > 0.f);
+    if (g_force_nepi) heavy = g_force_nepi == 16;
+    if (heavy) {
+        const int rc = launch_n<TN, 16>(ta, tb, tc, tp, p, st);
+        if (rc != MDV_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_n<TN, 8>(ta, tb, tc, tp, p, st);
 }
 
 }  // namespace
 
 extern "C" int mdv_gemm_tune(int force_bn, int force_stages, int force_split) {
     g_force_bn = force_bn;
-    g_force_stages = force_stages;
+    g_force_stages = force_stages & 0xff;
+    g_force_nepi = (force_stages >> 8) & 0xff;      // debug: bits 8..15 of force_stages force the epilogue warp count (8 / 16)
     g_force_split = force_split;
     return MDV_OK;
 }
