@@ -29,7 +29,7 @@ long long mdv_launch_count(void); /* kernels launched by this library so far (ho
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA) */
 /* Epilogue applied to acc = A.W^T, in this order:
- *   v = acc + bias[n];  out_preact[m,n] = bf16(v);  v = act(v);  v *= gelu'(mul_gelu_grad[m,n]);
+ *   v = acc + bias[n];  out_preact[m,n] = bf16(v) (see preact_mode);  v = act(v);  v *= gelu'(mul_gelu_grad[m,n]) (see mul_mode);
  *   v *= dropout_mask(rng, drop_stream, m*N+n)/(1-p);  v *= rowscale[m / rows_per_scale];
  *   v += residual[m,n];  out[m,n] = v;  colsum[n] += sum_m v   (bias gradient of the producing layer) */
 typedef struct MdvGemmEpi {
@@ -46,6 +46,9 @@ typedef struct MdvGemmEpi {
     int out_bf16;               /* 1: out is bf16, 0: fp32 */
     int act;                    /* MDV_ACT_NONE | MDV_ACT_GELU */
     int accumulate;             /* fp32 out only: out += v */
+    int preact_mode;            /* what out_preact receives: 0 = v before the activation; 1 = act'(v) * dropout_mask/(1-p), i.e. the
+                                   exact factor the backward pass multiplies the incoming gradient by (saves recomputing it there) */
+    int mul_mode;               /* how mul_gelu_grad is used: 0 = v *= gelu'(u[m,n]);  1 = v *= u[m,n] (u holds a preact_mode-1 factor) */
     float dropout_p;
     uint32_t drop_stream;
 } MdvGemmEpi;

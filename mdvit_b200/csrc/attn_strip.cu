@@ -181,7 +181,7 @@ __global__ void attn_combine_bwd_kernel(const float* __restrict__ part, const fl
 struct TileGeom {
     int ty0, tx0, th, tw, R, PW, PH, nsx;   // PW: padded row pitch (strips rounded up + halo); nsx strips per row
 };
-__device__ __forceinline__ TileGeom tile_geom(int H, int Wd, int WIN) {
+__device__ __forceinline__ TileGeom tile_geom(int H, int Wd, int WIN, int TX = 8) {
     TileGeom g;
     const int TH = min(H, TILE_H), TW = min(Wd, TILE_W);
     const int tiles_x = (Wd + TW - 1) / TW;
@@ -344,7 +344,7 @@ __device__ __forceinline__ void attn_fwd_strip_body(const bf16* __restrict__ qkv
 // ------------------------------------------------------------------------------------------------ backward
 // dQ = s dF.A^T + dF*E ; dK = S*(V.dA^T - r) ; dV = S.dA + convT(dE) ; dE = g dY Q ; dF = g dY            
 // dgate[b,c] += sum_n dY Y / g ;  dWconv[c,tap] += sum_n dE[n,c] V[n+tap,c] ;  dbconv[c] += sum_n dE[n,c]
-template <int CH, int WIN>
+template <int CH, int WIN, int TX>
 __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                     const bf16* __restrict__ yout, const float* __restrict__ gate,
                                                     const float* __restrict__ A, const float* __restrict__ dA,
@@ -365,7 +365,8 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     const int N = H * Wd;
     const int b = blockIdx.z, cg0 = (blockIdx.y + grp0) * G::CPW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const TileGeom g = tile_geom(H, Wd, WIN);
+    const TileGeom g = tile_geom(H, Wd, WIN, TX);
+    const int nwarp = blockDim.x >> 5;
     const bf16* qkv_b = qkv + (size_t)b * N * 3 * C;
     const bf16* dy_b = dy + (size_t)b * N * C;
     const bool want_w = cg.w[0] != nullptr;
@@ -457,7 +458,7 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     const int nstrips = g.th * g.nsx;
     float2 gacc = make_float2(0.f, 0.f);
     // ---- pass A: activation gradients
-    for (int s = warp; s < nstrips; s += 8) {
+    for (int s = warp; s < nstrips; s += nwarp) {
         const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
         const size_t n0 = (size_t)(g.ty0 + py) * Wd + g.tx0 + px0;
         // this strip's own pixels: issued before the convolution loops so their latency hides behind the math
@@ -563,7 +564,7 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
 #pragma unroll
         for (int j = 0; j < WIN; ++j) gw[j] = make_float2(0.f, 0.f);
         float2 gb = make_float2(0.f, 0.f);
-        for (int s = warp; s < nstrips; s += 8) {
+        for (int s = warp; s < nstrips; s += nwarp) {
             const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
             const uint32_t* rowv = sV + ((py + i) * g.PW + px0) * 32 + lane;
             const uint32_t* ce = sE + ((py + g.R) * g.PW + px0 + g.R) * 32 + lane;
@@ -627,8 +628,11 @@ __global__ void __launch_bounds__(256) attn_fwd_strip_kernel(const bf16* __restr
     else attn_fwd_strip_body<CH, 7>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
 }
 
+constexpr int BWD_THREADS = 512;   // 16 warps share one tile: twice the latency hiding of 8 (the kernel is register/latency bound)
+constexpr int BWD_TX = 4;          // 4-pixel strips keep the per-thread arrays within 128 registers
+
 template <int CH>
-__global__ void __launch_bounds__(256) attn_bwd_strip_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                               const bf16* __restrict__ yout, const float* __restrict__ gate,
                                                               const float* __restrict__ A, const float* __restrict__ dA,
                                                               const float* __restrict__ rk, const float* __restrict__ kmax,
@@ -637,9 +641,9 @@ __global__ void __launch_bounds__(256) attn_bwd_strip_kernel(const bf16* __restr
                                                               int Wd, int C) {
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
-    if (win == 3) attn_bwd_strip_body<CH, 3>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
-    else if (win == 5) attn_bwd_strip_body<CH, 5>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
-    else attn_bwd_strip_body<CH, 7>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    else attn_bwd_strip_body<CH, 7, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -680,7 +684,7 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
         if (rc) return rc;
         configured = true;
     }
-    attn_bwd_strip_kernel<CH><<<tile_grid(B, H, W, C / Cfg<CH>::CPW), 256, smem, st>>>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv,
+    attn_bwd_strip_kernel<CH><<<tile_grid(B, H, W, C / Cfg<CH>::CPW), BWD_THREADS, smem, st>>>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv,
                                                                                        dgate, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;

@@ -350,6 +350,35 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 __syncwarp();
                 uint8_t* s_out = myslab + (size_t)buf * p.buf_bytes;
                 uint8_t* s_pre = s_out + p.out_slab;
+                const bool fused_act = p.has_preact && e.preact_mode == 1 && e.act == MDV_ACT_GELU;
+                if (fused_act) {
+                    // one pass per pair: GELU, its derivative and the dropout scale share Phi(x), exp(-x^2/2) and the hash;
+                    // out_preact receives gelu'(x) * mask/(1-p) — the factor the backward multiplies the gradient by
+                    const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned)p.N + (unsigned)col0) >> 1);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 8 * j4 + 2 * u;
+                            const float2 x = make_float2(f[j], f[j + 1]);
+                            float2 ee;
+                            const float2 cdf = gauss_cdf2(x, &ee);
+                            float2 gl = __fmul2_rn(x, cdf);
+                            float2 gr = __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), ee, cdf);
+                            if (dthr) {
+                                const uint32_t h = drop_hash(dkey, pbase + (j >> 1));
+                                const float2 sc = make_float2(drop_lo(h, dthr, dinv), drop_hi(h, dthr, dinv));
+                                gl = __fmul2_rn(gl, sc);
+                                gr = __fmul2_rn(gr, sc);
+                            }
+                            f[j] = gl.x;
+                            f[j + 1] = gl.y;
+                            pk[u] = f2_to_bf2(gr.x, gr.y);
+                        }
+                        *reinterpret_cast<uint4*>(s_pre + lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                } else {
                 if (p.has_preact) {
                     // bf16 rows of 64 B, SWIZZLE_64B: 16B-chunk index ^= (row >> 1) & 3
 #pragma unroll
@@ -367,6 +396,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         f[j + 1] = r.y;
                     }
                 }
+                }
                 if (e.mul_gelu_grad && row_ok) {
                     const bf16* up = (const bf16*)e.mul_gelu_grad + (size_t)row * e.ld_mul + col0;
 #pragma unroll
@@ -376,18 +406,19 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                             const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float2 r = __fmul2_rn(make_float2(f[j + 2 * u], f[j + 2 * u + 1]), gelu_erf_grad2(bf2_to_f2(uu[u])));
+                                const float2 uf = bf2_to_f2(uu[u]);
+                                const float2 r = __fmul2_rn(make_float2(f[j + 2 * u], f[j + 2 * u + 1]), e.mul_mode == 1 ? uf : gelu_erf_grad2(uf));
                                 f[j + 2 * u] = r.x;
                                 f[j + 2 * u + 1] = r.y;
                             }
                         } else {
 #pragma unroll
                             for (int u = 0; u < 8; ++u)
-                                if (col0 + j + u < p.N) f[j + u] *= gelu_erf_grad(__bfloat162float(up[j + u]));
+                                if (col0 + j + u < p.N) f[j + u] *= e.mul_mode == 1 ? __bfloat162float(up[j + u]) : gelu_erf_grad(__bfloat162float(up[j + u]));
                         }
                     }
                 }
-                if (dthr) {
+                if (dthr && !fused_act) {
                     // N and col0 are even: elements (2j, 2j+1) of this chunk share one hash
                     const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned)p.N + (unsigned)col0) >> 1);
 #pragma unroll

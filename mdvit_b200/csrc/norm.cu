@@ -9,43 +9,54 @@ namespace {
 constexpr int LN_MAXV = 8;  // float2 per lane -> C <= 512
 
 // ---------------------------------------------------------------------------------- LayerNorm forward
-// one warp per row; the row lives in registers (C/32 values per lane).
+// one warp owns R rows per iteration (all loads issued before any arithmetic: at C = 64 a row is only 256 B, and one
+// row per warp leaves HBM latency exposed); a row lives in registers, NV float2 per lane.
+template <int NV, int R>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps, bf16* __restrict__ y,
-                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C) {
+                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int M) {
+    constexpr int C = NV * 64;
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const int nv = C >> 6;
-    const float* xr = x + (size_t)row * C;
-    float2 v[LN_MAXV];
-    float s = 0.f;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (row0 >= M) return;
+    float2 v[R][NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-        if (i < nv) {
-            v[i] = *reinterpret_cast<const float2*>(xr + i * 64 + lane * 2);
-            s += v[i].x + v[i].y;
-        }
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const bool ok = row0 + r < M;
+        const float* xr = x + (size_t)(ok ? row0 + r : row0) * C;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-        if (i < nv) {
-            float a = v[i].x - mean, b = v[i].y - mean;
-            q += a * a + b * b;
-        }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
-    bf16* yr = y + (size_t)row * C;
+        for (int i = 0; i < NV; ++i) v[r][i] = *reinterpret_cast<const float2*>(xr + i * 64 + lane * 2);
+    }
+    float2 g[NV], b[NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-        if (i < nv) {
-            const int c = i * 64 + lane * 2;
-            float2 g = *reinterpret_cast<const float2*>(gamma + c), b = *reinterpret_cast<const float2*>(beta + c);
-            *reinterpret_cast<uint32_t*>(yr + c) = f2_to_bf2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    for (int i = 0; i < NV; ++i) {
+        g[i] = *reinterpret_cast<const float2*>(gamma + i * 64 + lane * 2);
+        b[i] = *reinterpret_cast<const float2*>(beta + i * 64 + lane * 2);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r;
+        if (row >= M) break;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s += v[r][i].x + v[r][i].y;
+        const float mean = warp_sum(s) * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float a0 = v[r][i].x - mean, a1 = v[r][i].y - mean;
+            q += a0 * a0 + a1 * a1;
         }
-    if (lane == 0) {
-        mean_out[row] = mean;
-        rstd_out[row] = rstd;
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+        bf16* yr = y + (size_t)row * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            *reinterpret_cast<uint32_t*>(yr + i * 64 + lane * 2) =
+                f2_to_bf2((v[r][i].x - mean) * rstd * g[i].x + b[i].x, (v[r][i].y - mean) * rstd * g[i].y + b[i].y);
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
     }
 }
 
@@ -333,8 +344,20 @@ int stats_rows_per_block(int M, int C) {
 
 extern "C" int mdv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16, float* mean,
                                  float* rstd, int M, int C, void* stream) {
-    if (!x || !y_bf16 || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
-    ln_fwd_kernel<<<mdv_cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, (bf16*)y_bf16, mean, rstd, M, C);
+    if (!x || !y_bf16 || !gamma || !beta || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+#define MDV_LN_FWD(NV, R) ln_fwd_kernel<NV, R><<<mdv_cdiv(M, 8 * R), 256, 0, st>>>(x, gamma, beta, eps, (bf16*)y_bf16, mean, rstd, M); break;
+    switch (C >> 6) {
+        case 1: MDV_LN_FWD(1, 4)
+        case 2: MDV_LN_FWD(2, 4)
+        case 3: MDV_LN_FWD(3, 2)
+        case 4: MDV_LN_FWD(4, 2)
+        case 5: MDV_LN_FWD(5, 2)
+        case 6: MDV_LN_FWD(6, 1)
+        case 7: MDV_LN_FWD(7, 1)
+        default: MDV_LN_FWD(8, 1)
+    }
+#undef MDV_LN_FWD
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

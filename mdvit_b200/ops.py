@@ -87,7 +87,8 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
 
 # ------------------------------------------------------------------------------------------------- thin wrappers
 def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, residual=None, act=ACT_NONE, out_preact=None,
-            mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False, colsum=None):
+            mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False, colsum=None,
+            preact_mode=0, mul_mode=0):
     e = GemmEpi()
     e.bias, e.residual, e.mul_gelu_grad, e.out_preact = ptr(bias), ptr(residual), ptr(mul_gelu_grad), ptr(out_preact)
     e.out, e.rowscale, e.colsum = ptr(out), ptr(rowscale), ptr(colsum)
@@ -100,6 +101,7 @@ def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, resi
     e.out_bf16 = 1 if out.dtype == BF16 else 0
     e.act = act
     e.accumulate = 1 if accumulate else 0
+    e.preact_mode, e.mul_mode = preact_mode, mul_mode
     e.dropout_p = float(drop_p)
     e.drop_stream = drop_stream
     check(L.lib().mdv_gemm_nt(ptr(A), lda or K, ptr(W), ldw or K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
@@ -339,8 +341,9 @@ class BlockFn(torch.autograd.Function):
             ln2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, M, C)
             u = torch.empty((M, hidden), dtype=BF16, device=dev)
             hact = torch.empty((M, hidden), dtype=BF16, device=dev)
+            # u receives gelu'(fc1 output) * dropout mask/(1-p): the factor the backward multiplies d(hact) by
             gemm_nt(ln2, prep_weight(fc1_w, 0, hidden, C), M, hidden, C, hact, bias=fc1_b, act=ACT_GELU, out_preact=u, drop_p=p_drop,
-                    drop_stream=sid[1])
+                    drop_stream=sid[1], preact_mode=1)
             x3 = torch.empty((B, N, C), dtype=F32, device=dev)
             gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2, drop_p=p_drop,
                     drop_stream=sid[2], rowscale=dp2, rows_per_scale=N)
@@ -370,8 +373,7 @@ class BlockFn(torch.autograd.Function):
             d_fc2 = cast_bf16(dx3, M, C, rowscale=dp2, rows_per_scale=N, drop_p=p_drop, drop_stream=sid[2], colsum=G["fc2_b"])
             gemm_tn(d_fc2, hact, M, C, hidden, G["fc2_w"])
             du = torch.empty((M, hidden), dtype=BF16, device=dev)
-            gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, drop_p=p_drop, drop_stream=sid[1],
-                    colsum=G["fc1_b"])
+            gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, mul_mode=1, colsum=G["fc1_b"])
             gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
             dln2 = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(du, prep_weight(fc1_w, 1, hidden, C), M, C, hidden, dln2)

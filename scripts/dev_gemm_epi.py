@@ -29,6 +29,16 @@ def make(M, N, K, kind):
         e.out, e.ldc, e.out_bf16, e.mul_gelu_grad, e.ld_mul, e.colsum = L.ptr(out), N, 1, L.ptr(u), N, L.ptr(cs)
         e.dropout_p, e.rng, e.drop_stream = 0.1, L.ptr(rng), 3
         keep += [u, cs]
+    elif kind in ("fc2d_new", "fc2d_new_nocs"):
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16); u = torch.randn(M, N, device=dev).bfloat16(); cs = torch.zeros(N, device=dev)
+        e.out, e.ldc, e.out_bf16, e.mul_gelu_grad, e.ld_mul, e.mul_mode = L.ptr(out), N, 1, L.ptr(u), N, 1
+        if kind == "fc2d_new": e.colsum = L.ptr(cs)
+        keep += [u, cs]
+    elif kind == "fc1_new":
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16); pre = torch.empty_like(out)
+        e.out, e.ldc, e.out_bf16, e.bias, e.act, e.out_preact, e.ld_preact, e.preact_mode = L.ptr(out), N, 1, L.ptr(bias), 1, L.ptr(pre), N, 1
+        e.dropout_p, e.rng, e.drop_stream = 0.1, L.ptr(rng), 3
+        keep += [pre]
     elif kind == "lf":     # MLPDecoderFM.linear_fuse forward: bias, fp32 out
         out = torch.empty(M, N, device=dev); e.out, e.ldc, e.out_bf16, e.bias = L.ptr(out), N, 0, L.ptr(bias)
     elif kind == "res":
@@ -49,7 +59,7 @@ def bench(fn, n=20):
     t.record(); torch.cuda.synchronize()
     return s.elapsed_time(t) / n * 1e3
 
-cases = [(131072, 512, 64, k) for k in ("plain", "fc1_nodrop", "fc1", "fc2d")] + [(131072, 64, 512, "res"), (32768, 1024, 128, "fc1"), (32768, 1024, 128, "fc2d"), (131072, 512, 2112, "lf")]
+cases = [(131072, 512, 64, k) for k in ("plain", "fc1_nodrop", "fc1", "fc2d", "fc1_new", "fc2d_new", "fc2d_new_nocs")] + [(131072, 64, 512, "res"), (32768, 1024, 128, "fc1"), (32768, 1024, 128, "fc2d"), (131072, 512, 2112, "lf")]
 if os.environ.get("ONE"):
     M, N, K, kind = cases[int(os.environ["ONE"])]
     fn, keep = make(M, N, K, kind)

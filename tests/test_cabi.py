@@ -29,5 +29,5 @@ def test_version_and_arg_checks(built_lib):
 
 
 def test_epilogue_struct_layout_matches_header():
-    # 8 pointers + 10 ints/floats/uint32
-    assert ctypes.sizeof(_lib.GemmEpi) == 8 * 8 + 10 * 4
+    # 8 pointers + 12 ints/floats/uint32
+    assert ctypes.sizeof(_lib.GemmEpi) == 8 * 8 + 12 * 4

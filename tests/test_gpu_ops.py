@@ -77,6 +77,25 @@ def test_gemm_nt_gelu_preact_mulgrad_rowscale_ldc(env):
     F.gelu(uf).sum().backward()
     want = (acc - bias) * uf.grad * rs.repeat_interleave(500)[:, None]
     assert rel(out2, want) < BF16_TOL
+    # preact_mode 1: the forward stores gelu'(v) * dropout scale itself, the backward multiplies by it (mul_mode 1)
+    rng = torch.tensor([5, 9], dtype=torch.int64, device=dev)
+    fac = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    out3 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    e = L.GemmEpi()
+    e.bias, e.out, e.ldc, e.out_bf16, e.act, e.out_preact, e.ld_preact, e.preact_mode = L.ptr(bias), L.ptr(out3), N, 1, L.ACT_GELU, L.ptr(fac), N, 1
+    e.dropout_p, e.rng, e.drop_stream = 0.25, L.ptr(rng), 4
+    L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "gemm_nt")
+    mask = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    L.check(lib.mdv_cast_bf16(L.ptr(torch.ones(M, N, device=dev)), N, L.ptr(mask), N, M, N, None, 1, 0.25, L.ptr(rng), 4, None, L.stream()), "cast")
+    keep = (mask.float() != 0).float() / 0.75
+    af = acc.clone().requires_grad_()
+    F.gelu(af).sum().backward()
+    assert rel(out3, F.gelu(acc) * keep) < BF16_TOL and rel(fac, af.grad * keep) < BF16_TOL
+    out4 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    e = L.GemmEpi()
+    e.out, e.ldc, e.out_bf16, e.mul_gelu_grad, e.ld_mul, e.mul_mode = L.ptr(out4), N, 1, L.ptr(fac), N, 1
+    L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "gemm_nt")
+    assert rel(out4, (acc - bias) * fac.float()) < BF16_TOL
 
 
 def test_gemm_nt_dropout_mask_is_reproducible_and_unbiased(env):
