@@ -26,6 +26,9 @@ extern "C" {
 
 int mdv_version(void);
 long long mdv_launch_count(void); /* kernels launched by this library so far (host-side counter) */
+/* Programmatic dependent launch for every kernel of the library (default on; env MDV_NO_PDL=1 disables): each kernel's
+ * launch and prologue overlap the tail of its predecessor on the stream; results are unchanged. */
+int mdv_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA) */
 /* Epilogue applied to acc = A.W^T, in this order:

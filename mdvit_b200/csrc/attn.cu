@@ -22,6 +22,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 // kmax must be pre-filled with 0xFF bytes (identity of the atomic above).  thread = 2 channels, ty = row lane.
 __global__ void __launch_bounds__(256) attn_colmax_kernel(const bf16* __restrict__ qkv, float* __restrict__ kmax, int N, int C,
                                                            int rows_per_block) {
+    MDV_PDL_SYNC();
     const int half = C >> 1;
     const int tx = threadIdx.x % half, ty = threadIdx.x / half, nty = blockDim.x / half;
     const int b = blockIdx.y;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(256) da_gate_z_kernel(const float* __restrict_
                                                          const float* __restrict__ b1, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, float* __restrict__ hid_out,
                                                          float* __restrict__ z_out, int nd, int hid, int C) {
+    MDV_PDL_SYNC();
     extern __shared__ float sh[];   // hid
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(256) da_gate_z_kernel(const float* __restrict_
 }
 // Kernel 2: softmax over the heads, one thread per (sample, v); in place on the z buffer.
 __global__ void da_gate_softmax_kernel(float* __restrict__ gate, int B, int C, int heads) {
+    MDV_PDL_SYNC();
     const int Ch = C / heads;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Ch) return;
@@ -82,6 +85,7 @@ __global__ void da_gate_softmax_kernel(float* __restrict__ gate, int B, int C, i
 // DA gate backward, step 1a (thread per (sample, v)): dz = g * (dg - sum_h g*dg)
 __global__ void da_gate_bwd_dz_kernel(const float* __restrict__ gate, const float* __restrict__ dgate, float* __restrict__ dz_out,
                                       int B, int C, int heads) {
+    MDV_PDL_SYNC();
     const int Ch = C / heads;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Ch) return;
@@ -95,6 +99,7 @@ __global__ void da_gate_bwd_dz_kernel(const float* __restrict__ gate, const floa
 __global__ void __launch_bounds__(256) da_gate_bwd_dhid_kernel(const float* __restrict__ w2, const float* __restrict__ hid_in,
                                                                 const float* __restrict__ dz, float* __restrict__ dhid_out, int hid,
                                                                 int C) {
+    MDV_PDL_SYNC();
     __shared__ float red[8][33];
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(256) da_gate_bwd_dhid_kernel(const float* __re
 __global__ void da_gate_bwd2_kernel(const float* __restrict__ label, const float* __restrict__ hid_in, const float* __restrict__ dz,
                                     const float* __restrict__ dhid, float* __restrict__ dw1, float* __restrict__ db1,
                                     float* __restrict__ dw2, float* __restrict__ db2, int B, int nd, int hid, int C) {
+    MDV_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n2 = C * hid;
     if (i < n2) {
@@ -164,7 +170,7 @@ extern "C" int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float
         const int nty = 256 / half > 0 ? 256 / half : 1;
         int rpb = mdv_cdiv((long long)N * B, 4 * MDV_NUM_SMS);
         if (rpb < 8 * nty) rpb = 8 * nty;
-        attn_colmax_kernel<<<dim3(mdv_cdiv(N, rpb), B), half * nty, 0, st>>>(qkv, kmax, N, C, rpb);
+        mdv_launch(attn_colmax_kernel, dim3(dim3(mdv_cdiv(N, rpb), B)), dim3(half * nty), 0, st, qkv, kmax, N, C, rpb);
         MDV_CHECK_LAUNCH();
     }
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
@@ -196,9 +202,9 @@ extern "C" int mdv_da_gate_fwd(const float* label, const float* w1, const float*
                                float* gate, int B, int nd, int hid, int C, int heads, void* stream) {
     if (!label || !w1 || !w2 || !hid_out || !gate || C % heads) return MDV_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    da_gate_z_kernel<<<dim3(mdv_cdiv(C, 8), B), 256, hid * sizeof(float), st>>>(label, w1, b1, w2, b2, hid_out, gate, nd, hid, C);
+    mdv_launch(da_gate_z_kernel, dim3(dim3(mdv_cdiv(C, 8), B)), dim3(256), hid * sizeof(float), st, label, w1, b1, w2, b2, hid_out, gate, nd, hid, C);
     MDV_CHECK_LAUNCH();
-    da_gate_softmax_kernel<<<mdv_cdiv(B * (C / heads), 128), 128, 0, st>>>(gate, B, C, heads);
+    mdv_launch(da_gate_softmax_kernel, dim3(mdv_cdiv(B * (C / heads), 128)), dim3(128), 0, st, gate, B, C, heads);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -211,12 +217,12 @@ extern "C" int mdv_da_gate_bwd(const float* label, const float* w2, const float*
     cudaStream_t st = (cudaStream_t)stream;
     float* dz = ws;
     float* dhid = ws + (size_t)B * C;
-    da_gate_bwd_dz_kernel<<<mdv_cdiv(B * (C / heads), 128), 128, 0, st>>>(gate, dgate, dz, B, C, heads);
+    mdv_launch(da_gate_bwd_dz_kernel, dim3(mdv_cdiv(B * (C / heads), 128)), dim3(128), 0, st, gate, dgate, dz, B, C, heads);
     MDV_CHECK_LAUNCH();
-    da_gate_bwd_dhid_kernel<<<dim3(mdv_cdiv(hid, 32), B), 256, 0, st>>>(w2, hid_in, dz, dhid, hid, C);
+    mdv_launch(da_gate_bwd_dhid_kernel, dim3(dim3(mdv_cdiv(hid, 32), B)), dim3(256), 0, st, w2, hid_in, dz, dhid, hid, C);
     MDV_CHECK_LAUNCH();
     const int total = C * hid + C + hid * nd + hid;
-    da_gate_bwd2_kernel<<<mdv_cdiv(total, 256), 256, 0, st>>>(label, hid_in, dz, dhid, dw1, db1, dw2, db2, B, nd, hid, C);
+    mdv_launch(da_gate_bwd2_kernel, dim3(mdv_cdiv(total, 256)), dim3(256), 0, st, label, hid_in, dz, dhid, dw1, db1, dw2, db2, B, nd, hid, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

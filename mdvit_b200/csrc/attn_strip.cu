@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) attn_outer_kernel(const bf16* __restrict_
                                                           const float* __restrict__ gate, const float* __restrict__ kmax,
                                                           float* __restrict__ part, float* __restrict__ zpart, int N, int C,
                                                           int rows_per_block, int nchunk) {
+    MDV_PDL_SYNC();
     using G = Cfg<CH>;
     constexpr int KR = G::KR;
     __shared__ float2 red[KR][32];
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) attn_outer_kernel(const bf16* __restrict_
 // A[b,c,v] = sum_chunks part / sum_chunks zpart ; zsum[b,c]
 __global__ void attn_combine_fwd_kernel(const float* __restrict__ part, const float* __restrict__ zpart, float* __restrict__ A,
                                         float* __restrict__ zsum, int C, int Ch, int nchunk, long long total) {
+    MDV_PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long bc = i / Ch;
@@ -161,6 +163,7 @@ __global__ void attn_combine_fwd_kernel(const float* __restrict__ part, const fl
 // dA[b,c,v] = scale * sum_chunks part ;  rk[b,c] = sum_v A[b,c,v] dA[b,c,v]      (one warp per (b,c) row)
 __global__ void attn_combine_bwd_kernel(const float* __restrict__ part, const float* __restrict__ A, float* __restrict__ dA,
                                         float* __restrict__ rk, float scale, int C, int Ch, int nchunk, int rows) {
+    MDV_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const int bc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (bc >= rows) return;
@@ -621,6 +624,7 @@ template <int CH>
 __global__ void __launch_bounds__(256) attn_fwd_strip_kernel(const bf16* __restrict__ qkv, const float* __restrict__ A,
                                                               const float* __restrict__ gate, CrpeW cw, bf16* __restrict__ out,
                                                               float scale, int H, int Wd, int C) {
+    MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
     if (win == 3) attn_fwd_strip_body<CH, 3>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
@@ -639,6 +643,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf
                                                               const float* __restrict__ zsum, CrpeW cw, CrpeG cg,
                                                               bf16* __restrict__ dqkv, float* __restrict__ dgate, float scale, int H,
                                                               int Wd, int C) {
+    MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
     if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
@@ -668,7 +673,7 @@ int launch_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& 
         if (rc) return rc;
         configured = true;
     }
-    attn_fwd_strip_kernel<CH><<<tile_grid(B, H, W, C / Cfg<CH>::CPW), 256, smem, st>>>(qkv, A, gate, cw, out, scale, H, W, C);
+    mdv_launch(attn_fwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(256), smem, st, qkv, A, gate, cw, out, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -684,7 +689,7 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
         if (rc) return rc;
         configured = true;
     }
-    attn_bwd_strip_kernel<CH><<<tile_grid(B, H, W, C / Cfg<CH>::CPW), BWD_THREADS, smem, st>>>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv,
+    mdv_launch(attn_bwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv,
                                                                                        dgate, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -707,7 +712,7 @@ int launch_outer(const bf16* qkv, const bf16* dy, const float* gate, const float
     int rpb = mdv_cdiv(N, nchunk);
     rpb = ((rpb + 31) / 32) * 32;
     nchunk = mdv_cdiv(N, rpb);
-    attn_outer_kernel<CH, MODE><<<dim3(nchunk, by, B), 256, 0, st>>>(qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
+    mdv_launch((attn_outer_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(256), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -723,7 +728,7 @@ int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, f
     int rc = launch_outer<CH, 0>(qkv, nullptr, nullptr, kmax, part, zpart, B, N, C, nchunk, st);
     if (rc) return rc;
     const long long tot = (long long)B * C * CH;
-    attn_combine_fwd_kernel<<<mdv_cdiv(tot, 256), 256, 0, st>>>(part, zpart, A, zsum, C, CH, nchunk, tot);
+    mdv_launch(attn_combine_fwd_kernel, dim3(mdv_cdiv(tot, 256)), dim3(256), 0, st, part, zpart, A, zsum, C, CH, nchunk, tot);
     MDV_CHECK_LAUNCH();
     return launch_fwd<CH>(qkv, A, gate, cw, out, scale, B, H, W, C, st);
 }
@@ -739,7 +744,7 @@ int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gat
     float* rk = dA + (size_t)B * C * CH;
     int rc = launch_outer<CH, 1>(qkv, dy, gate, nullptr, part, nullptr, B, N, C, nchunk, st);
     if (rc) return rc;
-    attn_combine_bwd_kernel<<<mdv_cdiv(B * C, 8), 256, 0, st>>>(part, A, dA, rk, scale, C, CH, nchunk, B * C);
+    mdv_launch(attn_combine_bwd_kernel, dim3(mdv_cdiv(B * C, 8)), dim3(256), 0, st, part, A, dA, rk, scale, C, CH, nchunk, B * C);
     MDV_CHECK_LAUNCH();
     return launch_bwd<CH>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
 }

@@ -22,6 +22,35 @@ extern long long g_mdv_launches;
 
 #define MDV_NUM_SMS 148
 
+// ----------------------------------------------------------------------------- programmatic dependent launch (PDL)
+// A training step is ~4500 mostly short kernels on one stream; ~28% of its time is batch-independent launch / ramp
+// latency.  Every kernel is launched with the programmatic-stream-serialization attribute and begins with
+// griddepcontrol.wait (blocks until the preceding grid has completed and its writes are visible) followed by
+// griddepcontrol.launch_dependents: the NEXT kernel's launch, block scheduling and prologue then overlap this kernel's
+// execution instead of following it.  The wait is the first instruction, so no dependent read or write can be early.
+#define MDV_PDL_SYNC()                                                  \
+    do {                                                                \
+        asm volatile("griddepcontrol.wait;" ::: "memory");              \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+    } while (0)
+
+extern int g_mdv_pdl;   // 1: launch with the PDL attribute (default), 0: plain launches (MDV_NO_PDL=1 or mdv_set_pdl(0))
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mdv_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_mdv_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int mdv_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------- math

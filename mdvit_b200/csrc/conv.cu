@@ -31,6 +31,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) dwconv3_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ bias, TO* __restrict__ out, int B, int Hi,
                                                        int Wi, int Ho, int Wo, int C, int stride, int transposed, int residual) {
+    MDV_PDL_SYNC();
     extern __shared__ float sw[];  // [9][C] then bias [C]
     for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[(i % 9) * C + i / 9] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) sw[9 * C + i] = bias ? bias[i] : 0.f;
@@ -99,6 +100,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, TO* __restrict__ out, int H, int W, int C,
                                                           int flip, int residual, int seg) {
+    MDV_PDL_SYNC();
     const int L = W * C;
     const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (p >= L) return;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 float* __restrict__ dw, float* __restrict__ db, int H, int W, int C,
                                                                 int seg) {
+    MDV_PDL_SYNC();
     extern __shared__ float sacc[];     // [C][10]
     for (int i = threadIdx.x; i < C * 10; i += 256) sacc[i] = 0.f;
     __syncthreads();
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __re
 __global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              float* __restrict__ dw, float* __restrict__ db, int B, int Hi, int Wi,
                                                              int Ho, int Wo, int C, int stride, int pix_per_block) {
+    MDV_PDL_SYNC();
     __shared__ float sh[8][32][11];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -241,6 +245,7 @@ __global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const float* __restr
 __global__ void __launch_bounds__(256) gconv2_fwd_kernel(const float* __restrict__ skip, const float* __restrict__ up,
                                                           const float* __restrict__ w, bf16* __restrict__ out, int B, int H, int W,
                                                           int C) {
+    MDV_PDL_SYNC();
     const int g2n = C >> 1;
     const long long total = (long long)B * H * W * g2n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(256) gconv2_fwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) gconv2_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                                             float* __restrict__ dskip, float* __restrict__ dup, int B, int H, int W,
                                                             int C) {
+    MDV_PDL_SYNC();
     const int g2n = C >> 1;
     const long long total = (long long)B * H * W * g2n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(256) gconv2_dgrad_kernel(const float* __restri
 __global__ void __launch_bounds__(256) gconv2_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ skip,
                                                             const float* __restrict__ up, float* __restrict__ dw, int B, int H, int W,
                                                             int C, int pix_per_block) {
+    MDV_PDL_SYNC();
     __shared__ float sh[8][32][19];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int g = blockIdx.x * 32 + tx;
@@ -362,6 +369,7 @@ __global__ void __launch_bounds__(256) gconv2_wgrad_kernel(const float* __restri
 template <typename TI>
 __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in, bf16* __restrict__ col, int B, int Hi, int Wi,
                                                        int Ho, int Wo, int C, int stride, int ldc) {
+    MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const int per_row = 9 * c4n;
     const long long total = (long long)B * Ho * Wo * per_row;
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in,
 // first stem conv: NCHW fp32 image [B,3,H,W] -> col [B*Ho*Wo, 64] bf16, column = (i*3+j)*3 + ci for < 27, zero elsewhere.
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, bf16* __restrict__ col, int B, int Hi,
                                                            int Wi, int Ho, int Wo) {
+    MDV_PDL_SYNC();
     const long long total = (long long)B * Ho * Wo * 32;  // one thread = 2 columns
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(idx % 32) * 2;
@@ -406,6 +415,7 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
 // dx[b,y,x,c] = sum_ij dcol[(b,(y+1-i)/s,(x+1-j)/s), (i*3+j)*C + c]   (gather form of the im2col transpose)
 __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B, int Hi, int Wi,
                                                        int Ho, int Wo, int C, int stride, int ldc) {
+    MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const long long total = (long long)B * Hi * Wi * c4n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -448,6 +458,7 @@ __device__ __forceinline__ void bil_src(int d, float scale, int n_in, int& i0, i
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const TI* __restrict__ in, int ld_in, TO* __restrict__ out, int ld_out,
                                                             int B, int Hi, int Wi, int Ho, int Wo, int C) {
+    MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
     const long long total = (long long)B * Ho * Wo * c4n;
@@ -477,6 +488,7 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const TI* __restrict_
 // single-channel variant (the commuted segmentation heads): in [B,Hi,Wi] fp32 -> out [B,Ho,Wo] fp32
 __global__ void __launch_bounds__(256) upsample1_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int Hi,
                                                              int Wi, int Ho, int Wo) {
+    MDV_PDL_SYNC();
     const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
     const long long total = (long long)B * Ho * Wo;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -498,6 +510,7 @@ __global__ void __launch_bounds__(256) upsample1_fwd_kernel(const float* __restr
 template <typename TI, int VEC>
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const TI* __restrict__ dout, int ld_out, float* __restrict__ din,
                                                             int ld_in, int B, int Hi, int Wi, int Ho, int Wo, int C) {
+    MDV_PDL_SYNC();
     const int cvn = C / VEC;
     const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
     const float iy = (float)Ho / Hi, ix = (float)Wo / Wi;
@@ -552,6 +565,7 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const TI* __restrict_
 template <typename TI, int S>
 __global__ void __launch_bounds__(256) upsample_bwd_int_kernel(const TI* __restrict__ dout, int ld_out, float* __restrict__ din,
                                                                 int ld_in, int B, int Hi, int Wi, int C) {
+    MDV_PDL_SYNC();
     const int Ho = Hi * S, Wo = Wi * S;
     const int cvn = C >> 2;
     const float sc = 1.f / S;
@@ -619,15 +633,15 @@ extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, v
     if (stride == 1 && Hi == Ho && Wi == Wo) {
         const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
         dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
-        if (out_bf16) dwconv3_s1_kernel<bf16><<<grid, 256, 0, st>>>(in, w, bias, (bf16*)out, Hi, Wi, C, transposed, residual, seg);
-        else dwconv3_s1_kernel<float><<<grid, 256, 0, st>>>(in, w, bias, (float*)out, Hi, Wi, C, transposed, residual, seg);
+        if (out_bf16) mdv_launch(dwconv3_s1_kernel<bf16>, dim3(grid), dim3(256), 0, st, in, w, bias, (bf16*)out, Hi, Wi, C, transposed, residual, seg);
+        else mdv_launch(dwconv3_s1_kernel<float>, dim3(grid), dim3(256), 0, st, in, w, bias, (float*)out, Hi, Wi, C, transposed, residual, seg);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
     if (out_bf16)
-        dwconv3_kernel<bf16><<<grid_for(total), 256, smem, st>>>(in, w, bias, (bf16*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
+        mdv_launch(dwconv3_kernel<bf16>, dim3(grid_for(total)), dim3(256), smem, st, in, w, bias, (bf16*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
     else
-        dwconv3_kernel<float><<<grid_for(total), 256, smem, st>>>(in, w, bias, (float*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
+        mdv_launch(dwconv3_kernel<float>, dim3(grid_for(total)), dim3(256), smem, st, in, w, bias, (float*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -638,7 +652,7 @@ extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, flo
     if (stride == 1 && Hi == Ho && Wi == Wo && !(C & 3) && C * 40 <= 48 * 1024) {
         const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
         dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
-        dwconv3_s1_wgrad_kernel<<<grid, 256, (size_t)C * 10 * sizeof(float), (cudaStream_t)stream>>>(dy, x, dw, db, Hi, Wi, C, seg);
+        mdv_launch(dwconv3_s1_wgrad_kernel, dim3(grid), dim3(256), (size_t)C * 10 * sizeof(float), (cudaStream_t)stream, dy, x, dw, db, Hi, Wi, C, seg);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
@@ -646,7 +660,7 @@ extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, flo
     const int cb = mdv_cdiv(C, 32);
     const int ppb = pix_per_block_for(npix, cb);
     dim3 grid(cb, mdv_cdiv(npix, ppb));
-    dwconv3_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, dw, db, B, Hi, Wi, Ho, Wo, C, stride, ppb);
+    mdv_launch(dwconv3_wgrad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dy, x, dw, db, B, Hi, Wi, Ho, Wo, C, stride, ppb);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -654,7 +668,7 @@ extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, flo
 extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out_bf16, int B, int H, int W, int C,
                               void* stream) {
     if (!skip || !up || !w || !out_bf16 || (C & 3)) return MDV_ERR_ARG;
-    gconv2_fwd_kernel<<<grid_for((long long)B * H * W * (C / 2)), 256, 0, (cudaStream_t)stream>>>(skip, up, w, (bf16*)out_bf16, B, H, W, C);
+    mdv_launch(gconv2_fwd_kernel, dim3(grid_for((long long)B * H * W * (C / 2))), dim3(256), 0, (cudaStream_t)stream, skip, up, w, (bf16*)out_bf16, B, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -663,14 +677,14 @@ extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float*
                               float* dw, int B, int H, int W, int C, void* stream) {
     if (!dout || !skip || !up || !w || !dskip || !dup || (C & 3)) return MDV_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    gconv2_dgrad_kernel<<<grid_for((long long)B * H * W * (C / 2)), 256, 0, st>>>(dout, w, dskip, dup, B, H, W, C);
+    mdv_launch(gconv2_dgrad_kernel, dim3(grid_for((long long)B * H * W * (C / 2))), dim3(256), 0, st, dout, w, dskip, dup, B, H, W, C);
     MDV_CHECK_LAUNCH();
     if (!dw) return MDV_OK;   // weight gradient not wanted in this pass
     const long long npix = (long long)B * H * W;
     const int cb = mdv_cdiv(C, 32);
     const int ppb = pix_per_block_for(npix, cb);
     dim3 grid(cb, mdv_cdiv(npix, ppb));
-    gconv2_wgrad_kernel<<<grid, 256, 0, st>>>(dout, skip, up, dw, B, H, W, C, ppb);
+    mdv_launch(gconv2_wgrad_kernel, dim3(grid), dim3(256), 0, st, dout, skip, up, dw, B, H, W, C, ppb);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -685,9 +699,9 @@ extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, i
     }
     const long long total = (long long)B * Ho * Wo * 9 * (C / 4);
     if (in_bf16)
-        im2col3_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+        mdv_launch(im2col3_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, st, (const bf16*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
     else
-        im2col3_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+        mdv_launch(im2col3_kernel<float>, dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -695,7 +709,7 @@ extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, i
 extern "C" int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int Hi, int Wi, void* stream) {
     if (!img_nchw || !col_bf16 || (Hi & 1) || (Wi & 1)) return MDV_ERR_ARG;
     const int Ho = Hi / 2, Wo = Wi / 2;
-    im2col_stem_kernel<<<grid_for((long long)B * Ho * Wo * 32), 256, 0, (cudaStream_t)stream>>>(img_nchw, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo);
+    mdv_launch(im2col_stem_kernel, dim3(grid_for((long long)B * Ho * Wo * 32)), dim3(256), 0, (cudaStream_t)stream, img_nchw, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -703,7 +717,7 @@ extern "C" int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int
 extern "C" int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc,
                            void* stream) {
     if (!dcol || !dx || (C & 3)) return MDV_ERR_ARG;
-    col2im3_kernel<<<grid_for((long long)B * Hi * Wi * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dcol, dx, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    mdv_launch(col2im3_kernel, dim3(grid_for((long long)B * Hi * Wi * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, dx, B, Hi, Wi, Ho, Wo, C, stride, ldc);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -714,18 +728,18 @@ extern "C" int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* ou
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 1) {
         if (in_bf16 || out_bf16) return MDV_ERR_UNSUPPORTED;
-        upsample1_fwd_kernel<<<grid_for((long long)B * Ho * Wo), 256, 0, st>>>((const float*)in, (float*)out, B, Hi, Wi, Ho, Wo);
+        mdv_launch(upsample1_fwd_kernel, dim3(grid_for((long long)B * Ho * Wo)), dim3(256), 0, st, (const float*)in, (float*)out, B, Hi, Wi, Ho, Wo);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
     if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
     const int g = grid_for((long long)B * Ho * Wo * (C / 4));
     if (in_bf16 && out_bf16)
-        upsample_fwd_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
+        mdv_launch((upsample_fwd_kernel<bf16, bf16>), dim3(g), dim3(256), 0, st, (const bf16*)in, ld_in, (bf16*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
     else if (!in_bf16 && out_bf16)
-        upsample_fwd_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)in, ld_in, (bf16*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
+        mdv_launch((upsample_fwd_kernel<float, bf16>), dim3(g), dim3(256), 0, st, (const float*)in, ld_in, (bf16*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
     else if (!in_bf16 && !out_bf16)
-        upsample_fwd_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, ld_in, (float*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
+        mdv_launch((upsample_fwd_kernel<float, float>), dim3(g), dim3(256), 0, st, (const float*)in, ld_in, (float*)out, ld_out, B, Hi, Wi, Ho, Wo, C);
     else
         return MDV_ERR_UNSUPPORTED;
     MDV_CHECK_LAUNCH();
@@ -739,7 +753,7 @@ extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, flo
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 1) {
         if (dout_bf16) return MDV_ERR_UNSUPPORTED;
-        upsample_bwd_kernel<float, 1><<<grid_for((long long)B * Hi * Wi), 256, 0, st>>>((const float*)dout, 1, din, 1, B, Hi, Wi, Ho, Wo, 1);
+        mdv_launch((upsample_bwd_kernel<float, 1>), dim3(grid_for((long long)B * Hi * Wi)), dim3(256), 0, st, (const float*)dout, 1, din, 1, B, Hi, Wi, Ho, Wo, 1);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
@@ -748,17 +762,17 @@ extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, flo
     const int S = (Ho % Hi == 0 && Wo % Wi == 0 && Ho / Hi == Wo / Wi) ? Ho / Hi : 0;
     if ((S == 2 || S == 4 || S == 8) && (long long)B * Hi * Wi * (C / 4) < 0x7fffffffLL) {
 #define MDV_UPB(SS)                                                                                                              \
-    if (dout_bf16) upsample_bwd_int_kernel<bf16, SS><<<g, 256, 0, st>>>((const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, C);     \
-    else upsample_bwd_int_kernel<float, SS><<<g, 256, 0, st>>>((const float*)dout, ld_out, din, ld_in, B, Hi, Wi, C);
+    if (dout_bf16) mdv_launch((upsample_bwd_int_kernel<bf16, SS>), dim3(g), dim3(256), 0, st, (const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, C);     \
+    else mdv_launch((upsample_bwd_int_kernel<float, SS>), dim3(g), dim3(256), 0, st, (const float*)dout, ld_out, din, ld_in, B, Hi, Wi, C);
         if (S == 2) { MDV_UPB(2) } else if (S == 4) { MDV_UPB(4) } else { MDV_UPB(8) }
 #undef MDV_UPB
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
     if (dout_bf16)
-        upsample_bwd_kernel<bf16, 4><<<g, 256, 0, st>>>((const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
+        mdv_launch((upsample_bwd_kernel<bf16, 4>), dim3(g), dim3(256), 0, st, (const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
     else
-        upsample_bwd_kernel<float, 4><<<g, 256, 0, st>>>((const float*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
+        mdv_launch((upsample_bwd_kernel<float, 4>), dim3(g), dim3(256), 0, st, (const float*)dout, ld_out, din, ld_in, B, Hi, Wi, Ho, Wo, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

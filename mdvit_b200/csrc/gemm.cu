@@ -168,6 +168,7 @@ template <bool TN, int NEPI>
 __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next kernel start launching right away
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -211,6 +212,9 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    // PDL: barrier init, TMEM allocation and tensor-map prefetch above overlap the previous kernel's tail; nothing before
+    // this point reads or writes memory the previous kernel may still be producing / consuming
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -595,7 +599,7 @@ int launch_n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc
     const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
     int grid = total_tiles < MDV_NUM_SMS ? total_tiles : MDV_NUM_SMS;
     if (g_force_grid && g_force_grid < grid) grid = g_force_grid;
-    gemm_kernel<TN, NEPI><<<grid, 32 * (4 + NEPI), smem, st>>>(ta, tb, tc, tp, p);
+    mdv_launch((gemm_kernel<TN, NEPI>), dim3(grid), dim3(32 * (4 + NEPI)), smem, st, ta, tb, tc, tp, p);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

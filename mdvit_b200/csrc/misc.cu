@@ -1,6 +1,8 @@
 // Small HBM-bound kernels: 1-channel heads (commuted 1x1 conv), bias-gradient column sums, casts / weight
 // preparation, the fused segmentation + MKD losses, fused AdamW.
 #include "../../include/mdvit_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -14,6 +16,7 @@ __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const TI* __restrict__ 
                                                           const float* __restrict__ bias, float* __restrict__ out, int M, int C,
                                                           int rows_per_sample, float drop_p, const unsigned long long* __restrict__ rng,
                                                           uint32_t stream) {
+    MDV_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -41,6 +44,7 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
                                                           const float* __restrict__ w, float* __restrict__ dx, float* __restrict__ dw,
                                                           float* __restrict__ db, int M, int C, int rows_per_sample, float drop_p,
                                                           const unsigned long long* __restrict__ rng, uint32_t stream, int rows_per_block) {
+    MDV_PDL_SYNC();
     // thread = channel (strided), block = chunk of rows of ONE sample
     uint32_t thr = 0, key = 0;
     float inv = 1.f;
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
 template <typename TI>
 __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ x, int ld, float* __restrict__ out, int M, int C,
                                                       int rows_per_block) {
+    MDV_PDL_SYNC();
     __shared__ float sh[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ x, i
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
                                                          long long M, int C, const float* __restrict__ rowscale, int rps, float drop_p,
                                                          const unsigned long long* __restrict__ rng, uint32_t stream) {
+    MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const long long total = M * c4n;
     uint32_t thr = 0, key = 0;
@@ -134,6 +140,7 @@ __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __re
                                                                 int ld_out, int M, int C, const float* __restrict__ rowscale, int rps,
                                                                 float drop_p, const unsigned long long* __restrict__ rng,
                                                                 uint32_t stream, float* __restrict__ colsum, int rows_per_block) {
+    MDV_PDL_SYNC();
     __shared__ float4 sh[256];
     const int cg = C >> 2;
     const int nty = 256 / cg;
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __re
 template <typename TI>
 __global__ void __launch_bounds__(256) add_f32_kernel(const TI* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out,
                                                        long long M, int C, int accumulate) {
+    MDV_PDL_SYNC();
     const long long total = M * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C);
@@ -202,6 +210,7 @@ __global__ void __launch_bounds__(256) add_f32_kernel(const TI* __restrict__ in,
 //  mode 3: src [R, Cin, 3, 3]                          -> dst [9*Cin (pad to rows), ld] transposed of mode 2
 __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int Cc,
                                                            int ld, int mode, int cin) {
+    MDV_PDL_SYNC();
     const long long total = (long long)R * Cc;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(idx / Cc), c = (int)(idx % Cc);
@@ -222,6 +231,7 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
 // d(conv weight [R,Cin,3,3]) += dW_im2col[R, ld] (column (i*3+j)*Cin+ci)
 __global__ void __launch_bounds__(256) unperm_conv_grad_kernel(const float* __restrict__ g, int ld, float* __restrict__ dw, int R,
                                                                 int cin) {
+    MDV_PDL_SYNC();
     const long long total = (long long)R * cin * 9;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(idx / (cin * 9)), c = (int)(idx % (cin * 9));
@@ -240,6 +250,7 @@ __device__ __forceinline__ float bce_term(float p, float y) {
 
 __global__ void __launch_bounds__(256) loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ aux,
                                                          const float* __restrict__ label, double* __restrict__ sums, long long n) {
+    MDV_PDL_SYNC();
     __shared__ float red[32];
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -266,6 +277,7 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(const float* __restrict_
 
 // losses[0..2] = L_seg, L_aux, L_kt  (fp32), from (possibly all-reduced) sums;  n_total = global element count.
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, double n_total, float* __restrict__ losses) {
+    MDV_PDL_SYNC();
     const double eps = 1e-5;
     const double bce_p = sums[0] / n_total, bce_q = sums[1] / n_total;
     const double dice_p = 1.0 - (2.0 * sums[2] + eps) / (sums[3] + sums[4] + eps);
@@ -282,6 +294,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
                                                         const float* __restrict__ label, const double* __restrict__ sums,
                                                         double n_total, const float* __restrict__ coef, float* __restrict__ dout,
                                                         float* __restrict__ daux, long long n) {
+    MDV_PDL_SYNC();
     const double eps = 1e-5;
     const float c_seg = coef[0], c_aux = coef[1], c_kt = coef[2];
     const float inv_n = (float)(1.0 / n_total);
@@ -313,6 +326,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 // hyper (device fp32[8]): lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, grad_scale
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                      float* __restrict__ v, const float* __restrict__ hyper, long long n) {
+    MDV_PDL_SYNC();
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6],
                 gs = hyper[7];
     const float step = lr / bc1, isb2 = rsqrtf(bc2);
@@ -345,11 +359,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     }
 }
 
-__global__ void rng_bump_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+__global__ void rng_bump_kernel(unsigned long long* rng) {
+    MDV_PDL_SYNC(); rng[1] += 1ull; }
 
 // DropPath per-sample scale: scale[b] = Bernoulli(1-p)/(1-p)   (timm DropPath, mdvit.py:339)
 __global__ void droppath_scale_kernel(float* __restrict__ scale, int B, float p, const unsigned long long* __restrict__ rng,
                                       uint32_t stream) {
+    MDV_PDL_SYNC();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     scale[b] = drop_scale(rng_key(rng, stream), (unsigned long long)b, drop_thresh(p), 1.f / (1.f - p));
@@ -364,6 +380,15 @@ inline int grid_for(long long total_threads) {
 }  // namespace
 
 long long g_mdv_launches = 0;
+int g_mdv_pdl = []() {
+    const char* e = getenv("MDV_NO_PDL");
+    return (e && e[0] == '1') ? 0 : 1;
+}();
+
+extern "C" int mdv_set_pdl(int enabled) {
+    g_mdv_pdl = enabled ? 1 : 0;
+    return MDV_OK;
+}
 
 extern "C" int mdv_version(void) { return 100; }
 
@@ -374,9 +399,9 @@ extern "C" int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const f
     if (!x || !w || !out || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
     const int blocks = mdv_cdiv(M, 8);
     if (x_bf16)
-        rowdot_fwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
+        mdv_launch(rowdot_fwd_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
     else
-        rowdot_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
+        mdv_launch(rowdot_fwd_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const float*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -389,9 +414,9 @@ extern "C" int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, cons
     const int blocks = mdv_cdiv(M, rpb);
     const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
     if (x_bf16)
-        rowdot_bwd_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)stream>>>(dlog, (const bf16*)x, w, dx, dw, db, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream, rpb);
+        mdv_launch(rowdot_bwd_kernel<bf16>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, dlog, (const bf16*)x, w, dx, dw, db, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream, rpb);
     else
-        rowdot_bwd_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(dlog, (const float*)x, w, dx, dw, db, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream, rpb);
+        mdv_launch(rowdot_bwd_kernel<float>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, dlog, (const float*)x, w, dx, dw, db, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream, rpb);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -404,8 +429,8 @@ extern "C" int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, 
     int rpb = mdv_cdiv(M, want);
     if (rpb < 64) rpb = 64;
     dim3 grid(cb, mdv_cdiv(M, rpb));
-    if (x_bf16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, C, rpb);
-    else colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, out, M, C, rpb);
+    if (x_bf16) mdv_launch(colsum_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, C, rpb);
+    else mdv_launch(colsum_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, ld, out, M, C, rpb);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -418,13 +443,13 @@ extern "C" int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_
         int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);
         const int nty = 256 / (C / 4);
         if (rpb < 4 * nty) rpb = 4 * nty;
-        cast_bf16_colsum_kernel<<<mdv_cdiv(M, rpb), 256, 0, (cudaStream_t)stream>>>(in, ld_in, (bf16*)out_bf16, ld_out, (int)M, C, rowscale,
+        mdv_launch(cast_bf16_colsum_kernel, dim3(mdv_cdiv(M, rpb)), dim3(256), 0, (cudaStream_t)stream, in, ld_in, (bf16*)out_bf16, ld_out, (int)M, C, rowscale,
                                                                                     rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
                                                                                     (const unsigned long long*)rng, drop_stream, colsum, rpb);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
-    cast_bf16_kernel<<<grid_for(M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(in, ld_in, (bf16*)out_bf16, ld_out, M, C, rowscale,
+    mdv_launch(cast_bf16_kernel, dim3(grid_for(M * (C / 4))), dim3(256), 0, (cudaStream_t)stream, in, ld_in, (bf16*)out_bf16, ld_out, M, C, rowscale,
                                                                                rows_per_scale > 0 ? rows_per_scale : 1, drop_p,
                                                                                (const unsigned long long*)rng, drop_stream);
     MDV_CHECK_LAUNCH();
@@ -434,22 +459,22 @@ extern "C" int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_
 extern "C" int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate,
                            void* stream) {
     if (!in || !out) return MDV_ERR_ARG;
-    if (in_bf16) add_f32_kernel<bf16><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ld_in, out, ld_out, M, C, accumulate);
-    else add_f32_kernel<float><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, out, ld_out, M, C, accumulate);
+    if (in_bf16) mdv_launch(add_f32_kernel<bf16>, dim3(grid_for(M * C)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)in, ld_in, out, ld_out, M, C, accumulate);
+    else mdv_launch(add_f32_kernel<float>, dim3(grid_for(M * C)), dim3(256), 0, (cudaStream_t)stream, (const float*)in, ld_in, out, ld_out, M, C, accumulate);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
 extern "C" int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream) {
     if (!src || !dst_bf16 || mode < 0 || mode > 3) return MDV_ERR_ARG;
-    prep_weight_kernel<<<grid_for((long long)R * Cc), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst_bf16, R, Cc, ld, mode, cin);
+    mdv_launch(prep_weight_kernel, dim3(grid_for((long long)R * Cc)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst_bf16, R, Cc, ld, mode, cin);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
 extern "C" int mdv_unperm_conv_grad(const float* g, int ld, float* dw, int R, int cin, void* stream) {
     if (!g || !dw) return MDV_ERR_ARG;
-    unperm_conv_grad_kernel<<<grid_for((long long)R * cin * 9), 256, 0, (cudaStream_t)stream>>>(g, ld, dw, R, cin);
+    mdv_launch(unperm_conv_grad_kernel, dim3(grid_for((long long)R * cin * 9)), dim3(256), 0, (cudaStream_t)stream, g, ld, dw, R, cin);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -460,14 +485,14 @@ extern "C" int mdv_loss_sums(const float* out, const float* aux, const float* la
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, 8 * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
-    loss_sums_kernel<<<grid_for(n), 256, 0, st>>>(out, aux, label, (double*)sums, n);
+    mdv_launch(loss_sums_kernel, dim3(grid_for(n)), dim3(256), 0, st, out, aux, label, (double*)sums, n);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
 extern "C" int mdv_loss_finalize(const void* sums, double n_total, float* losses, void* stream) {
     if (!sums || !losses) return MDV_ERR_ARG;
-    loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const double*)sums, n_total, losses);
+    mdv_launch(loss_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (const double*)sums, n_total, losses);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -475,7 +500,7 @@ extern "C" int mdv_loss_finalize(const void* sums, double n_total, float* losses
 extern "C" int mdv_loss_bwd(const float* out, const float* aux, const float* label, const void* sums, double n_total,
                             const float* coef, float* dout, float* daux, long long n, void* stream) {
     if (!out || !label || !sums || !coef || !dout || (aux && !daux)) return MDV_ERR_ARG;
-    loss_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(out, aux, label, (const double*)sums, n_total, coef, dout, daux, n);
+    mdv_launch(loss_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, aux, label, (const double*)sums, n_total, coef, dout, daux, n);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -484,21 +509,21 @@ extern "C" int mdv_adamw(float* p, const float* g, float* m, float* v, const flo
     if (!p || !g || !m || !v || !hyper || n <= 0) return MDV_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15)
         return MDV_ERR_ARG;
-    adamw_kernel<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, hyper, n);
+    mdv_launch(adamw_kernel, dim3(grid_for((n + 3) / 4)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, hyper, n);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
 extern "C" int mdv_rng_bump(void* rng, void* stream) {
     if (!rng) return MDV_ERR_ARG;
-    rng_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)rng);
+    mdv_launch(rng_bump_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (unsigned long long*)rng);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
 extern "C" int mdv_droppath_scale(float* scale, int B, float p, const void* rng, uint32_t drop_stream, void* stream) {
     if (!scale || B <= 0 || p < 0.f || p >= 1.f) return MDV_ERR_ARG;
-    droppath_scale_kernel<<<mdv_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(scale, B, p, (const unsigned long long*)rng, drop_stream);
+    mdv_launch(droppath_scale_kernel, dim3(mdv_cdiv(B, 128)), dim3(128), 0, (cudaStream_t)stream, scale, B, p, (const unsigned long long*)rng, drop_stream);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -15,6 +15,7 @@ template <int NV, int R>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps, bf16* __restrict__ y,
                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out, int M) {
+    MDV_PDL_SYNC();
     constexpr int C = NV * 64;
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                       const unsigned long long* __restrict__ rng, uint32_t drop_stream,
                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                       float* __restrict__ dbias_masked, int M) {
+    MDV_PDL_SYNC();
     constexpr int C = NV * 64;
     __shared__ float red[8][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -194,6 +196,7 @@ __device__ __forceinline__ float act_bwd(float v, int act) {
 // sums[c] += sum_m z[m,c]; sums[C+c] += sum_m z[m,c]^2   (double accumulators; block = 32 channels x 8 row lanes)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, double* __restrict__ sums, int M, int C,
                                                         int rows_per_block) {
+    MDV_PDL_SYNC();
     __shared__ float sh[2][8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int M, int C, float eps, float momentum, int training,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches, float* __restrict__ mean, float* __restrict__ rstd) {
+    MDV_PDL_SYNC();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && training && num_batches) *num_batches += 1;
     if (c >= C) return;
@@ -244,6 +248,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int act, TO* __restrict__ y,
                                                           long long total, int C) {
+    MDV_PDL_SYNC();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= total) return;
     const int c = (int)(i % C);
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int act, double* __restrict__ sums, int M, int C, int rows_per_block) {
+    MDV_PDL_SYNC();
     __shared__ float sh[2][8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -295,6 +301,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 // coef[c] = sum_g / M, coef[C+c] = sum_gxhat / M;  dgamma += sum_gxhat; dbeta += sum_g
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int M, int C, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    MDV_PDL_SYNC();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     coef[c] = (float)(sums[c] / M);
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int act, const float* __restrict__ coef, TO* __restrict__ dz,
                                                             long long total, int C) {
+    MDV_PDL_SYNC();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= total) return;
     const int c = (int)(i % C);
@@ -346,7 +354,7 @@ extern "C" int mdv_layernorm_fwd(const float* x, const float* gamma, const float
                                  float* rstd, int M, int C, void* stream) {
     if (!x || !y_bf16 || !gamma || !beta || M <= 0 || (C & 63) || C > 64 * LN_MAXV) return MDV_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-#define MDV_LN_FWD(NV, R) ln_fwd_kernel<NV, R><<<mdv_cdiv(M, 8 * R), 256, 0, st>>>(x, gamma, beta, eps, (bf16*)y_bf16, mean, rstd, M); break;
+#define MDV_LN_FWD(NV, R) mdv_launch((ln_fwd_kernel<NV, R>), dim3(mdv_cdiv(M, 8 * R)), dim3(256), 0, st, x, gamma, beta, eps, (bf16*)y_bf16, mean, rstd, M); break;
     switch (C >> 6) {
         case 1: MDV_LN_FWD(1, 4)
         case 2: MDV_LN_FWD(2, 4)
@@ -374,7 +382,7 @@ extern "C" int mdv_layernorm_bwd(const float* dy, const float* x, const float* m
     {                                                                                                                            \
         int blocks = mdv_cdiv(M, 8 * R);                                                                                         \
         if (blocks > 4 * MDV_NUM_SMS) blocks = 4 * MDV_NUM_SMS;                                                                  \
-        ln_bwd_kernel<NV, R><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, (bf16*)dx_masked_bf16, rowscale, rps,   \
+        mdv_launch((ln_bwd_kernel<NV, R>), dim3(blocks), dim3(256), 0, st, dy, x, mean, rstd, gamma, dres, dx, (bf16*)dx_masked_bf16, rowscale, rps,   \
                                                      drop_p, (const unsigned long long*)rng, drop_stream, dgamma, dbeta,         \
                                                      dbias_masked, M);                                                           \
     }                                                                                                                            \
@@ -406,12 +414,12 @@ extern "C" int mdv_bn_stats(const float* z, int M, int C, float eps, float momen
         if (e != cudaSuccess) return (int)e;
         const int rpb = stats_rows_per_block(M, C);
         dim3 grid(mdv_cdiv(C, 32), mdv_cdiv(M, rpb));
-        bn_stats_kernel<<<grid, 256, 0, st>>>(z, (double*)ws, M, C, rpb);
+        mdv_launch(bn_stats_kernel, dim3(grid), dim3(256), 0, st, z, (double*)ws, M, C, rpb);
         MDV_CHECK_LAUNCH();
     } else if (!running_mean || !running_var) {
         return MDV_ERR_ARG;
     }
-    bn_finalize_kernel<<<mdv_cdiv(C, 128), 128, 0, st>>>((const double*)ws, M, C, eps, momentum, training, running_mean,
+    mdv_launch(bn_finalize_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)ws, M, C, eps, momentum, training, running_mean,
                                                          running_var, num_batches_tracked, mean, rstd);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -423,9 +431,9 @@ extern "C" int mdv_bn_act_fwd(const float* z, const float* mean, const float* rs
     const long long total = (long long)M * C;
     const int blocks = mdv_cdiv(total / 4, 256);
     if (y_bf16)
-        bn_act_fwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(z, mean, rstd, gamma, beta, act, (bf16*)y, total, C);
+        mdv_launch(bn_act_fwd_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, z, mean, rstd, gamma, beta, act, (bf16*)y, total, C);
     else
-        bn_act_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(z, mean, rstd, gamma, beta, act, (float*)y, total, C);
+        mdv_launch(bn_act_fwd_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, z, mean, rstd, gamma, beta, act, (float*)y, total, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -442,16 +450,16 @@ extern "C" int mdv_bn_act_bwd(const float* dy, const float* z, const float* mean
     if (e != cudaSuccess) return (int)e;
     const int rpb = stats_rows_per_block(M, C);
     dim3 grid(mdv_cdiv(C, 32), mdv_cdiv(M, rpb));
-    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, act, sums, M, C, rpb);
+    mdv_launch(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, sums, M, C, rpb);
     MDV_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<mdv_cdiv(C, 128), 128, 0, st>>>(sums, M, C, coef, dgamma, dbeta);
+    mdv_launch(bn_bwd_finalize_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, sums, M, C, coef, dgamma, dbeta);
     MDV_CHECK_LAUNCH();
     const long long total = (long long)M * C;
     const int blocks = mdv_cdiv(total / 4, 256);
     if (dz_bf16)
-        bn_bwd_apply_kernel<bf16><<<blocks, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C);
+        mdv_launch(bn_bwd_apply_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C);
     else
-        bn_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>(dy, z, mean, rstd, gamma, beta, act, coef, (float*)dz, total, C);
+        mdv_launch(bn_bwd_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (float*)dz, total, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
