@@ -695,6 +695,14 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
     return MDV_OK;
 }
 
+// upper bound of chunks_for() over N: sizes the partial-sum scratch
+int max_chunks(int B, int C, int Ch) {
+    const int cpw = Ch <= 16 ? 64 : (Ch == 40 ? 40 : 64), ksplit = Ch <= 16 ? 1 : 2;
+    int want = mdv_cdiv(4 * MDV_NUM_SMS, B * (C / cpw) * ksplit);
+    if (want > 64) want = 64;
+    return want < 1 ? 1 : want;
+}
+
 int chunks_for(int B, int N, int blocks_y) {
     int want = mdv_cdiv(4 * MDV_NUM_SMS, B * blocks_y);
     const int maxc = N / 64 > 0 ? N / 64 : 1;
@@ -724,7 +732,8 @@ int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, f
     int nchunk = 0;
     float* part = ws;
     // zpart sits behind the largest possible partial buffer of this shape
-    float* zpart = ws + (size_t)B * 64 * C * CH;
+    const size_t mc = (size_t)max_chunks(B, C, CH);
+    float* zpart = ws + (size_t)B * mc * C * CH;
     int rc = launch_outer<CH, 0>(qkv, nullptr, nullptr, kmax, part, zpart, B, N, C, nchunk, st);
     if (rc) return rc;
     const long long tot = (long long)B * C * CH;
@@ -740,7 +749,8 @@ int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gat
     const int N = H * W;
     int nchunk = 0;
     float* part = ws;
-    float* dA = ws + (size_t)B * 64 * C * CH + (size_t)B * 64 * C;
+    const size_t mc = (size_t)max_chunks(B, C, CH);
+    float* dA = ws + (size_t)B * mc * C * CH + (size_t)B * mc * C;
     float* rk = dA + (size_t)B * C * CH;
     int rc = launch_outer<CH, 1>(qkv, dy, gate, nullptr, part, nullptr, B, N, C, nchunk, st);
     if (rc) return rc;
@@ -753,7 +763,8 @@ int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gat
 
 // scratch floats needed by attn_strip_fwd / attn_strip_bwd: partial sums (<= 64 chunks) + zpart + dA + rk
 long long attn_strip_ws_floats(int B, int C, int Ch) {
-    return (long long)B * 64 * C * Ch + (long long)B * 64 * C + (long long)B * C * Ch + (long long)B * C;
+    const long long mc = max_chunks(B, C, Ch);
+    return (long long)B * mc * C * Ch + (long long)B * mc * C + (long long)B * C * Ch + (long long)B * C;
 }
 
 int attn_strip_fwd(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out,

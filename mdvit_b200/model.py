@@ -361,6 +361,33 @@ class MDViT(_Trunk):
             return {'seg': [out, aux_out], 'feat': enc[3][0].mean(dim=1)}
         return [out, aux_out]
 
+    def forward_multi(self, x, domain_label, domains):
+        """The G single-domain forwards of one training step (multi_train_MDViT.py:129-146 calls forward once per domain)
+        as ONE pass over the stacked batch: x = cat of G equal mini-batches [G*B,3,H,W], domain_label [G*B, num_domains],
+        domains = the G domain keys ('0'..'3') in stacking order.  Every trunk kernel runs once on G*B samples (the trunk is
+        per-sample except BatchNorm, which is evaluated per group of B samples — ops.bn_groups — exactly as G separate
+        forwards would); each domain's auxiliary decoder then runs on its slice.  Returns [(out_d, aux_d)] per domain.
+        Equivalent to [self(x_d, label_d, d) for d in domains] up to dropout masks."""
+        G = len(domains)
+        if x.shape[0] % G:
+            raise ValueError("forward_multi needs G equal mini-batches stacked along dim 0")
+        B = x.shape[0] // G
+        img_size = x.shape[2:]
+        with ops.bn_groups(G if self.training else 1):
+            enc = self._trunk_forward(x, domain_label)
+            dec4, h, w = self._decode(enc, domain_label)
+        out = self._head(dec4, h, w, img_size)
+        res = []
+        for g, d in enumerate(domains):
+            sl = slice(g * B, (g + 1) * B)
+            aux_out = None
+            if d in ('0', '1', '2', '3'):
+                branch = getattr(self, f'debranch{int(d) + 1}')
+                feats = [e[0][sl] for e in enc] + [dec4[sl]]
+                aux_out = branch(feats, [(e[1], e[2]) for e in enc], img_size)
+            res.append((out[sl], aux_out))
+        return res
+
 
 class BASE(_Trunk):
     """Drop-in for Models.Transformer.base.BASE (base.py:340-512): MDViT without auxiliary branches."""

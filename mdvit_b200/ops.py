@@ -171,28 +171,61 @@ class BNState:
         self.bn, self.C = bn, C
 
 
+# BatchNorm groups: the fused multi-domain forward (model.MDViT.forward_multi) stacks the G single-domain mini-batches
+# of one training step along the batch axis so that every per-sample kernel runs once on G*B samples; BatchNorm, whose
+# batch statistics the reference computes per domain forward (mdvit.py:667 is called once per domain), is then
+# evaluated per group of M/G consecutive rows — same kernels, on row slices; running statistics are updated group by
+# group in order, exactly as G consecutive forwards would.
+_BN_GROUPS = 1
+
+
+class bn_groups:
+    def __init__(self, g):
+        self.g = int(g)
+
+    def __enter__(self):
+        global _BN_GROUPS
+        self.prev, _BN_GROUPS = _BN_GROUPS, self.g
+
+    def __exit__(self, *exc):
+        global _BN_GROUPS
+        _BN_GROUPS = self.prev
+
+
 def bn_forward(z, M, C, weight, bias, running_mean, running_var, nbt, training, act, out_bf16, eps=1e-5, momentum=0.1):
     dev = z.device
-    mean = torch.empty(C, dtype=F32, device=dev)
-    rstd = torch.empty(C, dtype=F32, device=dev)
-    ws = torch.empty(2 * C, dtype=torch.float64, device=dev) if training else None
-    check(L.lib().mdv_bn_stats(ptr(z), M, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(training), ptr(running_mean),
-                               ptr(running_var), ptr(nbt), ptr(mean), ptr(rstd), ptr(ws), L.stream()), "mdv_bn_stats")
+    G = _BN_GROUPS if training else 1
+    if M % G:
+        raise ValueError("BatchNorm groups must divide the batch")
+    Mg = M // G
+    z = z.view(M, C)
+    mean = torch.empty((G, C), dtype=F32, device=dev)
+    rstd = torch.empty((G, C), dtype=F32, device=dev)
     y = torch.empty((M, C), dtype=BF16 if out_bf16 else F32, device=dev)
-    check(L.lib().mdv_bn_act_fwd(ptr(z), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), act, ptr(y), int(out_bf16), M, C, L.stream()),
-          "mdv_bn_act_fwd")
+    for g in range(G):
+        zs = z[g * Mg:(g + 1) * Mg]
+        ws = torch.empty(2 * C, dtype=torch.float64, device=dev) if training else None
+        check(L.lib().mdv_bn_stats(ptr(zs), Mg, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(training), ptr(running_mean),
+                                   ptr(running_var), ptr(nbt), ptr(mean[g]), ptr(rstd[g]), ptr(ws), L.stream()), "mdv_bn_stats")
+        check(L.lib().mdv_bn_act_fwd(ptr(zs), ptr(mean[g]), ptr(rstd[g]), ptr(weight), ptr(bias), act, ptr(y[g * Mg:(g + 1) * Mg]),
+                                     int(out_bf16), Mg, C, L.stream()), "mdv_bn_act_fwd")
     return y, mean, rstd
 
 
 def bn_backward(dy, z, mean, rstd, weight, bias, act, M, C, dz_bf16=True):
-    """Returns dz and the values to return from backward for (gamma, beta)."""
+    """Returns dz and the values to return from backward for (gamma, beta).  mean/rstd are [G, C]: one row per group."""
     dev = z.device
-    ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
+    G = mean.shape[0]
+    Mg = M // G
+    dy, z = dy.view(M, C), z.view(M, C)
     dz = torch.empty((M, C), dtype=BF16 if dz_bf16 else F32, device=dev)
     dg, rg = gtarget(weight)
     db, rb = gtarget(bias)
-    check(L.lib().mdv_bn_act_bwd(ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), act, ptr(dz), int(dz_bf16), ptr(dg),
-                                 ptr(db), M, C, ptr(ws), L.stream()), "mdv_bn_act_bwd")
+    for g in range(G):
+        ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
+        sl = slice(g * Mg, (g + 1) * Mg)
+        check(L.lib().mdv_bn_act_bwd(ptr(dy[sl]), ptr(z[sl]), ptr(mean[g]), ptr(rstd[g]), ptr(weight), ptr(bias), act, ptr(dz[sl]),
+                                     int(dz_bf16), ptr(dg), ptr(db), Mg, C, ptr(ws), L.stream()), "mdv_bn_act_bwd")
     return dz, rg, rb
 
 

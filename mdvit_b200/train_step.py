@@ -125,10 +125,11 @@ class GradBucketer:
 
 class MKDTrainer:
     def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, process_group=None,
-                 num_domains=4, with_aux=True, schedule="single_sweep", n_buckets=8):
+                 num_domains=4, with_aux=True, schedule="single_sweep", n_buckets=8, fuse_domains=True):
         if schedule not in ("single_sweep", "reference"):
             raise ValueError("schedule must be 'single_sweep' or 'reference'")
         self.schedule = schedule
+        self.fuse_domains = fuse_domains      # stack the domain mini-batches into one trunk pass (MDViT.forward_multi)
         self.model = model
         self.alpha = alpha
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
@@ -177,6 +178,9 @@ class MKDTrainer:
 
     def forward_losses(self, batches):
         """batches: list of (img [B,3,H,W], label [B,1,H,W], domain index).  Returns [n_dom, 3] losses (seg, aux, kt)."""
+        if (self.fuse_domains and self.with_aux and len(batches) > 1 and hasattr(self.model, "forward_multi")
+                and len({tuple(b[0].shape) for b in batches}) == 1):
+            return self._forward_losses_fused(batches)
         out = []
         recording = self.bucketer is not None and self.bucketer.uses is None
         for i, (img, label, d) in enumerate(batches):
@@ -196,6 +200,28 @@ class MKDTrainer:
             out.append(ops.seg_losses(o, a, label, n_total=n_total, reduce_sums=self._reduce_sums if self.world > 1 else None))
         ops.set_forward_use_cb(None)
         ops.set_forward_tag(None)
+        return torch.stack(out)
+
+    def _forward_losses_fused(self, batches):
+        """All domain mini-batches in one trunk pass (same result as the per-domain loop up to dropout masks)."""
+        B = batches[0][0].shape[0]
+        G = len(batches)
+        dev = batches[0][0].device
+        x = torch.cat([b[0] for b in batches], dim=0)
+        dl = torch.zeros((G * B, self.num_domains), dtype=torch.float32, device=dev)
+        for g, (_, _, d) in enumerate(batches):
+            dl[g * B:(g + 1) * B, int(d)] = 1.0
+        recording = self.bucketer is not None and self.bucketer.uses is None
+        ops.set_forward_tag(0)
+        if recording:
+            ops.set_forward_use_cb(lambda tag, params: self.bucketer.record_use([id(p) for p in params if p is not None]))
+        res = self.model.forward_multi(x, dl, [str(b[2]) for b in batches])
+        ops.set_forward_use_cb(None)
+        ops.set_forward_tag(None)
+        out = []
+        for (o, a), (_, label, _) in zip(res, batches):
+            n_total = o.numel() * self.world
+            out.append(ops.seg_losses(o, a, label, n_total=n_total, reduce_sums=self._reduce_sums if self.world > 1 else None))
         return torch.stack(out)
 
     def _final_backward(self, loss):

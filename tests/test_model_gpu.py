@@ -141,10 +141,10 @@ def test_forward_variants_and_dispatch_quirks(dev):
         assert rel_l2(o2[0], o0[0]) < 5e-3 and rel_l2(o2[1], o3[1]) < 5e-3 and rel_l2(o0[1], o3[1]) > 2e-2
 
 
-def _grads_of_step(dev, schedule):
+def _grads_of_step(dev, schedule, fuse_domains=True):
     from mdvit_b200.train_step import MKDTrainer
     m = build(dev).train()
-    tr = MKDTrainer(m, schedule=schedule)
+    tr = MKDTrainer(m, schedule=schedule, fuse_domains=fuse_domains)
     batches = [tuple(t.to(dev) for t in synth.synth_batch(1, d, 2, 64, 64)) + (d,) for d in range(4)]
     tr.grad.zero_()
     losses = tr.forward_losses(batches)
@@ -182,6 +182,31 @@ def test_single_sweep_schedule_equals_reference_two_pass(dev):
     assert (l_ref - l_one).abs().max().item() < 2e-3 * l_ref.abs().max().item()
     # same math, different bf16 rounding points (one summed cotangent vs two)
     g_all, w_tight, w_loose, text = grad_report(g_one, g_ref)
+    assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
+
+
+def test_fused_multi_domain_forward_equals_per_domain_forwards(dev):
+    """MDViT.forward_multi (one trunk pass over the 4 stacked domain mini-batches, BatchNorm per group) against four
+    separate forwards: logits, BatchNorm running statistics, and the gradients of the whole MKD step."""
+    m1, m2 = build(dev).train(), build(dev).train()
+    batches = [tuple(t.to(dev) for t in synth.synth_batch(1, d, 2, 64, 64)) + (d,) for d in range(4)]
+    with torch.no_grad():
+        sep = [m1(img, onehot(d, 2, dev), str(d)) for img, _, d in batches]
+        x = torch.cat([b[0] for b in batches])
+        dl = torch.cat([onehot(d, 2, dev) for _, _, d in batches])
+        fused = m2.forward_multi(x, dl, [str(d) for _, _, d in batches])
+    for (o1, a1), (o2, a2) in zip(sep, fused):
+        assert rel_l2(o2, o1) < 5e-3 and rel_l2(a2, a1) < 1e-2
+    sd1, sd2 = m1.state_dict(), m2.state_dict()
+    for k in sd1:
+        if "running" in k:
+            assert rel(sd2[k], sd1[k]) < 5e-3, k
+        if k.endswith("num_batches_tracked") and not k.startswith("debranch"):
+            assert int(sd1[k]) == int(sd2[k]) == 4, k
+    _, _, l_sep, g_sep = _grads_of_step(dev, "single_sweep", fuse_domains=False)
+    _, _, l_fus, g_fus = _grads_of_step(dev, "single_sweep", fuse_domains=True)
+    assert (l_sep - l_fus).abs().max().item() < 5e-3 * l_sep.abs().max().item()
+    g_all, w_tight, w_loose, text = grad_report(g_fus, g_sep)
     assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
 
 
