@@ -155,7 +155,7 @@ extern "C" long long mdv_attn_ws_floats(int B, int C, int heads) { return attn_s
 
 extern "C" int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float* crpe_w3, const float* crpe_b3,
                             const float* crpe_w5, const float* crpe_b5, const float* crpe_w7, const float* crpe_b7, float* stats,
-                            float* ws, void* out_bf16, int B, int H, int W, int C, int heads, void* stream) {
+                            float* ws, void* out_bf16, void* e_out_bf16, int B, int H, int W, int C, int heads, void* stream) {
     if (!qkv_bf16 || !stats || !ws || !out_bf16 || heads != 8 || (C % 64)) return MDV_ERR_ARG;
     const int Ch = C / heads, N = H * W;
     cudaStream_t st = (cudaStream_t)stream;
@@ -175,17 +175,17 @@ extern "C" int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float
     }
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
     const float scale = 1.0f / sqrtf((float)Ch);
-    return attn_strip_fwd(qkv, gate, cw, kmax, zsum, A, ws, (bf16*)out_bf16, scale, B, H, W, C, Ch, st);
+    return attn_strip_fwd(qkv, gate, cw, kmax, zsum, A, ws, (bf16*)out_bf16, (bf16*)e_out_bf16, scale, B, H, W, C, Ch, st);
 }
 
 // ws: mdv_attn_ws_floats() floats of scratch.  dqkv bf16 [B,N,3C] is overwritten; crpe grads (may all be NULL: skipped)
 // and dgate accumulate (+=).
-extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, const float* gate, const float* crpe_w3,
+extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, const void* e_bf16, const float* gate, const float* crpe_w3,
                             const float* crpe_b3, const float* crpe_w5, const float* crpe_b5, const float* crpe_w7,
                             const float* crpe_b7, const float* stats, void* dqkv_bf16, float* dgate, float* dcrpe_w3,
                             float* dcrpe_b3, float* dcrpe_w5, float* dcrpe_b5, float* dcrpe_w7, float* dcrpe_b7, float* ws, int B,
                             int H, int W, int C, int heads, void* stream) {
-    if (!qkv_bf16 || !dy_bf16 || !stats || !dqkv_bf16 || !ws || heads != 8 || (C % 64)) return MDV_ERR_ARG;
+    if (!qkv_bf16 || !dy_bf16 || !e_bf16 || !stats || !dqkv_bf16 || !ws || heads != 8 || (C % 64)) return MDV_ERR_ARG;
     if (gate && (!y_bf16 || !dgate)) return MDV_ERR_ARG;
     const int Ch = C / heads;
     const float* kmax = stats;
@@ -195,7 +195,7 @@ extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const voi
     CrpeG cg = {{dcrpe_w3, dcrpe_w5, dcrpe_w7}, {dcrpe_b3, dcrpe_b5, dcrpe_b7}};
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
     return attn_strip_bwd((const bf16*)qkv_bf16, (const bf16*)dy_bf16, (const bf16*)y_bf16, gate, kmax, zsum, A, ws, cw, cg,
-                          (bf16*)dqkv_bf16, dgate, scale, B, H, W, C, Ch, (cudaStream_t)stream);
+                          (const bf16*)e_bf16, (bf16*)dqkv_bf16, dgate, scale, B, H, W, C, Ch, (cudaStream_t)stream);
 }
 
 extern "C" int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,

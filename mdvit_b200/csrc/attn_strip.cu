@@ -253,7 +253,7 @@ __device__ __forceinline__ void load_taps(float2* sW, const CrpeW& cw, int cg0, 
 template <int CH, int WIN>
 __device__ __forceinline__ void attn_fwd_strip_body(const bf16* __restrict__ qkv, const float* __restrict__ A,
                                                     const float* __restrict__ gate, const CrpeW& cw, bf16* __restrict__ out,
-                                                    float scale, int H, int Wd, int C, uint8_t* smem_s) {
+                                                    bf16* __restrict__ eout, float scale, int H, int Wd, int C, uint8_t* smem_s) {
     using G = Cfg<CH>;
     const int grp0 = 0;
     uint32_t* sV = reinterpret_cast<uint32_t*>(smem_s);
@@ -339,6 +339,8 @@ __device__ __forceinline__ void attn_fwd_strip_body(const bf16* __restrict__ qkv
                 const float2 q = up2(qw[t]);
                 const float2 y = mul2(gt, fma2(splat(scale), fa[t], mul2(q, e[t])));
                 *reinterpret_cast<uint32_t*>(out + ((size_t)b * N + n0 + t) * C + c0) = f2_to_bf2(y.x, y.y);
+                // E = dwconv(V) + b is kept for the backward pass (dQ needs it; recomputing it there costs a third of that kernel)
+                if (eout) *reinterpret_cast<uint32_t*>(eout + ((size_t)b * N + n0 + t) * C + c0) = f2_to_bf2(e[t].x, e[t].y);
             }
         }
     }
@@ -353,13 +355,15 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
                                                     const float* __restrict__ A, const float* __restrict__ dA,
                                                     const float* __restrict__ rk, const float* __restrict__ kmax,
                                                     const float* __restrict__ zsum, const CrpeW& cw, const CrpeG& cg,
-                                                    bf16* __restrict__ dqkv, float* __restrict__ dgate, float scale, int H,
-                                                    int Wd, int C, uint8_t* smem_s) {
+                                                    const bf16* __restrict__ ein, bf16* __restrict__ dqkv,
+                                                    float* __restrict__ dgate, float scale, int H, int Wd, int C, uint8_t* smem_s) {
     using G = Cfg<CH>;
     const int grp0 = 0;
-    uint32_t* sV = reinterpret_cast<uint32_t*>(smem_s);
-    uint32_t* sE = sV + tile_words(WIN);
-    float2* sW = reinterpret_cast<float2*>(sE + tile_words(WIN));
+    const bool want_w = cg.w[0] != nullptr;
+    // the V tile is only needed by the weight-gradient pass: E = dwconv(V) + b comes saved from the forward
+    uint32_t* sE = reinterpret_cast<uint32_t*>(smem_s);
+    uint32_t* sV = sE + tile_words(WIN);
+    float2* sW = reinterpret_cast<float2*>(sV + (want_w ? tile_words(WIN) : 0));
     // per (j pair, lane): the two j-values of a matrix entry for each of the lane's two channels v0, v1
     float4* sAt = reinterpret_cast<float4*>(sW + WIN * WIN * 32);   // (A[v0][2jj],  A[v0][2jj+1],  A[v1][2jj],  A[v1][2jj+1])
     float4* sdA = sAt + (CH / 2) * 32;                               // (dA[2jj][v0], dA[2jj+1][v0], dA[2jj][v1], dA[2jj+1][v1])
@@ -372,8 +376,7 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     const int nwarp = blockDim.x >> 5;
     const bf16* qkv_b = qkv + (size_t)b * N * 3 * C;
     const bf16* dy_b = dy + (size_t)b * N * C;
-    const bool want_w = cg.w[0] != nullptr;
-    load_halo<G::ACT>(sV, qkv_b + 2 * C, 3 * C, cg0, g, H, Wd);
+    if (want_w) load_halo<G::ACT>(sV, qkv_b + 2 * C, 3 * C, cg0, g, H, Wd);
     {   // dE = g * dY * Q at every halo position (loads batched: 2 x UB requests in flight per thread)
         const int total = g.PH * g.PW * 8;
         constexpr int UB = 4;
@@ -464,49 +467,41 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     for (int s = warp; s < nstrips; s += nwarp) {
         const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
         const size_t n0 = (size_t)(g.ty0 + py) * Wd + g.tx0 + px0;
-        // this strip's own pixels: issued before the convolution loops so their latency hides behind the math
-        uint32_t qw[TX], kw[TX], dw[TX], yw[TX];
+        // this strip's own pixels: issued before the convolution loop so their latency hides behind the math
+        uint32_t kw[TX], dw[TX], yw[TX], ew[TX], vw[TX];
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
             const bool ok = act && px0 + t < g.tw;
-            qw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + c0) : 0u;
             kw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + C + c0) : 0u;
+            vw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + 2 * C + c0) : 0u;
             dw[t] = ok ? *reinterpret_cast<const uint32_t*>(dy_b + (n0 + t) * C + c0) : 0u;
+            ew[t] = ok ? *reinterpret_cast<const uint32_t*>(ein + ((size_t)b * N + n0 + t) * C + c0) : 0u;
             yw[t] = (ok && gate) ? *reinterpret_cast<const uint32_t*>(yout + ((size_t)b * N + n0 + t) * C + c0) : 0u;
         }
-        float2 e[TX], tc[TX];
+        // transposed convolution of dE (flipped taps): dV_conv[n] = sum_ij w[i,j] dE[n - (i-R, j-R)]
+        float2 tc[TX];
 #pragma unroll
-        for (int t = 0; t < TX; ++t) {
-            e[t] = bias;
-            tc[t] = make_float2(0.f, 0.f);
-        }
+        for (int t = 0; t < TX; ++t) tc[t] = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int i = 0; i < WIN; ++i) {
-            const uint32_t* rowv = sV + ((py + i) * g.PW + px0) * 32 + lane;
             const uint32_t* rowe = sE + ((py + i) * g.PW + px0) * 32 + lane;
-            float2 inv[TX + WIN - 1], ine[TX + WIN - 1];
+            float2 ine[TX + WIN - 1];
 #pragma unroll
-            for (int t = 0; t < TX + WIN - 1; ++t) {
-                inv[t] = up2(rowv[t * 32]);
-                ine[t] = up2(rowe[t * 32]);
-            }
+            for (int t = 0; t < TX + WIN - 1; ++t) ine[t] = up2(rowe[t * 32]);
 #pragma unroll
             for (int j = 0; j < WIN; ++j) {
-                const float2 w = sW[(i * WIN + j) * 32 + lane];
-                const float2 wf = sW[(WIN * WIN - 1 - (i * WIN + j)) * 32 + lane];   // transposed convolution: flipped taps
+                const float2 wf = sW[(WIN * WIN - 1 - (i * WIN + j)) * 32 + lane];
 #pragma unroll
-                for (int t = 0; t < TX; ++t) {
-                    e[t] = fma2(w, inv[t + j], e[t]);
-                    tc[t] = fma2(wf, ine[t + j], tc[t]);
-                }
+                for (int t = 0; t < TX; ++t) tc[t] = fma2(wf, ine[t + j], tc[t]);
             }
         }
-        uint32_t vw[TX];
+        float2 e[TX];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) e[t] = up2(ew[t]);
         float2 dF[TX], S[TX];
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
             const bool ok = act && px0 + t < g.tw;
-            vw[t] = sV[((py + g.R) * g.PW + px0 + g.R + t) * 32 + lane];
             const float2 kk = up2(kw[t]), d = up2(dw[t]);
             dF[t] = mul2(gt, d);
             S[t] = ok ? make_float2(__expf(kk.x - km.x) * zi.x, __expf(kk.y - km.y) * zi.y) : make_float2(0.f, 0.f);
@@ -623,13 +618,13 @@ __device__ __forceinline__ int win_of_group(int grp) { return win_of_head(((grp 
 template <int CH>
 __global__ void __launch_bounds__(256) attn_fwd_strip_kernel(const bf16* __restrict__ qkv, const float* __restrict__ A,
                                                               const float* __restrict__ gate, CrpeW cw, bf16* __restrict__ out,
-                                                              float scale, int H, int Wd, int C) {
+                                                              bf16* __restrict__ eout, float scale, int H, int Wd, int C) {
     MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
-    if (win == 3) attn_fwd_strip_body<CH, 3>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
-    else if (win == 5) attn_fwd_strip_body<CH, 5>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
-    else attn_fwd_strip_body<CH, 7>(qkv, A, gate, cw, out, scale, H, Wd, C, smem_dyn);
+    if (win == 3) attn_fwd_strip_body<CH, 3>(qkv, A, gate, cw, out, eout, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_fwd_strip_body<CH, 5>(qkv, A, gate, cw, out, eout, scale, H, Wd, C, smem_dyn);
+    else attn_fwd_strip_body<CH, 7>(qkv, A, gate, cw, out, eout, scale, H, Wd, C, smem_dyn);
 }
 
 constexpr int BWD_THREADS = 512;   // 16 warps share one tile: twice the latency hiding of 8 (the kernel is register/latency bound)
@@ -641,14 +636,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf
                                                               const float* __restrict__ A, const float* __restrict__ dA,
                                                               const float* __restrict__ rk, const float* __restrict__ kmax,
                                                               const float* __restrict__ zsum, CrpeW cw, CrpeG cg,
-                                                              bf16* __restrict__ dqkv, float* __restrict__ dgate, float scale, int H,
-                                                              int Wd, int C) {
+                                                              const bf16* __restrict__ ein, bf16* __restrict__ dqkv,
+                                                              float* __restrict__ dgate, float scale, int H, int Wd, int C) {
     MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
-    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
-    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
-    else attn_bwd_strip_body<CH, 7, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    else attn_bwd_strip_body<CH, 7, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, H, Wd, C, smem_dyn);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -664,8 +659,8 @@ inline dim3 tile_grid(int B, int H, int W, int groups) {
 }
 
 template <int CH>
-int launch_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& cw, bf16* out, float scale, int B, int H, int W, int C,
-               cudaStream_t st) {
+int launch_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& cw, bf16* out, bf16* eout, float scale, int B, int H, int W,
+               int C, cudaStream_t st) {
     const int smem = tile_words(7) * 4 + 49 * 32 * 8 + CH * 32 * 8;     // sized for the widest window
     static bool configured = false;
     if (!configured) {
@@ -673,23 +668,25 @@ int launch_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& 
         if (rc) return rc;
         configured = true;
     }
-    mdv_launch(attn_fwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(256), smem, st, qkv, A, gate, cw, out, scale, H, W, C);
+    mdv_launch(attn_fwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(256), smem, st, qkv, A, gate, cw, out, eout, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
 template <int CH>
 int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* A, const float* dA, const float* rk,
-               const float* kmax, const float* zsum, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B,
-               int H, int W, int C, cudaStream_t st) {
-    const int smem = 2 * tile_words(7) * 4 + 49 * 32 * 8 + 3 * CH * 32 * 8 + 50 * 64 * 4;
+               const float* kmax, const float* zsum, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate,
+               float scale, int B, int H, int W, int C, cudaStream_t st) {
+    const int full = 2 * tile_words(7) * 4 + 49 * 32 * 8 + 3 * CH * 32 * 8 + 50 * 64 * 4;
+    // activation-gradient-only pass: no V tile -> half the shared memory, two blocks per SM
+    const int smem = cg.w[0] ? full : full - tile_words(7) * 4;
     static bool configured = false;
     if (!configured) {
-        int rc = set_smem(attn_bwd_strip_kernel<CH>, smem);
+        int rc = set_smem(attn_bwd_strip_kernel<CH>, full);
         if (rc) return rc;
         configured = true;
     }
-    mdv_launch(attn_bwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv,
+    mdv_launch(attn_bwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv,
                                                                                        dgate, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -726,8 +723,8 @@ int launch_outer(const bf16* qkv, const bf16* dy, const float* gate, const float
 }
 
 template <int CH>
-int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out, float scale,
-             int B, int H, int W, int C, cudaStream_t st) {
+int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out, bf16* eout,
+             float scale, int B, int H, int W, int C, cudaStream_t st) {
     const int N = H * W;
     int nchunk = 0;
     float* part = ws;
@@ -739,13 +736,13 @@ int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, f
     const long long tot = (long long)B * C * CH;
     mdv_launch(attn_combine_fwd_kernel, dim3(mdv_cdiv(tot, 256)), dim3(256), 0, st, part, zpart, A, zsum, C, CH, nchunk, tot);
     MDV_CHECK_LAUNCH();
-    return launch_fwd<CH>(qkv, A, gate, cw, out, scale, B, H, W, C, st);
+    return launch_fwd<CH>(qkv, A, gate, cw, out, eout, scale, B, H, W, C, st);
 }
 
 template <int CH>
 int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum, const float* A,
-             float* ws, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B, int H, int W, int C,
-             cudaStream_t st) {
+             float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate, float scale, int B, int H, int W,
+             int C, cudaStream_t st) {
     const int N = H * W;
     int nchunk = 0;
     float* part = ws;
@@ -756,7 +753,7 @@ int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gat
     if (rc) return rc;
     mdv_launch(attn_combine_bwd_kernel, dim3(mdv_cdiv(B * C, 8)), dim3(256), 0, st, part, A, dA, rk, scale, C, CH, nchunk, B * C);
     MDV_CHECK_LAUNCH();
-    return launch_bwd<CH>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+    return launch_bwd<CH>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
 }
 
 }  // namespace
@@ -768,24 +765,24 @@ long long attn_strip_ws_floats(int B, int C, int Ch) {
 }
 
 int attn_strip_fwd(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out,
-                   float scale, int B, int H, int W, int C, int Ch, cudaStream_t st) {
+                   bf16* eout, float scale, int B, int H, int W, int C, int Ch, cudaStream_t st) {
     switch (Ch) {
-        case 8: return fwd_impl<8>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
-        case 16: return fwd_impl<16>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
-        case 40: return fwd_impl<40>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
-        case 64: return fwd_impl<64>(qkv, gate, cw, kmax, zsum, A, ws, out, scale, B, H, W, C, st);
+        case 8: return fwd_impl<8>(qkv, gate, cw, kmax, zsum, A, ws, out, eout, scale, B, H, W, C, st);
+        case 16: return fwd_impl<16>(qkv, gate, cw, kmax, zsum, A, ws, out, eout, scale, B, H, W, C, st);
+        case 40: return fwd_impl<40>(qkv, gate, cw, kmax, zsum, A, ws, out, eout, scale, B, H, W, C, st);
+        case 64: return fwd_impl<64>(qkv, gate, cw, kmax, zsum, A, ws, out, eout, scale, B, H, W, C, st);
         default: return MDV_ERR_UNSUPPORTED;
     }
 }
 
 int attn_strip_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum,
-                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, bf16* dqkv, float* dgate, float scale, int B, int H, int W,
-                   int C, int Ch, cudaStream_t st) {
+                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate, float scale,
+                   int B, int H, int W, int C, int Ch, cudaStream_t st) {
     switch (Ch) {
-        case 8: return bwd_impl<8>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
-        case 16: return bwd_impl<16>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
-        case 40: return bwd_impl<40>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
-        case 64: return bwd_impl<64>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, dqkv, dgate, scale, B, H, W, C, st);
+        case 8: return bwd_impl<8>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
+        case 16: return bwd_impl<16>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
+        case 40: return bwd_impl<40>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
+        case 64: return bwd_impl<64>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
         default: return MDV_ERR_UNSUPPORTED;
     }
 }

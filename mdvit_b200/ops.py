@@ -357,8 +357,10 @@ class BlockFn(torch.autograd.Function):
             stats = torch.empty(lib.mdv_attn_stats_floats(B, C, HEADS), dtype=F32, device=dev)
             ws = torch.empty(lib.mdv_attn_ws_floats(B, C, HEADS), dtype=F32, device=dev)
             y = torch.empty((M, C), dtype=BF16, device=dev)
+            # dwconv(V)+b is kept for the backward pass (grad mode is always off inside Function.forward: ask ctx instead)
+            ecrpe = torch.empty((M, C), dtype=BF16, device=dev) if any(ctx.needs_input_grad) else None
             check(lib.mdv_attn_fwd(ptr(qkv), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b), ptr(stats), ptr(ws),
-                                   ptr(y), B, H, W, C, HEADS, L.stream()), "mdv_attn_fwd")
+                                   ptr(y), ptr(ecrpe), B, H, W, C, HEADS, L.stream()), "mdv_attn_fwd")
             p_drop = drop if training else 0.0
             sid = [new_stream_id() for _ in range(5)] if training and (drop > 0 or dpr > 0) else [0] * 5
             dp1 = dp2 = None
@@ -380,7 +382,7 @@ class BlockFn(torch.autograd.Function):
             x3 = torch.empty((B, N, C), dtype=F32, device=dev)
             gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2, drop_p=p_drop,
                     drop_stream=sid[2], rowscale=dp2, rows_per_scale=N)
-        ctx.save_for_backward(x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2)
+        ctx.save_for_backward(x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2, ecrpe)
         ctx.params = (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2,
                       n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         ctx.meta = (B, N, C, H, W, hidden, p_drop, sid)
@@ -389,7 +391,7 @@ class BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx3):
-        (x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2) = ctx.saved_tensors
+        (x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2, ecrpe) = ctx.saved_tensors
         (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2, n2w, n2b,
          fc1_w, fc1_b, fc2_w, fc2_b) = ctx.params
         B, N, C, H, W, hidden, p_drop, sid = ctx.meta
@@ -421,7 +423,7 @@ class BlockFn(torch.autograd.Function):
             da_live = gate is not None and da_w1.requires_grad and da_w2.requires_grad
             dgate = torch.zeros((B, C), dtype=F32, device=dev) if gate is not None else None
             ws = torch.empty(lib.mdv_attn_ws_floats(B, C, HEADS), dtype=F32, device=dev)
-            check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
+            check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(ecrpe), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
                                    ptr(stats), ptr(dqkv), ptr(dgate), ptr(G["c3w"]), ptr(G["c3b"]), ptr(G["c5w"]), ptr(G["c5b"]),
                                    ptr(G["c7w"]), ptr(G["c7b"]), ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")
             if da_live:

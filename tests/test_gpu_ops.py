@@ -451,17 +451,18 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
     ws = torch.empty(lib.mdv_attn_ws_floats(B, C, 8), device=dev)
     y = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
     cw = [sd[f"crpe.conv_list.{i}.{n}"].detach() for i in range(3) for n in ("weight", "bias")]
-    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(ws), P(y), B, H, W, C, 8, L.stream()), "attn_fwd")
+    ecrpe = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(ws), P(y), P(ecrpe), B, H, W, C, 8, L.stream()), "attn_fwd")
     assert rel(y, yref) < BF16_TOL
     y2 = torch.empty_like(y)                       # no atomics in the forward: bit-reproducible
-    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(ws), P(y2), B, H, W, C, 8, L.stream()), "attn_fwd")
+    L.check(lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t_) for t_ in cw], P(stats), P(ws), P(y2), None, B, H, W, C, 8, L.stream()), "attn_fwd")
     assert torch.equal(y, y2)
     dy = torch.randn(B, N, C, device=dev).bfloat16()
     yref.backward(dy.float())
     dqkv = torch.empty_like(qkv)
     dgate = torch.zeros(B, C, device=dev) if sup else None
     gcw = [torch.zeros_like(t_) for t_ in cw]
-    L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv), P(dgate), *[P(t_) for t_ in gcw], P(ws),
+    L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv), P(dgate), *[P(t_) for t_ in gcw], P(ws),
                              B, H, W, C, 8, L.stream()), "attn_bwd")
     g = q32.grad
     for sl in (slice(0, C), slice(C, 2 * C), slice(2 * C, 3 * C)):
@@ -473,6 +474,6 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
         assert rel(dgate, gref.grad) < BF16_TOL
         # activation-gradient-only mode (CRPE gradient pointers NULL): same dqkv, dgate still accumulated
         dqkv2, dgate2 = torch.empty_like(qkv), torch.zeros(B, C, device=dev)
-        L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv2), P(dgate2), None, None, None, None,
+        L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv2), P(dgate2), None, None, None, None,
                                  None, None, P(ws), B, H, W, C, 8, L.stream()), "attn_bwd")
         assert torch.equal(dqkv2, dqkv) and rel(dgate2, gref.grad) < BF16_TOL
