@@ -90,6 +90,13 @@ int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const f
 int mdv_bn_act_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
                    void* stream);
+/* Same with a rank-1 output gradient dy[m,c] = dlog[m] * wrow[c] * dropout2d_mask(m / rows_per_sample, c) generated on the
+ * fly: the backward of Dropout2d + the 1-channel `linear_out` head of MLPDecoderFM (Decoders.py:334-337) never
+ * materialises the [M, C] gradient of the BatchNorm output. */
+int mdv_bn_act_bwd_rank1(const float* dlog, const float* wrow, int rows_per_sample, float drop_p, const void* rng,
+                         uint32_t drop_stream, const float* z, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
+                         void* stream);
 
 /* ------------------------------------------------------------------ stencils (token-major / NHWC) */
 /* depthwise 3x3, pad 1 (ConvPosEnc mpvit.py:244-246 with residual=1; patch-embed dwconv mdvit.py:118).

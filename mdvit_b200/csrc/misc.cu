@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
 #pragma unroll 4
             for (; r < rend; ++r) {
                 const float d = __ldg(dlog + r);
-                dx[(size_t)r * C + c] = d * wm;
+                if (dx) dx[(size_t)r * C + c] = d * wm;
                 acc += d * ldf(x + (size_t)r * C + c);
             }
             if (dw) atomicAdd(dw + c, acc * m);      // dw[c] += sum_m dlog[m] x[m,c] mask(b,c)
@@ -408,7 +408,7 @@ extern "C" int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const f
 
 extern "C" int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, const float* w, float* dx, float* dw, float* db, int M,
                               int C, int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
-    if (!dlog || !x || !w || !dx || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
+    if (!dlog || !x || !w || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
     int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);
     if (rpb < 8) rpb = 8;
     const int blocks = mdv_cdiv(M, rpb);

@@ -268,22 +268,52 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
 }
 
 // sums[c] += sum g, sums[C+c] += sum g*xhat with g = dy * act'(bn(z))
+// Rank-1 output gradient (the commuted 1-channel head, Decoders.py:334-337): dy[m,c] = dlog[m] * wrow[c] * dropout2d_mask(m / rps, c)
+// is generated on the fly instead of being materialised as an [M, C] fp32 tensor.
+struct Rank1Dy {
+    const float* dlog;      // [M] or NULL (then the dense dy is used)
+    const float* wrow;      // [C]
+    const unsigned long long* rng;
+    int rps;                // rows per sample
+    float drop_p;
+    uint32_t stream;
+};
+__device__ __forceinline__ float rank1_wm(const Rank1Dy& r1, int b, int c, int C) {
+    float wv = __ldg(r1.wrow + c);
+    if (r1.drop_p > 0.f) wv *= drop_scale(rng_key(r1.rng, r1.stream), (unsigned long long)b * C + c, drop_thresh(r1.drop_p), 1.f / (1.f - r1.drop_p));
+    return wv;
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             int act, double* __restrict__ sums, int M, int C, int rows_per_block) {
+                                                             int act, double* __restrict__ sums, int M, int C, int rows_per_block,
+                                                             Rank1Dy r1) {
     MDV_PDL_SYNC();
     __shared__ float sh[2][8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    const int r0 = blockIdx.y * rows_per_block, r1e = min(M, r0 + rows_per_block);
     float s = 0.f, q = 0.f;
     if (c < C) {
         const float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
-        for (int r = r0 + ty; r < r1; r += 8) {
+        int cur_b = -1;
+        float wm = 0.f;
+        for (int r = r0 + ty; r < r1e; r += 8) {
             const size_t o = (size_t)r * C + c;
             const float xh = (__ldg(z + o) - mu) * rs;
-            const float gg = __ldg(dy + o) * act_bwd(xh * g + b, act);
+            float d;
+            if (r1.dlog) {
+                const int bb = r / r1.rps;
+                if (bb != cur_b) {
+                    cur_b = bb;
+                    wm = rank1_wm(r1, bb, c, C);
+                }
+                d = __ldg(r1.dlog + r) * wm;
+            } else {
+                d = __ldg(dy + o);
+            }
+            const float gg = d * act_bwd(xh * g + b, act);
             s += gg;
             q += gg * xh;
         }
@@ -315,13 +345,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int act, const float* __restrict__ coef, TO* __restrict__ dz,
-                                                            long long total, int C) {
+                                                            long long total, int C, Rank1Dy r1) {
     MDV_PDL_SYNC();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= total) return;
     const int c = (int)(i % C);
     float4 zv = *reinterpret_cast<const float4*>(z + i);
-    float4 dv = *reinterpret_cast<const float4*>(dy + i);
+    float4 dv;
+    if (r1.dlog) {
+        // 32-bit index math (total < 2^31 checked on the host); b*C + c is a multiple of 4: two pair-hashes give the 4 masks
+        const int row = (int)i / C;
+        const int bb = row / r1.rps;
+        const float dl = __ldg(r1.dlog + row);
+        const float4 wv = *reinterpret_cast<const float4*>(r1.wrow + c);
+        float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
+        if (r1.drop_p > 0.f) {
+            const uint32_t key = rng_key(r1.rng, r1.stream), thr = drop_thresh(r1.drop_p);
+            const float inv = 1.f / (1.f - r1.drop_p);
+            const uint32_t pr = (uint32_t)(bb * C + c) >> 1;
+            const uint32_t h0 = drop_hash(key, pr), h1 = drop_hash(key, pr + 1);
+            m0 = drop_lo(h0, thr, inv); m1 = drop_hi(h0, thr, inv); m2 = drop_lo(h1, thr, inv); m3 = drop_hi(h1, thr, inv);
+        }
+        dv = make_float4(dl * wv.x * m0, dl * wv.y * m1, dl * wv.z * m2, dl * wv.w * m3);
+    } else {
+        dv = *reinterpret_cast<const float4*>(dy + i);
+    }
     float zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -439,27 +487,48 @@ extern "C" int mdv_bn_act_fwd(const float* z, const float* mean, const float* rs
 }
 
 // ws: >= 2*C doubles + 2*C floats.  dz = d(loss)/dz for y = act(BN_train(z)); dgamma/dbeta accumulate.
+static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
+                           cudaStream_t st);
+
 extern "C" int mdv_bn_act_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                               const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C,
                               void* ws, void* stream) {
     if (!dy || !z || !dz || !ws || M <= 0 || (C & 3)) return MDV_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
+    Rank1Dy r1 = {};
+    return bn_act_bwd_impl(dy, r1, z, mean, rstd, gamma, beta, act, dz, dz_bf16, dgamma, dbeta, M, C, ws, (cudaStream_t)stream);
+}
+
+// Same, with the output gradient given in rank-1 form dy[m,c] = dlog[m] * wrow[c] * dropout2d_mask(m / rows_per_sample, c).
+extern "C" int mdv_bn_act_bwd_rank1(const float* dlog, const float* wrow, int rows_per_sample, float drop_p, const void* rng,
+                                    uint32_t drop_stream, const float* z, const float* mean, const float* rstd, const float* gamma,
+                                    const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C,
+                                    void* ws, void* stream) {
+    if (!dlog || !wrow || !z || !dz || !ws || M <= 0 || (C & 3) || rows_per_sample <= 0) return MDV_ERR_ARG;
+    if ((long long)M * C >= 0x7fffffffLL || (long long)(M / rows_per_sample + 1) * C >= 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
+    Rank1Dy r1 = {dlog, wrow, (const unsigned long long*)rng, rows_per_sample, drop_p, drop_stream};
+    return bn_act_bwd_impl(nullptr, r1, z, mean, rstd, gamma, beta, act, dz, dz_bf16, dgamma, dbeta, M, C, ws, (cudaStream_t)stream);
+}
+
+static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
+                           cudaStream_t st) {
     double* sums = (double*)ws;
     float* coef = (float*)(sums + 2 * C);
     cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
     if (e != cudaSuccess) return (int)e;
     const int rpb = stats_rows_per_block(M, C);
     dim3 grid(mdv_cdiv(C, 32), mdv_cdiv(M, rpb));
-    mdv_launch(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, sums, M, C, rpb);
+    mdv_launch(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, sums, M, C, rpb, r1);
     MDV_CHECK_LAUNCH();
     mdv_launch(bn_bwd_finalize_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, sums, M, C, coef, dgamma, dbeta);
     MDV_CHECK_LAUNCH();
     const long long total = (long long)M * C;
     const int blocks = mdv_cdiv(total / 4, 256);
     if (dz_bf16)
-        mdv_launch(bn_bwd_apply_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C);
+        mdv_launch(bn_bwd_apply_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C, r1);
     else
-        mdv_launch(bn_bwd_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (float*)dz, total, C);
+        mdv_launch(bn_bwd_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (float*)dz, total, C, r1);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -783,12 +783,19 @@ class AuxFn(torch.autograd.Function):
         lw, lb = (l1w, l2w, l3w, l4w), (l1b, l2b, l3b, l4b)
         with _dev_ctx(dout):
             dlo = upsample_bwd(dout, B, H, W, Ho, Wo, 1)
-            da5 = torch.empty((M0, hc), dtype=F32, device=dev)
             g_ow, r_ow = gtarget(ow)
             g_ob, r_ob = gtarget(ob)
-            check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(a5), 1, ptr(ow), ptr(da5), ptr(g_ow), ptr(g_ob), M0, hc, H * W, ctypes.c_float(p2),
-                                     ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_bwd")
-            dz, rg, rb = bn_backward(da5, z, mean, rstd, g, b, ACT_RELU, M0, hc)
+            if g_ow is not None:    # weight / bias gradient of linear_out only: d(a5) is never materialised (rank-1, see below)
+                check(lib.mdv_rowdot_bwd(ptr(dlo), ptr(a5), 1, ptr(ow), None, ptr(g_ow), ptr(g_ob), M0, hc, H * W, ctypes.c_float(p2),
+                                         ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_bwd")
+            # BatchNorm backward with d(a5)[m,c] = dlo[m] * w_out[c] * dropout2d_mask generated on the fly
+            dz = torch.empty((M0, hc), dtype=BF16, device=dev)
+            ws_bn = torch.empty(3 * hc, dtype=torch.float64, device=dev)
+            g_g, rg = gtarget(g)
+            g_b, rb = gtarget(b)
+            check(lib.mdv_bn_act_bwd_rank1(ptr(dlo), ptr(ow), H * W, ctypes.c_float(p2), ptr(rng_tensor(dev)) if p2 > 0 else None, sid,
+                                           ptr(z), ptr(mean), ptr(rstd), ptr(g), ptr(b), ACT_RELU, ptr(dz), 1, ptr(g_g), ptr(g_b), M0, hc,
+                                           ptr(ws_bn), L.stream()), "mdv_bn_act_bwd_rank1")
             g_fw, r_fw = gtarget(fw, (hc, K))
             gemm_tn(dz, cat, M0, hc, K, g_fw)
             g_fb, r_fb = gtarget(fb)

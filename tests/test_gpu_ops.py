@@ -353,6 +353,44 @@ def test_rowdot_with_dropout2d_fwd_bwd(env):
     del ones, mask
 
 
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_bn_backward_with_rank1_output_gradient(env, p):
+    """mdv_bn_act_bwd_rank1 (dy generated on the fly from dlog, w_out and the Dropout2d mask) == mdv_bn_act_bwd on the
+    dense dy that mdv_rowdot_bwd materialises."""
+    L, lib, dev = env
+    torch.manual_seed(11)
+    B, HW, C = 3, 200, 64
+    M = B * HW
+    z = torch.randn(M, C, device=dev) * 2 + 0.5
+    gam, bet = 1 + 0.1 * torch.randn(C, device=dev), 0.1 * torch.randn(C, device=dev)
+    mean, var = z.mean(0), z.var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    a5 = torch.relu((z - mean) * rstd * gam + bet).bfloat16()
+    dlog, w = torch.randn(M, device=dev), torch.randn(C, device=dev)
+    rng = torch.tensor([3, 1], dtype=torch.int64, device=dev)
+    dense = torch.empty(M, C, device=dev)
+    dw, db = torch.zeros(C, device=dev), torch.zeros(1, device=dev)
+    L.check(lib.mdv_rowdot_bwd(L.ptr(dlog), L.ptr(a5), 1, L.ptr(w), L.ptr(dense), L.ptr(dw), L.ptr(db), M, C, HW, p, L.ptr(rng), 9, L.stream()), "rowdot_bwd")
+    outs = []
+    for rank1 in (False, True):
+        dz = torch.empty(M, C, device=dev)
+        dg, dbt = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
+        if rank1:
+            L.check(lib.mdv_bn_act_bwd_rank1(L.ptr(dlog), L.ptr(w), HW, p, L.ptr(rng), 9, L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(gam), L.ptr(bet), 2,
+                                             L.ptr(dz), 0, L.ptr(dg), L.ptr(dbt), M, C, L.ptr(ws), L.stream()), "bn_bwd_rank1")
+        else:
+            L.check(lib.mdv_bn_act_bwd(L.ptr(dense), L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(gam), L.ptr(bet), 2, L.ptr(dz), 0, L.ptr(dg), L.ptr(dbt),
+                                       M, C, L.ptr(ws), L.stream()), "bn_bwd")
+        outs.append((dz, dg, dbt))
+    for a, b in zip(outs[0], outs[1]):
+        assert rel(b, a) < 1e-5
+    # dx == NULL: weight gradients only
+    dw2, db2 = torch.zeros(C, device=dev), torch.zeros(1, device=dev)
+    L.check(lib.mdv_rowdot_bwd(L.ptr(dlog), L.ptr(a5), 1, L.ptr(w), None, L.ptr(dw2), L.ptr(db2), M, C, HW, p, L.ptr(rng), 9, L.stream()), "rowdot_bwd")
+    assert rel(dw2, dw) < 1e-5 and rel(db2, db) < 1e-5
+
+
 def test_fused_losses_match_reference_formulas(env):
     L, lib, dev = env
     from oracle import mdvit_oracle as O
