@@ -8,6 +8,10 @@
 
 namespace {
 
+// element / pixel indices of the stencil and resize kernels are 32-bit (64-bit divisions made these kernels issue-bound);
+// every entry point checks that the tensor has fewer than 2^31 elements
+typedef int idx_t;
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(bf16* p, float4 v) {
@@ -37,10 +41,10 @@ __global__ void __launch_bounds__(256) dwconv3_kernel(const float* __restrict__ 
     for (int i = threadIdx.x; i < C; i += blockDim.x) sw[9 * C + i] = bias ? bias[i] : 0.f;
     __syncthreads();
     const int c4n = C >> 2;
-    const long long total = (long long)B * Ho * Wo * c4n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Ho * Wo * c4n;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % c4n) * 4;
-        long long pix = idx / c4n;
+        idx_t pix = idx / c4n;
         const int xo = (int)(pix % Wo);
         pix /= Wo;
         const int yo = (int)(pix % Ho);
@@ -196,17 +200,17 @@ __global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const float* __restr
     __shared__ float sh[8][32][11];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
-    const long long npix = (long long)B * Ho * Wo;
-    const long long p0 = (long long)blockIdx.y * pix_per_block;
-    const long long p1 = min(npix, p0 + pix_per_block);
+    const idx_t npix = (idx_t)B * Ho * Wo;
+    const idx_t p0 = (idx_t)blockIdx.y * pix_per_block;
+    const idx_t p1 = min(npix, p0 + pix_per_block);
     float acc[10];
 #pragma unroll
     for (int t = 0; t < 10; ++t) acc[t] = 0.f;
     if (c < C)
-        for (long long p = p0 + ty; p < p1; p += 8) {
+        for (idx_t p = p0 + ty; p < p1; p += 8) {
             const int xo = (int)(p % Wo);
             const int yo = (int)((p / Wo) % Ho);
-            const int b = (int)(p / ((long long)Wo * Ho));
+            const int b = (int)(p / ((idx_t)Wo * Ho));
             const float g = __ldg(dy + (size_t)p * C + c);
             acc[9] += g;
             const float* xb = x + (size_t)b * Hi * Wi * C + c;
@@ -247,13 +251,13 @@ __global__ void __launch_bounds__(256) gconv2_fwd_kernel(const float* __restrict
                                                           int C) {
     MDV_PDL_SYNC();
     const int g2n = C >> 1;
-    const long long total = (long long)B * H * W * g2n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * H * W * g2n;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int g = (int)(idx % g2n) * 2;
-        long long pix = idx / g2n;
+        idx_t pix = idx / g2n;
         const int x0 = (int)(pix % W);
         const int y0 = (int)((pix / W) % H);
-        const int b = (int)(pix / ((long long)W * H));
+        const int b = (int)(pix / ((idx_t)W * H));
         const int k = 2 * g;  // first of 4 cat channels
         const float* src = (k < C ? skip + k : up + (k - C)) + (size_t)b * H * W * C;
         const float* wg = w + (size_t)g * 18;
@@ -282,13 +286,13 @@ __global__ void __launch_bounds__(256) gconv2_dgrad_kernel(const float* __restri
                                                             int C) {
     MDV_PDL_SYNC();
     const int g2n = C >> 1;
-    const long long total = (long long)B * H * W * g2n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * H * W * g2n;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int g = (int)(idx % g2n) * 2;
-        long long pix = idx / g2n;
+        idx_t pix = idx / g2n;
         const int x0 = (int)(pix % W);
         const int y0 = (int)((pix / W) % H);
-        const int b = (int)(pix / ((long long)W * H));
+        const int b = (int)(pix / ((idx_t)W * H));
         const float* wg = w + (size_t)g * 18;
         const float* db_ = dout + (size_t)b * H * W * C + g;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -322,18 +326,18 @@ __global__ void __launch_bounds__(256) gconv2_wgrad_kernel(const float* __restri
     __shared__ float sh[8][32][19];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int g = blockIdx.x * 32 + tx;
-    const long long npix = (long long)B * H * W;
-    const long long p0 = (long long)blockIdx.y * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+    const idx_t npix = (idx_t)B * H * W;
+    const idx_t p0 = (idx_t)blockIdx.y * pix_per_block, p1 = min(npix, p0 + pix_per_block);
     float acc[18];
 #pragma unroll
     for (int t = 0; t < 18; ++t) acc[t] = 0.f;
     if (g < C) {
         const int k = 2 * g;
         const float* srcbase = (k < C ? skip + k : up + (k - C));
-        for (long long p = p0 + ty; p < p1; p += 8) {
+        for (idx_t p = p0 + ty; p < p1; p += 8) {
             const int x0 = (int)(p % W);
             const int y0 = (int)((p / W) % H);
-            const int b = (int)(p / ((long long)W * H));
+            const int b = (int)(p / ((idx_t)W * H));
             const float d = __ldg(dout + (size_t)p * C + g);
             const float* src = srcbase + (size_t)b * H * W * C;
 #pragma unroll
@@ -372,14 +376,14 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in,
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const int per_row = 9 * c4n;
-    const long long total = (long long)B * Ho * Wo * per_row;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Ho * Wo * per_row;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int r = (int)(idx % per_row);
-        const long long pix = idx / per_row;
+        const idx_t pix = idx / per_row;
         const int t = r / c4n, c = (r % c4n) * 4;
         const int xo = (int)(pix % Wo);
         const int yo = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long long)Wo * Ho));
+        const int b = (int)(pix / ((idx_t)Wo * Ho));
         const int yi = yo * stride - 1 + t / 3, xi = xo * stride - 1 + t % 3;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v = ld4(in + (((size_t)b * Hi + yi) * Wi + xi) * C + c);
@@ -391,13 +395,13 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in,
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, bf16* __restrict__ col, int B, int Hi,
                                                            int Wi, int Ho, int Wo) {
     MDV_PDL_SYNC();
-    const long long total = (long long)B * Ho * Wo * 32;  // one thread = 2 columns
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Ho * Wo * 32;  // one thread = 2 columns
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int k = (int)(idx % 32) * 2;
-        const long long pix = idx / 32;
+        const idx_t pix = idx / 32;
         const int xo = (int)(pix % Wo);
         const int yo = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long long)Wo * Ho));
+        const int b = (int)(pix / ((idx_t)Wo * Ho));
         float v[2] = {0.f, 0.f};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -417,13 +421,13 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ 
                                                        int Ho, int Wo, int C, int stride, int ldc) {
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
-    const long long total = (long long)B * Hi * Wi * c4n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Hi * Wi * c4n;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % c4n) * 4;
-        const long long pix = idx / c4n;
+        const idx_t pix = idx / c4n;
         const int x = (int)(pix % Wi);
         const int y = (int)((pix / Wi) % Hi);
-        const int b = (int)(pix / ((long long)Wi * Hi));
+        const int b = (int)(pix / ((idx_t)Wi * Hi));
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -461,13 +465,13 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const TI* __restrict_
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
-    const long long total = (long long)B * Ho * Wo * c4n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Ho * Wo * c4n;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % c4n) * 4;
-        const long long pix = idx / c4n;
+        const idx_t pix = idx / c4n;
         const int x = (int)(pix % Wo);
         const int y = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long long)Wo * Ho));
+        const int b = (int)(pix / ((idx_t)Wo * Ho));
         int y0, y1, x0, x1;
         float ly, lx;
         bil_src(y, sy, Hi, y0, y1, ly);
@@ -490,11 +494,11 @@ __global__ void __launch_bounds__(256) upsample1_fwd_kernel(const float* __restr
                                                              int Wi, int Ho, int Wo) {
     MDV_PDL_SYNC();
     const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
-    const long long total = (long long)B * Ho * Wo;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Ho * Wo;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int x = (int)(idx % Wo);
         const int y = (int)((idx / Wo) % Ho);
-        const int b = (int)(idx / ((long long)Wo * Ho));
+        const int b = (int)(idx / ((idx_t)Wo * Ho));
         int y0, y1, x0, x1;
         float ly, lx;
         bil_src(y, sy, Hi, y0, y1, ly);
@@ -514,13 +518,13 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const TI* __restrict_
     const int cvn = C / VEC;
     const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
     const float iy = (float)Ho / Hi, ix = (float)Wo / Wi;
-    const long long total = (long long)B * Hi * Wi * cvn;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const idx_t total = (idx_t)B * Hi * Wi * cvn;
+    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cvn) * VEC;
-        const long long pix = idx / cvn;
+        const idx_t pix = idx / cvn;
         const int xi = (int)(pix % Wi);
         const int yi = (int)((pix / Wi) % Hi);
-        const int b = (int)(pix / ((long long)Wi * Hi));
+        const int b = (int)(pix / ((idx_t)Wi * Hi));
         // outputs whose source coordinate falls in (i-1, i+1):  x in ((i-0.5)*inv - 0.5, (i+1.5)*inv - 0.5), padded by one
         int ya = (int)floorf(((float)yi - 0.5f) * iy - 0.5f) - 1, yb = (int)ceilf(((float)yi + 1.5f) * iy - 0.5f) + 2;
         int xa = (int)floorf(((float)xi - 0.5f) * ix - 0.5f) - 1, xb = (int)ceilf(((float)xi + 1.5f) * ix - 0.5f) + 2;
@@ -614,6 +618,7 @@ inline int grid_for(long long total_threads) {
     const long long cap = (long long)MDV_NUM_SMS * 16;
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
+inline bool fits_i32(long long n) { return n > 0 && n < 0x7fffffffLL; }
 inline int pix_per_block_for(long long npix, int col_blocks) {
     int want = (8 * MDV_NUM_SMS) / (col_blocks > 0 ? col_blocks : 1);
     if (want < 1) want = 1;
@@ -627,6 +632,7 @@ inline int pix_per_block_for(long long npix, int col_blocks) {
 extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, void* out, int out_bf16, int B, int Hi, int Wi,
                            int Ho, int Wo, int C, int stride, int transposed, int residual, void* stream) {
     if (!in || !w || !out || (C & 3) || B <= 0) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * (Hi > Ho ? Hi : Ho) * (Wi > Wo ? Wi : Wo) * C)) return MDV_ERR_UNSUPPORTED;
     const long long total = (long long)B * Ho * Wo * (C / 4);
     const size_t smem = (size_t)10 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
@@ -649,6 +655,7 @@ extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, v
 extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int Hi, int Wi, int Ho, int Wo,
                                  int C, int stride, void* stream) {
     if (!dy || !x || !dw || B <= 0) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * Hi * Wi * C)) return MDV_ERR_UNSUPPORTED;
     if (stride == 1 && Hi == Ho && Wi == Wo && !(C & 3) && C * 40 <= 48 * 1024) {
         const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
         dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
@@ -668,6 +675,7 @@ extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, flo
 extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out_bf16, int B, int H, int W, int C,
                               void* stream) {
     if (!skip || !up || !w || !out_bf16 || (C & 3)) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * H * W * C)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(gconv2_fwd_kernel, dim3(grid_for((long long)B * H * W * (C / 2))), dim3(256), 0, (cudaStream_t)stream, skip, up, w, (bf16*)out_bf16, B, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -676,6 +684,7 @@ extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w
 extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float* up, const float* w, float* dskip, float* dup,
                               float* dw, int B, int H, int W, int C, void* stream) {
     if (!dout || !skip || !up || !w || !dskip || !dup || (C & 3)) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * H * W * C)) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     mdv_launch(gconv2_dgrad_kernel, dim3(grid_for((long long)B * H * W * (C / 2))), dim3(256), 0, st, dout, w, dskip, dup, B, H, W, C);
     MDV_CHECK_LAUNCH();
@@ -692,6 +701,7 @@ extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float*
 extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride,
                            int ldc, void* stream) {
     if (!in || !col_bf16 || (C & 3) || ldc < 9 * C || (ldc & 7)) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * Ho * Wo * ldc)) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (ldc > 9 * C) {
         cudaError_t e = cudaMemsetAsync(col_bf16, 0, (size_t)B * Ho * Wo * ldc * 2, st);
@@ -708,6 +718,7 @@ extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, i
 
 extern "C" int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int Hi, int Wi, void* stream) {
     if (!img_nchw || !col_bf16 || (Hi & 1) || (Wi & 1)) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * Hi * Wi * 16)) return MDV_ERR_UNSUPPORTED;
     const int Ho = Hi / 2, Wo = Wi / 2;
     mdv_launch(im2col_stem_kernel, dim3(grid_for((long long)B * Ho * Wo * 32)), dim3(256), 0, (cudaStream_t)stream, img_nchw, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo);
     MDV_CHECK_LAUNCH();
@@ -717,6 +728,7 @@ extern "C" int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int
 extern "C" int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc,
                            void* stream) {
     if (!dcol || !dx || (C & 3)) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * Ho * Wo * ldc)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(col2im3_kernel, dim3(grid_for((long long)B * Hi * Wi * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, dx, B, Hi, Wi, Ho, Wo, C, stride, ldc);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -725,6 +737,7 @@ extern "C" int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, 
 extern "C" int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* out, int out_bf16, int ld_out, int B, int Hi, int Wi,
                                 int Ho, int Wo, int C, void* stream) {
     if (!in || !out || B <= 0) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * Ho * Wo * (ld_out > C ? ld_out : C))) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 1) {
         if (in_bf16 || out_bf16) return MDV_ERR_UNSUPPORTED;
@@ -750,6 +763,7 @@ extern "C" int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* ou
 extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, float* din, int ld_in, int B, int Hi, int Wi, int Ho,
                                 int Wo, int C, void* stream) {
     if (!dout || !din || B <= 0) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * Ho * Wo * (ld_out > C ? ld_out : C))) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 1) {
         if (dout_bf16) return MDV_ERR_UNSUPPORTED;

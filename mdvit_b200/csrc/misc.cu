@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
                                                          const unsigned long long* __restrict__ rng, uint32_t stream) {
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
-    const long long total = M * c4n;
+    const int total = (int)(M * c4n);             // 32-bit element indices: the host checks M*C < 2^31
     uint32_t thr = 0, key = 0;
     float inv = 1.f;
     if (drop_p > 0.f) {
@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
         inv = 1.f / (1.f - drop_p);
         key = rng_key(rng, stream);
     }
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % c4n) * 4;
-        const long long m = idx / c4n;
-        float4 v = *reinterpret_cast<const float4*>(in + m * ld_in + c);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = (idx % c4n) * 4;
+        const int m = idx / c4n;
+        float4 v = *reinterpret_cast<const float4*>(in + (size_t)m * ld_in + c);
         float s = rowscale ? __ldg(rowscale + m / rps) : 1.f;
         float s0 = s, s1 = s, s2 = s, s3 = s;
         if (thr) {
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
             s2 *= drop_lo(h1, thr, inv);
             s3 *= drop_hi(h1, thr, inv);
         }
-        *reinterpret_cast<uint2*>(out + m * ld_out + c) = make_uint2(f2_to_bf2(v.x * s0, v.y * s1), f2_to_bf2(v.z * s2, v.w * s3));
+        *reinterpret_cast<uint2*>(out + (size_t)m * ld_out + c) = make_uint2(f2_to_bf2(v.x * s0, v.y * s1), f2_to_bf2(v.z * s2, v.w * s3));
     }
 }
 
@@ -438,6 +438,7 @@ extern "C" int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, 
 extern "C" int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
                              int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* colsum, void* stream) {
     if (!in || !out_bf16 || (C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
+    if (M * C >= 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
     if (colsum) {
         if (C > 1024 || M > 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
         int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);

@@ -247,11 +247,11 @@ template <typename TO>
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, int act, TO* __restrict__ y,
-                                                          long long total, int C) {
+                                                          int total, int C) {
     MDV_PDL_SYNC();
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;      // 32-bit: the host checks M*C < 2^31
     if (i >= total) return;
-    const int c = (int)(i % C);
+    const int c = i % C;
     float4 v = *reinterpret_cast<const float4*>(z + i);
     float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -345,16 +345,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int act, const float* __restrict__ coef, TO* __restrict__ dz,
-                                                            long long total, int C, Rank1Dy r1) {
+                                                            int total, int C, Rank1Dy r1) {
     MDV_PDL_SYNC();
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;      // 32-bit: the host checks M*C < 2^31
     if (i >= total) return;
-    const int c = (int)(i % C);
+    const int c = i % C;
     float4 zv = *reinterpret_cast<const float4*>(z + i);
     float4 dv;
     if (r1.dlog) {
         // 32-bit index math (total < 2^31 checked on the host); b*C + c is a multiple of 4: two pair-hashes give the 4 masks
-        const int row = (int)i / C;
+        const int row = i / C;
         const int bb = row / r1.rps;
         const float dl = __ldg(r1.dlog + row);
         const float4 wv = *reinterpret_cast<const float4*>(r1.wrow + c);
@@ -476,7 +476,8 @@ extern "C" int mdv_bn_stats(const float* z, int M, int C, float eps, float momen
 extern "C" int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
                               int act, void* y, int y_bf16, int M, int C, void* stream) {
     if (!z || !y || M <= 0 || (C & 3)) return MDV_ERR_ARG;
-    const long long total = (long long)M * C;
+    if ((long long)M * C >= 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
+    const int total = M * C;
     const int blocks = mdv_cdiv(total / 4, 256);
     if (y_bf16)
         mdv_launch(bn_act_fwd_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, z, mean, rstd, gamma, beta, act, (bf16*)y, total, C);
@@ -523,7 +524,8 @@ static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, c
     MDV_CHECK_LAUNCH();
     mdv_launch(bn_bwd_finalize_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, sums, M, C, coef, dgamma, dbeta);
     MDV_CHECK_LAUNCH();
-    const long long total = (long long)M * C;
+    if ((long long)M * C >= 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
+    const int total = M * C;
     const int blocks = mdv_cdiv(total / 4, 256);
     if (dz_bf16)
         mdv_launch(bn_bwd_apply_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C, r1);
