@@ -377,15 +377,15 @@ class MDViT(_Trunk):
             enc = self._trunk_forward(x, domain_label)
             dec4, h, w = self._decode(enc, domain_label)
         out = self._head(dec4, h, w, img_size)
+        # per-domain slices of the five feature maps the auxiliary decoders read, and of the main logits
+        split = [ops.SplitDomainsFn.apply(t, G) for t in [e[0] for e in enc] + [dec4, out]]
         res = []
         for g, d in enumerate(domains):
-            sl = slice(g * B, (g + 1) * B)
             aux_out = None
             if d in ('0', '1', '2', '3'):
                 branch = getattr(self, f'debranch{int(d) + 1}')
-                feats = [e[0][sl] for e in enc] + [dec4[sl]]
-                aux_out = branch(feats, [(e[1], e[2]) for e in enc], img_size)
-            res.append((out[sl], aux_out))
+                aux_out = branch([split[i][g] for i in range(5)], [(e[1], e[2]) for e in enc], img_size)
+            res.append((split[5][g], aux_out))
         return res
 
 

@@ -829,6 +829,25 @@ class AuxFn(torch.autograd.Function):
                 r_ob, None, None, None, None, None, None)
 
 
+# ------------------------------------------------------------------------------------------------- domain split
+class SplitDomainsFn(torch.autograd.Function):
+    """x [G*B, ...] -> G views [B, ...] (the per-domain slices the auxiliary decoders consume in MDViT.forward_multi).
+    Plain slicing would make autograd zero-fill and add a full-size tensor per slice in backward; here the G slice
+    gradients are concatenated once."""
+
+    @staticmethod
+    def forward(ctx, x, G):
+        B = x.shape[0] // G
+        ctx.G, ctx.shape_b = G, (B,) + tuple(x.shape[1:])
+        return tuple(x.narrow(0, g * B, B) for g in range(G))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ref = next(g for g in grads if g is not None)
+        parts = [g if g is not None else torch.zeros(ctx.shape_b, dtype=ref.dtype, device=ref.device) for g in grads]
+        return torch.cat(parts, dim=0), None
+
+
 # ------------------------------------------------------------------------------------------------- fused losses
 class SegLossFn(torch.autograd.Function):
     """(L_seg, L_aux, L_kt) of multi_train_MDViT.py:147-169 in one pass over (out, aux, label); `reduce_sums` (optional
