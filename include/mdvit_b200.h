@@ -155,6 +155,14 @@ int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long l
 int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate, void* stream);
 /* fp32 master weight -> bf16 GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2 */
 int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream);
+/* The same for a whole model in one launch: `descs_dev` is a DEVICE array of n descriptors (zero-padded dst regions are
+ * the caller's job, as with mdv_prep_weight). */
+typedef struct MdvPrepDesc {
+    const float* src;
+    void* dst;
+    int rows, cols, ld, mode, cin, pad_;
+} MdvPrepDesc;
+int mdv_prep_weights_batched(const MdvPrepDesc* descs_dev, int n, void* stream);
 int mdv_unperm_conv_grad(const float* g, int ld, float* dw, int R, int cin, void* stream);
 
 /* ------------------------------------------------------------------ losses (multi_train_MDViT.py:147-169, Utils/losses.py:8-16) */

@@ -228,6 +228,30 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
     }
 }
 
+// All bf16 operand copies of a model in ONE launch: blockIdx.y walks a device-resident table of (src, dst, shape, mode)
+// descriptors (same modes as prep_weight_kernel).  Replaces ~200 tiny launches per training step.
+__global__ void __launch_bounds__(256) prep_weights_batched_kernel(const MdvPrepDesc* __restrict__ descs) {
+    MDV_PDL_SYNC();
+    const MdvPrepDesc d = descs[blockIdx.y];
+    const float* __restrict__ src = d.src;
+    bf16* __restrict__ dst = (bf16*)d.dst;
+    const int total = d.rows * d.cols;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int r = idx / d.cols, c = idx % d.cols;
+        const bf16 v = __float2bfloat16_rn(src[idx]);
+        if (d.mode == 0) {
+            dst[(size_t)r * d.ld + c] = v;
+        } else if (d.mode == 1) {
+            dst[(size_t)c * d.ld + r] = v;
+        } else {
+            const int ci = c / 9, t = c % 9;
+            const int col = t * d.cin + ci;
+            if (d.mode == 2) dst[(size_t)r * d.ld + col] = v;
+            else dst[(size_t)col * d.ld + r] = v;
+        }
+    }
+}
+
 // d(conv weight [R,Cin,3,3]) += dW_im2col[R, ld] (column (i*3+j)*Cin+ci)
 __global__ void __launch_bounds__(256) unperm_conv_grad_kernel(const float* __restrict__ g, int ld, float* __restrict__ dw, int R,
                                                                 int cin) {
@@ -469,6 +493,13 @@ extern "C" int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, i
 extern "C" int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream) {
     if (!src || !dst_bf16 || mode < 0 || mode > 3) return MDV_ERR_ARG;
     mdv_launch(prep_weight_kernel, dim3(grid_for((long long)R * Cc)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst_bf16, R, Cc, ld, mode, cin);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_prep_weights_batched(const MdvPrepDesc* descs_dev, int n, void* stream) {
+    if (!descs_dev || n <= 0) return MDV_ERR_ARG;
+    mdv_launch(prep_weights_batched_kernel, dim3(32, n), dim3(256), 0, (cudaStream_t)stream, descs_dev);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

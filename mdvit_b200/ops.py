@@ -64,17 +64,69 @@ def bump_weight_epoch():
     _wcache.clear()
 
 
+class _PrepDesc(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("rows", ctypes.c_int), ("cols", ctypes.c_int), ("ld", ctypes.c_int),
+                ("mode", ctypes.c_int), ("cin", ctypes.c_int), ("pad_", ctypes.c_int)]
+
+
+class WeightMirror:
+    """Persistent bf16 operand copies of every weight a training step uses, refreshed by ONE kernel launch.
+
+    While `recording`, prep_weight() notes every (parameter, mode) it converts; freeze() uploads the descriptor table;
+    afterwards the fused trainer calls refresh() once per step (right after AdamW) instead of ~200 tiny conversion
+    launches, and prep_weight() hands out the persistent buffers."""
+
+    def __init__(self):
+        self.entries, self.table, self.recording = {}, None, True
+
+    def note(self, w, mode, rows, cols, out_ld, cin, dst):
+        if self.recording:
+            self.entries[(id(w), mode, out_ld)] = (weakref.ref(w), w.data_ptr(), dst, rows, cols, out_ld, mode, cin)
+
+    def lookup(self, w, mode, out_ld):
+        if self.table is None:
+            return None
+        e = self.entries.get((id(w), mode, out_ld))
+        if e is not None and e[0]() is w and e[1] == w.data_ptr():
+            return e[2]
+        return None
+
+    def freeze(self, device):
+        self.recording = False
+        arr = (_PrepDesc * len(self.entries))()
+        for i, (_, src, dst, rows, cols, out_ld, mode, cin) in enumerate(self.entries.values()):
+            arr[i] = _PrepDesc(src, dst.data_ptr(), rows, cols, out_ld, mode, cin, 0)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+        self.table = raw.to(device)
+        self.n = len(self.entries)
+
+    def refresh(self):
+        check(L.lib().mdv_prep_weights_batched(ptr(self.table), self.n, L.stream()), "mdv_prep_weights_batched")
+
+
+_mirror = None
+
+
+def set_weight_mirror(m):
+    global _mirror
+    _mirror = m
+
+
 def prep_weight(w, mode, rows, cols, ld=None, cin=0):
     """bf16 GEMM operand of fp32 parameter `w` (mode: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order)."""
-    key = (id(w), w.data_ptr(), w._version, mode, ld, WEIGHT_EPOCH)
-    hit = _wcache.get(key)
-    if hit is not None and hit[0]() is w:      # id()/data_ptr() are recycled once a model is freed: check liveness
-        return hit[1]
     R, Cc = rows, cols
     if mode == 0 or mode == 2:
         out_rows, out_ld = R, (ld or Cc)
     else:
         out_rows, out_ld = Cc, (ld or R)
+    if _mirror is not None:
+        hit = _mirror.lookup(w, mode, out_ld)
+        if hit is not None:
+            return hit
+    key = (id(w), w.data_ptr(), w._version, mode, ld, WEIGHT_EPOCH)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0]() is w:      # id()/data_ptr() are recycled once a model is freed: check liveness
+        return hit[1]
     with torch.no_grad():
         need_zero = mode >= 2 and out_ld != (Cc if mode == 2 else R)
         dst = (torch.zeros if need_zero or mode >= 2 else torch.empty)((out_rows, out_ld), dtype=BF16, device=w.device)
@@ -82,6 +134,8 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
     if len(_wcache) > 4096:
         _wcache.clear()
     _wcache[key] = (weakref.ref(w), dst)
+    if _mirror is not None:
+        _mirror.note(w, mode, R, Cc, out_ld, cin, dst)
     return dst
 
 

@@ -285,3 +285,28 @@ def test_data_parallel_two_gpus_nccl(dev):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(root, "scripts", "dp_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.count("DP_OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_graph_step_keeps_bf16_weight_mirror_fresh(dev):
+    """The captured step ends with AdamW followed by ONE launch that re-converts every bf16 GEMM operand copy
+    (ops.WeightMirror): after each replay every persistent copy must equal the bf16 cast of the updated fp32 weight, and
+    the graph-replayed losses must follow the eager trainer's."""
+    from mdvit_b200.train_step import MKDTrainer
+    batches = [tuple(t.to(dev) for t in synth.synth_batch(5, d, 2, 64, 64)) + (d,) for d in range(4)]
+    m1, m2 = build(dev).train(), build(dev).train()
+    eager, graph = MKDTrainer(m1), MKDTrainer(m2)
+    graph.capture(batches, warmup=1)
+    l_eager = [eager.step(batches).clone() for _ in range(3)][-1]          # warm-up step + capture-free replays below = 3 updates
+    l_graph = [graph.step_graph(None).clone() for _ in range(2)][-1]
+    torch.cuda.synchronize()
+    checked = 0
+    for (_, mode, _), (ref, _, dst, rows, cols, out_ld, _, cin) in graph.mirror.entries.items():
+        w = ref()
+        if mode == 0:
+            assert torch.equal(dst[:, :cols], w.detach().reshape(rows, cols).bfloat16()), "stale bf16 copy"
+            checked += 1
+        elif mode == 1:
+            assert torch.equal(dst[:, :rows], w.detach().reshape(rows, cols).t().bfloat16()), "stale transposed bf16 copy"
+            checked += 1
+    assert checked > 100
+    assert (l_eager - l_graph).abs().max().item() < 2e-2 * l_eager.abs().max().item()
