@@ -245,78 +245,7 @@ __global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------- decoder grouped 3x3 (2 inputs / group)
 // cat = concat(skip[C], up[C]) along channels; out[g] = sum_{t<2} sum_ij w[g,t,i,j] * cat[2g+t] shifted.  Decoders.py:30-38,198-205.
-// cat channel k lives in skip if k < C else in up (k - C).  One thread = one pixel x 2 output groups (= 4 cat channels).
-__global__ void __launch_bounds__(256) gconv2_fwd_kernel(const float* __restrict__ skip, const float* __restrict__ up,
-                                                          const float* __restrict__ w, bf16* __restrict__ out, int B, int H, int W,
-                                                          int C) {
-    MDV_PDL_SYNC();
-    const int g2n = C >> 1;
-    const idx_t total = (idx_t)B * H * W * g2n;
-    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % g2n) * 2;
-        idx_t pix = idx / g2n;
-        const int x0 = (int)(pix % W);
-        const int y0 = (int)((pix / W) % H);
-        const int b = (int)(pix / ((idx_t)W * H));
-        const int k = 2 * g;  // first of 4 cat channels
-        const float* src = (k < C ? skip + k : up + (k - C)) + (size_t)b * H * W * C;
-        const float* wg = w + (size_t)g * 18;
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int yi = y0 - 1 + i;
-            if (yi < 0 || yi >= H) continue;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int xi = x0 - 1 + j;
-                if (xi < 0 || xi >= W) continue;
-                const float4 v = ld4(src + ((size_t)yi * W + xi) * C);
-                const int t = i * 3 + j;
-                a0 += __ldg(wg + t) * v.x + __ldg(wg + 9 + t) * v.y;
-                a1 += __ldg(wg + 18 + t) * v.z + __ldg(wg + 27 + t) * v.w;
-            }
-        }
-        *reinterpret_cast<uint32_t*>(out + (size_t)pix * C + g) = f2_to_bf2(a0, a1);
-    }
-}
-
-// input gradient: dcat[k=2g+t] [y,x] = sum_ij w[g,t,i,j] * dout[g][y+1-i, x+1-j]; written to dskip / dup (both fp32 [.,C]).
-__global__ void __launch_bounds__(256) gconv2_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w,
-                                                            float* __restrict__ dskip, float* __restrict__ dup, int B, int H, int W,
-                                                            int C) {
-    MDV_PDL_SYNC();
-    const int g2n = C >> 1;
-    const idx_t total = (idx_t)B * H * W * g2n;
-    for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
-        const int g = (int)(idx % g2n) * 2;
-        idx_t pix = idx / g2n;
-        const int x0 = (int)(pix % W);
-        const int y0 = (int)((pix / W) % H);
-        const int b = (int)(pix / ((idx_t)W * H));
-        const float* wg = w + (size_t)g * 18;
-        const float* db_ = dout + (size_t)b * H * W * C + g;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int yi = y0 + 1 - i;
-            if (yi < 0 || yi >= H) continue;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int xi = x0 + 1 - j;
-                if (xi < 0 || xi >= W) continue;
-                const float2 d = *reinterpret_cast<const float2*>(db_ + ((size_t)yi * W + xi) * C);
-                const int t = i * 3 + j;
-                a.x += __ldg(wg + t) * d.x;
-                a.y += __ldg(wg + 9 + t) * d.x;
-                a.z += __ldg(wg + 18 + t) * d.y;
-                a.w += __ldg(wg + 27 + t) * d.y;
-            }
-        }
-        const int k = 2 * g;
-        float* dst = (k < C ? dskip + k : dup + (k - C)) + (size_t)pix * C;
-        st4(dst, a);
-    }
-}
+// cat channel k lives in skip if k < C else in up (k - C).  Forward and input gradient: sliding-window kernels further below.
 
 // weight gradient: dw[g,t,i,j] += sum dout[p,g] * cat[p shifted, 2g+t].  block = 32 groups x 8 pixel lanes.
 __global__ void __launch_bounds__(256) gconv2_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ skip,
@@ -365,6 +294,162 @@ __global__ void __launch_bounds__(256) gconv2_wgrad_kernel(const float* __restri
         for (int k = 0; k < 8; ++k) s += sh[k][gg][t];
         const int gi = blockIdx.x * 32 + gg;
         if (gi < C) atomicAdd(dw + (size_t)gi * 18 + t, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------- grouped 3x3, sliding-window versions
+// Same scheme as dwconv3_s1_kernel: a thread owns one pixel column x and 4 consecutive "cat" channels 4q..4q+3 (= output
+// channels g = 2q, 2q+1; cat = concat(skip, up), so the 4 channels are one float4 of `skip` (4q < C) or of `up`), walks
+// down a segment of rows with a 3-row register window: 3 coalesced 16-byte loads per output row instead of 9.
+struct GRow3 {
+    float4 l, m, r;
+};
+__device__ __forceinline__ GRow3 gload_row3(const float* __restrict__ row, int p, int C, bool ok, bool left_ok, bool right_ok) {
+    GRow3 t;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    t.m = ok ? ld4(row + p) : z;
+    t.l = (ok && left_ok) ? ld4(row + p - C) : z;
+    t.r = (ok && right_ok) ? ld4(row + p + C) : z;
+    return t;
+}
+// taps of the two output channels g, g+1 as float4 (w[g,0,t], w[g,1,t], w[g+1,0,t], w[g+1,1,t]);  w layout [C][2][3][3]
+__device__ __forceinline__ void gload_taps(const float* __restrict__ w, int g, bool flip, float4 (&wv)[9]) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int tt = flip ? 8 - t : t;
+        wv[t] = make_float4(__ldg(w + g * 18 + tt), __ldg(w + g * 18 + 9 + tt), __ldg(w + (g + 1) * 18 + tt), __ldg(w + (g + 1) * 18 + 9 + tt));
+    }
+}
+__device__ __forceinline__ void gfma(float2& a, const float4& w, const float4& v) {
+    a.x += w.x * v.x + w.y * v.y;
+    a.y += w.z * v.z + w.w * v.w;
+}
+
+__global__ void __launch_bounds__(256) gconv2_s_fwd_kernel(const float* __restrict__ skip, const float* __restrict__ up,
+                                                            const float* __restrict__ w, bf16* __restrict__ out, int H, int W, int C,
+                                                            int seg) {
+    MDV_PDL_SYNC();
+    const int half = C >> 1;                        // float4 groups per pixel of the concatenated input
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= W * half) return;
+    const int x = t / half, q = t % half;
+    const int k0 = 4 * q, g = 2 * q;
+    const float* src = (k0 < C ? skip + k0 : up + (k0 - C)) + (size_t)blockIdx.z * H * W * C;
+    const int p = x * C;                            // offset of pixel x inside an image row of the source
+    const int L = W * C;
+    const bool left_ok = x > 0, right_ok = x < W - 1;
+    float4 wv[9];
+    gload_taps(w, g, false, wv);
+    const int y0 = blockIdx.y * seg, y1 = min(H, y0 + seg);
+    bf16* oimg = out + (size_t)blockIdx.z * H * L;
+    GRow3 r0 = gload_row3(src + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
+    GRow3 r1 = gload_row3(src + (size_t)y0 * L, p, C, true, left_ok, right_ok);
+    for (int y = y0; y < y1; ++y) {
+        const GRow3 r2 = gload_row3(src + (size_t)(y + 1) * L, p, C, y + 1 < H, left_ok, right_ok);
+        float2 a = make_float2(0.f, 0.f);
+        gfma(a, wv[0], r0.l); gfma(a, wv[1], r0.m); gfma(a, wv[2], r0.r);
+        gfma(a, wv[3], r1.l); gfma(a, wv[4], r1.m); gfma(a, wv[5], r1.r);
+        gfma(a, wv[6], r2.l); gfma(a, wv[7], r2.m); gfma(a, wv[8], r2.r);
+        *reinterpret_cast<uint32_t*>(oimg + (size_t)y * L + p + g) = f2_to_bf2(a.x, a.y);
+        r0 = r1;
+        r1 = r2;
+    }
+}
+
+// input gradient: dcat[4q..4q+3][y,x] = sum_ij w[.,.,i,j] * dout[g(.)][y+1-i, x+1-j]   (flipped taps), written to dskip / dup
+__global__ void __launch_bounds__(256) gconv2_s_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                              float* __restrict__ dskip, float* __restrict__ dup, int H, int W, int C,
+                                                              int seg) {
+    MDV_PDL_SYNC();
+    const int half = C >> 1;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= W * half) return;
+    const int x = t / half, q = t % half;
+    const int k0 = 4 * q, g = 2 * q;
+    const int L = W * C;
+    const float* dimg = dout + (size_t)blockIdx.z * H * L + g;
+    float* dst = (k0 < C ? dskip + k0 : dup + (k0 - C)) + (size_t)blockIdx.z * H * L;
+    const int p = x * C;
+    const bool left_ok = x > 0, right_ok = x < W - 1;
+    float4 wv[9];
+    gload_taps(w, g, true, wv);
+    const int y0 = blockIdx.y * seg, y1 = min(H, y0 + seg);
+    auto ldrow = [&](int y, float2& l, float2& m, float2& r) {
+        const bool ok = y >= 0 && y < H;
+        const float* row = dimg + (size_t)y * L + p;
+        const float2 z = make_float2(0.f, 0.f);
+        m = ok ? *reinterpret_cast<const float2*>(row) : z;
+        l = (ok && left_ok) ? *reinterpret_cast<const float2*>(row - C) : z;
+        r = (ok && right_ok) ? *reinterpret_cast<const float2*>(row + C) : z;
+    };
+    float2 a0l, a0m, a0r, a1l, a1m, a1r;
+    ldrow(y0 - 1, a0l, a0m, a0r);
+    ldrow(y0, a1l, a1m, a1r);
+    for (int y = y0; y < y1; ++y) {
+        float2 a2l, a2m, a2r;
+        ldrow(y + 1, a2l, a2m, a2r);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto acc = [&](const float4& ww, const float2& d) {
+            a.x += ww.x * d.x; a.y += ww.y * d.x; a.z += ww.z * d.y; a.w += ww.w * d.y;
+        };
+        acc(wv[0], a0l); acc(wv[1], a0m); acc(wv[2], a0r);
+        acc(wv[3], a1l); acc(wv[4], a1m); acc(wv[5], a1r);
+        acc(wv[6], a2l); acc(wv[7], a2m); acc(wv[8], a2r);
+        st4(dst + (size_t)y * L + p, a);
+        a0l = a1l; a0m = a1m; a0r = a1r;
+        a1l = a2l; a1m = a2m; a1r = a2r;
+    }
+}
+
+// weight gradient: dw[g,t,i,j] += sum dout[g][y,x] * cat[2g+t][y-1+i, x-1+j]
+__global__ void __launch_bounds__(256) gconv2_s_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ skip,
+                                                              const float* __restrict__ up, float* __restrict__ dw, int H, int W, int C,
+                                                              int seg) {
+    MDV_PDL_SYNC();
+    extern __shared__ float sacc[];     // [C/2][36]
+    const int half = C >> 1;
+    for (int i = threadIdx.x; i < half * 36; i += 256) sacc[i] = 0.f;
+    __syncthreads();
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t < W * half) {
+        const int x = t / half, q = t % half;
+        const int k0 = 4 * q, g = 2 * q;
+        const int L = W * C;
+        const float* src = (k0 < C ? skip + k0 : up + (k0 - C)) + (size_t)blockIdx.z * H * L;
+        const float* dimg = dout + (size_t)blockIdx.z * H * L + g;
+        const int p = x * C;
+        const bool left_ok = x > 0, right_ok = x < W - 1;
+        const int y0 = blockIdx.y * seg, y1 = min(H, y0 + seg);
+        float4 acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        GRow3 r0 = gload_row3(src + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
+        GRow3 r1 = gload_row3(src + (size_t)y0 * L, p, C, true, left_ok, right_ok);
+        for (int y = y0; y < y1; ++y) {
+            const GRow3 r2 = gload_row3(src + (size_t)(y + 1) * L, p, C, y + 1 < H, left_ok, right_ok);
+            const float2 d = *reinterpret_cast<const float2*>(dimg + (size_t)y * L + p);
+            auto upd = [&](float4& a, const float4& v) {
+                a.x += d.x * v.x; a.y += d.x * v.y; a.z += d.y * v.z; a.w += d.y * v.w;
+            };
+            upd(acc[0], r0.l); upd(acc[1], r0.m); upd(acc[2], r0.r);
+            upd(acc[3], r1.l); upd(acc[4], r1.m); upd(acc[5], r1.r);
+            upd(acc[6], r2.l); upd(acc[7], r2.m); upd(acc[8], r2.r);
+            r0 = r1;
+            r1 = r2;
+        }
+        // sacc[q][36]: (g,0,tap) at tap, (g,1,tap) at 9+tap, (g+1,0,tap) at 18+tap, (g+1,1,tap) at 27+tap == dw + g*18 layout
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            atomicAdd(sacc + q * 36 + k, acc[k].x);
+            atomicAdd(sacc + q * 36 + 9 + k, acc[k].y);
+            atomicAdd(sacc + q * 36 + 18 + k, acc[k].z);
+            atomicAdd(sacc + q * 36 + 27 + k, acc[k].w);
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < half * 36; o += 256) {
+        const float v = sacc[o];
+        if (v != 0.f) atomicAdd(dw + o, v);      // q*36 + r == g*18 + r: the same linear layout as dw [C][2][3][3]
     }
 }
 
@@ -676,7 +761,11 @@ extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w
                               void* stream) {
     if (!skip || !up || !w || !out_bf16 || (C & 3)) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * H * W * C)) return MDV_ERR_UNSUPPORTED;
-    mdv_launch(gconv2_fwd_kernel, dim3(grid_for((long long)B * H * W * (C / 2))), dim3(256), 0, (cudaStream_t)stream, skip, up, w, (bf16*)out_bf16, B, H, W, C);
+    {
+        const int seg = H >= 64 ? 16 : (H >= 16 ? 8 : H);
+        mdv_launch(gconv2_s_fwd_kernel, dim3(mdv_cdiv(W * (C / 2), 256), mdv_cdiv(H, seg), B), dim3(256), 0, (cudaStream_t)stream, skip, up, w,
+                   (bf16*)out_bf16, H, W, C, seg);
+    }
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -686,14 +775,20 @@ extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float*
     if (!dout || !skip || !up || !w || !dskip || !dup || (C & 3)) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * H * W * C)) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    mdv_launch(gconv2_dgrad_kernel, dim3(grid_for((long long)B * H * W * (C / 2))), dim3(256), 0, st, dout, w, dskip, dup, B, H, W, C);
+    const int seg = H >= 64 ? 16 : (H >= 16 ? 8 : H);
+    mdv_launch(gconv2_s_dgrad_kernel, dim3(mdv_cdiv(W * (C / 2), 256), mdv_cdiv(H, seg), B), dim3(256), 0, st, dout, w, dskip, dup, H, W, C, seg);
     MDV_CHECK_LAUNCH();
     if (!dw) return MDV_OK;   // weight gradient not wanted in this pass
-    const long long npix = (long long)B * H * W;
-    const int cb = mdv_cdiv(C, 32);
-    const int ppb = pix_per_block_for(npix, cb);
-    dim3 grid(cb, mdv_cdiv(npix, ppb));
-    mdv_launch(gconv2_wgrad_kernel, dim3(grid), dim3(256), 0, st, dout, skip, up, dw, B, H, W, C, ppb);
+    if ((size_t)(C / 2) * 36 * sizeof(float) <= 48 * 1024) {
+        mdv_launch(gconv2_s_wgrad_kernel, dim3(mdv_cdiv(W * (C / 2), 256), mdv_cdiv(H, seg), B), dim3(256), (size_t)(C / 2) * 36 * sizeof(float), st,
+                   dout, skip, up, dw, H, W, C, seg);
+    } else {
+        const long long npix = (long long)B * H * W;
+        const int cb = mdv_cdiv(C, 32);
+        const int ppb = pix_per_block_for(npix, cb);
+        dim3 grid(cb, mdv_cdiv(npix, ppb));
+        mdv_launch(gconv2_wgrad_kernel, dim3(grid), dim3(256), 0, st, dout, skip, up, dw, B, H, W, C, ppb);
+    }
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

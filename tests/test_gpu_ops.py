@@ -266,10 +266,10 @@ def test_dwconv3_fwd_transposed_wgrad(env, B, H, W, C, stride):
         assert rel(dx2, x.grad + dy) < F32_TOL
 
 
-def test_gconv2_matches_grouped_conv_over_concat(env):
+@pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 128), (2, 64, 64, 64), (1, 20, 12, 320), (3, 5, 7, 512), (1, 33, 16, 64)])
+def test_gconv2_matches_grouped_conv_over_concat(env, B, H, W, C):
     L, lib, dev = env
     torch.manual_seed(3)
-    B, H, W, C = 2, 8, 8, 128
     skip = torch.randn(B, H, W, C, device=dev).requires_grad_()
     up = torch.randn(B, H, W, C, device=dev).requires_grad_()
     w = (torch.randn(C, 2, 3, 3, device=dev) * 0.3).requires_grad_()
