@@ -286,8 +286,9 @@ def main():
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": f"MDViT(adapt_method=Sup, decoder=MLPFM) MKD train step: 4 domains x {B} images/GPU at {IMG}x{IMG}, "
-                                   "dropout 0.1, DropPath 0.1, MKD backward (single-sweep schedule, gradient-equivalent to the reference's "
-                                   "two passes), AdamW; bf16 tensor-core operands, fp32 accumulate/residual",
+                                   "dropout 0.1, DropPath 0.1, the 4 domain mini-batches stacked through the trunk in one pass (BatchNorm per domain group), "
+                                   "MKD backward (single-sweep schedule, gradient-equivalent to the reference's two passes), AdamW; "
+                                   "bf16 tensor-core operands, fp32 accumulate/residual",
                        "batch_per_domain_per_gpu": B, "images_per_step": imgs_per_step, "parallelism": f"dp{world}",
                        "cuda_graph": use_graph, "l2": "per-step working set (>10 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * 3 * 4},
