@@ -133,7 +133,9 @@ int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float* crpe_w3, 
 int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, const void* e_bf16, const float* gate, const float* crpe_w3,
                  const float* crpe_b3, const float* crpe_w5, const float* crpe_b5, const float* crpe_w7, const float* crpe_b7,
                  const float* stats, void* dqkv_bf16, float* dgate, float* dcrpe_w3, float* dcrpe_b3, float* dcrpe_w5,
-                 float* dcrpe_b5, float* dcrpe_w7, float* dcrpe_b7, float* ws, int B, int H, int W, int C, int heads,
+                 float* dcrpe_b5, float* dcrpe_w7, float* dcrpe_b7,
+                 float* dbias_qkv /* [3C] += column sums of dqkv (bias gradient of the qkv Linear), or NULL */, float* ws, int B,
+                 int H, int W, int C, int heads,
                  void* stream);
 /* DA: gate[b,h,v] = softmax_h( W2 relu(W1 label_b + b1) + b2 )  (mdvit.py:272-276,301-303) */
 int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,

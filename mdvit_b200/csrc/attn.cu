@@ -119,30 +119,33 @@ __global__ void __launch_bounds__(256) da_gate_bwd_dhid_kernel(const float* __re
 // step 2: dW2[c,j] += sum_b dz[b,c] hid[b,j]; db2[c] += sum_b dz[b,c]; dW1[j,d] += sum_b dhid[b,j] label[b,d]; db1[j] += sum_b dhid[b,j]
 __global__ void da_gate_bwd2_kernel(const float* __restrict__ label, const float* __restrict__ hid_in, const float* __restrict__ dz,
                                     const float* __restrict__ dhid, float* __restrict__ dw1, float* __restrict__ db1,
-                                    float* __restrict__ dw2, float* __restrict__ db2, int B, int nd, int hid, int C) {
+                                    float* __restrict__ dw2, float* __restrict__ db2, int B, int nd, int hid, int C, int bsplit) {
     MDV_PDL_SYNC();
+    // blockIdx.y owns a slice of the samples (the per-thread loop over B was the critical path); partial sums are added atomically
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = (B + bsplit - 1) / bsplit;
+    const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
     const int n2 = C * hid;
     if (i < n2) {
         const int c = i / hid, j = i % hid;
         float a = 0.f;
-        for (int b = 0; b < B; ++b) a += dz[(size_t)b * C + c] * hid_in[(size_t)b * hid + j];
-        dw2[i] += a;
+        for (int b = b0; b < b1; ++b) a += dz[(size_t)b * C + c] * hid_in[(size_t)b * hid + j];
+        atomicAdd(dw2 + i, a);
     } else if (i < n2 + C) {
         const int c = i - n2;
         float a = 0.f;
-        for (int b = 0; b < B; ++b) a += dz[(size_t)b * C + c];
-        db2[c] += a;
+        for (int b = b0; b < b1; ++b) a += dz[(size_t)b * C + c];
+        atomicAdd(db2 + c, a);
     } else if (i < n2 + C + hid * nd) {
         const int k = i - n2 - C, j = k / nd, d = k % nd;
         float a = 0.f;
-        for (int b = 0; b < B; ++b) a += dhid[(size_t)b * hid + j] * label[b * nd + d];
-        dw1[k] += a;
+        for (int b = b0; b < b1; ++b) a += dhid[(size_t)b * hid + j] * label[b * nd + d];
+        atomicAdd(dw1 + k, a);
     } else if (i < n2 + C + hid * nd + hid) {
         const int j = i - n2 - C - hid * nd;
         float a = 0.f;
-        for (int b = 0; b < B; ++b) a += dhid[(size_t)b * hid + j];
-        db1[j] += a;
+        for (int b = b0; b < b1; ++b) a += dhid[(size_t)b * hid + j];
+        atomicAdd(db1 + j, a);
     }
 }
 
@@ -183,8 +186,8 @@ extern "C" int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float
 extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, const void* e_bf16, const float* gate, const float* crpe_w3,
                             const float* crpe_b3, const float* crpe_w5, const float* crpe_b5, const float* crpe_w7,
                             const float* crpe_b7, const float* stats, void* dqkv_bf16, float* dgate, float* dcrpe_w3,
-                            float* dcrpe_b3, float* dcrpe_w5, float* dcrpe_b5, float* dcrpe_w7, float* dcrpe_b7, float* ws, int B,
-                            int H, int W, int C, int heads, void* stream) {
+                            float* dcrpe_b3, float* dcrpe_w5, float* dcrpe_b5, float* dcrpe_w7, float* dcrpe_b7, float* dbias_qkv,
+                            float* ws, int B, int H, int W, int C, int heads, void* stream) {
     if (!qkv_bf16 || !dy_bf16 || !e_bf16 || !stats || !dqkv_bf16 || !ws || heads != 8 || (C % 64)) return MDV_ERR_ARG;
     if (gate && (!y_bf16 || !dgate)) return MDV_ERR_ARG;
     const int Ch = C / heads;
@@ -195,7 +198,7 @@ extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const voi
     CrpeG cg = {{dcrpe_w3, dcrpe_w5, dcrpe_w7}, {dcrpe_b3, dcrpe_b5, dcrpe_b7}};
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
     return attn_strip_bwd((const bf16*)qkv_bf16, (const bf16*)dy_bf16, (const bf16*)y_bf16, gate, kmax, zsum, A, ws, cw, cg,
-                          (const bf16*)e_bf16, (bf16*)dqkv_bf16, dgate, scale, B, H, W, C, Ch, (cudaStream_t)stream);
+                          (const bf16*)e_bf16, (bf16*)dqkv_bf16, dgate, dbias_qkv, scale, B, H, W, C, Ch, (cudaStream_t)stream);
 }
 
 extern "C" int mdv_da_gate_fwd(const float* label, const float* w1, const float* b1, const float* w2, const float* b2, float* hid_out,
@@ -222,7 +225,8 @@ extern "C" int mdv_da_gate_bwd(const float* label, const float* w2, const float*
     mdv_launch(da_gate_bwd_dhid_kernel, dim3(dim3(mdv_cdiv(hid, 32), B)), dim3(256), 0, st, w2, hid_in, dz, dhid, hid, C);
     MDV_CHECK_LAUNCH();
     const int total = C * hid + C + hid * nd + hid;
-    mdv_launch(da_gate_bwd2_kernel, dim3(mdv_cdiv(total, 256)), dim3(256), 0, st, label, hid_in, dz, dhid, dw1, db1, dw2, db2, B, nd, hid, C);
+    const int bsplit = B >= 64 ? 8 : (B >= 16 ? 4 : 1);
+    mdv_launch(da_gate_bwd2_kernel, dim3(mdv_cdiv(total, 256), bsplit), dim3(256), 0, st, label, hid_in, dz, dhid, dw1, db1, dw2, db2, B, nd, hid, C, bsplit);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

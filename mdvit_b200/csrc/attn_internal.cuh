@@ -16,5 +16,5 @@ long long attn_strip_ws_floats(int B, int C, int Ch);
 int attn_strip_fwd(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, float* zsum, float* A, float* ws, bf16* out,
                    bf16* eout, float scale, int B, int H, int W, int C, int Ch, cudaStream_t st);
 int attn_strip_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum,
-                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate, float scale,
-                   int B, int H, int W, int C, int Ch, cudaStream_t st);
+                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate,
+                   float* dbias_qkv, float scale, int B, int H, int W, int C, int Ch, cudaStream_t st);

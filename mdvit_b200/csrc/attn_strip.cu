@@ -356,7 +356,8 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
                                                     const float* __restrict__ rk, const float* __restrict__ kmax,
                                                     const float* __restrict__ zsum, const CrpeW& cw, const CrpeG& cg,
                                                     const bf16* __restrict__ ein, bf16* __restrict__ dqkv,
-                                                    float* __restrict__ dgate, float scale, int H, int Wd, int C, uint8_t* smem_s) {
+                                                    float* __restrict__ dgate, float* __restrict__ dbias_qkv, float scale, int H,
+                                                    int Wd, int C, uint8_t* smem_s) {
     using G = Cfg<CH>;
     const int grp0 = 0;
     const bool want_w = cg.w[0] != nullptr;
@@ -463,6 +464,7 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     __syncthreads();
     const int nstrips = g.th * g.nsx;
     float2 gacc = make_float2(0.f, 0.f);
+    float2 bq = make_float2(0.f, 0.f), bk = bq, bv = bq;      // column sums of dQ, dK, dV: the qkv Linear's bias gradient
     // ---- pass A: activation gradients
     for (int s = warp; s < nstrips; s += nwarp) {
         const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
@@ -542,6 +544,7 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
                     const float2 dq = fma2(splat(scale), sq, mul2(dF[t], e[t]));
                     const float2 dk = mul2(S[t], make_float2(sk.x - rr.x, sk.y - rr.y));
                     const float2 dv = make_float2(sv.x + tc[t].x, sv.y + tc[t].y);
+                    bq.x += dq.x; bq.y += dq.y; bk.x += dk.x; bk.y += dk.y; bv.x += dv.x; bv.y += dv.y;
                     bf16* drow = dqkv + ((size_t)b * N + n0 + t) * 3 * C + c0;
                     *reinterpret_cast<uint32_t*>(drow) = f2_to_bf2(dq.x, dq.y);
                     *reinterpret_cast<uint32_t*>(drow + C) = f2_to_bf2(dk.x, dk.y);
@@ -553,6 +556,14 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     if (gate && dgate && act) {
         atomicAdd(dgate + (size_t)b * C + c0, gacc.x / gt.x);
         atomicAdd(dgate + (size_t)b * C + c0 + 1, gacc.y / gt.y);
+    }
+    if (dbias_qkv && act) {
+        atomicAdd(dbias_qkv + c0, bq.x);
+        atomicAdd(dbias_qkv + c0 + 1, bq.y);
+        atomicAdd(dbias_qkv + C + c0, bk.x);
+        atomicAdd(dbias_qkv + C + c0 + 1, bk.y);
+        atomicAdd(dbias_qkv + 2 * C + c0, bv.x);
+        atomicAdd(dbias_qkv + 2 * C + c0 + 1, bv.y);
     }
     if (!want_w) return;   // block-uniform
     // ---- pass B: convolution weight / bias gradients, one kernel row at a time (7 float2 accumulators live)
@@ -637,13 +648,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf
                                                               const float* __restrict__ rk, const float* __restrict__ kmax,
                                                               const float* __restrict__ zsum, CrpeW cw, CrpeG cg,
                                                               const bf16* __restrict__ ein, bf16* __restrict__ dqkv,
-                                                              float* __restrict__ dgate, float scale, int H, int Wd, int C) {
+                                                              float* __restrict__ dgate, float* __restrict__ dbias_qkv, float scale,
+                                                              int H, int Wd, int C) {
     MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
-    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, H, Wd, C, smem_dyn);
-    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, H, Wd, C, smem_dyn);
-    else attn_bwd_strip_body<CH, 7, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, H, Wd, C, smem_dyn);
+    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
+    else attn_bwd_strip_body<CH, 7, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -676,7 +688,7 @@ int launch_fwd(const bf16* qkv, const float* A, const float* gate, const CrpeW& 
 template <int CH>
 int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* A, const float* dA, const float* rk,
                const float* kmax, const float* zsum, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate,
-               float scale, int B, int H, int W, int C, cudaStream_t st) {
+               float* dbias_qkv, float scale, int B, int H, int W, int C, cudaStream_t st) {
     const int full = 2 * tile_words(7) * 4 + 49 * 32 * 8 + 3 * CH * 32 * 8 + 50 * 64 * 4;
     // activation-gradient-only pass: no V tile -> half the shared memory, two blocks per SM
     const int smem = cg.w[0] ? full : full - tile_words(7) * 4;
@@ -687,7 +699,7 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
         configured = true;
     }
     mdv_launch(attn_bwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv,
-                                                                                       dgate, scale, H, W, C);
+                                                                                       dgate, dbias_qkv, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -741,8 +753,8 @@ int fwd_impl(const bf16* qkv, const float* gate, const CrpeW& cw, float* kmax, f
 
 template <int CH>
 int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum, const float* A,
-             float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate, float scale, int B, int H, int W,
-             int C, cudaStream_t st) {
+             float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate, float* dbias_qkv, float scale, int B,
+             int H, int W, int C, cudaStream_t st) {
     const int N = H * W;
     int nchunk = 0;
     float* part = ws;
@@ -753,7 +765,7 @@ int bwd_impl(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gat
     if (rc) return rc;
     mdv_launch(attn_combine_bwd_kernel, dim3(mdv_cdiv(B * C, 8)), dim3(256), 0, st, part, A, dA, rk, scale, C, CH, nchunk, B * C);
     MDV_CHECK_LAUNCH();
-    return launch_bwd<CH>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
+    return launch_bwd<CH>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, B, H, W, C, st);
 }
 
 }  // namespace
@@ -776,13 +788,13 @@ int attn_strip_fwd(const bf16* qkv, const float* gate, const CrpeW& cw, float* k
 }
 
 int attn_strip_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* kmax, const float* zsum,
-                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate, float scale,
-                   int B, int H, int W, int C, int Ch, cudaStream_t st) {
+                   const float* A, float* ws, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate,
+                   float* dbias_qkv, float scale, int B, int H, int W, int C, int Ch, cudaStream_t st) {
     switch (Ch) {
-        case 8: return bwd_impl<8>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
-        case 16: return bwd_impl<16>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
-        case 40: return bwd_impl<40>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
-        case 64: return bwd_impl<64>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, scale, B, H, W, C, st);
+        case 8: return bwd_impl<8>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, B, H, W, C, st);
+        case 16: return bwd_impl<16>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, B, H, W, C, st);
+        case 40: return bwd_impl<40>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, B, H, W, C, st);
+        case 64: return bwd_impl<64>(qkv, dy, yout, gate, kmax, zsum, A, ws, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, B, H, W, C, st);
         default: return MDV_ERR_UNSUPPORTED;
     }
 }

@@ -479,14 +479,13 @@ class BlockFn(torch.autograd.Function):
             ws = torch.empty(lib.mdv_attn_ws_floats(B, C, HEADS), dtype=F32, device=dev)
             check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(ecrpe), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
                                    ptr(stats), ptr(dqkv), ptr(dgate), ptr(G["c3w"]), ptr(G["c3b"]), ptr(G["c5w"]), ptr(G["c5b"]),
-                                   ptr(G["c7w"]), ptr(G["c7b"]), ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")
+                                   ptr(G["c7w"]), ptr(G["c7b"]), ptr(G["qkv_b"]), ptr(ws), B, H, W, C, HEADS, L.stream()), "mdv_attn_bwd")
             if da_live:
                 nd, hd = da_w1.shape[1], da_w1.shape[0]
                 ws2 = torch.empty(B * (C + hd), dtype=F32, device=dev)
                 check(lib.mdv_da_gate_bwd(ptr(label), ptr(da_w2), ptr(hid), ptr(gate), ptr(dgate), ptr(G["da_w1"]), ptr(G["da_b1"]),
                                           ptr(G["da_w2"]), ptr(G["da_b2"]), ptr(ws2), B, nd, hd, C, HEADS, L.stream()), "mdv_da_gate_bwd")
-            gemm_tn(dqkv, ln1, M, 3 * C, C, G["qkv_w"])
-            colsum(dqkv, M, 3 * C, G["qkv_b"])
+            gemm_tn(dqkv, ln1, M, 3 * C, C, G["qkv_w"])        # (qkv bias gradient: by-product of mdv_attn_bwd)
             dln1 = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(dqkv, prep_weight(qkv_w, 1, 3 * C, C), M, C, 3 * C, dln1)
             dx1, _ = layernorm_bwd(dln1, x1, mean1, rstd1, n1w, dx2, M, C, G["n1w"], G["n1b"])

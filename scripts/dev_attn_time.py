@@ -25,7 +25,7 @@ for (H, C) in ((64, 64), (32, 128), (16, 320), (8, 512)):
     ec = torch.empty_like(y); dqkv = torch.empty_like(qkv); dgate = torch.zeros(B, C, device=dev); gcw = [torch.zeros_like(t) for t in cw]
     st = L.stream()
     f = lambda: lib.mdv_attn_fwd(P(qkv), P(gate), *[P(t) for t in cw], P(stats), P(ws), P(y), P(ec), B, H, H, C, 8, st)
-    bw = lambda: lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ec), P(gate), *[P(t) for t in cw], P(stats), P(dqkv), P(dgate), *[P(t) for t in gcw], P(ws), B, H, H, C, 8, st)
-    bd = lambda: lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ec), P(gate), *[P(t) for t in cw], P(stats), P(dqkv), P(dgate), None, None, None, None, None, None, P(ws), B, H, H, C, 8, st)
+    bw = lambda: lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ec), P(gate), *[P(t) for t in cw], P(stats), P(dqkv), P(dgate), *[P(t) for t in gcw], None, P(ws), B, H, H, C, 8, st)
+    bd = lambda: lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ec), P(gate), *[P(t) for t in cw], P(stats), P(dqkv), P(dgate), None, None, None, None, None, None, None, P(ws), B, H, H, C, 8, st)
     mb = B * N * C * 2 / 1e6
     print(f"H={H} C={C}: fwd {bench(f):.1f} us (ideal {5*mb/6.45:.1f}), bwd {bench(bw):.1f} us, bwd(no wgrad) {bench(bd):.1f} us (ideal {9*mb/6.45:.1f})", flush=True)

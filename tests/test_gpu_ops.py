@@ -500,11 +500,13 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
     dqkv = torch.empty_like(qkv)
     dgate = torch.zeros(B, C, device=dev) if sup else None
     gcw = [torch.zeros_like(t_) for t_ in cw]
-    L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv), P(dgate), *[P(t_) for t_ in gcw], P(ws),
+    dbq = torch.zeros(3 * C, device=dev)
+    L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv), P(dgate), *[P(t_) for t_ in gcw], P(dbq), P(ws),
                              B, H, W, C, 8, L.stream()), "attn_bwd")
     g = q32.grad
     for sl in (slice(0, C), slice(C, 2 * C), slice(2 * C, 3 * C)):
         assert rel(dqkv[..., sl], g[..., sl]) < BF16_TOL
+    assert rel(dbq, g.sum(dim=(0, 1))) < BF16_TOL                                     # qkv bias gradient by-product
     for i in range(3):
         assert rel(gcw[2 * i], sd[f"crpe.conv_list.{i}.weight"].grad) < BF16_TOL
         assert rel(gcw[2 * i + 1], sd[f"crpe.conv_list.{i}.bias"].grad) < BF16_TOL
@@ -513,5 +515,5 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
         # activation-gradient-only mode (CRPE gradient pointers NULL): same dqkv, dgate still accumulated
         dqkv2, dgate2 = torch.empty_like(qkv), torch.zeros(B, C, device=dev)
         L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv2), P(dgate2), None, None, None, None,
-                                 None, None, P(ws), B, H, W, C, 8, L.stream()), "attn_bwd")
+                                 None, None, None, P(ws), B, H, W, C, 8, L.stream()), "attn_bwd")
         assert torch.equal(dqkv2, dqkv) and rel(dgate2, gref.grad) < BF16_TOL
