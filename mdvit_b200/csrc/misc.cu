@@ -499,7 +499,7 @@ extern "C" int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, 
 
 extern "C" int mdv_prep_weights_batched(const MdvPrepDesc* descs_dev, int n, void* stream) {
     if (!descs_dev || n <= 0) return MDV_ERR_ARG;
-    mdv_launch(prep_weights_batched_kernel, dim3(32, n), dim3(256), 0, (cudaStream_t)stream, descs_dev);
+    mdv_launch(prep_weights_batched_kernel, dim3(MDV_NUM_SMS, n), dim3(256), 0, (cudaStream_t)stream, descs_dev);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
