@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch-per-domain", type=int, default=1)
+    ap.add_argument("--model", default="MDViT", choices=["MDViT", "BASE"],
+                    help="MDViT (default, the headline metric) or BASE = BASELINE.json config 2: no DA, no MKD (extra, not the headline)")
     return ap.parse_args()
 
 
@@ -193,7 +195,7 @@ def main():
     import torch.distributed as dist
     from mdvit_b200 import _lib as L
     from mdvit_b200 import ops, synth
-    from mdvit_b200.model import MDViT
+    from mdvit_b200.model import BASE, MDViT
     from mdvit_b200.train_step import MKDTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,9 +212,12 @@ def main():
     B = args.batch_per_domain
 
     torch.manual_seed(0)
-    model = MDViT(img_size=IMG, drop_rate=0.1, drop_path_rate=0.1, adapt_method="Sup", num_domains=4, decoder_name="MLPFM").to(dev).train()
+    if args.model == "BASE":     # multi_train_BASE.py: BASE(adapt_method=False), seg loss only, one backward
+        model = BASE(img_size=IMG, drop_rate=0.1, drop_path_rate=0.1, adapt_method=False).to(dev).train()
+    else:
+        model = MDViT(img_size=IMG, drop_rate=0.1, drop_path_rate=0.1, adapt_method="Sup", num_domains=4, decoder_name="MLPFM").to(dev).train()
     ops.manual_seed(1234 + rank, dev)
-    trainer = MKDTrainer(model, lr=1e-4, weight_decay=0.05)
+    trainer = MKDTrainer(model, lr=1e-4, weight_decay=0.05, with_aux=(args.model != "BASE"))
     # synthetic inputs: per-rank slice of each domain batch, staged in pinned host memory for the e2e arm
     host = []
     for d in range(4):
@@ -275,20 +280,25 @@ def main():
     if rank == 0:
         roof = kernel_roofline(peaks, dev)
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.model == "MDViT":
             sec, cores = cpu_oracle_step_time(args.cpu_batch_per_domain, 2, 1)
             cpu = {"value": 4 * args.cpu_batch_per_domain / sec, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"oracle (torch fp32 restatement of the reference) train step, {4 * args.cpu_batch_per_domain} images/step "
                              f"at {IMG}x{IMG}, 1 warm-up + 2 timed steps"}
-        model_tflops = value * F_TRAIN_GFLOP_PER_IMG / 1e3
+        model_tflops = value * (34.4 if args.model == "BASE" else F_TRAIN_GFLOP_PER_IMG) / 1e3     # 3 x fwd GFLOP per image
+        if args.model == "BASE":
+            workload = (f"BASE(adapt_method=False) train step (BASELINE.json config 2): 4 domains x {B} images/GPU at {IMG}x{IMG}, dropout 0.1, "
+                        "DropPath 0.1, BCE+Dice, one backward, AdamW; bf16 tensor-core operands, fp32 accumulate/residual")
+        else:
+            workload = (f"MDViT(adapt_method=Sup, decoder=MLPFM) MKD train step: 4 domains x {B} images/GPU at {IMG}x{IMG}, "
+                        "dropout 0.1, DropPath 0.1, the 4 domain mini-batches stacked through the trunk in one pass (BatchNorm per domain "
+                        "group), MKD backward (single-sweep schedule, gradient-equivalent to the reference's two passes), AdamW; "
+                        "bf16 tensor-core operands, fp32 accumulate/residual")
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"MDViT(adapt_method=Sup, decoder=MLPFM) MKD train step: 4 domains x {B} images/GPU at {IMG}x{IMG}, "
-                                   "dropout 0.1, DropPath 0.1, the 4 domain mini-batches stacked through the trunk in one pass (BatchNorm per domain group), "
-                                   "MKD backward (single-sweep schedule, gradient-equivalent to the reference's two passes), AdamW; "
-                                   "bf16 tensor-core operands, fp32 accumulate/residual",
+            "config": {"workload": workload,
                        "batch_per_domain_per_gpu": B, "images_per_step": imgs_per_step, "parallelism": f"dp{world}",
                        "cuda_graph": use_graph, "l2": "per-step working set (>10 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * 3 * 4},

@@ -1,4 +1,4 @@
-"""Dev check (GPU): tcgen05 GEMM vs torch.matmul.  Not a pytest file; see tests/test_gemm_gpu.py."""
+"""Dev check (GPU): tcgen05 GEMM vs torch.matmul.  Not a pytest file; the pytest coverage is tests/test_gpu_ops.py::test_gemm_*."""
 import ctypes, sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
