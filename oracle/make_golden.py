@@ -100,6 +100,13 @@ def main():
         img, lab, d = batches[1]
         o, a = m(img, torch.nn.functional.one_hot(torch.full((2,), d), 4).float(), str(d))
         out["train64_out_after_1"], out["train64_aux_after_1"] = o.numpy(), a.numpy()
+    # ---- BASE (base.py:340-512; BASELINE.json config 2): no DA, no aux branch — eval and train-mode logits, 64x64, B=2
+    b = ref.BASE(img_size=64, drop_rate=0.0, drop_path_rate=0.0, adapt_method=False)
+    b.load_state_dict(synth.synth_state_dict(0, sup=False, aux=False), strict=True)
+    img, lab = synth.synth_batch(4, 0, 2, 64, 64)
+    with torch.no_grad():
+        out["base_eval64_out"] = b.eval()(img).numpy()
+        out["base_train64_out"] = b.train()(img).numpy()
     path = os.path.join(ROOT, "tests", "golden", "mdvit_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB;", len(out), "arrays")

@@ -260,6 +260,17 @@ def test_dropout_paths_run_and_are_reproducible(dev):
     assert rel_l2(o1, o2) < 5e-3 and rel_l2(o1, outs[0]) > 2e-2
 
 
+def test_base_logits_match_reference_golden_64(dev, golden):
+    """BASE (no DA, no aux branch; BASELINE.json config 2) against logits of the unmodified reference BASE, eval and train mode."""
+    from mdvit_b200.model import BASE
+    m = BASE(img_size=64, adapt_method=False).to(dev)
+    m.load_state_dict(synth.synth_state_dict(0, sup=False, aux=False), strict=True)
+    img, _ = synth.synth_batch(4, 0, 2, 64, 64)
+    with torch.no_grad():
+        assert rel(m.eval()(img.to(dev)), golden["base_eval64_out"]) < LOGIT_TOL_64
+        assert rel(m.train()(img.to(dev)), golden["base_train64_out"]) < LOGIT_TOL_64
+
+
 def test_base_model_without_adapter(dev):
     from mdvit_b200.model import BASE
     from mdvit_b200 import ops

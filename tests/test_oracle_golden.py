@@ -69,3 +69,19 @@ def test_bce_clamp_and_dice_edge_cases():
     assert torch.allclose(O.bce_loss(p, y), ref)
     z = torch.zeros(4)
     assert abs(O.dice_loss(z, z).item()) < 1e-12      # (0+eps)/(0+eps) -> loss 0
+
+
+def test_base_logits_64(golden):
+    """BASE (base.py:340-512): the oracle with domain_label=None / with_aux=False against the unmodified reference BASE."""
+    sd = {k: v.clone() for k, v in synth.synth_state_dict(0, sup=False, aux=False).items()}
+    for k in list(sd):
+        ck = synth.canonical_key(k)
+        if ck != k:
+            sd[k] = sd[ck]
+    img, _ = synth.synth_batch(4, 0, 2, 64, 64)
+    with torch.no_grad():
+        out, aux = O.mdvit_forward(sd, img, None, None, training=False, with_aux=False)
+        assert aux is None
+        np.testing.assert_allclose(out.numpy(), golden["base_eval64_out"], rtol=0, atol=2e-5)
+        out, _ = O.mdvit_forward(sd, img, None, None, training=True, with_aux=False)
+        np.testing.assert_allclose(out.numpy(), golden["base_train64_out"], rtol=0, atol=5e-5)
