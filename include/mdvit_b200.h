@@ -169,14 +169,22 @@ int mdv_unperm_conv_grad(const float* g, int ld, float* dw, int R, int cin, void
 
 /* ------------------------------------------------------------------ losses (multi_train_MDViT.py:147-169, Utils/losses.py:8-16) */
 /* sums: 8 doubles {bce(p,y), bce(q,y), p.y, p.p, y.y, q.y, q.q, q.p}; all-reduce them across ranks for the global Dice. */
-int mdv_loss_sums(const float* out, const float* aux, const float* label, void* sums, long long n, void* stream);
+/* label: fp32 [n] (label_u8 = 0; the reference's label.cuda().float(), multi_train_MDViT.py:136) or uint8 {0,1} (label_u8 = 1) */
+int mdv_loss_sums(const float* out, const float* aux, const void* label, int label_u8, void* sums, long long n, void* stream);
 int mdv_loss_finalize(const void* sums, double n_total, float* losses /* seg, aux, kt */, void* stream);
-int mdv_loss_bwd(const float* out, const float* aux, const float* label, const void* sums, double n_total, const float* coef,
-                 float* dout, float* daux, long long n, void* stream);
+int mdv_loss_bwd(const float* out, const float* aux, const void* label, int label_u8, const void* sums, double n_total,
+                 const float* coef, float* dout, float* daux, long long n, void* stream);
+
+/* Dice / Jaccard metrics of the trainer (multi_train_MDViT.py:172-177 calls medpy dc/jc on output.cpu().numpy() > 0.5, one
+ * host sync per domain per step): counts (DEVICE uint64[3]) += {|P & L|, |P|, |L|} with P = logits > 0 (== sigmoid > 0.5),
+ * L = label > 0.5.  dc = 2 c0 / (c1 + c2), jc = c0 / (c1 + c2 - c0); integer counts: bit-exact vs the host metric. */
+int mdv_seg_counts(const float* logits, const void* label, int label_u8, void* counts, long long n, void* stream);
 
 /* ------------------------------------------------------------------ optimizer / RNG */
-/* hyper (device fp32[8]): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale */
-int mdv_adamw(float* p, const float* g, float* m, float* v, const float* hyper, long long n, void* stream);
+/* One torch.optim.AdamW step (multi_train_MDViT.py:93-94,213) over a flat fp32 buffer.  hyper: DEVICE fp64[8] = {lr, beta1,
+ * beta2, eps, weight_decay, t, unused, grad_scale}; the call first bumps t (steps taken) on the device, then applies step t:
+ * the bias corrections 1-beta^t are computed on the device, so a captured CUDA graph replays correctly with no host input. */
+int mdv_adamw(float* p, const float* g, float* m, float* v, void* hyper, long long n, void* stream);
 int mdv_rng_bump(void* rng /* device uint64[2] {seed, step} */, void* stream);
 int mdv_droppath_scale(float* scale, int B, float p, const void* rng, uint32_t drop_stream, void* stream);
 

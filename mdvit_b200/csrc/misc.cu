@@ -272,13 +272,16 @@ __device__ __forceinline__ float bce_term(float p, float y) {
     return -(y * lp + (1.f - y) * l1p);
 }
 
+// labels travel as fp32 (the reference's label.cuda().float(), multi_train_MDViT.py:136) or as uint8 {0,1} (a quarter of
+// the host->device bytes; same values)
+template <typename LT>
 __global__ void __launch_bounds__(256) loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ aux,
-                                                         const float* __restrict__ label, double* __restrict__ sums, long long n) {
+                                                         const LT* __restrict__ label, double* __restrict__ sums, long long n) {
     MDV_PDL_SYNC();
     __shared__ float red[32];
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float y = label[i];
+        const float y = (float)label[i];
         const float p = 1.f / (1.f + expf(-out[i]));
         const float q = aux ? 1.f / (1.f + expf(-aux[i])) : 0.f;
         a[0] += bce_term(p, y);
@@ -314,8 +317,9 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, double n_t
 
 // Gradients w.r.t. the logits for  L = c_seg*L_seg + c_aux*L_aux + c_kt*L_kt  (coef[0..2]); see SURVEY.md App. E.
 // PyTorch's BCELoss backward: (p - y) / max(p(1-p), 1e-12) / n, times sigmoid' = p(1-p).
+template <typename LT>
 __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ aux,
-                                                        const float* __restrict__ label, const double* __restrict__ sums,
+                                                        const LT* __restrict__ label, const double* __restrict__ sums,
                                                         double n_total, const float* __restrict__ coef, float* __restrict__ dout,
                                                         float* __restrict__ daux, long long n) {
     MDV_PDL_SYNC();
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
     const float aq = (float)(2.0 / den_q), bq = (float)(2.0 * num_q / (den_q * den_q));
     const float ak = (float)(2.0 / den_k), bk = (float)(2.0 * num_k / (den_k * den_k));
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float y = label[i];
+        const float y = (float)label[i];
         const float p = 1.f / (1.f + expf(-out[i]));
         const float sp = p * (1.f - p);
         float gp = c_seg * ((p - y) / fmaxf(sp, 1e-12f) * inv_n + (-ap * y + bp * p));
@@ -346,14 +350,50 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
     }
 }
 
-// ---------------------------------------------------------------------------------- AdamW (torch.optim.AdamW semantics)
-// hyper (device fp32[8]): lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, grad_scale
-__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                     float* __restrict__ v, const float* __restrict__ hyper, long long n) {
+// Dice / Jaccard counts of the thresholded prediction (multi_train_MDViT.py:172-177: medpy dc/jc of sigmoid(out) > 0.5 vs
+// label > 0.5, on the host in the reference — one .cpu() sync per domain per step): counts[0..2] += |P&L|, |P|, |L|.
+template <typename LT>
+__global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ logits, const LT* __restrict__ label,
+                                                          unsigned long long* __restrict__ counts, long long n) {
     MDV_PDL_SYNC();
-    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6],
-                gs = hyper[7];
-    const float step = lr / bc1, isb2 = rsqrtf(bc2);
+    unsigned int c0 = 0, c1 = 0, c2 = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const bool p = logits[i] > 0.f;            // sigmoid(x) > 0.5  <=>  x > 0
+        const bool l = (float)label[i] > 0.5f;
+        c0 += p && l;
+        c1 += p;
+        c2 += l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counts + 0, (unsigned long long)c0);
+        atomicAdd(counts + 1, (unsigned long long)c1);
+        atomicAdd(counts + 2, (unsigned long long)c2);
+    }
+}
+
+// ---------------------------------------------------------------------------------- AdamW (torch.optim.AdamW semantics)
+// hyper (device fp64[8]): lr, beta1, beta2, eps, weight_decay, t (steps taken so far), unused, grad_scale
+__global__ void adamw_tick_kernel(double* hyper) {
+    MDV_PDL_SYNC();
+    hyper[5] += 1.0;
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ v, const double* __restrict__ hyper, long long n) {
+    MDV_PDL_SYNC();
+    // the step count lives on the device (bumped by adamw_tick_kernel just before this kernel), so a CUDA-graph replay
+    // needs no per-step host->device parameter traffic; bias corrections in double, as torch.optim.AdamW computes them
+    const double t = hyper[5];
+    const float lr = (float)hyper[0], b1 = (float)hyper[1], b2 = (float)hyper[2], eps = (float)hyper[3], wd = (float)hyper[4],
+                gs = (float)hyper[7];
+    const double bc1 = 1.0 - pow(hyper[1], t), bc2 = 1.0 - pow(hyper[2], t);
+    const float step = (float)(hyper[0] / bc1), isb2 = (float)(1.0 / sqrt(bc2));
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
         if (i + 3 < n) {
             float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
@@ -512,12 +552,13 @@ extern "C" int mdv_unperm_conv_grad(const float* g, int ld, float* dw, int R, in
 }
 
 // sums: 8 doubles (zeroed here).  aux may be NULL (BASE model: only L_seg is meaningful).
-extern "C" int mdv_loss_sums(const float* out, const float* aux, const float* label, void* sums, long long n, void* stream) {
+extern "C" int mdv_loss_sums(const float* out, const float* aux, const void* label, int label_u8, void* sums, long long n, void* stream) {
     if (!out || !label || !sums || n <= 0) return MDV_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, 8 * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
-    mdv_launch(loss_sums_kernel, dim3(grid_for(n)), dim3(256), 0, st, out, aux, label, (double*)sums, n);
+    if (label_u8) mdv_launch(loss_sums_kernel<uint8_t>, dim3(grid_for(n)), dim3(256), 0, st, out, aux, (const uint8_t*)label, (double*)sums, n);
+    else mdv_launch(loss_sums_kernel<float>, dim3(grid_for(n)), dim3(256), 0, st, out, aux, (const float*)label, (double*)sums, n);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -529,19 +570,34 @@ extern "C" int mdv_loss_finalize(const void* sums, double n_total, float* losses
     return MDV_OK;
 }
 
-extern "C" int mdv_loss_bwd(const float* out, const float* aux, const float* label, const void* sums, double n_total,
+extern "C" int mdv_loss_bwd(const float* out, const float* aux, const void* label, int label_u8, const void* sums, double n_total,
                             const float* coef, float* dout, float* daux, long long n, void* stream) {
     if (!out || !label || !sums || !coef || !dout || (aux && !daux)) return MDV_ERR_ARG;
-    mdv_launch(loss_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, aux, label, (const double*)sums, n_total, coef, dout, daux, n);
+    if (label_u8)
+        mdv_launch(loss_bwd_kernel<uint8_t>, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, aux, (const uint8_t*)label, (const double*)sums, n_total, coef, dout, daux, n);
+    else
+        mdv_launch(loss_bwd_kernel<float>, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, aux, (const float*)label, (const double*)sums, n_total, coef, dout, daux, n);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
-extern "C" int mdv_adamw(float* p, const float* g, float* m, float* v, const float* hyper, long long n, void* stream) {
+extern "C" int mdv_seg_counts(const float* logits, const void* label, int label_u8, void* counts, long long n, void* stream) {
+    if (!logits || !label || !counts || n <= 0) return MDV_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (label_u8) mdv_launch(seg_counts_kernel<uint8_t>, dim3(grid_for(n)), dim3(256), 0, st, logits, (const uint8_t*)label, (unsigned long long*)counts, n);
+    else mdv_launch(seg_counts_kernel<float>, dim3(grid_for(n)), dim3(256), 0, st, logits, (const float*)label, (unsigned long long*)counts, n);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_adamw(float* p, const float* g, float* m, float* v, void* hyper_, long long n, void* stream) {
+    double* hyper = (double*)hyper_;
     if (!p || !g || !m || !v || !hyper || n <= 0) return MDV_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15)
         return MDV_ERR_ARG;
-    mdv_launch(adamw_kernel, dim3(grid_for((n + 3) / 4)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, hyper, n);
+    mdv_launch(adamw_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, hyper);
+    MDV_CHECK_LAUNCH();
+    mdv_launch(adamw_kernel, dim3(grid_for((n + 3) / 4)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (const double*)hyper, n);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

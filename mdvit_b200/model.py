@@ -17,6 +17,15 @@ from . import ops
 CRPE_WINDOW = {3: 2, 5: 3, 7: 3}
 
 
+def _ctor_draw(*convs):
+    """The reference's conv containers re-draw their conv weights at construction time (mpvit.py:109-113, mdvit.py:104-112,
+    Decoders.py:45-53) before MDViT._init_weights overwrites them again.  The values are dead, but the draws advance the
+    torch RNG; repeating them keeps `torch.manual_seed(s); MDViT(...)` bit-identical to the reference's random init."""
+    for c in convs:
+        fan_out = c.kernel_size[0] * c.kernel_size[1] * c.out_channels
+        c.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+
+
 # ----------------------------------------------------------------------------------------------- parameter containers
 class Conv2d_BN(nn.Module):
     """mpvit.py:81-124 (conv no bias + BN + act)."""
@@ -25,6 +34,7 @@ class Conv2d_BN(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, pad, bias=False)
         self.bn = nn.BatchNorm2d(out_ch)
+        _ctor_draw(self.conv)
         self.act_layer = act_layer() if act_layer is not None else nn.Identity()
 
 
@@ -38,6 +48,7 @@ class DWConv2d_BN(nn.Module):
         self.bn = nn.BatchNorm2d(out_ch)
         self.act = nn.Hardswish()
         self.stride = stride
+        _ctor_draw(self.dwconv, self.pwconv)
 
 
 class DWCPatchEmbed(nn.Module):
@@ -66,6 +77,7 @@ class DecoderDWConv2d_BN(nn.Module):
         self.pwconv = nn.Conv2d(out_ch, out_ch, 1, 1, 0, bias=False)
         self.bn = nn.BatchNorm2d(out_ch)
         self.act = nn.Hardswish()
+        _ctor_draw(self.dwconv, self.pwconv)
 
 
 class ConvPosEnc(nn.Module):
@@ -411,5 +423,7 @@ class BASE(_Trunk):
         dec4, h, w = self._decode(enc, domain_label)
         out = self._head(dec4, h, w, img_size)
         if out_feat:
-            return {'seg': out, 'feat': enc[3][0].mean(dim=1)}
+            # base.py:509-510 returns the un-pooled last encoder map [B, C, H/32, W/32] here (only out_seg=False pools)
+            t3, H3, W3 = enc[3]
+            return {'seg': out, 'feat': t3.transpose(1, 2).reshape(t3.shape[0], t3.shape[2], H3, W3).contiguous()}
         return out

@@ -4,8 +4,8 @@ tape; all arithmetic runs in libmdvit_b200.so.  Activations are token-major fp32
 
 Every Function tolerates being back-propagated twice over one graph (multi_train_MDViT.py:201,207 call backward
 with retain_graph=True and then again): saved tensors are never written in backward, all backward scratch is
-freshly allocated, and parameter gradients are accumulated into `.grad` in place when it already exists (see
-gtarget) or returned for autograd to install; the requires_grad flips on `domain_layer` between the two passes are
+freshly allocated, and parameter gradients are returned for autograd to install (or, for a trainer that opted in, accumulated into its
+own `.grad` buffers in place — see gtarget); the requires_grad flips on `domain_layer` between the two passes are
 honoured at backward time.
 """
 import ctypes
@@ -358,21 +358,34 @@ def _grads_done(ctx):
         _GRAD_READY_CB(ctx.tag, ctx.params)
 
 
+def enable_inplace_grad_accumulation(params, on=True):
+    """Opt-in for gtarget()'s fast path: weight-gradient kernels of these parameters add straight into `p.grad` and
+    backward returns None for them, i.e. autograd's AccumulateGrad node (tensor hooks, post-accumulate-grad hooks, a
+    stock DDP/FSDP reducer, optimizer-in-backward) is BYPASSED.  Only a caller that owns the gradient buffers and the
+    reduction may switch it on — train_step.MKDTrainer does, for its flat buffer.  Off by default: a plain
+    `loss.backward()` / `torch.autograd.grad()` on the module behaves like any nn.Module."""
+    for p in params:
+        p._mdv_inplace_grad = bool(on)
+
+
 def gtarget(p, shape=None, da=False):
     """Where a parameter gradient is accumulated.  Returns (buffer, value_to_return_from_backward).
 
-    All parameter-gradient kernels ACCUMULATE (+=).  If the parameter already owns a contiguous fp32 .grad (the fused
-    trainer's flat buffer, or a second backward pass) the kernels add straight into it and backward returns None for it;
-    otherwise a zero buffer is returned for autograd to install.  A parameter whose requires_grad was switched off after
-    the forward (multi_train_MDViT.py:198-200 freezes `domain_layer`) gets a scratch buffer and nothing is returned."""
+    All parameter-gradient kernels ACCUMULATE (+=) into a zero-initialised buffer that backward returns, so autograd
+    installs / accumulates it through AccumulateGrad like any other gradient (hooks fire, torch.autograd.grad works).
+    Parameters opted in with enable_inplace_grad_accumulation() that already own a contiguous fp32 .grad get the kernels'
+    sums added straight into it instead, and backward returns None for them.  A parameter whose requires_grad was switched
+    off after the forward (multi_train_MDViT.py:198-200 freezes `domain_layer`) gets a scratch buffer and nothing is
+    returned."""
     if p is None or (_BWD_MODE == "da_only" and not da):
         return None, None
     if not p.requires_grad:      # frozen after the forward: compute into scratch, hand nothing to autograd
         z = torch.zeros_like(p, memory_format=torch.contiguous_format)
         return (z if shape is None else z.view(shape)), None
-    g = p.grad
-    if g is not None and g.dtype == F32 and g.is_contiguous() and g.device == p.device and g.data_ptr() % 16 == 0:
-        return (g if shape is None else g.view(shape)), None
+    if getattr(p, "_mdv_inplace_grad", False):
+        g = p.grad
+        if g is not None and g.dtype == F32 and g.is_contiguous() and g.device == p.device and g.data_ptr() % 16 == 0:
+            return (g if shape is None else g.view(shape)), None
     z = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return (z if shape is None else z.view(shape)), z
 
@@ -902,39 +915,88 @@ class SplitDomainsFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------- fused losses
+def _label_arg(label):
+    """Labels as the trainer hands them over: fp32 (label.cuda().float(), multi_train_MDViT.py:136) or uint8 {0,1}."""
+    if label.dtype == torch.uint8:
+        return _contig(label), 1
+    return _contig(label.float()), 0
+
+
 class SegLossFn(torch.autograd.Function):
-    """(L_seg, L_aux, L_kt) of multi_train_MDViT.py:147-169 in one pass over (out, aux, label); `reduce_sums` (optional
-    callable) all-reduces the 8 partial sums across data-parallel ranks so Dice is the global-batch Dice."""
+    """(L_seg, L_aux, L_kt) of multi_train_MDViT.py:147-169 for G domain mini-batches at once: one pass over each
+    (out, aux, label) -> [G,8] partial sums; `reduce_sums` (optional callable) all-reduces them ONCE across data-parallel
+    ranks so BCE/Dice are those of the gathered global batch; -> losses [G,3].  Inputs: out_0.., aux_0.. (or None), label_0.."""
 
     @staticmethod
-    def forward(ctx, out, aux, label, n_total, reduce_sums):
-        out, label = _contig(out.float()), _contig(label.float())
-        aux = _contig(aux.float()) if aux is not None else None
-        dev, n = out.device, out.numel()
+    def forward(ctx, n_total, reduce_sums, G, *tensors):
+        outs = [_contig(t.float()) for t in tensors[:G]]
+        auxs = [(_contig(t.float()) if t is not None else None) for t in tensors[G:2 * G]]
+        labs = [_label_arg(t) for t in tensors[2 * G:3 * G]]
+        dev = outs[0].device
         lib = L.lib()
-        with _dev_ctx(out):
-            sums = torch.empty(8, dtype=torch.float64, device=dev)
-            check(lib.mdv_loss_sums(ptr(out), ptr(aux), ptr(label), ptr(sums), n, L.stream()), "mdv_loss_sums")
+        with _dev_ctx(outs[0]):
+            sums = torch.empty((G, 8), dtype=torch.float64, device=dev)
+            for g in range(G):
+                check(lib.mdv_loss_sums(ptr(outs[g]), ptr(auxs[g]), ptr(labs[g][0]), labs[g][1], ptr(sums[g]), outs[g].numel(), L.stream()),
+                      "mdv_loss_sums")
             if reduce_sums is not None:
                 reduce_sums(sums)
-            losses = torch.empty(3, dtype=F32, device=dev)
-            check(lib.mdv_loss_finalize(ptr(sums), ctypes.c_double(n_total or n), ptr(losses), L.stream()), "mdv_loss_finalize")
-        ctx.save_for_backward(out, aux, label, sums)
-        ctx.n_total = float(n_total or n)
+            losses = torch.empty((G, 3), dtype=F32, device=dev)
+            nt = [float(n_total or o.numel()) for o in outs]
+            for g in range(G):
+                check(lib.mdv_loss_finalize(ptr(sums[g]), ctypes.c_double(nt[g]), ptr(losses[g]), L.stream()), "mdv_loss_finalize")
+        ctx.save_for_backward(sums, *outs, *[a for a in auxs if a is not None], *[l for l, _ in labs])
+        ctx.G, ctx.nt, ctx.has_aux, ctx.lab_u8 = G, nt, [a is not None for a in auxs], [u for _, u in labs]
         return losses
 
     @staticmethod
     def backward(ctx, dl):
-        out, aux, label, sums = ctx.saved_tensors
+        G = ctx.G
+        sums, *rest = ctx.saved_tensors
+        outs, rest = rest[:G], rest[G:]
+        na = sum(ctx.has_aux)
+        it = iter(rest[:na])
+        auxs = [next(it) if h else None for h in ctx.has_aux]
+        labs = rest[na:]
         lib = L.lib()
         dl = _contig(dl.float())
-        with _dev_ctx(out):
-            dout = torch.empty_like(out)
-            daux = torch.empty_like(aux) if aux is not None else None
-            check(lib.mdv_loss_bwd(ptr(out), ptr(aux), ptr(label), ptr(sums), ctypes.c_double(ctx.n_total), ptr(dl), ptr(dout), ptr(daux),
-                                   out.numel(), L.stream()), "mdv_loss_bwd")
-        return dout, daux, None, None, None
+        douts, dauxs = [], []
+        with _dev_ctx(outs[0]):
+            for g in range(G):
+                dout = torch.empty_like(outs[g])
+                daux = torch.empty_like(auxs[g]) if auxs[g] is not None else None
+                check(lib.mdv_loss_bwd(ptr(outs[g]), ptr(auxs[g]), ptr(labs[g]), ctx.lab_u8[g], ptr(sums[g]), ctypes.c_double(ctx.nt[g]),
+                                       ptr(dl[g]), ptr(dout), ptr(daux), outs[g].numel(), L.stream()), "mdv_loss_bwd")
+                douts.append(dout)
+                dauxs.append(daux)
+        return (None, None, None, *douts, *dauxs, *([None] * G))
+
+
+def seg_losses_multi(outs, auxs, labels, n_total=None, reduce_sums=None):
+    """[G,3] losses (seg, aux, kt) of G domain mini-batches; one all-reduce of the [G,8] partial sums when data-parallel."""
+    G = len(outs)
+    return SegLossFn.apply(n_total, reduce_sums, G, *outs, *auxs, *labels)
 
 
 def seg_losses(out, aux, label, n_total=None, reduce_sums=None):
-    return SegLossFn.apply(out, aux, label, n_total, reduce_sums)
+    return seg_losses_multi([out], [aux], [label], n_total, reduce_sums)[0]
+
+
+def seg_counts(logits, label, counts=None):
+    """Device-side Dice/Jaccard counts {|P&L|, |P|, |L|} (int64[3], accumulated) of the thresholded prediction — replaces the
+    per-domain `output.cpu().numpy()` + medpy dc/jc host round trip of multi_train_MDViT.py:172-177; read back when logging."""
+    logits = _contig(logits.detach().float())
+    lab, u8 = _label_arg(label)
+    if counts is None:
+        counts = torch.zeros(3, dtype=torch.int64, device=logits.device)
+    with _dev_ctx(logits):
+        check(L.lib().mdv_seg_counts(ptr(logits), ptr(lab), u8, ptr(counts), logits.numel(), L.stream()), "mdv_seg_counts")
+    return counts
+
+
+def dice_jaccard(counts):
+    """(dc, jc) from seg_counts() with medpy.metric.binary semantics (0.0 when the denominator is empty)."""
+    c = counts.tolist()
+    dc = 2.0 * c[0] / (c[1] + c[2]) if (c[1] + c[2]) > 0 else 0.0
+    jc = c[0] / (c[1] + c[2] - c[0]) if (c[1] + c[2] - c[0]) > 0 else 0.0
+    return dc, jc

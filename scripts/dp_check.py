@@ -51,7 +51,7 @@ lg = [torch.empty_like(losses) for _ in range(world)]
 dist.all_gather(lg, losses.detach())
 same_loss = all(torch.equal(lg[0], x) for x in lg)
 # (c) optimizer step keeps replicas in sync
-tr._set_hyper(); tr.optimizer_step(); torch.cuda.synchronize()
+tr.optimizer_step(); torch.cuda.synchronize()
 chk = tr.flat.double().sum().reshape(1)
 allc = [torch.empty_like(chk) for _ in range(world)]
 dist.all_gather(allc, chk)

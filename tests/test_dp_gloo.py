@@ -54,14 +54,18 @@ def _bucketer_case(rank, world):
     flat = torch.randn(total)
     local = flat.clone()
     ranges = {i: (o, n) for i, (o, n) in enumerate(zip(offs, sizes))}
-    bk = GradBucketer(flat, ranges, n_buckets=4)
+    bk = GradBucketer(flat, ranges, n_buckets=4, first_bucket_frac=0.05)
+    assert bk.bounds[0][1] - bk.bounds[0][0] < total // 4     # the first bucket (finalised last) is the small one
     # layout: contiguous, disjoint, covers everything
     assert bk.bounds[0][0] == 0 and bk.bounds[-1][1] == total
     assert all(a[1] == b[0] for a, b in zip(bk.bounds, bk.bounds[1:]))
     # uses: params 2 and 4 are shared by two Functions; params 8, 9 are never touched by the last-run graph
+    assert bk.needs_recording("fused")
+    bk.start_recording("fused")
     for keys in ([0, 1], [2, 3], [2, 4], [4, 5], [6, 7]):
         bk.record_use(keys)
-    bk.begin()
+    assert not bk.needs_recording("fused") and bk.needs_recording("per_domain")
+    bk.begin("fused")
     log = []
     order = [[6, 7], [4, 5], [2, 4], [2, 3], [0, 1]]          # backward visits Functions in reverse
     for keys in order:
@@ -85,6 +89,17 @@ def _bucketer_case(rank, world):
     gathered = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     assert torch.allclose(flat, sum(gathered), atol=1e-6)
+    # guards: a gradient reported after its bucket was reduced (forward path changed without re-recording), and a
+    # Function of another domain graph running after the first-forwarded graph started, must raise — never mis-reduce
+    import pytest
+    with pytest.raises(RuntimeError):
+        bk.report([0])              # every bucket has been reduced already
+    bk.begin("fused")
+    bk.report([6, 7])
+    with pytest.raises(RuntimeError):
+        bk.report([0], tag=2)       # another domain's graph after tag 0 started
+    bk.begin("fused")
+    bk.report([0], tag=3)           # before tag 0 starts: fine, ignored
     return log
 
 

@@ -402,11 +402,16 @@ def test_fused_losses_match_reference_formulas(env):
     y = (torch.rand(n, device=dev) < 0.3).float()
     sums = torch.empty(8, dtype=torch.float64, device=dev)
     losses = torch.empty(3, device=dev)
-    L.check(lib.mdv_loss_sums(L.ptr(out), L.ptr(aux), L.ptr(y), L.ptr(sums), n, L.stream()), "sums")
+    L.check(lib.mdv_loss_sums(L.ptr(out), L.ptr(aux), L.ptr(y), 0, L.ptr(sums), n, L.stream()), "sums")
     L.check(lib.mdv_loss_finalize(L.ptr(sums), float(n), L.ptr(losses), L.stream()), "fin")
     ref = O.seg_losses(out, aux, y)
     for a, b in zip(losses, ref):
         assert abs(a.item() - b.item()) < 2e-5 * max(1.0, abs(b.item()))
+    # uint8 labels (a quarter of the host->device bytes): identical sums
+    sums8 = torch.empty(8, dtype=torch.float64, device=dev)
+    y8 = y.to(torch.uint8)
+    L.check(lib.mdv_loss_sums(L.ptr(out), L.ptr(aux), L.ptr(y8), 1, L.ptr(sums8), n, L.stream()), "sums8")
+    assert (sums8 - sums).abs().max().item() <= 1e-9 * sums.abs().max().item()
     coef = torch.tensor([0.5, 1.0, 0.5], device=dev)
     # gradient reference: nn.BCELoss's own backward (the oracle's log().clamp() formula gives 0*inf = nan at saturated
     # sigmoids, where PyTorch's BCELoss backward — and the reference trainer — give 0)
@@ -415,8 +420,11 @@ def test_fused_losses_match_reference_formulas(env):
     l_seg, l_aux, l_kt = bce(p, y) + O.dice_loss(p, y), bce(q, y) + O.dice_loss(q, y), O.dice_loss(q, p)
     (0.5 * l_seg + l_aux + 0.5 * l_kt).backward()
     dout, daux = torch.empty(n, device=dev), torch.empty(n, device=dev)
-    L.check(lib.mdv_loss_bwd(L.ptr(out), L.ptr(aux), L.ptr(y), L.ptr(sums), float(n), L.ptr(coef), L.ptr(dout), L.ptr(daux), n, L.stream()), "lb")
+    L.check(lib.mdv_loss_bwd(L.ptr(out), L.ptr(aux), L.ptr(y), 0, L.ptr(sums), float(n), L.ptr(coef), L.ptr(dout), L.ptr(daux), n, L.stream()), "lb")
     assert rel(dout, out.grad) < 1e-4 and rel(daux, aux.grad) < 1e-4
+    dout8, daux8 = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    L.check(lib.mdv_loss_bwd(L.ptr(out), L.ptr(aux), L.ptr(y8), 1, L.ptr(sums), float(n), L.ptr(coef), L.ptr(dout8), L.ptr(daux8), n, L.stream()), "lb8")
+    assert torch.equal(dout8, dout) and torch.equal(daux8, daux)
 
 
 def test_adamw_matches_torch(env):
@@ -429,12 +437,14 @@ def test_adamw_matches_torch(env):
     ref = p.clone().requires_grad_()
     opt = torch.optim.AdamW([ref], lr=1e-4, weight_decay=0.05)
     m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
-    for t in range(1, 4):
+    # the step count t lives in hyper[5] on the device and is bumped by the call itself (graph replays need no host input)
+    hyper = torch.tensor([1e-4, 0.9, 0.999, 1e-8, 0.05, 0.0, 0.0, 1.0], dtype=torch.float64, device=dev)
+    for t in range(1, 8):
         ref.grad = g * t
         opt.step()
-        hyper = torch.tensor([1e-4, 0.9, 0.999, 1e-8, 0.05, 1 - 0.9 ** t, 1 - 0.999 ** t, 1.0], device=dev)
         gt = (g * t).contiguous()
         L.check(lib.mdv_adamw(L.ptr(p), L.ptr(gt), L.ptr(m), L.ptr(v), L.ptr(hyper), n, L.stream()), "adamw")
+    assert int(hyper[5].item()) == 7
     assert (p - ref.detach()).abs().max().item() < 2e-7
 
 

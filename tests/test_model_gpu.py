@@ -223,10 +223,10 @@ def test_train_step_vs_oracle_on_gpu_and_adamw(dev):
     assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
     # AdamW: p <- p(1 - lr wd) - lr m_hat / (sqrt(v_hat) + eps); at step 1 this is -lr*sign(g) wherever |g| >> eps
     before = {n: p.detach().clone() for n, p in m.named_parameters()}
-    tr._set_hyper()
     tr.optimizer_step()
     torch.cuda.synchronize()
-    for n, p in list(m.named_parameters())[:40]:
+    assert tr.t == 1
+    for n, p in m.named_parameters():
         want = before[n].clone()
         O.adamw_step(want, grads[n], torch.zeros_like(want), torch.zeros_like(want), step=1)
         assert (p.detach() - want).abs().max().item() < 1e-6, n
@@ -306,10 +306,15 @@ def test_graph_step_keeps_bf16_weight_mirror_fresh(dev):
     batches = [tuple(t.to(dev) for t in synth.synth_batch(5, d, 2, 64, 64)) + (d,) for d in range(4)]
     m1, m2 = build(dev).train(), build(dev).train()
     eager, graph = MKDTrainer(m1), MKDTrainer(m2)
-    graph.capture(batches, warmup=1)
-    l_eager = [eager.step(batches).clone() for _ in range(3)][-1]          # warm-up step + capture-free replays below = 3 updates
+    before = {k: v.clone() for k, v in m2.state_dict().items()}
+    graph.capture(batches, warmup=2)
+    # capture() warms up with real optimizer steps but restores parameters, moments, step count and BatchNorm buffers
+    assert graph.t == 0 and all(torch.equal(v, before[k]) for k, v in m2.state_dict().items())
+    assert float(graph.m.abs().max()) == 0.0 and float(graph.v.abs().max()) == 0.0
+    l_eager = [eager.step(batches).clone() for _ in range(2)][-1]
     l_graph = [graph.step_graph(None).clone() for _ in range(2)][-1]
     torch.cuda.synchronize()
+    assert graph.t == 2 and eager.t == 2
     checked = 0
     for (_, mode, _), (ref, _, dst, rows, cols, out_ld, _, cin) in graph.mirror.entries.items():
         w = ref()

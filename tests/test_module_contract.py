@@ -100,3 +100,29 @@ def test_bench_reference_arm_prints_contract_json():
     assert d["impl"] == "reference" and d["metric"] == "mdvit_train_images_per_sec" and d["unit"] == "images/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_random_init_is_bit_identical_to_the_reference_constructor():
+    """BASELINE.json north_star: parity "on identical random-init weights".  torch.manual_seed(0) + MDViT(...) must give the
+    weights the reference's stock constructor gives from the same seed (mdvit.py:484-504,648-664), including the dead
+    construction-time draws of its conv containers — checked against fingerprints of the UNMODIFIED reference's parameters
+    (oracle/make_golden_randinit.py), and directly against the reference when /root/reference is present."""
+    import os
+    import numpy as np
+    from mdvit_b200.model import MDViT
+    from tests.helpers import fingerprint
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rg = np.load(os.path.join(root, "tests", "golden", "mdvit_randinit_golden.npz"), allow_pickle=False)
+    torch.manual_seed(0)
+    m = MDViT(img_size=256, drop_rate=0.0, drop_path_rate=0.0, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")
+    names = [str(n) for n in rg["param_names"]]
+    assert names == [n for n, _ in m.named_parameters()]
+    fp = fingerprint(list(m.named_parameters()))
+    assert np.abs(fp - rg["init_fp"]).max() <= 1e-9 * np.abs(rg["init_fp"]).max()
+    from oracle import ref_shim
+    if ref_shim.available():
+        ref = ref_shim.load_reference()
+        torch.manual_seed(0)
+        r = ref.MDViT(img_size=256, drop_rate=0.0, drop_path_rate=0.0, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")
+        a, b = r.state_dict(), m.state_dict()
+        assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
