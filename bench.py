@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--impl", default="mdvit_b200")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the stock-PyTorch-eager-on-this-GPU baseline leg")
     ap.add_argument("--cpu-batch-per-domain", type=int, default=1)
     ap.add_argument("--model", default="MDViT", choices=["MDViT", "BASE"],
                     help="MDViT (default, the headline metric) or BASE = BASELINE.json config 2: no DA, no MKD (extra, not the headline)")
@@ -101,8 +102,8 @@ def cpu_oracle_step_time(batch_per_domain, steps, warmup, threads=None):
     from mdvit_b200 import synth
     from mdvit_b200.model import MDViT
     from oracle import mdvit_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must use all host cores regardless of the launcher
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0)
     holder = MDViT(img_size=IMG, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")   # parameter container: reference init
     sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
@@ -135,8 +136,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)
     bpd = args.cpu_batch_per_domain
-    steps = max(1, min(args.steps, 12))          # ~6 s of CPU work per 4-image step: keep the whole arm within ~2 minutes
+    steps = max(1, min(args.steps, 12))          # ~2 s of CPU work per 4-image step: keep the whole arm within ~2 minutes
     sec, cores = cpu_oracle_step_time(bpd, steps, min(args.warmup, 1))
     val = 4 * bpd / sec
     sample = f"{4 * bpd} images/step ({bpd}/domain x 4 domains) at {IMG}x{IMG}, fp32, dropout on, {steps} timed steps"
@@ -145,10 +147,62 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MDViT(Sup, MLPFM) MKD train step, CPU restatement of the reference (oracle port), {sample}"},
+        "config": {"workload": f"MDViT(Sup, MLPFM) MKD train step, CPU restatement of the reference (oracle port: the reference source is "
+                               f"not present on the GPU box), {sample}"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def gpu_eager_baseline(device, B, steps=2, warmup=1):
+    """The reference algorithm as stock PyTorch eager on THIS GPU (BASELINE.md section 2's "reference on B200" row): the
+    oracle port's MKD train step (4 domain forwards, two backward passes over the retained graphs, torch.optim.AdamW) at
+    the bench's batch, timed with CUDA events — in fp32 (torch defaults: cuBLAS fp32, cuDNN TF32 convs) and under bf16
+    autocast.  A reported baseline beside the CPU one; nothing of mdvit_b200's kernels runs here."""
+    import torch
+    from mdvit_b200 import synth
+    from mdvit_b200.model import MDViT
+    from oracle import mdvit_oracle as O
+    out = {"batch_per_domain": B, "what": "oracle port (torch eager restatement of the reference) MKD train step + torch.optim.AdamW, dropout on"}
+    for mode in ("fp32", "bf16_autocast"):
+        try:
+            torch.manual_seed(0)
+            holder = MDViT(img_size=IMG, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")
+            sd = {k: v.detach().clone().to(device) for k, v in holder.state_dict().items()}
+            del holder
+            for k, v in sd.items():
+                if v.is_floating_point() and "running" not in k:
+                    v.requires_grad_(True)
+            for k in list(sd):
+                ck = synth.canonical_key(k)
+                if ck != k:
+                    sd[k] = sd[ck]
+            names = [k for k, v in sd.items() if v.requires_grad and synth.canonical_key(k) == k]
+            opt = torch.optim.AdamW([sd[k] for k in names], lr=1e-4, weight_decay=0.05)
+            batches = [tuple(t.to(device) for t in synth.synth_batch(99, d, B, IMG, IMG)) + (d,) for d in range(4)]
+            times = []
+            for it in range(warmup + steps):
+                s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                    _, grads = O.train_step_grads(sd, batches, drop=0.1, dpr=0.1, drop2d=0.1)
+                for k in names:
+                    sd[k].grad = grads[k]
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                del grads
+                t.record()
+                t.synchronize()
+                if it >= warmup:
+                    times.append(s.elapsed_time(t))
+            ms = sum(times) / len(times)
+            out[mode] = {"images_per_s": 4 * B / (ms * 1e-3), "ms_per_step": ms}
+        except torch.cuda.OutOfMemoryError:
+            out[mode] = {"error": "out of memory at this batch"}
+        finally:
+            sd = opt = batches = None
+            torch.cuda.empty_cache()
+    return out
 
 
 def kernel_roofline(peaks, device):
@@ -258,15 +312,15 @@ def main():
     host = []
     for d in range(4):
         img, lab = synth.synth_batch(1234 + 17 * rank, d, B, IMG, IMG)
-        host.append((img.pin_memory(), lab.pin_memory(), d))
+        host.append((img.pin_memory(), lab.to(torch.uint8).pin_memory(), d))      # binary masks travel as uint8 {0,1}
     dev_batches = [(i.to(dev), l.to(dev), d) for i, l, d in host]
-    h2d = sum(i.numel() * 4 + l.numel() * 4 for i, l, _ in host)
+    h2d = sum(i.numel() * i.element_size() + l.numel() * l.element_size() for i, l, _ in host)
 
     use_graph = not args.no_graph
     if use_graph:
         trainer.capture(dev_batches, warmup=1)
         step_resident = lambda: trainer.step_graph(None)          # noqa: E731  inputs already in the static HBM buffers
-        step_e2e = lambda: trainer.step_graph(host)               # noqa: E731  H2D of this step's inputs inside the timed region
+        step_e2e = None      # pipelined below: H2D of step i+1 (side stream, staging buffers) overlaps the replay of step i
     else:
         step_resident = lambda: trainer.step(dev_batches)         # noqa: E731
         step_e2e = lambda: trainer.step([(i.to(dev, non_blocking=True), l.to(dev, non_blocking=True), d) for i, l, d in host])  # noqa: E731
@@ -281,10 +335,20 @@ def main():
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         loss_host = None
-        for _ in range(steps):
-            losses = fn()
-            if read_back:
-                loss_host = losses.to("cpu", non_blocking=False)   # device->host read of the step's result, every step
+        if fn is None:
+            # end to end through MKDTrainer's public API: every step's inputs come from pinned host memory (one H2D per
+            # step, all inside the timed region) and its losses are read back to the host
+            trainer.prefetch(host)
+            for i in range(steps):
+                if i + 1 < steps:
+                    trainer.prefetch(host)
+                losses = trainer.step_graph()
+                loss_host = losses.to("cpu", non_blocking=False)
+        else:
+            for _ in range(steps):
+                losses = fn()
+                if read_back:
+                    loss_host = losses.to("cpu", non_blocking=False)   # device->host read of the step's result, every step
         t.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(t)], device=dev)
@@ -325,6 +389,14 @@ def main():
             cpu = {"value": 4 * args.cpu_batch_per_domain / sec, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"oracle (torch fp32 restatement of the reference) train step, {4 * args.cpu_batch_per_domain} images/step "
                              f"at {IMG}x{IMG}, 1 warm-up + 2 timed steps"}
+        eager = None
+        if world == 1 and not args.no_gpu_eager and args.model == "MDViT":
+            del trainer, model
+            torch.cuda.empty_cache()
+            eager = gpu_eager_baseline(dev, B)
+            for k in ("fp32", "bf16_autocast"):
+                if "images_per_s" in eager.get(k, {}):
+                    eager[k]["speedup_of_this_repo"] = value / eager[k]["images_per_s"]
         model_tflops = value * (34.4 if args.model == "BASE" else F_TRAIN_GFLOP_PER_IMG) / 1e3     # 3 x fwd GFLOP per image
         if args.model == "BASE":
             workload = (f"BASE(adapt_method=False) train step (BASELINE.json config 2): 4 domains x {B} images/GPU at {IMG}x{IMG}, dropout 0.1, "
@@ -345,7 +417,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps * 2),
             "launches_per_step": int(launches_per_step),
             "model_algorithmic_tflops": model_tflops,
-            "roofline": roof, "roofline_hbm_kernel": roof_hbm, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "roofline_hbm_kernel": roof_hbm, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks,
             "final_losses_seg_aux_kt_per_domain": loss_host.tolist() if loss_host is not None else None,
         }))
     if world > 1:

@@ -64,6 +64,24 @@ int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M, int N, in
 /* C[P,Q] += A[R,P]^T . B[R,Q]  (fp32 atomics; A, B bf16 row-major).  Weight gradients of the above. */
 int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc, void* stream);
 
+/* ------------------------------------------------------------------ fused MLP (two chained tcgen05 GEMMs, hidden tile on chip) */
+/* 1 if mdv_mlp_fwd / mdv_mlp_bwd support this width (C in {64, 128}, hidden a multiple of 64, <= 2048). */
+int mdv_mlp_supported(int C, int hidden);
+/* Mlp.forward + the block's residual add (mpvit.py:71-78, mdvit.py:357-359) in ONE kernel:
+ *   h = dropout1(GELU(a W1^T + b1));  out = residual + rowscale[m / rows_per_scale] * dropout2(h W2^T + b2)
+ * a [M,C] bf16 (the LayerNorm output), w1 [hidden,C] bf16, w2 [C,hidden] bf16, residual/out [M,C] fp32.
+ * hact_out / u_out ([M,hidden] bf16, both or neither may be NULL): h, and u = GELU'(.) * dropout1 mask/(1-p) — the tensors
+ * the backward pass needs; NULL for inference, where the hidden activation then never leaves the SM. */
+int mdv_mlp_fwd(const void* a_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2, const float* residual,
+                float* out, void* hact_out, void* u_out, int M, int C, int hidden, float drop_p, const void* rng, uint32_t drop_stream1,
+                uint32_t drop_stream2, const float* rowscale, int rows_per_scale, void* stream);
+/* Input gradient of the same: du = (dy W2) * u;  dx = du W1.   dy [M,C] bf16 (gradient of the fc2 output, masks applied),
+ * w2t [hidden,C] bf16 (= W2^T), u [M,hidden] bf16 from mdv_mlp_fwd, w1t [C,hidden] bf16 (= W1^T), dx [M,C] fp32.
+ * du_out ([M,hidden] bf16) and colsum1 ([hidden] += column sums of du = fc1 bias gradient) are needed only when weight
+ * gradients are; both may be NULL (then du never leaves the SM). */
+int mdv_mlp_bwd(const void* dy_bf16, const void* w2t_bf16, const void* u_bf16, const void* w1t_bf16, void* du_out, float* dx_out,
+                float* colsum1, int M, int C, int hidden, void* stream);
+
 /* Debug/tuning knob (0 = automatic): force tile N, pipeline stages, TN split count. */
 int mdv_gemm_tune(int force_bn, int force_stages, int force_split);
 

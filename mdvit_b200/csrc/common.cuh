@@ -85,6 +85,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// GELU(x) and (optionally) GELU'(x) for two elements with the fewest issue slots (the fused MLP epilogue is issue-bound):
+//   a = |x|, t = 1/(1 + p a/sqrt2), e = exp(-x^2/2), hh = 0.5 erfc(a/sqrt2) = (poly(t) t e) with 0.5 folded into poly
+//   GELU(x)  = relu(x) - a hh                     (x >= 0: x (1 - hh);  x < 0: x hh)
+//   GELU'(x) = Phi(x) + x phi(x),  Phi = x >= 0 ? 1 - hh : hh,  phi = e / sqrt(2 pi)
+// Same A&S 7.1.26 erf as gauss_cdf2 (|abs err| <= 1.5e-7).
+template <bool GRAD>
+__device__ __forceinline__ void gelu_pair(float2 x, float2* g, float2* dg) {
+    const float ax = fabsf(x.x), ay = fabsf(x.y);
+    const float2 t = make_float2(rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)),
+                                 rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ay, 1.0f)));
+    const float2 w = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170f, -0.72134752044448170f));   // -x^2/2 * log2(e)
+    const float2 e = make_float2(ex2_approx(w.x), ex2_approx(w.y));
+    float2 poly = __ffma2_rn(make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+    const float2 hh = __fmul2_rn(__fmul2_rn(poly, t), e);
+    // relu(x) - |x| hh   (the |.| and the negation are free source modifiers of the scalar FFMA)
+    g->x = fmaf(-ax, hh.x, fmaxf(x.x, 0.0f));
+    g->y = fmaf(-ay, hh.y, fmaxf(x.y, 0.0f));
+    if (GRAD) {
+        const float2 phi = make_float2(x.x >= 0.0f ? 1.0f - hh.x : hh.x, x.y >= 0.0f ? 1.0f - hh.y : hh.y);
+        *dg = __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), e, phi);
+    }
+}
 __device__ __forceinline__ float2 gauss_cdf2(float2 x, float2* e_out) {
     const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
     const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
@@ -102,8 +132,9 @@ __device__ __forceinline__ float2 gauss_cdf2(float2 x, float2* e_out) {
     return __fadd2_rn(make_float2(copysignf(g.x, x.x), copysignf(g.y, x.y)), make_float2(0.5f, 0.5f));
 }
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
-    float2 e;
-    return __fmul2_rn(x, gauss_cdf2(x, &e));
+    float2 g, dg;
+    gelu_pair<false>(x, &g, &dg);
+    return g;
 }
 __device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {
     float2 e;

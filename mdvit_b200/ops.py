@@ -394,6 +394,11 @@ def _dev_ctx(t):
     return torch.cuda.device(t.device)
 
 
+# Fused fc1 -> GELU -> fc2 kernel for the widths it supports (C in {64,128}); MDV_NO_FUSED_MLP=1 keeps the two-GEMM path (A/B).
+import os as _os
+_FUSED_MLP = not bool(int(_os.environ.get("MDV_NO_FUSED_MLP", "0")))
+
+
 # ------------------------------------------------------------------------------------------------- SerialBlock
 class BlockFn(torch.autograd.Function):
     """SerialBlock_adapt.forward (mdvit.py:346-361) incl. ConvPosEnc, FactorAtt_ConvRelPosEnc(_Sup) and Mlp."""
@@ -441,18 +446,29 @@ class BlockFn(torch.autograd.Function):
             gemm_nt(y, prep_weight(proj_w, 0, C, C), M, C, C, x2, bias=proj_b, residual=x1, drop_p=p_drop, drop_stream=sid[0],
                     rowscale=dp1, rows_per_scale=N)
             ln2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, M, C)
-            u = torch.empty((M, hidden), dtype=BF16, device=dev)
-            hact = torch.empty((M, hidden), dtype=BF16, device=dev)
-            # u receives gelu'(fc1 output) * dropout mask/(1-p): the factor the backward multiplies d(hact) by
-            gemm_nt(ln2, prep_weight(fc1_w, 0, hidden, C), M, hidden, C, hact, bias=fc1_b, act=ACT_GELU, out_preact=u, drop_p=p_drop,
-                    drop_stream=sid[1], preact_mode=1)
+            need_grad = any(ctx.needs_input_grad)
             x3 = torch.empty((B, N, C), dtype=F32, device=dev)
-            gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2, drop_p=p_drop,
-                    drop_stream=sid[2], rowscale=dp2, rows_per_scale=N)
+            fused_mlp = bool(lib.mdv_mlp_supported(C, hidden)) and _FUSED_MLP
+            if fused_mlp:
+                # fc1 -> GELU -> dropout -> fc2 -> dropout -> DropPath -> + residual in ONE kernel: the hidden activation stays
+                # on the SM (it is written out, with u, only when a backward pass will need them)
+                u = torch.empty((M, hidden), dtype=BF16, device=dev) if need_grad else None
+                hact = torch.empty((M, hidden), dtype=BF16, device=dev) if need_grad else None
+                check(lib.mdv_mlp_fwd(ptr(ln2), ptr(prep_weight(fc1_w, 0, hidden, C)), ptr(fc1_b), ptr(prep_weight(fc2_w, 0, C, hidden)),
+                                      ptr(fc2_b), ptr(x2), ptr(x3), ptr(hact), ptr(u), M, C, hidden, ctypes.c_float(p_drop),
+                                      ptr(rng_tensor(dev)) if p_drop > 0 else None, sid[1], sid[2], ptr(dp2), N, L.stream()), "mdv_mlp_fwd")
+            else:
+                u = torch.empty((M, hidden), dtype=BF16, device=dev)
+                hact = torch.empty((M, hidden), dtype=BF16, device=dev)
+                # u receives gelu'(fc1 output) * dropout mask/(1-p): the factor the backward multiplies d(hact) by
+                gemm_nt(ln2, prep_weight(fc1_w, 0, hidden, C), M, hidden, C, hact, bias=fc1_b, act=ACT_GELU, out_preact=u, drop_p=p_drop,
+                        drop_stream=sid[1], preact_mode=1)
+                gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2, drop_p=p_drop,
+                        drop_stream=sid[2], rowscale=dp2, rows_per_scale=N)
         ctx.save_for_backward(x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2, ecrpe)
         ctx.params = (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2,
                       n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
-        ctx.meta = (B, N, C, H, W, hidden, p_drop, sid)
+        ctx.meta = (B, N, C, H, W, hidden, p_drop, sid, fused_mlp)
         _fwd_mark(ctx)
         return x3
 
@@ -461,7 +477,7 @@ class BlockFn(torch.autograd.Function):
         (x, label, x1, mean1, rstd1, ln1, qkv, gate, hid, stats, y, x2, mean2, rstd2, ln2, u, hact, dp1, dp2, ecrpe) = ctx.saved_tensors
         (cpe_w, cpe_b, c3w, c3b, c5w, c5b, c7w, c7b, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2, n2w, n2b,
          fc1_w, fc1_b, fc2_w, fc2_b) = ctx.params
-        B, N, C, H, W, hidden, p_drop, sid = ctx.meta
+        B, N, C, H, W, hidden, p_drop, sid, fused_mlp = ctx.meta
         M, dev = B * N, x.device
         lib = L.lib()
         dx3 = _contig(dx3.float())
@@ -474,11 +490,19 @@ class BlockFn(torch.autograd.Function):
             # bias gradients (column sums) are by-products of the kernels that produce each output gradient
             d_fc2 = cast_bf16(dx3, M, C, rowscale=dp2, rows_per_scale=N, drop_p=p_drop, drop_stream=sid[2], colsum=G["fc2_b"])
             gemm_tn(d_fc2, hact, M, C, hidden, G["fc2_w"])
-            du = torch.empty((M, hidden), dtype=BF16, device=dev)
-            gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, mul_mode=1, colsum=G["fc1_b"])
-            gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
             dln2 = torch.empty((M, C), dtype=F32, device=dev)
-            gemm_nt(du, prep_weight(fc1_w, 1, hidden, C), M, C, hidden, dln2)
+            if fused_mlp:
+                # du = (d_fc2 W2) * u and dln2 = du W1 in one kernel; du reaches HBM only when the fc1 weight gradient needs it
+                du = torch.empty((M, hidden), dtype=BF16, device=dev) if G["fc1_w"] is not None else None
+                check(lib.mdv_mlp_bwd(ptr(d_fc2), ptr(prep_weight(fc2_w, 1, C, hidden)), ptr(u), ptr(prep_weight(fc1_w, 1, hidden, C)),
+                                      ptr(du), ptr(dln2), ptr(G["fc1_b"]), M, C, hidden, L.stream()), "mdv_mlp_bwd")
+                if du is not None:
+                    gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
+            else:
+                du = torch.empty((M, hidden), dtype=BF16, device=dev)
+                gemm_nt(d_fc2, prep_weight(fc2_w, 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, mul_mode=1, colsum=G["fc1_b"])
+                gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
+                gemm_nt(du, prep_weight(fc1_w, 1, hidden, C), M, C, hidden, dln2)
             dx2, d_proj = layernorm_bwd(dln2, x2, mean2, rstd2, n2w, dx3, M, C, G["n2w"], G["n2b"], masked=True, rowscale=dp1,
                                         rows_per_scale=N, drop_p=p_drop, drop_stream=sid[0], dbias_masked=G["proj_b"])
             # ---- attention

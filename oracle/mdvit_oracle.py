@@ -234,8 +234,11 @@ def dice_loss(score, target):
 
 
 def bce_loss(p, y):
-    """nn.BCELoss(mean) with log clamped >= -100 (multi_train_MDViT.py:76)."""
-    return -(y * torch.log(p).clamp(min=-100) + (1 - y) * torch.log(1 - p).clamp(min=-100)).mean()
+    """nn.BCELoss(mean) (multi_train_MDViT.py:76): log clamped >= -100 in the forward, and torch's own backward
+    (p - y) / max(p (1 - p), 1e-12) / n, which stays finite at exactly saturated sigmoids (the hand-written
+    -(y log p + (1-y) log(1-p)) formula back-propagates 0 * inf = nan there; at the reference's random init most sigmoids
+    ARE saturated)."""
+    return F.binary_cross_entropy(p, y)
 
 
 def seg_losses(out, aux, label):

@@ -445,7 +445,7 @@ def test_adamw_matches_torch(env):
         gt = (g * t).contiguous()
         L.check(lib.mdv_adamw(L.ptr(p), L.ptr(gt), L.ptr(m), L.ptr(v), L.ptr(hyper), n, L.stream()), "adamw")
     assert int(hyper[5].item()) == 7
-    assert (p - ref.detach()).abs().max().item() < 2e-7
+    assert (p - ref.detach()).abs().max().item() < 5e-7      # 2 ulp at |p| ~ 2
 
 
 def test_da_gate_fwd_bwd(env):

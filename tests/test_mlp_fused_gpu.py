@@ -1,0 +1,121 @@
+"""GPU (B200) parity of the fused two-GEMM MLP kernels (csrc/mlp_fused.cu; Mlp.forward mpvit.py:71-78 + the block's residual
+add mdvit.py:357-359) through the C ABI, against the same arithmetic in torch fp32 (TF32 off) on identical seeded inputs.
+Tolerance 1e-2 of the tensor abs-max: operands and the hidden activation are bf16 (2^-9 per rounding), accumulation fp32."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from mdvit_b200 import _lib as L
+    return L, L.lib(), torch.device("cuda")
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-20)).item()
+
+
+def make(dev, M, C, hidden, seed):
+    torch.manual_seed(seed)
+    a = torch.randn(M, C, device=dev).bfloat16()
+    w1 = (torch.randn(hidden, C, device=dev) / C ** 0.5).bfloat16()
+    b1 = torch.randn(hidden, device=dev) * 0.5
+    w2 = (torch.randn(C, hidden, device=dev) / hidden ** 0.5).bfloat16()
+    b2 = torch.randn(C, device=dev) * 0.5
+    res = torch.randn(M, C, device=dev)
+    return a, w1, b1, w2, b2, res
+
+
+@pytest.mark.parametrize("M,C,hidden", [(128, 64, 512), (1000, 64, 512), (40000, 64, 512), (777, 128, 1024), (33000, 128, 1024),
+                                        (300, 64, 64), (129, 128, 128)])
+def test_mlp_fwd_inference_matches_torch(env, M, C, hidden):
+    """No dropout, nothing saved: the hidden activation never leaves the SM."""
+    L, lib, dev = env
+    assert lib.mdv_mlp_supported(C, hidden) == 1 and lib.mdv_mlp_supported(320, 1280) == 0
+    a, w1, b1, w2, b2, res = make(dev, M, C, hidden, M + C)
+    out = torch.empty(M, C, device=dev)
+    L.check(lib.mdv_mlp_fwd(L.ptr(a), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(res), L.ptr(out), None, None, M, C, hidden,
+                            0.0, None, 0, 0, None, 1, L.stream()), "mlp_fwd")
+    h = F.gelu(a.float() @ w1.float().t() + b1).bfloat16().float()
+    want = res + h @ w2.float().t() + b2
+    assert rel(out, want) < TOL
+    assert rel(out - res, want - res) < TOL
+
+
+@pytest.mark.parametrize("M,C,hidden", [(1000, 64, 512), (20000, 128, 1024)])
+def test_mlp_fwd_training_outputs_and_dropout(env, M, C, hidden):
+    """Training: hact and u = GELU'(.) * mask/(1-p) are stored for the backward pass; masks are a pure function of the RNG
+    state; DropPath row scale and the fc2 dropout use the same index convention as mdv_cast_bf16 (the backward regenerates
+    them there)."""
+    L, lib, dev = env
+    a, w1, b1, w2, b2, res = make(dev, M, C, hidden, 5)
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device=dev)
+    rows_per = 250 if M % 250 == 0 else M
+    rowscale = (torch.rand(M // rows_per, device=dev) > 0.3).float() / 0.7
+    pre = a.float() @ w1.float().t() + b1
+    # ---- p = 0: exact check of hact / u
+    out, hact, u = torch.empty(M, C, device=dev), torch.empty(M, hidden, device=dev, dtype=torch.bfloat16), torch.empty(M, hidden, device=dev, dtype=torch.bfloat16)
+    L.check(lib.mdv_mlp_fwd(L.ptr(a), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(res), L.ptr(out), L.ptr(hact), L.ptr(u), M, C, hidden,
+                            0.0, None, 0, 0, L.ptr(rowscale), rows_per, L.stream()), "mlp_fwd")
+    g = F.gelu(pre)
+    xg = pre.detach().clone().requires_grad_()
+    F.gelu(xg).sum().backward()
+    assert rel(hact, g) < TOL and rel(u, xg.grad) < TOL
+    want = res + rowscale.repeat_interleave(rows_per)[:, None] * (hact.float() @ w2.float().t() + b2)
+    assert rel(out, want) < 2e-3
+    # ---- p = 0.25: masks consistent between hact and u, unbiased, reproducible; output = f(stored hact)
+    p = 0.25
+    outs = []
+    for _ in range(2):
+        out2, hact2, u2 = torch.empty_like(out), torch.empty_like(hact), torch.empty_like(u)
+        L.check(lib.mdv_mlp_fwd(L.ptr(a), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(res), L.ptr(out2), L.ptr(hact2), L.ptr(u2), M, C,
+                                hidden, p, L.ptr(rng), 11, 12, L.ptr(rowscale), rows_per, L.stream()), "mlp_fwd")
+        outs.append((out2, hact2, u2))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    out2, hact2, u2 = outs[0]
+    kept = hact2.float() != 0
+    big = g.abs() > 1e-2
+    frac = (kept & big).float().sum() / big.float().sum()
+    assert abs(frac.item() - (1 - p)) < 5e-3
+    assert rel(torch.where(kept, hact2.float(), torch.zeros_like(g)), torch.where(kept, g / (1 - p), torch.zeros_like(g))) < TOL
+    assert bool(((u2.float() != 0) <= (kept | ~big)).all())          # u is masked with the same mask
+    # fc2 dropout mask: regenerate it with mdv_cast_bf16 on a tensor of ones (same stream id, same index convention)
+    ones = torch.ones(M, C, device=dev)
+    mask2 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    L.check(lib.mdv_cast_bf16(L.ptr(ones), C, L.ptr(mask2), C, M, C, None, 1, ctypes.c_float(p), L.ptr(rng), 12, None, L.stream()), "cast")
+    y = hact2.float() @ w2.float().t() + b2
+    want2 = res + rowscale.repeat_interleave(rows_per)[:, None] * (y * mask2.float())
+    assert rel(out2 - res, want2 - res) < TOL
+
+
+@pytest.mark.parametrize("M,C,hidden", [(128, 64, 512), (5000, 64, 512), (40000, 64, 512), (3000, 128, 1024), (300, 128, 128)])
+def test_mlp_bwd_matches_torch(env, M, C, hidden):
+    L, lib, dev = env
+    torch.manual_seed(M)
+    dy = torch.randn(M, C, device=dev).bfloat16()
+    w2t = (torch.randn(hidden, C, device=dev) / C ** 0.5).bfloat16()          # = W2^T
+    w1t = (torch.randn(C, hidden, device=dev) / hidden ** 0.5).bfloat16()     # = W1^T
+    u = torch.randn(M, hidden, device=dev).bfloat16()
+    du_ref = (dy.float() @ w2t.float().t()) * u.float()
+    dx_ref = du_ref.bfloat16().float() @ w1t.float().t()
+    for with_w in (True, False):
+        du = torch.zeros(M, hidden, device=dev, dtype=torch.bfloat16) if with_w else None
+        cs = torch.ones(hidden, device=dev) if with_w else None                # accumulates (+=)
+        dx = torch.empty(M, C, device=dev)
+        L.check(lib.mdv_mlp_bwd(L.ptr(dy), L.ptr(w2t), L.ptr(u), L.ptr(w1t), L.ptr(du), L.ptr(dx), L.ptr(cs), M, C, hidden, L.stream()),
+                "mlp_bwd")
+        assert rel(dx, dx_ref) < TOL
+        if with_w:
+            assert rel(du, du_ref) < TOL
+            assert rel(cs - 1.0, du_ref.sum(0)) < TOL
