@@ -44,10 +44,12 @@ typedef struct MdvGemmEpi {
     const float* rowscale;      /* [ceil(M / rows_per_scale)] fp32 or NULL (DropPath per-sample scale) */
     const void* rng;            /* device uint64[2] {seed, step}; may be NULL when dropout_p == 0 */
     float* colsum;              /* [N] fp32 or NULL: column sums of the stored values are ADDED here (atomics) */
+    const float* colscale;      /* [N] fp32 or NULL: v = acc * colscale[n] + bias[n] instead of acc + bias[n] (eval-mode BatchNorm folded
+                                   into the producing GEMM: colscale = gamma / sqrt(running_var + eps), bias = beta - mean * colscale) */
     int ld_res, ld_mul, ld_preact, ldc;
     int rows_per_scale;
     int out_bf16;               /* 1: out is bf16, 0: fp32 */
-    int act;                    /* MDV_ACT_NONE | MDV_ACT_GELU */
+    int act;                    /* MDV_ACT_NONE | MDV_ACT_GELU | MDV_ACT_RELU | MDV_ACT_HSWISH */
     int accumulate;             /* fp32 out only: out += v */
     int preact_mode;            /* what out_preact receives: 0 = v before the activation; 1 = act'(v) * dropout_mask/(1-p), i.e. the
                                    exact factor the backward pass multiplies the incoming gradient by (saves recomputing it there) */
@@ -60,6 +62,13 @@ typedef struct MdvGemmEpi {
  * nn.Linear / 1x1 Conv2d forward (mdvit.py:288,310; mpvit.py:72-76; Decoders.py:59,197,317-333) and,
  * with W := W^T, their input gradients. */
 int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, void* stream);
+
+/* The same with fp32 operands multiplied as TF32 (tcgen05 kind::tf32: 10 mantissa bits instead of bf16's 7, fp32
+ * accumulate); pitches in elements, multiples of 4.  Used for the convolutional trunk (stem, patch embeddings, bridge,
+ * decoder 1x1 convs): every one of them rewrites the whole residual stream, so their operand rounding is what the logits
+ * see — bf16 there put the logits 1.0-1.4e-2 from the reference at its random init, TF32 puts them at ~3e-3 (DESIGN.md
+ * section 7); the transformer blocks' GEMMs, whose outputs are small additive branches, stay bf16. */
+int mdv_gemm_nt_tf32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, void* stream);
 
 /* C[P,Q] += A[R,P]^T . B[R,Q]  (fp32 atomics; A, B bf16 row-major).  Weight gradients of the above. */
 int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc, void* stream);
@@ -102,6 +111,10 @@ int mdv_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
  * *num_batches_tracked += 1.  eval: mean,rstd from the running buffers.  ws >= 2*C doubles. */
 int mdv_bn_stats(const float* z, int M, int C, float eps, float momentum, int training, float* running_mean,
                  float* running_var, long long* num_batches_tracked, float* mean, float* rstd, void* ws, void* stream);
+/* Eval-mode BatchNorm as a per-channel affine map folded into the GEMM that produces its input (MdvGemmEpi.colscale/bias):
+ * scale[c] = gamma[c] / sqrt(running_var[c] + eps);  shift[c] = beta[c] + (conv_bias[c] - running_mean[c]) * scale[c]. */
+int mdv_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, const float* conv_bias,
+                float eps, float* scale, float* shift, int C, void* stream);
 int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta, int act,
                    void* y, int y_bf16, int M, int C, void* stream);
 /* dz for y = act(BN_train(z)); ws >= 2*C doubles + 2*C floats; dgamma/dbeta accumulate. */
@@ -124,13 +137,15 @@ int mdv_dwconv3(const float* in, const float* w, const float* bias, void* out, i
 int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int Hi, int Wi, int Ho, int Wo, int C,
                       int stride, void* stream);
 /* decoder conv_after.dwconv: 3x3, groups=C over cat(skip, up) (2 inputs per group), Decoders.py:30-38,198-205 */
-int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out_bf16, int B, int H, int W, int C, void* stream);
+int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out, int out_bf16, int B, int H, int W, int C,
+                   void* stream);
 int mdv_gconv2_bwd(const float* dout, const float* skip, const float* up, const float* w, float* dskip, float* dup, float* dw,
                    int B, int H, int W, int C, void* stream);
 /* im2col for dense 3x3 convs (stem mdvit.py:509-526, bridge :557-564): col[(b,yo,xo), (i*3+j)*C + c] */
-int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc,
-                void* stream);
-int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int Hi, int Wi, void* stream);
+int mdv_im2col3(const void* in, int in_bf16, void* col, int col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride,
+                int ldc, void* stream);
+/* col: [B*Ho*Wo, 64] bf16 (col_bf16 = 1) or [B*Ho*Wo, 32] fp32 (col_bf16 = 0), 27 columns used, the rest zero */
+int mdv_im2col_stem(const float* img_nchw, void* col, int col_bf16, int B, int Hi, int Wi, void* stream);
 int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc, void* stream);
 /* bilinear resize, align_corners=False (mdvit.py:699; Decoders.py:196,319-336) and its exact transpose */
 int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* out, int out_bf16, int ld_out, int B, int Hi, int Wi, int Ho,
@@ -173,8 +188,9 @@ int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, int C, void
 int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
                   int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* colsum, void* stream);
 int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate, void* stream);
-/* fp32 master weight -> bf16 GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2 */
-int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream);
+/* fp32 master weight -> GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2; dst is bf16, or
+ * fp32 (TF32 GEMM operand) when 8 is added to the mode */
+int mdv_prep_weight(const float* src, void* dst, int R, int Cc, int ld, int mode, int cin, void* stream);
 /* The same for a whole model in one launch: `descs_dev` is a DEVICE array of n descriptors (zero-padded dst regions are
  * the caller's job, as with mdv_prep_weight). */
 typedef struct MdvPrepDesc {

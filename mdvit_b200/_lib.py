@@ -17,7 +17,7 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_HSWISH = 0, 1, 2, 3
 class GemmEpi(ctypes.Structure):
     _fields_ = [
         ("bias", c_void_p), ("residual", c_void_p), ("mul_gelu_grad", c_void_p), ("out_preact", c_void_p),
-        ("out", c_void_p), ("rowscale", c_void_p), ("rng", c_void_p), ("colsum", c_void_p),
+        ("out", c_void_p), ("rowscale", c_void_p), ("rng", c_void_p), ("colsum", c_void_p), ("colscale", c_void_p),
         ("ld_res", c_int), ("ld_mul", c_int), ("ld_preact", c_int), ("ldc", c_int),
         ("rows_per_scale", c_int), ("out_bf16", c_int), ("act", c_int), ("accumulate", c_int), ("preact_mode", c_int), ("mul_mode", c_int),
         ("dropout_p", c_float), ("drop_stream", c_uint32),

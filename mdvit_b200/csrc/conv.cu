@@ -325,8 +325,9 @@ __device__ __forceinline__ void gfma(float2& a, const float4& w, const float4& v
     a.y += w.z * v.z + w.w * v.w;
 }
 
+template <typename TO>
 __global__ void __launch_bounds__(256) gconv2_s_fwd_kernel(const float* __restrict__ skip, const float* __restrict__ up,
-                                                            const float* __restrict__ w, bf16* __restrict__ out, int H, int W, int C,
+                                                            const float* __restrict__ w, TO* __restrict__ out, int H, int W, int C,
                                                             int seg) {
     MDV_PDL_SYNC();
     const int half = C >> 1;                        // float4 groups per pixel of the concatenated input
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(256) gconv2_s_fwd_kernel(const float* __restri
     float4 wv[9];
     gload_taps(w, g, false, wv);
     const int y0 = blockIdx.y * seg, y1 = min(H, y0 + seg);
-    bf16* oimg = out + (size_t)blockIdx.z * H * L;
+    TO* oimg = out + (size_t)blockIdx.z * H * L;
     GRow3 r0 = gload_row3(src + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
     GRow3 r1 = gload_row3(src + (size_t)y0 * L, p, C, true, left_ok, right_ok);
     for (int y = y0; y < y1; ++y) {
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(256) gconv2_s_fwd_kernel(const float* __restri
         gfma(a, wv[0], r0.l); gfma(a, wv[1], r0.m); gfma(a, wv[2], r0.r);
         gfma(a, wv[3], r1.l); gfma(a, wv[4], r1.m); gfma(a, wv[5], r1.r);
         gfma(a, wv[6], r2.l); gfma(a, wv[7], r2.m); gfma(a, wv[8], r2.r);
-        *reinterpret_cast<uint32_t*>(oimg + (size_t)y * L + p + g) = f2_to_bf2(a.x, a.y);
+        if (sizeof(TO) == 2) *reinterpret_cast<uint32_t*>(oimg + (size_t)y * L + p + g) = f2_to_bf2(a.x, a.y);
+        else *reinterpret_cast<float2*>(oimg + (size_t)y * L + p + g) = a;
         r0 = r1;
         r1 = r2;
     }
@@ -455,8 +457,8 @@ __global__ void __launch_bounds__(256) gconv2_s_wgrad_kernel(const float* __rest
 
 // ---------------------------------------------------------------------------------- im2col / col2im (3x3, pad 1)
 // col[(b,yo,xo), (i*3+j)*C + c] = in[b, yo*s-1+i, xo*s-1+j, c]  (0 outside); row pitch ldc >= 9*C (extra columns zeroed).
-template <typename TI>
-__global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in, bf16* __restrict__ col, int B, int Hi, int Wi,
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in, TO* __restrict__ col, int B, int Hi, int Wi,
                                                        int Ho, int Wo, int C, int stride, int ldc) {
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
@@ -476,14 +478,16 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in,
     }
 }
 
-// first stem conv: NCHW fp32 image [B,3,H,W] -> col [B*Ho*Wo, 64] bf16, column = (i*3+j)*3 + ci for < 27, zero elsewhere.
-__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, bf16* __restrict__ col, int B, int Hi,
+// first stem conv: NCHW fp32 image [B,3,H,W] -> col [B*Ho*Wo, LD] (LD = 64 bf16, or 32 fp32 for the TF32 GEMM), column =
+// (i*3+j)*3 + ci for < 27, zero elsewhere.
+template <typename TO, int LD>
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, TO* __restrict__ col, int B, int Hi,
                                                            int Wi, int Ho, int Wo) {
     MDV_PDL_SYNC();
-    const idx_t total = (idx_t)B * Ho * Wo * 32;  // one thread = 2 columns
+    const idx_t total = (idx_t)B * Ho * Wo * (LD / 2);  // one thread = 2 columns
     for (idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (idx_t)gridDim.x * blockDim.x) {
-        const int k = (int)(idx % 32) * 2;
-        const idx_t pix = idx / 32;
+        const int k = (int)(idx % (LD / 2)) * 2;
+        const idx_t pix = idx / (LD / 2);
         const int xo = (int)(pix % Wo);
         const int yo = (int)((pix / Wo) % Ho);
         const int b = (int)(pix / ((idx_t)Wo * Ho));
@@ -497,7 +501,8 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
                 if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v[u] = __ldg(img + (((size_t)b * 3 + ci) * Hi + yi) * Wi + xi);
             }
         }
-        *reinterpret_cast<uint32_t*>(col + (size_t)pix * 64 + k) = f2_to_bf2(v[0], v[1]);
+        if (sizeof(TO) == 2) *reinterpret_cast<uint32_t*>(col + (size_t)pix * LD + k) = f2_to_bf2(v[0], v[1]);
+        else *reinterpret_cast<float2*>(col + (size_t)pix * LD + k) = make_float2(v[0], v[1]);
     }
 }
 
@@ -769,14 +774,18 @@ extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, flo
     return MDV_OK;
 }
 
-extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out_bf16, int B, int H, int W, int C,
+extern "C" int mdv_gconv2_fwd(const float* skip, const float* up, const float* w, void* out, int out_bf16, int B, int H, int W, int C,
                               void* stream) {
-    if (!skip || !up || !w || !out_bf16 || (C & 3)) return MDV_ERR_ARG;
+    if (!skip || !up || !w || !out || (C & 3)) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * H * W * C)) return MDV_ERR_UNSUPPORTED;
     {
         const int seg = H >= 64 ? 16 : (H >= 16 ? 8 : H);
-        mdv_launch(gconv2_s_fwd_kernel, dim3(mdv_cdiv(W * (C / 2), 256), mdv_cdiv(H, seg), B), dim3(256), 0, (cudaStream_t)stream, skip, up, w,
-                   (bf16*)out_bf16, H, W, C, seg);
+        if (out_bf16)
+            mdv_launch(gconv2_s_fwd_kernel<bf16>, dim3(mdv_cdiv(W * (C / 2), 256), mdv_cdiv(H, seg), B), dim3(256), 0, (cudaStream_t)stream, skip, up, w,
+                       (bf16*)out, H, W, C, seg);
+        else
+            mdv_launch(gconv2_s_fwd_kernel<float>, dim3(mdv_cdiv(W * (C / 2), 256), mdv_cdiv(H, seg), B), dim3(256), 0, (cudaStream_t)stream, skip, up, w,
+                       (float*)out, H, W, C, seg);
     }
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -805,29 +814,36 @@ extern "C" int mdv_gconv2_bwd(const float* dout, const float* skip, const float*
     return MDV_OK;
 }
 
-extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride,
+extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col, int col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride,
                            int ldc, void* stream) {
-    if (!in || !col_bf16 || (C & 3) || ldc < 9 * C || (ldc & 7)) return MDV_ERR_ARG;
+    if (!in || !col || (C & 3) || ldc < 9 * C || (ldc & 7)) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * Ho * Wo * ldc)) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (ldc > 9 * C) {
-        cudaError_t e = cudaMemsetAsync(col_bf16, 0, (size_t)B * Ho * Wo * ldc * 2, st);
+        cudaError_t e = cudaMemsetAsync(col, 0, (size_t)B * Ho * Wo * ldc * (col_bf16 ? 2 : 4), st);
         if (e != cudaSuccess) return (int)e;
     }
     const long long total = (long long)B * Ho * Wo * 9 * (C / 4);
-    if (in_bf16)
-        mdv_launch(im2col3_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, st, (const bf16*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    if (in_bf16 && col_bf16)
+        mdv_launch((im2col3_kernel<bf16, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const bf16*)in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    else if (!in_bf16 && col_bf16)
+        mdv_launch((im2col3_kernel<float, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    else if (!in_bf16 && !col_bf16)
+        mdv_launch((im2col3_kernel<float, float>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (float*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc);
     else
-        mdv_launch(im2col3_kernel<float>, dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+        return MDV_ERR_UNSUPPORTED;
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
 
-extern "C" int mdv_im2col_stem(const float* img_nchw, void* col_bf16, int B, int Hi, int Wi, void* stream) {
-    if (!img_nchw || !col_bf16 || (Hi & 1) || (Wi & 1)) return MDV_ERR_ARG;
+extern "C" int mdv_im2col_stem(const float* img_nchw, void* col, int col_bf16, int B, int Hi, int Wi, void* stream) {
+    if (!img_nchw || !col || (Hi & 1) || (Wi & 1)) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * Hi * Wi * 16)) return MDV_ERR_UNSUPPORTED;
     const int Ho = Hi / 2, Wo = Wi / 2;
-    mdv_launch(im2col_stem_kernel, dim3(grid_for((long long)B * Ho * Wo * 32)), dim3(256), 0, (cudaStream_t)stream, img_nchw, (bf16*)col_bf16, B, Hi, Wi, Ho, Wo);
+    if (col_bf16)
+        mdv_launch((im2col_stem_kernel<bf16, 64>), dim3(grid_for((long long)B * Ho * Wo * 32)), dim3(256), 0, (cudaStream_t)stream, img_nchw, (bf16*)col, B, Hi, Wi, Ho, Wo);
+    else
+        mdv_launch((im2col_stem_kernel<float, 32>), dim3(grid_for((long long)B * Ho * Wo * 16)), dim3(256), 0, (cudaStream_t)stream, img_nchw, (float*)col, B, Hi, Wi, Ho, Wo);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

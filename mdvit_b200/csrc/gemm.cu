@@ -35,6 +35,8 @@ struct GemmParams {
     int stages;
     int n_tiles, m_tiles, splits, kb_per_split;
     int has_preact;
+    int tf32;             // NT only: operands are fp32, multiplied as TF32 (kind::tf32, 32-element k-blocks); else bf16 (64)
+    int bk;               // elements per k-block: 128 bytes of K per row of a stage
     int nbuf;             // staging buffers per epilogue warp (2 or 4)
     int out_slab, buf_bytes;   // bytes of the output slab (2 KB bf16 / 4 KB fp32) and of one buffer (out [+ 2 KB preact])
     MdvGemmEpi epi;
@@ -49,7 +51,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
     c.n_tile = t % p.n_tiles;
     const int r = t / p.n_tiles;
     c.m_tile = r % p.m_tiles;
-    const int total_kb = (p.K + BK - 1) / BK;
+    const int total_kb = (p.K + p.bk - 1) / p.bk;
     if (TN) {
         c.kb0 = (r / p.m_tiles) * p.kb_per_split;
         c.num_kb = min(p.kb_per_split, total_kb - c.kb0);
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                     mbar_expect_tx(&full_bar[s], stage_bytes);
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
-                    const int kc = (tc.kb0 + kb) * BK;
+                    const int kc = (tc.kb0 + kb) * p.bk;
                     if (!TN) {
                         tma_load_2d(sa, &tmA, kc, tc.m_tile * BM, &full_bar[s]);
                         tma_load_2d(sb, &tmB, kc, tc.n_tile * BN, &full_bar[s]);
@@ -139,7 +141,9 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BM, BN, TN);
+            // TF32: same descriptor with a/b format 2 instead of 1 (cute::UMMA::F16F32Format); one MMA consumes K=8 fp32 = 32 B,
+            // exactly the +32 B per step of the bf16 path (K=16), so the k-loop is shared
+            const uint32_t idesc = p.tf32 ? (make_idesc(BM, BN, TN) + (1u << 7) + (1u << 10)) : make_idesc(BM, BN, TN);
             int it = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const TileCoord tc = tile_coord<TN>(p, t);
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                             ad = make_desc(sa + k * 2048, 8192, 1024);
                             bd = make_desc(sb + k * 2048, 8192, 1024);
                         }
-                        tc_mma_bf16(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!TN && p.tf32) tc_mma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else tc_mma_bf16(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[s]);
                 }
@@ -237,7 +242,12 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (e.bias) {
+                if (e.colscale) {
+                    // eval-mode BatchNorm folded into the GEMM: v = acc * scale[n] + shift[n] (shift arrives as `bias`)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) f[j] = fmaf(f[j], __ldg(e.colscale + col0 + j), e.bias ? __ldg(e.bias + col0 + j) : 0.f);
+                } else if (e.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         if (full_cols) {
@@ -303,6 +313,12 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         f[j] = r.x;
                         f[j + 1] = r.y;
                     }
+                } else if (e.act == MDV_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                } else if (e.act == MDV_ACT_HSWISH) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = hardswish_f(f[j]);
                 }
                 }
                 if (e.mul_gelu_grad && row_ok) {
@@ -443,7 +459,7 @@ int launch_n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc
     p.out_slab = (TN || !p.epi.out_bf16) ? 4096 : 2048;
     p.buf_bytes = p.out_slab + (p.has_preact ? 2048 : 0);
     // short-K tiles are epilogue-bound (deep store buffering); long-K tiles are MMA-bound (spend smem on operand stages)
-    const int kbt = TN ? p.kb_per_split : mdv_cdiv(p.K, BK);
+    const int kbt = TN ? p.kb_per_split : mdv_cdiv(p.K, p.bk);
     p.nbuf = kbt <= 2 ? 4 : (kbt <= 8 ? 2 : 1);
     if (NEPI > 8 && p.nbuf > 2) p.nbuf = 2;      // twice the warps: the same number of stores in flight
     const size_t cs_bytes = p.epi.colsum ? NEPI * 128 * sizeof(float) : 0;
@@ -499,23 +515,25 @@ extern "C" int mdv_gemm_tune(int force_bn, int force_stages, int force_split) {
     return MDV_OK;
 }
 
-extern "C" int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi,
-                           void* stream) {
+static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, int tf32, void* stream) {
     if (!A || !W || !epi || !epi->out || M <= 0 || N <= 0 || K <= 0) return MDV_ERR_ARG;
-    if ((N & 3) || (K & 7) || epi->accumulate) return MDV_ERR_ARG;
+    if ((N & 3) || (K & (tf32 ? 3 : 7)) || epi->accumulate) return MDV_ERR_ARG;
     GemmParams p = {};
     p.M = M; p.N = N; p.K = K;
     p.epi = *epi;
+    p.tf32 = tf32;
+    p.bk = tf32 ? 32 : 64;
     p.BN = pick_bn(N, 32);
     p.n_tiles = mdv_cdiv(N, p.BN);
     p.m_tiles = mdv_cdiv(M, BM);
     p.splits = 1;
-    p.kb_per_split = mdv_cdiv(K, BK);
+    p.kb_per_split = mdv_cdiv(K, p.bk);
     p.has_preact = epi->out_preact != nullptr;
     CUtensorMap ta, tb, tc, tp;
-    int rc = make_map(&ta, A, 2, K, M, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    const int es = tf32 ? 4 : 2;
+    int rc = make_map(&ta, A, es, K, M, lda, p.bk, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, W, 2, K, N, ldw, BK, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map(&tb, W, es, K, N, ldw, p.bk, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (epi->out_bf16) rc = make_map(&tc, epi->out, 2, N, M, epi->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     else rc = make_map(&tc, epi->out, 4, N, M, epi->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -528,12 +546,23 @@ extern "C" int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M
     return launch<false>(ta, tb, tc, tp, p, (cudaStream_t)stream);
 }
 
+extern "C" int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi,
+                           void* stream) {
+    return gemm_nt_impl(A, lda, W, ldw, M, N, K, epi, 0, stream);
+}
+
+extern "C" int mdv_gemm_nt_tf32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi,
+                                void* stream) {
+    return gemm_nt_impl(A, lda, W, ldw, M, N, K, epi, 1, stream);
+}
+
 extern "C" int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc,
                            void* stream) {
     if (!A || !B || !C || R <= 0 || P <= 0 || Q <= 0) return MDV_ERR_ARG;
     if ((P & 7) || (Q & 7) || (ldc & 3)) return MDV_ERR_ARG;
     GemmParams p = {};
     p.M = P; p.N = Q; p.K = R;
+    p.bk = BK;
     p.BN = pick_bn(Q, 64);
     p.n_tiles = mdv_cdiv(Q, p.BN);
     p.m_tiles = mdv_cdiv(P, BM);

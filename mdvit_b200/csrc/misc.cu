@@ -208,13 +208,16 @@ __global__ void __launch_bounds__(256) add_f32_kernel(const TI* __restrict__ in,
 //  mode 1: src [R, Cc] row-major                       -> dst [Cc, ld] = src^T (for input gradients)
 //  mode 2: src [R, Cin, 3, 3] (PyTorch conv)           -> dst [R, ld], column (i*3+j)*Cin + ci    (im2col order)
 //  mode 3: src [R, Cin, 3, 3]                          -> dst [9*Cin (pad to rows), ld] transposed of mode 2
-__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int Cc,
+//  mode | 8: the same layouts with an fp32 destination (operands of the TF32 GEMMs of the conv trunk)
+template <typename TO>
+__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ src, TO* __restrict__ dst, int R, int Cc,
                                                            int ld, int mode, int cin) {
     MDV_PDL_SYNC();
     const long long total = (long long)R * Cc;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(idx / Cc), c = (int)(idx % Cc);
-        const bf16 v = __float2bfloat16_rn(src[idx]);
+        TO v;
+        stf(&v, src[idx]);
         if (mode == 0) {
             dst[(size_t)r * ld + c] = v;
         } else if (mode == 1) {
@@ -234,21 +237,23 @@ __global__ void __launch_bounds__(256) prep_weights_batched_kernel(const MdvPrep
     MDV_PDL_SYNC();
     const MdvPrepDesc d = descs[blockIdx.y];
     const float* __restrict__ src = d.src;
-    bf16* __restrict__ dst = (bf16*)d.dst;
     const int total = d.rows * d.cols;
+    const int mode = d.mode & 7;
+    const bool f32 = (d.mode & 8) != 0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int r = idx / d.cols, c = idx % d.cols;
-        const bf16 v = __float2bfloat16_rn(src[idx]);
-        if (d.mode == 0) {
-            dst[(size_t)r * d.ld + c] = v;
-        } else if (d.mode == 1) {
-            dst[(size_t)c * d.ld + r] = v;
+        size_t o;
+        if (mode == 0) {
+            o = (size_t)r * d.ld + c;
+        } else if (mode == 1) {
+            o = (size_t)c * d.ld + r;
         } else {
             const int ci = c / 9, t = c % 9;
             const int col = t * d.cin + ci;
-            if (d.mode == 2) dst[(size_t)r * d.ld + col] = v;
-            else dst[(size_t)col * d.ld + r] = v;
+            o = mode == 2 ? (size_t)r * d.ld + col : (size_t)col * d.ld + r;
         }
+        if (f32) ((float*)d.dst)[o] = src[idx];
+        else ((bf16*)d.dst)[o] = __float2bfloat16_rn(src[idx]);
     }
 }
 
@@ -530,9 +535,12 @@ extern "C" int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, i
     return MDV_OK;
 }
 
-extern "C" int mdv_prep_weight(const float* src, void* dst_bf16, int R, int Cc, int ld, int mode, int cin, void* stream) {
-    if (!src || !dst_bf16 || mode < 0 || mode > 3) return MDV_ERR_ARG;
-    mdv_launch(prep_weight_kernel, dim3(grid_for((long long)R * Cc)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst_bf16, R, Cc, ld, mode, cin);
+extern "C" int mdv_prep_weight(const float* src, void* dst, int R, int Cc, int ld, int mode, int cin, void* stream) {
+    if (!src || !dst || mode < 0 || (mode & 7) > 3 || mode > 11) return MDV_ERR_ARG;
+    if (mode & 8)
+        mdv_launch(prep_weight_kernel<float>, dim3(grid_for((long long)R * Cc)), dim3(256), 0, (cudaStream_t)stream, src, (float*)dst, R, Cc, ld, mode & 7, cin);
+    else
+        mdv_launch(prep_weight_kernel<bf16>, dim3(grid_for((long long)R * Cc)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst, R, Cc, ld, mode, cin);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -21,6 +21,8 @@
 //                 K-major shared-memory tile that IS the A operand of GEMM2 (and the source box of the TMA store);
 //                 per tile, all 16 warps: tcgen05.ld Y -> bias, dropout, DropPath scale, residual -> global
 // C in {64, 128} (encoder / decoder stages 0 and 1: 85% of the model's MLP time); other widths use mdv_gemm_nt.
+#include <stdlib.h>
+
 #include "../../include/mdvit_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             dkey2 = rng_key(p.rng, p.drop_stream2);
         }
         const uint32_t lane_taddr = (uint32_t)(q * 32) << 16;
+        const uint32_t mid_addr = smem_u32(sMid), aux_addr = smem_u32(sAux), cs_addr = smem_u32(cs_sm);
         // swizzled offsets of this lane's four 16-byte chunks inside a 128 x 128B tile
         uint32_t off[4];
 #pragma unroll
@@ -347,8 +350,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned)p.hidden + (unsigned)col0) >> 1);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(cs_sm + col0 + 4 * j4);      // broadcast read
-                    const float2 bb[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
+                    const uint4 b4 = lds128(cs_addr + (uint32_t)(col0 + 4 * j4) * 4u);      // broadcast read
+                    const float2 bb[2] = {make_float2(__uint_as_float(b4.x), __uint_as_float(b4.y)),
+                                          make_float2(__uint_as_float(b4.z), __uint_as_float(b4.w))};
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int j = 2 * j4 + u;                 // pair index: columns 2j, 2j+1
@@ -368,20 +372,25 @@ __global__ void __launch_bounds__(THREADS, 1)
                     }
                 }
                 mbar_wait(&mid_empty[sb], par ^ 1);
-                uint8_t* mt = sMid + sb * TILE_BYTES;
+                const uint32_t mt = mid_addr + sb * TILE_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mt + off[j]) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) sts128(mt + off[j], make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
                 if (TRAIN) {
-                    uint8_t* at = sAux + sb * TILE_BYTES;
+                    const uint32_t at = aux_addr + sb * TILE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(at + off[j]) = make_uint4(uk[4 * j], uk[4 * j + 1], uk[4 * j + 2], uk[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) sts128(at + off[j], make_uint4(uk[4 * j], uk[4 * j + 1], uk[4 * j + 2], uk[4 * j + 3]));
                 }
             } else {
                 mbar_wait(&aux_full[sb], par);
-                const uint8_t* ua = sAux + sb * TILE_BYTES;
+                const uint32_t ua = aux_addr + sb * TILE_BYTES;
                 uint4 uq[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) uq[j] = *reinterpret_cast<const uint4*>(ua + off[j]);
+                for (int j = 0; j < 4; ++j) uq[j] = lds128(ua + off[j]);
+                // The loads must have RETURNED before the buffer is handed back to the TMA producer: an mbarrier arrive does not
+                // wait for this thread's outstanding shared-memory loads (it is executed by a different unit than the LSU
+                // queue they sit in), and nothing between here and the arrive consumes uq[].  Without this fence the next
+                // u tile landed under loads still in flight: a few lanes of a warp saw rows of the wrong tile.
+                __threadfence_block();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&aux_empty[sb]);
                 float d[32];
@@ -398,9 +407,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                     }
                 }
                 mbar_wait(&mid_empty[sb], par ^ 1);
-                uint8_t* mt = sMid + sb * TILE_BYTES;
+                const uint32_t mt = mid_addr + sb * TILE_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mt + off[j]) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) sts128(mt + off[j], make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
                 if (p.colsum1) {
                     // column sums of this warp's 32 x 32 block by a transposing butterfly: after the step with offset `o` a
                     // lane keeps half of its columns, each summed over twice as many rows; lane l ends with column l

@@ -473,6 +473,26 @@ extern "C" int mdv_bn_stats(const float* z, int M, int C, float eps, float momen
     return MDV_OK;
 }
 
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                               const float* __restrict__ rv, const float* __restrict__ cbias, float eps, float* __restrict__ scale,
+                               float* __restrict__ shift, int C) {
+    MDV_PDL_SYNC();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float s = gamma[c] * rsqrtf(rv[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] + ((cbias ? cbias[c] : 0.f) - rm[c]) * s;
+}
+
+extern "C" int mdv_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                           const float* conv_bias, float eps, float* scale, float* shift, int C, void* stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || C <= 0) return MDV_ERR_ARG;
+    mdv_launch(bn_fold_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, (cudaStream_t)stream, gamma, beta, running_mean, running_var, conv_bias, eps,
+               scale, shift, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
 extern "C" int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
                               int act, void* y, int y_bf16, int M, int C, void* stream) {
     if (!z || !y || M <= 0 || (C & 3)) return MDV_ERR_ARG;

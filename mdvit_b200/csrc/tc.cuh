@@ -8,6 +8,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Explicit shared-space accesses: pointers derived from the 1024-byte-aligned dynamic shared-memory base lose their
+// address-space provenance and compile to generic LD/ST (long-scoreboard latency class); these stay LDS/STS.
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -32,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(addr),
         "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -73,6 +97,16 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");

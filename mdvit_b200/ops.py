@@ -113,9 +113,11 @@ def set_weight_mirror(m):
 
 
 def prep_weight(w, mode, rows, cols, ld=None, cin=0):
-    """bf16 GEMM operand of fp32 parameter `w` (mode: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order)."""
+    """GEMM operand of fp32 parameter `w`: bf16, or fp32 (TF32 GEMM operand) when 8 is added to the mode
+    (mode & 7: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order)."""
     R, Cc = rows, cols
-    if mode == 0 or mode == 2:
+    m = mode & 7
+    if m == 0 or m == 2:
         out_rows, out_ld = R, (ld or Cc)
     else:
         out_rows, out_ld = Cc, (ld or R)
@@ -128,8 +130,7 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
     if hit is not None and hit[0]() is w:      # id()/data_ptr() are recycled once a model is freed: check liveness
         return hit[1]
     with torch.no_grad():
-        need_zero = mode >= 2 and out_ld != (Cc if mode == 2 else R)
-        dst = (torch.zeros if need_zero or mode >= 2 else torch.empty)((out_rows, out_ld), dtype=BF16, device=w.device)
+        dst = (torch.zeros if m >= 2 else torch.empty)((out_rows, out_ld), dtype=F32 if mode & 8 else BF16, device=w.device)
         check(L.lib().mdv_prep_weight(ptr(w), ptr(dst), R, Cc, out_ld, mode, cin, L.stream()), "mdv_prep_weight")
     if len(_wcache) > 4096:
         _wcache.clear()
@@ -142,7 +143,9 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
 # ------------------------------------------------------------------------------------------------- thin wrappers
 def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, residual=None, act=ACT_NONE, out_preact=None,
             mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False, colsum=None,
-            preact_mode=0, mul_mode=0):
+            preact_mode=0, mul_mode=0, tf32=False):
+    """out = epilogue(A . W^T).  A, W bf16 — or both fp32 with tf32=True (TF32 tensor-core math: the conv trunk, see
+    include/mdvit_b200.h mdv_gemm_nt_tf32)."""
     e = GemmEpi()
     e.bias, e.residual, e.mul_gelu_grad, e.out_preact = ptr(bias), ptr(residual), ptr(mul_gelu_grad), ptr(out_preact)
     e.out, e.rowscale, e.colsum = ptr(out), ptr(rowscale), ptr(colsum)
@@ -158,7 +161,12 @@ def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, resi
     e.preact_mode, e.mul_mode = preact_mode, mul_mode
     e.dropout_p = float(drop_p)
     e.drop_stream = drop_stream
-    check(L.lib().mdv_gemm_nt(ptr(A), lda or K, ptr(W), ldw or K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
+    if tf32:
+        if A.dtype != F32 or W.dtype != F32:
+            raise TypeError("tf32 GEMM needs fp32 operands")
+        check(L.lib().mdv_gemm_nt_tf32(ptr(A), lda or K, ptr(W), ldw or K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt_tf32")
+    else:
+        check(L.lib().mdv_gemm_nt(ptr(A), lda or K, ptr(W), ldw or K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
     return out
 
 
@@ -553,15 +561,16 @@ class StemFn(torch.autograd.Function):
         rm0, rv0, nb0, rm1, rv1, nb1 = bufs
         lib = L.lib()
         with _dev_ctx(img):
-            col0 = torch.empty((M0, 64), dtype=BF16, device=dev)
-            check(lib.mdv_im2col_stem(ptr(img), ptr(col0), B, H, W, L.stream()), "mdv_im2col_stem")
+            # TF32 operands (fp32 in memory) for both stem convs: see mdv_gemm_nt_tf32
+            col0 = torch.empty((M0, 32), dtype=F32, device=dev)
+            check(lib.mdv_im2col_stem(ptr(img), ptr(col0), 0, B, H, W, L.stream()), "mdv_im2col_stem")
             z0 = torch.empty((M0, 32), dtype=F32, device=dev)
-            gemm_nt(col0, prep_weight(w0, 2, 32, 27, ld=64, cin=3), M0, 32, 64, z0)
-            a0, mean0, rstd0 = bn_forward(z0, M0, 32, g0, b0, rm0, rv0, nb0, training, ACT_HSWISH, True)
-            col1 = torch.empty((M1, 288), dtype=BF16, device=dev)
-            check(lib.mdv_im2col3(ptr(a0), 1, ptr(col1), B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_im2col3")
+            gemm_nt(col0, prep_weight(w0, 2 | 8, 32, 27, ld=32, cin=3), M0, 32, 32, z0, tf32=True)
+            a0, mean0, rstd0 = bn_forward(z0, M0, 32, g0, b0, rm0, rv0, nb0, training, ACT_HSWISH, False)
+            col1 = torch.empty((M1, 288), dtype=F32, device=dev)
+            check(lib.mdv_im2col3(ptr(a0), 0, ptr(col1), 0, B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_im2col3")
             z1 = torch.empty((M1, 64), dtype=F32, device=dev)
-            gemm_nt(col1, prep_weight(w1, 2, 64, 288, cin=32), M1, 64, 288, z1)
+            gemm_nt(col1, prep_weight(w1, 2 | 8, 64, 288, cin=32), M1, 64, 288, z1, tf32=True)
             y, mean1, rstd1 = bn_forward(z1, M1, 64, g1, b1, rm1, rv1, nb1, training, ACT_HSWISH, False)
         ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
         ctx.params = (w0, g0, b0, w1, g1, b1)
@@ -585,8 +594,8 @@ class StemFn(torch.autograd.Function):
         with _dev_ctx(dy):
             dz1, rg1, rb1 = bn_backward(dy, z1, mean1, rstd1, g1, b1, ACT_HSWISH, M1, 64)
             gw1, rw1 = gtarget(w1)
-            if gw1 is not None:
-                gw1p = gemm_tn(dz1, col1, M1, 64, 288, torch.zeros((64, 288), dtype=F32, device=dev))
+            if gw1 is not None:     # (weight gradients run on bf16 operands: cast the saved fp32 im2col matrices)
+                gw1p = gemm_tn(dz1, cast_bf16(col1, M1, 288), M1, 64, 288, torch.zeros((64, 288), dtype=F32, device=dev))
                 check(lib.mdv_unperm_conv_grad(ptr(gw1p), 288, ptr(gw1), 64, 32, L.stream()), "mdv_unperm_conv_grad")
             dcol1 = torch.empty((M1, 288), dtype=F32, device=dev)
             gemm_nt(dz1, prep_weight(w1, 3, 64, 288, cin=32), M1, 288, 64, dcol1)
@@ -595,8 +604,8 @@ class StemFn(torch.autograd.Function):
             dz0, rg0, rb0 = bn_backward(da0, z0, mean0, rstd0, g0, b0, ACT_HSWISH, M0, 32)
             gw0, rw0 = gtarget(w0)
             if gw0 is not None:
-                gw0p = gemm_tn(dz0, col0, M0, 32, 64, torch.zeros((32, 64), dtype=F32, device=dev))
-                check(lib.mdv_unperm_conv_grad(ptr(gw0p), 64, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
+                gw0p = gemm_tn(dz0, cast_bf16(col0, M0, 32), M0, 32, 32, torch.zeros((32, 32), dtype=F32, device=dev))
+                check(lib.mdv_unperm_conv_grad(ptr(gw0p), 32, ptr(gw0), 32, 3, L.stream()), "mdv_unperm_conv_grad")
         _grads_done(ctx)
         return None, rw0, rg0, rb0, rw1, rg1, rb1, None, None
 
@@ -613,9 +622,9 @@ class PatchEmbedFn(torch.autograd.Function):
         x = _contig(x)
         rm, rv, nb = bufs
         with _dev_ctx(x):
-            t = dwconv3(x, dw_w, None, B, Hi, Wi, Ho, Wo, Cin, stride, out_bf16=True)
+            t = dwconv3(x, dw_w, None, B, Hi, Wi, Ho, Wo, Cin, stride)          # fp32: TF32 operand of the pointwise conv
             z = torch.empty((M, C), dtype=F32, device=dev)
-            gemm_nt(t, prep_weight(pw_w, 0, C, Cin), M, C, Cin, z)
+            gemm_nt(t, _contig(pw_w).view(C, Cin), M, C, Cin, z, tf32=True)
             y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
         ctx.save_for_backward(x, t, z, mean, rstd)
         ctx.params = (dw_w, pw_w, g, b)
@@ -639,7 +648,8 @@ class PatchEmbedFn(torch.autograd.Function):
         with _dev_ctx(dy):
             dz, rg, rb = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
             g_pw, r_pw = gtarget(pw_w, (C, Cin))
-            gemm_tn(dz, t, M, C, Cin, g_pw)
+            if g_pw is not None:
+                gemm_tn(dz, cast_bf16(t, M, Cin), M, C, Cin, g_pw)
             dt = torch.empty((M, Cin), dtype=F32, device=dev)
             gemm_nt(dz, prep_weight(pw_w, 1, C, Cin), M, Cin, C, dt)
             dx = dwconv3(dt, dw_w, None, B, Ho, Wo, Hi, Wi, Cin, stride, transposed=True)
@@ -661,15 +671,15 @@ class BridgeFn(torch.autograd.Function):
         rm0, rv0, nb0, rm1, rv1, nb1 = bufs
         lib = L.lib()
         with _dev_ctx(x):
-            col0 = torch.empty((M, 9 * C), dtype=BF16, device=dev)
-            check(lib.mdv_im2col3(ptr(x), 0, ptr(col0), B, H, W, H, W, C, 1, 9 * C, L.stream()), "mdv_im2col3")
+            col0 = torch.empty((M, 9 * C), dtype=F32, device=dev)
+            check(lib.mdv_im2col3(ptr(x), 0, ptr(col0), 0, B, H, W, H, W, C, 1, 9 * C, L.stream()), "mdv_im2col3")
             z0 = torch.empty((M, C0), dtype=F32, device=dev)
-            gemm_nt(col0, prep_weight(w0, 2, C0, 9 * C, cin=C), M, C0, 9 * C, z0, bias=c0)
-            a0, mean0, rstd0 = bn_forward(z0, M, C0, g0, b0, rm0, rv0, nb0, training, ACT_RELU, True)
-            col1 = torch.empty((M, 9 * C0), dtype=BF16, device=dev)
-            check(lib.mdv_im2col3(ptr(a0), 1, ptr(col1), B, H, W, H, W, C0, 1, 9 * C0, L.stream()), "mdv_im2col3")
+            gemm_nt(col0, prep_weight(w0, 2 | 8, C0, 9 * C, cin=C), M, C0, 9 * C, z0, bias=c0, tf32=True)
+            a0, mean0, rstd0 = bn_forward(z0, M, C0, g0, b0, rm0, rv0, nb0, training, ACT_RELU, False)
+            col1 = torch.empty((M, 9 * C0), dtype=F32, device=dev)
+            check(lib.mdv_im2col3(ptr(a0), 0, ptr(col1), 0, B, H, W, H, W, C0, 1, 9 * C0, L.stream()), "mdv_im2col3")
             z1 = torch.empty((M, C1), dtype=F32, device=dev)
-            gemm_nt(col1, prep_weight(w1, 2, C1, 9 * C0, cin=C0), M, C1, 9 * C0, z1, bias=c1)
+            gemm_nt(col1, prep_weight(w1, 2 | 8, C1, 9 * C0, cin=C0), M, C1, 9 * C0, z1, bias=c1, tf32=True)
             y, mean1, rstd1 = bn_forward(z1, M, C1, g1, b1, rm1, rv1, nb1, training, ACT_RELU, False)
         ctx.save_for_backward(col0, z0, mean0, rstd0, col1, z1, mean1, rstd1)
         ctx.params = (w0, c0, g0, b0, w1, c1, g1, b1)
@@ -691,7 +701,7 @@ class BridgeFn(torch.autograd.Function):
         def conv_bwd(dz, col, w, cb, Cout, Cin):
             gw, rw = gtarget(w)
             if gw is not None:
-                gwp = gemm_tn(dz, col, M, Cout, 9 * Cin, torch.zeros((Cout, 9 * Cin), dtype=F32, device=dev))
+                gwp = gemm_tn(dz, cast_bf16(col, M, 9 * Cin), M, Cout, 9 * Cin, torch.zeros((Cout, 9 * Cin), dtype=F32, device=dev))
                 check(lib.mdv_unperm_conv_grad(ptr(gwp), 9 * Cin, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
             gb, rb = gtarget(cb)
             colsum(dz, M, Cout, gb)
@@ -723,16 +733,16 @@ class DecoderConvFn(torch.autograd.Function):
         rm, rv, nb = bufs
         lib = L.lib()
         with _dev_ctx(inp):
-            a = cast_bf16(inp, m, Cin)
+            # both 1x1 convs of the decoder trunk run on TF32 operands (fp32 in memory): see mdv_gemm_nt_tf32
             t = torch.empty((m, C), dtype=F32, device=dev)
-            gemm_nt(a, prep_weight(cb_w, 0, C, Cin), m, C, Cin, t, bias=cb_b)
+            gemm_nt(inp.view(m, Cin), _contig(cb_w).view(C, Cin), m, C, Cin, t, bias=cb_b, tf32=True)
             up = upsample_fwd(t, torch.empty((M, C), dtype=F32, device=dev), B, h, w, H, W, C)
-            gc = torch.empty((M, C), dtype=BF16, device=dev)
-            check(lib.mdv_gconv2_fwd(ptr(skip), ptr(up), ptr(dw_w), ptr(gc), B, H, W, C, L.stream()), "mdv_gconv2_fwd")
+            gc = torch.empty((M, C), dtype=F32, device=dev)
+            check(lib.mdv_gconv2_fwd(ptr(skip), ptr(up), ptr(dw_w), ptr(gc), 0, B, H, W, C, L.stream()), "mdv_gconv2_fwd")
             z = torch.empty((M, C), dtype=F32, device=dev)
-            gemm_nt(gc, prep_weight(pw_w, 0, C, C), M, C, C, z)
+            gemm_nt(gc, _contig(pw_w).view(C, C), M, C, C, z, tf32=True)
             y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
-        ctx.save_for_backward(skip, a, up, gc, z, mean, rstd)
+        ctx.save_for_backward(skip, inp, up, gc, z, mean, rstd)
         ctx.params = (cb_w, cb_b, dw_w, pw_w, g, b)
         ctx.meta = (B, h, w, H, W, Cin, C, training)
         _fwd_mark(ctx)
@@ -740,7 +750,7 @@ class DecoderConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        skip, a, up, gc, z, mean, rstd = ctx.saved_tensors
+        skip, inp, up, gc, z, mean, rstd = ctx.saved_tensors
         cb_w, cb_b, dw_w, pw_w, g, b = ctx.params
         B, h, w, H, W, Cin, C, training = ctx.meta
         if not training:
@@ -751,7 +761,8 @@ class DecoderConvFn(torch.autograd.Function):
         with _dev_ctx(dy):
             dz, rg, rb = bn_backward(dy, z, mean, rstd, g, b, ACT_HSWISH, M, C)
             g_pw, r_pw = gtarget(pw_w, (C, C))
-            gemm_tn(dz, gc, M, C, C, g_pw)
+            if g_pw is not None:
+                gemm_tn(dz, cast_bf16(gc, M, C), M, C, C, g_pw)
             dgc = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(dz, prep_weight(pw_w, 1, C, C), M, C, C, dgc)
             dskip = torch.empty((M, C), dtype=F32, device=dev)
@@ -762,7 +773,8 @@ class DecoderConvFn(torch.autograd.Function):
             dt = upsample_bwd(dup, B, h, w, H, W, C)
             dtb = cast_bf16(dt, m, C)
             g_cb, r_cb = gtarget(cb_w, (C, Cin))
-            gemm_tn(dtb, a, m, C, Cin, g_cb)
+            if g_cb is not None:
+                gemm_tn(dtb, cast_bf16(inp, m, Cin), m, C, Cin, g_cb)
             g_cbb, r_cbb = gtarget(cb_b)
             colsum(dt, m, C, g_cbb)
             dinp = torch.empty((m, Cin), dtype=F32, device=dev)

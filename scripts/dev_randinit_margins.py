@@ -22,7 +22,9 @@ fp = fingerprint([(n, named[n]) for n in names]); ref = rg["traj_param_fp"]
 en = np.abs(fp[:, 0] - ref[:, 0]) / np.maximum(ref[:, 0], 1e-6)
 ep = np.abs(fp[:, 1] - ref[:, 1]) / np.maximum(ref[:, 0] * np.sqrt([named[n].numel() for n in names]), 1e-6)
 print("   param fp: norm err max", en.max(), names[int(en.argmax())], "probe err max", ep.max(), names[int(ep.argmax())])
-for e, n in sorted(zip(np.maximum(en, ep), names))[-14:]:
+live = [not T.zero_grad_param(n) for n in names]
+print("   zero-gradient biases excluded:", len(names) - sum(live), "max |p| there", max(float(named[n].abs().max()) for n, l in zip(names, live) if not l))
+for e, n in sorted((e, n) for e, n, l in zip(np.maximum(en, ep), names, live) if l)[-10:]:
     print(f"      {e:.3e} {n}")
 for B in (int(os.environ.get("MARGIN_B", 32)),):
     losses, ref_l, rep = T.graph_step_vs_oracle(dev, B=B)

@@ -29,5 +29,15 @@ def test_version_and_arg_checks(built_lib):
 
 
 def test_epilogue_struct_layout_matches_header():
-    # 8 pointers + 12 ints/floats/uint32
-    assert ctypes.sizeof(_lib.GemmEpi) == 8 * 8 + 12 * 4
+    # 9 pointers + 12 ints/floats/uint32; and the field ORDER of the ctypes mirror is the header's
+    assert ctypes.sizeof(_lib.GemmEpi) == 9 * 8 + 12 * 4
+    import re
+    text = open(_lib.HEADER_PATH).read()
+    body = text[text.index("typedef struct MdvGemmEpi {"):text.index("} MdvGemmEpi;")]
+    body = re.sub(r"/\*.*?\*/", " ", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip().lstrip("*") for n in decl.rsplit(" ", 1)[0:0]] or [d.strip().split()[-1].lstrip("*") for d in decl.split(",")]
+    assert names == [f[0] for f in _lib.GemmEpi._fields_], (names, [f[0] for f in _lib.GemmEpi._fields_])

@@ -50,6 +50,38 @@ def test_gemm_nt_shapes(env, M, N, K):
         assert rel(out, want) < (BF16_TOL if out_dtype == torch.bfloat16 else 1e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 64, 32), (300, 320, 128), (5000, 32, 32), (3000, 64, 288), (8192, 512, 4608),
+                                   (16384, 128, 64), (777, 1024, 4608), (130, 64, 36)])
+def test_gemm_nt_tf32_shapes(env, M, N, K):
+    """fp32 operands multiplied as TF32 (tcgen05 kind::tf32), fp32 accumulate: the conv-trunk GEMMs.  TF32 keeps 10 mantissa
+    bits (2^-11 per operand rounding): 5e-4 of the output abs-max, 4x tighter than the bf16 path's 2e-3."""
+    L, lib, dev = env
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    bias = torch.randn(N, device=dev)
+    ref = A.double() @ W.double().t() + bias.double()
+    for out_dtype in (torch.float32, torch.bfloat16):
+        out = torch.empty(M, N, device=dev, dtype=out_dtype)
+        e = L.GemmEpi()
+        e.bias, e.out, e.ldc, e.out_bf16 = L.ptr(bias), L.ptr(out), N, int(out_dtype == torch.bfloat16)
+        L.check(lib.mdv_gemm_nt_tf32(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "gemm_nt_tf32")
+        assert rel(out, ref.float()) < (BF16_TOL if out_dtype == torch.bfloat16 else 1e-3)
+    # the same product on bf16 operands is ~4x further from the fp64 result
+    out16 = torch.empty(M, N, device=dev)
+    e = L.GemmEpi()
+    e.bias, e.out, e.ldc, e.out_bf16 = L.ptr(bias), L.ptr(out16), N, 0
+    if K % 8 == 0:
+        Ab, Wb = A.bfloat16(), W.bfloat16()
+        L.check(lib.mdv_gemm_nt(L.ptr(Ab), K, L.ptr(Wb), K, M, N, K, ctypes.byref(e), L.stream()), "gemm_nt")
+        e32 = ((out.float() if out.dtype != torch.float32 else out) - ref.float()).norm()
+        out32 = torch.empty(M, N, device=dev)
+        e2 = L.GemmEpi()
+        e2.bias, e2.out, e2.ldc, e2.out_bf16 = L.ptr(bias), L.ptr(out32), N, 0
+        L.check(lib.mdv_gemm_nt_tf32(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e2), L.stream()), "gemm_nt_tf32")
+        assert (out32 - ref.float()).norm() < 0.5 * (out16 - ref.float()).norm()
+
+
 def test_gemm_nt_gelu_preact_mulgrad_rowscale_ldc(env):
     L, lib, dev = env
     torch.manual_seed(1)
@@ -276,8 +308,11 @@ def test_gconv2_matches_grouped_conv_over_concat(env, B, H, W, C):
     cat = torch.cat((skip, up), dim=3).permute(0, 3, 1, 2)
     ref = F.conv2d(cat, w, None, padding=1, groups=C).permute(0, 2, 3, 1)          # Decoders.py:30-38
     out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
-    L.check(lib.mdv_gconv2_fwd(L.ptr(skip), L.ptr(up), L.ptr(w), L.ptr(out), B, H, W, C, L.stream()), "gconv2")
+    L.check(lib.mdv_gconv2_fwd(L.ptr(skip), L.ptr(up), L.ptr(w), L.ptr(out), 1, B, H, W, C, L.stream()), "gconv2")
     assert rel(out, ref) < BF16_TOL
+    out32 = torch.empty(B, H, W, C, device=dev)                                   # fp32 output: the TF32 pointwise conv's operand
+    L.check(lib.mdv_gconv2_fwd(L.ptr(skip), L.ptr(up), L.ptr(w), L.ptr(out32), 0, B, H, W, C, L.stream()), "gconv2")
+    assert rel(out32, ref) < F32_TOL
     dy = torch.randn(B, H, W, C, device=dev)
     (ref * dy).sum().backward()
     ds, du, dw = torch.empty_like(skip), torch.empty_like(up), torch.zeros_like(w)
@@ -295,10 +330,21 @@ def test_im2col_col2im_are_transposes_of_conv3x3(env, stride, C):
     w = (torch.randn(Cout, C, 3, 3, device=dev) / (9 * C) ** 0.5).bfloat16().float()
     ref = F.conv2d(x.permute(0, 3, 1, 2), w, None, stride=stride, padding=1).permute(0, 2, 3, 1)
     col = torch.empty(B * Ho * Wo, 9 * C, device=dev, dtype=torch.bfloat16)
-    L.check(lib.mdv_im2col3(L.ptr(x), 0, L.ptr(col), B, H, W, Ho, Wo, C, stride, 9 * C, L.stream()), "im2col")
+    L.check(lib.mdv_im2col3(L.ptr(x), 0, L.ptr(col), 1, B, H, W, Ho, Wo, C, stride, 9 * C, L.stream()), "im2col")
     wp = torch.zeros(Cout, 9 * C, device=dev, dtype=torch.bfloat16)
     L.check(lib.mdv_prep_weight(L.ptr(w), L.ptr(wp), Cout, 9 * C, 9 * C, 2, C, L.stream()), "prep")
     assert rel(col.float() @ wp.float().t(), ref.reshape(-1, Cout)) < 1e-4
+    # fp32 variants (operands of the TF32 GEMM): identical values, fp32 storage; and the GEMM itself against F.conv2d
+    col32 = torch.empty(B * Ho * Wo, 9 * C, device=dev)
+    L.check(lib.mdv_im2col3(L.ptr(x), 0, L.ptr(col32), 0, B, H, W, Ho, Wo, C, stride, 9 * C, L.stream()), "im2col")
+    wp32 = torch.zeros(Cout, 9 * C, device=dev)
+    L.check(lib.mdv_prep_weight(L.ptr(w), L.ptr(wp32), Cout, 9 * C, 9 * C, 2 | 8, C, L.stream()), "prep")
+    assert torch.equal(col32, col.float()) and torch.equal(wp32, wp.float())
+    out = torch.empty(B * Ho * Wo, Cout, device=dev)
+    e = L.GemmEpi()
+    e.out, e.ldc, e.out_bf16 = L.ptr(out), Cout, 0
+    L.check(lib.mdv_gemm_nt_tf32(L.ptr(col32), 9 * C, L.ptr(wp32), 9 * C, B * Ho * Wo, Cout, 9 * C, ctypes.byref(e), L.stream()), "gemm_tf32")
+    assert rel(out, ref.reshape(-1, Cout)) < 1e-4
     dcol = torch.randn(B * Ho * Wo, 9 * C, device=dev)
     colr = F.unfold(x.permute(0, 3, 1, 2), 3, padding=1, stride=stride)            # [B, C*9, L] with (c, tap) ordering
     colr = colr.reshape(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)
