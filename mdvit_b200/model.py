@@ -355,6 +355,10 @@ class MDViT(_Trunk):
         self.debranch2 = MLPDecoderFM(embed_dims, 1, 512)
         self.debranch3 = MLPDecoderFM(embed_dims, 1, 512)
         self.debranch4 = MLPDecoderFM(embed_dims, 1, 512)
+        # Inference-only switch (not a constructor argument: the signature stays the reference's).  The reference's test loop
+        # passes `d`, computes the auxiliary decoder (45% of the forward FLOPs) and then uses only output[0]
+        # (multi_train_MDViT.py:377-378).  With this flag set, an eval-mode forward returns [out, None] even when `d` is given.
+        self.skip_aux_in_eval = False
         self.apply(self._init_weights)
 
     def forward(self, x, domain_label=None, d=None, out_feat=False, out_seg=True):
@@ -365,7 +369,7 @@ class MDViT(_Trunk):
         dec4, h, w = self._decode(enc, domain_label)
         out = self._head(dec4, h, w, img_size)
         aux_out = None
-        if d in ('0', '1', '2', '3'):
+        if d in ('0', '1', '2', '3') and (self.training or not self.skip_aux_in_eval):
             branch = getattr(self, f'debranch{int(d) + 1}')
             feats = [e[0] for e in enc] + [dec4]
             aux_out = branch(feats, [(e[1], e[2]) for e in enc], img_size)

@@ -143,12 +143,12 @@ def prep_weight(w, mode, rows, cols, ld=None, cin=0):
 # ------------------------------------------------------------------------------------------------- thin wrappers
 def gemm_nt(A, W, M, N, K, out, *, lda=None, ldw=None, ldc=None, bias=None, residual=None, act=ACT_NONE, out_preact=None,
             mul_gelu_grad=None, drop_p=0.0, drop_stream=0, rowscale=None, rows_per_scale=1, accumulate=False, colsum=None,
-            preact_mode=0, mul_mode=0, tf32=False):
+            preact_mode=0, mul_mode=0, tf32=False, colscale=None):
     """out = epilogue(A . W^T).  A, W bf16 — or both fp32 with tf32=True (TF32 tensor-core math: the conv trunk, see
     include/mdvit_b200.h mdv_gemm_nt_tf32)."""
     e = GemmEpi()
     e.bias, e.residual, e.mul_gelu_grad, e.out_preact = ptr(bias), ptr(residual), ptr(mul_gelu_grad), ptr(out_preact)
-    e.out, e.rowscale, e.colsum = ptr(out), ptr(rowscale), ptr(colsum)
+    e.out, e.rowscale, e.colsum, e.colscale = ptr(out), ptr(rowscale), ptr(colsum), ptr(colscale)
     e.rng = ptr(rng_tensor(out.device)) if drop_p > 0 else None
     e.ld_res = N if residual is not None else 0
     e.ld_mul = N if mul_gelu_grad is not None else 0
@@ -252,6 +252,16 @@ class bn_groups:
     def __exit__(self, *exc):
         global _BN_GROUPS
         _BN_GROUPS = self.prev
+
+
+def bn_fold(weight, bias, running_mean, running_var, conv_bias=None, eps=1e-5):
+    """Eval-mode BatchNorm as (scale, shift) for the epilogue of the GEMM that feeds it (gemm_nt(colscale=scale, bias=shift,
+    act=...)): the normalised tensor is produced by the GEMM itself, its fp32 pre-activation never reaches HBM."""
+    C = weight.numel()
+    st = torch.empty((2, C), dtype=F32, device=weight.device)
+    check(L.lib().mdv_bn_fold(ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var), ptr(conv_bias), ctypes.c_float(eps), ptr(st[0]),
+                              ptr(st[1]), C, L.stream()), "mdv_bn_fold")
+    return st[0], st[1]
 
 
 def bn_forward(z, M, C, weight, bias, running_mean, running_var, nbt, training, act, out_bf16, eps=1e-5, momentum=0.1):
@@ -564,10 +574,21 @@ class StemFn(torch.autograd.Function):
             # TF32 operands (fp32 in memory) for both stem convs: see mdv_gemm_nt_tf32
             col0 = torch.empty((M0, 32), dtype=F32, device=dev)
             check(lib.mdv_im2col_stem(ptr(img), ptr(col0), 0, B, H, W, L.stream()), "mdv_im2col_stem")
+            col1 = torch.empty((M1, 288), dtype=F32, device=dev)
+            if not training:
+                # eval: BatchNorm (running statistics) + Hardswish folded into the GEMM epilogues
+                a0, y = torch.empty((M0, 32), dtype=F32, device=dev), torch.empty((M1, 64), dtype=F32, device=dev)
+                s0, t0 = bn_fold(g0, b0, rm0, rv0)
+                gemm_nt(col0, prep_weight(w0, 2 | 8, 32, 27, ld=32, cin=3), M0, 32, 32, a0, tf32=True, colscale=s0, bias=t0, act=ACT_HSWISH)
+                check(lib.mdv_im2col3(ptr(a0), 0, ptr(col1), 0, B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_im2col3")
+                s1, t1 = bn_fold(g1, b1, rm1, rv1)
+                gemm_nt(col1, prep_weight(w1, 2 | 8, 64, 288, cin=32), M1, 64, 288, y, tf32=True, colscale=s1, bias=t1, act=ACT_HSWISH)
+                ctx.meta = (B, H1, W1, H2, W2, training)
+                ctx.set_materialize_grads(False)
+                return y.view(B, H2 * W2, 64)
             z0 = torch.empty((M0, 32), dtype=F32, device=dev)
             gemm_nt(col0, prep_weight(w0, 2 | 8, 32, 27, ld=32, cin=3), M0, 32, 32, z0, tf32=True)
             a0, mean0, rstd0 = bn_forward(z0, M0, 32, g0, b0, rm0, rv0, nb0, training, ACT_HSWISH, False)
-            col1 = torch.empty((M1, 288), dtype=F32, device=dev)
             check(lib.mdv_im2col3(ptr(a0), 0, ptr(col1), 0, B, H1, W1, H2, W2, 32, 2, 288, L.stream()), "mdv_im2col3")
             z1 = torch.empty((M1, 64), dtype=F32, device=dev)
             gemm_nt(col1, prep_weight(w1, 2 | 8, 64, 288, cin=32), M1, 64, 288, z1, tf32=True)
@@ -583,11 +604,11 @@ class StemFn(torch.autograd.Function):
     def backward(ctx, dy):
         if dy is None:       # the da_only pass stops at the first patch embedding
             return (None,) * 9
-        col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
-        w0, g0, b0, w1, g1, b1 = ctx.params
         B, H1, W1, H2, W2, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        w0, g0, b0, w1, g1, b1 = ctx.params
         M0, M1, dev = B * H1 * W1, B * H2 * W2, dy.device
         lib = L.lib()
         dy = _contig(dy.float())
@@ -623,6 +644,12 @@ class PatchEmbedFn(torch.autograd.Function):
         rm, rv, nb = bufs
         with _dev_ctx(x):
             t = dwconv3(x, dw_w, None, B, Hi, Wi, Ho, Wo, Cin, stride)          # fp32: TF32 operand of the pointwise conv
+            if not training:      # eval: BatchNorm + Hardswish folded into the GEMM epilogue
+                y = torch.empty((M, C), dtype=F32, device=dev)
+                sc, sh = bn_fold(g, b, rm, rv)
+                gemm_nt(t, _contig(pw_w).view(C, Cin), M, C, Cin, y, tf32=True, colscale=sc, bias=sh, act=ACT_HSWISH)
+                ctx.meta = (B, Hi, Wi, Ho, Wo, Cin, C, stride, training)
+                return y.view(B, Ho * Wo, C)
             z = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(t, _contig(pw_w).view(C, Cin), M, C, Cin, z, tf32=True)
             y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
@@ -635,11 +662,11 @@ class PatchEmbedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, t, z, mean, rstd = ctx.saved_tensors
-        dw_w, pw_w, g, b = ctx.params
         B, Hi, Wi, Ho, Wo, Cin, C, stride, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        x, t, z, mean, rstd = ctx.saved_tensors
+        dw_w, pw_w, g, b = ctx.params
         if ctx.after_stem and not wgrad_on():
             # nothing upstream of the first patch embedding owns a domain adapter: the da_only pass stops here
             return (None,) * 11
@@ -673,10 +700,19 @@ class BridgeFn(torch.autograd.Function):
         with _dev_ctx(x):
             col0 = torch.empty((M, 9 * C), dtype=F32, device=dev)
             check(lib.mdv_im2col3(ptr(x), 0, ptr(col0), 0, B, H, W, H, W, C, 1, 9 * C, L.stream()), "mdv_im2col3")
+            col1 = torch.empty((M, 9 * C0), dtype=F32, device=dev)
+            if not training:      # eval: conv bias + BatchNorm + ReLU folded into the GEMM epilogues
+                a0, y = torch.empty((M, C0), dtype=F32, device=dev), torch.empty((M, C1), dtype=F32, device=dev)
+                s0, t0 = bn_fold(g0, b0, rm0, rv0, c0)
+                gemm_nt(col0, prep_weight(w0, 2 | 8, C0, 9 * C, cin=C), M, C0, 9 * C, a0, tf32=True, colscale=s0, bias=t0, act=ACT_RELU)
+                check(lib.mdv_im2col3(ptr(a0), 0, ptr(col1), 0, B, H, W, H, W, C0, 1, 9 * C0, L.stream()), "mdv_im2col3")
+                s1, t1 = bn_fold(g1, b1, rm1, rv1, c1)
+                gemm_nt(col1, prep_weight(w1, 2 | 8, C1, 9 * C0, cin=C0), M, C1, 9 * C0, y, tf32=True, colscale=s1, bias=t1, act=ACT_RELU)
+                ctx.meta = (B, H, W, C, C0, C1, training)
+                return y.view(B, H * W, C1)
             z0 = torch.empty((M, C0), dtype=F32, device=dev)
             gemm_nt(col0, prep_weight(w0, 2 | 8, C0, 9 * C, cin=C), M, C0, 9 * C, z0, bias=c0, tf32=True)
             a0, mean0, rstd0 = bn_forward(z0, M, C0, g0, b0, rm0, rv0, nb0, training, ACT_RELU, False)
-            col1 = torch.empty((M, 9 * C0), dtype=F32, device=dev)
             check(lib.mdv_im2col3(ptr(a0), 0, ptr(col1), 0, B, H, W, H, W, C0, 1, 9 * C0, L.stream()), "mdv_im2col3")
             z1 = torch.empty((M, C1), dtype=F32, device=dev)
             gemm_nt(col1, prep_weight(w1, 2 | 8, C1, 9 * C0, cin=C0), M, C1, 9 * C0, z1, bias=c1, tf32=True)
@@ -689,11 +725,11 @@ class BridgeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
-        w0, c0, g0, b0, w1, c1, g1, b1 = ctx.params
         B, H, W, C, C0, C1, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        col0, z0, mean0, rstd0, col1, z1, mean1, rstd1 = ctx.saved_tensors
+        w0, c0, g0, b0, w1, c1, g1, b1 = ctx.params
         M, dev = B * H * W, dy.device
         lib = L.lib()
         dy = _contig(dy.float())
@@ -739,6 +775,12 @@ class DecoderConvFn(torch.autograd.Function):
             up = upsample_fwd(t, torch.empty((M, C), dtype=F32, device=dev), B, h, w, H, W, C)
             gc = torch.empty((M, C), dtype=F32, device=dev)
             check(lib.mdv_gconv2_fwd(ptr(skip), ptr(up), ptr(dw_w), ptr(gc), 0, B, H, W, C, L.stream()), "mdv_gconv2_fwd")
+            if not training:      # eval: BatchNorm + Hardswish folded into the GEMM epilogue
+                y = torch.empty((M, C), dtype=F32, device=dev)
+                sc, sh = bn_fold(g, b, rm, rv)
+                gemm_nt(gc, _contig(pw_w).view(C, C), M, C, C, y, tf32=True, colscale=sc, bias=sh, act=ACT_HSWISH)
+                ctx.meta = (B, h, w, H, W, Cin, C, training)
+                return y.view(B, H * W, C)
             z = torch.empty((M, C), dtype=F32, device=dev)
             gemm_nt(gc, _contig(pw_w).view(C, C), M, C, C, z, tf32=True)
             y, mean, rstd = bn_forward(z, M, C, g, b, rm, rv, nb, training, ACT_HSWISH, False)
@@ -750,11 +792,11 @@ class DecoderConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        skip, inp, up, gc, z, mean, rstd = ctx.saved_tensors
-        cb_w, cb_b, dw_w, pw_w, g, b = ctx.params
         B, h, w, H, W, Cin, C, training = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        skip, inp, up, gc, z, mean, rstd = ctx.saved_tensors
+        cb_w, cb_b, dw_w, pw_w, g, b = ctx.params
         m, M, dev = B * h * w, B * H * W, dy.device
         lib = L.lib()
         dy = _contig(dy.float())
@@ -856,9 +898,15 @@ class AuxFn(torch.autograd.Function):
                     gemm_nt(a, wb, Mi, hc, Ci, t, bias=lb[i])
                     upsample_fwd(t, cat[:, i * hc:], B, Hi, Wi, H, W, hc, ld_out=K)
             cast_bf16(x5, M0, C5, out=cat[:, 4 * hc:], ld_out=K)
-            z = torch.empty((M0, hc), dtype=F32, device=dev)
-            gemm_nt(cat, prep_weight(fw, 0, hc, K), M0, hc, K, z, bias=fb)
-            a5, mean, rstd = bn_forward(z, M0, hc, g, b, rm, rv, nb, training, ACT_RELU, True)
+            if not training:      # eval: conv bias + BatchNorm + ReLU folded into the linear_fuse GEMM epilogue
+                a5 = torch.empty((M0, hc), dtype=BF16, device=dev)
+                sc, sh = bn_fold(g, b, rm, rv, fb)
+                gemm_nt(cat, prep_weight(fw, 0, hc, K), M0, hc, K, a5, colscale=sc, bias=sh, act=ACT_RELU)
+                z = mean = rstd = None
+            else:
+                z = torch.empty((M0, hc), dtype=F32, device=dev)
+                gemm_nt(cat, prep_weight(fw, 0, hc, K), M0, hc, K, z, bias=fb)
+                a5, mean, rstd = bn_forward(z, M0, hc, g, b, rm, rv, nb, training, ACT_RELU, True)
             p2 = drop2d if training else 0.0
             sid = new_stream_id() if p2 > 0 else 0
             lo = torch.empty(M0, dtype=F32, device=dev)
@@ -873,11 +921,11 @@ class AuxFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        cat, z, mean, rstd, a5, *acts = ctx.saved_tensors
-        l1w, l1b, l2w, l2b, l3w, l3b, l4w, l4b, fw, fb, g, b, ow, ob = ctx.params
         B, sizes, Ho, Wo, hc, K, C5, p2, sid, training, Cs = ctx.meta
         if not training:
             raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        cat, z, mean, rstd, a5, *acts = ctx.saved_tensors
+        l1w, l1b, l2w, l2b, l3w, l3b, l4w, l4b, fw, fb, g, b, ow, ob = ctx.params
         (H, W) = sizes[0]
         M0, dev = B * H * W, dout.device
         lib = L.lib()

@@ -24,8 +24,9 @@ ep = np.abs(fp[:, 1] - ref[:, 1]) / np.maximum(ref[:, 0] * np.sqrt([named[n].num
 print("   param fp: norm err max", en.max(), names[int(en.argmax())], "probe err max", ep.max(), names[int(ep.argmax())])
 live = [not T.zero_grad_param(n) for n in names]
 print("   zero-gradient biases excluded:", len(names) - sum(live), "max |p| there", max(float(named[n].abs().max()) for n, l in zip(names, live) if not l))
-for e, n in sorted((e, n) for e, n, l in zip(np.maximum(en, ep), names, live) if l)[-10:]:
+for e, n in sorted((e, n) for e, n, l in zip(np.maximum(en, ep), names, live) if l)[-4:]:
     print(f"      {e:.3e} {n}")
+print("   worst non-bias:", sorted((e, n) for e, n, l in zip(np.maximum(en, ep), names, live) if l and not n.endswith(".bias"))[-3:])
 for B in (int(os.environ.get("MARGIN_B", 32)),):
     losses, ref_l, rep = T.graph_step_vs_oracle(dev, B=B)
     print(f"== graph step B={B}: loss rel err", np.abs(losses / ref_l - 1).max(), "grads (global, worst tight, worst loose)", rep[:3])

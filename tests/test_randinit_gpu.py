@@ -26,7 +26,10 @@ LOGIT_L2_TOL = 1.0e-2        # logits 1.8-3.0e-3 (L2 2.1-2.3e-3), aux logits 4.3
 TRAJ_LOSS_TOL = 5e-3         # per-step per-domain (L_seg, L_aux, L_kt) relative to the reference value; measured <= 1.5e-3
 TRAJ_DICE_TOL = 1e-3         # Dice of the thresholded prediction after EVERY one of the 5 steps (north_star: "Dice within 1e-3");
                              # measured <= 6e-4
-PARAM_FP_TOL = 2e-2          # per-parameter fingerprint (norm, probe projection) after 5 AdamW steps; see ZERO_GRAD below
+PARAM_FP_TOL = 5e-3          # per-parameter fingerprint (norm, probe projection) after 5 AdamW steps, weights
+PARAM_FP_TOL_BIAS = 8e-2     # ... biases: zero-initialised, so after 5 steps the whole tensor IS 5 AdamW updates of +-lr-sized
+                             # elements, and every element whose gradient sign sits inside the bf16 noise differs by 2*lr:
+                             # measured worst 3.6e-2 (norm1.bias of stage 0); see zero_grad_param for the exactly-zero ones
 
 
 def zero_grad_param(name):
@@ -121,7 +124,8 @@ def test_five_step_mkd_adamw_trajectory_vs_reference_golden(dev, rgold):
     live = np.asarray([not zero_grad_param(n) for n in names])
     err = np.maximum(err_norm, err_probe)
     worst = sorted(zip(err[live], np.asarray(names)[live]))[-5:]
-    assert live.sum() >= 432 - 26 and err[live].max() < PARAM_FP_TOL, worst
+    is_bias = np.asarray([n.endswith(".bias") for n in names])
+    assert live.sum() >= 432 - 26 and err[live & is_bias].max() < PARAM_FP_TOL_BIAS and err[live & ~is_bias].max() < PARAM_FP_TOL, worst
     for n in np.asarray(names)[~live]:           # zero-gradient biases: initialised to 0, moved by at most 5 * lr * (1 + wd) each
         assert float(named[n].detach().abs().max()) <= 5 * 1e-4 * 1.01, n
     sd = m.state_dict()
