@@ -121,6 +121,15 @@ int mdv_bn_act_fwd(const float* z, const float* mean, const float* rstd, const f
 int mdv_bn_act_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                    const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
                    void* stream);
+/* Grouped forms: z is [G*Mg, C], group g = rows [g*Mg, (g+1)*Mg) = one single-domain mini-batch of the stacked multi-domain
+ * forward; statistics, running-buffer updates (in group order) and gradients are exactly those of G consecutive
+ * nn.BatchNorm2d calls, in 3 launches instead of 4G / 3G.  mean/rstd: [G, C].  C % 4 == 0, 32 <= C <= 1024.
+ * fwd ws >= 2*C*G doubles; bwd ws >= 2*C*G doubles + 2*C*G floats. */
+int mdv_bn_train_fwd_grouped(const float* z, int G, int Mg, int C, float eps, float momentum, float* running_mean, float* running_var,
+                             long long* num_batches_tracked, const float* gamma, const float* beta, int act, float* mean, float* rstd,
+                             void* y, int y_bf16, void* ws, void* stream);
+int mdv_bn_act_bwd_grouped(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                           int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int G, int Mg, int C, void* ws, void* stream);
 /* Same with a rank-1 output gradient dy[m,c] = dlog[m] * wrow[c] * dropout2d_mask(m / rows_per_sample, c) generated on the
  * fly: the backward of Dropout2d + the 1-channel `linear_out` head of MLPDecoderFM (Decoders.py:334-337) never
  * materialises the [M, C] gradient of the BatchNorm output. */

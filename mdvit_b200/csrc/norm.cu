@@ -386,6 +386,178 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------ grouped BatchNorm
+// The fused multi-domain forward stacks G single-domain mini-batches along the rows; BatchNorm statistics are per group of
+// Mg consecutive rows (one reference forward each).  These kernels handle all groups in ONE launch (grid.z = group) with
+// float4 loads and 4 rows in flight per thread, instead of G launches of scalar-load kernels.
+// Thread layout: C/4 threads per row (one float4 of channels each), RPI = 256 / (C/4) rows per block iteration.
+template <bool BWD>
+__global__ void __launch_bounds__(256) bn_reduce_g_kernel(const float* __restrict__ a, const float* __restrict__ z,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                           double* __restrict__ sums, int Mg, int C, int rows_per_block) {
+    MDV_PDL_SYNC();
+    __shared__ float4 sh[2][256];
+    const int tpr = C >> 2;                       // threads per row
+    const int rpi = 256 / tpr;                    // rows per block iteration
+    const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+    const int g = blockIdx.z;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(Mg, r0 + rows_per_block);
+    const size_t base = (size_t)g * Mg * C;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (rl < rpi) {
+        float4 mu = s, rs = s, ga = s, be = s;
+        if (BWD) {
+            mu = *reinterpret_cast<const float4*>(mean + (size_t)g * C + 4 * cl);
+            rs = *reinterpret_cast<const float4*>(rstd + (size_t)g * C + 4 * cl);
+            ga = *reinterpret_cast<const float4*>(gamma + 4 * cl);
+            be = *reinterpret_cast<const float4*>(beta + 4 * cl);
+        }
+        constexpr int U = 4;
+        for (int r = r0 + rl; r < r1; r += rpi * U) {
+            float4 zv[U], dv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + u * rpi;
+                const bool ok = rr < r1;
+                const size_t o = base + (size_t)rr * C + 4 * cl;
+                zv[u] = ok ? *reinterpret_cast<const float4*>(z + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BWD) dv[u] = ok ? *reinterpret_cast<const float4*>(a + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * rpi >= r1) break;
+                if (!BWD) {
+                    s.x += zv[u].x; s.y += zv[u].y; s.z += zv[u].z; s.w += zv[u].w;
+                    q.x += zv[u].x * zv[u].x; q.y += zv[u].y * zv[u].y; q.z += zv[u].z * zv[u].z; q.w += zv[u].w * zv[u].w;
+                } else {
+                    const float xh0 = (zv[u].x - mu.x) * rs.x, xh1 = (zv[u].y - mu.y) * rs.y, xh2 = (zv[u].z - mu.z) * rs.z,
+                                xh3 = (zv[u].w - mu.w) * rs.w;
+                    const float g0 = dv[u].x * act_bwd(xh0 * ga.x + be.x, act), g1 = dv[u].y * act_bwd(xh1 * ga.y + be.y, act),
+                                g2 = dv[u].z * act_bwd(xh2 * ga.z + be.z, act), g3 = dv[u].w * act_bwd(xh3 * ga.w + be.w, act);
+                    s.x += g0; s.y += g1; s.z += g2; s.w += g3;
+                    q.x += g0 * xh0; q.y += g1 * xh1; q.z += g2 * xh2; q.w += g3 * xh3;
+                }
+            }
+        }
+    }
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = q;
+    __syncthreads();
+    for (int tid = threadIdx.x; tid < 2 * tpr; tid += 256) {
+        const int which = tid / tpr, c4 = tid % tpr;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < rpi; ++i) {
+            const float4 v = sh[which][i * tpr + c4];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        double* dst = sums + (size_t)g * 2 * C + which * C + 4 * c4;
+        atomicAdd(dst, (double)t.x);
+        atomicAdd(dst + 1, (double)t.y);
+        atomicAdd(dst + 2, (double)t.z);
+        atomicAdd(dst + 3, (double)t.w);
+    }
+}
+
+// train-mode statistics of G groups; the running buffers are updated group by group IN ORDER, exactly as G consecutive
+// nn.BatchNorm2d forwards would (momentum update is not commutative)
+__global__ void bn_finalize_g_kernel(const double* __restrict__ sums, int G, int Mg, int C, float eps, float momentum,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                     long long* __restrict__ num_batches, float* __restrict__ mean, float* __restrict__ rstd) {
+    MDV_PDL_SYNC();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches) *num_batches += G;
+    if (c >= C) return;
+    float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+    for (int g = 0; g < G; ++g) {
+        const double mu = sums[(size_t)g * 2 * C + c] / Mg;
+        double var = sums[(size_t)g * 2 * C + C + c] / Mg - mu * mu;
+        if (var < 0) var = 0;
+        mean[(size_t)g * C + c] = (float)mu;
+        rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+        rm = (1.f - momentum) * rm + momentum * (float)mu;
+        const double unb = Mg > 1 ? var * Mg / (Mg - 1) : var;
+        rv = (1.f - momentum) * rv + momentum * (float)unb;
+    }
+    if (running_mean) {
+        running_mean[c] = rm;
+        running_var[c] = rv;
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) bn_act_fwd_g_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int act, TO* __restrict__ y, int total,
+                                                            int C, int group_elems) {
+    MDV_PDL_SYNC();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const int c = i % C, g = i / group_elems;
+    const float4 v = *reinterpret_cast<const float4*>(z + i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + (size_t)g * C + c), rs = *reinterpret_cast<const float4*>(rstd + (size_t)g * C + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float o[4] = {act_fwd((v.x - mu.x) * rs.x * ga.x + be.x, act), act_fwd((v.y - mu.y) * rs.y * ga.y + be.y, act),
+                  act_fwd((v.z - mu.z) * rs.z * ga.z + be.z, act), act_fwd((v.w - mu.w) * rs.w * ga.w + be.w, act)};
+    if (sizeof(TO) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + i) = make_float4(o[0], o[1], o[2], o[3]);
+    else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + i) = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
+}
+
+// coef[g][c] = sum_g / Mg, coef[g][C+c] = sum_gxhat / Mg;  dgamma += sum over groups of sum_gxhat; dbeta += ... sum_g
+__global__ void bn_bwd_finalize_g_kernel(const double* __restrict__ sums, int G, int Mg, int C, float* __restrict__ coef,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    MDV_PDL_SYNC();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sg = 0.0, sq = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double a = sums[(size_t)g * 2 * C + c], b = sums[(size_t)g * 2 * C + C + c];
+        coef[(size_t)g * 2 * C + c] = (float)(a / Mg);
+        coef[(size_t)g * 2 * C + C + c] = (float)(b / Mg);
+        sg += a;
+        sq += b;
+    }
+    if (dbeta) atomicAdd(dbeta + c, (float)sg);
+    if (dgamma) atomicAdd(dgamma + c, (float)sq);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) bn_bwd_apply_g_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                              const float* __restrict__ coef, TO* __restrict__ dz, int total, int C,
+                                                              int group_elems) {
+    MDV_PDL_SYNC();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const int c = i % C, g = i / group_elems;
+    const float4 zv = *reinterpret_cast<const float4*>(z + i), dv = *reinterpret_cast<const float4*>(dy + i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + (size_t)g * C + c), rs = *reinterpret_cast<const float4*>(rstd + (size_t)g * C + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float4 k0 = *reinterpret_cast<const float4*>(coef + (size_t)g * 2 * C + c), k1 = *reinterpret_cast<const float4*>(coef + (size_t)g * 2 * C + C + c);
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w},
+                g4[4] = {ga.x, ga.y, ga.z, ga.w}, b4[4] = {be.x, be.y, be.z, be.w}, c0[4] = {k0.x, k0.y, k0.z, k0.w}, c1[4] = {k1.x, k1.y, k1.z, k1.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float xh = (zz[j] - m4[j]) * r4[j];
+        const float gg = dd[j] * act_bwd(xh * g4[j] + b4[j], act);
+        o[j] = g4[j] * r4[j] * (gg - c0[j] - xh * c1[j]);
+    }
+    if (sizeof(TO) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(dz) + i) = make_float4(o[0], o[1], o[2], o[3]);
+    else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dz) + i) = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
+}
+
+int grouped_rows_per_block(int Mg, int C, int G) {
+    const int rpi = 256 / (C / 4);
+    int want = (6 * MDV_NUM_SMS) / G;                     // ~6 blocks per SM over all groups
+    if (want < 1) want = 1;
+    int rpb = mdv_cdiv(Mg, want);
+    const int minr = rpi * 16;
+    if (rpb < minr) rpb = minr;
+    return rpb;
+}
+
 int stats_rows_per_block(int M, int C) {
     // aim at ~4 waves of 148 SMs
     int col_blocks = mdv_cdiv(C, 32);
@@ -551,6 +723,59 @@ static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, c
         mdv_launch(bn_bwd_apply_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (bf16*)dz, total, C, r1);
     else
         mdv_launch(bn_bwd_apply_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, coef, (float*)dz, total, C, r1);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+// ---- grouped train-mode BatchNorm (+activation): one call = G consecutive nn.BatchNorm2d forwards on [G*Mg, C]
+static bool bn_grouped_ok(int G, int Mg, int C) { return G >= 1 && Mg >= 1 && C >= 32 && C <= 1024 && (C & 3) == 0 && (long long)G * Mg * C < 0x7fffffffLL; }
+
+extern "C" int mdv_bn_train_fwd_grouped(const float* z, int G, int Mg, int C, float eps, float momentum, float* running_mean,
+                                        float* running_var, long long* num_batches_tracked, const float* gamma, const float* beta, int act,
+                                        float* mean, float* rstd, void* y, int y_bf16, void* ws, void* stream) {
+    if (!z || !gamma || !beta || !mean || !rstd || !y || !ws) return MDV_ERR_ARG;
+    if (!bn_grouped_ok(G, Mg, C)) return MDV_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C * G, st);
+    if (e != cudaSuccess) return (int)e;
+    const int rpb = grouped_rows_per_block(Mg, C, G);
+    mdv_launch(bn_reduce_g_kernel<false>, dim3(mdv_cdiv(Mg, rpb), 1, G), dim3(256), 0, st, (const float*)nullptr, z, (const float*)nullptr,
+               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, 0, (double*)ws, Mg, C, rpb);
+    MDV_CHECK_LAUNCH();
+    mdv_launch(bn_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)ws, G, Mg, C, eps, momentum, running_mean, running_var,
+               num_batches_tracked, mean, rstd);
+    MDV_CHECK_LAUNCH();
+    const int total = G * Mg * C;
+    const int blocks = mdv_cdiv(total / 4, 256);
+    if (y_bf16)
+        mdv_launch(bn_act_fwd_g_kernel<bf16>, dim3(blocks), dim3(256), 0, st, z, (const float*)mean, (const float*)rstd, gamma, beta, act, (bf16*)y, total, C, Mg * C);
+    else
+        mdv_launch(bn_act_fwd_g_kernel<float>, dim3(blocks), dim3(256), 0, st, z, (const float*)mean, (const float*)rstd, gamma, beta, act, (float*)y, total, C, Mg * C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_bn_act_bwd_grouped(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                                      const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int G, int Mg, int C,
+                                      void* ws, void* stream) {
+    if (!dy || !z || !mean || !rstd || !gamma || !beta || !dz || !ws) return MDV_ERR_ARG;
+    if (!bn_grouped_ok(G, Mg, C)) return MDV_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sums = (double*)ws;
+    float* coef = (float*)(sums + (size_t)2 * C * G);
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C * G, st);
+    if (e != cudaSuccess) return (int)e;
+    const int rpb = grouped_rows_per_block(Mg, C, G);
+    mdv_launch(bn_reduce_g_kernel<true>, dim3(mdv_cdiv(Mg, rpb), 1, G), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, sums, Mg, C, rpb);
+    MDV_CHECK_LAUNCH();
+    mdv_launch(bn_bwd_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)sums, G, Mg, C, coef, dgamma, dbeta);
+    MDV_CHECK_LAUNCH();
+    const int total = G * Mg * C;
+    const int blocks = mdv_cdiv(total / 4, 256);
+    if (dz_bf16)
+        mdv_launch(bn_bwd_apply_g_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (bf16*)dz, total, C, Mg * C);
+    else
+        mdv_launch(bn_bwd_apply_g_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (float*)dz, total, C, Mg * C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -274,13 +274,16 @@ def bn_forward(z, M, C, weight, bias, running_mean, running_var, nbt, training, 
     mean = torch.empty((G, C), dtype=F32, device=dev)
     rstd = torch.empty((G, C), dtype=F32, device=dev)
     y = torch.empty((M, C), dtype=BF16 if out_bf16 else F32, device=dev)
-    for g in range(G):
-        zs = z[g * Mg:(g + 1) * Mg]
-        ws = torch.empty(2 * C, dtype=torch.float64, device=dev) if training else None
-        check(L.lib().mdv_bn_stats(ptr(zs), Mg, C, ctypes.c_float(eps), ctypes.c_float(momentum), int(training), ptr(running_mean),
-                                   ptr(running_var), ptr(nbt), ptr(mean[g]), ptr(rstd[g]), ptr(ws), L.stream()), "mdv_bn_stats")
-        check(L.lib().mdv_bn_act_fwd(ptr(zs), ptr(mean[g]), ptr(rstd[g]), ptr(weight), ptr(bias), act, ptr(y[g * Mg:(g + 1) * Mg]),
-                                     int(out_bf16), Mg, C, L.stream()), "mdv_bn_act_fwd")
+    if training:
+        ws = torch.empty(2 * C * G, dtype=torch.float64, device=dev)
+        check(L.lib().mdv_bn_train_fwd_grouped(ptr(z), G, Mg, C, ctypes.c_float(eps), ctypes.c_float(momentum), ptr(running_mean),
+                                               ptr(running_var), ptr(nbt), ptr(weight), ptr(bias), act, ptr(mean), ptr(rstd), ptr(y),
+                                               int(out_bf16), ptr(ws), L.stream()), "mdv_bn_train_fwd_grouped")
+        return y, mean, rstd
+    check(L.lib().mdv_bn_stats(ptr(z), M, C, ctypes.c_float(eps), ctypes.c_float(momentum), 0, ptr(running_mean), ptr(running_var), ptr(nbt),
+                               ptr(mean[0]), ptr(rstd[0]), None, L.stream()), "mdv_bn_stats")
+    check(L.lib().mdv_bn_act_fwd(ptr(z), ptr(mean[0]), ptr(rstd[0]), ptr(weight), ptr(bias), act, ptr(y), int(out_bf16), M, C, L.stream()),
+          "mdv_bn_act_fwd")
     return y, mean, rstd
 
 
@@ -293,11 +296,9 @@ def bn_backward(dy, z, mean, rstd, weight, bias, act, M, C, dz_bf16=True):
     dz = torch.empty((M, C), dtype=BF16 if dz_bf16 else F32, device=dev)
     dg, rg = gtarget(weight)
     db, rb = gtarget(bias)
-    for g in range(G):
-        ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
-        sl = slice(g * Mg, (g + 1) * Mg)
-        check(L.lib().mdv_bn_act_bwd(ptr(dy[sl]), ptr(z[sl]), ptr(mean[g]), ptr(rstd[g]), ptr(weight), ptr(bias), act, ptr(dz[sl]),
-                                     int(dz_bf16), ptr(dg), ptr(db), Mg, C, ptr(ws), L.stream()), "mdv_bn_act_bwd")
+    ws = torch.empty(3 * C * G, dtype=torch.float64, device=dev)
+    check(L.lib().mdv_bn_act_bwd_grouped(ptr(dy), ptr(z), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), act, ptr(dz), int(dz_bf16), ptr(dg),
+                                         ptr(db), G, Mg, C, ptr(ws), L.stream()), "mdv_bn_act_bwd_grouped")
     return dz, rg, rb
 
 

@@ -265,6 +265,38 @@ def test_batchnorm_train_fwd_bwd_and_running_stats(env, M, C, act):
     assert rel(mean, rm) == 0 and rel(rstd, torch.rsqrt(rv + 1e-5)) < 1e-6
 
 
+@pytest.mark.parametrize("G,Mg,C,act,bf16_out", [(4, 512, 32, 3, False), (4, 1000, 64, 3, True), (1, 128, 1024, 2, False), (4, 3000, 320, 2, False),
+                                                  (2, 4096, 512, 2, True), (4, 77, 128, 3, False)])
+def test_batchnorm_grouped_equals_consecutive_batchnorm_calls(env, G, Mg, C, act, bf16_out):
+    """mdv_bn_train_fwd_grouped / mdv_bn_act_bwd_grouped on G stacked mini-batches == G consecutive nn.BatchNorm2d forwards
+    (train mode: per-group batch statistics, running buffers updated in group order) and their autograd."""
+    L, lib, dev = env
+    torch.manual_seed(G * C + Mg)
+    M = G * Mg
+    z = (torch.randn(M, C, device=dev) * 2 + torch.arange(G, device=dev).repeat_interleave(Mg)[:, None] * 0.7).requires_grad_()
+    g = (1 + 0.1 * torch.randn(C, device=dev)).requires_grad_()
+    b = (0.1 * torch.randn(C, device=dev)).requires_grad_()
+    rm, rv = torch.randn(C, device=dev) * 0.1, 1 + 0.2 * torch.rand(C, device=dev)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    nbt = torch.zeros((), dtype=torch.long, device=dev)
+    mean, rstd = torch.empty(G, C, device=dev), torch.empty(G, C, device=dev)
+    y = torch.empty(M, C, device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    ws = torch.empty(2 * C * G, dtype=torch.float64, device=dev)
+    L.check(lib.mdv_bn_train_fwd_grouped(L.ptr(z), G, Mg, C, 1e-5, 0.1, L.ptr(rm), L.ptr(rv), L.ptr(nbt), L.ptr(g), L.ptr(b), act, L.ptr(mean),
+                                         L.ptr(rstd), L.ptr(y), int(bf16_out), L.ptr(ws), L.stream()), "bn_g")
+    actf = F.relu if act == 2 else F.hardswish
+    ref = torch.cat([actf(F.batch_norm(z[i * Mg:(i + 1) * Mg], rm_ref, rv_ref, g, b, True, 0.1, 1e-5)) for i in range(G)])
+    assert rel(y, ref) < (BF16_TOL if bf16_out else F32_TOL)
+    assert rel(rm, rm_ref) < 1e-5 and rel(rv, rv_ref) < 1e-5 and nbt.item() == G
+    dy = torch.randn(M, C, device=dev)
+    (ref * dy).sum().backward()
+    dz, dg, db = torch.empty(M, C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    ws2 = torch.empty(3 * C * G, dtype=torch.float64, device=dev)
+    L.check(lib.mdv_bn_act_bwd_grouped(L.ptr(dy), L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(g), L.ptr(b), act, L.ptr(dz), 0, L.ptr(dg), L.ptr(db),
+                                       G, Mg, C, L.ptr(ws2), L.stream()), "bn_bwd_g")
+    assert rel(dz, z.grad) < 1e-3 and rel(dg, g.grad) < 1e-3 and rel(db, b.grad) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------- stencils
 @pytest.mark.parametrize("B,H,W,C,stride", [(2, 16, 16, 64, 1), (2, 16, 16, 64, 2), (1, 8, 12, 320, 2), (3, 4, 4, 512, 1),
                                             (2, 64, 64, 64, 1), (1, 24, 40, 128, 1), (2, 16, 20, 320, 1), (1, 70, 9, 64, 1)])
