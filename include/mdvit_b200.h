@@ -186,6 +186,15 @@ int mdv_da_gate_bwd(const float* label, const float* w2, const float* hid_in, co
                     float* db1, float* dw2, float* db2, float* ws /* B*(C+hid) floats */, int B, int nd, int hid, int C, int heads,
                     void* stream);
 
+/* ------------------------------------------------------------------ softmax(Q K^T) V attention + DA gate (TransFuse_S_adapt's DeiT branch) */
+/* Attention_Sup.forward between its qkv and proj Linears (Models/Hybrid_models/TransFuseFolder/vision_transformer.py:149-169):
+ *   out[b,n,h*64+v] = gate[b,h*64+v] * sum_m softmax_m(scale * q[b,h,n,:].k[b,h,m,:]) v[b,h,m,v]
+ * qkv bf16 [B,N,3C] (rows q | k | v, heads contiguous inside each, as nn.Linear(dim, 3*dim) lays them out), gate fp32 [B,C]
+ * from mdv_da_gate_fwd (softmax over heads) or NULL (plain Attention, vision_transformer.py:110-122), out bf16 [B,N,C].
+ * lse (optional, [B,heads,N] fp32) receives the row log-sum-exp for a backward pass.  head_dim 64, N in {128, 256}. */
+int mdv_sdpa_fwd(const void* qkv_bf16, const float* gate, void* out_bf16, float* lse, int B, int N, int C, int heads, float scale,
+                 void* stream);
+
 /* ------------------------------------------------------------------ heads, reductions, casts */
 /* logits[m] = sum_c x[m,c] w[c] dropout2d(b,c) + bias  — the C->1 1x1 conv commuted in front of the final resize */
 int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const float* bias, float* out, int M, int C, int rows_per_sample,

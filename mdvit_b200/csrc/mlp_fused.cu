@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             uint32_t pk[16];
             if (MODE == 0) {
                 uint32_t uk[TRAIN ? 16 : 1];
+                uint32_t hw = 0;
                 const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned)p.hidden + (unsigned)col0) >> 1);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -361,7 +362,15 @@ __global__ void __launch_bounds__(THREADS, 1)
                         gelu_pair<TRAIN>(x, &gl, &gr);
                         if (TRAIN) {
                             if (dthr) {
-                                const uint32_t h = drop_hash(dkey1, pbase + j);
+                                // the hidden-activation mask lives only in this kernel (u carries it to the backward pass), so it
+                                // need not follow the library-wide one-hash-per-pair convention: one full hash per 8 elements, then
+                                // a multiply-add + xorshift step per further pair (3 instructions instead of 10; issue-bound loop)
+                                if ((j & 3) == 0) hw = drop_hash(dkey1, pbase + j);
+                                else {
+                                    hw = hw * 0x9E3779B1u + 0x7F4A7C15u;
+                                    hw ^= hw >> 15;
+                                }
+                                const uint32_t h = hw;
                                 const float2 sc = make_float2(drop_lo(h, dthr, dinv), drop_hi(h, dthr, dinv));
                                 gl = __fmul2_rn(gl, sc);
                                 gr = __fmul2_rn(gr, sc);
@@ -386,13 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 uint4 uq[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) uq[j] = lds128(ua + off[j]);
-                // The loads must have RETURNED before the buffer is handed back to the TMA producer: an mbarrier arrive does not
-                // wait for this thread's outstanding shared-memory loads (it is executed by a different unit than the LSU
-                // queue they sit in), and nothing between here and the arrive consumes uq[].  Without this fence the next
-                // u tile landed under loads still in flight: a few lanes of a warp saw rows of the wrong tile.
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&aux_empty[sb]);
+                // (the u buffer is handed back to the TMA producer further down, AFTER the stores that consume these loads)
                 float d[32];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -410,6 +413,13 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const uint32_t mt = mid_addr + sb * TILE_BYTES;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sts128(mt + off[j], make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+                // Hand the u buffer back to the TMA producer only now: the stores above DEPEND on the u loads, so the loads have
+                // returned.  An mbarrier arrive does not wait for the thread's outstanding shared-memory loads (it is executed by
+                // a different unit than the LSU queue they sit in) and MEMBAR.CTA did not close the window either: arriving
+                // right after issuing the loads let the next u tile land under loads still in flight — a few lanes of a
+                // warp then saw rows of the wrong tile, in roughly one run out of six.
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&aux_empty[sb]);
                 if (p.colsum1) {
                     // column sums of this warp's 32 x 32 block by a transposing butterfly: after the step with offset `o` a
                     // lane keeps half of its columns, each summed over twice as many rows; lane l ends with column l

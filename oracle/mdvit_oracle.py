@@ -105,6 +105,23 @@ def factor_attention(sd, prefix, crpe_prefix, x, H, W, domain_label, drop_p=0.0,
     return F.dropout(y, drop_p, training)
 
 
+def attention_sup(sd, prefix, x, domain_label, num_heads, return_pre_proj=False):
+    """Attention_Sup.forward, Models/Hybrid_models/TransFuseFolder/vision_transformer.py:149-169 (TransFuse_S_adapt's DeiT
+    branch; plain Attention :110-122 when domain_label is None): softmax(q k^T * scale) v, the softmax-over-heads DA gate,
+    then proj.  attn_drop / proj_drop are 0 in the TransFuse trainer's configuration."""
+    B, N, C = x.shape
+    hd = C // num_heads
+    qkv = F.linear(x, sd[prefix + ".qkv.weight"], sd.get(prefix + ".qkv.bias")).reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1)
+    y = attn @ v                                                    # [B,h,N,hd]
+    if domain_label is not None:
+        y = domain_gate(sd, prefix, domain_label, num_heads)[:, :, None, :] * y
+    y = y.transpose(1, 2).reshape(B, N, C)
+    out = F.linear(y, sd[prefix + ".proj.weight"], sd[prefix + ".proj.bias"])
+    return (out, y) if return_pre_proj else out
+
+
 def mlp(sd, prefix, x, drop_p=0.0, training=False):
     """Mlp.forward, mpvit.py:71-78 (GELU = exact erf)."""
     x = F.gelu(F.linear(x, sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"]))

@@ -115,10 +115,17 @@ def test_mlp_bwd_matches_torch(env, M, C, hidden):
     for with_w in (True, False) * (3 if M >= 40000 else 1):
         du = torch.zeros(M, hidden, device=dev, dtype=torch.bfloat16) if with_w else None
         cs = torch.ones(hidden, device=dev) if with_w else None                # accumulates (+=)
-        dx = torch.empty(M, C, device=dev)
+        # (no kernel between the previous round's checks and this launch when the buffer is merely allocated: the timing in
+        # which a too-early release of the u buffer showed up; NaN prefill in the other rounds catches unwritten rows)
+        dx = torch.empty(M, C, device=dev) if with_w is False else torch.full((M, C), float("nan"), device=dev)
         L.check(lib.mdv_mlp_bwd(L.ptr(dy), L.ptr(w2t), L.ptr(u), L.ptr(w1t), L.ptr(du), L.ptr(dx), L.ptr(cs), M, C, hidden, L.stream()),
                 "mlp_bwd")
-        assert rel(dx, dx_ref) < TOL
+        def diag(a, b):
+            bad = ((a.float() - b).abs().amax(dim=1) > 0.02 * b.abs().max()).nonzero().flatten()
+            t = torch.unique(bad // 128)
+            return (f"with_w={with_w}: {bad.numel()} bad rows, tiles {t[:8].tolist()} (tile // 148 = {[int(x) // 148 for x in t[:8]]}), "
+                    f"rows in tile {torch.unique(bad % 128)[:24].tolist()}, nan {int(torch.isnan(a.float()).sum())}")
+        assert rel(dx, dx_ref) < TOL, diag(dx, dx_ref)
         if with_w:
-            assert rel(du, du_ref) < TOL
+            assert rel(du, du_ref) < TOL, diag(du, du_ref)
             assert rel(cs - 1.0, du_ref.sum(0)) < TOL

@@ -1,0 +1,88 @@
+"""softmax(QK^T)V attention with the DA head gate (TransFuse_S_adapt's DeiT-S branch, BASELINE.json config 4 / SURVEY 8f-1):
+ * CPU: the oracle restatement (oracle.mdvit_oracle.attention_sup) against golden outputs of the UNMODIFIED reference
+   Attention_Sup / Attention modules (oracle/make_golden_transfuse.py);
+ * GPU: qkv GEMM -> mdv_da_gate_fwd -> mdv_sdpa_fwd (tcgen05) -> proj GEMM through the C ABI against the same goldens.
+Tolerance of the bf16 tensor-core path: 1e-2 of the tensor abs-max (bf16 q/k/v, bf16 probabilities, fp32 accumulation)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.make_golden_transfuse import DIM, HEADS, N, attention_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def tgold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "transfuse_attention_golden.npz"), allow_pickle=False)
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def test_oracle_attention_sup_matches_reference_golden(tgold):
+    from oracle import mdvit_oracle as O
+    sd, x, label = attention_case()
+    sd = {"a." + k: v for k, v in sd.items()}
+    out, pre = O.attention_sup(sd, "a", x, label, HEADS, return_pre_proj=True)
+    assert rel(out, tgold["sup_out"].astype(np.float32)) < 2e-3 and rel(pre, tgold["sup_pre_proj"].astype(np.float32)) < 2e-3   # fp16 storage
+    out2, pre2 = O.attention_sup(sd, "a", x, None, HEADS, return_pre_proj=True)
+    assert rel(out2, tgold["plain_out"].astype(np.float32)) < 2e-3 and rel(pre2, tgold["plain_pre_proj"].astype(np.float32)) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sup", [True, False])
+def test_sdpa_kernel_matches_reference_attention_golden(tgold, sup):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200 import _lib as L
+    lib, dev = L.lib(), torch.device("cuda")
+    sd, x, label = attention_case()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    B, M = x.shape[0], x.shape[0] * N
+    xb = x.to(dev).reshape(M, DIM).bfloat16()
+    qkv = torch.empty(M, 3 * DIM, device=dev, dtype=torch.bfloat16)
+    e = L.GemmEpi()
+    e.out, e.ldc, e.out_bf16, e.bias = L.ptr(qkv), 3 * DIM, 1, L.ptr(sd["qkv.bias"])
+    wq = sd["qkv.weight"].bfloat16()
+    L.check(lib.mdv_gemm_nt(L.ptr(xb), DIM, L.ptr(wq), DIM, M, 3 * DIM, DIM, ctypes.byref(e), L.stream()), "qkv")
+    gate = None
+    if sup:
+        hid = sd["domain_layer.0.weight"].shape[0]
+        gate, hidb = torch.empty(B, DIM, device=dev), torch.empty(B, hid, device=dev)
+        lab = label.to(dev)
+        L.check(lib.mdv_da_gate_fwd(L.ptr(lab), L.ptr(sd["domain_layer.0.weight"]), L.ptr(sd["domain_layer.0.bias"]), L.ptr(sd["domain_layer.2.weight"]),
+                                    L.ptr(sd["domain_layer.2.bias"]), L.ptr(hidb), L.ptr(gate), B, 4, hid, DIM, HEADS, L.stream()), "gate")
+    y = torch.empty(M, DIM, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, HEADS, N, device=dev)
+    L.check(lib.mdv_sdpa_fwd(L.ptr(qkv), L.ptr(gate), L.ptr(y), L.ptr(lse), B, N, DIM, HEADS, ctypes.c_float((DIM // HEADS) ** -0.5), L.stream()), "sdpa")
+    out = torch.empty(M, DIM, device=dev)
+    e2 = L.GemmEpi()
+    e2.out, e2.ldc, e2.out_bf16, e2.bias = L.ptr(out), DIM, 0, L.ptr(sd["proj.bias"])
+    wp = sd["proj.weight"].bfloat16()
+    L.check(lib.mdv_gemm_nt(L.ptr(y), DIM, L.ptr(wp), DIM, M, DIM, DIM, ctypes.byref(e2), L.stream()), "proj")
+    key = "sup" if sup else "plain"
+    assert rel(y.reshape(B, N, DIM), tgold[key + "_pre_proj"].astype(np.float32)) < 1e-2
+    assert rel(out.reshape(B, N, DIM), tgold[key + "_out"].astype(np.float32)) < 1e-2
+    # the saved log-sum-exp is that of the scaled scores
+    q, k = qkv.float().reshape(B, N, 3, HEADS, 64)[:, :, 0], qkv.float().reshape(B, N, 3, HEADS, 64)[:, :, 1]
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k) * 0.125
+    assert rel(lse, torch.logsumexp(s, dim=-1)) < 2e-3
+    # N = 128 variant and odd batch: against torch on the same bf16 qkv
+    for Bn, Nn in ((3, 128), (5, 256)):
+        torch.manual_seed(Bn)
+        qkv2 = (torch.randn(Bn * Nn, 3 * DIM, device=dev) * 1.5).bfloat16()
+        g2 = torch.softmax(torch.randn(Bn, HEADS, 64, device=dev), dim=1).reshape(Bn, DIM).contiguous() if sup else None
+        y2 = torch.empty(Bn * Nn, DIM, device=dev, dtype=torch.bfloat16)
+        L.check(lib.mdv_sdpa_fwd(L.ptr(qkv2), L.ptr(g2), L.ptr(y2), None, Bn, Nn, DIM, HEADS, ctypes.c_float(0.125), L.stream()), "sdpa")
+        t = qkv2.float().reshape(Bn, Nn, 3, HEADS, 64)
+        a = torch.softmax(torch.einsum("bnhd,bmhd->bhnm", t[:, :, 0], t[:, :, 1]) * 0.125, dim=-1)
+        ref = torch.einsum("bhnm,bmhd->bnhd", a, t[:, :, 2])
+        if sup:
+            ref = ref * g2.reshape(Bn, 1, HEADS, 64)
+        assert rel(y2.reshape(Bn, Nn, HEADS, 64), ref) < 1e-2
