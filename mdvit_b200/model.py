@@ -37,30 +37,53 @@ class Conv2d_BN(nn.Module):
         _ctor_draw(self.conv)
         self.act_layer = act_layer() if act_layer is not None else nn.Identity()
 
+    def norm(self, d=None):
+        return self.bn
+
+
+class Conv2d_BN_M(nn.Module):
+    """mdvit.py:23-71: Conv2d_BN with one BatchNorm per domain (`bns[int(d)]`)."""
+
+    def __init__(self, in_ch, out_ch, kernel_size=1, stride=1, pad=0, act_layer=None, num_domains=1):
+        super().__init__()
+        self.conv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, pad, bias=False)
+        self.bns = nn.ModuleList([nn.BatchNorm2d(out_ch) for _ in range(num_domains)])
+        _ctor_draw(self.conv)
+        self.act_layer = act_layer() if act_layer is not None else nn.Identity()
+
+    def norm(self, d=None):
+        return self.bns[int(d)]
+
 
 class DWConv2d_BN(nn.Module):
     """mdvit.py:74-123: depthwise (groups=in_ch) + pointwise in->out + BN + Hardswish."""
 
-    def __init__(self, in_ch, out_ch, kernel_size=3, stride=1):
+    def __init__(self, in_ch, out_ch, kernel_size=3, stride=1, num_domains=None):
         super().__init__()
         self.dwconv = nn.Conv2d(in_ch, in_ch, kernel_size, stride, (kernel_size - 1) // 2, groups=in_ch, bias=False)
         self.pwconv = nn.Conv2d(in_ch, out_ch, 1, 1, 0, bias=False)
-        self.bn = nn.BatchNorm2d(out_ch)
+        if num_domains is None:
+            self.bn = nn.BatchNorm2d(out_ch)
+        else:       # DWConv2d_BN_M, mdvit.py:127-180: domain-specific norms
+            self.bns = nn.ModuleList([nn.BatchNorm2d(out_ch) for _ in range(num_domains)])
         self.act = nn.Hardswish()
         self.stride = stride
         _ctor_draw(self.dwconv, self.pwconv)
+
+    def norm(self, d=None):
+        return self.bn if hasattr(self, "bn") else self.bns[int(d)]
 
 
 class DWCPatchEmbed(nn.Module):
     """mdvit.py:183-208."""
 
-    def __init__(self, in_chans, embed_dim, patch_size=3, stride=1):
+    def __init__(self, in_chans, embed_dim, patch_size=3, stride=1, num_domains=None):
         super().__init__()
-        self.patch_conv = DWConv2d_BN(in_chans, embed_dim, patch_size, stride)
+        self.patch_conv = DWConv2d_BN(in_chans, embed_dim, patch_size, stride, num_domains)
 
-    def forward(self, x, H, W, after_stem=False):
+    def forward(self, x, H, W, after_stem=False, d=None):
         pc = self.patch_conv
-        bn = pc.bn
+        bn = pc.norm(d)
         y = ops.PatchEmbedFn.apply(x, pc.dwconv.weight, pc.pwconv.weight, bn.weight, bn.bias,
                                    (bn.running_mean, bn.running_var, bn.num_batches_tracked), H, W, pc.stride,
                                    self.training, after_stem)
@@ -71,13 +94,19 @@ class DWCPatchEmbed(nn.Module):
 class DecoderDWConv2d_BN(nn.Module):
     """Decoders.py:15-63: 3x3 conv groups=out_ch over 2*out_ch inputs, pointwise out->out, BN, Hardswish."""
 
-    def __init__(self, in_ch, out_ch):
+    def __init__(self, in_ch, out_ch, num_domains=None):
         super().__init__()
         self.dwconv = nn.Conv2d(in_ch, out_ch, 3, 1, 1, groups=out_ch, bias=False)
         self.pwconv = nn.Conv2d(out_ch, out_ch, 1, 1, 0, bias=False)
-        self.bn = nn.BatchNorm2d(out_ch)
+        if num_domains is None:
+            self.bn = nn.BatchNorm2d(out_ch)
+        else:       # Decoders.DWConv2d_BN_M, Decoders.py:66-118
+            self.bns = nn.ModuleList([nn.BatchNorm2d(out_ch) for _ in range(num_domains)])
         self.act = nn.Hardswish()
         _ctor_draw(self.dwconv, self.pwconv)
+
+    def norm(self, d=None):
+        return self.bn if hasattr(self, "bn") else self.bns[int(d)]
 
 
 class ConvPosEnc(nn.Module):
@@ -145,13 +174,17 @@ class SerialBlock_adapt(nn.Module):
     """mdvit.py:316-361."""
 
     def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, drop, attn_drop, drop_path, norm_layer, shared_cpe, shared_crpe,
-                 adapt_method, num_domains, label_only_guard=False):
+                 adapt_method, num_domains, label_only_guard=False, dsn=False):
         super().__init__()
         self.label_only_guard = label_only_guard   # base.py:216 tests only `domain_label != None`
         if num_heads != ops.HEADS:
             raise ValueError("mdvit_b200 kernels are specialised for 8 attention heads (the reference's only setting)")
         self.cpe = shared_cpe
-        self.norm1 = norm_layer(dim)
+        self.dsn = dsn          # SerialBlock_adapt_M (mdvit.py:364-412): norm1s / norm2s, one LayerNorm per domain
+        if dsn:
+            self.norm1s = nn.ModuleList([norm_layer(dim) for _ in range(num_domains)])
+        else:
+            self.norm1 = norm_layer(dim)
         self.adapt_method = adapt_method
         if adapt_method == 'Sup':
             self.factoratt_crpe = FactorAtt_ConvRelPosEnc_Sup(dim, num_heads, qkv_bias, attn_drop, drop, shared_crpe,
@@ -161,11 +194,16 @@ class SerialBlock_adapt(nn.Module):
         self.drop_path = nn.Identity()
         self.drop_path_rate = float(drop_path)
         self.drop_rate = float(drop)
-        self.norm2 = norm_layer(dim)
+        if dsn:
+            self.norm2s = nn.ModuleList([norm_layer(dim) for _ in range(num_domains)])
+        else:
+            self.norm2 = norm_layer(dim)
         self.mlp = Mlp(dim, int(dim * mlp_ratio), drop)
 
-    def forward(self, x, size, domain_label=None):
+    def forward(self, x, size, domain_label=None, d=None):
         H, W = size
+        norm1 = self.norm1s[int(d)] if self.dsn else self.norm1
+        norm2 = self.norm2s[int(d)] if self.dsn else self.norm2
         att = self.factoratt_crpe
         # dispatch quirks of mdvit.py:350-353 preserved: Sup attention needs a label, plain attention rejects one
         use_label = domain_label is not None and (self.label_only_guard or self.adapt_method is not None)
@@ -176,13 +214,13 @@ class SerialBlock_adapt(nn.Module):
         dl = att.domain_layer
         da = (dl[0].weight, dl[0].bias, dl[2].weight, dl[2].bias) if dl is not None else (None, None, None, None)
         cl = att.crpe.conv_list
-        if not (isinstance(self.norm1, nn.LayerNorm) and abs(self.norm1.eps - 1e-6) < 1e-12):
+        if not (isinstance(norm1, nn.LayerNorm) and abs(norm1.eps - 1e-6) < 1e-12):
             raise ValueError("mdvit_b200 supports norm_layer=LayerNorm(eps=1e-6) (the reference default)")
         return ops.BlockFn.apply(
             x, domain_label if use_label else None, self.cpe.proj.weight, self.cpe.proj.bias,
             cl[0].weight, cl[0].bias, cl[1].weight, cl[1].bias, cl[2].weight, cl[2].bias,
-            self.norm1.weight, self.norm1.bias, att.qkv.weight, att.qkv.bias, att.proj.weight, att.proj.bias,
-            da[0], da[1], da[2], da[3], self.norm2.weight, self.norm2.bias,
+            norm1.weight, norm1.bias, att.qkv.weight, att.qkv.bias, att.proj.weight, att.proj.bias,
+            da[0], da[1], da[2], da[3], norm2.weight, norm2.bias,
             self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
             H, W, self.drop_rate, self.drop_path_rate, self.training)
 
@@ -191,35 +229,36 @@ class MHSA_stage_adapt(nn.Module):
     """mdvit.py:415-440: one shared ConvPosEnc + ConvRelPosEnc, `num_layers` serial blocks."""
 
     def __init__(self, dim, num_layers, num_heads, mlp_ratio, qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
-                 num_domains=4, norm_layer=nn.LayerNorm, adapt_method=None, label_only_guard=False):
+                 num_domains=4, norm_layer=nn.LayerNorm, adapt_method=None, label_only_guard=False, dsn=False):
         super().__init__()
         self.cpe = ConvPosEnc(dim, k=3)
         self.crpe = ConvRelPosEnc(Ch=dim // num_heads, h=num_heads, window=CRPE_WINDOW)
         self.mhca_blks = nn.ModuleList([
             SerialBlock_adapt(dim, num_heads, mlp_ratio, qkv_bias, drop_rate, attn_drop_rate, drop_path_rate, norm_layer,
-                              self.cpe, self.crpe, adapt_method, num_domains, label_only_guard) for _ in range(num_layers)])
+                              self.cpe, self.crpe, adapt_method, num_domains, label_only_guard, dsn) for _ in range(num_layers)])
 
-    def forward(self, x, H, W, domain_label=None):
+    def forward(self, x, H, W, domain_label=None, d=None):
         for blk in self.mhca_blks:
-            x = blk(x, (H, W), domain_label)
+            x = blk(x, (H, W), domain_label, d)
         return x
 
 
 class UnetDecodingBlockTransformer(nn.Module):
     """Decoders.py:174-214 (use_res=False)."""
 
-    def __init__(self, in_channel, out_channel, mhsa_block):
+    def __init__(self, in_channel, out_channel, mhsa_block, num_domains=None):
         super().__init__()
         self.conv_before = nn.Conv2d(in_channel, out_channel, kernel_size=1)
-        self.conv_after = DecoderDWConv2d_BN(out_channel * 2, out_channel)
+        self.conv_after = DecoderDWConv2d_BN(out_channel * 2, out_channel, num_domains)
         self.mhsa_block = mhsa_block
 
-    def forward(self, x, h, w, skip, H, W, domain_label=None):
+    def forward(self, x, h, w, skip, H, W, domain_label=None, d=None):
         ca = self.conv_after
+        bn = ca.norm(d)
         out = ops.DecoderConvFn.apply(x, skip, self.conv_before.weight, self.conv_before.bias, ca.dwconv.weight, ca.pwconv.weight,
-                                      ca.bn.weight, ca.bn.bias, (ca.bn.running_mean, ca.bn.running_var, ca.bn.num_batches_tracked),
+                                      bn.weight, bn.bias, (bn.running_mean, bn.running_var, bn.num_batches_tracked),
                                       h, w, H, W, self.training)
-        return self.mhsa_block(out, H, W, domain_label)
+        return self.mhsa_block(out, H, W, domain_label, d)
 
 
 class MLPDecoderFM(nn.Module):
@@ -302,32 +341,39 @@ class _Trunk(nn.Module):
             m.weight.data.fill_(1)
             m.bias.data.zero_()
 
-    def _trunk_forward(self, x, domain_label):
+    def _stem_parts(self, d=None):
+        return self.stem[0].conv, self.stem[0].bn, self.stem[1].conv, self.stem[1].bn
+
+    def _bridge_parts(self, d=None):
+        b = self.bridge
+        return b[0], b[1], b[3], b[4]
+
+    def _trunk_forward(self, x, domain_label, d=None):
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
             raise ValueError("input must be [B,3,H,W] with H and W divisible by 32")
         if not x.is_cuda:
             raise RuntimeError("mdvit_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-        s0, s1 = self.stem[0], self.stem[1]
+        c0, n0, c1, n1 = self._stem_parts(d)
         H, W = x.shape[2] // 4, x.shape[3] // 4
-        t = ops.StemFn.apply(x, s0.conv.weight, s0.bn.weight, s0.bn.bias, s1.conv.weight, s1.bn.weight, s1.bn.bias,
-                             (s0.bn.running_mean, s0.bn.running_var, s0.bn.num_batches_tracked,
-                              s1.bn.running_mean, s1.bn.running_var, s1.bn.num_batches_tracked), self.training)
+        t = ops.StemFn.apply(x, c0.weight, n0.weight, n0.bias, c1.weight, n1.weight, n1.bias,
+                             (n0.running_mean, n0.running_var, n0.num_batches_tracked,
+                              n1.running_mean, n1.running_var, n1.num_batches_tracked), self.training)
         enc = []
         for idx in range(self.num_stages):
-            t, H, W = self.patch_embed_stages[idx](t, H, W, after_stem=(idx == 0))
-            t = self.mhsa_stages[idx](t, H, W, domain_label)
+            t, H, W = self.patch_embed_stages[idx](t, H, W, after_stem=(idx == 0), d=d)
+            t = self.mhsa_stages[idx](t, H, W, domain_label, d)
             enc.append((t, H, W))
         return enc
 
-    def _decode(self, enc, domain_label):
+    def _decode(self, enc, domain_label, d=None):
         t3, H3, W3 = enc[3]
-        b = self.bridge
-        out = ops.BridgeFn.apply(t3, b[0].weight, b[0].bias, b[1].weight, b[1].bias, b[3].weight, b[3].bias, b[4].weight, b[4].bias,
-                                 (b[1].running_mean, b[1].running_var, b[1].num_batches_tracked,
-                                  b[4].running_mean, b[4].running_var, b[4].num_batches_tracked), H3, W3, self.training)
+        c0, n0, c1, n1 = self._bridge_parts(d)
+        out = ops.BridgeFn.apply(t3, c0.weight, c0.bias, n0.weight, n0.bias, c1.weight, c1.bias, n1.weight, n1.bias,
+                                 (n0.running_mean, n0.running_var, n0.num_batches_tracked,
+                                  n1.running_mean, n1.running_var, n1.num_batches_tracked), H3, W3, self.training)
         h, w = H3, W3
         for dec, (skip, H, W) in zip((self.decoder1, self.decoder2, self.decoder3, self.decoder4), (enc[3], enc[2], enc[1], enc[0])):
-            out = dec(out, h, w, skip, H, W, domain_label)
+            out = dec(out, h, w, skip, H, W, domain_label, d)
             h, w = H, W
         return out, h, w
 
@@ -403,6 +449,76 @@ class MDViT(_Trunk):
                 aux_out = branch([split[i][g] for i in range(5)], [(e[1], e[2]) for e in enc], img_size)
             res.append((split[5][g], aux_out))
         return res
+
+
+class MDViT_DSN(_Trunk):
+    """Drop-in for Models.Transformer.mdvit.MDViT_DSN (mdvit.py:735-960): MDViT with DOMAIN-SPECIFIC NORMS — every
+    BatchNorm (stem, patch embeddings, bridge, decoder convs) and every LayerNorm (norm1s / norm2s of each block) exists
+    once per domain and forward(x, domain_label, d) uses the set `int(d)`.  The kernels are the same: the autograd
+    Functions take the norm parameters as arguments, so domain selection is a pointer choice on the host.
+    decoder_name='MLPFM' is the implemented auxiliary decoder (the reference class defaults to 'MLP')."""
+
+    def __init__(self, img_size=512, in_chans=3, num_stages=4, num_layers=[2, 2, 2, 2], embed_dims=[64, 128, 320, 512],
+                 mlp_ratios=[8, 8, 4, 4], num_heads=[8, 8, 8, 8], qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), conv_norm=nn.BatchNorm2d, adapt_method=None,
+                 num_domains=4, decoder_name='MLP', **kwargs):
+        super().__init__()
+        if qk_scale is not None or num_stages != 4 or in_chans != 3 or conv_norm is not nn.BatchNorm2d:
+            raise ValueError("mdvit_b200 implements the 4-stage, 3-channel, BatchNorm2d configuration of the reference trainers")
+        if decoder_name != 'MLPFM':
+            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' for MDViT_DSN")
+        self.num_stages, self.decoder_name, self.embed_dims = num_stages, decoder_name, list(embed_dims)
+        self.stem_1 = Conv2d_BN_M(in_chans, embed_dims[0] // 2, 3, 2, 1, act_layer=nn.Hardswish, num_domains=num_domains)
+        self.stem_2 = Conv2d_BN_M(embed_dims[0] // 2, embed_dims[0], 3, 2, 1, act_layer=nn.Hardswish, num_domains=num_domains)
+        self.patch_embed_stages = nn.ModuleList([
+            DWCPatchEmbed(embed_dims[idx] if idx == 0 else embed_dims[idx - 1], embed_dims[idx], 3, 1 if idx == 0 else 2, num_domains)
+            for idx in range(num_stages)])
+
+        def stage(idx):
+            return MHSA_stage_adapt(embed_dims[idx], num_layers[idx], num_heads[idx], mlp_ratios[idx], qkv_bias, drop_rate,
+                                    attn_drop_rate, drop_path_rate, num_domains, norm_layer, adapt_method, dsn=True)
+
+        self.mhsa_stages = nn.ModuleList([stage(idx) for idx in range(num_stages)])
+        self.bridge_conv1 = nn.Conv2d(embed_dims[3], embed_dims[3], 3, 1, 1)
+        self.bridge_norms1 = nn.ModuleList([nn.BatchNorm2d(embed_dims[3]) for _ in range(num_domains)])
+        self.bridge_act1 = nn.ReLU(inplace=True)
+        self.bridge_conv2 = nn.Conv2d(embed_dims[3], embed_dims[3] * 2, 3, 1, 1)
+        self.bridge_norms2 = nn.ModuleList([nn.BatchNorm2d(embed_dims[3] * 2) for _ in range(num_domains)])
+        self.bridge_act2 = nn.ReLU(inplace=True)
+        self.mhsa_list = [stage(idx) for idx in range(num_stages)]
+        self.decoder1 = UnetDecodingBlockTransformer(embed_dims[3] * 2, embed_dims[3], self.mhsa_list[3], num_domains)
+        self.decoder2 = UnetDecodingBlockTransformer(embed_dims[3], embed_dims[2], self.mhsa_list[2], num_domains)
+        self.decoder3 = UnetDecodingBlockTransformer(embed_dims[2], embed_dims[1], self.mhsa_list[1], num_domains)
+        self.decoder4 = UnetDecodingBlockTransformer(embed_dims[1], embed_dims[0], self.mhsa_list[0], num_domains)
+        self.finalconv = nn.Sequential(nn.Conv2d(embed_dims[0], 1, kernel_size=1))
+        self.debranch1 = MLPDecoderFM(embed_dims, 1, 512)
+        self.debranch2 = MLPDecoderFM(embed_dims, 1, 512)
+        self.debranch3 = MLPDecoderFM(embed_dims, 1, 512)
+        self.debranch4 = MLPDecoderFM(embed_dims, 1, 512)
+        self.skip_aux_in_eval = False
+        self.apply(self._init_weights)
+
+    def _stem_parts(self, d=None):
+        return self.stem_1.conv, self.stem_1.norm(d), self.stem_2.conv, self.stem_2.norm(d)
+
+    def _bridge_parts(self, d=None):
+        return self.bridge_conv1, self.bridge_norms1[int(d)], self.bridge_conv2, self.bridge_norms2[int(d)]
+
+    def forward(self, x, domain_label=None, d=None, out_feat=False, out_seg=True):
+        img_size = x.shape[2:]
+        int(d)      # the reference indexes its norm lists with int(d) everywhere (mdvit.py:65,398,917): d is required
+        enc = self._trunk_forward(x, domain_label, d)
+        if not out_seg:
+            return {'seg': None, 'feat': enc[3][0].mean(dim=1)}
+        dec4, h, w = self._decode(enc, domain_label, d)
+        out = self._head(dec4, h, w, img_size)
+        aux_out = None
+        if d in ('0', '1', '2', '3') and (self.training or not self.skip_aux_in_eval):
+            branch = getattr(self, f'debranch{int(d) + 1}')
+            aux_out = branch([e[0] for e in enc] + [dec4], [(e[1], e[2]) for e in enc], img_size)
+        if out_feat:
+            return {'seg': [out, aux_out], 'feat': enc[3][0].mean(dim=1)}
+        return [out, aux_out]
 
 
 class BASE(_Trunk):

@@ -164,3 +164,23 @@ def synth_batch(seed, dom, B, H=256, W=256):
         r = g.uniform(0.15, 0.35) * min(H, W)
         lab[b, 0] = ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r).astype(np.float32)
     return img, torch.from_numpy(lab)
+
+
+def dsn_perturb(state_dict, seed=7):
+    """Make the domain-specific norm sets of an MDViT_DSN state_dict differ from each other (a fresh model has identical
+    gamma=1 / beta=0 in every set, so the domain index would not change the output): deterministic in the key name."""
+    out = {}
+    for k, v in state_dict.items():
+        if any(t in k for t in (".bns.", ".norm1s.", ".norm2s.", "bridge_norms1.", "bridge_norms2.")) and v.is_floating_point():
+            g = _rng(seed, k)
+            n = torch.from_numpy(g.standard_normal(tuple(v.shape)).astype(np.float32))
+            if k.endswith("running_var"):
+                v = 1.0 + 0.3 * n.abs()
+            elif k.endswith("running_mean"):
+                v = 0.2 * n
+            elif k.endswith("weight"):
+                v = 1.0 + 0.2 * n
+            else:
+                v = 0.2 * n
+        out[k] = v.clone()
+    return out

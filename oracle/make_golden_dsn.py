@@ -1,0 +1,42 @@
+"""TEST INFRASTRUCTURE ONLY.  Golden logits of the UNMODIFIED reference MDViT_DSN (domain-specific norms,
+Models/Transformer/mdvit.py:735-960) -> tests/golden/mdvit_dsn_golden.npz.   python oracle/make_golden_dsn.py
+
+Weights: torch.manual_seed(0) + the stock constructor (mdvit_b200.model.MDViT_DSN reproduces them bit for bit), then
+synth.dsn_perturb so that the four norm sets differ.  Dropout2d of the aux decoders off."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mdvit_b200 import synth  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from oracle.make_golden import fingerprint  # noqa: E402
+
+
+def main():
+    ref_shim.load_reference()
+    from Models.Transformer.mdvit import MDViT_DSN
+    torch.manual_seed(0)
+    m = MDViT_DSN(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")
+    out = {"keys": np.asarray(list(m.state_dict().keys())), "init_fp": fingerprint(list(m.named_parameters()))}
+    m.load_state_dict(synth.dsn_perturb(m.state_dict()), strict=True)
+    for k in range(1, 5):
+        getattr(m, f"debranch{k}").dropout.p = 0.0
+    with torch.no_grad():
+        for mode in ("eval", "train"):
+            m.train(mode == "train")
+            for d in (1, 3):
+                img, _ = synth.synth_batch(11, d, 2, 64, 64)
+                dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float()
+                o, a = m(img, dl, str(d))
+                out[f"{mode}_out_{d}"], out[f"{mode}_aux_{d}"] = o.numpy(), a.numpy()
+    path = os.path.join(ROOT, "tests", "golden", "mdvit_dsn_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""MDViT_DSN (domain-specific norms; Models/Transformer/mdvit.py:735-960): schema and random init on
+CPU, logits against golden outputs of the UNMODIFIED reference on the GPU (oracle/make_golden_dsn.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mdvit_b200 import synth
+from tests.helpers import fingerprint
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dgold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "mdvit_dsn_golden.npz"), allow_pickle=False)
+
+
+def build():
+    from mdvit_b200.model import MDViT_DSN
+    torch.manual_seed(0)
+    return MDViT_DSN(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="MLPFM")
+
+
+def test_dsn_state_dict_schema_and_random_init_match_the_reference(dgold):
+    m = build()
+    assert list(m.state_dict().keys()) == [str(k) for k in dgold["keys"]] and len(dgold["keys"]) == 980
+    fp = fingerprint(list(m.named_parameters()))
+    assert np.abs(fp - dgold["init_fp"]).max() <= 1e-9 * np.abs(dgold["init_fp"]).max()
+    with pytest.raises(NotImplementedError):
+        from mdvit_b200.model import MDViT_DSN
+        MDViT_DSN(img_size=64)            # the reference default decoder_name='MLP' is not built
+
+
+@pytest.mark.gpu
+def test_dsn_logits_match_reference_golden(dgold):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    dev = torch.device("cuda")
+    m = build()
+    m.load_state_dict(synth.dsn_perturb(m.state_dict()), strict=True)
+    for k in range(1, 5):
+        getattr(m, f"debranch{k}").dropout.p = 0.0
+    m = m.to(dev)
+
+    def rel(a, b):
+        b = torch.as_tensor(b)
+        return ((a.detach().float().cpu() - b).abs().max() / b.abs().max()).item()
+
+    outs = {}
+    with torch.no_grad():
+        for mode in ("eval", "train"):
+            m.train(mode == "train")
+            for d in (1, 3):
+                img, _ = synth.synth_batch(11, d, 2, 64, 64)
+                dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float().to(dev)
+                o, a = m(img.to(dev), dl, str(d))
+                outs[(mode, d)] = o
+                assert rel(o, dgold[f"{mode}_out_{d}"]) < 2e-2 and rel(a, dgold[f"{mode}_aux_{d}"]) < 2e-2, (mode, d)
+        # the domain index selects the norm set: same image, other d -> different logits
+        m.eval()
+        img, _ = synth.synth_batch(11, 1, 2, 64, 64)
+        dl = torch.nn.functional.one_hot(torch.full((2,), 1), 4).float().to(dev)
+        o_other = m(img.to(dev), dl, "2")[0]
+        assert rel(o_other, outs[("eval", 1)].cpu()) > 5e-2
+    with pytest.raises((TypeError, ValueError)):
+        m(img.to(dev), dl, None)          # int(d) is required by the reference as well
