@@ -207,76 +207,85 @@ def gpu_eager_baseline(device, B, steps=2, warmup=1):
     return out
 
 
-def kernel_roofline(peaks, device):
-    """Dominant kernel = the tcgen05 GEMM at the MLPDecoderFM.linear_fuse shape (42.7% of forward FLOPs):
-    M = 32*4096 tokens, K = 2112, N = 512.  Timed alone with CUDA events on the launching stream, L2 flushed between launches."""
+def _time_launch(fn, device, reps=8, skip=3):
+    """Average CUDA-event duration of one launch on the launching stream, L2 flushed (256 MB write) between launches."""
+    import torch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    st = torch.cuda.current_stream(device)
+    times = []
+    for i in range(reps):
+        flush.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        fn()
+        t.record(st)
+        t.synchronize()
+        if i >= skip:
+            times.append(s.elapsed_time(t))
+    return sum(times) / len(times)
+
+
+def gemm_roofline(peaks, device, M, N, K, out_bf16, what, traffic=None, traffic_source=None):
+    """The tcgen05 GEMM (gemm_kernel<NT, 8 epilogue warps>: the kernel with the largest share of the step in
+    profiles/r2_launches_step_graph_final.txt) at one of its MLPDecoderFM.linear_fuse shapes, timed alone."""
     import ctypes
     import torch
     from mdvit_b200 import _lib as L
     lib = L.lib()
-    M, N, K = 32 * 4096, 512, 2112
     A = torch.randn(M, K, device=device).bfloat16()
     W = (torch.randn(N, K, device=device) / K ** 0.5).bfloat16()
     bias = torch.zeros(N, device=device)
-    out = torch.empty(M, N, device=device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = torch.empty(M, N, device=device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     e = L.GemmEpi()
-    e.out, e.ldc, e.out_bf16, e.bias = L.ptr(out), N, 0, L.ptr(bias)
-    st = torch.cuda.current_stream(device)
-    times = []
-    for i in range(8):
-        flush.zero_()
-        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(st)
-        L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
-        t.record(st)
-        t.synchronize()
-        if i >= 3:
-            times.append(s.elapsed_time(t))
-    ms = sum(times) / len(times)
+    e.out, e.ldc, e.out_bf16 = L.ptr(out), N, int(out_bf16)
+    if not out_bf16:
+        e.bias = L.ptr(bias)
+    ms = _time_launch(lambda: L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt"), device)
     achieved = 2.0 * M * N * K / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "gemm_kernel<BN,NT> (tcgen05) @ linear_fuse M=131072 N=512 K=2112", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": LINEAR_FUSE_DRAM_BYTES,
-            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_gemm_linear_fuse.txt",
-            "algorithmic_flops_per_launch": 2.0 * M * N * K, "algorithmic_bytes_per_launch": (M * K + N * K) * 2 + M * N * 4,
+    return {"bound": "tensor", "kernel": f"gemm_kernel<NT, 8 epilogue warps> (tcgen05) @ {what} M={M} N={N} K={K}", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+            "algorithmic_flops_per_launch": 2.0 * M * N * K,
+            "algorithmic_bytes_per_launch": (M * K + N * K) * 2 + M * N * (2 if out_bf16 else 4),
             "peak_source": peaks["source"] + " (burst)", "ms_per_launch": ms}
 
 
-def hbm_kernel_roofline(peaks, device):
-    """Second roofline view, for an HBM-bound kernel of the same family: the tcgen05 GEMM at the stage-0 fc2-dgrad shape
-    (M = 128*4096 tokens, K = 64 -> N = 512, epilogue: multiply by the saved gelu'*mask factor + fc1 bias-gradient column
-    sums).  Algorithmic bytes = A + W + factor + out = M*K*2 + N*K*2 + 2*M*N*2; timed like kernel_roofline()."""
-    import ctypes
+def mlp_fused_roofline(peaks, device, backward):
+    """The fused fc1-GELU-fc2 kernels (mlp_fused_kernel, csrc/mlp_fused.cu) at the stage-0 shape of the step (M = 128*4096
+    tokens, C = 64, hidden = 512): HBM-bound by design (the hidden tile stays on chip; in training hact / u / du still have to
+    be written for the weight gradients).  Algorithmic bytes: forward(train) = M*C*(2+4+4) + 2*M*hidden*2; backward =
+    M*C*(2+4) + 2*M*hidden*2 (u read, du written)."""
     import torch
     from mdvit_b200 import _lib as L
     lib = L.lib()
-    M, N, K = 128 * 4096, 512, 64
-    A = torch.randn(M, K, device=device).bfloat16()
-    W = (torch.randn(N, K, device=device) / K ** 0.5).bfloat16()
-    fac = torch.rand(M, N, device=device).bfloat16()
-    out = torch.empty(M, N, device=device, dtype=torch.bfloat16)
-    cs = torch.zeros(N, device=device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    e = L.GemmEpi()
-    e.out, e.ldc, e.out_bf16, e.mul_gelu_grad, e.ld_mul, e.mul_mode, e.colsum = L.ptr(out), N, 1, L.ptr(fac), N, 1, L.ptr(cs)
-    st = torch.cuda.current_stream(device)
-    times = []
-    for i in range(8):
-        flush.zero_()
-        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(st)
-        L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt")
-        t.record(st)
-        t.synchronize()
-        if i >= 3:
-            times.append(s.elapsed_time(t))
-    ms = sum(times) / len(times)
-    nbytes = M * K * 2 + N * K * 2 + 2 * M * N * 2
+    M, C, hidden = 128 * 4096, 64, 512
+    a = torch.randn(M, C, device=device).bfloat16()
+    w1 = (torch.randn(hidden, C, device=device) / C ** 0.5).bfloat16()
+    w2 = (torch.randn(C, hidden, device=device) / hidden ** 0.5).bfloat16()
+    b1, b2 = torch.zeros(hidden, device=device), torch.zeros(C, device=device)
+    res, out = torch.randn(M, C, device=device), torch.empty(M, C, device=device)
+    hact = torch.empty(M, hidden, device=device, dtype=torch.bfloat16)
+    u = torch.rand(M, hidden, device=device).bfloat16()
+    rng = torch.tensor([1, 2], dtype=torch.int64, device=device)
+    cs = torch.zeros(hidden, device=device)
+    st = L.stream()
+    if backward:
+        fn = lambda: L.check(lib.mdv_mlp_bwd(L.ptr(a), L.ptr(w1), L.ptr(u), L.ptr(w2), L.ptr(hact), L.ptr(out), L.ptr(cs), M, C, hidden, st), "mdv_mlp_bwd")  # noqa: E731
+        nbytes = M * C * 6 + 2 * M * hidden * 2
+        name = "mlp_fused_kernel<backward> du=(dY W2)*u, dX=du W1, du stored + fc1 bias-gradient sums"
+        traffic, src = 604202752 + 621095680, "profiles/r2_ncu_mlp_fused_bwd.txt"
+    else:
+        fn = lambda: L.check(lib.mdv_mlp_fwd(L.ptr(a), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(res), L.ptr(out), L.ptr(hact), L.ptr(u), M, C,  # noqa: E731
+                                             hidden, 0.1, L.ptr(rng), 3, 4, None, 1, st), "mdv_mlp_fwd")
+        nbytes = M * C * 10 + 2 * M * hidden * 2
+        name = "mlp_fused_kernel<forward, training> fc1-GELU-dropout-fc2-dropout-residual, hact and u stored"
+        traffic, src = 201570048 + 1150855000, "profiles/r2_ncu_mlp_fused_fwd_train.txt"
+    ms = _time_launch(fn, device)
     achieved = nbytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "gemm_kernel<NT, 16 epilogue warps> (tcgen05) @ stage-0 fc2 dgrad M=524288 N=512 K=64, gelu'*mask multiply + bias-grad sums",
-            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-            "algorithmic_bytes_per_launch": nbytes, "peak_source": peaks["source"], "ms_per_launch": ms}
+    return {"bound": "hbm", "kernel": name + f" @ stage 0: M={M} C={C} hidden={hidden}", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": "ncu --set full dram bytes, " + src,
+            "algorithmic_bytes_per_launch": nbytes, "algorithmic_flops_per_launch": 4.0 * M * C * hidden, "peak_source": peaks["source"],
+            "ms_per_launch": ms}
 
 
 def run_infer(args):
@@ -461,11 +470,20 @@ def main():
     value = imgs_per_step / (ms_res * 1e-3)
     e2e = imgs_per_step / (ms_e2e * 1e-3)
     if rank == 0:
-        roof = kernel_roofline(peaks, dev)
-        try:
-            roof_hbm = hbm_kernel_roofline(peaks, dev)
-        except Exception as ex:  # never let the secondary view take the headline line down
-            roof_hbm = {"error": str(ex)[:200]}
+        # `roofline`: the time-dominant kernel of the step (gemm_kernel<NT,8>: 15% of the kernel time over 200 launches,
+        # profiles/r2_launches_step_graph_final.txt) at its heaviest shape, the linear_fuse input-gradient GEMM (8 launches,
+        # 2.1 ms per step); secondary views: the same kernel at the linear_fuse forward shape (r1's headline view), and the
+        # fused MLP kernels that replaced r1's issue-bound GELU / gelu'-epilogue GEMM family (HBM-bound views)
+        roof = gemm_roofline(peaks, dev, 32 * 4096, 2112, 512, True, "linear_fuse dgrad")
+        extra = {}
+        for key, fn in (("roofline_linear_fuse_fwd", lambda: gemm_roofline(peaks, dev, 32 * 4096, 512, 2112, False, "linear_fuse forward", LINEAR_FUSE_DRAM_BYTES,
+                                                                             "ncu --set full dram bytes, profiles/r1_ncu_gemm_linear_fuse.txt")),
+                        ("roofline_hbm_kernel", lambda: mlp_fused_roofline(peaks, dev, True)),
+                        ("roofline_hbm_kernel_fwd", lambda: mlp_fused_roofline(peaks, dev, False))):
+            try:
+                extra[key] = fn()
+            except Exception as ex:  # never let a secondary view take the headline line down
+                extra[key] = {"error": str(ex)[:200]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.model == "MDViT":
             sec, cores = cpu_oracle_step_time(args.cpu_batch_per_domain, 2, 1)
@@ -500,7 +518,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps * 2),
             "launches_per_step": int(launches_per_step),
             "model_algorithmic_tflops": model_tflops,
-            "roofline": roof, "roofline_hbm_kernel": roof_hbm, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks,
+            "roofline": roof, **extra, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks,
             "final_losses_seg_aux_kt_per_domain": loss_host.tolist() if loss_host is not None else None,
         }))
     if world > 1:

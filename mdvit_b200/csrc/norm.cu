@@ -391,11 +391,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // Mg consecutive rows (one reference forward each).  These kernels handle all groups in ONE launch (grid.z = group) with
 // float4 loads and 4 rows in flight per thread, instead of G launches of scalar-load kernels.
 // Thread layout: C/4 threads per row (one float4 of channels each), RPI = 256 / (C/4) rows per block iteration.
-template <bool BWD>
+// (b*C + c) is a multiple of 4: two pair-hashes give the four Dropout2d masks of a float4 of channels
+__device__ __forceinline__ float4 rank1_w4(const Rank1Dy& r1, int b, int c, int C) {
+    float4 w = *reinterpret_cast<const float4*>(r1.wrow + c);
+    if (r1.drop_p > 0.f) {
+        const uint32_t key = rng_key(r1.rng, r1.stream), thr = drop_thresh(r1.drop_p);
+        const float inv = 1.f / (1.f - r1.drop_p);
+        const uint32_t pr = (uint32_t)(b * C + c) >> 1;
+        const uint32_t h0 = drop_hash(key, pr), h1 = drop_hash(key, pr + 1);
+        w.x *= drop_lo(h0, thr, inv); w.y *= drop_hi(h0, thr, inv); w.z *= drop_lo(h1, thr, inv); w.w *= drop_hi(h1, thr, inv);
+    }
+    return w;
+}
+
+template <bool BWD, bool RANK1 = false>
 __global__ void __launch_bounds__(256) bn_reduce_g_kernel(const float* __restrict__ a, const float* __restrict__ z,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                                           double* __restrict__ sums, int Mg, int C, int rows_per_block) {
+                                                           double* __restrict__ sums, int Mg, int C, int rows_per_block,
+                                                           Rank1Dy rk = Rank1Dy()) {
     MDV_PDL_SYNC();
     __shared__ float4 sh[2][256];
     const int tpr = C >> 2;                       // threads per row
@@ -414,6 +428,8 @@ __global__ void __launch_bounds__(256) bn_reduce_g_kernel(const float* __restric
             be = *reinterpret_cast<const float4*>(beta + 4 * cl);
         }
         constexpr int U = 4;
+        int cur_b = -1;
+        float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = r0 + rl; r < r1; r += rpi * U) {
             float4 zv[U], dv[U];
 #pragma unroll
@@ -422,7 +438,20 @@ __global__ void __launch_bounds__(256) bn_reduce_g_kernel(const float* __restric
                 const bool ok = rr < r1;
                 const size_t o = base + (size_t)rr * C + 4 * cl;
                 zv[u] = ok ? *reinterpret_cast<const float4*>(z + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (BWD) dv[u] = ok ? *reinterpret_cast<const float4*>(a + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BWD && !RANK1) dv[u] = ok ? *reinterpret_cast<const float4*>(a + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BWD && RANK1) {
+                    // dy[m, c] = dlog[m] * wrow[c] * dropout2d_mask(m / rps, c), generated on the fly (G == 1)
+                    dv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) {
+                        const int bb = rr / rk.rps;
+                        if (bb != cur_b) {
+                            cur_b = bb;
+                            wm = rank1_w4(rk, bb, 4 * cl, C);
+                        }
+                        const float dl = __ldg(rk.dlog + rr);
+                        dv[u] = make_float4(dl * wm.x, dl * wm.y, dl * wm.z, dl * wm.w);
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -521,17 +550,26 @@ __global__ void bn_bwd_finalize_g_kernel(const double* __restrict__ sums, int G,
     if (dgamma) atomicAdd(dgamma + c, (float)sq);
 }
 
-template <typename TO>
+template <typename TO, bool RANK1 = false>
 __global__ void __launch_bounds__(256) bn_bwd_apply_g_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                                               const float* __restrict__ coef, TO* __restrict__ dz, int total, int C,
-                                                              int group_elems) {
+                                                              int group_elems, Rank1Dy r1 = Rank1Dy()) {
     MDV_PDL_SYNC();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= total) return;
     const int c = i % C, g = i / group_elems;
-    const float4 zv = *reinterpret_cast<const float4*>(z + i), dv = *reinterpret_cast<const float4*>(dy + i);
+    const float4 zv = *reinterpret_cast<const float4*>(z + i);
+    float4 dv;
+    if (RANK1) {
+        const int row = i / C;
+        const float dl = __ldg(r1.dlog + row);
+        const float4 w = rank1_w4(r1, row / r1.rps, c, C);
+        dv = make_float4(dl * w.x, dl * w.y, dl * w.z, dl * w.w);
+    } else {
+        dv = *reinterpret_cast<const float4*>(dy + i);
+    }
     const float4 mu = *reinterpret_cast<const float4*>(mean + (size_t)g * C + c), rs = *reinterpret_cast<const float4*>(rstd + (size_t)g * C + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
     const float4 k0 = *reinterpret_cast<const float4*>(coef + (size_t)g * 2 * C + c), k1 = *reinterpret_cast<const float4*>(coef + (size_t)g * 2 * C + C + c);
@@ -703,9 +741,34 @@ extern "C" int mdv_bn_act_bwd_rank1(const float* dlog, const float* wrow, int ro
     return bn_act_bwd_impl(nullptr, r1, z, mean, rstd, gamma, beta, act, dz, dz_bf16, dgamma, dbeta, M, C, ws, (cudaStream_t)stream);
 }
 
+static bool bn_grouped_ok(int G, int Mg, int C);
+
 static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
                            cudaStream_t st) {
+    if (r1.dlog && bn_grouped_ok(1, M, C)) {
+        // rank-1 output gradient through the float4 / 4-rows-in-flight kernels (one group)
+        double* sums = (double*)ws;
+        float* coef = (float*)(sums + 2 * C);
+        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+        if (e != cudaSuccess) return (int)e;
+        const int rpb = grouped_rows_per_block(M, C, 1);
+        mdv_launch((bn_reduce_g_kernel<true, true>), dim3(mdv_cdiv(M, rpb), 1, 1), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
+                   sums, M, C, rpb, r1);
+        MDV_CHECK_LAUNCH();
+        mdv_launch(bn_bwd_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)sums, 1, M, C, coef, dgamma, dbeta);
+        MDV_CHECK_LAUNCH();
+        const int total = M * C;
+        const int blocks = mdv_cdiv(total / 4, 256);
+        if (dz_bf16)
+            mdv_launch((bn_bwd_apply_g_kernel<bf16, true>), dim3(blocks), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
+                       (const float*)coef, (bf16*)dz, total, C, M * C, r1);
+        else
+            mdv_launch((bn_bwd_apply_g_kernel<float, true>), dim3(blocks), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
+                       (const float*)coef, (float*)dz, total, C, M * C, r1);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     double* sums = (double*)ws;
     float* coef = (float*)(sums + 2 * C);
     cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
@@ -740,7 +803,7 @@ extern "C" int mdv_bn_train_fwd_grouped(const float* z, int G, int Mg, int C, fl
     if (e != cudaSuccess) return (int)e;
     const int rpb = grouped_rows_per_block(Mg, C, G);
     mdv_launch(bn_reduce_g_kernel<false>, dim3(mdv_cdiv(Mg, rpb), 1, G), dim3(256), 0, st, (const float*)nullptr, z, (const float*)nullptr,
-               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, 0, (double*)ws, Mg, C, rpb);
+               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, 0, (double*)ws, Mg, C, rpb, Rank1Dy());
     MDV_CHECK_LAUNCH();
     mdv_launch(bn_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)ws, G, Mg, C, eps, momentum, running_mean, running_var,
                num_batches_tracked, mean, rstd);
@@ -766,16 +829,16 @@ extern "C" int mdv_bn_act_bwd_grouped(const float* dy, const float* z, const flo
     cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C * G, st);
     if (e != cudaSuccess) return (int)e;
     const int rpb = grouped_rows_per_block(Mg, C, G);
-    mdv_launch(bn_reduce_g_kernel<true>, dim3(mdv_cdiv(Mg, rpb), 1, G), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, sums, Mg, C, rpb);
+    mdv_launch(bn_reduce_g_kernel<true>, dim3(mdv_cdiv(Mg, rpb), 1, G), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, sums, Mg, C, rpb, Rank1Dy());
     MDV_CHECK_LAUNCH();
     mdv_launch(bn_bwd_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)sums, G, Mg, C, coef, dgamma, dbeta);
     MDV_CHECK_LAUNCH();
     const int total = G * Mg * C;
     const int blocks = mdv_cdiv(total / 4, 256);
     if (dz_bf16)
-        mdv_launch(bn_bwd_apply_g_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (bf16*)dz, total, C, Mg * C);
+        mdv_launch(bn_bwd_apply_g_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (bf16*)dz, total, C, Mg * C, Rank1Dy());
     else
-        mdv_launch(bn_bwd_apply_g_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (float*)dz, total, C, Mg * C);
+        mdv_launch(bn_bwd_apply_g_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (float*)dz, total, C, Mg * C, Rank1Dy());
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -264,10 +264,14 @@ class UnetDecodingBlockTransformer(nn.Module):
 class MLPDecoderFM(nn.Module):
     """Decoders.py:289-339."""
 
+    with_feature = True      # MLPDecoderFM also consumes the main decoder's last feature map (x5)
+
     def __init__(self, in_channels, out_channel, hidden_channel=256, outfeature_channel=64, dropout_ratio=0.1):
         super().__init__()
         if out_channel != 1:
             raise ValueError("mdvit_b200 implements the single-class head used by the reference trainers")
+        if not self.with_feature:
+            outfeature_channel = 0
         self.linear1 = nn.Conv2d(in_channels[0], hidden_channel, 1)
         self.linear2 = nn.Conv2d(in_channels[1], hidden_channel, 1)
         self.linear3 = nn.Conv2d(in_channels[2], hidden_channel, 1)
@@ -279,13 +283,25 @@ class MLPDecoderFM(nn.Module):
         self.avg_pool = nn.AdaptiveAvgPool2d((1, 1))
 
     def forward(self, feats, sizes, img_size):
-        x1, x2, x3, x4, x5 = feats
+        x1, x2, x3, x4 = feats[:4]
+        x5 = feats[4] if self.with_feature else None
         bn = self.linear_fuse[1]
         return ops.AuxFn.apply(x1, x2, x3, x4, x5, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                                self.linear3.weight, self.linear3.bias, self.linear4.weight, self.linear4.bias,
                                self.linear_fuse[0].weight, self.linear_fuse[0].bias, bn.weight, bn.bias, self.linear_out.weight,
                                self.linear_out.bias, (bn.running_mean, bn.running_var, bn.num_batches_tracked), tuple(sizes),
                                int(img_size[0]), int(img_size[1]), float(self.dropout.p), self.training)
+
+
+class MLPDecoder(MLPDecoderFM):
+    """Decoders.py:239-286: the SegFormer-style auxiliary decoder WITHOUT the main-decoder feature (decoder_name='MLP')."""
+    with_feature = False
+
+    def __init__(self, in_channels, out_channel, hidden_channel=256, dropout_ratio=0.1):
+        super().__init__(in_channels, out_channel, hidden_channel, 0, dropout_ratio)
+
+
+AUX_DECODERS = {'MLPFM': MLPDecoderFM, 'MLP': MLPDecoder}
 
 
 # ----------------------------------------------------------------------------------------------- models
@@ -392,15 +408,17 @@ class MDViT(_Trunk):
         super().__init__()
         if qk_scale is not None:
             raise ValueError("mdvit_b200 implements qk_scale=None (head_dim**-0.5), the reference trainers' setting")
-        if decoder_name != 'MLPFM':
-            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' (hard-coded by multi_train_MDViT.py:60)")
+        if decoder_name not in AUX_DECODERS:
+            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' (hard-coded by multi_train_MDViT.py:60) and 'MLP' "
+                                      "(mdvit.py:607-611); 'DeepLabV3' and 'Transformer' are not built")
         self.decoder_name = decoder_name
         self._build_trunk(in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, drop_rate, attn_drop_rate,
                           drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains)
-        self.debranch1 = MLPDecoderFM(embed_dims, 1, 512)
-        self.debranch2 = MLPDecoderFM(embed_dims, 1, 512)
-        self.debranch3 = MLPDecoderFM(embed_dims, 1, 512)
-        self.debranch4 = MLPDecoderFM(embed_dims, 1, 512)
+        Aux = AUX_DECODERS[decoder_name]
+        self.debranch1 = Aux(embed_dims, 1, 512)
+        self.debranch2 = Aux(embed_dims, 1, 512)
+        self.debranch3 = Aux(embed_dims, 1, 512)
+        self.debranch4 = Aux(embed_dims, 1, 512)
         # Inference-only switch (not a constructor argument: the signature stays the reference's).  The reference's test loop
         # passes `d`, computes the auxiliary decoder (45% of the forward FLOPs) and then uses only output[0]
         # (multi_train_MDViT.py:377-378).  With this flag set, an eval-mode forward returns [out, None] even when `d` is given.
@@ -465,8 +483,8 @@ class MDViT_DSN(_Trunk):
         super().__init__()
         if qk_scale is not None or num_stages != 4 or in_chans != 3 or conv_norm is not nn.BatchNorm2d:
             raise ValueError("mdvit_b200 implements the 4-stage, 3-channel, BatchNorm2d configuration of the reference trainers")
-        if decoder_name != 'MLPFM':
-            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' for MDViT_DSN")
+        if decoder_name not in AUX_DECODERS:
+            raise NotImplementedError("mdvit_b200 implements decoder_name in ('MLPFM', 'MLP') for MDViT_DSN")
         self.num_stages, self.decoder_name, self.embed_dims = num_stages, decoder_name, list(embed_dims)
         self.stem_1 = Conv2d_BN_M(in_chans, embed_dims[0] // 2, 3, 2, 1, act_layer=nn.Hardswish, num_domains=num_domains)
         self.stem_2 = Conv2d_BN_M(embed_dims[0] // 2, embed_dims[0], 3, 2, 1, act_layer=nn.Hardswish, num_domains=num_domains)
@@ -491,10 +509,11 @@ class MDViT_DSN(_Trunk):
         self.decoder3 = UnetDecodingBlockTransformer(embed_dims[2], embed_dims[1], self.mhsa_list[1], num_domains)
         self.decoder4 = UnetDecodingBlockTransformer(embed_dims[1], embed_dims[0], self.mhsa_list[0], num_domains)
         self.finalconv = nn.Sequential(nn.Conv2d(embed_dims[0], 1, kernel_size=1))
-        self.debranch1 = MLPDecoderFM(embed_dims, 1, 512)
-        self.debranch2 = MLPDecoderFM(embed_dims, 1, 512)
-        self.debranch3 = MLPDecoderFM(embed_dims, 1, 512)
-        self.debranch4 = MLPDecoderFM(embed_dims, 1, 512)
+        Aux = AUX_DECODERS[decoder_name]
+        self.debranch1 = Aux(embed_dims, 1, 512)
+        self.debranch2 = Aux(embed_dims, 1, 512)
+        self.debranch3 = Aux(embed_dims, 1, 512)
+        self.debranch4 = Aux(embed_dims, 1, 512)
         self.skip_aux_in_eval = False
         self.apply(self._init_weights)
 

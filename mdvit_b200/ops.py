@@ -874,12 +874,12 @@ class AuxFn(torch.autograd.Function):
         B = x1.shape[0]
         dev = x1.device
         xs = [_contig(t) for t in (x1, x2, x3, x4)]
-        x5 = _contig(x5)
+        x5 = _contig(x5) if x5 is not None else None      # None: MLPDecoder (Decoders.py:239-286), no main-decoder feature
         (H, W) = sizes[0]
         M0 = B * H * W
         hc = fw.shape[0]               # 512
-        K = fw.shape[1]                # 2112
-        C5 = x5.shape[2]
+        K = fw.shape[1]                # 2112 (MLPDecoderFM) / 2048 (MLPDecoder)
+        C5 = x5.shape[2] if x5 is not None else 0
         rm, rv, nb = bufs
         lib = L.lib()
         lw, lb = (l1w, l2w, l3w, l4w), (l1b, l2b, l3b, l4b)
@@ -898,7 +898,8 @@ class AuxFn(torch.autograd.Function):
                     t = torch.empty((Mi, hc), dtype=BF16, device=dev)
                     gemm_nt(a, wb, Mi, hc, Ci, t, bias=lb[i])
                     upsample_fwd(t, cat[:, i * hc:], B, Hi, Wi, H, W, hc, ld_out=K)
-            cast_bf16(x5, M0, C5, out=cat[:, 4 * hc:], ld_out=K)
+            if x5 is not None:
+                cast_bf16(x5, M0, C5, out=cat[:, 4 * hc:], ld_out=K)
             if not training:      # eval: conv bias + BatchNorm + ReLU folded into the linear_fuse GEMM epilogue
                 a5 = torch.empty((M0, hc), dtype=BF16, device=dev)
                 sc, sh = bn_fold(g, b, rm, rv, fb)
@@ -973,8 +974,10 @@ class AuxFn(torch.autograd.Function):
                 gx.append(dxi)
                 rw.append(r_w)
                 rbs.append(r_b)
-            dx5 = torch.empty((B, H * W, C5), dtype=F32, device=dev)
-            check(lib.mdv_add_f32(ptr(dcat[:, 4 * hc:]), 1, K, ptr(dx5), C5, M0, C5, 0, L.stream()), "mdv_add_f32")
+            dx5 = None
+            if C5:
+                dx5 = torch.empty((B, H * W, C5), dtype=F32, device=dev)
+                check(lib.mdv_add_f32(ptr(dcat[:, 4 * hc:]), 1, K, ptr(dx5), C5, M0, C5, 0, L.stream()), "mdv_add_f32")
         _grads_done(ctx)
         return (gx[0], gx[1], gx[2], gx[3], dx5, rw[0], rbs[0], rw[1], rbs[1], rw[2], rbs[2], rw[3], rbs[3], r_fw, r_fb, rg, rb, r_ow,
                 r_ob, None, None, None, None, None, None)

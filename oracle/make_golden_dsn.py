@@ -16,6 +16,11 @@ from oracle import ref_shim  # noqa: E402
 from oracle.make_golden import fingerprint  # noqa: E402
 
 
+def mlp_aux_state(model):
+    """Deterministic weights for the debranch* tensors of a decoder_name='MLP' model (synth_tensor handles any key/shape)."""
+    return {k: synth.synth_tensor(k, tuple(v.shape)) for k, v in model.state_dict().items() if k.startswith("debranch")}
+
+
 def main():
     ref_shim.load_reference()
     from Models.Transformer.mdvit import MDViT_DSN
@@ -33,6 +38,20 @@ def main():
                 dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float()
                 o, a = m(img, dl, str(d))
                 out[f"{mode}_out_{d}"], out[f"{mode}_aux_{d}"] = o.numpy(), a.numpy()
+    # ---- MDViT with the 'MLP' auxiliary decoder (Decoders.MLPDecoder, Decoders.py:239-286; mdvit.py:607-611)
+    from Models.Transformer.mdvit import MDViT
+    m = MDViT(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="MLP")
+    m.load_state_dict(synth.synth_state_dict(0, aux=False) | {k: v for k, v in mlp_aux_state(m).items()}, strict=True)
+    for k in range(1, 5):
+        getattr(m, f"debranch{k}").dropout.p = 0.0
+    out["mlp_keys"] = np.asarray(list(m.state_dict().keys()))
+    with torch.no_grad():
+        for mode in ("eval", "train"):
+            m.train(mode == "train")
+            img, _ = synth.synth_batch(12, 2, 2, 64, 64)
+            dl = torch.nn.functional.one_hot(torch.full((2,), 2), 4).float()
+            o, a = m(img, dl, "2")
+            out[f"mlp_{mode}_out"], out[f"mlp_{mode}_aux"] = o.numpy(), a.numpy()
     path = os.path.join(ROOT, "tests", "golden", "mdvit_dsn_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -59,7 +59,7 @@ def bench(fn, n=20):
     t.record(); torch.cuda.synchronize()
     return s.elapsed_time(t) / n * 1e3
 
-cases = [(131072, 512, 64, k) for k in ("plain", "fc1_nodrop", "fc1", "fc2d", "fc1_new", "fc2d_new", "fc2d_new_nocs")] + [(131072, 64, 512, "res"), (32768, 1024, 128, "fc1"), (32768, 1024, 128, "fc2d"), (131072, 512, 2112, "lf")]
+cases = [(131072, 512, 64, k) for k in ("plain", "fc1_nodrop", "fc1", "fc2d", "fc1_new", "fc2d_new", "fc2d_new_nocs")] + [(131072, 64, 512, "res"), (32768, 1024, 128, "fc1"), (32768, 1024, 128, "fc2d"), (131072, 512, 2112, "lf"), (131072, 2112, 512, "plain")]
 if os.environ.get("ONE"):
     M, N, K, kind = cases[int(os.environ["ONE"])]
     fn, keep = make(M, N, K, kind)

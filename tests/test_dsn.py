@@ -28,9 +28,11 @@ def test_dsn_state_dict_schema_and_random_init_match_the_reference(dgold):
     assert list(m.state_dict().keys()) == [str(k) for k in dgold["keys"]] and len(dgold["keys"]) == 980
     fp = fingerprint(list(m.named_parameters()))
     assert np.abs(fp - dgold["init_fp"]).max() <= 1e-9 * np.abs(dgold["init_fp"]).max()
+    from mdvit_b200.model import MDViT, MDViT_DSN
+    assert len(MDViT_DSN(img_size=64, adapt_method="Sup").state_dict()) == 980     # the reference default decoder_name is "MLP"
     with pytest.raises(NotImplementedError):
-        from mdvit_b200.model import MDViT_DSN
-        MDViT_DSN(img_size=64)            # the reference default decoder_name='MLP' is not built
+        MDViT_DSN(img_size=64, decoder_name="DeepLabV3")
+    assert list(MDViT(img_size=64, adapt_method="Sup", decoder_name="MLP").state_dict().keys()) == [str(k) for k in dgold["mlp_keys"]]
 
 
 @pytest.mark.gpu
@@ -66,3 +68,33 @@ def test_dsn_logits_match_reference_golden(dgold):
         assert rel(o_other, outs[("eval", 1)].cpu()) > 5e-2
     with pytest.raises((TypeError, ValueError)):
         m(img.to(dev), dl, None)          # int(d) is required by the reference as well
+
+
+@pytest.mark.gpu
+def test_mlp_aux_decoder_logits_match_reference_golden(dgold):
+    """decoder_name='MLP' (Decoders.MLPDecoder: MLPDecoderFM without the main-decoder feature) against the unmodified reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200.model import MDViT
+    from oracle.make_golden_dsn import mlp_aux_state
+    dev = torch.device("cuda")
+    m = MDViT(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="MLP")
+    m.load_state_dict(synth.synth_state_dict(0, aux=False) | mlp_aux_state(m), strict=True)
+    for k in range(1, 5):
+        getattr(m, f"debranch{k}").dropout.p = 0.0
+    m = m.to(dev)
+    img, lab = synth.synth_batch(12, 2, 2, 64, 64)
+    dl = torch.nn.functional.one_hot(torch.full((2,), 2), 4).float().to(dev)
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        with torch.no_grad():
+            o, a = m(img.to(dev), dl, "2")
+        for t, ref in ((o, dgold[f"mlp_{mode}_out"]), (a, dgold[f"mlp_{mode}_aux"])):
+            ref = torch.as_tensor(ref)
+            assert ((t.float().cpu() - ref).abs().max() / ref.abs().max()).item() < 3e-2, mode
+    # and it trains: the MKD losses back-propagate through the 2048-channel fuse
+    from mdvit_b200 import ops
+    m.train()
+    o, a = m(img.to(dev), dl, "2")
+    ops.seg_losses(o, a, lab.to(dev)).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all().item() for n, p in m.named_parameters() if "debranch3" in n or "stem" in n)
