@@ -201,6 +201,8 @@ def gpu_eager_baseline(device, B, steps=2, warmup=1):
             out[mode] = {"images_per_s": 4 * B / (ms * 1e-3), "ms_per_step": ms}
         except torch.cuda.OutOfMemoryError:
             out[mode] = {"error": "out of memory at this batch"}
+        except Exception as ex:      # a baseline leg must never take the headline line down
+            out[mode] = {"error": str(ex)[:200]}
         finally:
             sd = opt = batches = None
             torch.cuda.empty_cache()
@@ -474,7 +476,8 @@ def main():
         # profiles/r2_launches_step_graph_final.txt) at its heaviest shape, the linear_fuse input-gradient GEMM (8 launches,
         # 2.1 ms per step); secondary views: the same kernel at the linear_fuse forward shape (r1's headline view), and the
         # fused MLP kernels that replaced r1's issue-bound GELU / gelu'-epilogue GEMM family (HBM-bound views)
-        roof = gemm_roofline(peaks, dev, 32 * 4096, 2112, 512, True, "linear_fuse dgrad")
+        roof = gemm_roofline(peaks, dev, 32 * 4096, 2112, 512, True, "linear_fuse dgrad", 136498432 + 501603840,
+                             "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_ncu_gemm_linear_fuse_dgrad.txt")
         extra = {}
         for key, fn in (("roofline_linear_fuse_fwd", lambda: gemm_roofline(peaks, dev, 32 * 4096, 512, 2112, False, "linear_fuse forward", LINEAR_FUSE_DRAM_BYTES,
                                                                              "ncu --set full dram bytes, profiles/r1_ncu_gemm_linear_fuse.txt")),

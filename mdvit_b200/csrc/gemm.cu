@@ -20,6 +20,9 @@
 
 namespace {
 using namespace tc;
+#ifdef MDV_GEMM_SPIN_EPILOGUE
+#define mbar_wait mbar_wait_spin
+#endif
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_wait_spin(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], stage_bytes);
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
@@ -144,17 +147,18 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
             // TF32: same descriptor with a/b format 2 instead of 1 (cute::UMMA::F16F32Format); one MMA consumes K=8 fp32 = 32 B,
             // exactly the +32 B per step of the bf16 path (K=16), so the k-loop is shared
             const uint32_t idesc = p.tf32 ? (make_idesc(BM, BN, TN) + (1u << 7) + (1u << 10)) : make_idesc(BM, BN, TN);
+            const bool is_tf32 = p.tf32 != 0;        // (kept in a register: the issue loop is the critical path of MMA-bound shapes)
             int it = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const TileCoord tc = tile_coord<TN>(p, t);
                 const int as = lt & 1;
-                mbar_wait(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);
+                mbar_wait_spin(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait_spin(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + A_BYTES;
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                             ad = make_desc(sa + k * 2048, 8192, 1024);
                             bd = make_desc(sb + k * 2048, 8192, 1024);
                         }
-                        if (!TN && p.tf32) tc_mma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!TN && is_tf32) tc_mma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                         else tc_mma_bf16(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[s]);
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 const int col0 = n0 + c0;
                 const bool full_cols = col0 + 32 <= p.N;
                 // the multiplier tile (fc2 dgrad: gelu'(.)*mask saved by the forward) is read row-per-lane from global memory:
-                // issue those loads BEFORE the TMEM load so their latency overlaps it (profiles/r2_ncu_gemm_fc2_dgrad.txt:
+                // issue those loads BEFORE the TMEM load so their latency overlaps it (profiles/r2_ncu_gemm_fc2_dgrad_before_hoist.txt:
                 // long-scoreboard stall 8.6 issue slots per instruction when they were issued at the point of use)
                 uint4 uq[4];
                 const bool pre_u = e.mul_gelu_grad && row_ok && full_cols;

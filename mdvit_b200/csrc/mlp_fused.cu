@@ -146,21 +146,21 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int lt = 0; lt < my_tiles; ++lt) {
                 const int m0 = ((int)blockIdx.x + lt * (int)gridDim.x) * BM;
                 const int ab = lt % p.a_bufs, ak = lt / p.a_bufs;
-                mbar_wait(&a_empty[ab], (ak & 1) ^ 1);
+                mbar_wait_spin(&a_empty[ab], (ak & 1) ^ 1);
                 mbar_expect_tx(&a_full[ab], a_bytes);
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + (size_t)ab * a_bytes + kb * TILE_BYTES, &tmA, kb * 64, m0, &a_full[ab]);
                 for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
                     const int ws = g % p.w_stages, wk = g / p.w_stages;
                     uint8_t* sb1 = sW + (size_t)ws * w_bytes;
-                    mbar_wait(&w1_empty[ws], (wk & 1) ^ 1);
+                    mbar_wait_spin(&w1_empty[ws], (wk & 1) ^ 1);
                     mbar_expect_tx(&w1_full[ws], b1_bytes);
                     for (int kb = 0; kb < KB; ++kb) tma_load_2d(sb1 + kb * (HC * 128), &tmB1, kb * 64, ch * HC, &w1_full[ws]);
-                    mbar_wait(&w2_empty[ws], (wk & 1) ^ 1);
+                    mbar_wait_spin(&w2_empty[ws], (wk & 1) ^ 1);
                     mbar_expect_tx(&w2_full[ws], b2_bytes);
                     tma_load_2d(sb1 + b1_bytes, &tmB2, ch * HC, 0, &w2_full[ws]);
                     if (p.load_aux) {
                         const int xb = g & 1;
-                        mbar_wait(&aux_empty[xb], ((g >> 1) & 1) ^ 1);
+                        mbar_wait_spin(&aux_empty[xb], ((g >> 1) & 1) ^ 1);
                         mbar_expect_tx(&aux_full[xb], TILE_BYTES);
                         tma_load_2d(sAux + xb * TILE_BYTES, &tmAux, ch * HC, m0, &aux_full[xb]);
                     }
@@ -175,13 +175,13 @@ __global__ void __launch_bounds__(THREADS, 1)
             int g = 0;
             for (int lt = 0; lt < my_tiles; ++lt) {
                 const int ab = lt % p.a_bufs, ak = lt / p.a_bufs;
-                mbar_wait(&a_full[ab], ak & 1);
+                mbar_wait_spin(&a_full[ab], ak & 1);
                 const uint32_t a0 = smem_u32(sA + (size_t)ab * a_bytes);
                 for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
                     const int ws = g % p.w_stages, wk = g / p.w_stages;
                     const int sb = g & 1;
-                    mbar_wait(&w1_full[ws], wk & 1);
-                    mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1);
+                    mbar_wait_spin(&w1_full[ws], wk & 1);
+                    mbar_wait_spin(&s_empty[sb], ((g >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t b0 = smem_u32(sW + (size_t)ws * w_bytes);
                     const uint32_t d = tmem_s + (uint32_t)sb * HC;
@@ -207,13 +207,13 @@ __global__ void __launch_bounds__(THREADS, 1)
             int g = 0;
             for (int lt = 0; lt < my_tiles; ++lt) {
                 const int yb = lt & 1;
-                mbar_wait(&y_empty[yb], ((lt >> 1) & 1) ^ 1);
+                mbar_wait_spin(&y_empty[yb], ((lt >> 1) & 1) ^ 1);
                 const uint32_t d = tmem_y + (uint32_t)yb * C;
                 for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
                     const int ws = g % p.w_stages, wk = g / p.w_stages;
                     const int mb = g & 1;
-                    mbar_wait(&w2_full[ws], wk & 1);
-                    mbar_wait(&mid_full[mb], (g >> 1) & 1);
+                    mbar_wait_spin(&w2_full[ws], wk & 1);
+                    mbar_wait_spin(&mid_full[mb], (g >> 1) & 1);
                     tc_fence_after();
                     const uint64_t ad = dbase + (smem_u32(sMid + mb * TILE_BYTES) >> 4);
                     const uint64_t bd = dbase + (smem_u32(sW + (size_t)ws * w_bytes + b1_bytes) >> 4);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const int m0 = ((int)blockIdx.x + lt * (int)gridDim.x) * BM;
                 for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
                     const int mb = g & 1;
-                    mbar_wait(&mid_full[mb], (g >> 1) & 1);
+                    mbar_wait_spin(&mid_full[mb], (g >> 1) & 1);
                     if (p.store_mid) tma_store_2d(&tmMid, sMid + mb * TILE_BYTES, ch * HC, m0);
                     if (p.store_aux) tma_store_2d(&tmAux, sAux + mb * TILE_BYTES, ch * HC, m0);
                     tma_commit();

@@ -44,6 +44,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// Spinning variant for the single-thread roles (TMA producer, MMA issuers): they are latency-critical and one spinning
+// thread costs few issue slots; the many-warp epilogue uses the suspending mbar_wait above.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     asm volatile(

@@ -255,7 +255,8 @@ def bce_loss(p, y):
     (p - y) / max(p (1 - p), 1e-12) / n, which stays finite at exactly saturated sigmoids (the hand-written
     -(y log p + (1-y) log(1-p)) formula back-propagates 0 * inf = nan there; at the reference's random init most sigmoids
     ARE saturated)."""
-    return F.binary_cross_entropy(p, y)
+    with torch.autocast(device_type=p.device.type, enabled=False):      # (BCELoss refuses to run under autocast)
+        return F.binary_cross_entropy(p.float(), y.float())
 
 
 def seg_losses(out, aux, label):
