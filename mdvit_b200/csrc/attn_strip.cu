@@ -349,7 +349,9 @@ __device__ __forceinline__ void attn_fwd_strip_body(const bf16* __restrict__ qkv
 // ------------------------------------------------------------------------------------------------ backward
 // dQ = s dF.A^T + dF*E ; dK = S*(V.dA^T - r) ; dV = S.dA + convT(dE) ; dE = g dY Q ; dF = g dY            
 // dgate[b,c] += sum_n dY Y / g ;  dWconv[c,tap] += sum_n dE[n,c] V[n+tap,c] ;  dbconv[c] += sum_n dE[n,c]
-template <int CH, int WIN, int TX>
+// EXT: the three per-head mat-vecs (and with them dQ and dK) are done by attn_mm_bwd_kernel on the tensor cores; this
+// kernel then only does the convolutional part: dV = dv_part + conv^T(dE), the CRPE weight gradients and the gate sums.
+template <int CH, int WIN, int TX, bool EXT>
 __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                     const bf16* __restrict__ yout, const float* __restrict__ gate,
                                                     const float* __restrict__ A, const float* __restrict__ dA,
@@ -421,7 +423,7 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
         }
     }
     load_taps<CH, WIN>(sW, cw, cg0, G::ACT);
-    for (int e = threadIdx.x; e < (CH / 2) * 32; e += blockDim.x) {
+    for (int e = threadIdx.x; e < (EXT ? 0 : (CH / 2) * 32); e += blockDim.x) {
         const int jj = e >> 5, l = e & 31;
         float4 at = make_float4(0.f, 0.f, 0.f, 0.f), da = at, dat = at;
         if (l < G::ACT) {
@@ -456,10 +458,12 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
         bias.y = __ldg(bp);
         const size_t bc = (size_t)b * C + c0;
         if (gate) gt = *reinterpret_cast<const float2*>(gate + bc);
-        km = *reinterpret_cast<const float2*>(kmax + bc);
-        const float2 z = *reinterpret_cast<const float2*>(zsum + bc);
-        zi = make_float2(1.f / z.x, 1.f / z.y);
-        rr = *reinterpret_cast<const float2*>(rk + bc);
+        if (!EXT) {
+            km = *reinterpret_cast<const float2*>(kmax + bc);
+            const float2 z = *reinterpret_cast<const float2*>(zsum + bc);
+            zi = make_float2(1.f / z.x, 1.f / z.y);
+            rr = *reinterpret_cast<const float2*>(rk + bc);
+        }
     }
     __syncthreads();
     const int nstrips = g.th * g.nsx;
@@ -471,14 +475,17 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
         const size_t n0 = (size_t)(g.ty0 + py) * Wd + g.tx0 + px0;
         // this strip's own pixels: issued before the convolution loop so their latency hides behind the math
         uint32_t kw[TX], dw[TX], yw[TX], ew[TX], vw[TX];
+        float2 dvp[TX];
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
             const bool ok = act && px0 + t < g.tw;
-            kw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + C + c0) : 0u;
-            vw[t] = ok ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + 2 * C + c0) : 0u;
-            dw[t] = ok ? *reinterpret_cast<const uint32_t*>(dy_b + (n0 + t) * C + c0) : 0u;
-            ew[t] = ok ? *reinterpret_cast<const uint32_t*>(ein + ((size_t)b * N + n0 + t) * C + c0) : 0u;
+            kw[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + C + c0) : 0u;
+            vw[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + 2 * C + c0) : 0u;
+            dw[t] = (ok && (!EXT || gate)) ? *reinterpret_cast<const uint32_t*>(dy_b + (n0 + t) * C + c0) : 0u;
+            ew[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(ein + ((size_t)b * N + n0 + t) * C + c0) : 0u;
             yw[t] = (ok && gate) ? *reinterpret_cast<const uint32_t*>(yout + ((size_t)b * N + n0 + t) * C + c0) : 0u;
+            // (the mat-vec part of dV was parked, as bf16, in the dV slot of dqkv by attn_mm_bwd_kernel)
+            dvp[t] = (ok && EXT) ? up2(*reinterpret_cast<const uint32_t*>(dqkv + ((size_t)b * N + n0 + t) * 3 * C + 2 * C + c0)) : make_float2(0.f, 0.f);
         }
         // transposed convolution of dE (flipped taps): dV_conv[n] = sum_ij w[i,j] dE[n - (i-R, j-R)]
         float2 tc[TX];
@@ -496,6 +503,20 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
 #pragma unroll
                 for (int t = 0; t < TX; ++t) tc[t] = fma2(wf, ine[t + j], tc[t]);
             }
+        }
+        if (EXT) {
+            // dQ, dK and the mat-vec part of dV come from attn_mm_bwd_kernel: finish dV, the gate sums and the bias sums
+            if (act) {
+#pragma unroll
+                for (int t = 0; t < TX; ++t) {
+                    if (px0 + t >= g.tw) break;
+                    gacc = fma2(up2(dw[t]), up2(yw[t]), gacc);
+                    const float2 dv = make_float2(dvp[t].x + tc[t].x, dvp[t].y + tc[t].y);
+                    bv.x += dv.x; bv.y += dv.y;
+                    *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * N + n0 + t) * 3 * C + 2 * C + c0) = f2_to_bf2(dv.x, dv.y);
+                }
+            }
+            continue;
         }
         float2 e[TX];
 #pragma unroll
@@ -558,10 +579,12 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
         atomicAdd(dgate + (size_t)b * C + c0 + 1, gacc.y / gt.y);
     }
     if (dbias_qkv && act) {
-        atomicAdd(dbias_qkv + c0, bq.x);
-        atomicAdd(dbias_qkv + c0 + 1, bq.y);
-        atomicAdd(dbias_qkv + C + c0, bk.x);
-        atomicAdd(dbias_qkv + C + c0 + 1, bk.y);
+        if (!EXT) {
+            atomicAdd(dbias_qkv + c0, bq.x);
+            atomicAdd(dbias_qkv + c0 + 1, bq.y);
+            atomicAdd(dbias_qkv + C + c0, bk.x);
+            atomicAdd(dbias_qkv + C + c0 + 1, bk.y);
+        }
         atomicAdd(dbias_qkv + 2 * C + c0, bv.x);
         atomicAdd(dbias_qkv + 2 * C + c0 + 1, bv.y);
     }
@@ -622,6 +645,195 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward mat-vecs on tensor cores
+// For Ch >= 40 (stages 2 and 3) the three per-head contractions of the backward,
+//     T1 = dF A^T  (-> dQ = s T1 + dF*E),   T2 = V dA^T  (-> dK = S*(T2 - r)),   T3 = S dA  (-> mat-vec part of dV),
+// cost 3*Ch^2 multiply-adds per token and head: as shuffled FFMA2 mat-vecs they were 60-65% of attn_bwd_strip_kernel<40/64>.
+// Here a warp takes 16 tokens of one head and runs them as bf16 mma.sync m16n8k16 (fp32 accumulate): the token rows are the
+// A fragments (loaded straight from global memory in fragment layout), the Ch x Ch matrices (A, dA, dA^T as bf16 in shared
+// memory, row pitch padded against bank conflicts) the B fragments.  S = softmax_N(K) is computed once in A-fragment layout,
+// which for m16n8k16 coincides with the accumulator layout of n-tiles (2t, 2t+1): the same registers serve as the A operand
+// of T3 and as the elementwise factor of dK.  dQ and dK are final here; the mat-vec part of dV is parked (bf16) in the dV
+// slot of dqkv for attn_bwd_strip_kernel<CH, EXT> to add the transposed convolution.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+                                                          const bf16* __restrict__ ein, const float* __restrict__ gate,
+                                                          const float* __restrict__ A, const float* __restrict__ dA,
+                                                          const float* __restrict__ rk, const float* __restrict__ kmax,
+                                                          const float* __restrict__ zsum, bf16* __restrict__ dqkv,
+                                                          float* __restrict__ dbias_qkv, float scale, int N, int C) {
+    MDV_PDL_SYNC();
+    constexpr int KS = (CH + 15) / 16;      // k-steps of 16
+    constexpr int NT = CH / 8;              // n-tiles of 8
+    constexpr int LD = KS * 16 + 8;         // shared-memory row pitch (bf16): +8 keeps the fragment loads conflict-free
+    __shared__ __align__(16) bf16 sA[CH * LD], sdA[CH * LD], sdAt[CH * LD];
+    __shared__ float sbias[2][CH];
+    __shared__ float srk[CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const size_t hbase = ((size_t)b * C + h * CH) * CH;
+    for (int e = threadIdx.x; e < CH * LD; e += blockDim.x) {
+        const int r = e / LD, c = e % LD;
+        const bool in = c < CH;
+        sA[e] = __float2bfloat16_rn(in ? A[hbase + (size_t)r * CH + c] : 0.f);
+        sdA[e] = __float2bfloat16_rn(in ? dA[hbase + (size_t)r * CH + c] : 0.f);
+        sdAt[e] = __float2bfloat16_rn(in ? dA[hbase + (size_t)c * CH + r] : 0.f);
+    }
+    for (int e = threadIdx.x; e < 2 * CH; e += blockDim.x) (&sbias[0][0])[e] = 0.f;
+    __syncthreads();
+    // r_k = sum_n S[n,k] dS[n,k] = sum_v A[k,v] dA[k,v] — with the SAME bf16-rounded dA the mat-vec below uses, so that
+    // sum_n dK[n,k] = sum_n S (dS - r) still cancels to fp32 round-off (the softmax over tokens is shift-invariant: the K bias
+    // has an identically-zero gradient, and AdamW would turn a 2^-9-sized residual into +-lr steps); `rk` is the fp32 one
+    for (int k = threadIdx.x; k < CH; k += blockDim.x) {
+        float r = 0.f;
+        for (int v = 0; v < CH; ++v) r = fmaf(A[hbase + (size_t)k * CH + v], __bfloat162float(sdA[k * LD + v]), r);
+        srk[k] = r;
+    }
+    __syncthreads();
+    const int n0 = blockIdx.x * 64 + warp * 16;           // first token of this warp
+    const int cb = b * C + h * CH;                        // index of this head's first channel in [B, C] tables
+    const int row[2] = {n0 + gid, n0 + gid + 8};
+    const bool rok[2] = {row[0] < N, row[1] < N};
+    // ---- A fragments: dy (-> dF), k (-> S), v; column c = 16 t + 8 hf + 2 tig (+1); zero outside the head / the image
+    uint32_t fdf[KS][4], fs[KS][4], fv[KS][4];
+    float2 s32[KS][4];                                    // S in fp32, same layout (elementwise factor of dK)
+#pragma unroll
+    for (int t = 0; t < KS; ++t) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                     // q = 2 hf + r: fragment register order (r0,c0) (r1,c0) (r0,c8) (r1,c8)
+            const int r = q & 1, hf = q >> 1;
+            const int c = 16 * t + 8 * hf + 2 * tig;
+            const bool ok = rok[r] && c < CH;
+            uint32_t dw = 0u, kw = 0u, vw = 0u;
+            if (ok) {
+                const size_t tok = (size_t)b * N + row[r];
+                dw = *reinterpret_cast<const uint32_t*>(dy + tok * C + h * CH + c);
+                kw = *reinterpret_cast<const uint32_t*>(qkv + tok * 3 * C + C + h * CH + c);
+                vw = *reinterpret_cast<const uint32_t*>(qkv + tok * 3 * C + 2 * C + h * CH + c);
+            }
+            float2 g = make_float2(1.f, 1.f), km = make_float2(0.f, 0.f), zi = make_float2(0.f, 0.f);
+            if (c < CH) {
+                if (gate) g = *reinterpret_cast<const float2*>(gate + cb + c);
+                km = *reinterpret_cast<const float2*>(kmax + cb + c);
+                const float2 z = *reinterpret_cast<const float2*>(zsum + cb + c);
+                zi = make_float2(1.f / z.x, 1.f / z.y);
+            }
+            const float2 d = up2(dw), kk = up2(kw);
+            fdf[t][q] = f2_to_bf2(g.x * d.x, g.y * d.y);
+            const float2 sv = ok ? make_float2(__expf(kk.x - km.x) * zi.x, __expf(kk.y - km.y) * zi.y) : make_float2(0.f, 0.f);
+            s32[t][q] = sv;
+            fs[t][q] = f2_to_bf2(sv.x, sv.y);
+            fv[t][q] = vw;
+        }
+    }
+    const uint32_t* wA = reinterpret_cast<const uint32_t*>(sA);
+    const uint32_t* wdA = reinterpret_cast<const uint32_t*>(sdA);
+    const uint32_t* wdAt = reinterpret_cast<const uint32_t*>(sdAt);
+    auto bfrag = [&](const uint32_t* m, int j, int t, uint32_t& b0, uint32_t& b1) {
+        const int o = ((8 * j + gid) * LD + 16 * t + 2 * tig) >> 1;      // 32-bit word index
+        b0 = m[o];
+        b1 = m[o + 4];
+    };
+    float bq[NT][2], bk[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) bq[j][0] = bq[j][1] = bk[j][0] = bk[j][1] = 0.f;
+    // ---- T1 -> dQ = s T1 + dF * E
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < KS; ++t) {
+            uint32_t b0, b1;
+            bfrag(wA, j, t, b0, b1);
+            mma_bf16_16816(acc, fdf[t], b0, b1);
+        }
+        const int c = 8 * j + 2 * tig;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!rok[r]) continue;
+            const size_t tok = (size_t)b * N + row[r];
+            const float2 e = up2(*reinterpret_cast<const uint32_t*>(ein + tok * C + h * CH + c));
+            const float2 df = up2(fdf[j >> 1][2 * (j & 1) + r]);
+            const float qx = fmaf(scale, acc[2 * r], df.x * e.x), qy = fmaf(scale, acc[2 * r + 1], df.y * e.y);
+            bq[j][0] += qx;
+            bq[j][1] += qy;
+            *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + h * CH + c) = f2_to_bf2(qx, qy);
+        }
+    }
+    // ---- T2 -> dK = S * (T2 - r)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < KS; ++t) {
+            uint32_t b0, b1;
+            bfrag(wdA, j, t, b0, b1);
+            mma_bf16_16816(acc, fv[t], b0, b1);
+        }
+        const int c = 8 * j + 2 * tig;
+        const float2 rr = make_float2(srk[c], srk[c + 1]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!rok[r]) continue;
+            const size_t tok = (size_t)b * N + row[r];
+            const float2 sv = s32[j >> 1][2 * (j & 1) + r];
+            const float kx = sv.x * (acc[2 * r] - rr.x), ky = sv.y * (acc[2 * r + 1] - rr.y);
+            bk[j][0] += kx;
+            bk[j][1] += ky;
+            *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + C + h * CH + c) = f2_to_bf2(kx, ky);
+        }
+    }
+    // ---- T3 -> mat-vec part of dV, parked in the dV slot
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < KS; ++t) {
+            uint32_t b0, b1;
+            bfrag(wdAt, j, t, b0, b1);
+            mma_bf16_16816(acc, fs[t], b0, b1);
+        }
+        const int c = 8 * j + 2 * tig;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!rok[r]) continue;
+            const size_t tok = (size_t)b * N + row[r];
+            *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + 2 * C + h * CH + c) = f2_to_bf2(acc[2 * r], acc[2 * r + 1]);
+        }
+    }
+    // ---- bias-gradient column sums of dQ and dK: over the 8 row groups of the warp, then the block, then one atomic per column
+    if (dbias_qkv) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float a = bq[j][u], k2 = bk[j][u];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    k2 += __shfl_xor_sync(0xffffffffu, k2, o);
+                }
+                if (gid == 0) {
+                    atomicAdd(&sbias[0][8 * j + 2 * tig + u], a);
+                    atomicAdd(&sbias[1][8 * j + 2 * tig + u], k2);
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2 * CH; e += blockDim.x) {
+            const int which = e / CH, c = e % CH;
+            atomicAdd(dbias_qkv + which * C + h * CH + c, sbias[which][c]);
+        }
+    }
+}
+
 // One launch covers every channel group; the window of a group (that of its last head) selects the instantiation.
 template <int CH>
 __device__ __forceinline__ int win_of_group(int grp) { return win_of_head(((grp + 1) * Cfg<CH>::CPW - 1) / CH); }
@@ -641,7 +853,7 @@ __global__ void __launch_bounds__(256) attn_fwd_strip_kernel(const bf16* __restr
 constexpr int BWD_THREADS = 512;   // 16 warps share one tile: twice the latency hiding of 8 (the kernel is register/latency bound)
 constexpr int BWD_TX = 4;          // 4-pixel strips keep the per-thread arrays within 128 registers
 
-template <int CH>
+template <int CH, bool EXT>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                               const bf16* __restrict__ yout, const float* __restrict__ gate,
                                                               const float* __restrict__ A, const float* __restrict__ dA,
@@ -653,9 +865,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf
     MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
-    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
-    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
-    else attn_bwd_strip_body<CH, 7, BWD_TX>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
+    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX, EXT>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
+    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX, EXT>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
+    else attn_bwd_strip_body<CH, 7, BWD_TX, EXT>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -694,11 +906,17 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
     const int smem = cg.w[0] ? full : full - tile_words(7) * 4;
     static bool configured = false;
     if (!configured) {
-        int rc = set_smem(attn_bwd_strip_kernel<CH>, full);
+        int rc = set_smem(attn_bwd_strip_kernel<CH, (CH >= 40)>, full);
         if (rc) return rc;
         configured = true;
     }
-    mdv_launch(attn_bwd_strip_kernel<CH>, dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv,
+    constexpr bool EXT = CH >= 40;      // stages 2 / 3: the mat-vecs run on the tensor cores first
+    if (EXT) {
+        mdv_launch(attn_mm_bwd_kernel<CH>, dim3(mdv_cdiv(H * W, 64), C / CH, B), dim3(128), 0, st, qkv, dy, ein, gate, A, dA, rk, kmax, zsum, dqkv, dbias_qkv,
+                   scale, H * W, C);
+        MDV_CHECK_LAUNCH();
+    }
+    mdv_launch((attn_bwd_strip_kernel<CH, EXT>), dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv,
                                                                                        dgate, dbias_qkv, scale, H, W, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
