@@ -133,6 +133,7 @@ int mdv_bn_act_bwd_grouped(const float* dy, const float* z, const float* mean, c
 /* Same with a rank-1 output gradient dy[m,c] = dlog[m] * wrow[c] * dropout2d_mask(m / rows_per_sample, c) generated on the
  * fly: the backward of Dropout2d + the 1-channel `linear_out` head of MLPDecoderFM (Decoders.py:334-337) never
  * materialises the [M, C] gradient of the BatchNorm output. */
+/* (ws here: >= 3*C doubles + (M / rows_per_sample)*C floats) */
 int mdv_bn_act_bwd_rank1(const float* dlog, const float* wrow, int rows_per_sample, float drop_p, const void* rng,
                          uint32_t drop_stream, const float* z, const float* mean, const float* rstd, const float* gamma,
                          const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
@@ -159,8 +160,9 @@ int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int
 /* bilinear resize, align_corners=False (mdvit.py:699; Decoders.py:196,319-336) and its exact transpose */
 int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* out, int out_bf16, int ld_out, int B, int Hi, int Wi, int Ho,
                      int Wo, int C, void* stream);
+/* ws: optional scratch of B*Ho*Wi*C floats; with it, integer factors 4 and 8 use the separable two-pass form */
 int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, float* din, int ld_in, int B, int Hi, int Wi, int Ho, int Wo,
-                     int C, void* stream);
+                     int C, float* ws, void* stream);
 
 /* ------------------------------------------------------------------ factorized attention + CRPE + DA gate */
 long long mdv_attn_stats_floats(int B, int C, int heads); /* floats of `stats` (column max, softmax denominators, K^T V): kept for backward */

@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ A, const float* __restrict__ dA,
                                                           const float* __restrict__ rk, const float* __restrict__ kmax,
                                                           const float* __restrict__ zsum, bf16* __restrict__ dqkv,
-                                                          float* __restrict__ dbias_qkv, float scale, int N, int C) {
+                                                          float* __restrict__ dbias_qkv, float scale, int N, int C, int tok_per_cta) {
     MDV_PDL_SYNC();
     constexpr int KS = (CH + 15) / 16;      // k-steps of 16
     constexpr int NT = CH / 8;              // n-tiles of 8
@@ -697,10 +697,23 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
         srk[k] = r;
     }
     __syncthreads();
-    const int n0 = blockIdx.x * 64 + warp * 16;           // first token of this warp
+    float bq[NT][2], bk[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) bq[j][0] = bq[j][1] = bk[j][0] = bk[j][1] = 0.f;
     const int cb = b * C + h * CH;                        // index of this head's first channel in [B, C] tables
+    const uint32_t* wA = reinterpret_cast<const uint32_t*>(sA);
+    const uint32_t* wdA = reinterpret_cast<const uint32_t*>(sdA);
+    const uint32_t* wdAt = reinterpret_cast<const uint32_t*>(sdAt);
+    auto bfrag = [&](const uint32_t* m, int j, int t, uint32_t& b0, uint32_t& b1) {
+        const int o = ((8 * j + gid) * LD + 16 * t + 2 * tig) >> 1;      // 32-bit word index
+        b0 = m[o];
+        b1 = m[o + 4];
+    };
+    // a CTA owns `tok_per_cta` tokens of this (image, head): the matrix staging above is amortised over all of them
+    const int t_begin = blockIdx.x * tok_per_cta, t_end = min(N, t_begin + tok_per_cta);
+    for (int n0 = t_begin + warp * 16; n0 < t_end; n0 += 4 * 16) {
     const int row[2] = {n0 + gid, n0 + gid + 8};
-    const bool rok[2] = {row[0] < N, row[1] < N};
+    const bool rok[2] = {row[0] < t_end, row[1] < t_end};
     // ---- A fragments: dy (-> dF), k (-> S), v; column c = 16 t + 8 hf + 2 tig (+1); zero outside the head / the image
     uint32_t fdf[KS][4], fs[KS][4], fv[KS][4];
     float2 s32[KS][4];                                    // S in fp32, same layout (elementwise factor of dK)
@@ -733,17 +746,6 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
             fv[t][q] = vw;
         }
     }
-    const uint32_t* wA = reinterpret_cast<const uint32_t*>(sA);
-    const uint32_t* wdA = reinterpret_cast<const uint32_t*>(sdA);
-    const uint32_t* wdAt = reinterpret_cast<const uint32_t*>(sdAt);
-    auto bfrag = [&](const uint32_t* m, int j, int t, uint32_t& b0, uint32_t& b1) {
-        const int o = ((8 * j + gid) * LD + 16 * t + 2 * tig) >> 1;      // 32-bit word index
-        b0 = m[o];
-        b1 = m[o + 4];
-    };
-    float bq[NT][2], bk[NT][2];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) bq[j][0] = bq[j][1] = bk[j][0] = bk[j][1] = 0.f;
     // ---- T1 -> dQ = s T1 + dF * E
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -807,6 +809,7 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
             const size_t tok = (size_t)b * N + row[r];
             *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + 2 * C + h * CH + c) = f2_to_bf2(acc[2 * r], acc[2 * r + 1]);
         }
+    }
     }
     // ---- bias-gradient column sums of dQ and dK: over the 8 row groups of the warp, then the block, then one atomic per column
     if (dbias_qkv) {
@@ -912,8 +915,11 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
     }
     constexpr bool EXT = CH >= 40;      // stages 2 / 3: the mat-vecs run on the tensor cores first
     if (EXT) {
-        mdv_launch(attn_mm_bwd_kernel<CH>, dim3(mdv_cdiv(H * W, 64), C / CH, B), dim3(128), 0, st, qkv, dy, ein, gate, A, dA, rk, kmax, zsum, dqkv, dbias_qkv,
-                   scale, H * W, C);
+        // tokens per CTA: the whole image up to 512 (more CTAs only while the grid would not fill the machine)
+        int tpc = 64;
+        while (tpc < 512 && (long long)mdv_cdiv(H * W, tpc) * (C / CH) * B > 4 * MDV_NUM_SMS) tpc *= 2;
+        mdv_launch(attn_mm_bwd_kernel<CH>, dim3(mdv_cdiv(H * W, tpc), C / CH, B), dim3(128), 0, st, qkv, dy, ein, gate, A, dA, rk, kmax, zsum, dqkv, dbias_qkv,
+                   scale, H * W, C, tpc);
         MDV_CHECK_LAUNCH();
     }
     mdv_launch((attn_bwd_strip_kernel<CH, EXT>), dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv,

@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict
     TO* oimg = out + (size_t)blockIdx.z * H * L;
     Row3 r0 = load_row3(img + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
     Row3 r1 = load_row3(img + (size_t)y0 * L, p, C, true, left_ok, right_ok);
-    for (int y = y0; y < y1; ++y) {
+#pragma unroll 4
+    for (int y = y0; y < y1; ++y) {      // (unrolled: the loads of the next rows are independent of the arithmetic: more bytes in flight)
         const Row3 r2 = load_row3(img + (size_t)(y + 1) * L, p, C, y + 1 < H, left_ok, right_ok);
         float4 acc = bv;
         fma4(acc, wv[0], r0.l); fma4(acc, wv[1], r0.m); fma4(acc, wv[2], r0.r);
@@ -715,6 +716,71 @@ __global__ void __launch_bounds__(256) upsample_bwd_int_kernel(const TI* __restr
     }
 }
 
+// Separable form of the same transposed resize for the larger factors: a horizontal pass into an fp32 scratch
+// tmp[B, Ho, Wi, C] (every output pixel read by 2 input columns instead of the 2x2 = 4 input pixels of the one-pass kernel,
+// which was L2-bandwidth bound on its 4x re-reads), then a vertical pass over the S-times smaller scratch.
+template <typename TI, int S>
+__global__ void __launch_bounds__(256) upsample_bwd_h_kernel(const TI* __restrict__ dout, int ld_out, float* __restrict__ tmp, int B,
+                                                              int Ho, int Wi, int C) {
+    MDV_PDL_SYNC();
+    const int Wo = Wi * S;
+    const int cvn = C >> 2;
+    const float sc = 1.f / S;
+    const int total = B * Ho * Wi * cvn;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = (idx % cvn) * 4;
+        const int pix = idx / cvn;            // (b, y, xi)
+        const int xi = pix % Wi;
+        const int row = pix / Wi;             // b * Ho + y
+        const int xa = S * xi - S / 2;
+        const TI* prow = dout + (size_t)row * Wo * ld_out + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 2 * S; ++k) {
+            const int x = xa + k;
+            if (x < 0 || x >= Wo) continue;
+            int x0, x1;
+            float lx;
+            bil_src(x, sc, Wi, x0, x1, lx);
+            const float wgt = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+            const float4 v = ld4(prow + (size_t)x * ld_out);
+            acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+        }
+        st4(tmp + (size_t)pix * C + c, acc);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) upsample_bwd_v_kernel(const float* __restrict__ tmp, float* __restrict__ din, int ld_in, int B,
+                                                              int Hi, int Wi, int C) {
+    MDV_PDL_SYNC();
+    const int Ho = Hi * S;
+    const int cvn = C >> 2;
+    const float sc = 1.f / S;
+    const int total = B * Hi * Wi * cvn;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = (idx % cvn) * 4;
+        const int pix = idx / cvn;
+        const int xi = pix % Wi;
+        const int yi = (pix / Wi) % Hi;
+        const int b = pix / (Wi * Hi);
+        const int ya = S * yi - S / 2;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 2 * S; ++r) {
+            const int y = ya + r;
+            if (y < 0 || y >= Ho) continue;
+            int y0, y1;
+            float ly;
+            bil_src(y, sc, Hi, y0, y1, ly);
+            const float wgt = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+            const float4 v = ld4(tmp + ((size_t)(b * Ho + y) * Wi + xi) * C + c);
+            acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+        }
+        st4(din + (size_t)pix * ld_in + c, acc);
+    }
+}
+
 inline int grid_for(long long total_threads) {
     long long b = (total_threads + 255) / 256;
     const long long cap = (long long)MDV_NUM_SMS * 16;
@@ -739,7 +805,9 @@ extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, v
     const size_t smem = (size_t)10 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     if (stride == 1 && Hi == Ho && Wi == Wo) {
-        const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
+        // rows per thread: long segments amortise the 36 weight loads and the 2 halo rows, as long as the grid still fills the SMs
+        int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
+        while (seg < Hi && seg < 64 && (long long)mdv_cdiv((long long)Wi * C, 1024) * mdv_cdiv(Hi, 2 * seg) * B >= 4 * MDV_NUM_SMS) seg *= 2;
         dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
         if (out_bf16) mdv_launch(dwconv3_s1_kernel<bf16>, dim3(grid), dim3(256), 0, st, in, w, bias, (bf16*)out, Hi, Wi, C, transposed, residual, seg);
         else mdv_launch(dwconv3_s1_kernel<float>, dim3(grid), dim3(256), 0, st, in, w, bias, (float*)out, Hi, Wi, C, transposed, residual, seg);
@@ -885,7 +953,7 @@ extern "C" int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* ou
 
 // din[B,Hi,Wi,C] (fp32, overwritten) = resize^T(dout[B,Ho,Wo,C])
 extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, float* din, int ld_in, int B, int Hi, int Wi, int Ho,
-                                int Wo, int C, void* stream) {
+                                int Wo, int C, float* ws, void* stream) {
     if (!dout || !din || B <= 0) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * Ho * Wo * (ld_out > C ? ld_out : C))) return MDV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -898,6 +966,19 @@ extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, flo
     if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
     const int g = grid_for((long long)B * Hi * Wi * (C / 4));
     const int S = (Ho % Hi == 0 && Wo % Wi == 0 && Ho / Hi == Wo / Wi) ? Ho / Hi : 0;
+    if (ws && (S == 4 || S == 8) && fits_i32((long long)B * Ho * Wi * C)) {
+        // separable two-pass form (scratch: B*Ho*Wi*C floats)
+        const int gh = grid_for((long long)B * Ho * Wi * (C / 4));
+#define MDV_UPH(SS)                                                                                                                  \
+    if (dout_bf16) mdv_launch((upsample_bwd_h_kernel<bf16, SS>), dim3(gh), dim3(256), 0, st, (const bf16*)dout, ld_out, ws, B, Ho, Wi, C);     \
+    else mdv_launch((upsample_bwd_h_kernel<float, SS>), dim3(gh), dim3(256), 0, st, (const float*)dout, ld_out, ws, B, Ho, Wi, C);             \
+    MDV_CHECK_LAUNCH();                                                                                                              \
+    mdv_launch((upsample_bwd_v_kernel<SS>), dim3(g), dim3(256), 0, st, (const float*)ws, din, ld_in, B, Hi, Wi, C);
+        if (S == 4) { MDV_UPH(4) } else { MDV_UPH(8) }
+#undef MDV_UPH
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     if ((S == 2 || S == 4 || S == 8) && (long long)B * Hi * Wi * (C / 4) < 0x7fffffffLL) {
 #define MDV_UPB(SS)                                                                                                              \
     if (dout_bf16) mdv_launch((upsample_bwd_int_kernel<bf16, SS>), dim3(g), dim3(256), 0, st, (const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, C);     \

@@ -277,6 +277,7 @@ struct Rank1Dy {
     int rps;                // rows per sample
     float drop_p;
     uint32_t stream;
+    const float* wtab;      // [samples, C] = wrow[c] * dropout2d_mask(b, c), precomputed once per call (vectorised kernels)
 };
 __device__ __forceinline__ float rank1_wm(const Rank1Dy& r1, int b, int c, int C) {
     float wv = __ldg(r1.wrow + c);
@@ -404,6 +405,13 @@ __device__ __forceinline__ float4 rank1_w4(const Rank1Dy& r1, int b, int c, int 
     return w;
 }
 
+__global__ void rank1_table_kernel(Rank1Dy r1, float* __restrict__ wtab, int samples, int C) {
+    MDV_PDL_SYNC();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= samples * C) return;
+    *reinterpret_cast<float4*>(wtab + i) = rank1_w4(r1, i / C, i % C, C);
+}
+
 template <bool BWD, bool RANK1 = false>
 __global__ void __launch_bounds__(256) bn_reduce_g_kernel(const float* __restrict__ a, const float* __restrict__ z,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(256) bn_reduce_g_kernel(const float* __restric
                         const int bb = rr / rk.rps;
                         if (bb != cur_b) {
                             cur_b = bb;
-                            wm = rank1_w4(rk, bb, 4 * cl, C);
+                            wm = *reinterpret_cast<const float4*>(rk.wtab + (size_t)bb * C + 4 * cl);
                         }
                         const float dl = __ldg(rk.dlog + rr);
                         dv[u] = make_float4(dl * wm.x, dl * wm.y, dl * wm.z, dl * wm.w);
@@ -565,7 +573,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_g_kernel(const float* __rest
     if (RANK1) {
         const int row = i / C;
         const float dl = __ldg(r1.dlog + row);
-        const float4 w = rank1_w4(r1, row / r1.rps, c, C);
+        const float4 w = *reinterpret_cast<const float4*>(r1.wtab + (size_t)(row / r1.rps) * C + c);
         dv = make_float4(dl * w.x, dl * w.y, dl * w.z, dl * w.w);
     } else {
         dv = *reinterpret_cast<const float4*>(dy + i);
@@ -737,7 +745,7 @@ extern "C" int mdv_bn_act_bwd_rank1(const float* dlog, const float* wrow, int ro
                                     void* ws, void* stream) {
     if (!dlog || !wrow || !z || !dz || !ws || M <= 0 || (C & 3) || rows_per_sample <= 0) return MDV_ERR_ARG;
     if ((long long)M * C >= 0x7fffffffLL || (long long)(M / rows_per_sample + 1) * C >= 0x7fffffffLL) return MDV_ERR_UNSUPPORTED;
-    Rank1Dy r1 = {dlog, wrow, (const unsigned long long*)rng, rows_per_sample, drop_p, drop_stream};
+    Rank1Dy r1 = {dlog, wrow, (const unsigned long long*)rng, rows_per_sample, drop_p, drop_stream, nullptr};
     return bn_act_bwd_impl(nullptr, r1, z, mean, rstd, gamma, beta, act, dz, dz_bf16, dgamma, dbeta, M, C, ws, (cudaStream_t)stream);
 }
 
@@ -746,15 +754,22 @@ static bool bn_grouped_ok(int G, int Mg, int C);
 static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, const float* mean, const float* rstd, const float* gamma,
                            const float* beta, int act, void* dz, int dz_bf16, float* dgamma, float* dbeta, int M, int C, void* ws,
                            cudaStream_t st) {
-    if (r1.dlog && bn_grouped_ok(1, M, C)) {
-        // rank-1 output gradient through the float4 / 4-rows-in-flight kernels (one group)
+    if (r1.dlog && bn_grouped_ok(1, M, C) && M % r1.rps == 0) {
+        // rank-1 output gradient through the float4 / 4-rows-in-flight kernels (one group); the per-(sample, channel) factor
+        // wrow[c] * dropout2d mask is tabulated once (ws: 3*C doubles + samples*C floats)
         double* sums = (double*)ws;
         float* coef = (float*)(sums + 2 * C);
+        float* wtab = (float*)(sums + 3 * C);
+        const int samples = M / r1.rps;
         cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
         if (e != cudaSuccess) return (int)e;
+        Rank1Dy rt = r1;
+        rt.wtab = wtab;
+        mdv_launch(rank1_table_kernel, dim3(mdv_cdiv(samples * C / 4, 256)), dim3(256), 0, st, r1, wtab, samples, C);
+        MDV_CHECK_LAUNCH();
         const int rpb = grouped_rows_per_block(M, C, 1);
         mdv_launch((bn_reduce_g_kernel<true, true>), dim3(mdv_cdiv(M, rpb), 1, 1), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
-                   sums, M, C, rpb, r1);
+                   sums, M, C, rpb, rt);
         MDV_CHECK_LAUNCH();
         mdv_launch(bn_bwd_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)sums, 1, M, C, coef, dgamma, dbeta);
         MDV_CHECK_LAUNCH();
@@ -762,10 +777,10 @@ static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, c
         const int blocks = mdv_cdiv(total / 4, 256);
         if (dz_bf16)
             mdv_launch((bn_bwd_apply_g_kernel<bf16, true>), dim3(blocks), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
-                       (const float*)coef, (bf16*)dz, total, C, M * C, r1);
+                       (const float*)coef, (bf16*)dz, total, C, M * C, rt);
         else
             mdv_launch((bn_bwd_apply_g_kernel<float, true>), dim3(blocks), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
-                       (const float*)coef, (float*)dz, total, C, M * C, r1);
+                       (const float*)coef, (float*)dz, total, C, M * C, rt);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }

@@ -310,7 +310,9 @@ def upsample_fwd(x, out, B, Hi, Wi, Ho, Wo, C, ld_in=None, ld_out=None):
 
 def upsample_bwd(dout, B, Hi, Wi, Ho, Wo, C, ld_out=None):
     din = torch.empty((B * Hi * Wi, C), dtype=F32, device=dout.device)
-    check(L.lib().mdv_upsample_bwd(ptr(dout), int(dout.dtype == BF16), ld_out or C, ptr(din), C, B, Hi, Wi, Ho, Wo, C, L.stream()),
+    # separable two-pass form for the 4x / 8x resizes of wide tensors (the aux decoder's 512-channel maps)
+    ws = torch.empty(B * Ho * Wi * C, dtype=F32, device=dout.device) if (C >= 64 and Ho == Wo and Hi == Wi and Ho // Hi in (4, 8) and Ho % Hi == 0) else None
+    check(L.lib().mdv_upsample_bwd(ptr(dout), int(dout.dtype == BF16), ld_out or C, ptr(din), C, B, Hi, Wi, Ho, Wo, C, ptr(ws), L.stream()),
           "mdv_upsample_bwd")
     return din
 
@@ -942,7 +944,7 @@ class AuxFn(torch.autograd.Function):
                                          ptr(rng_tensor(dev)) if p2 > 0 else None, sid, L.stream()), "mdv_rowdot_bwd")
             # BatchNorm backward with d(a5)[m,c] = dlo[m] * w_out[c] * dropout2d_mask generated on the fly
             dz = torch.empty((M0, hc), dtype=BF16, device=dev)
-            ws_bn = torch.empty(3 * hc, dtype=torch.float64, device=dev)
+            ws_bn = torch.empty(3 * hc + (B * hc + 1) // 2, dtype=torch.float64, device=dev)
             g_g, rg = gtarget(g)
             g_b, rb = gtarget(b)
             check(lib.mdv_bn_act_bwd_rank1(ptr(dlo), ptr(ow), H * W, ctypes.c_float(p2), ptr(rng_tensor(dev)) if p2 > 0 else None, sid,

@@ -401,7 +401,11 @@ def test_bilinear_resize_and_transpose(env, hi, ho, C):
     dy = torch.randn(B, ho, ho, C, device=dev)
     (ref * dy).sum().backward()
     dx = torch.empty(B, hi, hi, C, device=dev)
-    L.check(lib.mdv_upsample_bwd(L.ptr(dy), 0, C, L.ptr(dx), C, B, hi, hi, ho, ho, C, L.stream()), "up_b")
+    L.check(lib.mdv_upsample_bwd(L.ptr(dy), 0, C, L.ptr(dx), C, B, hi, hi, ho, ho, C, None, L.stream()), "up_b")
+    if C % 4 == 0 and ho % hi == 0 and ho // hi in (4, 8):        # separable two-pass form: same result
+        dx2, ws = torch.empty_like(dx), torch.empty(B * ho * hi * C, device=dev)
+        L.check(lib.mdv_upsample_bwd(L.ptr(dy), 0, C, L.ptr(dx2), C, B, hi, hi, ho, ho, C, L.ptr(ws), L.stream()), "up_b2")
+        assert rel(dx2, dx) < 1e-5
     assert rel(dx, x.grad) < 1e-5
 
 
@@ -453,7 +457,7 @@ def test_bn_backward_with_rank1_output_gradient(env, p):
     for rank1 in (False, True):
         dz = torch.empty(M, C, device=dev)
         dg, dbt = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-        ws = torch.empty(3 * C, dtype=torch.float64, device=dev)
+        ws = torch.empty(3 * C + (B * C + 1) // 2, dtype=torch.float64, device=dev)      # + the [samples, C] factor table of the rank-1 form
         if rank1:
             L.check(lib.mdv_bn_act_bwd_rank1(L.ptr(dlog), L.ptr(w), HW, p, L.ptr(rng), 9, L.ptr(z), L.ptr(mean), L.ptr(rstd), L.ptr(gam), L.ptr(bet), 2,
                                              L.ptr(dz), 0, L.ptr(dg), L.ptr(dbt), M, C, L.ptr(ws), L.stream()), "bn_bwd_rank1")
