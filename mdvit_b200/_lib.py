@@ -7,7 +7,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdvit_b200.so")
+LIB_PATH = os.environ.get("MDV_LIB_PATH") or os.path.join(_HERE, "libmdvit_b200.so")   # (override: A/B builds during development)
 
 c_void_p, c_int, c_float, c_uint32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint32
 

@@ -44,8 +44,9 @@ __device__ __forceinline__ void crpe_of_channel(const CrpeW& cw, int c, int CH, 
     const int grp = h < 2 ? 0 : (h < 5 ? 1 : 2);
     const int cl = c - (grp == 0 ? 0 : (grp == 1 ? 2 * CH : 5 * CH));
     win = 3 + 2 * grp;
-    w = cw.w[grp] + (size_t)cl * win * win;
-    b = cw.b[grp] + cl;
+    // (selects, not cw.w[grp]: a dynamically indexed kernel parameter is copied to local memory)
+    w = (grp == 0 ? cw.w[0] : (grp == 1 ? cw.w[1] : cw.w[2])) + (size_t)cl * win * win;
+    b = (grp == 0 ? cw.b[0] : (grp == 1 ? cw.b[1] : cw.b[2])) + cl;
 }
 
 // ------------------------------------------------------------------------------------------------ cross-token sums
@@ -351,7 +352,28 @@ __device__ __forceinline__ void attn_fwd_strip_body(const bf16* __restrict__ qkv
 // dgate[b,c] += sum_n dY Y / g ;  dWconv[c,tap] += sum_n dE[n,c] V[n+tap,c] ;  dbconv[c] += sum_n dE[n,c]
 // EXT: the three per-head mat-vecs (and with them dQ and dK) are done by attn_mm_bwd_kernel on the tensor cores; this
 // kernel then only does the convolutional part: dV = dv_part + conv^T(dE), the CRPE weight gradients and the gate sums.
-template <int CH, int WIN, int TX, bool EXT>
+//
+// Shared memory: dE at every halo position as fp32 pairs (no unpacking in the 7x7 loops), V as bf16 pairs (weight-gradient
+// pass only), the FLIPPED taps, the three per-head matrices.  The halo tile has a fixed pitch of TILE_W + WIN - 1 positions,
+// so all position arithmetic is by compile-time constants; FULL = the block's tile is a whole 16 x 16 one (no bounds tests).
+// Pass B (weight gradients) gives every warp ONE kernel row i and a band of tile rows: 7 live accumulators, no division,
+// and the per-warp results are parked over the dE tile and summed in a fixed order (no shared-memory atomics).
+constexpr int BWD_THREADS = 512;   // 16 warps share one tile (register bound: one block per SM)
+constexpr int BWD_TX = 4;          // activation-gradient strips: 4 pixels keep the per-thread arrays within 128 registers
+constexpr int BWD_TXB = 8;         // weight-gradient strips
+#ifndef MDV_MVU
+#define MDV_MVU 2
+#endif
+#ifndef MDV_MVJ
+#define MDV_MVJ 2
+#endif
+constexpr int MVU = MDV_MVU;       // pixels per group of the in-kernel mat-vecs (Ch <= 16)
+constexpr int MVJ = MDV_MVJ;       // unroll of their j loop
+
+template <int WIN>
+__host__ __device__ constexpr int bwd_tile_pos() { return (TILE_H + WIN - 1) * (TILE_W + WIN - 1); }
+
+template <int CH, int WIN, int TX, bool EXT, bool FULL>
 __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                     const bf16* __restrict__ yout, const float* __restrict__ gate,
                                                     const float* __restrict__ A, const float* __restrict__ dA,
@@ -361,69 +383,106 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
                                                     float* __restrict__ dgate, float* __restrict__ dbias_qkv, float scale, int H,
                                                     int Wd, int C, uint8_t* smem_s) {
     using G = Cfg<CH>;
-    const int grp0 = 0;
+    constexpr int NT = BWD_THREADS, NW = NT / 32;
+    constexpr int R = WIN >> 1, PW = TILE_W + WIN - 1, NPOS = bwd_tile_pos<WIN>(), NTAP = WIN * WIN;
     const bool want_w = cg.w[0] != nullptr;
-    // the V tile is only needed by the weight-gradient pass: E = dwconv(V) + b comes saved from the forward
-    uint32_t* sE = reinterpret_cast<uint32_t*>(smem_s);
-    uint32_t* sV = sE + tile_words(WIN);
-    float2* sW = reinterpret_cast<float2*>(sV + (want_w ? tile_words(WIN) : 0));
+    float2* sE = reinterpret_cast<float2*>(smem_s);                  // [NPOS][32] dE, fp32 pairs
+    uint32_t* sV = reinterpret_cast<uint32_t*>(sE + NPOS * 32);      // [NPOS][32] V, bf16 pairs (weight-gradient pass only)
+    float2* sW = reinterpret_cast<float2*>(sV + (want_w ? NPOS * 32 : 0));   // [NTAP][32] flipped taps
     // per (j pair, lane): the two j-values of a matrix entry for each of the lane's two channels v0, v1
-    float4* sAt = reinterpret_cast<float4*>(sW + WIN * WIN * 32);   // (A[v0][2jj],  A[v0][2jj+1],  A[v1][2jj],  A[v1][2jj+1])
+    float4* sAt = reinterpret_cast<float4*>(sW + NTAP * 32);         // (A[v0][2jj],  A[v0][2jj+1],  A[v1][2jj],  A[v1][2jj+1])
     float4* sdA = sAt + (CH / 2) * 32;                               // (dA[2jj][v0], dA[2jj+1][v0], dA[2jj][v1], dA[2jj+1][v1])
     float4* sdAt = sdA + (CH / 2) * 32;                              // (dA[v0][2jj], dA[v0][2jj+1], dA[v1][2jj], dA[v1][2jj+1])
-    float* sG = reinterpret_cast<float*>(sdAt + (CH / 2) * 32);      // [WIN*WIN + 1][64] conv weight / bias gradient accumulators
     const int N = H * Wd;
-    const int b = blockIdx.z, cg0 = (blockIdx.y + grp0) * G::CPW;
+    const int b = blockIdx.z, cg0 = blockIdx.y * G::CPW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const TileGeom g = tile_geom(H, Wd, WIN, TX);
-    const int nwarp = blockDim.x >> 5;
+    int ty0, tx0, th, tw;
+    {
+        const int TH = min(H, TILE_H), TW = min(Wd, TILE_W);
+        const int tiles_x = (Wd + TW - 1) / TW;
+        ty0 = (blockIdx.x / tiles_x) * TH;
+        tx0 = (blockIdx.x % tiles_x) * TW;
+        th = FULL ? TILE_H : min(TH, H - ty0);
+        tw = FULL ? TILE_W : min(TW, Wd - tx0);
+    }
     const bf16* qkv_b = qkv + (size_t)b * N * 3 * C;
     const bf16* dy_b = dy + (size_t)b * N * C;
-    if (want_w) load_halo<G::ACT>(sV, qkv_b + 2 * C, 3 * C, cg0, g, H, Wd);
-    {   // dE = g * dY * Q at every halo position (loads batched: 2 x UB requests in flight per thread)
-        const int total = g.PH * g.PW * 8;
-        constexpr int UB = 4;
-        for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * UB) {
+    const int npos = (th + 2 * R) * PW;
+    {   // staging: a thread always handles the same 8-channel part of a position
+        const int part = threadIdx.x & 7;
+        const bool pact = part * 4 < G::ACT;
+        const int cc = cg0 + part * 8;
+        float2 gg[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            gg[w] = (gate && pact) ? *reinterpret_cast<const float2*>(gate + (size_t)b * C + cc + 2 * w) : make_float2(1.f, 1.f);
+        constexpr int UB = 4, PSTEP = NT / 8;
+        // dE = g * dY * Q at every halo position (2 x UB 16-byte requests in flight per thread)
+        for (int p0 = threadIdx.x >> 3; p0 < npos; p0 += PSTEP * UB) {
             uint4 dv[UB], qv[UB];
-            bool ok[UB];
 #pragma unroll
             for (int u = 0; u < UB; ++u) {
-                const int e = e0 + u * blockDim.x;
-                const int pos = e >> 3, part = e & 7;
-                const int py = pos / g.PW, px = pos - py * g.PW;
-                const int y = g.ty0 - g.R + py, x = g.tx0 - g.R + px;
-                ok[u] = e < total && part * 4 < G::ACT && y >= 0 && y < H && x >= 0 && x < Wd && px < g.tw + 2 * g.R;
+                const int pos = p0 + u * PSTEP;
+                const int py = pos / PW, px = pos - py * PW;
+                const int y = ty0 - R + py, x = tx0 - R + px;
                 dv[u] = qv[u] = make_uint4(0, 0, 0, 0);
-                if (ok[u]) {
+                if (pos < npos && pact && y >= 0 && y < H && x >= 0 && x < Wd && px < tw + 2 * R) {
                     const size_t n = (size_t)y * Wd + x;
-                    dv[u] = *reinterpret_cast<const uint4*>(dy_b + n * C + cg0 + part * 8);
-                    qv[u] = *reinterpret_cast<const uint4*>(qkv_b + n * 3 * C + cg0 + part * 8);
+                    dv[u] = *reinterpret_cast<const uint4*>(dy_b + n * C + cc);
+                    qv[u] = *reinterpret_cast<const uint4*>(qkv_b + n * 3 * C + cc);
                 }
             }
 #pragma unroll
             for (int u = 0; u < UB; ++u) {
-                const int e = e0 + u * blockDim.x;
-                if (e >= total) continue;
-                const int cc = cg0 + (e & 7) * 8;
-                uint4 r = make_uint4(0, 0, 0, 0);
-                if (ok[u]) {
-                    const uint32_t d4[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, q4[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
-                    uint32_t o4[4];
+                const int pos = p0 + u * PSTEP;
+                if (pos >= npos) continue;
+                const float2 o0 = mul2(mul2(gg[0], up2(dv[u].x)), up2(qv[u].x)), o1 = mul2(mul2(gg[1], up2(dv[u].y)), up2(qv[u].y));
+                const float2 o2 = mul2(mul2(gg[2], up2(dv[u].z)), up2(qv[u].z)), o3 = mul2(mul2(gg[3], up2(dv[u].w)), up2(qv[u].w));
+                float4* dst = reinterpret_cast<float4*>(sE + pos * 32 + part * 4);
+                dst[0] = make_float4(o0.x, o0.y, o1.x, o1.y);
+                dst[1] = make_float4(o2.x, o2.y, o3.x, o3.y);
+            }
+        }
+        if (want_w) {
+            constexpr int UV = 8;
+            for (int p0 = threadIdx.x >> 3; p0 < npos; p0 += PSTEP * UV) {
+                uint4 v[UV];
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const float2 d = up2(d4[w]), q = up2(q4[w]);
-                        float2 gg = make_float2(1.f, 1.f);
-                        if (gate) gg = *reinterpret_cast<const float2*>(gate + (size_t)b * C + cc + 2 * w);
-                        o4[w] = f2_to_bf2(gg.x * d.x * q.x, gg.y * d.y * q.y);
-                    }
-                    r = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                for (int u = 0; u < UV; ++u) {
+                    const int pos = p0 + u * PSTEP;
+                    const int py = pos / PW, px = pos - py * PW;
+                    const int y = ty0 - R + py, x = tx0 - R + px;
+                    v[u] = make_uint4(0, 0, 0, 0);
+                    if (pos < npos && pact && y >= 0 && y < H && x >= 0 && x < Wd && px < tw + 2 * R)
+                        v[u] = *reinterpret_cast<const uint4*>(qkv_b + ((size_t)y * Wd + x) * 3 * C + 2 * C + cc);
                 }
-                *reinterpret_cast<uint4*>(sE + (e >> 3) * 32 + (e & 7) * 4) = r;
+#pragma unroll
+                for (int u = 0; u < UV; ++u) {
+                    const int pos = p0 + u * PSTEP;
+                    if (pos < npos) *reinterpret_cast<uint4*>(sV + pos * 32 + part * 4) = v[u];
+                }
             }
         }
     }
-    load_taps<CH, WIN>(sW, cw, cg0, G::ACT);
-    for (int e = threadIdx.x; e < (EXT ? 0 : (CH / 2) * 32); e += blockDim.x) {
+    const bool act = lane < G::ACT;
+    const int c0 = cg0 + 2 * (act ? lane : 0);
+    {   // flipped, zero-padded WIN x WIN taps of every lane's channel pair: sW[tap][lane] = w[NTAP - 1 - tap]
+        const float* wp0; const float* wp1; const float* bp; int wc0, wc1;
+        crpe_of_channel(cw, c0, CH, wp0, bp, wc0);
+        crpe_of_channel(cw, c0 + 1, CH, wp1, bp, wc1);
+        for (int tap = warp; tap < NTAP; tap += NW) {
+            const int ft = NTAP - 1 - tap, i = ft / WIN, j = ft - i * WIN;
+            float2 w = make_float2(0.f, 0.f);
+            if (act) {
+                const int o0 = (WIN - wc0) >> 1, o1 = (WIN - wc1) >> 1;
+                const int i0 = i - o0, j0 = j - o0, i1 = i - o1, j1 = j - o1;
+                if (i0 >= 0 && i0 < wc0 && j0 >= 0 && j0 < wc0) w.x = __ldg(wp0 + i0 * wc0 + j0);
+                if (i1 >= 0 && i1 < wc1 && j1 >= 0 && j1 < wc1) w.y = __ldg(wp1 + i1 * wc1 + j1);
+            }
+            sW[tap * 32 + lane] = w;
+        }
+    }
+    for (int e = threadIdx.x; e < (EXT ? 0 : (CH / 2) * 32); e += NT) {
         const int jj = e >> 5, l = e & 31;
         float4 at = make_float4(0.f, 0.f, 0.f, 0.f), da = at, dat = at;
         if (l < G::ACT) {
@@ -443,19 +502,9 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
         sdA[e] = da;
         sdAt[e] = dat;
     }
-    if (want_w)
-        for (int e = threadIdx.x; e < (WIN * WIN + 1) * 64; e += blockDim.x) sG[e] = 0.f;
-    const bool act = lane < G::ACT;
-    const int c0 = cg0 + 2 * (act ? lane : 0);
     const int hb = (lane / G::LPH) * G::LPH;
-    float2 bias = make_float2(0.f, 0.f), gt = make_float2(1.f, 1.f), km = make_float2(0.f, 0.f), zi = make_float2(0.f, 0.f),
-           rr = make_float2(0.f, 0.f);
+    float2 gt = make_float2(1.f, 1.f), km = make_float2(0.f, 0.f), zi = make_float2(0.f, 0.f), rr = make_float2(0.f, 0.f);
     if (act) {
-        const float* wp; const float* bp; int wc;
-        crpe_of_channel(cw, c0, CH, wp, bp, wc);
-        bias.x = __ldg(bp);
-        crpe_of_channel(cw, c0 + 1, CH, wp, bp, wc);
-        bias.y = __ldg(bp);
         const size_t bc = (size_t)b * C + c0;
         if (gate) gt = *reinterpret_cast<const float2*>(gate + bc);
         if (!EXT) {
@@ -466,83 +515,87 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
         }
     }
     __syncthreads();
-    const int nstrips = g.th * g.nsx;
+    const int nsx = FULL ? TILE_W / TX : (tw + TX - 1) / TX;
+    const int nstrips = th * nsx;
     float2 gacc = make_float2(0.f, 0.f);
     float2 bq = make_float2(0.f, 0.f), bk = bq, bv = bq;      // column sums of dQ, dK, dV: the qkv Linear's bias gradient
     // ---- pass A: activation gradients
-    for (int s = warp; s < nstrips; s += nwarp) {
-        const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
-        const size_t n0 = (size_t)(g.ty0 + py) * Wd + g.tx0 + px0;
+    for (int s = warp; s < nstrips; s += NW) {
+        const int py = s / nsx, px0 = (s - py * nsx) * TX;
+        const size_t n0 = (size_t)(ty0 + py) * Wd + tx0 + px0;
         // this strip's own pixels: issued before the convolution loop so their latency hides behind the math
         uint32_t kw[TX], dw[TX], yw[TX], ew[TX], vw[TX];
         float2 dvp[TX];
+        const bf16* qrow = qkv_b + n0 * 3 * C + c0;
+        const bf16* drow_in = dy_b + n0 * C + c0;
+        const size_t nb = ((size_t)b * N + n0) * C + c0;
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
-            const bool ok = act && px0 + t < g.tw;
-            kw[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + C + c0) : 0u;
-            vw[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(qkv_b + (n0 + t) * 3 * C + 2 * C + c0) : 0u;
-            dw[t] = (ok && (!EXT || gate)) ? *reinterpret_cast<const uint32_t*>(dy_b + (n0 + t) * C + c0) : 0u;
-            ew[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(ein + ((size_t)b * N + n0 + t) * C + c0) : 0u;
-            yw[t] = (ok && gate) ? *reinterpret_cast<const uint32_t*>(yout + ((size_t)b * N + n0 + t) * C + c0) : 0u;
+            const bool ok = FULL ? act : (act && px0 + t < tw);
+            kw[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(qrow + t * 3 * C + C) : 0u;
+            vw[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(qrow + t * 3 * C + 2 * C) : 0u;
+            dw[t] = (ok && (!EXT || gate)) ? *reinterpret_cast<const uint32_t*>(drow_in + t * C) : 0u;
+            ew[t] = (ok && !EXT) ? *reinterpret_cast<const uint32_t*>(ein + nb + t * C) : 0u;
+            yw[t] = (ok && gate) ? *reinterpret_cast<const uint32_t*>(yout + nb + t * C) : 0u;
             // (the mat-vec part of dV was parked, as bf16, in the dV slot of dqkv by attn_mm_bwd_kernel)
-            dvp[t] = (ok && EXT) ? up2(*reinterpret_cast<const uint32_t*>(dqkv + ((size_t)b * N + n0 + t) * 3 * C + 2 * C + c0)) : make_float2(0.f, 0.f);
+            dvp[t] = (ok && EXT) ? up2(*reinterpret_cast<const uint32_t*>(dqkv + 3 * nb - 2 * c0 + 2 * C + t * 3 * C)) : make_float2(0.f, 0.f);
         }
         // transposed convolution of dE (flipped taps): dV_conv[n] = sum_ij w[i,j] dE[n - (i-R, j-R)]
         float2 tc[TX];
 #pragma unroll
         for (int t = 0; t < TX; ++t) tc[t] = make_float2(0.f, 0.f);
+        {
+            const float2* rowe = sE + (py * PW + px0) * 32 + lane;
+            const float2* wrow = sW + lane;
 #pragma unroll 1
-        for (int i = 0; i < WIN; ++i) {
-            const uint32_t* rowe = sE + ((py + i) * g.PW + px0) * 32 + lane;
-            float2 ine[TX + WIN - 1];
+            for (int i = 0; i < WIN; ++i, rowe += PW * 32, wrow += WIN * 32) {
+                float2 ine[TX + WIN - 1];
 #pragma unroll
-            for (int t = 0; t < TX + WIN - 1; ++t) ine[t] = up2(rowe[t * 32]);
+                for (int t = 0; t < TX + WIN - 1; ++t) ine[t] = rowe[t * 32];
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) {
-                const float2 wf = sW[(WIN * WIN - 1 - (i * WIN + j)) * 32 + lane];
+                for (int j = 0; j < WIN; ++j) {
+                    const float2 wf = wrow[j * 32];
 #pragma unroll
-                for (int t = 0; t < TX; ++t) tc[t] = fma2(wf, ine[t + j], tc[t]);
+                    for (int t = 0; t < TX; ++t) tc[t] = fma2(wf, ine[t + j], tc[t]);
+                }
             }
         }
-        if (EXT) {
+        bf16* drow = dqkv + 3 * nb - 2 * c0;       // = dqkv + ((b N + n0) 3C + c0)
+        if constexpr (EXT) {
             // dQ, dK and the mat-vec part of dV come from attn_mm_bwd_kernel: finish dV, the gate sums and the bias sums
             if (act) {
 #pragma unroll
                 for (int t = 0; t < TX; ++t) {
-                    if (px0 + t >= g.tw) break;
+                    if (!FULL && px0 + t >= tw) break;
                     gacc = fma2(up2(dw[t]), up2(yw[t]), gacc);
                     const float2 dv = make_float2(dvp[t].x + tc[t].x, dvp[t].y + tc[t].y);
                     bv.x += dv.x; bv.y += dv.y;
-                    *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * N + n0 + t) * 3 * C + 2 * C + c0) = f2_to_bf2(dv.x, dv.y);
+                    *reinterpret_cast<uint32_t*>(drow + t * 3 * C + 2 * C) = f2_to_bf2(dv.x, dv.y);
                 }
             }
-            continue;
-        }
-        float2 e[TX];
-#pragma unroll
-        for (int t = 0; t < TX; ++t) e[t] = up2(ew[t]);
+        } else {
         float2 dF[TX], S[TX];
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
-            const bool ok = act && px0 + t < g.tw;
+            const bool ok = FULL ? act : (act && px0 + t < tw);
             const float2 kk = up2(kw[t]), d = up2(dw[t]);
             dF[t] = mul2(gt, d);
             S[t] = ok ? make_float2(__expf(kk.x - km.x) * zi.x, __expf(kk.y - km.y) * zi.y) : make_float2(0.f, 0.f);
             gacc = fma2(d, up2(yw[t]), gacc);
         }
-        // three per-head mat-vecs, 4 pixels at a time (register pressure); packed accumulators hold the (even j, odd j)
+        // three per-head mat-vecs, MVU pixels at a time (register pressure); packed accumulators hold the (even j, odd j)
         // partial sums, so the shuffled pairs are used as packed operands without splatting
 #pragma unroll
-        for (int half = 0; half < TX / 4; ++half) {
-            float2 q0[4], q1[4], v0[4], v1[4], k0[4], k1[4];
+        for (int half = 0; half < TX / MVU; ++half) {
+            float2 q0[MVU], q1[MVU], v0[MVU], v1[MVU], k0[MVU], k1[MVU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q0[u] = q1[u] = v0[u] = v1[u] = k0[u] = k1[u] = make_float2(0.f, 0.f);
-#pragma unroll 2
+            for (int u = 0; u < MVU; ++u) q0[u] = q1[u] = v0[u] = v1[u] = k0[u] = k1[u] = make_float2(0.f, 0.f);
+#pragma unroll (MVJ)
             for (int jj = 0; jj < CH / 2; ++jj) {
                 const float4 at = sAt[jj * 32 + lane], da = sdA[jj * 32 + lane], dt = sdAt[jj * 32 + lane];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = half * 4 + u;
+                for (int u = 0; u < MVU; ++u) {
+                    const int t = half * MVU + u;
                     const float2 f = shfl2(dF[t], hb + jj);
                     const float2 ss = shfl2(S[t], hb + jj);
                     const float2 vv = up2(__shfl_sync(0xffffffffu, vw[t], hb + jj));
@@ -556,92 +609,126 @@ __device__ __forceinline__ void attn_bwd_strip_body(const bf16* __restrict__ qkv
             }
             if (act) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = half * 4 + u;
-                    if (px0 + t >= g.tw) break;
+                for (int u = 0; u < MVU; ++u) {
+                    const int t = half * MVU + u;
+                    if (!FULL && px0 + t >= tw) break;
                     const float2 sq = make_float2(q0[u].x + q0[u].y, q1[u].x + q1[u].y);
                     const float2 sv = make_float2(v0[u].x + v0[u].y, v1[u].x + v1[u].y);
                     const float2 sk = make_float2(k0[u].x + k0[u].y, k1[u].x + k1[u].y);
-                    const float2 dq = fma2(splat(scale), sq, mul2(dF[t], e[t]));
+                    const float2 dq = fma2(splat(scale), sq, mul2(dF[t], up2(ew[t])));
                     const float2 dk = mul2(S[t], make_float2(sk.x - rr.x, sk.y - rr.y));
                     const float2 dv = make_float2(sv.x + tc[t].x, sv.y + tc[t].y);
                     bq.x += dq.x; bq.y += dq.y; bk.x += dk.x; bk.y += dk.y; bv.x += dv.x; bv.y += dv.y;
-                    bf16* drow = dqkv + ((size_t)b * N + n0 + t) * 3 * C + c0;
-                    *reinterpret_cast<uint32_t*>(drow) = f2_to_bf2(dq.x, dq.y);
-                    *reinterpret_cast<uint32_t*>(drow + C) = f2_to_bf2(dk.x, dk.y);
-                    *reinterpret_cast<uint32_t*>(drow + 2 * C) = f2_to_bf2(dv.x, dv.y);
+                    *reinterpret_cast<uint32_t*>(drow + t * 3 * C) = f2_to_bf2(dq.x, dq.y);
+                    *reinterpret_cast<uint32_t*>(drow + t * 3 * C + C) = f2_to_bf2(dk.x, dk.y);
+                    *reinterpret_cast<uint32_t*>(drow + t * 3 * C + 2 * C) = f2_to_bf2(dv.x, dv.y);
+                }
+            }
+        }
+        }
+    }
+    // ---- pass B: convolution weight / bias gradients.  warp -> (kernel row i, band of tile rows); one spare warp sums the bias
+    constexpr int NPARTS = NW / WIN, NSLOT = NTAP + 1;
+    float2 gw[WIN];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) gw[j] = make_float2(0.f, 0.f);
+    float2 gb = make_float2(0.f, 0.f);
+    const int item_i = warp / NPARTS, item_p = warp - item_i * NPARTS;
+    if (want_w) {
+        if (item_i < WIN) {
+            const int rows = (th + NPARTS - 1) / NPARTS;
+            const int r0 = item_p * rows, r1 = min(th, r0 + rows);
+            const int nsxb = FULL ? TILE_W / BWD_TXB : (tw + BWD_TXB - 1) / BWD_TXB;
+            for (int py = r0; py < r1; ++py) {
+                for (int sx = 0; sx < nsxb; ++sx) {
+                    const int px0 = sx * BWD_TXB;
+                    const uint32_t* rowv = sV + ((py + item_i) * PW + px0) * 32 + lane;
+                    const float2* ce = sE + ((py + R) * PW + px0 + R) * 32 + lane;
+                    float2 inv[BWD_TXB + WIN - 1], de[BWD_TXB];
+#pragma unroll
+                    for (int t = 0; t < BWD_TXB + WIN - 1; ++t) inv[t] = up2(rowv[t * 32]);
+#pragma unroll
+                    for (int t = 0; t < BWD_TXB; ++t)      // (halo columns past the tile hold the neighbours' dE)
+                        de[t] = (FULL || px0 + t < tw) ? ce[t * 32] : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j)
+#pragma unroll
+                        for (int t = 0; t < BWD_TXB; ++t) gw[j] = fma2(de[t], inv[t + j], gw[j]);
+                }
+            }
+        } else if (warp == WIN * NPARTS) {
+            for (int py = 0; py < th; ++py) {
+                const float2* ce = sE + ((py + R) * PW + R) * 32 + lane;
+                for (int px = 0; px < tw; ++px) {
+                    const float2 d = ce[px * 32];
+                    gb.x += d.x; gb.y += d.y;
                 }
             }
         }
     }
-    if (gate && dgate && act) {
-        atomicAdd(dgate + (size_t)b * C + c0, gacc.x / gt.x);
-        atomicAdd(dgate + (size_t)b * C + c0 + 1, gacc.y / gt.y);
-    }
-    if (dbias_qkv && act) {
-        if (!EXT) {
-            atomicAdd(dbias_qkv + c0, bq.x);
-            atomicAdd(dbias_qkv + c0 + 1, bq.y);
-            atomicAdd(dbias_qkv + C + c0, bk.x);
-            atomicAdd(dbias_qkv + C + c0 + 1, bk.y);
-        }
-        atomicAdd(dbias_qkv + 2 * C + c0, bv.x);
-        atomicAdd(dbias_qkv + 2 * C + c0 + 1, bv.y);
-    }
-    if (!want_w) return;   // block-uniform
-    // ---- pass B: convolution weight / bias gradients, one kernel row at a time (7 float2 accumulators live)
-#pragma unroll 1
-    for (int i = 0; i < WIN; ++i) {
-        float2 gw[WIN];
-#pragma unroll
-        for (int j = 0; j < WIN; ++j) gw[j] = make_float2(0.f, 0.f);
-        float2 gb = make_float2(0.f, 0.f);
-        for (int s = warp; s < nstrips; s += nwarp) {
-            const int py = s / g.nsx, px0 = (s % g.nsx) * TX;
-            const uint32_t* rowv = sV + ((py + i) * g.PW + px0) * 32 + lane;
-            const uint32_t* ce = sE + ((py + g.R) * g.PW + px0 + g.R) * 32 + lane;
-            float2 inv[TX + WIN - 1], de[TX];
-#pragma unroll
-            for (int t = 0; t < TX + WIN - 1; ++t) inv[t] = up2(rowv[t * 32]);
-#pragma unroll
-            for (int t = 0; t < TX; ++t) {
-                de[t] = (px0 + t < g.tw) ? up2(ce[t * 32]) : make_float2(0.f, 0.f);   // halo columns past the tile hold neighbours' dE
-                if (i == 0) {
-                    gb.x += de[t].x;
-                    gb.y += de[t].y;
-                }
-            }
+    __syncthreads();     // every warp is done with the dE tile: the per-warp sums are parked over it
+    float2* sR = reinterpret_cast<float2*>(smem_s);                   // [NW][4][32]: dQ, dK, dV column sums and the gate sum
+    float* sP = reinterpret_cast<float*>(sR + NW * 4 * 32);           // [NPARTS][NSLOT][SPP] weight-gradient partials
+    constexpr int SPP = 66;                                           // (row pitch: the final sum reads columns)
+    sR[(warp * 4 + 0) * 32 + lane] = bq;
+    sR[(warp * 4 + 1) * 32 + lane] = bk;
+    sR[(warp * 4 + 2) * 32 + lane] = bv;
+    sR[(warp * 4 + 3) * 32 + lane] = gacc;
+    if (want_w) {
+        if (item_i < WIN) {
 #pragma unroll
             for (int j = 0; j < WIN; ++j)
-#pragma unroll
-                for (int t = 0; t < TX; ++t) gw[j] = fma2(de[t], inv[t + j], gw[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < WIN; ++j) {
-            atomicAdd(sG + (i * WIN + j) * 64 + 2 * lane, gw[j].x);
-            atomicAdd(sG + (i * WIN + j) * 64 + 2 * lane + 1, gw[j].y);
-        }
-        if (i == 0) {
-            atomicAdd(sG + WIN * WIN * 64 + 2 * lane, gb.x);
-            atomicAdd(sG + WIN * WIN * 64 + 2 * lane + 1, gb.y);
+                *reinterpret_cast<float2*>(sP + (item_p * NSLOT + item_i * WIN + j) * SPP + 2 * lane) = gw[j];
+        } else if (warp == WIN * NPARTS) {
+            *reinterpret_cast<float2*>(sP + NTAP * SPP + 2 * lane) = gb;
         }
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < (WIN * WIN + 1) * G::CPW; o += blockDim.x) {
-        const int t = o / G::CPW, cl_ = o % G::CPW;
-        const float sum = sG[t * 64 + cl_];
+    if (threadIdx.x < 128) {
+        const int q = threadIdx.x >> 5;          // 0: dQ bias, 1: dK bias, 2: dV bias, 3: gate
+        float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float2 v = sR[(w * 4 + q) * 32 + lane];
+            sum.x += v.x; sum.y += v.y;
+        }
+        if (act) {
+            if (q == 3) {
+                if (gate && dgate) {
+                    atomicAdd(dgate + (size_t)b * C + c0, sum.x / gt.x);
+                    atomicAdd(dgate + (size_t)b * C + c0 + 1, sum.y / gt.y);
+                }
+            } else if (dbias_qkv && (!EXT || q == 2)) {
+                atomicAdd(dbias_qkv + q * C + c0, sum.x);
+                atomicAdd(dbias_qkv + q * C + c0 + 1, sum.y);
+            }
+        }
+    }
+    if (!want_w) return;   // block-uniform
+    // lanes walk the taps of one channel: consecutive addresses of the gradient array
+    for (int o = threadIdx.x; o < NSLOT * G::CPW; o += NT) {
+#ifndef MDV_EXP_NO_TAIL
+        const int cl_ = o / NSLOT, t = o - cl_ * NSLOT;
+        float sum = sP[t * SPP + cl_];
+        if (t < NTAP)
+#pragma unroll
+            for (int p = 1; p < NPARTS; ++p) sum += sP[(p * NSLOT + t) * SPP + cl_];
         const int c = cg0 + cl_;
         const int h = c / CH;
         const int grp = h < 2 ? 0 : (h < 5 ? 1 : 2);
         const int cl = c - (grp == 0 ? 0 : (grp == 1 ? 2 * CH : 5 * CH));
         const int wc = 3 + 2 * grp;
-        if (t < WIN * WIN) {
+        float* gwp = grp == 0 ? cg.w[0] : (grp == 1 ? cg.w[1] : cg.w[2]);
+        float* gbp = grp == 0 ? cg.b[0] : (grp == 1 ? cg.b[1] : cg.b[2]);
+        if (t < NTAP) {
             const int o2 = (WIN - wc) >> 1;
-            const int ii = t / WIN - o2, jj = t % WIN - o2;
-            if (ii >= 0 && ii < wc && jj >= 0 && jj < wc) atomicAdd(cg.w[grp] + (size_t)cl * wc * wc + ii * wc + jj, sum);
+            const int ti = t / WIN;
+            const int ii = ti - o2, jj = t - ti * WIN - o2;
+            if (ii >= 0 && ii < wc && jj >= 0 && jj < wc) atomicAdd(gwp + (size_t)cl * wc * wc + ii * wc + jj, sum);
         } else {
-            atomicAdd(cg.b[grp] + cl, sum);
+            atomicAdd(gbp + cl, sum);
         }
+#endif
     }
 }
 
@@ -853,9 +940,6 @@ __global__ void __launch_bounds__(256) attn_fwd_strip_kernel(const bf16* __restr
     else attn_fwd_strip_body<CH, 7>(qkv, A, gate, cw, out, eout, scale, H, Wd, C, smem_dyn);
 }
 
-constexpr int BWD_THREADS = 512;   // 16 warps share one tile: twice the latency hiding of 8 (the kernel is register/latency bound)
-constexpr int BWD_TX = 4;          // 4-pixel strips keep the per-thread arrays within 128 registers
-
 template <int CH, bool EXT>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                               const bf16* __restrict__ yout, const float* __restrict__ gate,
@@ -868,9 +952,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_strip_kernel(const bf
     MDV_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_dyn[];
     const int win = win_of_group<CH>(blockIdx.y);
-    if (win == 3) attn_bwd_strip_body<CH, 3, BWD_TX, EXT>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
-    else if (win == 5) attn_bwd_strip_body<CH, 5, BWD_TX, EXT>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
-    else attn_bwd_strip_body<CH, 7, BWD_TX, EXT>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn);
+    const bool full = (H % TILE_H) == 0 && (Wd % TILE_W) == 0;
+#define MDV_BWD_BODY(WIN_, FULL_) \
+    attn_bwd_strip_body<CH, WIN_, BWD_TX, EXT, FULL_>(qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv, dgate, dbias_qkv, scale, H, Wd, C, smem_dyn)
+    if (full) {
+        if (win == 3) MDV_BWD_BODY(3, true);
+        else if (win == 5) MDV_BWD_BODY(5, true);
+        else MDV_BWD_BODY(7, true);
+    } else {
+        if (win == 3) MDV_BWD_BODY(3, false);
+        else if (win == 5) MDV_BWD_BODY(5, false);
+        else MDV_BWD_BODY(7, false);
+    }
+#undef MDV_BWD_BODY
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -904,9 +998,9 @@ template <int CH>
 int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* gate, const float* A, const float* dA, const float* rk,
                const float* kmax, const float* zsum, const CrpeW& cw, const CrpeG& cg, const bf16* ein, bf16* dqkv, float* dgate,
                float* dbias_qkv, float scale, int B, int H, int W, int C, cudaStream_t st) {
-    const int full = 2 * tile_words(7) * 4 + 49 * 32 * 8 + 3 * CH * 32 * 8 + 50 * 64 * 4;
-    // activation-gradient-only pass: no V tile -> half the shared memory, two blocks per SM
-    const int smem = cg.w[0] ? full : full - tile_words(7) * 4;
+    // dE tile (fp32 pairs) + V tile (bf16 pairs) + taps + the three matrices, sized for the widest window
+    const int full = bwd_tile_pos<7>() * 32 * 12 + 49 * 32 * 8 + (CH >= 40 ? 0 : 3 * (CH / 2) * 32 * 16);
+    const int smem = cg.w[0] ? full : full - bwd_tile_pos<7>() * 32 * 4;      // activation-gradient-only pass: no V tile
     static bool configured = false;
     if (!configured) {
         int rc = set_smem(attn_bwd_strip_kernel<CH, (CH >= 40)>, full);
