@@ -10,9 +10,14 @@
 //   warp 2      TMEM allocator
 //   warps 4..11 epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / dropout / DropPath / residual in registers ->
 //               swizzled shared-memory slab -> TMA store (bf16 or fp32), overlapping the next tile's loads and MMAs
+// PAIR (large NT GEMMs): the kernel is launched as 2-CTA clusters and a CTA pair works on one 256 x BN tile with
+//   tcgen05.mma.cta_group::2 — each CTA loads its own 128 rows of A and HALF of the B tile, so the operand bytes an SM pulls
+//   from L2 per flop drop by 30-40% (these GEMMs are L2->SM bandwidth bound: K is short).
 // Replaces the aten::addmm / cudnn 1x1-conv calls behind nn.Linear / nn.Conv2d(k=1) in the reference
 // (Models/Transformer/mdvit.py:288,310, mpvit.py:72-76, Decoders.py:197,59,317-333) and their backward passes.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "../../include/mdvit_b200.h"
 #include "common.cuh"
@@ -38,6 +43,8 @@ struct GemmParams {
     int stages;
     int n_tiles, m_tiles, splits, kb_per_split;
     int has_preact;
+    int exp;              // development experiments (MDV_GEMM_EXP): 1 = skip the output stores
+    int pair;             // NT only: 2-CTA clusters, one 256 x BN tile per CTA pair (tcgen05 cta_group::2)
     int tf32;             // NT only: operands are fp32, multiplied as TF32 (kind::tf32, 32-element k-blocks); else bf16 (64)
     int bk;               // elements per k-block: 128 bytes of K per row of a stage
     int nbuf;             // staging buffers per epilogue warp (2 or 4)
@@ -65,7 +72,10 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
     return c;
 }
 
-template <bool TN, int NEPI>
+// LIGHT: the epilogue only adds a bias, sums columns and stores (no activation / multiplier / dropout / row scale / residual /
+// second output): the feature tests of the general epilogue cost ~220 instructions per 32 x 32 chunk even when every feature is
+// off, and the chunk chain of an epilogue warp is latency bound (profiles/r2_ncu_gemm_linear_fuse_dgrad.txt).
+template <bool TN, int NEPI, bool PAIR, bool LIGHT>
 __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
@@ -81,7 +91,12 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
     const int stages = p.stages;
-    const uint32_t b_bytes = (uint32_t)BN * BK * 2;
+    // PAIR: this CTA's half of the B tile; its rows of the 256-row tile; the pair's position in the persistent tile walk
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cta_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int TM = PAIR ? 2 * BM : BM;          // rows of an output tile
+    const int bn_cta = PAIR ? BN / 2 : BN;          // B rows held by this CTA
+    const uint32_t b_bytes = (uint32_t)bn_cta * BK * 2;
     const uint32_t stage_bytes = A_BYTES + b_bytes;
     uint8_t* slabs = smem + (size_t)stages * stage_bytes;          // [8 warps][nbuf][out (+ preact)]
     float* cs_all = reinterpret_cast<float*>(slabs + (size_t)NEPI * p.nbuf * p.buf_bytes);   // [NEPI warps][4 chunks][32]
@@ -100,17 +115,24 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], NEPI);
+            mbar_init(&tempty_bar[i], PAIR ? 2 * NEPI : NEPI);      // PAIR: the epilogue warps of both CTAs arrive at the leader's
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything can arrive on them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     // PDL: barrier init, TMEM allocation and tensor-map prefetch above overlap the previous kernel's tail; nothing before
@@ -121,16 +143,29 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = cta_id; t < total_tiles; t += cta_step) {
                 const TileCoord tc = tile_coord<TN>(p, t);
                 for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
                     mbar_wait_spin(&empty_bar[s], ph ^ 1);
-                    mbar_expect_tx(&full_bar[s], stage_bytes);
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
                     const int kc = (tc.kb0 + kb) * p.bk;
+                    if (p.exp == 4) {       // experiment: no operand loads (MMA + epilogue alone)
+                        if (rank == 0) mbar_arrive(&full_bar[s]);
+                        continue;
+                    }
+                    if (PAIR) {
+                        // the bytes of both CTAs are counted on the leader's barrier (a complete_tx that overtakes the
+                        // leader's expect_tx only drives the transaction count negative within the same phase)
+                        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                        tma_load_2d_pair(sa, &tmA, kc, tc.m_tile * TM + (int)rank * BM, fb);
+                        tma_load_2d_pair(sb, &tmB, kc, tc.n_tile * BN + (int)rank * bn_cta, fb);
+                        continue;
+                    }
+                    mbar_expect_tx(&full_bar[s], stage_bytes);
                     if (!TN) {
                         tma_load_2d(sa, &tmA, kc, tc.m_tile * BM, &full_bar[s]);
                         tma_load_2d(sb, &tmB, kc, tc.n_tile * BN, &full_bar[s]);
@@ -143,41 +178,63 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The WHOLE warp walks the loops (uniform control flow) and one elected lane issues: tcgen05.mma / commit take their
+        // operands from uniform registers, and inside an `if (lane == 0)` region the compiler has to move every descriptor
+        // there with ELECT / R2UR.BROADCAST waterfall loops — ~270 cycles per MMA, twice the 96-128 cycles the MMA itself takes
+        // (the loop was issue-bound: same time with the operand loads removed).
+        if (rank == 0) {
             // TF32: same descriptor with a/b format 2 instead of 1 (cute::UMMA::F16F32Format); one MMA consumes K=8 fp32 = 32 B,
             // exactly the +32 B per step of the bf16 path (K=16), so the k-loop is shared
-            const uint32_t idesc = p.tf32 ? (make_idesc(BM, BN, TN) + (1u << 7) + (1u << 10)) : make_idesc(BM, BN, TN);
-            const bool is_tf32 = p.tf32 != 0;        // (kept in a register: the issue loop is the critical path of MMA-bound shapes)
-            int it = 0, lt = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const uint32_t idesc = p.tf32 ? (make_idesc(TM, BN, TN) + (1u << 7) + (1u << 10)) : make_idesc(TM, BN, TN);
+            const bool is_tf32 = p.tf32 != 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);      // (a value the compiler knows to be warp-uniform)
+            // descriptors of stage 0, k-step 0: a stage / k-step only moves the start-address field (16-byte units, bits 0-13)
+            //   K-major : 8-row groups 1024B apart; +32B per K=16 step inside the 128B swizzle span
+            //   MN-major: 64-element MN chunks 8192B apart (LBO), 8 k-rows = 1024B (SBO); K=16 -> +2048B
+            const uint32_t smem0 = smem_u32(smem);
+            const uint64_t adesc0 = TN ? make_desc(smem0, 8192, 1024) : make_desc(smem0, 16, 1024);
+            const uint64_t bdesc0 = TN ? make_desc(smem0 + A_BYTES, 8192, 1024) : make_desc(smem0 + A_BYTES, 16, 1024);
+            constexpr uint32_t KSTEP16 = (TN ? 2048 : 32) >> 4;
+            const uint32_t sstep16 = stage_bytes >> 4;
+            const bool no_mma = p.exp == 3;      // experiment: no MMAs (loads + epilogue alone)
+            int lt = 0, s = 0;
+            uint32_t ph = 0;
+            for (int t = cta_id; t < total_tiles; t += cta_step, ++lt) {
                 const TileCoord tc = tile_coord<TN>(p, t);
                 const int as = lt & 1;
                 mbar_wait_spin(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
-                for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                const uint32_t tacc = tmem_u + (uint32_t)as * 256u;
+                for (int kb = 0; kb < tc.num_kb; ++kb) {
                     mbar_wait_spin(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * sstep16), bd = bdesc0 + (uint64_t)((uint32_t)s * sstep16);
+                    if (elect_one()) {
+                        if (!no_mma) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        uint64_t ad, bd;
-                        if (!TN) {  // K-major: 8-row groups 1024B apart; +32B per K=16 step inside the 128B swizzle span
-                            ad = make_desc(sa + k * 32, 16, 1024);
-                            bd = make_desc(sb + k * 32, 16, 1024);
-                        } else {    // MN-major: 64-element MN chunks 8192B apart (LBO), 8 k-rows = 1024B (SBO); K=16 -> +2048B
-                            ad = make_desc(sa + k * 2048, 8192, 1024);
-                            bd = make_desc(sb + k * 2048, 8192, 1024);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                                if (PAIR) {
+                                    if (is_tf32) tc_mma2_tf32(tacc, ad + k * KSTEP16, bd + k * KSTEP16, idesc, acc);
+                                    else tc_mma2_bf16(tacc, ad + k * KSTEP16, bd + k * KSTEP16, idesc, acc);
+                                } else if (!TN && is_tf32) tc_mma_tf32(tacc, ad + k * KSTEP16, bd + k * KSTEP16, idesc, acc);
+                                else tc_mma_bf16(tacc, ad + k * KSTEP16, bd + k * KSTEP16, idesc, acc);
+                            }
                         }
-                        if (!TN && is_tf32) tc_mma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else tc_mma_bf16(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (PAIR) tc_commit_pair(&empty_bar[s]);
+                        else tc_commit(&empty_bar[s]);
                     }
-                    tc_commit(&empty_bar[s]);
+                    __syncwarp();
+                    if (++s == stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                tc_commit(&tfull_bar[as]);
+                if (elect_one()) {
+                    if (PAIR) tc_commit_pair(&tfull_bar[as]);
+                    else tc_commit(&tfull_bar[as]);
+                }
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -190,29 +247,31 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
         const int nbuf_mask = p.nbuf - 1;
         uint32_t dthr = 0, dkey = 0;
         float dinv = 1.0f;
-        if (e.dropout_p > 0.0f) {
+        if (!LIGHT && e.dropout_p > 0.0f) {
             dthr = drop_thresh(e.dropout_p);
             dinv = 1.0f / (1.0f - e.dropout_p);
             dkey = rng_key((const unsigned long long*)e.rng, e.drop_stream);
         }
         const bool out_bf16 = e.out_bf16 != 0;
+        const float* const bias_p = e.bias;
+        float* const colsum_p = e.colsum;
         // bias-gradient by-product: per-lane column sums of the stored tile, kept in shared memory across this CTA's
         // tiles while they share an n_tile and flushed with one atomic per column when it changes / at the end
         float* cs = cs_all + (warp - 4) * 128;
         int cs_n0 = -1;
-        if (e.colsum) {
+        if (colsum_p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) cs[i * 32 + lane] = 0.f;
         }
         int lt = 0, nstore = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        for (int t = cta_id; t < total_tiles; t += cta_step, ++lt) {
             const TileCoord tc = tile_coord<TN>(p, t);
             const int as = lt & 1;
-            if (e.colsum && tc.n_tile * BN != cs_n0) {
+            if (colsum_p && tc.n_tile * BN != cs_n0) {
                 if (cs_n0 >= 0) {
                     for (int i = 0; i < 4; ++i) {
                         const int col = cs_n0 + half * 32 + CSTEP * i + lane;
-                        if (half * 32 + CSTEP * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
+                        if (half * 32 + CSTEP * i < BN && col < p.N) atomicAdd(colsum_p + col, cs[i * 32 + lane]);
                         cs[i * 32 + lane] = 0.f;
                     }
                 }
@@ -220,12 +279,12 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
             }
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
-            const int row0 = tc.m_tile * BM + q * 32;     // first row of this warp's slab
+            const int row0 = tc.m_tile * TM + (int)rank * BM + q * 32;     // first row of this warp's slab
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
             const int n0 = tc.n_tile * BN;
             float rs = 1.0f;
-            if (e.rowscale && row_ok) rs = __ldg(e.rowscale + row / e.rows_per_scale);
+            if (!LIGHT && e.rowscale && row_ok) rs = __ldg(e.rowscale + row / e.rows_per_scale);
             for (int c0 = half * 32; c0 < BN; c0 += CSTEP) {
                 const int col0 = n0 + c0;
                 const bool full_cols = col0 + 32 <= p.N;
@@ -233,7 +292,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 // issue those loads BEFORE the TMEM load so their latency overlaps it (profiles/r2_ncu_gemm_fc2_dgrad_before_hoist.txt:
                 // long-scoreboard stall 8.6 issue slots per instruction when they were issued at the point of use)
                 uint4 uq[4];
-                const bool pre_u = e.mul_gelu_grad && row_ok && full_cols;
+                const bool pre_u = !LIGHT && e.mul_gelu_grad && row_ok && full_cols;
                 if (pre_u) {
                     const bf16* up = (const bf16*)e.mul_gelu_grad + (size_t)row * e.ld_mul + col0;
 #pragma unroll
@@ -246,21 +305,21 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (e.colscale) {
+                if (!LIGHT && e.colscale) {
                     // eval-mode BatchNorm folded into the GEMM: v = acc * scale[n] + shift[n] (shift arrives as `bias`)
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (col0 + j < p.N) f[j] = fmaf(f[j], __ldg(e.colscale + col0 + j), e.bias ? __ldg(e.bias + col0 + j) : 0.f);
-                } else if (e.bias) {
+                } else if (bias_p) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         if (full_cols) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_p + col0 + j));
                             f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
                         } else {
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
-                                if (col0 + j + u < p.N) f[j + u] += __ldg(e.bias + col0 + j + u);
+                                if (col0 + j + u < p.N) f[j + u] += __ldg(bias_p + col0 + j + u);
                         }
                     }
                 }
@@ -274,7 +333,8 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                 __syncwarp();
                 uint8_t* s_out = myslab + (size_t)buf * p.buf_bytes;
                 uint8_t* s_pre = s_out + p.out_slab;
-                const bool fused_act = p.has_preact && e.preact_mode == 1 && e.act == MDV_ACT_GELU;
+                const uint32_t s_out_u = smem_u32(s_out);
+                const bool fused_act = !LIGHT && p.has_preact && e.preact_mode == 1 && e.act == MDV_ACT_GELU;
                 if (fused_act) {
                     // one pass per pair: GELU, its derivative and the dropout scale share Phi(x), exp(-x^2/2) and the hash;
                     // out_preact receives gelu'(x) * mask/(1-p) — the factor the backward multiplies the gradient by
@@ -300,7 +360,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         }
                         *reinterpret_cast<uint4*>(s_pre + lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
-                } else {
+                } else if (!LIGHT) {
                 if (p.has_preact) {
                     // bf16 rows of 64 B, SWIZZLE_64B: 16B-chunk index ^= (row >> 1) & 3
 #pragma unroll
@@ -325,7 +385,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                     for (int j = 0; j < 32; ++j) f[j] = hardswish_f(f[j]);
                 }
                 }
-                if (e.mul_gelu_grad && row_ok) {
+                if (!LIGHT && e.mul_gelu_grad && row_ok) {
                     const bf16* up = (const bf16*)e.mul_gelu_grad + (size_t)row * e.ld_mul + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
@@ -346,7 +406,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         }
                     }
                 }
-                if (dthr && !fused_act) {
+                if (!LIGHT && dthr && !fused_act) {
                     // N and col0 are even: elements (2j, 2j+1) of this chunk share one hash
                     const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned)p.N + (unsigned)col0) >> 1);
 #pragma unroll
@@ -357,11 +417,11 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         f[2 * j + 1] = r.y;
                     }
                 }
-                if (e.rowscale) {
+                if (!LIGHT && e.rowscale) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] *= rs;
                 }
-                if (e.residual && row_ok) {
+                if (!LIGHT && e.residual && row_ok) {
                     const float* rp = e.residual + (size_t)row * e.ld_res + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -375,7 +435,7 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         }
                     }
                 }
-                if (e.colsum && !row_ok) {
+                if (colsum_p && !row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = 0.f;      // rows past M are clipped by the TMA store; keep them out of the sums
                 }
@@ -384,18 +444,18 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                     for (int j = 0; j < 4; ++j) {
                         uint4 pk = make_uint4(f2_to_bf2(f[8 * j], f[8 * j + 1]), f2_to_bf2(f[8 * j + 2], f[8 * j + 3]),
                                               f2_to_bf2(f[8 * j + 4], f[8 * j + 5]), f2_to_bf2(f[8 * j + 6], f[8 * j + 7]));
-                        *reinterpret_cast<uint4*>(s_out + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+                        sts128(s_out_u + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk);
                     }
                 } else {
                     // fp32 rows of 128 B, SWIZZLE_128B: 16B-chunk index ^= row & 7
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(s_out + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        sts128(s_out_u + lane * 128 + ((j ^ (lane & 7)) << 4),
+                               make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (e.colsum) {
+                if (colsum_p) {
                     // lane = column: walk the 32 rows of the staged (swizzled) tile
                     float s = 0.f;
                     if (out_bf16) {
@@ -409,10 +469,10 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                     }
                     cs[((c0 - half * 32) / CSTEP) * 32 + lane] += s;
                 }
-                if (lane == 0) {
+                if (lane == 0 && p.exp != 1) {
                     if (TN) tma_reduce_add_2d(&tmC, s_out, col0, row0);
                     else tma_store_2d(&tmC, s_out, col0, row0);
-                    if (p.has_preact) tma_store_2d(&tmP, s_pre, col0, row0);
+                    if (!LIGHT && p.has_preact) tma_store_2d(&tmP, s_pre, col0, row0);
                     tma_commit();
                 }
                 ++nstore;
@@ -420,12 +480,15 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
             // all of this warp's tcgen05.ld for the tile have completed -> hand the accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+                else mbar_arrive(&tempty_bar[as]);
+            }
         }
-        if (e.colsum && cs_n0 >= 0) {
+        if (colsum_p && cs_n0 >= 0) {
             for (int i = 0; i < 4; ++i) {
                 const int col = cs_n0 + half * 32 + CSTEP * i + lane;
-                if (half * 32 + CSTEP * i < BN && col < p.N) atomicAdd(e.colsum + col, cs[i * 32 + lane]);
+                if (half * 32 + CSTEP * i < BN && col < p.N) atomicAdd(colsum_p + col, cs[i * 32 + lane]);
             }
         }
         if (lane == 0) tma_wait_all();
@@ -433,38 +496,51 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // neither CTA leaves (or frees TMEM) while the other can still signal it / write into it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
 // ----------------------------------------------------------------------------- host side
 int g_force_bn = 0, g_force_stages = 0, g_force_split = 0, g_force_grid = 0;
+int g_force_light = [] {
+    const char* e = getenv("MDV_GEMM_LIGHT");
+    return e ? atoi(e) : 1;
+}();
+int g_force_pair = [] {
+    const char* e = getenv("MDV_GEMM_PAIR");
+    return e ? atoi(e) : -1;
+}();
 
-// widest tile (multiple of `step`, <= 256) that wastes the least of N; ties go to the wider tile
+// Tile width (multiple of `step`, <= 256).  Measured with the operand loads switched off (scripts/dev_gemm_bn.py, MDV_GEMM_EXP=4),
+// a K=16 MMA of width BN costs ~(224 + BN) units — a large width-independent part — so a wide tile that overhangs N by a few
+// percent beats a narrower exact fit: minimise n_tiles * (224 + BN); ties go to the wider tile.
 int pick_bn(int N, int step) {
     if (g_force_bn) return g_force_bn;
     int best = step;
-    double best_w = 1e9;
+    long long best_c = -1;
     for (int bn = 256; bn >= step; bn -= step) {
-        const double w = (double)mdv_cdiv(N, bn) * bn / N;
-        if (w < best_w - 1e-9) {
-            best_w = w;
+        const long long c = (long long)mdv_cdiv(N, bn) * (224 + bn);
+        if (best_c < 0 || c < best_c) {
+            best_c = c;
             best = bn;
         }
     }
     return best;
 }
 
-template <bool TN, int NEPI>
+template <bool TN, int NEPI, bool PAIR, bool LIGHT>
 int launch_n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp, GemmParams& p, cudaStream_t st) {
-    const size_t stage_bytes = (size_t)A_BYTES + (size_t)p.BN * BK * 2;
+    const size_t stage_bytes = (size_t)A_BYTES + (size_t)(PAIR ? p.BN / 2 : p.BN) * BK * 2;
     p.out_slab = (TN || !p.epi.out_bf16) ? 4096 : 2048;
     p.buf_bytes = p.out_slab + (p.has_preact ? 2048 : 0);
     // short-K tiles are epilogue-bound (deep store buffering); long-K tiles are MMA-bound (spend smem on operand stages)
     const int kbt = TN ? p.kb_per_split : mdv_cdiv(p.K, p.bk);
     p.nbuf = kbt <= 2 ? 4 : (kbt <= 8 ? 2 : 1);
+    if (p.exp == 2) p.nbuf = 4;
     if (NEPI > 8 && p.nbuf > 2) p.nbuf = 2;      // twice the warps: the same number of stores in flight
     const size_t cs_bytes = p.epi.colsum ? NEPI * 128 * sizeof(float) : 0;
     const size_t budget = 226 * 1024 - 1024 - 512;
@@ -483,14 +559,36 @@ int launch_n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc
     const size_t smem = stages * stage_bytes + slab_bytes + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<TN, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<TN, NEPI, PAIR, LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const int total_tiles = p.n_tiles * p.m_tiles * p.splits;
+    if (PAIR) {
+        // one cluster of two CTAs (a TPC) per tile walker
+        int pairs = total_tiles < MDV_NUM_SMS / 2 ? total_tiles : MDV_NUM_SMS / 2;
+        if (g_force_grid && g_force_grid / 2 < pairs && g_force_grid >= 2) pairs = g_force_grid / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(32 * (4 + NEPI));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_mdv_pdl ? 2 : 1;
+        cudaLaunchKernelEx(&cfg, gemm_kernel<TN, NEPI, PAIR, LIGHT>, ta, tb, tc, tp, p);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
     int grid = total_tiles < MDV_NUM_SMS ? total_tiles : MDV_NUM_SMS;
     if (g_force_grid && g_force_grid < grid) grid = g_force_grid;
-    mdv_launch((gemm_kernel<TN, NEPI>), dim3(grid), dim3(32 * (4 + NEPI)), smem, st, ta, tb, tc, tp, p);
+    mdv_launch((gemm_kernel<TN, NEPI, PAIR, LIGHT>), dim3(grid), dim3(32 * (4 + NEPI)), smem, st, ta, tb, tc, tp, p);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -502,11 +600,24 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     const MdvGemmEpi& e = p.epi;
     bool heavy = !TN && (e.act != MDV_ACT_NONE || e.mul_gelu_grad != nullptr || e.dropout_p > 0.f);
     if (g_force_nepi) heavy = g_force_nepi == 16;
-    if (heavy) {
-        const int rc = launch_n<TN, 16>(ta, tb, tc, tp, p, st);
-        if (rc != MDV_ERR_UNSUPPORTED) return rc;
+    // LIGHT: nothing but (bias,) column sums and the store
+    const bool light = !heavy && !e.rowscale && !e.residual && !e.colscale && !p.has_preact && g_force_light != 0;
+    if constexpr (TN) {
+        return launch_n<true, 8, false, true>(ta, tb, tc, tp, p, st);
+    } else {
+        if (p.pair) {
+            if (heavy) {
+                const int rc = launch_n<false, 16, true, false>(ta, tb, tc, tp, p, st);
+                if (rc != MDV_ERR_UNSUPPORTED) return rc;
+            }
+            return light ? launch_n<false, 8, true, true>(ta, tb, tc, tp, p, st) : launch_n<false, 8, true, false>(ta, tb, tc, tp, p, st);
+        }
+        if (heavy) {
+            const int rc = launch_n<false, 16, false, false>(ta, tb, tc, tp, p, st);
+            if (rc != MDV_ERR_UNSUPPORTED) return rc;
+        }
+        return light ? launch_n<false, 8, false, true>(ta, tb, tc, tp, p, st) : launch_n<false, 8, false, false>(ta, tb, tc, tp, p, st);
     }
-    return launch_n<TN, 8>(ta, tb, tc, tp, p, st);
 }
 
 }  // namespace
@@ -529,7 +640,18 @@ static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, i
     p.bk = tf32 ? 32 : 64;
     p.BN = pick_bn(N, 32);
     p.n_tiles = mdv_cdiv(N, p.BN);
-    p.m_tiles = mdv_cdiv(M, BM);
+    {
+        static const int exp = getenv("MDV_GEMM_EXP") ? atoi(getenv("MDV_GEMM_EXP")) : 0;
+        p.exp = exp;
+    }
+    // CTA pairs for long-K problems with enough 256-row tiles for every pair (they are bound by operand traffic and power: a
+    // pair moves 30-40% fewer operand bytes per flop).  Short-K tiles are epilogue bound and lose to the cross-CTA
+    // accumulator hand-shake (K=64: 31 -> 43 us), narrow tiles have no B half worth sharing (N=64: 55 -> 63 us), small problems
+    // would leave SMs idle.  MDV_GEMM_PAIR=0/1 overrides (A/B runs).
+    p.pair = g_force_pair >= 0 ? g_force_pair
+                               : (mdv_cdiv(K, p.bk) >= 8 && p.BN >= 128 && (long long)mdv_cdiv(M, 2 * BM) * p.n_tiles >= 2 * (MDV_NUM_SMS / 2));
+    if (M < 2 * BM) p.pair = 0;
+    p.m_tiles = mdv_cdiv(M, p.pair ? 2 * BM : BM);
     p.splits = 1;
     p.kb_per_split = mdv_cdiv(K, p.bk);
     p.has_preact = epi->out_preact != nullptr;
@@ -537,7 +659,7 @@ static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, i
     const int es = tf32 ? 4 : 2;
     int rc = make_map(&ta, A, es, K, M, lda, p.bk, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, W, es, K, N, ldw, p.bk, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map(&tb, W, es, K, N, ldw, p.bk, p.pair ? p.BN / 2 : p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (epi->out_bf16) rc = make_map(&tc, epi->out, 2, N, M, epi->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     else rc = make_map(&tc, epi->out, 4, N, M, epi->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
