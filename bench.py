@@ -24,7 +24,7 @@ METRIC = "mdvit_train_images_per_sec"
 UNIT = "images/s"
 IMG = 256
 F_TRAIN_GFLOP_PER_IMG = 62.3     # 3 x 20.77 GFLOP algorithmic fwd+bwd per image
-LINEAR_FUSE_DRAM_BYTES = 789904384    # 556.36 MB read + 233.54 MB write per launch (profiles/r1_ncu_gemm_linear_fuse.txt)
+LINEAR_FUSE_DRAM_BYTES = 557116416 + 236415744   # ncu --set full, profiles/r2_ncu_gemm_linear_fuse_fwd.txt (dram read + write, one launch)
 
 
 def parse():
@@ -245,7 +245,7 @@ def gemm_roofline(peaks, device, M, N, K, out_bf16, what, traffic=None, traffic_
     ms = _time_launch(lambda: L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "mdv_gemm_nt"), device)
     achieved = 2.0 * M * N * K / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": f"gemm_kernel<NT, 8 epilogue warps> (tcgen05) @ {what} M={M} N={N} K={K}", "achieved": achieved,
+    return {"bound": "tensor", "kernel": f"gemm_kernel<NT, 8 epilogue warps, CTA pair> (tcgen05 cta_group::2) @ {what} M={M} N={N} K={K}", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
             "algorithmic_flops_per_launch": 2.0 * M * N * K,
             "algorithmic_bytes_per_launch": (M * K + N * K) * 2 + M * N * (2 if out_bf16 else 4),
@@ -472,15 +472,15 @@ def main():
     value = imgs_per_step / (ms_res * 1e-3)
     e2e = imgs_per_step / (ms_e2e * 1e-3)
     if rank == 0:
-        # `roofline`: the time-dominant kernel of the step (gemm_kernel<NT,8>: 15% of the kernel time over 200 launches,
+        # `roofline`: the time-dominant kernel family of the step (gemm_kernel: 25% of the kernel time over ~350 launches,
         # profiles/r2_launches_step_graph_final.txt) at its heaviest shape, the linear_fuse input-gradient GEMM (8 launches,
-        # 2.1 ms per step); secondary views: the same kernel at the linear_fuse forward shape (r1's headline view), and the
+        # 2.0 ms per step; CTA-pair instantiation); secondary views: the same kernel at the linear_fuse forward shape (r1's headline view), and the
         # fused MLP kernels that replaced r1's issue-bound GELU / gelu'-epilogue GEMM family (HBM-bound views)
-        roof = gemm_roofline(peaks, dev, 32 * 4096, 2112, 512, True, "linear_fuse dgrad", 136498432 + 501603840,
+        roof = gemm_roofline(peaks, dev, 32 * 4096, 2112, 512, True, "linear_fuse dgrad", 136420864 + 500927232,
                              "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_ncu_gemm_linear_fuse_dgrad.txt")
         extra = {}
         for key, fn in (("roofline_linear_fuse_fwd", lambda: gemm_roofline(peaks, dev, 32 * 4096, 512, 2112, False, "linear_fuse forward", LINEAR_FUSE_DRAM_BYTES,
-                                                                             "ncu --set full dram bytes, profiles/r1_ncu_gemm_linear_fuse.txt")),
+                                                                             "ncu --set full dram bytes, profiles/r2_ncu_gemm_linear_fuse_fwd.txt")),
                         ("roofline_hbm_kernel", lambda: mlp_fused_roofline(peaks, dev, True)),
                         ("roofline_hbm_kernel_fwd", lambda: mlp_fused_roofline(peaks, dev, False))):
             try:

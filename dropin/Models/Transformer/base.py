@@ -6,4 +6,4 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from mdvit_b200.model import BASE  # noqa: E402,F401
+from mdvit_b200.model import BASE, BASE_DSN  # noqa: E402,F401

@@ -381,17 +381,22 @@ class _Trunk(nn.Module):
             enc.append((t, H, W))
         return enc
 
-    def _decode(self, enc, domain_label, d=None):
+    def _bridge(self, enc, d=None):
         t3, H3, W3 = enc[3]
         c0, n0, c1, n1 = self._bridge_parts(d)
-        out = ops.BridgeFn.apply(t3, c0.weight, c0.bias, n0.weight, n0.bias, c1.weight, c1.bias, n1.weight, n1.bias,
-                                 (n0.running_mean, n0.running_var, n0.num_batches_tracked,
-                                  n1.running_mean, n1.running_var, n1.num_batches_tracked), H3, W3, self.training)
-        h, w = H3, W3
-        for dec, (skip, H, W) in zip((self.decoder1, self.decoder2, self.decoder3, self.decoder4), (enc[3], enc[2], enc[1], enc[0])):
+        return ops.BridgeFn.apply(t3, c0.weight, c0.bias, n0.weight, n0.bias, c1.weight, c1.bias, n1.weight, n1.bias,
+                                  (n0.running_mean, n0.running_var, n0.num_batches_tracked,
+                                   n1.running_mean, n1.running_var, n1.num_batches_tracked), H3, W3, self.training)
+
+    def _decode_from(self, out, enc, decoders, domain_label, d=None):
+        h, w = enc[3][1], enc[3][2]
+        for dec, (skip, H, W) in zip(decoders, (enc[3], enc[2], enc[1], enc[0])):
             out = dec(out, h, w, skip, H, W, domain_label, d)
             h, w = H, W
         return out, h, w
+
+    def _decode(self, enc, domain_label, d=None):
+        return self._decode_from(self._bridge(enc, d), enc, (self.decoder1, self.decoder2, self.decoder3, self.decoder4), domain_label, d)
 
     def _head(self, dec4, h, w, img_size):
         fc = self.finalconv[0]
@@ -408,17 +413,31 @@ class MDViT(_Trunk):
         super().__init__()
         if qk_scale is not None:
             raise ValueError("mdvit_b200 implements qk_scale=None (head_dim**-0.5), the reference trainers' setting")
-        if decoder_name not in AUX_DECODERS:
-            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' (hard-coded by multi_train_MDViT.py:60) and 'MLP' "
-                                      "(mdvit.py:607-611); 'DeepLabV3' and 'Transformer' are not built")
+        if decoder_name not in AUX_DECODERS and decoder_name != 'Transformer':
+            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' (hard-coded by multi_train_MDViT.py:60), 'MLP' "
+                                      "(mdvit.py:607-611) and 'Transformer' (mdvit.py:613-642); 'DeepLabV3' is not built")
         self.decoder_name = decoder_name
         self._build_trunk(in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, drop_rate, attn_drop_rate,
                           drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains)
-        Aux = AUX_DECODERS[decoder_name]
-        self.debranch1 = Aux(embed_dims, 1, 512)
-        self.debranch2 = Aux(embed_dims, 1, 512)
-        self.debranch3 = Aux(embed_dims, 1, 512)
-        self.debranch4 = Aux(embed_dims, 1, 512)
+        if decoder_name == 'Transformer':
+            # mdvit.py:613-642: one more transformer decoder (4 stages without the domain adapter + a 1x1 head) per domain
+            debranchs = []
+            for _ in range(num_domains):
+                mh = [MHSA_stage_adapt(embed_dims[idx], num_layers[idx], num_heads[idx], mlp_ratios[idx], qkv_bias, drop_rate,
+                                       attn_drop_rate, drop_path_rate, num_domains, norm_layer, False) for idx in range(num_stages)]
+                debranchs.append(nn.ModuleList([
+                    UnetDecodingBlockTransformer(embed_dims[3] * 2, embed_dims[3], mh[3]),
+                    UnetDecodingBlockTransformer(embed_dims[3], embed_dims[2], mh[2]),
+                    UnetDecodingBlockTransformer(embed_dims[2], embed_dims[1], mh[1]),
+                    UnetDecodingBlockTransformer(embed_dims[1], embed_dims[0], mh[0]),
+                    nn.Sequential(nn.Conv2d(embed_dims[0], 1, kernel_size=1))]))
+            self.debranchs = nn.ModuleList(debranchs)
+        else:
+            Aux = AUX_DECODERS[decoder_name]
+            self.debranch1 = Aux(embed_dims, 1, 512)
+            self.debranch2 = Aux(embed_dims, 1, 512)
+            self.debranch3 = Aux(embed_dims, 1, 512)
+            self.debranch4 = Aux(embed_dims, 1, 512)
         # Inference-only switch (not a constructor argument: the signature stays the reference's).  The reference's test loop
         # passes `d`, computes the auxiliary decoder (45% of the forward FLOPs) and then uses only output[0]
         # (multi_train_MDViT.py:377-378).  With this flag set, an eval-mode forward returns [out, None] even when `d` is given.
@@ -430,16 +449,27 @@ class MDViT(_Trunk):
         enc = self._trunk_forward(x, domain_label)
         if not out_seg:
             return {'seg': None, 'feat': enc[3][0].mean(dim=1)}
-        dec4, h, w = self._decode(enc, domain_label)
+        bridge_out = self._bridge(enc)
+        dec4, h, w = self._decode_from(bridge_out, enc, (self.decoder1, self.decoder2, self.decoder3, self.decoder4), domain_label)
         out = self._head(dec4, h, w, img_size)
         aux_out = None
-        if d in ('0', '1', '2', '3') and (self.training or not self.skip_aux_in_eval):
+        if self.decoder_name == 'Transformer':
+            branch = self.debranchs[int(d)]          # (mdvit.py:704-706: int(d) is unconditional for this decoder)
+            if self.training or not self.skip_aux_in_eval:
+                aux_out = self._transformer_aux(branch, bridge_out, enc, img_size)
+        elif d in ('0', '1', '2', '3') and (self.training or not self.skip_aux_in_eval):
             branch = getattr(self, f'debranch{int(d) + 1}')
             feats = [e[0] for e in enc] + [dec4]
             aux_out = branch(feats, [(e[1], e[2]) for e in enc], img_size)
         if out_feat:
             return {'seg': [out, aux_out], 'feat': enc[3][0].mean(dim=1)}
         return [out, aux_out]
+
+    def _transformer_aux(self, branch, bridge_out, enc, img_size):
+        """mdvit.py:704-712: the per-domain transformer decoder on the shared bridge output and encoder skips (no DA gate)."""
+        a4, h, w = self._decode_from(bridge_out, enc, (branch[0], branch[1], branch[2], branch[3]), None)
+        fc = branch[4][0]
+        return ops.HeadFn.apply(a4, fc.weight, fc.bias, h, w, int(img_size[0]), int(img_size[1]))
 
     def forward_multi(self, x, domain_label, domains):
         """The G single-domain forwards of one training step (multi_train_MDViT.py:129-146 calls forward once per domain)
@@ -455,14 +485,19 @@ class MDViT(_Trunk):
         img_size = x.shape[2:]
         with ops.bn_groups(G if self.training else 1):
             enc = self._trunk_forward(x, domain_label)
-            dec4, h, w = self._decode(enc, domain_label)
+            bridge_out = self._bridge(enc)
+            dec4, h, w = self._decode_from(bridge_out, enc, (self.decoder1, self.decoder2, self.decoder3, self.decoder4), domain_label)
         out = self._head(dec4, h, w, img_size)
         # per-domain slices of the five feature maps the auxiliary decoders read, and of the main logits
-        split = [ops.SplitDomainsFn.apply(t, G) for t in [e[0] for e in enc] + [dec4, out]]
+        fifth = bridge_out if self.decoder_name == 'Transformer' else dec4
+        split = [ops.SplitDomainsFn.apply(t, G) for t in [e[0] for e in enc] + [fifth, out]]
         res = []
         for g, d in enumerate(domains):
             aux_out = None
-            if d in ('0', '1', '2', '3'):
+            if self.decoder_name == 'Transformer':
+                enc_g = [(split[i][g], enc[i][1], enc[i][2]) for i in range(4)]
+                aux_out = self._transformer_aux(self.debranchs[int(d)], split[4][g], enc_g, img_size)
+            elif d in ('0', '1', '2', '3'):
                 branch = getattr(self, f'debranch{int(d) + 1}')
                 aux_out = branch([split[i][g] for i in range(5)], [(e[1], e[2]) for e in enc], img_size)
             res.append((split[5][g], aux_out))
@@ -483,7 +518,7 @@ class MDViT_DSN(_Trunk):
         super().__init__()
         if qk_scale is not None or num_stages != 4 or in_chans != 3 or conv_norm is not nn.BatchNorm2d:
             raise ValueError("mdvit_b200 implements the 4-stage, 3-channel, BatchNorm2d configuration of the reference trainers")
-        if decoder_name not in AUX_DECODERS:
+        if decoder_name is not None and decoder_name not in AUX_DECODERS:      # (None: BASE_DSN, no auxiliary branches)
             raise NotImplementedError("mdvit_b200 implements decoder_name in ('MLPFM', 'MLP') for MDViT_DSN")
         self.num_stages, self.decoder_name, self.embed_dims = num_stages, decoder_name, list(embed_dims)
         self.stem_1 = Conv2d_BN_M(in_chans, embed_dims[0] // 2, 3, 2, 1, act_layer=nn.Hardswish, num_domains=num_domains)
@@ -509,11 +544,12 @@ class MDViT_DSN(_Trunk):
         self.decoder3 = UnetDecodingBlockTransformer(embed_dims[2], embed_dims[1], self.mhsa_list[1], num_domains)
         self.decoder4 = UnetDecodingBlockTransformer(embed_dims[1], embed_dims[0], self.mhsa_list[0], num_domains)
         self.finalconv = nn.Sequential(nn.Conv2d(embed_dims[0], 1, kernel_size=1))
-        Aux = AUX_DECODERS[decoder_name]
-        self.debranch1 = Aux(embed_dims, 1, 512)
-        self.debranch2 = Aux(embed_dims, 1, 512)
-        self.debranch3 = Aux(embed_dims, 1, 512)
-        self.debranch4 = Aux(embed_dims, 1, 512)
+        if decoder_name is not None:
+            Aux = AUX_DECODERS[decoder_name]
+            self.debranch1 = Aux(embed_dims, 1, 512)
+            self.debranch2 = Aux(embed_dims, 1, 512)
+            self.debranch3 = Aux(embed_dims, 1, 512)
+            self.debranch4 = Aux(embed_dims, 1, 512)
         self.skip_aux_in_eval = False
         self.apply(self._init_weights)
 
@@ -538,6 +574,30 @@ class MDViT_DSN(_Trunk):
         if out_feat:
             return {'seg': [out, aux_out], 'feat': enc[3][0].mean(dim=1)}
         return [out, aux_out]
+
+
+class BASE_DSN(MDViT_DSN):
+    """Drop-in for Models.Transformer.base.BASE_DSN (base.py:515-696): BASE with domain-specific norms — the MDViT_DSN trunk
+    without auxiliary branches; forward(x, domain_label, d) returns the main logits only (base.py:651-693)."""
+
+    def __init__(self, img_size=512, in_chans=3, num_stages=4, num_layers=[2, 2, 2, 2], embed_dims=[64, 128, 320, 512],
+                 mlp_ratios=[8, 8, 4, 4], num_heads=[8, 8, 8, 8], qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), conv_norm=nn.BatchNorm2d, adapt_method=None,
+                 num_domains=4, feature_dim=512, **kwargs):
+        super().__init__(img_size, in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, qk_scale, drop_rate,
+                         attn_drop_rate, drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains, decoder_name=None)
+
+    def forward(self, x, domain_label=None, d=None, out_feat=False, out_seg=True):
+        img_size = x.shape[2:]
+        int(d)      # base.py:230-280,672: the norm lists are indexed with int(d)
+        enc = self._trunk_forward(x, domain_label, d)
+        if not out_seg:
+            return {'seg': None, 'feat': enc[3][0].mean(dim=1)}
+        dec4, h, w = self._decode(enc, domain_label, d)
+        out = self._head(dec4, h, w, img_size)
+        if out_feat:
+            return {'seg': out, 'feat': enc[3][0].mean(dim=1)}      # (pooled, base.py:688-690 — unlike BASE.forward)
+        return out
 
 
 class BASE(_Trunk):

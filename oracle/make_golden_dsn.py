@@ -16,9 +16,13 @@ from oracle import ref_shim  # noqa: E402
 from oracle.make_golden import fingerprint  # noqa: E402
 
 
+def aux_state(model, prefix="debranch"):
+    """Deterministic weights for the auxiliary-decoder tensors of a model (synth_tensor handles any key/shape)."""
+    return {k: synth.synth_tensor(k, tuple(v.shape)) for k, v in model.state_dict().items() if k.startswith(prefix)}
+
+
 def mlp_aux_state(model):
-    """Deterministic weights for the debranch* tensors of a decoder_name='MLP' model (synth_tensor handles any key/shape)."""
-    return {k: synth.synth_tensor(k, tuple(v.shape)) for k, v in model.state_dict().items() if k.startswith("debranch")}
+    return aux_state(model, "debranch")
 
 
 def main():
@@ -52,6 +56,36 @@ def main():
             dl = torch.nn.functional.one_hot(torch.full((2,), 2), 4).float()
             o, a = m(img, dl, "2")
             out[f"mlp_{mode}_out"], out[f"mlp_{mode}_aux"] = o.numpy(), a.numpy()
+    # ---- MDViT with the 'Transformer' auxiliary decoder (mdvit.py:613-642,704-712): one extra 4-stage decoder per domain
+    torch.manual_seed(0)
+    m = MDViT(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="Transformer")
+    out["tr_keys"] = np.asarray(list(m.state_dict().keys()))
+    out["tr_init_fp"] = fingerprint(list(m.named_parameters()))
+    m.load_state_dict(synth.synth_state_dict(0, aux=False) | aux_state(m, "debranchs"), strict=True)
+    with torch.no_grad():
+        for mode in ("eval", "train"):
+            m.train(mode == "train")
+            for d in (0, 3):
+                img, _ = synth.synth_batch(14, d, 2, 64, 64)
+                dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float()
+                o, a = m(img, dl, str(d))
+                out[f"tr_{mode}_out_{d}"], out[f"tr_{mode}_aux_{d}"] = o.numpy(), a.numpy()
+    # ---- BASE_DSN (Models/Transformer/base.py:515-696): the DSN trunk without auxiliary branches, Sup and plain attention
+    from Models.Transformer.base import BASE_DSN
+    for am in ("Sup", None):
+        tag = "sup" if am else "plain"
+        torch.manual_seed(0)
+        m = BASE_DSN(img_size=64, adapt_method=am, num_domains=4)
+        out[f"base_dsn_{tag}_keys"] = np.asarray(list(m.state_dict().keys()))
+        out[f"base_dsn_{tag}_init_fp"] = fingerprint(list(m.named_parameters()))
+        m.load_state_dict(synth.dsn_perturb(m.state_dict()), strict=True)
+        with torch.no_grad():
+            for mode in ("eval", "train"):
+                m.train(mode == "train")
+                for d in (0, 2):
+                    img, _ = synth.synth_batch(13, d, 2, 64, 64)
+                    dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float() if am else None
+                    out[f"base_dsn_{tag}_{mode}_{d}"] = m(img, dl, str(d)).numpy()
     path = os.path.join(ROOT, "tests", "golden", "mdvit_dsn_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

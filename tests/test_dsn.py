@@ -32,6 +32,8 @@ def test_dsn_state_dict_schema_and_random_init_match_the_reference(dgold):
     assert len(MDViT_DSN(img_size=64, adapt_method="Sup").state_dict()) == 980     # the reference default decoder_name is "MLP"
     with pytest.raises(NotImplementedError):
         MDViT_DSN(img_size=64, decoder_name="DeepLabV3")
+    with pytest.raises(NotImplementedError):
+        MDViT_DSN(img_size=64, decoder_name="Transformer")
     assert list(MDViT(img_size=64, adapt_method="Sup", decoder_name="MLP").state_dict().keys()) == [str(k) for k in dgold["mlp_keys"]]
 
 
@@ -68,6 +70,108 @@ def test_dsn_logits_match_reference_golden(dgold):
         assert rel(o_other, outs[("eval", 1)].cpu()) > 5e-2
     with pytest.raises((TypeError, ValueError)):
         m(img.to(dev), dl, None)          # int(d) is required by the reference as well
+
+
+def test_transformer_aux_decoder_schema_and_random_init_match_the_reference(dgold):
+    """decoder_name='Transformer' (mdvit.py:613-642): 1460 state_dict keys, bit-identical init."""
+    from mdvit_b200.model import MDViT
+    torch.manual_seed(0)
+    m = MDViT(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="Transformer")
+    assert list(m.state_dict().keys()) == [str(k) for k in dgold["tr_keys"]] and len(dgold["tr_keys"]) == 1460
+    fp = fingerprint(list(m.named_parameters()))
+    assert np.abs(fp - dgold["tr_init_fp"]).max() <= 1e-9 * np.abs(dgold["tr_init_fp"]).max()
+    with pytest.raises(NotImplementedError):
+        MDViT(img_size=64, decoder_name="DeepLabV3")
+
+
+@pytest.mark.gpu
+def test_transformer_aux_decoder_logits_match_reference_golden(dgold):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200 import ops
+    from mdvit_b200.model import MDViT
+    from oracle.make_golden_dsn import aux_state
+    dev = torch.device("cuda")
+    m = MDViT(img_size=64, adapt_method="Sup", num_domains=4, decoder_name="Transformer")
+    m.load_state_dict(synth.synth_state_dict(0, aux=False) | aux_state(m, "debranchs"), strict=True)
+    m = m.to(dev)
+
+    def rel(a, b):
+        b = torch.as_tensor(b)
+        return ((a.detach().float().cpu() - b).abs().max() / b.abs().max()).item()
+
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        for d in (0, 3):
+            img, lab = synth.synth_batch(14, d, 2, 64, 64)
+            dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float().to(dev)
+            with torch.no_grad():
+                o, a = m(img.to(dev), dl, str(d))
+            # (the auxiliary logits are small here — abs-max ~1.2 after 8 more bf16 blocks — so max-abs/abs-max is the noisier
+            # figure; the error is a smooth offset of ~1e-2 absolute, the same size as the main output's: bound both ratios at 4e-2)
+            assert rel(o, dgold[f"tr_{mode}_out_{d}"]) < 2e-2 and rel(a, dgold[f"tr_{mode}_aux_{d}"]) < 4e-2, (mode, d)
+            ra = torch.as_tensor(dgold[f"tr_{mode}_aux_{d}"])
+            assert ((a.float().cpu() - ra).norm() / ra.norm()).item() < 4e-2, (mode, d)
+    # the stacked multi-domain forward gives the same auxiliary logits as the per-domain calls (eval: no batch statistics;
+    # the train-mode forwards above moved the BatchNorm running statistics: restore them first)
+    m.load_state_dict({k: v.to(dev) for k, v in (synth.synth_state_dict(0, aux=False) | aux_state(m, "debranchs")).items()}, strict=True)
+    m.eval()
+    imgs = torch.cat([synth.synth_batch(14, d, 2, 64, 64)[0] for d in (0, 3)]).to(dev)
+    dls = torch.cat([torch.nn.functional.one_hot(torch.full((2,), d), 4).float() for d in (0, 3)]).to(dev)
+    with torch.no_grad():
+        res = m.forward_multi(imgs, dls, ["0", "3"])
+    for (o, a), d in zip(res, (0, 3)):
+        assert rel(o, dgold[f"tr_eval_out_{d}"]) < 2e-2 and rel(a, dgold[f"tr_eval_aux_{d}"]) < 4e-2
+    # and it trains: only the selected domain's decoder receives gradients
+    m.train()
+    o, a = m(img.to(dev), dl, "3")
+    ops.seg_losses(o, a, lab.to(dev)).sum().backward()
+    g3 = [p.grad for n, p in m.named_parameters() if n.startswith("debranchs.3.")]
+    assert all(g is not None and torch.isfinite(g).all().item() for g in g3)
+    assert all(p.grad is None or p.grad.abs().max().item() == 0 for n, p in m.named_parameters() if n.startswith("debranchs.0."))
+    with pytest.raises((TypeError, ValueError)):
+        m(img.to(dev), dl, None)
+
+
+@pytest.mark.parametrize("am", ["Sup", None])
+def test_base_dsn_schema_and_random_init_match_the_reference(dgold, am):
+    """BASE_DSN (base.py:515-696): 912 / 848 state_dict keys, bit-identical stock-constructor init."""
+    from mdvit_b200.model import BASE_DSN
+    tag = "sup" if am else "plain"
+    torch.manual_seed(0)
+    m = BASE_DSN(img_size=64, adapt_method=am, num_domains=4)
+    assert list(m.state_dict().keys()) == [str(k) for k in dgold[f"base_dsn_{tag}_keys"]]
+    fp = fingerprint(list(m.named_parameters()))
+    ref = dgold[f"base_dsn_{tag}_init_fp"]
+    assert np.abs(fp - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("am", ["Sup", None])
+def test_base_dsn_logits_match_reference_golden(dgold, am):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200.model import BASE_DSN
+    dev = torch.device("cuda")
+    tag = "sup" if am else "plain"
+    torch.manual_seed(0)
+    m = BASE_DSN(img_size=64, adapt_method=am, num_domains=4)
+    m.load_state_dict(synth.dsn_perturb(m.state_dict()), strict=True)
+    m = m.to(dev)
+    with torch.no_grad():
+        for mode in ("eval", "train"):
+            m.train(mode == "train")
+            for d in (0, 2):
+                img, _ = synth.synth_batch(13, d, 2, 64, 64)
+                dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float().to(dev) if am else None
+                o = m(img.to(dev), dl, str(d))
+                ref = torch.as_tensor(dgold[f"base_dsn_{tag}_{mode}_{d}"])
+                assert tuple(o.shape) == tuple(ref.shape)
+                assert ((o.float().cpu() - ref).abs().max() / ref.abs().max()).item() < 2e-2, (mode, d)
+        m.eval()
+        f = m(img.to(dev), dl, "2", out_feat=True)
+        assert tuple(f["feat"].shape) == (2, 512) and tuple(f["seg"].shape) == (2, 1, 64, 64)
+        assert m(img.to(dev), dl, "2", out_seg=False)["seg"] is None
 
 
 @pytest.mark.gpu
