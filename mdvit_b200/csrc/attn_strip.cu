@@ -26,6 +26,7 @@ struct Cfg {
     static constexpr int CPW = 2 * ACT;                       // channels per warp / group
     static constexpr int KR = CH <= 16 ? CH : CH / 2;         // k-range per block of the outer-product kernel
     static constexpr int KSPLIT = CH / KR;
+    static_assert(KR * KSPLIT == CH, "k-range split");
 };
 
 __host__ __device__ inline int win_of_head(int h) { return h < 2 ? 3 : (h < 5 ? 5 : 7); }
@@ -748,6 +749,153 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// ------------------------------------------------------------------------------------------------ cross-token sums on tensor cores
+// Ch >= 40 (stages 2 / 3): part[k,v] = sum_n P[n,k] V'[n,v] is a (Ch x tokens).(tokens x Ch) product per head — as shuffled FFMA2
+// outer products it was issue bound at 14x its HBM time.  Here: mma.sync m16n8k16 bf16, fp32 accumulation.  A tile of 64 tokens
+// of both operands is staged in shared memory as plain [token][channel] bf16 rows (pitch padded by 16 B: conflict-free
+// ldmatrix); ldmatrix.trans turns the token-major rows into the K-major fragments.  One warp per 8-column n-tile, all m-tiles.
+//   MODE 0: P = exp(K - kmax) is split into bf16 hi + lo parts (two MMAs per fragment): the sums keep fp32-level accuracy;
+//           zpart is accumulated from the fp32 values during staging.
+//   MODE 1: P = Q, V' = dY; the gate g[v] is a column factor and is applied to the finished sums.
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t& r0, uint32_t& r1, uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(saddr));
+}
+
+template <int CH, int MODE>
+__global__ void __launch_bounds__(32 * (CH / 8)) attn_outer_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+                                                                       const float* __restrict__ gate, const float* __restrict__ kmax,
+                                                                       float* __restrict__ part, float* __restrict__ zpart, int N, int C,
+                                                                       int rows_per_block, int nchunk) {
+    MDV_PDL_SYNC();
+    constexpr int NP = CH / 8;                 // 16-byte parts per token row = warps = n-tiles
+    constexpr int NT = 32 * NP;
+    constexpr int MT = (CH + 15) / 16;         // m-tiles (Ch = 40: rows 40..47 are zero padding)
+    constexpr int PITCH = MT * 32 + 16;        // bytes per staged token row
+    constexpr int TT = 64;                     // tokens per tile
+    __shared__ __align__(16) uint8_t sPh[TT * PITCH];
+    __shared__ __align__(16) uint8_t sPl[MODE == 0 ? TT * PITCH : 16];
+    __shared__ __align__(16) uint8_t sV[TT * PITCH];
+    __shared__ float sZ[MODE == 0 ? 32 * CH : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, h = blockIdx.y, chunk = blockIdx.x;
+    const int r0 = chunk * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    const int prt = threadIdx.x % NP, prow = threadIdx.x / NP;       // staging role: 8 channels of token (tile row prow, prow + 32)
+    const int cb = h * CH + prt * 8;                                  // first channel of this thread's part
+    const bf16* base = qkv + (size_t)b * N * 3 * C;
+    // zero the padding columns once (never written again)
+    for (int i = threadIdx.x; i < TT * PITCH / 16; i += NT) {
+        reinterpret_cast<uint4*>(sPh)[i] = make_uint4(0, 0, 0, 0);
+        if (MODE == 0) reinterpret_cast<uint4*>(sPl)[i] = make_uint4(0, 0, 0, 0);
+    }
+    float km[8], z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        km[j] = MODE == 0 ? kmax[(size_t)b * C + cb + j] : 0.f;
+        z[j] = 0.f;
+    }
+    float acc[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+    const uint32_t sph = (uint32_t)__cvta_generic_to_shared(sPh), spl = (uint32_t)__cvta_generic_to_shared(sPl),
+                   sv = (uint32_t)__cvta_generic_to_shared(sV);
+    // ldmatrix row addresses of this lane: A (x4.trans): token = k0 + (lane & 7) + ((lane >> 4) << 3), column = m0 + ((lane >> 3) & 1) * 8
+    const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16);
+    // B (x2.trans): token = k0 + (lane & 7) + ((lane >> 3) & 1) * 8, column = 8 * warp
+    const uint32_t b_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + warp * 16);
+    __syncthreads();
+    for (int t0 = r0; t0 < r1; t0 += TT) {
+        // ---- stage the tile (two token rows per thread)
+        uint4 pv[2], vv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int n = t0 + prow + 32 * u;
+            pv[u] = vv[u] = make_uint4(0, 0, 0, 0);
+            if (n < r1) {
+                if (MODE == 0) {
+                    pv[u] = *reinterpret_cast<const uint4*>(base + (size_t)n * 3 * C + C + cb);
+                    vv[u] = *reinterpret_cast<const uint4*>(base + (size_t)n * 3 * C + 2 * C + cb);
+                } else {
+                    pv[u] = *reinterpret_cast<const uint4*>(base + (size_t)n * 3 * C + cb);
+                    vv[u] = *reinterpret_cast<const uint4*>(dy + ((size_t)b * N + n) * C + cb);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int n = t0 + prow + 32 * u;
+            const uint32_t so = (uint32_t)((prow + 32 * u) * PITCH + prt * 16);
+            if (MODE == 0) {
+                const uint32_t w4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const float2 kk = bf2_to_f2(w4[w]);
+                    float2 p = make_float2(0.f, 0.f);
+                    if (n < r1) p = make_float2(__expf(kk.x - km[2 * w]), __expf(kk.y - km[2 * w + 1]));
+                    z[2 * w] += p.x;
+                    z[2 * w + 1] += p.y;
+                    hi[w] = f2_to_bf2(p.x, p.y);
+                    const float2 hf = bf2_to_f2(hi[w]);
+                    lo[w] = f2_to_bf2(p.x - hf.x, p.y - hf.y);
+                }
+                *reinterpret_cast<uint4*>(sPh + so) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(sPl + so) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            } else {
+                *reinterpret_cast<uint4*>(sPh + so) = pv[u];
+            }
+            *reinterpret_cast<uint4*>(sV + so) = vv[u];
+        }
+        __syncthreads();
+        // ---- 4 k-steps of 16 tokens
+#pragma unroll
+        for (int ks = 0; ks < TT / 16; ++ks) {
+            uint32_t b0, b1;
+            ldsm_x2_t(b0, b1, sv + ks * 16 * PITCH + b_off);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                uint32_t a[4];
+                ldsm_x4_t(a, sph + ks * 16 * PITCH + m * 32 + a_off);
+                mma_bf16_16816(acc[m], a, b0, b1);
+                if (MODE == 0) {
+                    ldsm_x4_t(a, spl + ks * 16 * PITCH + m * 32 + a_off);
+                    mma_bf16_16816(acc[m], a, b0, b1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- results: acc[m] = rows k = 16 m + g (+8), columns v = 8 warp + 2 t (+1)
+    const int g = lane >> 2, t = lane & 3;
+    const int v = warp * 8 + 2 * t;
+    float2 gt = make_float2(1.f, 1.f);
+    if (MODE == 1 && gate) gt = *reinterpret_cast<const float2*>(gate + (size_t)b * C + h * CH + v);
+    float* pbase = part + (((size_t)(b * nchunk + chunk) * C) + h * CH) * CH;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int k0 = 16 * m + g;
+        if (k0 < CH) *reinterpret_cast<float2*>(pbase + (size_t)k0 * CH + v) = make_float2(acc[m][0] * gt.x, acc[m][1] * gt.y);
+        if (k0 + 8 < CH) *reinterpret_cast<float2*>(pbase + (size_t)(k0 + 8) * CH + v) = make_float2(acc[m][2] * gt.x, acc[m][3] * gt.y);
+    }
+    if (MODE == 0) {
+        // zpart[c] = sum over this chunk's tokens of exp(K - kmax): every thread summed 8 channels over its rows
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sZ[prow * CH + prt * 8 + j] = z[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < CH; c += NT) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) s += sZ[r * CH + c];
+            zpart[(size_t)(b * nchunk + chunk) * C + h * CH + c] = s;
+        }
+    }
+}
+
+
 template <int CH>
 __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                           const bf16* __restrict__ ein, const float* __restrict__ gate,
@@ -1042,14 +1190,29 @@ template <int CH, int MODE>
 int launch_outer(const bf16* qkv, const bf16* dy, const float* gate, const float* kmax, float* part, float* zpart, int B, int N, int C,
                  int& nchunk, cudaStream_t st) {
     using G = Cfg<CH>;
-    const int by = (C / G::CPW) * G::KSPLIT;
-    nchunk = chunks_for(B, N, by);
-    int rpb = mdv_cdiv(N, nchunk);
-    rpb = ((rpb + 31) / 32) * 32;
-    nchunk = mdv_cdiv(N, rpb);
-    mdv_launch((attn_outer_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(256), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
-    MDV_CHECK_LAUNCH();
-    return MDV_OK;
+    if constexpr (CH >= 40) {
+        // tensor-core version: one CTA per (token chunk, head, image); the chunk count stays within the scratch sized by max_chunks()
+        const int by = C / CH;
+        nchunk = chunks_for(B, N, by);
+        const int mc = max_chunks(B, C, CH);
+        if (nchunk > mc) nchunk = mc;
+        int rpb = mdv_cdiv(N, nchunk);
+        rpb = ((rpb + 63) / 64) * 64;
+        nchunk = mdv_cdiv(N, rpb);
+        mdv_launch((attn_outer_mma_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(32 * (CH / 8)), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb,
+                   nchunk);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    } else {
+        const int by = (C / G::CPW) * G::KSPLIT;
+        nchunk = chunks_for(B, N, by);
+        int rpb = mdv_cdiv(N, nchunk);
+        rpb = ((rpb + 31) / 32) * 32;
+        nchunk = mdv_cdiv(N, rpb);
+        mdv_launch((attn_outer_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(256), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
 }
 
 template <int CH>

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __re
         for (int t = 0; t < 10; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         Row3 r0 = load_row3(img + (size_t)(y0 - 1) * L, p, C, y0 > 0, left_ok, right_ok);
         Row3 r1 = load_row3(img + (size_t)y0 * L, p, C, true, left_ok, right_ok);
+#pragma unroll 4
         for (int y = y0; y < y1; ++y) {
             const Row3 r2 = load_row3(img + (size_t)(y + 1) * L, p, C, y + 1 < H, left_ok, right_ok);
             const float4 g = ld4(gimg + (size_t)y * L + p);
@@ -827,7 +828,9 @@ extern "C" int mdv_dwconv3_wgrad(const float* dy, const float* x, float* dw, flo
     if (!dy || !x || !dw || B <= 0) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * Hi * Wi * C)) return MDV_ERR_UNSUPPORTED;
     if (stride == 1 && Hi == Ho && Wi == Wo && !(C & 3) && C * 40 <= 48 * 1024) {
-        const int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
+        // long row segments: the per-thread tail (40 shared + the block's global atomics) is amortised over more rows
+        int seg = Hi >= 64 ? 16 : (Hi >= 16 ? 8 : Hi);
+        while (seg < Hi && seg < 64 && (long long)mdv_cdiv((long long)Wi * C, 1024) * mdv_cdiv(Hi, 2 * seg) * B >= 4 * MDV_NUM_SMS) seg *= 2;
         dim3 grid(mdv_cdiv((long long)Wi * C, 1024), mdv_cdiv(Hi, seg), B);
         mdv_launch(dwconv3_s1_wgrad_kernel, dim3(grid), dim3(256), (size_t)C * 10 * sizeof(float), (cudaStream_t)stream, dy, x, dw, db, Hi, Wi, C, seg);
         MDV_CHECK_LAUNCH();
