@@ -10,6 +10,8 @@
 //
 // Channel groups: a warp handles CPW = 64 channels (8 heads at Ch=8, 4 at Ch=16, 1 at Ch=64) or one 40-channel head
 // (20 active lanes) at Ch=40.  The convolution window of a group is that of its last head (windows grow with the head).
+#include <cstdlib>
+
 #include "attn_internal.cuh"
 
 namespace {
@@ -764,26 +766,31 @@ __device__ __forceinline__ void ldsm_x2_t(uint32_t& r0, uint32_t& r1, uint32_t s
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(saddr));
 }
 
+// A CTA covers one channel group: a whole head for Ch >= 40, 64 channels (8 or 4 heads) for Ch = 8 / 16 — there an n-tile only
+// needs the m-tile that holds its own head (for Ch = 8 half of that 16-row tile belongs to the neighbouring head and is dropped).
 template <int CH, int MODE>
-__global__ void __launch_bounds__(32 * (CH / 8)) attn_outer_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(32 * ((CH <= 16 ? 64 : CH) / 8)) attn_outer_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                                        const float* __restrict__ gate, const float* __restrict__ kmax,
                                                                        float* __restrict__ part, float* __restrict__ zpart, int N, int C,
                                                                        int rows_per_block, int nchunk) {
     MDV_PDL_SYNC();
-    constexpr int NP = CH / 8;                 // 16-byte parts per token row = warps = n-tiles
+    constexpr int CPB = CH <= 16 ? 64 : CH;    // channels per CTA
+    constexpr int NP = CPB / 8;                // 16-byte parts per token row = warps = n-tiles
     constexpr int NT = 32 * NP;
-    constexpr int MT = (CH + 15) / 16;         // m-tiles (Ch = 40: rows 40..47 are zero padding)
-    constexpr int PITCH = MT * 32 + 16;        // bytes per staged token row
+    constexpr int MTALL = (CPB + 15) / 16;     // m-tiles of the staged tile (Ch = 40: rows 40..47 are zero padding)
+    constexpr int MT = CH <= 16 ? 1 : MTALL;   // m-tiles a warp multiplies
+    constexpr int PITCH = MTALL * 32 + 16;     // bytes per staged token row
     constexpr int TT = 64;                     // tokens per tile
     __shared__ __align__(16) uint8_t sPh[TT * PITCH];
     __shared__ __align__(16) uint8_t sPl[MODE == 0 ? TT * PITCH : 16];
     __shared__ __align__(16) uint8_t sV[TT * PITCH];
-    __shared__ float sZ[MODE == 0 ? 32 * CH : 1];
+    __shared__ float sZ[MODE == 0 ? 32 * CPB : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.z, h = blockIdx.y, chunk = blockIdx.x;
+    const int b = blockIdx.z, cg0 = blockIdx.y * CPB, chunk = blockIdx.x;
     const int r0 = chunk * rows_per_block, r1 = min(N, r0 + rows_per_block);
     const int prt = threadIdx.x % NP, prow = threadIdx.x / NP;       // staging role: 8 channels of token (tile row prow, prow + 32)
-    const int cb = h * CH + prt * 8;                                  // first channel of this thread's part
+    const int cb = cg0 + prt * 8;                                     // first channel of this thread's part
+    const int m_base = CH <= 16 ? ((warp * 8) / 16) * 16 : 0;         // first row (group channel) of this warp's m-tiles
     const bf16* base = qkv + (size_t)b * N * 3 * C;
     // zero the padding columns once (never written again)
     for (int i = threadIdx.x; i < TT * PITCH / 16; i += NT) {
@@ -804,7 +811,7 @@ __global__ void __launch_bounds__(32 * (CH / 8)) attn_outer_mma_kernel(const bf1
     const uint32_t sph = (uint32_t)__cvta_generic_to_shared(sPh), spl = (uint32_t)__cvta_generic_to_shared(sPl),
                    sv = (uint32_t)__cvta_generic_to_shared(sV);
     // ldmatrix row addresses of this lane: A (x4.trans): token = k0 + (lane & 7) + ((lane >> 4) << 3), column = m0 + ((lane >> 3) & 1) * 8
-    const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16);
+    const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 16 + m_base * 2);
     // B (x2.trans): token = k0 + (lane & 7) + ((lane >> 3) & 1) * 8, column = 8 * warp
     const uint32_t b_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + warp * 16);
     __syncthreads();
@@ -869,28 +876,33 @@ __global__ void __launch_bounds__(32 * (CH / 8)) attn_outer_mma_kernel(const bf1
         }
         __syncthreads();
     }
-    // ---- results: acc[m] = rows k = 16 m + g (+8), columns v = 8 warp + 2 t (+1)
+    // ---- results: acc[m] = rows (group channel) m_base + 16 m + g (+8), columns (group channel) 8 warp + 2 t (+1);
+    //      part[b][chunk][c = head * CH + k][v]: only the rows of the column's own head are kept
     const int g = lane >> 2, t = lane & 3;
-    const int v = warp * 8 + 2 * t;
+    const int vg = warp * 8 + 2 * t;                  // column within the group
+    const int hv = vg / CH;                           // its head within the group
     float2 gt = make_float2(1.f, 1.f);
-    if (MODE == 1 && gate) gt = *reinterpret_cast<const float2*>(gate + (size_t)b * C + h * CH + v);
-    float* pbase = part + (((size_t)(b * nchunk + chunk) * C) + h * CH) * CH;
+    if (MODE == 1 && gate) gt = *reinterpret_cast<const float2*>(gate + (size_t)b * C + cg0 + vg);
+    float* pbase = part + ((size_t)(b * nchunk + chunk) * C + cg0) * CH;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-        const int k0 = 16 * m + g;
-        if (k0 < CH) *reinterpret_cast<float2*>(pbase + (size_t)k0 * CH + v) = make_float2(acc[m][0] * gt.x, acc[m][1] * gt.y);
-        if (k0 + 8 < CH) *reinterpret_cast<float2*>(pbase + (size_t)(k0 + 8) * CH + v) = make_float2(acc[m][2] * gt.x, acc[m][3] * gt.y);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int kg = m_base + 16 * m + g + 8 * half;      // row within the group
+            if (kg < CPB && kg / CH == hv)
+                *reinterpret_cast<float2*>(pbase + (size_t)kg * CH + (vg - hv * CH)) = make_float2(acc[m][2 * half] * gt.x, acc[m][2 * half + 1] * gt.y);
+        }
     }
     if (MODE == 0) {
         // zpart[c] = sum over this chunk's tokens of exp(K - kmax): every thread summed 8 channels over its rows
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sZ[prow * CH + prt * 8 + j] = z[j];
+        for (int j = 0; j < 8; ++j) sZ[prow * CPB + prt * 8 + j] = z[j];
         __syncthreads();
-        for (int c = threadIdx.x; c < CH; c += NT) {
+        for (int c = threadIdx.x; c < CPB; c += NT) {
             float s = 0.f;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) s += sZ[r * CH + c];
-            zpart[(size_t)(b * nchunk + chunk) * C + h * CH + c] = s;
+            for (int r = 0; r < 32; ++r) s += sZ[r * CPB + c];
+            zpart[(size_t)(b * nchunk + chunk) * C + cg0 + c] = s;
         }
     }
 }
@@ -1189,30 +1201,32 @@ int chunks_for(int B, int N, int blocks_y) {
 template <int CH, int MODE>
 int launch_outer(const bf16* qkv, const bf16* dy, const float* gate, const float* kmax, float* part, float* zpart, int B, int N, int C,
                  int& nchunk, cudaStream_t st) {
-    using G = Cfg<CH>;
-    if constexpr (CH >= 40) {
-        // tensor-core version: one CTA per (token chunk, head, image); the chunk count stays within the scratch sized by max_chunks()
-        const int by = C / CH;
+    // tensor-core version: one CTA per (token chunk, channel group, image); the chunk count stays within the scratch sized by
+    // max_chunks().  (attn_outer_kernel, the FFMA2 version, is kept for A/B runs: MDV_ATTN_OUTER_FFMA=1.)
+    static const bool ffma = getenv("MDV_ATTN_OUTER_FFMA") && atoi(getenv("MDV_ATTN_OUTER_FFMA")) != 0;
+    if (!ffma) {
+        constexpr int CPB = CH <= 16 ? 64 : CH;
+        const int by = C / CPB;
         nchunk = chunks_for(B, N, by);
         const int mc = max_chunks(B, C, CH);
         if (nchunk > mc) nchunk = mc;
         int rpb = mdv_cdiv(N, nchunk);
         rpb = ((rpb + 63) / 64) * 64;
         nchunk = mdv_cdiv(N, rpb);
-        mdv_launch((attn_outer_mma_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(32 * (CH / 8)), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb,
+        mdv_launch((attn_outer_mma_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(32 * (CPB / 8)), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb,
                    nchunk);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
-    } else {
-        const int by = (C / G::CPW) * G::KSPLIT;
-        nchunk = chunks_for(B, N, by);
-        int rpb = mdv_cdiv(N, nchunk);
-        rpb = ((rpb + 31) / 32) * 32;
-        nchunk = mdv_cdiv(N, rpb);
-        mdv_launch((attn_outer_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(256), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
-        MDV_CHECK_LAUNCH();
-        return MDV_OK;
     }
+    using G = Cfg<CH>;
+    const int by = (C / G::CPW) * G::KSPLIT;
+    nchunk = chunks_for(B, N, by);
+    int rpb = mdv_cdiv(N, nchunk);
+    rpb = ((rpb + 31) / 32) * 32;
+    nchunk = mdv_cdiv(N, rpb);
+    mdv_launch((attn_outer_kernel<CH, MODE>), dim3(dim3(nchunk, by, B)), dim3(256), 0, st, qkv, dy, gate, kmax, part, zpart, N, C, rpb, nchunk);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
 }
 
 template <int CH>
