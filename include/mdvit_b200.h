@@ -157,6 +157,10 @@ int mdv_im2col3(const void* in, int in_bf16, void* col, int col_bf16, int B, int
 /* col: [B*Ho*Wo, 64] bf16 (col_bf16 = 1) or [B*Ho*Wo, 32] fp32 (col_bf16 = 0), 27 columns used, the rest zero */
 int mdv_im2col_stem(const float* img_nchw, void* col, int col_bf16, int B, int Hi, int Wi, void* stream);
 int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int stride, int ldc, void* stream);
+/* dilated 3x3 convs of the DeepLabV3 auxiliary decoder's ASPP (Utils/_deeplab.py:115-122, Decoders.py:218-235): stride 1,
+   padding = dilation, same size; col is bf16 [B*H*W, 9*C]; the transpose optionally accumulates into dx */
+int mdv_im2col3_dil(const void* in, int in_bf16, void* col, int B, int H, int W, int C, int dil, int ldc, void* stream);
+int mdv_col2im3_dil(const float* dcol, float* dx, int B, int H, int W, int C, int dil, int ldc, int accumulate, void* stream);
 /* bilinear resize, align_corners=False (mdvit.py:699; Decoders.py:196,319-336) and its exact transpose */
 int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* out, int out_bf16, int ld_out, int B, int Hi, int Wi, int Ho,
                      int Wo, int C, void* stream);

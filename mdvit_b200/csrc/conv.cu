@@ -458,10 +458,11 @@ __global__ void __launch_bounds__(256) gconv2_s_wgrad_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------- im2col / col2im (3x3, pad 1)
-// col[(b,yo,xo), (i*3+j)*C + c] = in[b, yo*s-1+i, xo*s-1+j, c]  (0 outside); row pitch ldc >= 9*C (extra columns zeroed).
+// col[(b,yo,xo), (i*3+j)*C + c] = in[b, yo*s+(i-1)*d, xo*s+(j-1)*d, c]  (0 outside; d = dilation, padding = d); row pitch
+// ldc >= 9*C (extra columns zeroed).
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in, TO* __restrict__ col, int B, int Hi, int Wi,
-                                                       int Ho, int Wo, int C, int stride, int ldc) {
+                                                       int Ho, int Wo, int C, int stride, int ldc, int dil) {
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const int per_row = 9 * c4n;
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const TI* __restrict__ in,
         const int xo = (int)(pix % Wo);
         const int yo = (int)((pix / Wo) % Ho);
         const int b = (int)(pix / ((idx_t)Wo * Ho));
-        const int yi = yo * stride - 1 + t / 3, xi = xo * stride - 1 + t % 3;
+        const int yi = yo * stride + (t / 3 - 1) * dil, xi = xo * stride + (t % 3 - 1) * dil;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi) v = ld4(in + (((size_t)b * Hi + yi) * Wi + xi) * C + c);
         st4(col + (size_t)pix * ldc + t * C + c, v);
@@ -508,9 +509,9 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
     }
 }
 
-// dx[b,y,x,c] = sum_ij dcol[(b,(y+1-i)/s,(x+1-j)/s), (i*3+j)*C + c]   (gather form of the im2col transpose)
+// dx[b,y,x,c] (+)= sum_ij dcol[(b,(y-(i-1)d)/s,(x-(j-1)d)/s), (i*3+j)*C + c]   (gather form of the im2col transpose)
 __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B, int Hi, int Wi,
-                                                       int Ho, int Wo, int C, int stride, int ldc) {
+                                                       int Ho, int Wo, int C, int stride, int ldc, int dil, int accumulate) {
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const idx_t total = (idx_t)B * Hi * Wi * c4n;
@@ -523,19 +524,23 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ 
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            int t = y + 1 - i;
+            int t = y - (i - 1) * dil;
             if (t < 0 || (t % stride)) continue;
             const int yo = t / stride;
             if (yo >= Ho) continue;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                int u = x + 1 - j;
+                int u = x - (j - 1) * dil;
                 if (u < 0 || (u % stride)) continue;
                 const int xo = u / stride;
                 if (xo >= Wo) continue;
                 const float4 v = ld4(dcol + (((size_t)b * Ho + yo) * Wo + xo) * ldc + (i * 3 + j) * C + c);
                 a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
+        }
+        if (accumulate) {
+            const float4 o = ld4(dx + (size_t)pix * C + c);
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
         }
         st4(dx + (size_t)pix * C + c, a);
     }
@@ -896,11 +901,11 @@ extern "C" int mdv_im2col3(const void* in, int in_bf16, void* col, int col_bf16,
     }
     const long long total = (long long)B * Ho * Wo * 9 * (C / 4);
     if (in_bf16 && col_bf16)
-        mdv_launch((im2col3_kernel<bf16, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const bf16*)in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+        mdv_launch((im2col3_kernel<bf16, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const bf16*)in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc, 1);
     else if (!in_bf16 && col_bf16)
-        mdv_launch((im2col3_kernel<float, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+        mdv_launch((im2col3_kernel<float, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc, 1);
     else if (!in_bf16 && !col_bf16)
-        mdv_launch((im2col3_kernel<float, float>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (float*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+        mdv_launch((im2col3_kernel<float, float>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (float*)col, B, Hi, Wi, Ho, Wo, C, stride, ldc, 1);
     else
         return MDV_ERR_UNSUPPORTED;
     MDV_CHECK_LAUNCH();
@@ -923,7 +928,29 @@ extern "C" int mdv_col2im3(const float* dcol, float* dx, int B, int Hi, int Wi, 
                            void* stream) {
     if (!dcol || !dx || (C & 3)) return MDV_ERR_ARG;
     if (!fits_i32((long long)B * Ho * Wo * ldc)) return MDV_ERR_UNSUPPORTED;
-    mdv_launch(col2im3_kernel, dim3(grid_for((long long)B * Hi * Wi * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, dx, B, Hi, Wi, Ho, Wo, C, stride, ldc);
+    mdv_launch(col2im3_kernel, dim3(grid_for((long long)B * Hi * Wi * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, dx, B, Hi, Wi, Ho, Wo, C, stride, ldc, 1, 0);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_im2col3_dil(const void* in, int in_bf16, void* col, int B, int H, int W, int C, int dil, int ldc, void* stream) {
+    if (!in || !col || (C & 3) || ldc != 9 * C || dil < 1) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * H * W * ldc)) return MDV_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)B * H * W * 9 * (C / 4);
+    if (in_bf16)
+        mdv_launch((im2col3_kernel<bf16, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const bf16*)in, (bf16*)col, B, H, W, H, W, C, 1, ldc, dil);
+    else
+        mdv_launch((im2col3_kernel<float, bf16>), dim3(grid_for(total)), dim3(256), 0, st, (const float*)in, (bf16*)col, B, H, W, H, W, C, 1, ldc, dil);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_col2im3_dil(const float* dcol, float* dx, int B, int H, int W, int C, int dil, int ldc, int accumulate, void* stream) {
+    if (!dcol || !dx || (C & 3) || dil < 1) return MDV_ERR_ARG;
+    if (!fits_i32((long long)B * H * W * ldc)) return MDV_ERR_UNSUPPORTED;
+    mdv_launch(col2im3_kernel, dim3(grid_for((long long)B * H * W * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, dx, B, H, W, H, W, C, 1, ldc, dil,
+               accumulate);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

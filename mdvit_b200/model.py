@@ -301,6 +301,63 @@ class MLPDecoder(MLPDecoderFM):
         super().__init__(in_channels, out_channel, hidden_channel, 0, dropout_ratio)
 
 
+class ASPPConv(nn.Sequential):
+    """Utils/_deeplab.py:115-122."""
+
+    def __init__(self, in_channels, out_channels, dilation):
+        super().__init__(nn.Conv2d(in_channels, out_channels, 3, padding=dilation, dilation=dilation, bias=False),
+                         nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
+
+
+class ASPPPooling(nn.Sequential):
+    """Utils/_deeplab.py:124-135."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__(nn.AdaptiveAvgPool2d(1), nn.Conv2d(in_channels, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels),
+                         nn.ReLU(inplace=True))
+
+
+class ASPP(nn.Module):
+    """Utils/_deeplab.py:137-165 (parameter container; the arithmetic is ops.DeepLabFn)."""
+
+    def __init__(self, in_channels, atrous_rates):
+        super().__init__()
+        out_channels = 256
+        modules = [nn.Sequential(nn.Conv2d(in_channels, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))]
+        modules += [ASPPConv(in_channels, out_channels, r) for r in tuple(atrous_rates)]
+        modules.append(ASPPPooling(in_channels, out_channels))
+        self.convs = nn.ModuleList(modules)
+        self.project = nn.Sequential(nn.Conv2d(5 * out_channels, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels),
+                                     nn.ReLU(inplace=True), nn.Dropout(0.1))
+        self.atrous_rates = tuple(atrous_rates)
+
+
+class DeepLabV3Decoder(nn.Module):
+    """Decoders.py:218-235: ASPP(512, [6,12,18]) -> 3x3 conv -> BN -> ReLU -> 1x1 conv on the LAST encoder map, resized to the
+    image.  Called like the other auxiliary decoders (token-major feature list + their sizes)."""
+
+    with_feature = False
+
+    def __init__(self, in_channel, out_channel, aspp_dilate=[6, 12, 18], conv_norm=nn.BatchNorm2d):
+        super().__init__()
+        if conv_norm is not nn.BatchNorm2d or out_channel != 1:
+            raise ValueError("mdvit_b200 implements DeepLabV3Decoder(in_channel, 1) with BatchNorm2d")
+        self.classifier = nn.Sequential(ASPP(in_channel, aspp_dilate), nn.Conv2d(256, 256, 3, padding=1, bias=False), conv_norm(256),
+                                        nn.ReLU(inplace=True), nn.Conv2d(256, out_channel, 1))
+
+    def forward(self, feats, sizes, img_size):
+        x, (H, W) = feats[3], sizes[3]          # `feature[-1]` of the four encoder maps (mdvit.py:715-722, Decoders.py:230-231)
+        aspp, conv, bn, _, fc = self.classifier
+        pairs = [(aspp.convs[0][0], aspp.convs[0][1]), (aspp.convs[1][0], aspp.convs[1][1]), (aspp.convs[2][0], aspp.convs[2][1]),
+                 (aspp.convs[3][0], aspp.convs[3][1]), (aspp.convs[4][1], aspp.convs[4][2]), (aspp.project[0], aspp.project[1]), (conv, bn)]
+        wgb, bufs = [], []
+        for c, n in pairs:
+            wgb += [c.weight, n.weight, n.bias]
+            bufs.append((n.running_mean, n.running_var, n.num_batches_tracked))
+        y = ops.DeepLabFn.apply(x, H, W, aspp.atrous_rates, float(aspp.project[3].p), self.training, bufs, *wgb)
+        return ops.HeadFn.apply(y, fc.weight, fc.bias, H, W, int(img_size[0]), int(img_size[1]))
+
+
 AUX_DECODERS = {'MLPFM': MLPDecoderFM, 'MLP': MLPDecoder}
 
 
@@ -413,9 +470,8 @@ class MDViT(_Trunk):
         super().__init__()
         if qk_scale is not None:
             raise ValueError("mdvit_b200 implements qk_scale=None (head_dim**-0.5), the reference trainers' setting")
-        if decoder_name not in AUX_DECODERS and decoder_name != 'Transformer':
-            raise NotImplementedError("mdvit_b200 implements decoder_name='MLPFM' (hard-coded by multi_train_MDViT.py:60), 'MLP' "
-                                      "(mdvit.py:607-611) and 'Transformer' (mdvit.py:613-642); 'DeepLabV3' is not built")
+        if decoder_name not in AUX_DECODERS and decoder_name not in ('Transformer', 'DeepLabV3'):
+            raise NotImplementedError("mdvit_b200 implements decoder_name in ('MLPFM', 'MLP', 'DeepLabV3', 'Transformer') (mdvit.py:594-642)")
         self.decoder_name = decoder_name
         self._build_trunk(in_chans, num_stages, num_layers, embed_dims, mlp_ratios, num_heads, qkv_bias, drop_rate, attn_drop_rate,
                           drop_path_rate, norm_layer, conv_norm, adapt_method, num_domains)
@@ -432,6 +488,11 @@ class MDViT(_Trunk):
                     UnetDecodingBlockTransformer(embed_dims[1], embed_dims[0], mh[0]),
                     nn.Sequential(nn.Conv2d(embed_dims[0], 1, kernel_size=1))]))
             self.debranchs = nn.ModuleList(debranchs)
+        elif decoder_name == 'DeepLabV3':
+            self.debranch1 = DeepLabV3Decoder(512, 1)
+            self.debranch2 = DeepLabV3Decoder(512, 1)
+            self.debranch3 = DeepLabV3Decoder(512, 1)
+            self.debranch4 = DeepLabV3Decoder(512, 1)
         else:
             Aux = AUX_DECODERS[decoder_name]
             self.debranch1 = Aux(embed_dims, 1, 512)

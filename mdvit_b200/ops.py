@@ -828,6 +828,148 @@ class DecoderConvFn(torch.autograd.Function):
         return (dinp.view(B, h * w, Cin), dskip.view(B, H * W, C), r_cb, r_cbb, r_dw, r_pw, rg, rb, None, None, None, None, None, None)
 
 
+def _sum_tokens(t, B, H, W, C):
+    """[B, H*W, C] -> [B, C] sums over the tokens of each image: the exact transpose of the 1x1 -> HxW bilinear resize."""
+    out = torch.empty((B, C), dtype=F32, device=t.device)
+    check(L.lib().mdv_upsample_bwd(ptr(t), int(t.dtype == BF16), C, ptr(out), C, B, 1, 1, H, W, C, None, L.stream()), "mdv_upsample_bwd")
+    return out
+
+
+class DeepLabFn(torch.autograd.Function):
+    """DeepLabV3Decoder.classifier[0:4] (Decoders.py:218-227, Utils/_deeplab.py:115-166) on token-major input: ASPP (1x1 conv,
+    three dilated 3x3 convs, image pooling; each conv -> BN -> ReLU) -> concat -> 1x1 project -> BN -> ReLU -> Dropout(0.1) ->
+    3x3 conv -> BN -> ReLU.  The final 1x1 conv + bilinear resize is ops.HeadFn.  Every conv is an (im2col +) tcgen05 GEMM with
+    bf16 operands; the branch outputs are written straight into their column slice of the concat buffer.  The maps are tiny
+    (H/32 x W/32), so this Function is written for coverage, not speed."""
+
+    NB = 7      # conv+BN pairs: aspp 1x1, 3 dilated, pooling, project, 3x3
+
+    @staticmethod
+    def forward(ctx, x, H, W, dils, drop_p, training, bufs, *wgb):
+        B, N, Cin = x.shape
+        M, dev = B * N, x.device
+        x = _contig(x)
+        ws, gs, bs = wgb[0::3], wgb[1::3], wgb[2::3]
+        Co = ws[0].shape[0]
+        lib = L.lib()
+        sid = new_stream_id() if (training and drop_p > 0) else 0
+        saved = {}
+
+        def bn(k, z, rows):
+            rm, rv, nb = bufs[k]
+            y, mean, rstd = bn_forward(z, rows, Co, gs[k], bs[k], rm, rv, nb, training, ACT_RELU, False)
+            saved[k] = (z, mean, rstd)
+            return y
+
+        with _dev_ctx(x):
+            xb = cast_bf16(x, M, Cin)
+            cat = torch.empty((M, 5 * Co), dtype=BF16, device=dev)
+            # 1x1 branch
+            z = gemm_nt(xb, prep_weight(ws[0], 0, Co, Cin), M, Co, Cin, torch.empty((M, Co), dtype=F32, device=dev))
+            cast_bf16(bn(0, z, M), M, Co, out=cat[:, 0:Co], ld_out=5 * Co)
+            # dilated 3x3 branches
+            col = torch.empty((M, 9 * Cin), dtype=BF16, device=dev)
+            for k in (1, 2, 3):
+                check(lib.mdv_im2col3_dil(ptr(xb), 1, ptr(col), B, H, W, Cin, int(dils[k - 1]), 9 * Cin, L.stream()), "mdv_im2col3_dil")
+                z = gemm_nt(col, prep_weight(ws[k], 2, Co, 9 * Cin, cin=Cin), M, Co, 9 * Cin, torch.empty((M, Co), dtype=F32, device=dev))
+                cast_bf16(bn(k, z, M), M, Co, out=cat[:, k * Co:(k + 1) * Co], ld_out=5 * Co)
+            # image pooling: mean over the tokens of an image (the transpose of a 1x1 -> HxW resize is the sum), 1x1 conv, BN over the
+            # B pooled rows, ReLU, broadcast back (bilinear resize from 1x1)
+            inv_n = torch.full((B,), 1.0 / N, dtype=F32, device=dev)
+            pooled = cast_bf16(_sum_tokens(x, B, H, W, Cin), B, Cin, rowscale=inv_n, rows_per_scale=1)
+            z = gemm_nt(pooled, prep_weight(ws[4], 0, Co, Cin), B, Co, Cin, torch.empty((B, Co), dtype=F32, device=dev))
+            upsample_fwd(bn(4, z, B), cat[:, 4 * Co:], B, 1, 1, H, W, Co, ld_out=5 * Co)
+            # project + dropout
+            z = gemm_nt(cat, prep_weight(ws[5], 0, Co, 5 * Co), M, Co, 5 * Co, torch.empty((M, Co), dtype=F32, device=dev))
+            pj = cast_bf16(bn(5, z, M), M, Co, drop_p=drop_p if training else 0.0, drop_stream=sid)
+            # 3x3 conv
+            col2 = torch.empty((M, 9 * Co), dtype=BF16, device=dev)
+            check(lib.mdv_im2col3_dil(ptr(pj), 1, ptr(col2), B, H, W, Co, 1, 9 * Co, L.stream()), "mdv_im2col3_dil")
+            z = gemm_nt(col2, prep_weight(ws[6], 2, Co, 9 * Co, cin=Co), M, Co, 9 * Co, torch.empty((M, Co), dtype=F32, device=dev))
+            y = bn(6, z, M)
+        ctx.meta = (B, N, Cin, Co, H, W, tuple(int(d) for d in dils), float(drop_p), sid, training)
+        if training:
+            flat = []
+            for k in range(DeepLabFn.NB):
+                flat += list(saved[k])
+            ctx.save_for_backward(xb, pooled, cat, col2, *flat)
+        ctx.params = tuple(wgb)
+        _fwd_mark(ctx)
+        return y.view(B, N, Co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, N, Cin, Co, H, W, dils, drop_p, sid, training = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        xb, pooled, cat, col2, *flat = ctx.saved_tensors
+        wgb = ctx.params
+        ws, gs, bs = wgb[0::3], wgb[1::3], wgb[2::3]
+        M, dev = B * N, dy.device
+        lib = L.lib()
+        dy = _contig(dy.float())
+        rets = [None] * (3 * DeepLabFn.NB)
+
+        def bn_bwd(k, d, rows):
+            z, mean, rstd = flat[3 * k:3 * k + 3]
+            dz, rg, rb = bn_backward(d, z, mean, rstd, gs[k], bs[k], ACT_RELU, rows, Co)
+            rets[3 * k + 1], rets[3 * k + 2] = rg, rb
+            return dz
+
+        def wgrad3(k, dz, col, cin):
+            gw, rw = gtarget(ws[k])
+            if gw is not None:
+                gwp = gemm_tn(dz, col, M, Co, 9 * cin, torch.zeros((Co, 9 * cin), dtype=F32, device=dev))
+                check(lib.mdv_unperm_conv_grad(ptr(gwp), 9 * cin, ptr(gw), Co, cin, L.stream()), "mdv_unperm_conv_grad")
+            rets[3 * k] = rw
+
+        def wgrad1(k, dz, a, rows, cin):
+            gw, rw = gtarget(ws[k], (Co, cin))
+            gemm_tn(dz, a, rows, Co, cin, gw)
+            rets[3 * k] = rw
+
+        with _dev_ctx(dy):
+            # 3x3 conv
+            dz = bn_bwd(6, dy, M)
+            wgrad3(6, dz, col2, Co)
+            dcol = gemm_nt(dz, prep_weight(ws[6], 3, Co, 9 * Co, cin=Co), M, 9 * Co, Co, torch.empty((M, 9 * Co), dtype=F32, device=dev))
+            dpj = torch.empty((M, Co), dtype=F32, device=dev)
+            check(lib.mdv_col2im3_dil(ptr(dcol), ptr(dpj), B, H, W, Co, 1, 9 * Co, 0, L.stream()), "mdv_col2im3_dil")
+            if drop_p > 0:      # the forward's mask, regenerated from the same counter stream
+                dpj = cast_bf16(dpj, M, Co, drop_p=drop_p, drop_stream=sid).float()
+            # project
+            dz = bn_bwd(5, dpj, M)
+            wgrad1(5, dz, cat, M, 5 * Co)
+            wt = prep_weight(ws[5], 1, Co, 5 * Co)                       # [5 Co, Co]: rows = input channels of the concat
+
+            def dcat(k):      # gradient of branch k's slice of the concat (contiguous)
+                return gemm_nt(dz, wt[k * Co:(k + 1) * Co], M, Co, Co, torch.empty((M, Co), dtype=F32, device=dev))
+
+            # image pooling: the broadcast's transpose sums over the tokens of an image
+            dzp = bn_bwd(4, _sum_tokens(dcat(4), B, H, W, Co), B)
+            wgrad1(4, dzp, pooled, B, Cin)
+            inv_n = torch.full((B,), 1.0 / N, dtype=F32, device=dev)
+            dpool = gemm_nt(dzp, prep_weight(ws[4], 1, Co, Cin), B, Cin, Co, torch.empty((B, Cin), dtype=F32, device=dev), rowscale=inv_n,
+                            rows_per_scale=1)
+            dx = upsample_fwd(dpool, torch.empty((M, Cin), dtype=F32, device=dev), B, 1, 1, H, W, Cin)
+            # dilated branches (the im2col matrices are rebuilt instead of saved)
+            col = torch.empty((M, 9 * Cin), dtype=BF16, device=dev)
+            dcolk = torch.empty((M, 9 * Cin), dtype=F32, device=dev)
+            for k in (1, 2, 3):
+                dzk = bn_bwd(k, dcat(k), M)
+                if wgrad_on():
+                    check(lib.mdv_im2col3_dil(ptr(xb), 1, ptr(col), B, H, W, Cin, dils[k - 1], 9 * Cin, L.stream()), "mdv_im2col3_dil")
+                wgrad3(k, dzk, col, Cin)
+                gemm_nt(dzk, prep_weight(ws[k], 3, Co, 9 * Cin, cin=Cin), M, 9 * Cin, Co, dcolk)
+                check(lib.mdv_col2im3_dil(ptr(dcolk), ptr(dx), B, H, W, Cin, dils[k - 1], 9 * Cin, 1, L.stream()), "mdv_col2im3_dil")
+            # 1x1 branch: dx += dz0 . W0
+            dz0 = bn_bwd(0, dcat(0), M)
+            wgrad1(0, dz0, xb, M, Cin)
+            gemm_nt(dz0, prep_weight(ws[0], 1, Co, Cin), M, Cin, Co, dx, residual=dx)
+        _grads_done(ctx)
+        return (dx.view(B, N, Cin), None, None, None, None, None, None, *rets)
+
+
 class HeadFn(torch.autograd.Function):
     """bilinear up to the image size -> 1x1 conv C->1 (mdvit.py:699-700), evaluated as conv-then-resize (exact)."""
 

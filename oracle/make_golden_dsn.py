@@ -70,6 +70,32 @@ def main():
                 dl = torch.nn.functional.one_hot(torch.full((2,), d), 4).float()
                 o, a = m(img, dl, str(d))
                 out[f"tr_{mode}_out_{d}"], out[f"tr_{mode}_aux_{d}"] = o.numpy(), a.numpy()
+    # ---- MDViT with the 'DeepLabV3' auxiliary decoder (mdvit.py:608-611, Decoders.py:218-235, Utils/_deeplab.py:115-166).  256x256 so
+    # that the last encoder map is 8x8 and the dilation-6 taps land inside it; ASPP's Dropout(0.1) off.  Besides the logits: the
+    # gradients of sum(aux * R) w.r.t. every parameter of the active branch and w.r.t. the stem (through the whole encoder).
+    torch.manual_seed(0)
+    m = MDViT(img_size=256, adapt_method="Sup", num_domains=4, decoder_name="DeepLabV3")
+    out["dl_keys"] = np.asarray(list(m.state_dict().keys()))
+    out["dl_init_fp"] = fingerprint(list(m.named_parameters()))
+    m.load_state_dict(synth.synth_state_dict(0, aux=False) | aux_state(m, "debranch"), strict=True)
+    for k in range(1, 5):
+        getattr(m, f"debranch{k}").classifier[0].project[3].p = 0.0
+    img, _ = synth.synth_batch(15, 1, 2, 256, 256)
+    dl = torch.nn.functional.one_hot(torch.full((2,), 1), 4).float()
+    with torch.no_grad():
+        m.eval()
+        o, a = m(img, dl, "1")
+        out["dl_eval_out"], out["dl_eval_aux"] = o.numpy().astype(np.float16), a.numpy().astype(np.float16)
+        out["dl_eval_absmax"] = np.asarray([o.abs().max().item(), a.abs().max().item()])
+    m.train()
+    o, a = m(img, dl, "1")
+    out["dl_train_aux"] = a.detach().numpy().astype(np.float16)
+    out["dl_train_absmax"] = np.asarray([a.abs().max().item()])
+    R = synth.synth_tensor("dl_probe", tuple(a.shape))
+    (a * R).sum().backward()
+    gnames = [n for n, p in m.named_parameters() if n.startswith("debranch2.") or n.startswith("stem.")]
+    out["dl_grad_names"] = np.asarray(gnames)
+    out["dl_grad_fp"] = fingerprint([(n, dict(m.named_parameters())[n].grad) for n in gnames])
     # ---- BASE_DSN (Models/Transformer/base.py:515-696): the DSN trunk without auxiliary branches, Sup and plain attention
     from Models.Transformer.base import BASE_DSN
     for am in ("Sup", None):

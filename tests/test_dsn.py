@@ -80,8 +80,6 @@ def test_transformer_aux_decoder_schema_and_random_init_match_the_reference(dgol
     assert list(m.state_dict().keys()) == [str(k) for k in dgold["tr_keys"]] and len(dgold["tr_keys"]) == 1460
     fp = fingerprint(list(m.named_parameters()))
     assert np.abs(fp - dgold["tr_init_fp"]).max() <= 1e-9 * np.abs(dgold["tr_init_fp"]).max()
-    with pytest.raises(NotImplementedError):
-        MDViT(img_size=64, decoder_name="DeepLabV3")
 
 
 @pytest.mark.gpu
@@ -131,6 +129,130 @@ def test_transformer_aux_decoder_logits_match_reference_golden(dgold):
     assert all(p.grad is None or p.grad.abs().max().item() == 0 for n, p in m.named_parameters() if n.startswith("debranchs.0."))
     with pytest.raises((TypeError, ValueError)):
         m(img.to(dev), dl, None)
+
+
+def test_deeplab_aux_decoder_schema_and_random_init_match_the_reference(dgold):
+    """decoder_name='DeepLabV3' (mdvit.py:608-611, Decoders.py:218-235): 716 state_dict keys, bit-identical init."""
+    from mdvit_b200.model import MDViT
+    torch.manual_seed(0)
+    m = MDViT(img_size=256, adapt_method="Sup", num_domains=4, decoder_name="DeepLabV3")
+    assert list(m.state_dict().keys()) == [str(k) for k in dgold["dl_keys"]] and len(dgold["dl_keys"]) == 716
+    fp = fingerprint(list(m.named_parameters()))
+    assert np.abs(fp - dgold["dl_init_fp"]).max() <= 1e-9 * np.abs(dgold["dl_init_fp"]).max()
+    with pytest.raises(NotImplementedError):
+        MDViT(img_size=64, decoder_name="UNet")
+
+
+@pytest.mark.gpu
+def test_deeplab_aux_decoder_logits_and_gradients_match_reference_golden(dgold):
+    """ASPP with dilated 3x3 convs on the 8x8 encoder map (256x256 input), image pooling, project, 3x3 conv, head: logits in eval
+    and train mode and the gradients of sum(aux * R) (branch parameters + the stem, i.e. through the decoder's input gradient)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200.model import MDViT
+    from oracle.make_golden_dsn import aux_state
+    dev = torch.device("cuda")
+    m = MDViT(img_size=256, adapt_method="Sup", num_domains=4, decoder_name="DeepLabV3")
+    m.load_state_dict(synth.synth_state_dict(0, aux=False) | aux_state(m, "debranch"), strict=True)
+    for k in range(1, 5):
+        getattr(m, f"debranch{k}").classifier[0].project[3].p = 0.0
+    m = m.to(dev)
+    img, _ = synth.synth_batch(15, 1, 2, 256, 256)
+    dl = torch.nn.functional.one_hot(torch.full((2,), 1), 4).float().to(dev)
+
+    def rel(a, b):
+        b = torch.as_tensor(b).float()
+        return ((a.detach().float().cpu() - b).abs().max() / b.abs().max()).item()
+
+    m.eval()
+    with torch.no_grad():
+        o, a = m(img.to(dev), dl, "1")
+    assert rel(o, dgold["dl_eval_out"]) < 2e-2 and rel(a, dgold["dl_eval_aux"]) < 3e-2
+    m.train()
+    o, a = m(img.to(dev), dl, "1")
+    assert rel(a, dgold["dl_train_aux"]) < 3e-2
+    R = synth.synth_tensor("dl_probe", tuple(a.shape)).to(dev)
+    (a * R).sum().backward()
+    names = [str(n) for n in dgold["dl_grad_names"]]
+    params = dict(m.named_parameters())
+    fp = fingerprint([(n, params[n].grad) for n in names])
+    ref = dgold["dl_grad_fp"]
+    bad = []
+    for i, n in enumerate(names):
+        # Only 2 x 8 x 8 = 128 rows feed every BatchNorm / ReLU of the decoder here, so a handful of ReLU masks flipped by the bf16
+        # forward moves a gradient by several percent: norms within 8 %, probe projections within 0.4 of the norm.  The tight
+        # check of the backward is test_deeplab_fn_matches_stock_pytorch_modules (same op in torch fp32, more rows, cosines).
+        if abs(fp[i, 0] - ref[i, 0]) > 0.08 * ref[i, 0] + 1e-6 or abs(fp[i, 1] - ref[i, 1]) > 0.40 * ref[i, 0] + 1e-6:
+            bad.append((n, fp[i].tolist(), ref[i].tolist()))
+    assert not bad, bad[:6]
+    assert all(params[n].grad is None or params[n].grad.abs().max().item() == 0 for n in params if n.startswith("debranch1."))
+    # dropout on: runs, finite, and the mask is the same in forward and backward (gradient of a linear probe is reproducible)
+    m.debranch2.classifier[0].project[3].p = 0.1
+    m.zero_grad()
+    o, a = m(img.to(dev), dl, "1")
+    (a * R).sum().backward()
+    assert torch.isfinite(a).all().item() and all(torch.isfinite(params[n].grad).all().item() for n in names)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W", [(8, 8, 8), (3, 7, 10)])
+def test_deeplab_fn_matches_stock_pytorch_modules(B, H, W):
+    """ops.DeepLabFn + HeadFn against the SAME decoder evaluated by stock PyTorch (its parameter containers are plain
+    nn.Conv2d / BatchNorm2d / ReLU Sequentials with the reference's structure, so `classifier(x)` is the reference arithmetic in
+    fp32): outputs, input gradient and every parameter gradient, train mode (batch statistics), dropout off."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import copy
+    from mdvit_b200.model import DeepLabV3Decoder
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    dec = DeepLabV3Decoder(512, 1)
+    with torch.no_grad():
+        for n, p in dec.named_parameters():      # BN affine parameters away from (1, 0)
+            if p.dim() == 1 and "classifier.4" not in n:
+                p.copy_(1.0 + 0.2 * torch.randn_like(p) if n.endswith("weight") else 0.2 * torch.randn_like(p))
+    dec.classifier[0].project[3].p = 0.0
+    dec = dec.to(dev).train()
+    ref = copy.deepcopy(dec)
+    x = torch.randn(B, H * W, 512, device=dev)
+    probe = torch.randn(B, 1, 32 * H, 32 * W, device=dev)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xr = x.clone().requires_grad_(True)
+        F = torch.nn.functional
+        aspp = ref.classifier[0]            # Utils/_deeplab.py:137-165 with stock torch ops (the containers carry no forward)
+        xn = xr.transpose(1, 2).reshape(B, 512, H, W)
+        res = [aspp.convs[k](xn) for k in range(4)]
+        res.append(F.interpolate(aspp.convs[4](xn), size=(H, W), mode="bilinear", align_corners=False))
+        t = aspp.project(torch.cat(res, dim=1))
+        for layer in list(ref.classifier)[1:]:
+            t = layer(t)
+        yr = F.interpolate(t, size=(32 * H, 32 * W), mode="bilinear", align_corners=False)
+        (yr * probe).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    xo = x.clone().requires_grad_(True)
+    feats = [None, None, None, xo]
+    yo = dec(feats, [None, None, None, (H, W)], (32 * H, 32 * W))
+    (yo * probe).sum().backward()
+
+    def cos(a, b):
+        a, b = a.flatten().double(), b.flatten().double()
+        return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+    assert ((yo - yr).abs().max() / yr.abs().max()).item() < 2e-2
+    assert cos(xo.grad, xr.grad) > 0.99 and abs(xo.grad.norm().item() / xr.grad.norm().item() - 1) < 0.03      # (bf16 operands, a few hundred rows)
+    worst = min((cos(p.grad, q.grad), n) for (n, p), (_, q) in zip(dec.named_parameters(), ref.named_parameters()))
+    assert worst[0] > 0.99, worst
+    for (n, p), (_, q) in zip(dec.named_parameters(), ref.named_parameters()):
+        assert abs(p.grad.norm().item() / (q.grad.norm().item() + 1e-30) - 1) < 0.05, n
+    # running statistics advanced identically (train-mode BatchNorm side effect)
+    for (n, b1), (_, b2) in zip(dec.named_buffers(), ref.named_buffers()):
+        if b1.is_floating_point():
+            assert (b1 - b2).abs().max().item() <= 2e-2 * (b2.abs().max().item() + 1e-3), n
+        else:
+            assert torch.equal(b1, b2), n
 
 
 @pytest.mark.parametrize("am", ["Sup", None])

@@ -60,7 +60,7 @@ def test_no_cpu_fallback(model):
 
 def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
-        MDViT(decoder_name="DeepLabV3")
+        MDViT(decoder_name="UNet")
     with pytest.raises(ValueError):
         MDViT(num_heads=[4, 4, 4, 4])
 
