@@ -200,6 +200,10 @@ int mdv_da_gate_bwd(const float* label, const float* w2, const float* hid_in, co
  * lse (optional, [B,heads,N] fp32) receives the row log-sum-exp for a backward pass.  head_dim 64, N in {128, 256}. */
 int mdv_sdpa_fwd(const void* qkv_bf16, const float* gate, void* out_bf16, float* lse, int B, int N, int C, int heads, float scale,
                  void* stream);
+/* Its backward (what autograd runs for vision_transformer.py:155-166): dqkv bf16 [B,N,3C] (rows dq | dk | dv) from dout bf16
+ * [B,N,C], the forward's out and lse; dgate fp32 [B,C] (optional, written: feed it to mdv_da_gate_bwd).  P is recomputed. */
+int mdv_sdpa_bwd(const void* qkv_bf16, const float* gate, const void* out_bf16, const float* lse, const void* dout_bf16,
+                 void* dqkv_bf16, float* dgate, int B, int N, int C, int heads, float scale, void* stream);
 
 /* ------------------------------------------------------------------ heads, reductions, casts */
 /* logits[m] = sum_c x[m,c] w[c] dropout2d(b,c) + bias  — the C->1 1x1 conv commuted in front of the final resize */

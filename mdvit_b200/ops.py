@@ -970,6 +970,79 @@ class DeepLabFn(torch.autograd.Function):
         return (dx.view(B, N, Cin), None, None, None, None, None, None, *rets)
 
 
+class SdpaAttentionFn(torch.autograd.Function):
+    """Attention_Sup.forward / Attention.forward of TransFuse_S_adapt's DeiT branch (vision_transformer.py:110-122,149-169):
+    qkv Linear -> softmax(s Q K^T) V -> DA head gate -> proj Linear, as bf16 tcgen05 GEMMs around mdv_sdpa_fwd / mdv_sdpa_bwd.
+    head_dim 64, N in {128, 256}; attn_drop = proj_drop = 0 (the reference's DeiT-S setting)."""
+
+    @staticmethod
+    def forward(ctx, x, label, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2, heads, scale):
+        B, N, C = x.shape
+        M, dev = B * N, x.device
+        x = _contig(x)
+        lib = L.lib()
+        with _dev_ctx(x):
+            xb = cast_bf16(x, M, C)
+            qkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
+            gemm_nt(xb, prep_weight(qkv_w, 0, 3 * C, C), M, 3 * C, C, qkv, bias=qkv_b)
+            gate = hid = None
+            if da_w1 is not None:
+                label = _contig(label.float())
+                nd, hd = da_w1.shape[1], da_w1.shape[0]
+                gate = torch.empty((B, C), dtype=F32, device=dev)
+                hid = torch.empty((B, hd), dtype=F32, device=dev)
+                check(lib.mdv_da_gate_fwd(ptr(label), ptr(da_w1), ptr(da_b1), ptr(da_w2), ptr(da_b2), ptr(hid), ptr(gate), B, nd, hd, C, heads,
+                                          L.stream()), "mdv_da_gate_fwd")
+            y = torch.empty((M, C), dtype=BF16, device=dev)
+            lse = torch.empty((B, heads, N), dtype=F32, device=dev)
+            check(lib.mdv_sdpa_fwd(ptr(qkv), ptr(gate), ptr(y), ptr(lse), B, N, C, heads, ctypes.c_float(scale), L.stream()), "mdv_sdpa_fwd")
+            out = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(y, prep_weight(proj_w, 0, C, C), M, C, C, out, bias=proj_b)
+        ctx.save_for_backward(xb, qkv, y, lse, gate, hid, label if da_w1 is not None else None)
+        ctx.params = (qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2)
+        ctx.meta = (B, N, C, heads, float(scale))
+        _fwd_mark(ctx)
+        return out.view(B, N, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, N, C, heads, scale = ctx.meta
+        xb, qkv, y, lse, gate, hid, label = ctx.saved_tensors
+        qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2 = ctx.params
+        M, dev = B * N, dout.device
+        lib = L.lib()
+        dout = _contig(dout.float())
+        with _dev_ctx(dout):
+            dob = cast_bf16(dout, M, C)
+            g_pw, r_pw = gtarget(proj_w)
+            gemm_tn(dob, y, M, C, C, g_pw)
+            g_pb, r_pb = gtarget(proj_b)
+            colsum(dout, M, C, g_pb)
+            dy = torch.empty((M, C), dtype=BF16, device=dev)
+            gemm_nt(dob, prep_weight(proj_w, 1, C, C), M, C, C, dy)
+            dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
+            dgate = torch.empty((B, C), dtype=F32, device=dev) if gate is not None else None
+            check(lib.mdv_sdpa_bwd(ptr(qkv), ptr(gate), ptr(y), ptr(lse), ptr(dy), ptr(dqkv), ptr(dgate), B, N, C, heads, ctypes.c_float(scale),
+                                   L.stream()), "mdv_sdpa_bwd")
+            r_da = [None] * 4
+            if gate is not None:
+                tg = [gtarget(p, da=True) for p in (da_w1, da_b1, da_w2, da_b2)]
+                if tg[0][0] is not None:
+                    nd, hd = da_w1.shape[1], da_w1.shape[0]
+                    ws2 = torch.empty(B * (C + hd), dtype=F32, device=dev)
+                    check(lib.mdv_da_gate_bwd(ptr(label), ptr(da_w2), ptr(hid), ptr(gate), ptr(dgate), ptr(tg[0][0]), ptr(tg[1][0]), ptr(tg[2][0]),
+                                              ptr(tg[3][0]), ptr(ws2), B, nd, hd, C, heads, L.stream()), "mdv_da_gate_bwd")
+                r_da = [t[1] for t in tg]
+            g_qw, r_qw = gtarget(qkv_w)
+            gemm_tn(dqkv, xb, M, 3 * C, C, g_qw)
+            g_qb, r_qb = gtarget(qkv_b)
+            colsum(dqkv, M, 3 * C, g_qb)
+            dx = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(dqkv, prep_weight(qkv_w, 1, 3 * C, C), M, C, 3 * C, dx)
+        _grads_done(ctx)
+        return (dx.view(B, N, C), None, r_qw, r_qb, r_pw, r_pb, *r_da, None, None)
+
+
 class HeadFn(torch.autograd.Function):
     """bilinear up to the image size -> 1x1 conv C->1 (mdvit.py:699-700), evaluated as conv-then-resize (exact)."""
 

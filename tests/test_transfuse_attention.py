@@ -86,3 +86,79 @@ def test_sdpa_kernel_matches_reference_attention_golden(tgold, sup):
         if sup:
             ref = ref * g2.reshape(Bn, 1, HEADS, 64)
         assert rel(y2.reshape(Bn, Nn, HEADS, 64), ref) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,heads,sup", [(2, 256, 6, True), (3, 128, 2, False), (1, 256, 1, True)])
+def test_sdpa_backward_matches_torch_autograd(B, N, heads, sup):
+    """mdv_sdpa_bwd (mma.sync, P recomputed from the log-sum-exp) against torch autograd of the same op in fp32 on the same
+    bf16-rounded q, k, v and output gradient: dq, dk, dv within 2e-2 of each tensor's abs-max (bf16 P / dS operands, bf16
+    outputs), the gate gradient within 1e-2."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200 import _lib as L
+    lib, dev = L.lib(), torch.device("cuda")
+    torch.manual_seed(5)
+    C = heads * 64
+    scale = 64 ** -0.5
+    qkv = (torch.randn(B, N, 3 * C, device=dev) * 1.5).bfloat16()
+    gate = torch.softmax(torch.randn(B, heads, 64, device=dev), dim=1).reshape(B, C).contiguous() if sup else None
+    dy = torch.randn(B, N, C, device=dev).bfloat16()
+    out = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, N, device=dev)
+    st = L.stream()
+    L.check(lib.mdv_sdpa_fwd(L.ptr(qkv), L.ptr(gate), L.ptr(out), L.ptr(lse), B, N, C, heads, ctypes.c_float(scale), st), "sdpa_fwd")
+    dqkv = torch.full((B, N, 3 * C), float("nan"), device=dev, dtype=torch.bfloat16)
+    dgate = torch.full((B, C), float("nan"), device=dev) if sup else None
+    L.check(lib.mdv_sdpa_bwd(L.ptr(qkv), L.ptr(gate), L.ptr(out), L.ptr(lse), L.ptr(dy), L.ptr(dqkv), L.ptr(dgate), B, N, C, heads,
+                             ctypes.c_float(scale), st), "sdpa_bwd")
+    # reference: fp32 autograd
+    x = qkv.float().requires_grad_(True)
+    gr = gate.clone().requires_grad_(True) if sup else None
+    q, k, v = (t.reshape(B, N, heads, 64).transpose(1, 2) for t in x.split(C, dim=2))
+    p = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1)
+    y = (p @ v).transpose(1, 2).reshape(B, N, C)
+    if sup:
+        y = y * gr[:, None, :]
+    assert ((out.float() - y).abs().max() / y.abs().max()).item() < 1e-2
+    y.backward(dy.float())
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        a, r = dqkv[:, :, sl].float(), x.grad[:, :, sl]
+        assert torch.isfinite(a).all().item(), name
+        assert ((a - r).abs().max() / r.abs().max()).item() < 2e-2, (name, ((a - r).abs().max() / r.abs().max()).item())
+        assert ((a - r).norm() / r.norm()).item() < 1.5e-2, name
+    if sup:
+        assert ((dgate - gr.grad).abs().max() / gr.grad.abs().max()).item() < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sup", [True, False])
+def test_attention_module_dropin_forward_backward_match_reference(tgold, sup):
+    """mdvit_b200.transfuse.Attention_Sup / Attention (same ctor / state_dict / forward as vision_transformer.py:96-169): output,
+    input gradient and every parameter gradient of sum(y * R) against the unmodified reference modules."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200 import transfuse as T
+    from oracle.make_golden_transfuse import _t, grad_sample
+    dev = torch.device("cuda")
+    sd, x, label = attention_case()
+    key = "sup" if sup else "plain"
+    if sup:
+        m = T.Attention_Sup(DIM, num_heads=HEADS, qkv_bias=True)
+        m.load_state_dict(sd, strict=True)
+    else:
+        m = T.Attention(DIM, num_heads=HEADS, qkv_bias=True)
+        m.load_state_dict({k: v for k, v in sd.items() if not k.startswith("domain_layer")}, strict=True)
+    m = m.to(dev).train()
+    xr = x.to(dev).requires_grad_(True)
+    y = m(xr, label.to(dev)) if sup else m(xr)
+    assert rel(y, tgold[key + "_out"].astype(np.float32)) < 1e-2
+    R = _t("tfprobe", tuple(y.shape), 1.0).to(dev)
+    (y * R).sum().backward()
+    assert rel(xr.grad, tgold[key + "_dx"].astype(np.float32)) < 2e-2
+    for n, p in m.named_parameters():
+        ref = torch.as_tensor(tgold[f"{key}_grad.{n}"])
+        err = ((grad_sample(p.grad).float().cpu() - ref).norm() / (ref.norm() + 1e-30)).item()
+        assert err < 2e-2, (n, err)
+    with pytest.raises(NotImplementedError):
+        T.Attention(256, num_heads=8)          # head_dim 32
