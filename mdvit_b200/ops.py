@@ -1043,6 +1043,156 @@ class SdpaAttentionFn(torch.autograd.Function):
         return (dx.view(B, N, C), None, r_qw, r_qb, r_pw, r_pb, *r_da, None, None)
 
 
+class DeiTBlockFn(torch.autograd.Function):
+    """Block_adapt.forward / Block.forward of TransFuse_S_adapt's DeiT branch (vision_transformer.py:172-211):
+    x + attn(LN1(x)[, label]); then + mlp(LN2(.)).  LayerNorm kernels, bf16 tcgen05 GEMMs with the bias / GELU / residual
+    epilogues, mdv_sdpa_fwd / mdv_sdpa_bwd.  drop = attn_drop = drop_path = 0 (the reference's DeiT-S setting)."""
+
+    @staticmethod
+    def forward(ctx, x, label, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                heads, scale, eps):
+        B, N, C = x.shape
+        M, dev = B * N, x.device
+        hidden = fc1_w.shape[0]
+        x = _contig(x.float())
+        lib = L.lib()
+        with _dev_ctx(x):
+            ln1, mean1, rstd1 = layernorm_fwd(x, n1w, n1b, M, C, eps)
+            qkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
+            gemm_nt(ln1, prep_weight(qkv_w, 0, 3 * C, C), M, 3 * C, C, qkv, bias=qkv_b)
+            gate = hid = None
+            if da_w1 is not None:
+                label = _contig(label.float())
+                nd, hd = da_w1.shape[1], da_w1.shape[0]
+                gate = torch.empty((B, C), dtype=F32, device=dev)
+                hid = torch.empty((B, hd), dtype=F32, device=dev)
+                check(lib.mdv_da_gate_fwd(ptr(label), ptr(da_w1), ptr(da_b1), ptr(da_w2), ptr(da_b2), ptr(hid), ptr(gate), B, nd, hd, C, heads,
+                                          L.stream()), "mdv_da_gate_fwd")
+            y = torch.empty((M, C), dtype=BF16, device=dev)
+            lse = torch.empty((B, heads, N), dtype=F32, device=dev)
+            check(lib.mdv_sdpa_fwd(ptr(qkv), ptr(gate), ptr(y), ptr(lse), B, N, C, heads, ctypes.c_float(scale), L.stream()), "mdv_sdpa_fwd")
+            x2 = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(y, prep_weight(proj_w, 0, C, C), M, C, C, x2, bias=proj_b, residual=x)
+            ln2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, M, C, eps)
+            u = torch.empty((M, hidden), dtype=BF16, device=dev)
+            hact = torch.empty((M, hidden), dtype=BF16, device=dev)
+            gemm_nt(ln2, prep_weight(fc1_w, 0, hidden, C), M, hidden, C, hact, bias=fc1_b, act=ACT_GELU, out_preact=u, preact_mode=1)
+            x3 = torch.empty((B, N, C), dtype=F32, device=dev)
+            gemm_nt(hact, prep_weight(fc2_w, 0, C, hidden), M, C, hidden, x3, bias=fc2_b, residual=x2)
+        ctx.save_for_backward(x, mean1, rstd1, ln1, qkv, y, lse, gate, hid, label if da_w1 is not None else None, x2, mean2, rstd2, ln2, u, hact)
+        ctx.params = (n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, da_w1, da_b1, da_w2, da_b2, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+        ctx.meta = (B, N, C, hidden, heads, float(scale))
+        _fwd_mark(ctx)
+        return x3
+
+    @staticmethod
+    def backward(ctx, dx3):
+        x, mean1, rstd1, ln1, qkv, y, lse, gate, hid, label, x2, mean2, rstd2, ln2, u, hact = ctx.saved_tensors
+        names = ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "da_w1", "da_b1", "da_w2", "da_b2", "n2w", "n2b", "fc1_w", "fc1_b",
+                 "fc2_w", "fc2_b")
+        P = dict(zip(names, ctx.params))
+        B, N, C, hidden, heads, scale = ctx.meta
+        M, dev = B * N, x.device
+        lib = L.lib()
+        dx3 = _contig(dx3.float())
+        T = {n: gtarget(P[n], da=n.startswith("da_")) for n in names}
+        G = {k: v[0] for k, v in T.items()}
+        with _dev_ctx(x):
+            d_fc2 = cast_bf16(dx3, M, C, colsum=G["fc2_b"])
+            gemm_tn(d_fc2, hact, M, C, hidden, G["fc2_w"])
+            du = torch.empty((M, hidden), dtype=BF16, device=dev)
+            gemm_nt(d_fc2, prep_weight(P["fc2_w"], 1, C, hidden), M, hidden, C, du, mul_gelu_grad=u, mul_mode=1, colsum=G["fc1_b"])
+            gemm_tn(du, ln2, M, hidden, C, G["fc1_w"])
+            dln2 = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(du, prep_weight(P["fc1_w"], 1, hidden, C), M, C, hidden, dln2)
+            dx2, d_proj = layernorm_bwd(dln2, x2, mean2, rstd2, P["n2w"], dx3, M, C, G["n2w"], G["n2b"], masked=True, dbias_masked=G["proj_b"])
+            gemm_tn(d_proj, y, M, C, C, G["proj_w"])
+            dy = torch.empty((M, C), dtype=BF16, device=dev)
+            gemm_nt(d_proj, prep_weight(P["proj_w"], 1, C, C), M, C, C, dy)
+            dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
+            dgate = torch.empty((B, C), dtype=F32, device=dev) if gate is not None else None
+            check(lib.mdv_sdpa_bwd(ptr(qkv), ptr(gate), ptr(y), ptr(lse), ptr(dy), ptr(dqkv), ptr(dgate), B, N, C, heads, ctypes.c_float(scale),
+                                   L.stream()), "mdv_sdpa_bwd")
+            if gate is not None and G["da_w1"] is not None:
+                nd, hd = P["da_w1"].shape[1], P["da_w1"].shape[0]
+                ws2 = torch.empty(B * (C + hd), dtype=F32, device=dev)
+                check(lib.mdv_da_gate_bwd(ptr(label), ptr(P["da_w2"]), ptr(hid), ptr(gate), ptr(dgate), ptr(G["da_w1"]), ptr(G["da_b1"]),
+                                          ptr(G["da_w2"]), ptr(G["da_b2"]), ptr(ws2), B, nd, hd, C, heads, L.stream()), "mdv_da_gate_bwd")
+            gemm_tn(dqkv, ln1, M, 3 * C, C, G["qkv_w"])
+            colsum(dqkv, M, 3 * C, G["qkv_b"])
+            dln1 = torch.empty((M, C), dtype=F32, device=dev)
+            gemm_nt(dqkv, prep_weight(P["qkv_w"], 1, 3 * C, C), M, C, 3 * C, dln1)
+            dx, _ = layernorm_bwd(dln1, x, mean1, rstd1, P["n1w"], dx2, M, C, G["n1w"], G["n1b"])
+        _grads_done(ctx)
+        return (dx.view(B, N, C), None, *[T[n][1] for n in names], None, None, None)
+
+
+class DeiTEmbedFn(torch.autograd.Function):
+    """PatchEmbed (Conv2d kernel = stride = patch: one GEMM over the flattened patches) + positional embedding
+    (vision_transformer.py:214-236, DeiT.py:116-125).  `patches` [B*n, 3*p*p] are the image's patches in (c, i, j) order."""
+
+    @staticmethod
+    def forward(ctx, patches, w, b, pos, B, n):
+        M, K = patches.shape
+        C = w.shape[0]
+        dev = patches.device
+        with _dev_ctx(patches):
+            pb = cast_bf16(_contig(patches.float()), M, K)
+            pe = _contig(pos.reshape(1, n, C).expand(B, n, C)).view(M, C)
+            out = torch.empty((B, n, C), dtype=F32, device=dev)
+            gemm_nt(pb, prep_weight(w, 0, C, K), M, C, K, out, bias=b, residual=pe)
+        ctx.save_for_backward(pb)
+        ctx.params = (w, b, pos)
+        ctx.meta = (B, n, C, K)
+        _fwd_mark(ctx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (pb,) = ctx.saved_tensors
+        w, b, pos = ctx.params
+        B, n, C, K = ctx.meta
+        M = B * n
+        dout = _contig(dout.float())
+        with _dev_ctx(dout):
+            g_w, r_w = gtarget(w, (C, K))
+            gemm_tn(cast_bf16(dout, M, C), pb, M, C, K, g_w)
+            g_b, r_b = gtarget(b)
+            colsum(dout, M, C, g_b)
+            g_p, r_p = gtarget(pos, (n * C,))
+            colsum(dout, B, n * C, g_p)          # sum over the batch: rows = images
+        _grads_done(ctx)
+        return None, r_w, r_b, r_p, None, None
+
+
+class LayerNormOutFn(torch.autograd.Function):
+    """A LayerNorm whose output leaves the library (the final norm of the DeiT branch): fp32 in, fp32 out."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        B, N, C = x.shape
+        x = _contig(x.float())
+        with _dev_ctx(x):
+            y, mean, rstd = layernorm_fwd(x, w, b, B * N, C, eps)
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.params = (w, b)
+        _fwd_mark(ctx)
+        return y.float().view(B, N, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        w, b = ctx.params
+        B, N, C = x.shape
+        dy = _contig(dy.float())
+        with _dev_ctx(x):
+            g_w, r_w = gtarget(w)
+            g_b, r_b = gtarget(b)
+            dx, _ = layernorm_bwd(dy, x, mean, rstd, w, None, B * N, C, g_w, g_b)
+        _grads_done(ctx)
+        return dx.view(B, N, C), r_w, r_b, None
+
+
 class HeadFn(torch.autograd.Function):
     """bilinear up to the image size -> 1x1 conv C->1 (mdvit.py:699-700), evaluated as conv-then-resize (exact)."""
 

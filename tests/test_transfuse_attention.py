@@ -162,3 +162,49 @@ def test_attention_module_dropin_forward_backward_match_reference(tgold, sup):
         assert err < 2e-2, (n, err)
     with pytest.raises(NotImplementedError):
         T.Attention(256, num_heads=8)          # head_dim 32
+
+
+def test_deit_adapt_schema_and_random_init_match_the_reference(tgold):
+    """deit_small_patch16_224_adapt (DeiT.py:157-181): 134 state_dict keys, bit-identical stock-constructor init, pos_embed [1,256,384]."""
+    from mdvit_b200.transfuse import deit_small_patch16_224_adapt
+    from tests.helpers import fingerprint
+    torch.manual_seed(0)
+    m = deit_small_patch16_224_adapt(pretrained=False, num_domains=4)
+    assert list(m.state_dict().keys()) == [str(k) for k in tgold["deit_keys"]] and tuple(m.pos_embed.shape) == (1, 256, 384)
+    fp = fingerprint(list(m.named_parameters()))
+    assert np.abs(fp - tgold["deit_init_fp"]).max() <= 1e-9 * np.abs(tgold["deit_init_fp"]).max()
+
+
+@pytest.mark.gpu
+def test_deit_adapt_tokens_and_gradients_match_reference(tgold):
+    """The transformer branch of TransFuse_S_adapt end to end (patch embedding GEMM + pos_embed, 8 Block_adapt, final LayerNorm) at the
+    reference's own random init: output tokens and the gradients of a probe loss for all 133 trained parameters."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mdvit_b200.transfuse import deit_small_patch16_224_adapt
+    from oracle.make_golden_transfuse import _t
+    from tests.helpers import fingerprint
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    m = deit_small_patch16_224_adapt(pretrained=False, num_domains=4)
+    with torch.no_grad():
+        m.pos_embed.copy_(_t("deitpos", tuple(m.pos_embed.shape), 0.02))
+    m = m.to(dev).train()
+    img = _t("deitimg", (2, 3, 256, 256), 1.0).to(dev)
+    dlab = torch.nn.functional.one_hot(torch.tensor([1, 3]), 4).float().to(dev)
+    tok = m(img, dlab)
+    assert rel(tok, tgold["deit_tokens"].astype(np.float32)) < 1e-2
+    Rd = _t("deitprobe", tuple(tok.shape), 1.0).to(dev)
+    (tok * Rd).sum().backward()
+    names = [str(n) for n in tgold["deit_grad_names"]]
+    P = dict(m.named_parameters())
+    assert set(names) == {n for n, p in P.items() if p.grad is not None}
+    fp, ref = fingerprint([(n, P[n].grad) for n in names]), tgold["deit_grad_fp"]
+    bad = [(n, fp[i].tolist(), ref[i].tolist()) for i, n in enumerate(names)
+           if abs(fp[i, 0] - ref[i, 0]) > 0.03 * ref[i, 0] + 1e-7 or abs(fp[i, 1] - ref[i, 1]) > 0.06 * ref[i, 0] + 1e-7]
+    assert not bad, bad[:5]
+    for n in names:
+        if "deit_grad." + n in tgold.files:
+            r = torch.as_tensor(tgold["deit_grad." + n])
+            e = ((P[n].grad.float().cpu() - r).norm() / (r.norm() + 1e-30)).item()
+            assert e < 3e-2, (n, e)
