@@ -165,11 +165,12 @@ def test_train_step_losses_and_gradients_vs_reference_golden(dev, golden):
                       for i, n in enumerate(names))
     # every gradient tensor's l2 norm is within 10% of the reference's (median within 2%); a 2x2-pixel stage with
     # batch-stat BN over 8 samples (bridge) and the DA's softmax-over-heads cancellation are the noisy ones
-    assert dev_norm[len(dev_norm) // 2][0] < 0.02, dev_norm[len(dev_norm) // 2]
-    assert all(d < (0.35 if ("bridge." in n or "domain_layer" in n) else 0.12) for d, n in dev_norm), dev_norm[-8:]
+    # measured (scripts/dev_margins.py, end of round 2): median 0.0015, worst 0.022 -> bounds at ~3x
+    assert dev_norm[len(dev_norm) // 2][0] < 0.005, dev_norm[len(dev_norm) // 2]
+    assert all(d < 0.07 for d, n in dev_norm), dev_norm[-8:]
     full = {k.split("/", 1)[1]: golden[k] for k in golden.files if k.startswith("train64_grad/")}
     g_all, w_tight, w_loose, text = grad_report(grads, full)
-    assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
+    assert g_all < 0.02 and w_tight < 0.08 and w_loose < 0.12, text      # measured 0.0074 / 0.032 / 0.044 (scripts/dev_margins.py)
     # BatchNorm running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased running var), 4 forwards
     sd = m.state_dict()
     assert int(sd["stem.0.bn.num_batches_tracked"]) == 4
@@ -182,7 +183,7 @@ def test_single_sweep_schedule_equals_reference_two_pass(dev):
     assert (l_ref - l_one).abs().max().item() < 2e-3 * l_ref.abs().max().item()
     # same math, different bf16 rounding points (one summed cotangent vs two)
     g_all, w_tight, w_loose, text = grad_report(g_one, g_ref)
-    assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
+    assert g_all < 0.02 and w_tight < 0.08 and w_loose < 0.12, text      # measured 0.0074 / 0.032 / 0.044 (scripts/dev_margins.py)
 
 
 def test_fused_multi_domain_forward_equals_per_domain_forwards(dev):
@@ -207,7 +208,7 @@ def test_fused_multi_domain_forward_equals_per_domain_forwards(dev):
     _, _, l_fus, g_fus = _grads_of_step(dev, "single_sweep", fuse_domains=True)
     assert (l_sep - l_fus).abs().max().item() < 5e-3 * l_sep.abs().max().item()
     g_all, w_tight, w_loose, text = grad_report(g_fus, g_sep)
-    assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
+    assert g_all < 0.02 and w_tight < 0.08 and w_loose < 0.12, text      # measured 0.0074 / 0.032 / 0.044 (scripts/dev_margins.py)
 
 
 def test_train_step_vs_oracle_on_gpu_and_adamw(dev):
@@ -220,7 +221,8 @@ def test_train_step_vs_oracle_on_gpu_and_adamw(dev):
     ref_l = torch.stack([torch.stack(e) for e in Lr["each"]])
     assert (losses - ref_l).abs().max().item() < 2e-2 * ref_l.abs().max().item()
     g_all, w_tight, w_loose, text = grad_report(grads, {n: gr[n] for n in grads})
-    assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.35, text
+    # (against the oracle's fp32 autograd on the GPU the 2x2-pixel bridge / last-stage DA tensors sit at 0.10-0.13, global 0.020)
+    assert g_all < 0.03 and w_tight < 0.12 and w_loose < 0.20, text
     # AdamW: p <- p(1 - lr wd) - lr m_hat / (sqrt(v_hat) + eps); at step 1 this is -lr*sign(g) wherever |g| >> eps
     before = {n: p.detach().clone() for n, p in m.named_parameters()}
     tr.optimizer_step()
