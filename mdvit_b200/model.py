@@ -664,6 +664,20 @@ class BASE_DSN(MDViT_DSN):
 class BASE(_Trunk):
     """Drop-in for Models.Transformer.base.BASE (base.py:340-512): MDViT without auxiliary branches."""
 
+    def forward_multi(self, x, domain_label, domains):
+        """The G single-domain forwards of one training step (multi_train_BASE.py calls forward once per domain) as ONE pass over the
+        stacked batch, BatchNorm evaluated per group of B samples exactly as G separate forwards would (see MDViT.forward_multi).
+        Returns [(out_d, None)] per domain."""
+        G = len(domains)
+        if x.shape[0] % G:
+            raise ValueError("forward_multi needs G equal mini-batches stacked along dim 0")
+        img_size = x.shape[2:]
+        with ops.bn_groups(G if self.training else 1):
+            enc = self._trunk_forward(x, domain_label)
+            dec4, h, w = self._decode(enc, domain_label)
+        out = self._head(dec4, h, w, img_size)
+        return [(o, None) for o in ops.SplitDomainsFn.apply(out, G)]
+
     def __init__(self, img_size=512, in_chans=3, num_stages=4, num_layers=[2, 2, 2, 2], embed_dims=[64, 128, 320, 512],
                  mlp_ratios=[8, 8, 4, 4], num_heads=[8, 8, 8, 8], qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
                  drop_path_rate=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), conv_norm=nn.BatchNorm2d, adapt_method=None,

@@ -243,8 +243,9 @@ class MKDTrainer:
     def forward_losses(self, batches):
         """batches: list of (img [B,3,H,W], label [B,1,H,W] fp32 or uint8, domain index).  Returns [n_dom, 3] losses
         (seg, aux, kt).  The partial sums of all domains are all-reduced in ONE collective after the last forward."""
-        if (self.fuse_domains and self.with_aux and len(batches) > 1 and hasattr(self.model, "forward_multi")
-                and len({tuple(b[0].shape) for b in batches}) == 1):
+        # (with_aux=False on a model WITH auxiliary branches keeps the per-domain loop: its forward_multi would compute them)
+        if (self.fuse_domains and (self.with_aux or not hasattr(self.model, "decoder_name")) and len(batches) > 1
+                and hasattr(self.model, "forward_multi") and len({tuple(b[0].shape) for b in batches}) == 1):
             return self._forward_losses_fused(batches)
         outs, auxs = [], []
         recording = self._recording("per_domain")
@@ -300,7 +301,8 @@ class MKDTrainer:
         ops.set_forward_tag(0)
         if recording:
             ops.set_forward_use_cb(lambda tag, params: self.bucketer.record_use([id(p) for p in params if p is not None]))
-        res = self.model.forward_multi(x, dl, [str(b[2]) for b in batches])
+        # (a model without auxiliary branches is trained without the domain label, as multi_train_BASE.py does: model(img))
+        res = self.model.forward_multi(x, dl if self.with_aux else None, [str(b[2]) for b in batches])
         ops.set_forward_use_cb(None)
         ops.set_forward_tag(None)
         n_total = res[0][0].numel() * self.world
