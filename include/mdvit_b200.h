@@ -9,7 +9,7 @@
  * ([B, H*W, C] == NHWC); `stream` is a cudaStream_t passed as void*; every function returns
  * 0 on success, a positive cudaError_t on a CUDA failure, or a negative MDV_ERR_* code on bad
  * arguments.  Nothing is allocated or freed by the library; workspaces are caller-owned.
- * Functions are re-entrant (no global mutable state apart from mdv_gemm_tune, a debug knob).
+ * Functions are re-entrant (no global mutable state apart from the debug knobs mdv_gemm_tune / mdv_gemm_force_pair).
  */
 #ifndef MDVIT_B200_H
 #define MDVIT_B200_H
@@ -93,6 +93,9 @@ int mdv_mlp_bwd(const void* dy_bf16, const void* w2t_bf16, const void* u_bf16, c
 
 /* Debug/tuning knob (0 = automatic): force tile N, pipeline stages, TN split count. */
 int mdv_gemm_tune(int force_bn, int force_stages, int force_split);
+/* Debug/test knob: -1 = automatic choice of the CTA-pair (tcgen05 cta_group::2) instantiation of mdv_gemm_nt, 0 / 1 = never / always
+   (the automatic rule only picks pairs for large long-K problems; tests force them on small and ragged shapes as well). */
+int mdv_gemm_force_pair(int mode);
 
 /* ------------------------------------------------------------------ LayerNorm (mdvit.py:349,357; eps 1e-6) */
 /* y = bf16(LN(x)); mean/rstd [M] are saved for backward.  C % 64 == 0, C <= 512. */

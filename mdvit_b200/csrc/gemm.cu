@@ -630,6 +630,11 @@ extern "C" int mdv_gemm_tune(int force_bn, int force_stages, int force_split) {
     return MDV_OK;
 }
 
+extern "C" int mdv_gemm_force_pair(int mode) {
+    g_force_pair = mode < 0 ? -1 : (mode != 0);
+    return MDV_OK;
+}
+
 static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, int tf32, void* stream) {
     if (!A || !W || !epi || !epi->out || M <= 0 || N <= 0 || K <= 0) return MDV_ERR_ARG;
     if ((N & 3) || (K & (tf32 ? 3 : 7)) || epi->accumulate) return MDV_ERR_ARG;

@@ -50,6 +50,35 @@ def test_gemm_nt_shapes(env, M, N, K):
         assert rel(out, want) < (BF16_TOL if out_dtype == torch.bfloat16 else 1e-5)
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(256, 64, 64), (1000, 192, 64), (300, 320, 320), (2048, 512, 2112), (5000, 32, 64), (777, 960, 320),
+                                   (131072, 2112, 512), (131072, 512, 2112), (524288, 192, 64)])
+def test_gemm_nt_cta_pair_and_bench_sizes(env, M, N, K, pair):
+    """The CTA-pair instantiation (tcgen05.mma.cta_group::2: two CTAs of a cluster share one 256-row tile) forced on and off over
+    small, ragged and the benchmark's own shapes (linear_fuse forward / input gradient at B=32/domain, the stage-0 qkv GEMM at
+    M = 524 288), bf16 and fp32 outputs, against torch fp32 on the same bf16 operands."""
+    L, lib, dev = env
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=dev)
+    ref = torch.addmm(bias, A.float(), W.float().t())
+    lib.mdv_gemm_force_pair(pair)
+    try:
+        for out_dtype, with_bias in ((torch.bfloat16, False), (torch.float32, True)):
+            out = torch.full((M, N), float("nan"), device=dev, dtype=out_dtype)
+            e = L.GemmEpi()
+            e.out, e.ldc, e.out_bf16 = L.ptr(out), N, int(out_dtype == torch.bfloat16)
+            if with_bias:
+                e.bias = L.ptr(bias)
+            L.check(lib.mdv_gemm_nt(L.ptr(A), K, L.ptr(W), K, M, N, K, ctypes.byref(e), L.stream()), "gemm_nt")
+            want = ref if with_bias else ref - bias
+            assert rel(out, want) < (BF16_TOL if out_dtype == torch.bfloat16 else 1e-5), (out_dtype, pair)
+            del out
+    finally:
+        lib.mdv_gemm_force_pair(-1)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 64, 32), (300, 320, 128), (5000, 32, 32), (3000, 64, 288), (8192, 512, 4608),
                                    (16384, 128, 64), (777, 1024, 4608), (130, 64, 36)])
 def test_gemm_nt_tf32_shapes(env, M, N, K):
