@@ -180,7 +180,7 @@ int mdv_attn_fwd(const void* qkv_bf16, const float* gate, const float* crpe_w3, 
                  const float* crpe_b5, const float* crpe_w7, const float* crpe_b7, float* stats, float* ws, void* out_bf16,
                  void* e_out_bf16 /* [B,N,C] bf16 or NULL: dwconv(V)+b, kept for mdv_attn_bwd */, int B, int H, int W, int C, int heads,
                  void* stream);
-/* dqkv overwritten; dgate and the CRPE gradients accumulate (the six CRPE gradient pointers may all be NULL: skipped). */
+/* dqkv and dgate are overwritten; the CRPE gradients accumulate (the six CRPE gradient pointers may all be NULL: skipped). */
 int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const void* y_bf16, const void* e_bf16, const float* gate, const float* crpe_w3,
                  const float* crpe_b3, const float* crpe_w5, const float* crpe_b5, const float* crpe_w7, const float* crpe_b7,
                  const float* stats, void* dqkv_bf16, float* dgate, float* dcrpe_w3, float* dcrpe_b3, float* dcrpe_w5,

@@ -197,6 +197,10 @@ extern "C" int mdv_attn_bwd(const void* qkv_bf16, const void* dy_bf16, const voi
     const float scale = 1.0f / sqrtf((float)Ch);
     CrpeG cg = {{dcrpe_w3, dcrpe_w5, dcrpe_w7}, {dcrpe_b3, dcrpe_b5, dcrpe_b7}};
     CrpeW cw = {{crpe_w3, crpe_w5, crpe_w7}, {crpe_b3, crpe_b5, crpe_b7}};
+    if (gate) {      // the tiles of an image add their gate sums with atomics: start from zero (a memset node, not a fill kernel)
+        cudaError_t e = cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     return attn_strip_bwd((const bf16*)qkv_bf16, (const bf16*)dy_bf16, (const bf16*)y_bf16, gate, kmax, zsum, A, ws, cw, cg,
                           (const bf16*)e_bf16, (bf16*)dqkv_bf16, dgate, dbias_qkv, scale, B, H, W, C, Ch, (cudaStream_t)stream);
 }

@@ -533,7 +533,7 @@ class BlockFn(torch.autograd.Function):
             dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dev)
             Ch = C // HEADS
             da_live = gate is not None and da_w1.requires_grad and da_w2.requires_grad
-            dgate = torch.zeros((B, C), dtype=F32, device=dev) if gate is not None else None
+            dgate = torch.empty((B, C), dtype=F32, device=dev) if gate is not None else None      # (zeroed by mdv_attn_bwd)
             ws = torch.empty(lib.mdv_attn_ws_floats(B, C, HEADS), dtype=F32, device=dev)
             check(lib.mdv_attn_bwd(ptr(qkv), ptr(dy), ptr(y), ptr(ecrpe), ptr(gate), ptr(c3w), ptr(c3b), ptr(c5w), ptr(c5b), ptr(c7w), ptr(c7b),
                                    ptr(stats), ptr(dqkv), ptr(dgate), ptr(G["c3w"]), ptr(G["c3b"]), ptr(G["c5w"]), ptr(G["c5b"]),

@@ -200,6 +200,7 @@ class MKDTrainer:
         self.da_params = [p for n, p in model.named_parameters() if "domain_layer" in n]
         ops.bump_weight_epoch()
         self._graph = None
+        self._onehot_cache = {}
         self.bucketer = None
         self._path = None
         if self.world > 1:
@@ -294,9 +295,13 @@ class MKDTrainer:
         G = len(batches)
         dev = batches[0][0].device
         x = torch.cat([b[0] for b in batches], dim=0)
-        dl = torch.zeros((G * B, self.num_domains), dtype=torch.float32, device=dev)
-        for g, (_, _, d) in enumerate(batches):
-            dl[g * B:(g + 1) * B, int(d)] = 1.0
+        key = (B, tuple(int(b[2]) for b in batches), dev)
+        dl = self._onehot_cache.get(key)
+        if dl is None:      # the stacked one-hot domain labels only depend on (B, domain order): built once
+            dl = torch.zeros((G * B, self.num_domains), dtype=torch.float32, device=dev)
+            for g, (_, _, d) in enumerate(batches):
+                dl[g * B:(g + 1) * B, int(d)] = 1.0
+            self._onehot_cache[key] = dl
         recording = self._recording("fused")
         ops.set_forward_tag(0)
         if recording:

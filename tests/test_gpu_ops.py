@@ -619,7 +619,7 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
     dy = torch.randn(B, N, C, device=dev).bfloat16()
     yref.backward(dy.float())
     dqkv = torch.empty_like(qkv)
-    dgate = torch.zeros(B, C, device=dev) if sup else None
+    dgate = torch.full((B, C), float("nan"), device=dev) if sup else None      # overwritten by the call
     gcw = [torch.zeros_like(t_) for t_ in cw]
     dbq = torch.zeros(3 * C, device=dev)
     L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv), P(dgate), *[P(t_) for t_ in gcw], P(dbq), P(ws),
@@ -633,8 +633,8 @@ def test_factorized_attention_fwd_bwd(env, B, H, W, C, sup):
         assert rel(gcw[2 * i + 1], sd[f"crpe.conv_list.{i}.bias"].grad) < BF16_TOL
     if sup:
         assert rel(dgate, gref.grad) < BF16_TOL
-        # activation-gradient-only mode (CRPE gradient pointers NULL): same dqkv, dgate still accumulated
-        dqkv2, dgate2 = torch.empty_like(qkv), torch.zeros(B, C, device=dev)
+        # activation-gradient-only mode (CRPE gradient pointers NULL): same dqkv, dgate still produced
+        dqkv2, dgate2 = torch.empty_like(qkv), torch.full((B, C), float("nan"), device=dev)
         L.check(lib.mdv_attn_bwd(P(qkv), P(dy), P(y), P(ecrpe), P(gate), *[P(t_) for t_ in cw], P(stats), P(dqkv2), P(dgate2), None, None, None, None,
                                  None, None, None, P(ws), B, H, W, C, 8, L.stream()), "attn_bwd")
         assert torch.equal(dqkv2, dqkv) and rel(dgate2, gref.grad) < BF16_TOL
