@@ -908,6 +908,14 @@ __global__ void __launch_bounds__(32 * ((CH <= 16 ? 64 : CH) / 8)) attn_outer_mm
 }
 
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+
+// Token tiles of 64 are staged through shared memory with coalesced 16-byte loads (g dY, S = softmax_N(K) in bf16 and fp32, V, E as
+// [token][channel] rows), the A fragments come from ldmatrix, and the results (dQ, dK, the mat-vec part of dV) overwrite the
+// staged rows of their own warp before one coalesced store — the first version loaded every fragment word straight from global
+// memory (4-byte accesses, half-used sectors, ~70 load instructions per 16 tokens) and was latency bound at 4-5x its HBM time.
 template <int CH>
 __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dy,
                                                           const bf16* __restrict__ ein, const float* __restrict__ gate,
@@ -917,15 +925,30 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
                                                           float* __restrict__ dbias_qkv, float scale, int N, int C, int tok_per_cta) {
     MDV_PDL_SYNC();
     constexpr int KS = (CH + 15) / 16;      // k-steps of 16
-    constexpr int NT = CH / 8;              // n-tiles of 8
-    constexpr int LD = KS * 16 + 8;         // shared-memory row pitch (bf16): +8 keeps the fragment loads conflict-free
-    __shared__ __align__(16) bf16 sA[CH * LD], sdA[CH * LD], sdAt[CH * LD];
-    __shared__ float sbias[2][CH];
-    __shared__ float srk[CH];
+    constexpr int NT = CH / 8;              // n-tiles of 8 = 16-byte parts of a token row
+    constexpr int LD = KS * 16 + 8;         // matrix row pitch (bf16): +8 keeps the B-fragment loads conflict-free
+    constexpr int PITCH = KS * 32 + 16;     // bytes per staged token row (padded channels + 16 B: conflict-free ldmatrix)
+    constexpr int P32 = CH + 2;             // floats per row of the fp32 S tile
+    constexpr int TT = 64;                  // tokens per tile: 16 per warp
+    extern __shared__ __align__(16) uint8_t smem_mm[];
+    bf16* sA = reinterpret_cast<bf16*>(smem_mm);
+    bf16* sdA = sA + CH * LD;
+    bf16* sdAt = sdA + CH * LD;
+    uint8_t* tF = reinterpret_cast<uint8_t*>(sdAt + CH * LD);      // g * dY      -> dQ
+    uint8_t* tV = tF + TT * PITCH;                                  // V           -> dK
+    uint8_t* tS = tV + TT * PITCH;                                  // S (bf16)    -> mat-vec part of dV
+    uint8_t* tE = tS + TT * PITCH;                                  // E = dwconv(V) + b
+    float* tS32 = reinterpret_cast<float*>(tE + TT * PITCH);        // S (fp32): the elementwise factor of dK
+    float* sbias = tS32 + TT * P32;                                 // [2][CH]
+    float* srk = sbias + 2 * CH;                                    // [CH]
+    float* sG = srk + CH;                                           // gate, kmax, 1 / zsum of this head's channels
+    float* sKm = sG + CH;
+    float* sZi = sKm + CH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int h = blockIdx.y, b = blockIdx.z;
     const size_t hbase = ((size_t)b * C + h * CH) * CH;
+    const int cb = b * C + h * CH;                        // index of this head's first channel in [B, C] tables
     for (int e = threadIdx.x; e < CH * LD; e += blockDim.x) {
         const int r = e / LD, c = e % LD;
         const bool in = c < CH;
@@ -933,7 +956,13 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
         sdA[e] = __float2bfloat16_rn(in ? dA[hbase + (size_t)r * CH + c] : 0.f);
         sdAt[e] = __float2bfloat16_rn(in ? dA[hbase + (size_t)c * CH + r] : 0.f);
     }
-    for (int e = threadIdx.x; e < 2 * CH; e += blockDim.x) (&sbias[0][0])[e] = 0.f;
+    for (int e = threadIdx.x; e < CH; e += blockDim.x) {
+        sbias[e] = sbias[CH + e] = 0.f;
+        sG[e] = gate ? gate[cb + e] : 1.f;
+        sKm[e] = kmax[cb + e];
+        sZi[e] = 1.f / zsum[cb + e];
+    }
+    for (int e = threadIdx.x; e < 4 * TT * PITCH / 16; e += blockDim.x) reinterpret_cast<uint4*>(tF)[e] = make_uint4(0, 0, 0, 0);   // padding columns
     __syncthreads();
     // r_k = sum_n S[n,k] dS[n,k] = sum_v A[k,v] dA[k,v] — with the SAME bf16-rounded dA the mat-vec below uses, so that
     // sum_n dK[n,k] = sum_n S (dS - r) still cancels to fp32 round-off (the softmax over tokens is shift-invariant: the K bias
@@ -943,11 +972,9 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
         for (int v = 0; v < CH; ++v) r = fmaf(A[hbase + (size_t)k * CH + v], __bfloat162float(sdA[k * LD + v]), r);
         srk[k] = r;
     }
-    __syncthreads();
     float bq[NT][2], bk[NT][2];
 #pragma unroll
     for (int j = 0; j < NT; ++j) bq[j][0] = bq[j][1] = bk[j][0] = bk[j][1] = 0.f;
-    const int cb = b * C + h * CH;                        // index of this head's first channel in [B, C] tables
     const uint32_t* wA = reinterpret_cast<const uint32_t*>(sA);
     const uint32_t* wdA = reinterpret_cast<const uint32_t*>(sdA);
     const uint32_t* wdAt = reinterpret_cast<const uint32_t*>(sdAt);
@@ -956,107 +983,129 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
         b0 = m[o];
         b1 = m[o + 4];
     };
+    const uint32_t uF = (uint32_t)__cvta_generic_to_shared(tF), uV = (uint32_t)__cvta_generic_to_shared(tV),
+                   uS = (uint32_t)__cvta_generic_to_shared(tS);
+    // ldmatrix (x4) addresses of this lane inside its warp's 16 rows: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), ...
+    const uint32_t a_off = (uint32_t)((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16);
     // a CTA owns `tok_per_cta` tokens of this (image, head): the matrix staging above is amortised over all of them
     const int t_begin = blockIdx.x * tok_per_cta, t_end = min(N, t_begin + tok_per_cta);
-    for (int n0 = t_begin + warp * 16; n0 < t_end; n0 += 4 * 16) {
-    const int row[2] = {n0 + gid, n0 + gid + 8};
-    const bool rok[2] = {row[0] < t_end, row[1] < t_end};
-    // ---- A fragments: dy (-> dF), k (-> S), v; column c = 16 t + 8 hf + 2 tig (+1); zero outside the head / the image
-    uint32_t fdf[KS][4], fs[KS][4], fv[KS][4];
-    float2 s32[KS][4];                                    // S in fp32, same layout (elementwise factor of dK)
-#pragma unroll
-    for (int t = 0; t < KS; ++t) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {                     // q = 2 hf + r: fragment register order (r0,c0) (r1,c0) (r0,c8) (r1,c8)
-            const int r = q & 1, hf = q >> 1;
-            const int c = 16 * t + 8 * hf + 2 * tig;
-            const bool ok = rok[r] && c < CH;
-            uint32_t dw = 0u, kw = 0u, vw = 0u;
-            if (ok) {
-                const size_t tok = (size_t)b * N + row[r];
-                dw = *reinterpret_cast<const uint32_t*>(dy + tok * C + h * CH + c);
-                kw = *reinterpret_cast<const uint32_t*>(qkv + tok * 3 * C + C + h * CH + c);
-                vw = *reinterpret_cast<const uint32_t*>(qkv + tok * 3 * C + 2 * C + h * CH + c);
+    for (int n0 = t_begin; n0 < t_end; n0 += TT) {
+        __syncthreads();      // (first pass: srk and the tables are ready; later: the previous tile's stores are done)
+        // ---- stage 64 tokens: thread = (token row, 8-channel part)
+        for (int it = threadIdx.x; it < TT * NT; it += 128) {
+            const int row = it / NT, prt = it - row * NT;
+            const int n = n0 + row;
+            uint4 d4 = make_uint4(0, 0, 0, 0), k4 = d4, v4 = d4, e4 = d4;
+            if (n < t_end) {
+                const size_t tok = (size_t)b * N + n;
+                d4 = *reinterpret_cast<const uint4*>(dy + tok * C + h * CH + prt * 8);
+                k4 = *reinterpret_cast<const uint4*>(qkv + tok * 3 * C + C + h * CH + prt * 8);
+                v4 = *reinterpret_cast<const uint4*>(qkv + tok * 3 * C + 2 * C + h * CH + prt * 8);
+                e4 = *reinterpret_cast<const uint4*>(ein + tok * C + h * CH + prt * 8);
             }
-            float2 g = make_float2(1.f, 1.f), km = make_float2(0.f, 0.f), zi = make_float2(0.f, 0.f);
-            if (c < CH) {
-                if (gate) g = *reinterpret_cast<const float2*>(gate + cb + c);
-                km = *reinterpret_cast<const float2*>(kmax + cb + c);
-                const float2 z = *reinterpret_cast<const float2*>(zsum + cb + c);
-                zi = make_float2(1.f / z.x, 1.f / z.y);
+            const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w}, kw[4] = {k4.x, k4.y, k4.z, k4.w};
+            uint32_t fw[4], sw[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int c = prt * 8 + 2 * w;
+                const float2 d = up2(dw[w]), kk = up2(kw[w]);
+                fw[w] = f2_to_bf2(sG[c] * d.x, sG[c + 1] * d.y);
+                float2 sv = make_float2(0.f, 0.f);
+                if (n < t_end) sv = make_float2(__expf(kk.x - sKm[c]) * sZi[c], __expf(kk.y - sKm[c + 1]) * sZi[c + 1]);
+                sw[w] = f2_to_bf2(sv.x, sv.y);
+                *reinterpret_cast<float2*>(tS32 + row * P32 + c) = sv;
             }
-            const float2 d = up2(dw), kk = up2(kw);
-            fdf[t][q] = f2_to_bf2(g.x * d.x, g.y * d.y);
-            const float2 sv = ok ? make_float2(__expf(kk.x - km.x) * zi.x, __expf(kk.y - km.y) * zi.y) : make_float2(0.f, 0.f);
-            s32[t][q] = sv;
-            fs[t][q] = f2_to_bf2(sv.x, sv.y);
-            fv[t][q] = vw;
+            const uint32_t so = (uint32_t)(row * PITCH + prt * 16);
+            *reinterpret_cast<uint4*>(tF + so) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+            *reinterpret_cast<uint4*>(tS + so) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+            *reinterpret_cast<uint4*>(tV + so) = v4;
+            *reinterpret_cast<uint4*>(tE + so) = e4;
         }
-    }
-    // ---- T1 -> dQ = s T1 + dF * E
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        __syncthreads();
+        // ---- this warp's 16 tokens: A fragments of dF, V, S
+        uint32_t fdf[KS][4], fv[KS][4], fs[KS][4];
 #pragma unroll
         for (int t = 0; t < KS; ++t) {
-            uint32_t b0, b1;
-            bfrag(wA, j, t, b0, b1);
-            mma_bf16_16816(acc, fdf[t], b0, b1);
+            ldsm_x4(fdf[t], uF + a_off + t * 32);
+            ldsm_x4(fv[t], uV + a_off + t * 32);
+            ldsm_x4(fs[t], uS + a_off + t * 32);
         }
-        const int c = 8 * j + 2 * tig;
+        __syncwarp();      // every lane has its fragments: the rows may now be overwritten with the results
+        const int rl[2] = {warp * 16 + gid, warp * 16 + gid + 8};       // tile rows of this thread's accumulator halves
+        const bool rok[2] = {n0 + rl[0] < t_end, n0 + rl[1] < t_end};
+        // ---- T1 -> dQ = s T1 + dF * E          (written over the dF rows)
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (!rok[r]) continue;
-            const size_t tok = (size_t)b * N + row[r];
-            const float2 e = up2(*reinterpret_cast<const uint32_t*>(ein + tok * C + h * CH + c));
-            const float2 df = up2(fdf[j >> 1][2 * (j & 1) + r]);
-            const float qx = fmaf(scale, acc[2 * r], df.x * e.x), qy = fmaf(scale, acc[2 * r + 1], df.y * e.y);
-            bq[j][0] += qx;
-            bq[j][1] += qy;
-            *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + h * CH + c) = f2_to_bf2(qx, qy);
+        for (int j = 0; j < NT; ++j) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < KS; ++t) {
+                uint32_t b0, b1;
+                bfrag(wA, j, t, b0, b1);
+                mma_bf16_16816(acc, fdf[t], b0, b1);
+            }
+            const int c = 8 * j + 2 * tig;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                uint32_t* pf = reinterpret_cast<uint32_t*>(tF + rl[r] * PITCH + c * 2);
+                const float2 e = up2(*reinterpret_cast<const uint32_t*>(tE + rl[r] * PITCH + c * 2));
+                const float2 df = up2(*pf);
+                const float qx = fmaf(scale, acc[2 * r], df.x * e.x), qy = fmaf(scale, acc[2 * r + 1], df.y * e.y);
+                if (rok[r]) {
+                    bq[j][0] += qx;
+                    bq[j][1] += qy;
+                }
+                *pf = f2_to_bf2(qx, qy);
+            }
         }
-    }
-    // ---- T2 -> dK = S * (T2 - r)
+        // ---- T2 -> dK = S * (T2 - r)           (written over the V rows)
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < NT; ++j) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int t = 0; t < KS; ++t) {
-            uint32_t b0, b1;
-            bfrag(wdA, j, t, b0, b1);
-            mma_bf16_16816(acc, fv[t], b0, b1);
+            for (int t = 0; t < KS; ++t) {
+                uint32_t b0, b1;
+                bfrag(wdA, j, t, b0, b1);
+                mma_bf16_16816(acc, fv[t], b0, b1);
+            }
+            const int c = 8 * j + 2 * tig;
+            const float2 rr = make_float2(srk[c], srk[c + 1]);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float2 sv = *reinterpret_cast<const float2*>(tS32 + rl[r] * P32 + c);
+                const float kx = sv.x * (acc[2 * r] - rr.x), ky = sv.y * (acc[2 * r + 1] - rr.y);
+                if (rok[r]) {
+                    bk[j][0] += kx;
+                    bk[j][1] += ky;
+                }
+                *reinterpret_cast<uint32_t*>(tV + rl[r] * PITCH + c * 2) = f2_to_bf2(kx, ky);
+            }
         }
-        const int c = 8 * j + 2 * tig;
-        const float2 rr = make_float2(srk[c], srk[c + 1]);
+        // ---- T3 -> mat-vec part of dV            (written over the S rows; parked in the dV slot of dqkv)
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (!rok[r]) continue;
-            const size_t tok = (size_t)b * N + row[r];
-            const float2 sv = s32[j >> 1][2 * (j & 1) + r];
-            const float kx = sv.x * (acc[2 * r] - rr.x), ky = sv.y * (acc[2 * r + 1] - rr.y);
-            bk[j][0] += kx;
-            bk[j][1] += ky;
-            *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + C + h * CH + c) = f2_to_bf2(kx, ky);
+        for (int j = 0; j < NT; ++j) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < KS; ++t) {
+                uint32_t b0, b1;
+                bfrag(wdAt, j, t, b0, b1);
+                mma_bf16_16816(acc, fs[t], b0, b1);
+            }
+            const int c = 8 * j + 2 * tig;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) *reinterpret_cast<uint32_t*>(tS + rl[r] * PITCH + c * 2) = f2_to_bf2(acc[2 * r], acc[2 * r + 1]);
         }
-    }
-    // ---- T3 -> mat-vec part of dV, parked in the dV slot
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int t = 0; t < KS; ++t) {
-            uint32_t b0, b1;
-            bfrag(wdAt, j, t, b0, b1);
-            mma_bf16_16816(acc, fs[t], b0, b1);
+        __syncthreads();
+        // ---- coalesced stores of the three result tiles
+        for (int it = threadIdx.x; it < TT * NT; it += 128) {
+            const int row = it / NT, prt = it - row * NT;
+            const int n = n0 + row;
+            if (n >= t_end) continue;
+            bf16* o = dqkv + ((size_t)b * N + n) * 3 * C + h * CH + prt * 8;
+            const uint32_t so = (uint32_t)(row * PITCH + prt * 16);
+            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(tF + so);
+            *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(tV + so);
+            *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(tS + so);
         }
-        const int c = 8 * j + 2 * tig;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (!rok[r]) continue;
-            const size_t tok = (size_t)b * N + row[r];
-            *reinterpret_cast<uint32_t*>(dqkv + tok * 3 * C + 2 * C + h * CH + c) = f2_to_bf2(acc[2 * r], acc[2 * r + 1]);
-        }
-    }
     }
     // ---- bias-gradient column sums of dQ and dK: over the 8 row groups of the warp, then the block, then one atomic per column
     if (dbias_qkv) {
@@ -1071,17 +1120,23 @@ __global__ void __launch_bounds__(128) attn_mm_bwd_kernel(const bf16* __restrict
                     k2 += __shfl_xor_sync(0xffffffffu, k2, o);
                 }
                 if (gid == 0) {
-                    atomicAdd(&sbias[0][8 * j + 2 * tig + u], a);
-                    atomicAdd(&sbias[1][8 * j + 2 * tig + u], k2);
+                    atomicAdd(&sbias[8 * j + 2 * tig + u], a);
+                    atomicAdd(&sbias[CH + 8 * j + 2 * tig + u], k2);
                 }
             }
         }
         __syncthreads();
         for (int e = threadIdx.x; e < 2 * CH; e += blockDim.x) {
             const int which = e / CH, c = e % CH;
-            atomicAdd(dbias_qkv + which * C + h * CH + c, sbias[which][c]);
+            atomicAdd(dbias_qkv + which * C + h * CH + c, sbias[which * CH + c]);
         }
     }
+}
+
+template <int CH>
+constexpr int attn_mm_smem_bytes() {
+    constexpr int KS = (CH + 15) / 16, LD = KS * 16 + 8, PITCH = KS * 32 + 16;
+    return 3 * CH * LD * 2 + 4 * 64 * PITCH + 64 * (CH + 2) * 4 + (2 * CH + CH + 3 * CH) * 4;
 }
 
 // One launch covers every channel group; the window of a group (that of its last head) selects the instantiation.
@@ -1172,8 +1227,14 @@ int launch_bwd(const bf16* qkv, const bf16* dy, const bf16* yout, const float* g
         // tokens per CTA: the whole image up to 512 (more CTAs only while the grid would not fill the machine)
         int tpc = 64;
         while (tpc < 512 && (long long)mdv_cdiv(H * W, tpc) * (C / CH) * B > 4 * MDV_NUM_SMS) tpc *= 2;
-        mdv_launch(attn_mm_bwd_kernel<CH>, dim3(mdv_cdiv(H * W, tpc), C / CH, B), dim3(128), 0, st, qkv, dy, ein, gate, A, dA, rk, kmax, zsum, dqkv, dbias_qkv,
-                   scale, H * W, C, tpc);
+        static bool mm_configured = false;
+        if (!mm_configured) {
+            int rc = set_smem(attn_mm_bwd_kernel<CH>, attn_mm_smem_bytes<CH>());
+            if (rc) return rc;
+            mm_configured = true;
+        }
+        mdv_launch(attn_mm_bwd_kernel<CH>, dim3(mdv_cdiv(H * W, tpc), C / CH, B), dim3(128), attn_mm_smem_bytes<CH>(), st, qkv, dy, ein, gate, A, dA, rk,
+                   kmax, zsum, dqkv, dbias_qkv, scale, H * W, C, tpc);
         MDV_CHECK_LAUNCH();
     }
     mdv_launch((attn_bwd_strip_kernel<CH, EXT>), dim3(tile_grid(B, H, W, C / Cfg<CH>::CPW)), dim3(BWD_THREADS), smem, st, qkv, dy, yout, gate, A, dA, rk, kmax, zsum, cw, cg, ein, dqkv,
