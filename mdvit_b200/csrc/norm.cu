@@ -522,22 +522,42 @@ __global__ void bn_finalize_g_kernel(const double* __restrict__ sums, int G, int
     }
 }
 
+// y = act(gamma (z - mean) rstd + beta): row-walking like the backward apply kernel (parameters once per thread, 4 rows in flight)
 template <typename TO>
 __global__ void __launch_bounds__(256) bn_act_fwd_g_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, int act, TO* __restrict__ y, int total,
-                                                            int C, int group_elems) {
+                                                            const float* __restrict__ beta, int act, TO* __restrict__ y, int Mg,
+                                                            int C, int rows_per_block) {
     MDV_PDL_SYNC();
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= total) return;
-    const int c = i % C, g = i / group_elems;
-    const float4 v = *reinterpret_cast<const float4*>(z + i);
+    const int tpr = C >> 2, rpi = 256 / tpr;
+    const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+    if (rl >= rpi) return;
+    const int g = blockIdx.z, c = 4 * cl;
+    const int r0 = blockIdx.x * rows_per_block, r1e = min(Mg, r0 + rows_per_block);
+    const size_t base = (size_t)g * Mg * C;
     const float4 mu = *reinterpret_cast<const float4*>(mean + (size_t)g * C + c), rs = *reinterpret_cast<const float4*>(rstd + (size_t)g * C + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-    float o[4] = {act_fwd((v.x - mu.x) * rs.x * ga.x + be.x, act), act_fwd((v.y - mu.y) * rs.y * ga.y + be.y, act),
-                  act_fwd((v.z - mu.z) * rs.z * ga.z + be.z, act), act_fwd((v.w - mu.w) * rs.w * ga.w + be.w, act)};
-    if (sizeof(TO) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + i) = make_float4(o[0], o[1], o[2], o[3]);
-    else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + i) = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
+    // y = z * a + b with a = gamma rstd, b = beta - mean a
+    const float4 sa = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+    constexpr int U = 4;
+    for (int r = r0 + rl; r < r1e; r += rpi * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = r + u * rpi;
+            v[u] = rr < r1e ? *reinterpret_cast<const float4*>(z + base + (size_t)rr * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = r + u * rpi;
+            if (rr >= r1e) break;
+            const float o0 = act_fwd((v[u].x - mu.x) * sa.x + be.x, act), o1 = act_fwd((v[u].y - mu.y) * sa.y + be.y, act),
+                        o2 = act_fwd((v[u].z - mu.z) * sa.z + be.z, act), o3 = act_fwd((v[u].w - mu.w) * sa.w + be.w, act);
+            const size_t o = base + (size_t)rr * C + c;
+            if (sizeof(TO) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o) = make_float4(o0, o1, o2, o3);
+            else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + o) = make_uint2(f2_to_bf2(o0, o1), f2_to_bf2(o2, o3));
+        }
+    }
 }
 
 // coef[g][c] = sum_g / Mg, coef[g][C+c] = sum_gxhat / Mg;  dgamma += sum over groups of sum_gxhat; dbeta += ... sum_g
@@ -558,45 +578,88 @@ __global__ void bn_bwd_finalize_g_kernel(const double* __restrict__ sums, int G,
     if (dgamma) atomicAdd(dgamma + c, (float)sq);
 }
 
+// dz = gamma rstd (g - c0 - xhat c1), g = dy act'(.).  Same thread mapping as bn_reduce_g_kernel: a thread owns 4 channels and walks
+// the rows of its block's band, 4 rows in flight — the per-channel parameters (7 float4) are loaded once instead of once per 16
+// bytes of z, and there is no index arithmetic per element.
 template <typename TO, bool RANK1 = false>
 __global__ void __launch_bounds__(256) bn_bwd_apply_g_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                                              const float* __restrict__ coef, TO* __restrict__ dz, int total, int C,
-                                                              int group_elems, Rank1Dy r1 = Rank1Dy()) {
+                                                              const float* __restrict__ coef, TO* __restrict__ dz, int Mg, int C,
+                                                              int rows_per_block, Rank1Dy r1 = Rank1Dy()) {
     MDV_PDL_SYNC();
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= total) return;
-    const int c = i % C, g = i / group_elems;
-    const float4 zv = *reinterpret_cast<const float4*>(z + i);
-    float4 dv;
-    if (RANK1) {
-        const int row = i / C;
-        const float dl = __ldg(r1.dlog + row);
-        const float4 w = *reinterpret_cast<const float4*>(r1.wtab + (size_t)(row / r1.rps) * C + c);
-        dv = make_float4(dl * w.x, dl * w.y, dl * w.z, dl * w.w);
-    } else {
-        dv = *reinterpret_cast<const float4*>(dy + i);
-    }
+    const int tpr = C >> 2;                       // threads per row
+    const int rpi = 256 / tpr;                    // rows per block iteration
+    const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+    if (rl >= rpi) return;
+    const int g = blockIdx.z;
+    const int r0 = blockIdx.x * rows_per_block, r1e = min(Mg, r0 + rows_per_block);
+    const size_t base = (size_t)g * Mg * C;
+    const int c = 4 * cl;
     const float4 mu = *reinterpret_cast<const float4*>(mean + (size_t)g * C + c), rs = *reinterpret_cast<const float4*>(rstd + (size_t)g * C + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
     const float4 k0 = *reinterpret_cast<const float4*>(coef + (size_t)g * 2 * C + c), k1 = *reinterpret_cast<const float4*>(coef + (size_t)g * 2 * C + C + c);
-    const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w},
-                g4[4] = {ga.x, ga.y, ga.z, ga.w}, b4[4] = {be.x, be.y, be.z, be.w}, c0[4] = {k0.x, k0.y, k0.z, k0.w}, c1[4] = {k1.x, k1.y, k1.z, k1.w};
-    float o[4];
+    const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w}, g4[4] = {ga.x, ga.y, ga.z, ga.w},
+                b4[4] = {be.x, be.y, be.z, be.w}, c0[4] = {k0.x, k0.y, k0.z, k0.w}, c1[4] = {k1.x, k1.y, k1.z, k1.w};
+    constexpr int U = 4;
+    int cur_b = -1;
+    float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0 + rl; r < r1e; r += rpi * U) {
+        float4 zv[U], dv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float xh = (zz[j] - m4[j]) * r4[j];
-        const float gg = dd[j] * act_bwd(xh * g4[j] + b4[j], act);
-        o[j] = g4[j] * r4[j] * (gg - c0[j] - xh * c1[j]);
+        for (int u = 0; u < U; ++u) {
+            const int rr = r + u * rpi;
+            const bool ok = rr < r1e;
+            const size_t o = base + (size_t)rr * C + c;
+            zv[u] = ok ? *reinterpret_cast<const float4*>(z + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!RANK1) {
+                dv[u] = ok ? *reinterpret_cast<const float4*>(dy + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                dv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {      // dy[m, c] = dlog[m] * wrow[c] * dropout2d_mask(m / rps, c), from the per-sample factor table (G == 1)
+                    const int bb = rr / r1.rps;
+                    if (bb != cur_b) {
+                        cur_b = bb;
+                        wm = *reinterpret_cast<const float4*>(r1.wtab + (size_t)bb * C + c);
+                    }
+                    const float dl = __ldg(r1.dlog + rr);
+                    dv[u] = make_float4(dl * wm.x, dl * wm.y, dl * wm.z, dl * wm.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = r + u * rpi;
+            if (rr >= r1e) break;
+            const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (zz[j] - m4[j]) * r4[j];
+                const float gg = dd[j] * act_bwd(xh * g4[j] + b4[j], act);
+                o4[j] = g4[j] * r4[j] * (gg - c0[j] - xh * c1[j]);
+            }
+            const size_t o = base + (size_t)rr * C + c;
+            if (sizeof(TO) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(dz) + o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dz) + o) = make_uint2(f2_to_bf2(o4[0], o4[1]), f2_to_bf2(o4[2], o4[3]));
+        }
     }
-    if (sizeof(TO) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(dz) + i) = make_float4(o[0], o[1], o[2], o[3]);
-    else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dz) + i) = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
 }
 
 int grouped_rows_per_block(int Mg, int C, int G) {
     const int rpi = 256 / (C / 4);
     int want = (6 * MDV_NUM_SMS) / G;                     // ~6 blocks per SM over all groups
+    if (want < 1) want = 1;
+    int rpb = mdv_cdiv(Mg, want);
+    const int minr = rpi * 16;
+    if (rpb < minr) rpb = minr;
+    return rpb;
+}
+
+// streaming apply pass: ~16 blocks per SM over all groups, at least 4 iterations of 4 rows per thread
+int apply_rows_per_block(int Mg, int C, int G) {
+    const int rpi = 256 / (C / 4);
+    int want = (16 * MDV_NUM_SMS) / G;
     if (want < 1) want = 1;
     int rpb = mdv_cdiv(Mg, want);
     const int minr = rpi * 16;
@@ -773,14 +836,13 @@ static int bn_act_bwd_impl(const float* dy, const Rank1Dy& r1, const float* z, c
         MDV_CHECK_LAUNCH();
         mdv_launch(bn_bwd_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)sums, 1, M, C, coef, dgamma, dbeta);
         MDV_CHECK_LAUNCH();
-        const int total = M * C;
-        const int blocks = mdv_cdiv(total / 4, 256);
+        const int rpa = apply_rows_per_block(M, C, 1);
         if (dz_bf16)
-            mdv_launch((bn_bwd_apply_g_kernel<bf16, true>), dim3(blocks), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
-                       (const float*)coef, (bf16*)dz, total, C, M * C, rt);
+            mdv_launch((bn_bwd_apply_g_kernel<bf16, true>), dim3(mdv_cdiv(M, rpa), 1, 1), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta,
+                       act, (const float*)coef, (bf16*)dz, M, C, rpa, rt);
         else
-            mdv_launch((bn_bwd_apply_g_kernel<float, true>), dim3(blocks), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta, act,
-                       (const float*)coef, (float*)dz, total, C, M * C, rt);
+            mdv_launch((bn_bwd_apply_g_kernel<float, true>), dim3(mdv_cdiv(M, rpa), 1, 1), dim3(256), 0, st, (const float*)nullptr, z, mean, rstd, gamma, beta,
+                       act, (const float*)coef, (float*)dz, M, C, rpa, rt);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
@@ -825,10 +887,13 @@ extern "C" int mdv_bn_train_fwd_grouped(const float* z, int G, int Mg, int C, fl
     MDV_CHECK_LAUNCH();
     const int total = G * Mg * C;
     const int blocks = mdv_cdiv(total / 4, 256);
+    const int rpa = apply_rows_per_block(Mg, C, G);
     if (y_bf16)
-        mdv_launch(bn_act_fwd_g_kernel<bf16>, dim3(blocks), dim3(256), 0, st, z, (const float*)mean, (const float*)rstd, gamma, beta, act, (bf16*)y, total, C, Mg * C);
+        mdv_launch(bn_act_fwd_g_kernel<bf16>, dim3(mdv_cdiv(Mg, rpa), 1, G), dim3(256), 0, st, z, (const float*)mean, (const float*)rstd, gamma, beta, act,
+                   (bf16*)y, Mg, C, rpa);
     else
-        mdv_launch(bn_act_fwd_g_kernel<float>, dim3(blocks), dim3(256), 0, st, z, (const float*)mean, (const float*)rstd, gamma, beta, act, (float*)y, total, C, Mg * C);
+        mdv_launch(bn_act_fwd_g_kernel<float>, dim3(mdv_cdiv(Mg, rpa), 1, G), dim3(256), 0, st, z, (const float*)mean, (const float*)rstd, gamma, beta, act,
+                   (float*)y, Mg, C, rpa);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
@@ -848,12 +913,13 @@ extern "C" int mdv_bn_act_bwd_grouped(const float* dy, const float* z, const flo
     MDV_CHECK_LAUNCH();
     mdv_launch(bn_bwd_finalize_g_kernel, dim3(mdv_cdiv(C, 128)), dim3(128), 0, st, (const double*)sums, G, Mg, C, coef, dgamma, dbeta);
     MDV_CHECK_LAUNCH();
-    const int total = G * Mg * C;
-    const int blocks = mdv_cdiv(total / 4, 256);
+    const int rpa = apply_rows_per_block(Mg, C, G);
     if (dz_bf16)
-        mdv_launch(bn_bwd_apply_g_kernel<bf16>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (bf16*)dz, total, C, Mg * C, Rank1Dy());
+        mdv_launch(bn_bwd_apply_g_kernel<bf16>, dim3(mdv_cdiv(Mg, rpa), 1, G), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef,
+                   (bf16*)dz, Mg, C, rpa, Rank1Dy());
     else
-        mdv_launch(bn_bwd_apply_g_kernel<float>, dim3(blocks), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef, (float*)dz, total, C, Mg * C, Rank1Dy());
+        mdv_launch(bn_bwd_apply_g_kernel<float>, dim3(mdv_cdiv(Mg, rpa), 1, G), dim3(256), 0, st, dy, z, mean, rstd, gamma, beta, act, (const float*)coef,
+                   (float*)dz, Mg, C, rpa, Rank1Dy());
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }
