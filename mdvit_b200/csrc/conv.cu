@@ -756,6 +756,102 @@ __global__ void __launch_bounds__(256) upsample_bwd_h_kernel(const TI* __restric
     }
 }
 
+// bf16 gradients, 8 channels (16 bytes) per thread, tap weights from a per-block table: the scalar versions above spent more
+// instructions on bil_src per tap than on the 4 multiply-adds and moved 8 bytes per load (0.3-0.4 of HBM at the aux decoder's
+// 512-channel maps).  wtab[i][k] = weight of output pixel S*i - S/2 + k in input pixel i (0 outside the image).
+template <int S>
+__device__ __forceinline__ void upsample_wtab(float* wtab, int n_in) {
+    const int n_out = n_in * S;
+    const float sc = 1.f / S;
+    for (int e = threadIdx.x; e < n_in * 2 * S; e += blockDim.x) {
+        const int i = e / (2 * S), k = e - i * 2 * S;
+        const int x = S * i - S / 2 + k;
+        float w = 0.f;
+        if (x >= 0 && x < n_out) {
+            int x0, x1;
+            float lx;
+            bil_src(x, sc, n_in, x0, x1, lx);
+            w = (x0 == i ? 1.f - lx : 0.f) + (x1 == i ? lx : 0.f);
+        }
+        wtab[e] = w;
+    }
+}
+__device__ __forceinline__ void fma8(float (&acc)[8], float w, uint4 v) {
+    const float2 a = bf2_to_f2(v.x), b = bf2_to_f2(v.y), c = bf2_to_f2(v.z), d = bf2_to_f2(v.w);
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * b.x; acc[3] += w * b.y;
+    acc[4] += w * c.x; acc[5] += w * c.y; acc[6] += w * d.x; acc[7] += w * d.y;
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) upsample_bwd_h8_kernel(const bf16* __restrict__ dout, int ld_out, float* __restrict__ tmp, int B,
+                                                               int Ho, int Wi, int C) {
+    MDV_PDL_SYNC();
+    extern __shared__ float wtab[];      // [Wi][2S]
+    upsample_wtab<S>(wtab, Wi);
+    __syncthreads();
+    const int Wo = Wi * S;
+    const int cvn = C >> 3;
+    const int total = B * Ho * Wi * cvn;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = (idx % cvn) * 8;
+        const int pix = idx / cvn;            // (b, y, xi)
+        const int xi = pix % Wi;
+        const int row = pix / Wi;             // b * Ho + y
+        const int xa = S * xi - S / 2;
+        const bf16* prow = dout + (size_t)row * Wo * ld_out + c;
+        uint4 v[2 * S];
+#pragma unroll
+        for (int k = 0; k < 2 * S; ++k) {
+            const int x = min(max(xa + k, 0), Wo - 1);          // (clamped address; the table holds weight 0 outside)
+            v[k] = *reinterpret_cast<const uint4*>(prow + (size_t)x * ld_out);
+        }
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 2 * S; ++k) fma8(acc, wtab[xi * 2 * S + k], v[k]);
+        float* o = tmp + (size_t)pix * C + c;
+        st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        st4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+}
+
+// one-pass 2x version (window 4 x 4)
+__global__ void __launch_bounds__(256) upsample_bwd_int8x2_kernel(const bf16* __restrict__ dout, int ld_out, float* __restrict__ din,
+                                                                   int ld_in, int B, int Hi, int Wi, int C) {
+    MDV_PDL_SYNC();
+    constexpr int S = 2;
+    extern __shared__ float wtab[];      // [Wi][4] then [Hi][4]
+    float* wty = wtab + Wi * 2 * S;
+    upsample_wtab<S>(wtab, Wi);
+    upsample_wtab<S>(wty, Hi);
+    __syncthreads();
+    const int Ho = Hi * S, Wo = Wi * S;
+    const int cvn = C >> 3;
+    const int total = B * Hi * Wi * cvn;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = (idx % cvn) * 8;
+        const int pix = idx / cvn;
+        const int xi = pix % Wi;
+        const int yi = (pix / Wi) % Hi;
+        const int b = pix / (Wi * Hi);
+        const int xa = S * xi - S / 2, ya = S * yi - S / 2;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2 * S; ++r) {
+            const int y = min(max(ya + r, 0), Ho - 1);
+            const float wy = wty[yi * 2 * S + r];
+            const bf16* prow = dout + ((size_t)(b * Ho + y) * Wo) * ld_out + c;
+            uint4 v[2 * S];
+#pragma unroll
+            for (int k = 0; k < 2 * S; ++k) v[k] = *reinterpret_cast<const uint4*>(prow + (size_t)min(max(xa + k, 0), Wo - 1) * ld_out);
+#pragma unroll
+            for (int k = 0; k < 2 * S; ++k) fma8(acc, wy * wtab[xi * 2 * S + k], v[k]);
+        }
+        float* o = din + (size_t)pix * ld_in + c;
+        st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        st4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+}
+
 template <int S>
 __global__ void __launch_bounds__(256) upsample_bwd_v_kernel(const float* __restrict__ tmp, float* __restrict__ din, int ld_in, int B,
                                                               int Hi, int Wi, int C) {
@@ -999,13 +1095,22 @@ extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, flo
     if (ws && (S == 4 || S == 8) && fits_i32((long long)B * Ho * Wi * C)) {
         // separable two-pass form (scratch: B*Ho*Wi*C floats)
         const int gh = grid_for((long long)B * Ho * Wi * (C / 4));
+        const bool v8 = dout_bf16 && !(C & 7) && !(ld_out & 7) && !(reinterpret_cast<uintptr_t>(dout) & 15);
+        const int gh8 = grid_for((long long)B * Ho * Wi * (C / 8));
 #define MDV_UPH(SS)                                                                                                                  \
-    if (dout_bf16) mdv_launch((upsample_bwd_h_kernel<bf16, SS>), dim3(gh), dim3(256), 0, st, (const bf16*)dout, ld_out, ws, B, Ho, Wi, C);     \
+    if (v8) mdv_launch((upsample_bwd_h8_kernel<SS>), dim3(gh8), dim3(256), (size_t)Wi * 2 * SS * sizeof(float), st, (const bf16*)dout, ld_out, ws, B, Ho, Wi, C); \
+    else if (dout_bf16) mdv_launch((upsample_bwd_h_kernel<bf16, SS>), dim3(gh), dim3(256), 0, st, (const bf16*)dout, ld_out, ws, B, Ho, Wi, C);     \
     else mdv_launch((upsample_bwd_h_kernel<float, SS>), dim3(gh), dim3(256), 0, st, (const float*)dout, ld_out, ws, B, Ho, Wi, C);             \
     MDV_CHECK_LAUNCH();                                                                                                              \
     mdv_launch((upsample_bwd_v_kernel<SS>), dim3(g), dim3(256), 0, st, (const float*)ws, din, ld_in, B, Hi, Wi, C);
         if (S == 4) { MDV_UPH(4) } else { MDV_UPH(8) }
 #undef MDV_UPH
+        MDV_CHECK_LAUNCH();
+        return MDV_OK;
+    }
+    if (S == 2 && dout_bf16 && !(C & 7) && !(ld_out & 7) && !(ld_in & 3) && !(reinterpret_cast<uintptr_t>(dout) & 15)) {
+        mdv_launch(upsample_bwd_int8x2_kernel, dim3(grid_for((long long)B * Hi * Wi * (C / 8))), dim3(256), (size_t)(Wi + Hi) * 4 * sizeof(float), st,
+                   (const bf16*)dout, ld_out, din, ld_in, B, Hi, Wi, C);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
