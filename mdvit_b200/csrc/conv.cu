@@ -852,6 +852,41 @@ __global__ void __launch_bounds__(256) upsample_bwd_int8x2_kernel(const bf16* __
     }
 }
 
+// single-channel maps (the gradients of the commuted segmentation heads' logits): integer factor, table weights — the generic
+// gather kernel scanned a (3S)^2 candidate window with two bil_src evaluations per candidate
+template <int S>
+__global__ void __launch_bounds__(256) upsample_bwd_int1_kernel(const float* __restrict__ dout, float* __restrict__ din, int B, int Hi,
+                                                                 int Wi) {
+    MDV_PDL_SYNC();
+    extern __shared__ float wtab[];      // [Wi][2S] then [Hi][2S]
+    float* wty = wtab + Wi * 2 * S;
+    upsample_wtab<S>(wtab, Wi);
+    upsample_wtab<S>(wty, Hi);
+    __syncthreads();
+    const int Ho = Hi * S, Wo = Wi * S;
+    const int total = B * Hi * Wi;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int xi = idx % Wi;
+        const int yi = (idx / Wi) % Hi;
+        const int b = idx / (Wi * Hi);
+        const int xa = S * xi - S / 2, ya = S * yi - S / 2;
+        float wx[2 * S];
+#pragma unroll
+        for (int k = 0; k < 2 * S; ++k) wx[k] = wtab[xi * 2 * S + k];
+        float acc = 0.f;
+#pragma unroll 2
+        for (int r = 0; r < 2 * S; ++r) {
+            const int y = min(max(ya + r, 0), Ho - 1);
+            const float* prow = dout + (size_t)(b * Ho + y) * Wo;
+            float rs = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2 * S; ++k) rs = fmaf(wx[k], __ldg(prow + min(max(xa + k, 0), Wo - 1)), rs);
+            acc = fmaf(wty[yi * 2 * S + r], rs, acc);
+        }
+        din[idx] = acc;
+    }
+}
+
 template <int S>
 __global__ void __launch_bounds__(256) upsample_bwd_v_kernel(const float* __restrict__ tmp, float* __restrict__ din, int ld_in, int B,
                                                               int Hi, int Wi, int C) {
@@ -1085,6 +1120,16 @@ extern "C" int mdv_upsample_bwd(const void* dout, int dout_bf16, int ld_out, flo
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 1) {
         if (dout_bf16) return MDV_ERR_UNSUPPORTED;
+        const int S1 = (Ho % Hi == 0 && Wo % Wi == 0 && Ho / Hi == Wo / Wi) ? Ho / Hi : 0;
+        if ((S1 == 2 || S1 == 4 || S1 == 8) && (size_t)(Wi + Hi) * 2 * S1 * sizeof(float) <= 40 * 1024) {
+            const dim3 g1(grid_for((long long)B * Hi * Wi));
+            const size_t sm = (size_t)(Wi + Hi) * 2 * S1 * sizeof(float);
+            if (S1 == 2) mdv_launch(upsample_bwd_int1_kernel<2>, g1, dim3(256), sm, st, (const float*)dout, din, B, Hi, Wi);
+            else if (S1 == 4) mdv_launch(upsample_bwd_int1_kernel<4>, g1, dim3(256), sm, st, (const float*)dout, din, B, Hi, Wi);
+            else mdv_launch(upsample_bwd_int1_kernel<8>, g1, dim3(256), sm, st, (const float*)dout, din, B, Hi, Wi);
+            MDV_CHECK_LAUNCH();
+            return MDV_OK;
+        }
         mdv_launch((upsample_bwd_kernel<float, 1>), dim3(grid_for((long long)B * Hi * Wi)), dim3(256), 0, st, (const float*)dout, 1, din, 1, B, Hi, Wi, Ho, Wo, 1);
         MDV_CHECK_LAUNCH();
         return MDV_OK;
