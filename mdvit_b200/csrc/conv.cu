@@ -598,6 +598,56 @@ __global__ void __launch_bounds__(256) upsample_fwd_walk_kernel(const TI* __rest
     }
 }
 
+// bf16 -> bf16 with 8 channels (16 bytes) per thread: the aux decoder's 512-channel maps written into the concat buffer
+__global__ void __launch_bounds__(256) upsample_fwd_walk8_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
+                                                                  int Hi, int Wi, int Ho, int Wo, int C, int seg) {
+    MDV_PDL_SYNC();
+    const int c8n = C >> 3;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= Wo * c8n) return;
+    const int x = t / c8n, c = (t % c8n) * 8;
+    const float sy = (float)Hi / Ho, sx = (float)Wi / Wo;
+    int x0, x1;
+    float lx;
+    bil_src(x, sx, Wi, x0, x1, lx);
+    const bf16* base = in + (size_t)blockIdx.z * Hi * Wi * ld_in + c;
+    bf16* obase = out + ((size_t)blockIdx.z * Ho * Wo + x) * ld_out + c;
+    struct F8 { float v[8]; };
+    auto hload = [&](int ys) {
+        const uint4 a = *reinterpret_cast<const uint4*>(base + ((size_t)ys * Wi + x0) * ld_in), b = *reinterpret_cast<const uint4*>(base + ((size_t)ys * Wi + x1) * ld_in);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        F8 r;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float2 fa = bf2_to_f2(aw[w]), fb = bf2_to_f2(bw[w]);
+            r.v[2 * w] = fa.x + lx * (fb.x - fa.x);
+            r.v[2 * w + 1] = fa.y + lx * (fb.y - fa.y);
+        }
+        return r;
+    };
+    int i0 = -1, i1 = -1;
+    F8 h0 = {}, h1 = {};
+    const int y0 = blockIdx.y * seg, y1 = min(Ho, y0 + seg);
+    for (int y = y0; y < y1; ++y) {
+        int ys0, ys1;
+        float ly;
+        bil_src(y, sy, Hi, ys0, ys1, ly);
+        if (ys0 != i0) {
+            if (ys0 == i1) h0 = h1; else h0 = hload(ys0);
+            i0 = ys0;
+        }
+        if (ys1 != i1) {
+            if (ys1 == i0) h1 = h0; else h1 = hload(ys1);
+            i1 = ys1;
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            o[w] = f2_to_bf2(h0.v[2 * w] + ly * (h1.v[2 * w] - h0.v[2 * w]), h0.v[2 * w + 1] + ly * (h1.v[2 * w + 1] - h0.v[2 * w + 1]));
+        *reinterpret_cast<uint4*>(obase + (size_t)y * Wo * ld_out) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // single-channel variant (the commuted segmentation heads): in [B,Hi,Wi] fp32 -> out [B,Ho,Wo] fp32
 __global__ void __launch_bounds__(256) upsample1_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int Hi,
                                                              int Wi, int Ho, int Wo) {
@@ -1100,7 +1150,10 @@ extern "C" int mdv_upsample_fwd(const void* in, int in_bf16, int ld_in, void* ou
     if ((C & 3) || (ld_in & 3) || (ld_out & 3)) return MDV_ERR_ARG;
     const int seg = Ho >= 64 ? 32 : Ho;
     const dim3 grid(mdv_cdiv(Wo * (C / 4), 256), mdv_cdiv(Ho, seg), B);
-    if (in_bf16 && out_bf16)
+    if (in_bf16 && out_bf16 && !(C & 7) && !(ld_in & 7) && !(ld_out & 7) && !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15))
+        mdv_launch(upsample_fwd_walk8_kernel, dim3(mdv_cdiv(Wo * (C / 8), 256), mdv_cdiv(Ho, seg), B), dim3(256), 0, st, (const bf16*)in, ld_in, (bf16*)out,
+                   ld_out, Hi, Wi, Ho, Wo, C, seg);
+    else if (in_bf16 && out_bf16)
         mdv_launch((upsample_fwd_walk_kernel<bf16, bf16>), grid, dim3(256), 0, st, (const bf16*)in, ld_in, (bf16*)out, ld_out, Hi, Wi, Ho, Wo, C, seg);
     else if (!in_bf16 && out_bf16)
         mdv_launch((upsample_fwd_walk_kernel<float, bf16>), grid, dim3(256), 0, st, (const float*)in, ld_in, (bf16*)out, ld_out, Hi, Wi, Ho, Wo, C, seg);

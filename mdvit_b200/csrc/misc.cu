@@ -80,6 +80,173 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
     }
 }
 
+// ---- vectorised versions (C a multiple of the 16-byte chunk, power-of-two chunks per row): the kernels above move 2-4 bytes per
+// load, re-hash the Dropout2d mask of every (row, channel), and the backward ran 64-thread blocks at C = 64 (5x their HBM time)
+template <typename TI> struct Chunk;
+template <> struct Chunk<float> { static constexpr int E = 4; };
+template <> struct Chunk<bf16> { static constexpr int E = 8; };
+template <typename TI>
+__device__ __forceinline__ void load_chunk(const TI* p, float (&v)[Chunk<TI>::E]) {
+    if constexpr (sizeof(TI) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const float2 a = bf2_to_f2(t.x), b = bf2_to_f2(t.y), c = bf2_to_f2(t.z), d = bf2_to_f2(t.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+}
+
+// forward: LPR = min(32, chunks per row) lanes share a row (32 / LPR rows per warp pass), a warp owns a contiguous band of rows and
+// keeps w * mask of its chunks in registers, re-evaluated only when the sample changes
+template <typename TI, int NCH>      // NCH = chunks per lane (chunks per row / LPR)
+__global__ void __launch_bounds__(256) rowdot_fwd_v_kernel(const TI* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out, int M, int C,
+                                                            int rows_per_sample, float drop_p, const unsigned long long* __restrict__ rng,
+                                                            uint32_t stream, int rows_per_warp) {
+    MDV_PDL_SYNC();
+    constexpr int E = Chunk<TI>::E;
+    const int cpr = C / E;
+    const int lpr = cpr < 32 ? cpr : 32, rpw = 32 / lpr;
+    const int lane = threadIdx.x & 31, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int cl = lane % lpr, rsub = lane / lpr;
+    uint32_t thr = 0, key = 0;
+    float inv = 1.f;
+    if (drop_p > 0.f) {
+        thr = drop_thresh(drop_p);
+        inv = 1.f / (1.f - drop_p);
+        key = rng_key(rng, stream);
+    }
+    const float b0 = bias ? bias[0] : 0.f;
+    float wm[NCH][E];
+    int cur_b = -1;
+    const int r0 = wid * rows_per_warp, r1 = min(M, r0 + rows_per_warp);
+    for (int r = r0 + rsub; r < r1 + rsub; r += rpw) {      // (all lanes of a row group iterate together: shuffles below)
+        const bool ok = r < r1;
+        const int rr = ok ? r : r1 - 1;
+        const int b = rr / rows_per_sample;
+        if (b != cur_b) {
+            cur_b = b;
+#pragma unroll
+            for (int n = 0; n < NCH; ++n)
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const int c = (cl + n * lpr) * E + j;
+                    wm[n][j] = __ldg(w + c) * (thr ? drop_scale(key, (unsigned long long)b * C + c, thr, inv) : 1.f);
+                }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int n = 0; n < NCH; ++n) {
+            float v[E];
+            load_chunk<TI>(x + (size_t)rr * C + (cl + n * lpr) * E, v);
+#pragma unroll
+            for (int j = 0; j < E; ++j) s = fmaf(v[j], wm[n][j], s);
+        }
+        for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (ok && cl == 0) out[r] = s + b0;
+    }
+}
+
+// backward: thread = one 16-byte chunk column, rows strided over the block's row lanes (4 in flight); dw partial sums in
+// registers, reduced over the row lanes in shared memory, one atomic per channel and block
+template <typename TI>
+__global__ void __launch_bounds__(256) rowdot_bwd_v_kernel(const float* __restrict__ dlog, const TI* __restrict__ x,
+                                                            const float* __restrict__ w, float* __restrict__ dx, float* __restrict__ dw,
+                                                            float* __restrict__ db, int M, int C, int rows_per_sample, float drop_p,
+                                                            const unsigned long long* __restrict__ rng, uint32_t stream, int rows_per_block) {
+    MDV_PDL_SYNC();
+    constexpr int E = Chunk<TI>::E;
+    __shared__ float sh[256 * 8];
+    const int tpr = C / E, rpi = 256 / tpr;
+    const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+    uint32_t thr = 0, key = 0;
+    float inv = 1.f;
+    if (drop_p > 0.f) {
+        thr = drop_thresh(drop_p);
+        inv = 1.f / (1.f - drop_p);
+        key = rng_key(rng, stream);
+    }
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float acc[E], wv[E], mk[E], dbacc = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        acc[j] = 0.f;
+        mk[j] = 1.f;
+        wv[j] = rl < rpi ? __ldg(w + cl * E + j) : 0.f;
+    }
+    if (rl < rpi) {
+        int cur_b = -1;
+        constexpr int U = 4;
+        for (int r = r0 + rl; r < r1; r += rpi * U) {
+            float v[U][E], d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + u * rpi;
+                d[u] = rr < r1 ? __ldg(dlog + rr) : 0.f;
+                if (dw && rr < r1) load_chunk<TI>(x + (size_t)rr * C + cl * E, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = r + u * rpi;
+                if (rr >= r1) break;
+                const int b = rr / rows_per_sample;
+                if (b != cur_b) {      // rows of one sample share the Dropout2d mask of (sample, channel): flush, then re-hash
+                    if (dw && cur_b >= 0) {
+#pragma unroll
+                        for (int j = 0; j < E; ++j) {
+                            atomicAdd(dw + cl * E + j, acc[j] * mk[j]);
+                            acc[j] = 0.f;
+                        }
+                    }
+                    cur_b = b;
+#pragma unroll
+                    for (int j = 0; j < E; ++j) mk[j] = thr ? drop_scale(key, (unsigned long long)b * C + cl * E + j, thr, inv) : 1.f;
+                }
+                if (cl == 0) dbacc += d[u];
+                if (dw) {
+#pragma unroll
+                    for (int j = 0; j < E; ++j) acc[j] = fmaf(d[u], v[u][j], acc[j]);
+                }
+                if (dx) {
+                    float* o = dx + (size_t)rr * C + cl * E;
+#pragma unroll
+                    for (int j = 0; j < E; j += 4)
+                        *reinterpret_cast<float4*>(o + j) = make_float4(d[u] * wv[j] * mk[j], d[u] * wv[j + 1] * mk[j + 1], d[u] * wv[j + 2] * mk[j + 2],
+                                                                        d[u] * wv[j + 3] * mk[j + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j) acc[j] *= mk[j];
+    }
+    // reduce the row lanes: sh[rl][cl][j]
+    if (dw) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) sh[threadIdx.x * E + j] = rl < rpi ? acc[j] : 0.f;
+        __syncthreads();
+        for (int e = threadIdx.x; e < tpr * E; e += 256) {
+            float t = 0.f;
+            for (int q = 0; q < rpi; ++q) t += sh[(q * tpr) * E + e];
+            atomicAdd(dw + e, t);
+        }
+    }
+    if (db) {
+        // (cl == 0 threads hold the dlog sums of their rows)
+        __syncthreads();
+        float* shb = sh;
+        if (threadIdx.x < 32) shb[threadIdx.x] = 0.f;
+        __syncthreads();
+        if (rl < rpi && cl == 0) atomicAdd(shb + (rl & 31), dbacc);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int q = 0; q < 32; ++q) t += shb[q];
+            atomicAdd(db, t);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- column sums (bias gradients)
 template <typename TI>
 __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ x, int ld, float* __restrict__ out, int M, int C,
@@ -466,6 +633,26 @@ extern "C" long long mdv_launch_count(void) { return g_mdv_launches; }
 extern "C" int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const float* bias, float* out, int M, int C,
                               int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
     if (!x || !w || !out || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
+    {   // vectorised path: 16-byte chunks, power-of-two chunks per row
+        const int E = x_bf16 ? 8 : 4;
+        const int cpr = C / E;
+        const bool pow2 = cpr > 0 && (cpr & (cpr - 1)) == 0;
+        if (!(C % E) && pow2 && cpr <= 128 && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+            const int nch = cpr <= 32 ? 1 : cpr / 32;
+            int rpw = mdv_cdiv(M, 8 * 8 * MDV_NUM_SMS);      // ~8 blocks of 8 warps per SM
+            const int rows_pass = cpr < 32 ? 32 / cpr : 1;
+            rpw = mdv_cdiv(rpw < 16 ? 16 : rpw, rows_pass) * rows_pass;
+            const int nb = mdv_cdiv(mdv_cdiv(M, rpw), 8);
+            cudaStream_t st = (cudaStream_t)stream;
+#define MDV_RDF(TI, N) mdv_launch((rowdot_fwd_v_kernel<TI, N>), dim3(nb), dim3(256), 0, st, (const TI*)x, w, bias, out, M, C, rows_per_sample, drop_p, \
+                                  (const unsigned long long*)rng, drop_stream, rpw)
+            if (x_bf16) { if (nch == 1) MDV_RDF(bf16, 1); else if (nch == 2) MDV_RDF(bf16, 2); else MDV_RDF(bf16, 4); }
+            else { if (nch == 1) MDV_RDF(float, 1); else if (nch == 2) MDV_RDF(float, 2); else MDV_RDF(float, 4); }
+#undef MDV_RDF
+            MDV_CHECK_LAUNCH();
+            return MDV_OK;
+        }
+    }
     const int blocks = mdv_cdiv(M, 8);
     if (x_bf16)
         mdv_launch(rowdot_fwd_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, w, bias, out, M, C, rows_per_sample, drop_p, (const unsigned long long*)rng, drop_stream);
@@ -478,6 +665,24 @@ extern "C" int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const f
 extern "C" int mdv_rowdot_bwd(const float* dlog, const void* x, int x_bf16, const float* w, float* dx, float* dw, float* db, int M,
                               int C, int rows_per_sample, float drop_p, const void* rng, uint32_t drop_stream, void* stream) {
     if (!dlog || !x || !w || M <= 0 || rows_per_sample <= 0) return MDV_ERR_ARG;
+    {
+        const int E = x_bf16 ? 8 : 4;
+        const int tpr = C / E;
+        if (!(C % E) && tpr >= 1 && tpr <= 256 && !(reinterpret_cast<uintptr_t>(x) & 15) && (!dx || !(reinterpret_cast<uintptr_t>(dx) & 15))) {
+            const int rpi = 256 / tpr;
+            int rpbv = mdv_cdiv(M, 8 * MDV_NUM_SMS);
+            if (rpbv < rpi * 16) rpbv = rpi * 16;
+            const int nb = mdv_cdiv(M, rpbv);
+            if (x_bf16)
+                mdv_launch(rowdot_bwd_v_kernel<bf16>, dim3(nb), dim3(256), 0, (cudaStream_t)stream, dlog, (const bf16*)x, w, dx, dw, db, M, C, rows_per_sample,
+                           drop_p, (const unsigned long long*)rng, drop_stream, rpbv);
+            else
+                mdv_launch(rowdot_bwd_v_kernel<float>, dim3(nb), dim3(256), 0, (cudaStream_t)stream, dlog, (const float*)x, w, dx, dw, db, M, C, rows_per_sample,
+                           drop_p, (const unsigned long long*)rng, drop_stream, rpbv);
+            MDV_CHECK_LAUNCH();
+            return MDV_OK;
+        }
+    }
     int rpb = mdv_cdiv(M, 4 * MDV_NUM_SMS);
     if (rpb < 8) rpb = 8;
     const int blocks = mdv_cdiv(M, rpb);
