@@ -208,6 +208,39 @@ int mdv_sdpa_fwd(const void* qkv_bf16, const float* gate, void* out_bf16, float*
 int mdv_sdpa_bwd(const void* qkv_bf16, const float* gate, const void* out_bf16, const float* lse, const void* dout_bf16,
                  void* dqkv_bf16, float* dgate, int B, int N, int C, int heads, float scale, void* stream);
 
+/* ------------------------------------------------------------------ TransFuse_S_adapt: CNN branch, fusion and decoder (Models/Hybrid_models/TransFuseFolder/TransFuse.py:182-283) */
+/* Generic k x k im2col of an fp32 NHWC tensor (in_nchw = 1: the NCHW input image, resnet.conv1 TransFuse.py:231):
+ *   col[(b,yo,xo), c*k*k + i*k + j] = in[b, yo*stride - pad + i, xo*stride - pad + j, c], zero outside the image and in the
+ * columns [C*k*k, ldc).  The column order is that of the flattened nn.Conv2d weight, so the GEMM's W operand is the parameter.
+ * Used for the 7x7 stride-2 stem, the 1x1 stride-2 downsample convs (torchvision resnet34) and BiFusion_block.spatial (7x7 on 2
+ * channels, TransFuse.py:38); the 3x3 convs use mdv_im2col3. */
+int mdv_im2col_k(const float* in, int in_nchw, void* col, int col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int k, int stride,
+                 int pad, int ldc, void* stream);
+/* its transpose (input gradient): dx NHWC fp32 [B,Hi,Wi,C], overwritten */
+int mdv_col2im_k(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int k, int stride, int pad, int ldc,
+                 void* stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) on NHWC fp32 (resnet.maxpool, TransFuse.py:234); tap_u8 [B,Ho,Wo,C] keeps which of the 9
+ * taps won (first maximum in scan order, where nn.MaxPool2d sends the gradient).  Ho = (Hi-1)/2 + 1.  C % 4 == 0. */
+int mdv_maxpool3s2_fwd(const float* in, float* out, void* tap_u8, int B, int Hi, int Wi, int C, void* stream);
+int mdv_maxpool3s2_bwd(const float* dout, const void* tap_u8, float* din, int B, int Hi, int Wi, int C, void* stream);
+/* out = act(a + b), act in {NONE, RELU}: `out += identity; relu(out)` of the ResNet BasicBlock, DoubleConv (TransFuse.py:589) and
+ * Attention_block (TransFuse.py:617).  n % 4 == 0. */
+int mdv_add_act(const float* a, const float* b, float* out, long long n, int act, void* stream);
+/* dx = dy * [y > 0] with y the ReLU's OUTPUT */
+int mdv_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream);
+/* bilinear resize with align_corners=True on NHWC fp32 (nn.Upsample in Up, TransFuse.py:559; the three output maps,
+ * TransFuse.py:262-264) and its exact transpose (gather form, deterministic) */
+int mdv_resize_ac_fwd(const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream);
+int mdv_resize_ac_bwd(const float* dout, float* din, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream);
+/* structure_loss (multi_train_TransFuse.py:29-38): weit = 1 + 5 |avg_pool2d(mask, 31, 1, 15) - mask| (ws: B*H*W floats);
+ * loss = mean_b( sum(weit*bce)/sum(weit) + 1 - (I+1)/(U-I+1) ), I = sum(sigmoid(pred)*mask*weit), U = sum((sigmoid(pred)+mask)*weit).
+ * sums: DEVICE double[4*B] (per sample: sum weit, sum weit*bce, I, U), written by _fwd, read by _bwd;
+ * dpred (=|+=) gout[0] * coef * dloss/dpred  (gout may be NULL = 1). */
+int mdv_structure_weit(const float* mask, float* weit, float* ws, int B, int H, int W, void* stream);
+int mdv_structure_loss_fwd(const float* pred, const float* mask, const float* weit, void* sums, float* loss, int B, int HW, void* stream);
+int mdv_structure_loss_bwd(const float* pred, const float* mask, const float* weit, const void* sums, const float* gout, float coef,
+                           float* dpred, int B, int HW, int accumulate, void* stream);
+
 /* ------------------------------------------------------------------ heads, reductions, casts */
 /* logits[m] = sum_c x[m,c] w[c] dropout2d(b,c) + bias  — the C->1 1x1 conv commuted in front of the final resize */
 int mdv_rowdot_fwd(const void* x, int x_bf16, const float* w, const float* bias, float* out, int M, int C, int rows_per_sample,

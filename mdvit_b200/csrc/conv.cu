@@ -31,11 +31,14 @@ __device__ __forceinline__ void fma4(float4& a, const float4& w, const float4& x
 // transposed: out[b,y,x,c]   = sum_ij w[c,i,j] * in[b, (y+1-i)/s, (x+1-j)/s, c]           (+ in[b,y,x,c] if residual)
 //             (input-gradient of the forward; `in` is then the output-gradient on the Ho x Wo grid)
 // Weights are staged in shared memory as [9][C].
-template <typename TO>
+// STRIDE = 1 / 2 at compile time (0: runtime `stride_rt`): the transposed form divides and takes remainders by the stride for
+// every tap — with a runtime stride the stride-2 input gradients of the patch embeddings were instruction bound at 6x their HBM time.
+template <typename TO, int STRIDE>
 __global__ void __launch_bounds__(256) dwconv3_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ bias, TO* __restrict__ out, int B, int Hi,
-                                                       int Wi, int Ho, int Wo, int C, int stride, int transposed, int residual) {
+                                                       int Wi, int Ho, int Wo, int C, int stride_rt, int transposed, int residual) {
     MDV_PDL_SYNC();
+    const int stride = STRIDE ? STRIDE : stride_rt;
     extern __shared__ float sw[];  // [9][C] then bias [C]
     for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[(i % 9) * C + i / 9] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) sw[9 * C + i] = bias ? bias[i] : 0.f;
@@ -1001,10 +1004,13 @@ extern "C" int mdv_dwconv3(const float* in, const float* w, const float* bias, v
         MDV_CHECK_LAUNCH();
         return MDV_OK;
     }
-    if (out_bf16)
-        mdv_launch(dwconv3_kernel<bf16>, dim3(grid_for(total)), dim3(256), smem, st, in, w, bias, (bf16*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
-    else
-        mdv_launch(dwconv3_kernel<float>, dim3(grid_for(total)), dim3(256), smem, st, in, w, bias, (float*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual);
+#define MDV_DW(TO_, S_) mdv_launch((dwconv3_kernel<TO_, S_>), dim3(grid_for(total)), dim3(256), smem, st, in, w, bias, (TO_*)out, B, Hi, Wi, Ho, Wo, C, stride, transposed, residual)
+    if (out_bf16) {
+        if (stride == 2) MDV_DW(bf16, 2); else if (stride == 1) MDV_DW(bf16, 1); else MDV_DW(bf16, 0);
+    } else {
+        if (stride == 2) MDV_DW(float, 2); else if (stride == 1) MDV_DW(float, 1); else MDV_DW(float, 0);
+    }
+#undef MDV_DW
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -1455,3 +1455,289 @@ def dice_jaccard(counts):
     dc = 2.0 * c[0] / (c[1] + c[2]) if (c[1] + c[2]) > 0 else 0.0
     jc = c[0] / (c[1] + c[2] - c[0]) if (c[1] + c[2] - c[0]) > 0 else 0.0
     return dc, jc
+
+
+# ------------------------------------------------------------------------------------------------- TransFuse_S_adapt: CNN side
+# Dense convolutions of the ResNet34 branch, BiFusion blocks, Up blocks and output heads
+# (Models/Hybrid_models/TransFuseFolder/TransFuse.py:182-283, 556-650; torchvision resnet34 BasicBlock) on NHWC fp32 maps
+# ([B, H*W, C]): im2col + TF32 tcgen05 GEMM forward, bf16 tcgen05 GEMMs for the input / weight gradients.
+def conv_geom(H, W, k, stride):
+    pad = (k - 1) // 2
+    return (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1, pad
+
+
+def _conv_cols(x, B, H, W, Cin, k, stride, nchw):
+    """fp32 A operand of the conv GEMM: (A [M, ld], ld, kind).  kind 'direct': the map itself (1x1, stride 1); 'k3': im2col in
+    (tap, channel) order (mdv_im2col3); 'gen': generic k x k im2col in the flattened-weight (channel, tap) order."""
+    Ho, Wo, pad = conv_geom(H, W, k, stride)
+    M, dev = B * Ho * Wo, x.device
+    lib = L.lib()
+    if k == 1 and stride == 1 and not nchw and Cin % 8 == 0:
+        return x.view(M, Cin), Cin, "direct"
+    if k == 3 and not nchw and Cin % 8 == 0:
+        col = torch.empty((M, 9 * Cin), dtype=F32, device=dev)
+        check(lib.mdv_im2col3(ptr(x), 0, ptr(col), 0, B, H, W, Ho, Wo, Cin, stride, 9 * Cin, L.stream()), "mdv_im2col3")
+        return col, 9 * Cin, "k3"
+    K = Cin * k * k
+    ld = (K + 7) // 8 * 8
+    col = torch.empty((M, ld), dtype=F32, device=dev)
+    check(lib.mdv_im2col_k(ptr(x), int(nchw), ptr(col), 0, B, H, W, Ho, Wo, Cin, k, stride, pad, ld, L.stream()), "mdv_im2col_k")
+    return col, ld, "gen"
+
+
+def _conv_weight_f32(w, kind, ld):
+    """fp32 W operand [Cout, ld] matching _conv_cols' column order."""
+    Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+    if kind == "k3":
+        return prep_weight(w, 2 | 8, Cout, 9 * Cin, cin=Cin)
+    K = Cin * k * k
+    if ld == K:
+        return _contig(w).view(Cout, K)
+    dst = torch.zeros((Cout, ld), dtype=F32, device=w.device)
+    with torch.no_grad():
+        check(L.lib().mdv_prep_weight(ptr(_contig(w)), ptr(dst), Cout, K, ld, 0 | 8, 0, L.stream()), "mdv_prep_weight")
+    return dst
+
+
+class ConvBnActFn(torch.autograd.Function):
+    """y = act( BN?( conv_kxk(x) + bias? ) + residual? ) on NHWC maps: nn.Conv2d (+ nn.BatchNorm2d) (+ `out += identity`) (+ ReLU)
+    of TransFuse.py's Conv / DoubleConv / Residual / Attention_block and of torchvision's BasicBlock.  k in {1,3,7}, stride in
+    {1,2}, padding (k-1)//2.  x: [B, H*W, Cin] fp32, or the NCHW image [B, Cin, H, W] (nchw=True, resnet.conv1).  Cout == 1
+    (the output heads and BiFusion_block.spatial) runs as a row dot product instead of a GEMM (no BN / residual there)."""
+
+    @staticmethod
+    def forward(ctx, x, w, cbias, gamma, beta, residual, bufs, B, H, W, stride, act, training, nchw):
+        if not x.is_cuda:
+            raise RuntimeError("mdvit_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        Ho, Wo, pad = conv_geom(H, W, k, stride)
+        M, dev = B * Ho * Wo, x.device
+        x = _contig(x)
+        has_bn = gamma is not None
+        lib = L.lib()
+        with _dev_ctx(x):
+            A, ld, kind = _conv_cols(x, B, H, W, Cin, k, stride, nchw)
+            Wf = _conv_weight_f32(w, kind, ld)
+            z = mean = rstd = None
+            if Cout == 1:
+                if has_bn or residual is not None or act != ACT_NONE:
+                    raise NotImplementedError("single-channel conv: no BN / residual / activation")
+                y = torch.empty(M, dtype=F32, device=dev)
+                check(lib.mdv_rowdot_fwd(ptr(A), 0, ptr(Wf), ptr(cbias), ptr(y), M, ld, Ho * Wo, ctypes.c_float(0.0), None, 0, L.stream()),
+                      "mdv_rowdot_fwd")
+            elif not has_bn:
+                if act != ACT_NONE and residual is not None:
+                    raise NotImplementedError("activation after a residual add needs BN in between")
+                res = _contig(residual).view(M, Cout) if residual is not None else None
+                y = gemm_nt(A, Wf, M, Cout, ld, torch.empty((M, Cout), dtype=F32, device=dev), bias=cbias, residual=res, act=act, tf32=True)
+            else:
+                rm, rv, nb = bufs
+                z = gemm_nt(A, Wf, M, Cout, ld, torch.empty((M, Cout), dtype=F32, device=dev), bias=cbias, tf32=True)
+                if residual is None:
+                    y, mean, rstd = bn_forward(z, M, Cout, gamma, beta, rm, rv, nb, training, act, False)
+                else:
+                    t, mean, rstd = bn_forward(z, M, Cout, gamma, beta, rm, rv, nb, training, ACT_NONE, False)
+                    y = torch.empty((M, Cout), dtype=F32, device=dev)
+                    check(lib.mdv_add_act(ptr(t), ptr(_contig(residual)), ptr(y), M * Cout, act, L.stream()), "mdv_add_act")
+        need_y = act == ACT_RELU and (residual is not None or not has_bn)
+        ctx.save_for_backward(A, z, mean, rstd, y if need_y else None)
+        ctx.params = (w, cbias, gamma, beta)
+        ctx.meta = (B, H, W, Ho, Wo, Cin, Cout, k, stride, pad, ld, kind, act, training, residual is not None, has_bn)
+        _fwd_mark(ctx)
+        return y.view(B, Ho * Wo, Cout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, Ho, Wo, Cin, Cout, k, stride, pad, ld, kind, act, training, has_res, has_bn = ctx.meta
+        if has_bn and not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        A, z, mean, rstd, y = ctx.saved_tensors
+        w, cbias, gamma, beta = ctx.params
+        M, dev = B * Ho * Wo, dy.device
+        K = Cin * k * k
+        lib = L.lib()
+        dy = _contig(dy.float())
+        rg = rb = dres = dx = None
+        need_dx = ctx.needs_input_grad[0]
+        with _dev_ctx(dy):
+            if Cout == 1:
+                gwv = torch.zeros(ld, dtype=F32, device=dev)
+                gb, rcb = gtarget(cbias)
+                dcol = torch.empty((M, ld), dtype=F32, device=dev) if need_dx else None
+                Wf = _conv_weight_f32(w, kind, ld)
+                check(lib.mdv_rowdot_bwd(ptr(dy), ptr(A), 0, ptr(Wf), ptr(dcol), ptr(gwv), ptr(gb), M, ld, Ho * Wo, ctypes.c_float(0.0), None, 0,
+                                         L.stream()), "mdv_rowdot_bwd")
+                gw, rw = gtarget(w)
+                if gw is not None:
+                    if kind == "k3":
+                        check(lib.mdv_unperm_conv_grad(ptr(gwv), ld, ptr(gw), 1, Cin, L.stream()), "mdv_unperm_conv_grad")
+                    else:
+                        check(lib.mdv_add_f32(ptr(gwv), 0, ld, ptr(gw), K, 1, K, 1, L.stream()), "mdv_add_f32")
+            else:
+                g = dy.view(M, Cout)
+                if y is not None:      # ReLU whose input is not the BatchNorm output alone: mask from the saved output
+                    g = torch.empty((M, Cout), dtype=F32, device=dev)
+                    check(lib.mdv_relu_bwd(ptr(dy), ptr(y), ptr(g), M * Cout, L.stream()), "mdv_relu_bwd")
+                if has_res:
+                    dres = g.view(B, Ho * Wo, Cout)
+                if has_bn:
+                    dz, rg, rb = bn_backward(g, z, mean, rstd, gamma, beta, ACT_NONE if has_res else act, M, Cout)
+                else:
+                    dz = cast_bf16(g, M, Cout)
+                gb, rcb = gtarget(cbias)
+                colsum(dz, M, Cout, gb)
+                gw, rw = gtarget(w)
+                if gw is not None:
+                    Ab = cast_bf16(A, M, ld)
+                    if kind == "k3":
+                        gwp = gemm_tn(dz, Ab, M, Cout, ld, torch.zeros((Cout, ld), dtype=F32, device=dev))
+                        check(lib.mdv_unperm_conv_grad(ptr(gwp), ld, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
+                    elif ld == K:
+                        gemm_tn(dz, Ab, M, Cout, K, gw.view(Cout, K))
+                    else:
+                        gwp = gemm_tn(dz, Ab, M, Cout, ld, torch.zeros((Cout, ld), dtype=F32, device=dev))
+                        check(lib.mdv_add_f32(ptr(gwp), 0, ld, ptr(gw), K, Cout, K, 1, L.stream()), "mdv_add_f32")
+                dcol = None
+                if need_dx:
+                    if kind == "direct":
+                        dx = gemm_nt(dz, prep_weight(w, 1, Cout, Cin), M, Cin, Cout, torch.empty((M, Cin), dtype=F32, device=dev))
+                    elif kind == "k3":
+                        dcol = gemm_nt(dz, prep_weight(w, 3, Cout, 9 * Cin, cin=Cin), M, 9 * Cin, Cout, torch.empty((M, ld), dtype=F32, device=dev))
+                    else:
+                        if K != ld:
+                            raise NotImplementedError("input gradient of a generic conv needs Cin*k*k % 8 == 0")
+                        dcol = gemm_nt(dz, prep_weight(w, 1, Cout, K), M, K, Cout, torch.empty((M, ld), dtype=F32, device=dev))
+            if need_dx and dx is None and kind == "direct":
+                dx = dcol
+            elif need_dx and dx is None:
+                dx = torch.empty((B * H * W, Cin), dtype=F32, device=dev)
+                if kind == "k3":
+                    check(lib.mdv_col2im3(ptr(dcol), ptr(dx), B, H, W, Ho, Wo, Cin, stride, ld, L.stream()), "mdv_col2im3")
+                else:
+                    check(lib.mdv_col2im_k(ptr(dcol), ptr(dx), B, H, W, Ho, Wo, Cin, k, stride, pad, ld, L.stream()), "mdv_col2im_k")
+        _grads_done(ctx)
+        return (dx.view(B, H * W, Cin) if dx is not None else None, rw, rcb, rg, rb, dres, None, None, None, None, None, None, None, None)
+
+
+class BnActFn(torch.autograd.Function):
+    """y = act(BatchNorm2d(x)) on an NHWC map (the pre-activation BatchNorms of TransFuse.py's Residual block, :626-640)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bufs, act, training):
+        B, N, C = x.shape
+        x = _contig(x)
+        rm, rv, nb = bufs
+        with _dev_ctx(x):
+            y, mean, rstd = bn_forward(x.view(B * N, C), B * N, C, gamma, beta, rm, rv, nb, training, act, False)
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.params = (gamma, beta)
+        ctx.meta = (B, N, C, act, training)
+        _fwd_mark(ctx)
+        return y.view(B, N, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, N, C, act, training = ctx.meta
+        if not training:
+            raise RuntimeError("mdvit_b200: backward through eval-mode BatchNorm is not supported")
+        x, mean, rstd = ctx.saved_tensors
+        gamma, beta = ctx.params
+        dy = _contig(dy.float())
+        with _dev_ctx(dy):
+            dx, rg, rb = bn_backward(dy, x, mean, rstd, gamma, beta, act, B * N, C, dz_bf16=False)
+        _grads_done(ctx)
+        return dx.view(B, N, C), rg, rb, None, None, None
+
+
+class MaxPool3s2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of torchvision's resnet34 (TransFuse.py:234) on an NHWC map."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        B, _, C = x.shape
+        x = _contig(x)
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = torch.empty((B, Ho * Wo, C), dtype=F32, device=x.device)
+        tap = torch.empty((B, Ho * Wo, C), dtype=torch.uint8, device=x.device)
+        with _dev_ctx(x):
+            check(L.lib().mdv_maxpool3s2_fwd(ptr(x), ptr(out), ptr(tap), B, H, W, C, L.stream()), "mdv_maxpool3s2_fwd")
+        ctx.save_for_backward(tap)
+        ctx.meta = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (tap,) = ctx.saved_tensors
+        B, H, W, C = ctx.meta
+        dout = _contig(dout.float())
+        din = torch.empty((B, H * W, C), dtype=F32, device=dout.device)
+        with _dev_ctx(dout):
+            check(L.lib().mdv_maxpool3s2_bwd(ptr(dout), ptr(tap), ptr(din), B, H, W, C, L.stream()), "mdv_maxpool3s2_bwd")
+        return din, None, None
+
+
+class ResizeACFn(torch.autograd.Function):
+    """Bilinear resize with align_corners=True on an NHWC map (nn.Upsample in Up, TransFuse.py:559; F.interpolate of the three
+    output maps, TransFuse.py:262-264)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, Ho, Wo):
+        B, _, C = x.shape
+        x = _contig(x)
+        out = torch.empty((B, Ho * Wo, C), dtype=F32, device=x.device)
+        with _dev_ctx(x):
+            check(L.lib().mdv_resize_ac_fwd(ptr(x), ptr(out), B, H, W, Ho, Wo, C, L.stream()), "mdv_resize_ac_fwd")
+        ctx.meta = (B, H, W, Ho, Wo, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, Ho, Wo, C = ctx.meta
+        dout = _contig(dout.float())
+        din = torch.empty((B, H * W, C), dtype=F32, device=dout.device)
+        with _dev_ctx(dout):
+            check(L.lib().mdv_resize_ac_bwd(ptr(dout), ptr(din), B, H, W, Ho, Wo, C, L.stream()), "mdv_resize_ac_bwd")
+        return din, None, None, None, None
+
+
+def structure_weit(mask):
+    """weit = 1 + 5 |avg_pool2d(mask, 31, stride 1, padding 15) - mask| (multi_train_TransFuse.py:30); mask [B,1,H,W] fp32."""
+    B, _, H, W = mask.shape
+    mask = _contig(mask.float())
+    weit, ws = torch.empty_like(mask), torch.empty_like(mask)
+    with _dev_ctx(mask):
+        check(L.lib().mdv_structure_weit(ptr(mask), ptr(weit), ptr(ws), B, H, W, L.stream()), "mdv_structure_weit")
+    return weit
+
+
+class StructureLossFn(torch.autograd.Function):
+    """structure_loss(pred, mask) of multi_train_TransFuse.py:29-38 (weighted BCE + weighted IoU, mean over the batch)."""
+
+    @staticmethod
+    def forward(ctx, pred, mask, weit):
+        B, HW = pred.shape[0], pred[0].numel()
+        pred, mask = _contig(pred), _contig(mask.float())
+        sums = torch.empty(4 * B, dtype=torch.float64, device=pred.device)
+        loss = torch.empty(1, dtype=F32, device=pred.device)
+        with _dev_ctx(pred):
+            check(L.lib().mdv_structure_loss_fwd(ptr(pred), ptr(mask), ptr(weit), ptr(sums), ptr(loss), B, HW, L.stream()), "mdv_structure_loss_fwd")
+        ctx.save_for_backward(pred, mask, weit, sums)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, mask, weit, sums = ctx.saved_tensors
+        B, HW = pred.shape[0], pred[0].numel()
+        g = _contig(g.float()).view(1)
+        dpred = torch.empty_like(pred)
+        with _dev_ctx(pred):
+            check(L.lib().mdv_structure_loss_bwd(ptr(pred), ptr(mask), ptr(weit), ptr(sums), ptr(g), ctypes.c_float(1.0), ptr(dpred), B, HW, 0,
+                                                 L.stream()), "mdv_structure_loss_bwd")
+        return dpred, None, None
+
+
+def structure_loss(pred, mask, weit=None):
+    """Drop-in for multi_train_TransFuse.py:29-38; pass `weit` (structure_weit(mask)) to share it between the three maps."""
+    if weit is None:
+        weit = structure_weit(mask)
+    return StructureLossFn.apply(pred, mask, weit)

@@ -181,3 +181,343 @@ def deit_small_patch16_224_adapt(pretrained=False, pretrained_folder=None, num_d
     model.pos_embed = nn.Parameter(pe.flatten(2).transpose(-1, -2))
     model.head = nn.Identity()
     return model
+
+
+# ================================================================================================ TransFuse_S_adapt
+# Models/Hybrid_models/TransFuseFolder/TransFuse.py:20-78 (ChannelPool, BiFusion_block), :182-283 (TransFuse_S_adapt), :533-650
+# (init_weights, Up, Attention_block, DoubleConv, Residual, Conv).  Same class names, constructor signatures, registration
+# order (=> the same state_dict keys and, under one seed, the same initial weights) and forward signatures.  Inside, maps are
+# NHWC fp32 ([B, H*W, C]); every convolution / BatchNorm / pooling / resize is a C-ABI kernel (ops.ConvBnActFn, ops.BnActFn,
+# ops.MaxPool3s2Fn, ops.ResizeACFn); the per-pixel / per-sample gates of BiFusion_block and Attention_block (sigmoid gates,
+# channel max / mean, the squeeze-and-excitation Linears on [B, C], the two single-channel BatchNorms) are torch tensor
+# expressions on those maps.  Each block's `forward` keeps the reference's NCHW signature; `run` is the NHWC form the model
+# chains internally.
+import torch.nn.functional as F
+
+ACT_NONE, ACT_RELU = ops.ACT_NONE, ops.ACT_RELU
+
+
+def _to_nhwc(x):
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B, H * W, C), H, W
+
+
+def _to_nchw(x, H, W):
+    B, _, C = x.shape
+    return x.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def _bn_bufs(bn):
+    return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
+
+
+def _cba(x, H, W, conv, bn=None, act=ACT_NONE, residual=None, nchw=False):
+    """act(BN?(conv(x)) + residual?) -> (y [B, Ho*Wo, Cout], Ho, Wo)"""
+    k, s = conv.kernel_size[0], conv.stride[0]
+    if conv.kernel_size[0] != conv.kernel_size[1] or conv.padding[0] != (k - 1) // 2 or conv.groups != 1 or conv.dilation[0] != 1:
+        raise NotImplementedError("mdvit_b200: square dense convolutions with 'same' padding only")
+    B = x.shape[0]
+    training = bn.training if bn is not None else False
+    y = ops.ConvBnActFn.apply(x, conv.weight, conv.bias, bn.weight if bn is not None else None, bn.bias if bn is not None else None,
+                              residual, _bn_bufs(bn) if bn is not None else None, B, H, W, s, act, training, nchw)
+    Ho, Wo, _ = ops.conv_geom(H, W, k, s)
+    return y, Ho, Wo
+
+
+def _bn1(z, bn, H, W):
+    """BatchNorm2d(1) on a single-channel NHWC map [B, H*W, 1]"""
+    B = z.shape[0]
+    return F.batch_norm(z.view(B, 1, H, W), bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps).view(B, H * W, 1)
+
+
+def _drop2d(x, p, training):
+    """nn.Dropout2d on an NHWC map: whole (sample, channel) planes"""
+    if p <= 0. or not training:
+        return x
+    B, _, C = x.shape
+    keep = (torch.rand((B, 1, C), device=x.device) >= p).to(x.dtype) / (1. - p)
+    return x * keep
+
+
+class ChannelPool(nn.Module):
+    def run(self, x):
+        return torch.cat((x.max(dim=2, keepdim=True)[0], x.mean(dim=2, keepdim=True)), dim=2)
+
+    def forward(self, x):
+        return torch.cat((torch.max(x, 1)[0].unsqueeze(1), torch.mean(x, 1).unsqueeze(1)), dim=1)
+
+
+class Conv(nn.Module):
+    def __init__(self, inp_dim, out_dim, kernel_size=3, stride=1, bn=False, relu=True, bias=True):
+        super().__init__()
+        self.inp_dim = inp_dim
+        self.conv = nn.Conv2d(inp_dim, out_dim, kernel_size, stride, padding=(kernel_size - 1) // 2, bias=bias)
+        self.relu = None
+        self.bn = None
+        if relu:
+            self.relu = nn.ReLU(inplace=True)
+        if bn:
+            self.bn = nn.BatchNorm2d(out_dim)
+
+    def run(self, x, H, W, residual=None):
+        assert x.shape[2] == self.inp_dim, "{} {}".format(x.shape[2], self.inp_dim)
+        act = ACT_RELU if self.relu is not None else ACT_NONE
+        if self.conv.out_channels == 1:      # single-channel output: row-dot kernel, BatchNorm2d(1) / ReLU as tensor expressions
+            y, Ho, Wo = _cba(x, H, W, self.conv)
+            if self.bn is not None:
+                y = _bn1(y, self.bn, Ho, Wo)
+            return (torch.relu(y) if self.relu is not None else y), Ho, Wo
+        return _cba(x, H, W, self.conv, self.bn, act, residual)
+
+    def forward(self, x):
+        t, H, W = _to_nhwc(x)
+        y, Ho, Wo = self.run(t, H, W)
+        return _to_nchw(y, Ho, Wo)
+
+
+class Residual(nn.Module):
+    def __init__(self, inp_dim, out_dim):
+        super().__init__()
+        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = nn.BatchNorm2d(inp_dim)
+        self.conv1 = Conv(inp_dim, int(out_dim / 2), 1, relu=False)
+        self.bn2 = nn.BatchNorm2d(int(out_dim / 2))
+        self.conv2 = Conv(int(out_dim / 2), int(out_dim / 2), 3, relu=False)
+        self.bn3 = nn.BatchNorm2d(int(out_dim / 2))
+        self.conv3 = Conv(int(out_dim / 2), out_dim, 1, relu=False)
+        self.skip_layer = Conv(inp_dim, out_dim, 1, relu=False)
+        self.need_skip = inp_dim != out_dim
+
+    def run(self, x, H, W):
+        residual = self.skip_layer.run(x, H, W)[0] if self.need_skip else x
+        out = ops.BnActFn.apply(x, self.bn1.weight, self.bn1.bias, _bn_bufs(self.bn1), ACT_RELU, self.bn1.training)
+        out, _, _ = _cba(out, H, W, self.conv1.conv, self.bn2, ACT_RELU)      # conv1 -> bn2 -> relu
+        out, _, _ = _cba(out, H, W, self.conv2.conv, self.bn3, ACT_RELU)      # conv2 -> bn3 -> relu
+        out, _, _ = _cba(out, H, W, self.conv3.conv, None, ACT_NONE, residual)      # conv3, out += residual
+        return out
+
+    def forward(self, x):
+        t, H, W = _to_nhwc(x)
+        return _to_nchw(self.run(t, H, W), H, W)
+
+
+class DoubleConv(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1),
+            nn.BatchNorm2d(out_channels)
+        )
+        self.identity = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0),
+            nn.BatchNorm2d(out_channels)
+        )
+        self.relu = nn.ReLU(inplace=True)
+
+    def run(self, x, H, W):
+        dc, idt = self.double_conv, self.identity
+        i, _, _ = _cba(x, H, W, idt[0], idt[1], ACT_NONE)
+        y, _, _ = _cba(x, H, W, dc[0], dc[1], ACT_RELU)
+        y, _, _ = _cba(y, H, W, dc[3], dc[4], ACT_RELU, i)      # relu(double_conv(x) + identity(x))
+        return y
+
+    def forward(self, x):
+        t, H, W = _to_nhwc(x)
+        return _to_nchw(self.run(t, H, W), H, W)
+
+
+class Attention_block(nn.Module):
+    def __init__(self, F_g, F_l, F_int):
+        super().__init__()
+        self.W_g = nn.Sequential(nn.Conv2d(F_g, F_int, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(F_int))
+        self.W_x = nn.Sequential(nn.Conv2d(F_l, F_int, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(F_int))
+        self.psi = nn.Sequential(nn.Conv2d(F_int, 1, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(1), nn.Sigmoid())
+        self.relu = nn.ReLU(inplace=True)
+
+    def run(self, g, x, H, W):
+        g1, _, _ = _cba(g, H, W, self.W_g[0], self.W_g[1], ACT_NONE)
+        s, _, _ = _cba(x, H, W, self.W_x[0], self.W_x[1], ACT_RELU, g1)      # relu(g1 + x1)
+        p, _, _ = _cba(s, H, W, self.psi[0])
+        p = torch.sigmoid(_bn1(p, self.psi[1], H, W))
+        return x * p
+
+    def forward(self, g, x):
+        gt, H, W = _to_nhwc(g)
+        xt, _, _ = _to_nhwc(x)
+        return _to_nchw(self.run(gt, xt, H, W), H, W)
+
+
+class Up(nn.Module):
+    """Upscaling then double conv"""
+
+    def __init__(self, in_ch1, out_ch, in_ch2=0, attn=False):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+        self.conv = DoubleConv(in_ch1 + in_ch2, out_ch)
+        self.attn_block = Attention_block(in_ch1, in_ch2, out_ch) if attn else None
+
+    def run(self, x1, H, W, x2=None):
+        """x1 at H x W is upsampled to 2H x 2W, where x2 (if given) lives; returns the map at 2H x 2W"""
+        Ho, Wo = 2 * H, 2 * W
+        x1 = ops.ResizeACFn.apply(x1, H, W, Ho, Wo)
+        if x2 is not None:
+            if x2.shape[1] != Ho * Wo:
+                raise NotImplementedError("mdvit_b200: Up expects the skip map at exactly twice the resolution")
+            if self.attn_block is not None:
+                x2 = self.attn_block.run(x1, x2, Ho, Wo)
+            x1 = torch.cat([x2, x1], dim=2)
+        return self.conv.run(x1, Ho, Wo)
+
+    def forward(self, x1, x2=None):
+        t1, H, W = _to_nhwc(x1)
+        t2 = _to_nhwc(x2)[0] if x2 is not None else None
+        return _to_nchw(self.run(t1, H, W, t2), 2 * H, 2 * W)
+
+
+class BiFusion_block(nn.Module):
+    def __init__(self, ch_1, ch_2, r_2, ch_int, ch_out, drop_rate=0.):
+        super().__init__()
+        # channel attention for F_g, use SE Block
+        self.fc1 = nn.Conv2d(ch_2, ch_2 // r_2, kernel_size=1)
+        self.relu = nn.ReLU(inplace=True)
+        self.fc2 = nn.Conv2d(ch_2 // r_2, ch_2, kernel_size=1)
+        self.sigmoid = nn.Sigmoid()
+        # spatial attention for F_l
+        self.compress = ChannelPool()
+        self.spatial = Conv(2, 1, 7, bn=True, relu=False, bias=False)
+        # bi-linear modelling for both
+        self.W_g = Conv(ch_1, ch_int, 1, bn=True, relu=False)
+        self.W_x = Conv(ch_2, ch_int, 1, bn=True, relu=False)
+        self.W = Conv(ch_int, ch_int, 3, bn=True, relu=True)
+        self.relu = nn.ReLU(inplace=True)
+        self.residual = Residual(ch_1 + ch_2 + ch_int, ch_out)
+        self.dropout = nn.Dropout2d(drop_rate)
+        self.drop_rate = drop_rate
+
+    def run(self, g, x, H, W):
+        # bilinear pooling
+        W_g, _, _ = self.W_g.run(g, H, W)
+        W_x, _, _ = self.W_x.run(x, H, W)
+        bp, _, _ = self.W.run(W_g * W_x, H, W)
+        # spatial attention for cnn branch
+        s, _, _ = self.spatial.run(self.compress.run(g), H, W)
+        g = torch.sigmoid(s) * g
+        # channel attention for transformer branch (the 1x1 convs act on the [B, C] pooled vector)
+        v = x.mean(dim=1)
+        v = torch.relu(F.linear(v, self.fc1.weight.flatten(1), self.fc1.bias))
+        v = torch.sigmoid(F.linear(v, self.fc2.weight.flatten(1), self.fc2.bias))
+        x = v.unsqueeze(1) * x
+        fuse = self.residual.run(torch.cat([g, x, bp], dim=2), H, W)
+        return _drop2d(fuse, self.drop_rate, self.training)
+
+    def forward(self, g, x):
+        gt, H, W = _to_nhwc(g)
+        xt, _, _ = _to_nhwc(x)
+        return _to_nchw(self.run(gt, xt, H, W), H, W)
+
+
+def init_weights(m):
+    """TransFuse.py:533-553"""
+    if isinstance(m, nn.Conv2d):
+        nn.init.kaiming_normal_(m.weight, mode='fan_in', nonlinearity='relu')
+        if m.bias is not None:
+            fan_in, _ = nn.init._calculate_fan_in_and_fan_out(m.weight)
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(m.bias, -bound, bound)
+    elif isinstance(m, nn.BatchNorm2d):
+        nn.init.constant_(m.weight, 1)
+        nn.init.constant_(m.bias, 0)
+
+
+class TransFuse_S_adapt(nn.Module):
+    """TransFuse.py:182-283: ResNet34 (layers 1-3) || DeiT-S-adapt, fused by BiFusion blocks and attention-gated Up blocks; returns
+    the three logit maps (map_x, map_1, map_2), each [B, num_classes, H, W].  256 x 256 inputs (16 x 16 tokens)."""
+
+    def __init__(self, num_classes=1, drop_rate=0.2, normal_init=True, pretrained=False,
+                 pretrained_folder='/bigdata/siyiplace/data/skin_lesion', num_domains=4):
+        super().__init__()
+        from torchvision.models import resnet34      # parameter container only (same keys / init as the reference); forward is ours
+        if num_classes != 1:
+            raise NotImplementedError("mdvit_b200 implements the binary-segmentation heads (num_classes=1)")
+        self.resnet = resnet34()
+        if pretrained:
+            self.resnet.load_state_dict(torch.load(pretrained_folder + '/pretrained/resnet34-333f7ec4.pth'))
+        self.resnet.fc = nn.Identity()
+        self.resnet.layer4 = nn.Identity()
+        self.transformer = deit_small_patch16_224_adapt(pretrained=False, pretrained_folder=pretrained_folder, num_domains=num_domains)
+        if pretrained:
+            raise NotImplementedError("load the DeiT checkpoint with load_state_dict() (see deit_small_patch16_224_adapt)")
+        self.up1 = Up(in_ch1=384, out_ch=128)
+        self.up2 = Up(128, 64)
+        self.final_x = nn.Sequential(Conv(256, 64, 1, bn=True, relu=True), Conv(64, 64, 3, bn=True, relu=True),
+                                     Conv(64, num_classes, 3, bn=False, relu=False))
+        self.final_1 = nn.Sequential(Conv(64, 64, 3, bn=True, relu=True), Conv(64, num_classes, 3, bn=False, relu=False))
+        self.final_2 = nn.Sequential(Conv(64, 64, 3, bn=True, relu=True), Conv(64, num_classes, 3, bn=False, relu=False))
+        self.up_c = BiFusion_block(ch_1=256, ch_2=384, r_2=4, ch_int=256, ch_out=256, drop_rate=drop_rate / 2)
+        self.up_c_1_1 = BiFusion_block(ch_1=128, ch_2=128, r_2=2, ch_int=128, ch_out=128, drop_rate=drop_rate / 2)
+        self.up_c_1_2 = Up(in_ch1=256, out_ch=128, in_ch2=128, attn=True)
+        self.up_c_2_1 = BiFusion_block(ch_1=64, ch_2=64, r_2=1, ch_int=64, ch_out=64, drop_rate=drop_rate / 2)
+        self.up_c_2_2 = Up(128, 64, 64, attn=True)
+        self.drop = nn.Dropout2d(drop_rate)
+        if normal_init:
+            self.init_weights()
+
+    def _basic_block(self, blk, x, H, W):
+        """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + downsample(x))"""
+        y, Ho, Wo = _cba(x, H, W, blk.conv1, blk.bn1, ACT_RELU)
+        idt = x if blk.downsample is None else _cba(x, H, W, blk.downsample[0], blk.downsample[1], ACT_NONE)[0]
+        y, _, _ = _cba(y, Ho, Wo, blk.conv2, blk.bn2, ACT_RELU, idt)
+        return y, Ho, Wo
+
+    def _layer(self, layer, x, H, W):
+        for blk in layer:
+            x, H, W = self._basic_block(blk, x, H, W)
+        return x, H, W
+
+    @staticmethod
+    def _head(seq, x, H, W, Ho, Wo):
+        for m in seq:
+            x, H, W = m.run(x, H, W)
+        B = x.shape[0]
+        return ops.ResizeACFn.apply(x, H, W, Ho, Wo).view(B, 1, Ho, Wo)      # one channel: NHWC == NCHW
+
+    def forward(self, imgs, domain_label, labels=None):
+        B, _, Hi, Wi = imgs.shape
+        if Hi % 16 or Wi % 16:
+            raise ValueError("image sides must be multiples of 16")
+        p, tr = self.drop.p, self.training
+        r = self.resnet
+        # bottom-up path: the DeiT tokens [B, (H/16)(W/16), 384] are already the NHWC map the reference builds by transpose + view
+        h, w = Hi // 16, Wi // 16
+        x_b = _drop2d(self.transformer(imgs, domain_label), p, tr)
+        x_b_1 = _drop2d(self.up1.run(x_b, h, w), p, tr)
+        x_b_2 = _drop2d(self.up2.run(x_b_1, 2 * h, 2 * w), p, tr)      # transformer pred supervise here
+        # top-down path
+        x_u, H, W = _cba(imgs.float(), Hi, Wi, r.conv1, r.bn1, ACT_RELU, nchw=True)
+        x_u = ops.MaxPool3s2Fn.apply(x_u, H, W)
+        H, W = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        x_u_2, H2, W2 = self._layer(r.layer1, x_u, H, W)
+        x_u_2 = _drop2d(x_u_2, p, tr)
+        x_u_1, H1, W1 = self._layer(r.layer2, x_u_2, H2, W2)
+        x_u_1 = _drop2d(x_u_1, p, tr)
+        x_u, H0, W0 = self._layer(r.layer3, x_u_1, H1, W1)
+        x_u = _drop2d(x_u, p, tr)
+        # joint path
+        x_c = self.up_c.run(x_u, x_b, H0, W0)
+        x_c_1_1 = self.up_c_1_1.run(x_u_1, x_b_1, H1, W1)
+        x_c_1 = self.up_c_1_2.run(x_c, H0, W0, x_c_1_1)
+        x_c_2_1 = self.up_c_2_1.run(x_u_2, x_b_2, H2, W2)
+        x_c_2 = self.up_c_2_2.run(x_c_1, H1, W1, x_c_2_1)      # joint predict low supervise here
+        # decoder part
+        map_x = self._head(self.final_x, x_c, H0, W0, Hi, Wi)
+        map_1 = self._head(self.final_1, x_b_2, H2, W2, Hi, Wi)
+        map_2 = self._head(self.final_2, x_c_2, H2, W2, Hi, Wi)
+        return map_x, map_1, map_2
+
+    def init_weights(self):
+        for m in (self.up1, self.up2, self.final_x, self.final_1, self.final_2, self.up_c, self.up_c_1_1, self.up_c_1_2, self.up_c_2_1,
+                  self.up_c_2_2):
+            m.apply(init_weights)

@@ -1,0 +1,119 @@
+"""CPU test of TransFuse_S_adapt's HOST logic (module wiring, NHWC plumbing, gates, registration order / init) against goldens of
+the unmodified reference (oracle/make_golden_transfuse_model.py): the C-ABI Functions are replaced by torch expressions of what
+each kernel computes, so everything except the kernels themselves is checked here without a GPU.  The kernels are checked by
+tests/test_transfuse_model_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mdvit_b200 import ops, transfuse as T
+from oracle.make_golden_transfuse_model import case, structure_loss_ref
+from tests.helpers import fingerprint
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "transfuse_model_golden.npz")
+
+
+class _EmuConv:
+    @staticmethod
+    def apply(x, w, cbias, gamma, beta, residual, bufs, B, H, W, stride, act, training, nchw):
+        k = w.shape[2]
+        xin = x if nchw else x.view(B, H, W, -1).permute(0, 3, 1, 2)
+        z = F.conv2d(xin, w, cbias, stride, (k - 1) // 2)
+        if gamma is not None:
+            z = F.batch_norm(z, bufs[0], bufs[1], gamma, beta, training, 0.1, 1e-5)
+            if training:
+                bufs[2].add_(1)
+        y = z.permute(0, 2, 3, 1).reshape(B, -1, w.shape[0])
+        if gamma is None and act == ops.ACT_RELU:
+            y = torch.relu(y)
+        if residual is not None:
+            y = y + residual
+        if gamma is not None and act == ops.ACT_RELU:
+            y = torch.relu(y)
+        return y
+
+
+class _EmuBn:
+    @staticmethod
+    def apply(x, gamma, beta, bufs, act, training):
+        y = F.batch_norm(x.transpose(1, 2), bufs[0], bufs[1], gamma, beta, training, 0.1, 1e-5).transpose(1, 2)
+        return torch.relu(y) if act == ops.ACT_RELU else y
+
+
+class _EmuPool:
+    @staticmethod
+    def apply(x, H, W):
+        B, _, C = x.shape
+        y = F.max_pool2d(x.view(B, H, W, C).permute(0, 3, 1, 2), 3, 2, 1)
+        return y.permute(0, 2, 3, 1).reshape(B, -1, C)
+
+
+class _EmuResize:
+    @staticmethod
+    def apply(x, H, W, Ho, Wo):
+        B, _, C = x.shape
+        y = F.interpolate(x.view(B, H, W, C).permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True)
+        return y.permute(0, 2, 3, 1).reshape(B, -1, C)
+
+
+def deit_forward_torch(tr, imgs, label):
+    """plain-torch DeiT-S-adapt forward over the module's parameters (vision_transformer.py:125-211,322-389; DeiT.py:116-139)"""
+    x = F.conv2d(imgs, tr.patch_embed.proj.weight, tr.patch_embed.proj.bias, stride=16).flatten(2).transpose(1, 2) + tr.pos_embed
+    for blk in tr.blocks:
+        a = blk.attn
+        B, N, C = x.shape
+        h = F.layer_norm(x, (C,), blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+        qkv = a.qkv(h).reshape(B, N, 3, a.num_heads, C // a.num_heads).permute(2, 0, 3, 1, 4)
+        att = ((qkv[0] @ qkv[1].transpose(-2, -1)) * a.scale).softmax(dim=-1)
+        o = att @ qkv[2]                                                              # [B, heads, N, 64]
+        gate = a.domain_layer(label).reshape(B, a.num_heads, 1, C // a.num_heads).softmax(dim=1)
+        o = (o * gate).transpose(1, 2).reshape(B, N, C)
+        x = x + a.proj(o)
+        h = F.layer_norm(x, (C,), blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+        x = x + blk.mlp.fc2(F.gelu(blk.mlp.fc1(h)))
+    return F.layer_norm(x, (x.shape[-1],), tr.norm.weight, tr.norm.bias, tr.norm.eps)
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    monkeypatch.setattr(ops, "ConvBnActFn", _EmuConv)
+    monkeypatch.setattr(ops, "BnActFn", _EmuBn)
+    monkeypatch.setattr(ops, "MaxPool3s2Fn", _EmuPool)
+    monkeypatch.setattr(ops, "ResizeACFn", _EmuResize)
+    monkeypatch.setattr(T.DeiT_adapt, "forward", lambda self, imgs, label: deit_forward_torch(self, imgs, label))
+
+
+def test_constructor_reproduces_reference_keys_and_init():
+    g = np.load(GOLD)
+    torch.manual_seed(0)
+    m = T.TransFuse_S_adapt(drop_rate=0.0)
+    assert list(m.state_dict().keys()) == list(g["keys"])
+    np.testing.assert_array_equal(fingerprint(list(m.named_parameters())), g["init_fp"])      # bit-identical weights
+
+
+def test_wiring_matches_reference_forward_backward_on_cpu(emulated):
+    g = np.load(GOLD)
+    torch.manual_seed(0)
+    m = T.TransFuse_S_adapt(drop_rate=0.0).train()
+    img, mask, dlab = case()
+    maps = m(img, dlab)
+    for n, p in zip(("map_x", "map_1", "map_2"), maps):
+        ref = torch.from_numpy(g[n])
+        assert p.shape == ref.shape
+        assert (p - ref).abs().max().item() <= 2e-4 * ref.abs().max().item(), n
+    losses = [structure_loss_ref(p, mask) for p in maps]
+    loss = 0.5 * losses[2] + 0.3 * losses[1] + 0.2 * losses[0]
+    np.testing.assert_allclose([l.item() for l in losses] + [loss.item()], g["losses"], rtol=2e-5)
+    loss.backward()
+    named = [(n, p.grad) for n, p in m.named_parameters() if p.grad is not None]
+    assert [n for n, _ in named] == list(g["grad_names"])      # the same parameters are reached (skip_layer of square Residuals is not)
+    fp, ref_fp = fingerprint(named), g["grad_fp"]
+    # (conv biases in front of a BatchNorm have an exactly-zero true gradient: round-off there is compared on an absolute scale)
+    err = np.abs(fp - ref_fp).max(axis=1) / (ref_fp[:, 0] + 1e-3 * np.median(ref_fp[:, 0]))
+    assert err.max() < 5e-3, (named[int(err.argmax())][0], err.max(), ref_fp[int(err.argmax())])
+    for k in g.files:
+        if k.startswith("buf."):
+            np.testing.assert_allclose(m.state_dict()[k[4:]].numpy(), g[k], rtol=1e-4, atol=1e-6)
