@@ -40,8 +40,9 @@ def parse():
     ap.add_argument("--cpu-batch-per-domain", type=int, default=1)
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train (default, the headline metric) or infer = BASELINE.json config 5: eval-mode throughput / latency sweep over batch 1..256")
-    ap.add_argument("--model", default="MDViT", choices=["MDViT", "BASE"],
-                    help="MDViT (default, the headline metric) or BASE = BASELINE.json config 2: no DA, no MKD (extra, not the headline)")
+    ap.add_argument("--model", default="MDViT", choices=["MDViT", "BASE", "TransFuse"],
+                    help="MDViT (default, the headline metric); BASE = BASELINE.json config 2: no DA, no MKD; TransFuse = config 4: "
+                         "TransFuse_S_adapt train step (extras, not the headline)")
     return ap.parse_args()
 
 
@@ -369,12 +370,104 @@ def run_infer(args):
         "gpu_launches": int(launches), "sweep": sweep, "clocks": clocks}))
 
 
+def run_transfuse(args):
+    """BASELINE.json config 4: the TransFuse_S_adapt train step of multi_train_TransFuse.py:145-197 (4 datasets x B images, three
+    structure losses per dataset, one backward, AdamW).  An extra line, not the headline metric."""
+    import torch
+    import torch.distributed as dist
+    from mdvit_b200 import _lib as L
+    from mdvit_b200 import ops, synth
+    from mdvit_b200.train_step import TransFuseTrainer
+    from mdvit_b200.transfuse import TransFuse_S_adapt
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — mdvit_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+    B = args.batch_per_domain
+    torch.manual_seed(0)
+    model = TransFuse_S_adapt(drop_rate=0.2, num_domains=4).to(dev).train()
+    ops.manual_seed(1234 + rank, dev)
+    trainer = TransFuseTrainer(model, lr=1e-4, weight_decay=0.05)
+    host = []
+    for d in range(4):
+        img, lab = synth.synth_batch(1234 + 17 * rank, d, B, IMG, IMG)
+        host.append((img.pin_memory(), lab.to(torch.uint8).pin_memory(), d))
+    dev_batches = [(i.to(dev), l.to(dev), d) for i, l, d in host]
+    h2d = sum(i.numel() * i.element_size() + l.numel() * l.element_size() for i, l, _ in host)
+    use_graph = not args.no_graph
+    if use_graph:
+        trainer.capture(dev_batches, warmup=1)
+        step_resident = lambda: trainer.step_graph(None)      # noqa: E731
+        step_e2e = lambda: trainer.step_graph(host)      # noqa: E731  H2D of the step's inputs from pinned memory, then the replay
+    else:
+        step_resident = lambda: trainer.step(dev_batches)      # noqa: E731
+        step_e2e = lambda: trainer.step([(i.to(dev, non_blocking=True), l.to(dev, non_blocking=True), d) for i, l, d in host])      # noqa: E731
+
+    def timed(fn, steps, read_back):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss_host = None
+        for _ in range(steps):
+            losses = fn()
+            if read_back:
+                loss_host = losses.to("cpu", non_blocking=False)
+        t.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([s.elapsed_time(t)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, loss_host
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.mdv_launch_count()
+    ms_res, _ = timed(step_resident, args.steps, False)
+    n1 = lib.mdv_launch_count()
+    ms_e2e, loss_host = timed(step_e2e, args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = trainer.launches_per_step if use_graph else (n1 - n0) // max(args.steps, 1)
+    imgs = 4 * B * world
+    if rank == 0:
+        print(json.dumps({
+            "metric": "transfuse_train_images_per_sec", "value": imgs / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 forward convs / bf16 transformer and gradient GEMMs, fp32 accumulate", "data": "synthetic",
+            "config": {"workload": f"TransFuse_S_adapt train step (BASELINE.json config 4): 4 datasets x {B} images/GPU at {IMG}x{IMG}, Dropout2d 0.2 / 0.1, "
+                                   "0.5/0.3/0.2 structure_loss deep supervision, one backward, AdamW",
+                       "batch_per_domain_per_gpu": B, "images_per_step": imgs, "parallelism": f"dp{world}", "cuda_graph": use_graph,
+                       "l2": "per-step working set (>10 GB) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * 4},
+            "gpu_launches": int(launches * args.steps * 2), "launches_per_step": int(launches),
+            "model_algorithmic_tflops": imgs / (ms_res * 1e-3) * 71.2 / 1e3,      # SURVEY section 8(d): 3 x 23.72 GFLOP per image
+            "clocks": clocks, "final_losses_per_dataset": loss_host.tolist() if loss_host is not None else None,
+        }))
+    if world > 1:
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
     if args.mode == "infer":
         return run_infer(args)
+    if args.model == "TransFuse":
+        return run_transfuse(args)
     import torch
     import torch.distributed as dist
     from mdvit_b200 import _lib as L

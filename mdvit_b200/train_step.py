@@ -449,3 +449,109 @@ class MKDTrainer:
             self._consumed[k] = ev
         self._graph.replay()
         return self._static_losses
+
+
+class TransFuseTrainer:
+    """One training step of multi_train_TransFuse.py:145-197 for TransFuse_S_adapt: per dataset one mini-batch -> three logit maps
+    -> loss = 0.5 structure_loss(map_2) + 0.3 structure_loss(map_1) + 0.2 structure_loss(map_x); the dataset losses are summed,
+    one backward, one AdamW step (flat fp32 parameter / gradient / moment buffers, mdv_adamw).  Data parallel: one all-reduce of
+    the flat gradient buffer (the loss is a per-sample mean, so the average over ranks is the global-batch gradient).  The whole
+    step can be captured into one CUDA graph over static input buffers (capture() / step_graph())."""
+
+    def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, process_group=None, num_domains=4):
+        self.model = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.num_domains = num_domains
+        self.params = [p for p in model.parameters()]
+        dev = self.params[0].device
+        self.device = dev
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += _align(p.numel())
+        self.total = total
+        with torch.no_grad():
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            for p, o in zip(self.params, offs):
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+        ops.enable_inplace_grad_accumulation(self.params)      # this trainer owns the gradient buffers and their reduction
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 0.0, 0.0, 1.0], dtype=torch.float64, device=dev)
+        ops.bump_weight_epoch()
+        self._graph = None
+
+    def _onehot(self, B, d):
+        dl = torch.zeros((B, self.num_domains), dtype=torch.float32, device=self.device)
+        dl[:, int(d)] = 1.0
+        return dl
+
+    def forward_losses(self, batches):
+        """batches: [(img [B,3,H,W], mask [B,1,H,W] fp32 or uint8, domain index)] -> per-dataset losses [n]"""
+        losses = []
+        for img, mask, d in batches:
+            mask = mask.float()
+            map_x, map_1, map_2 = self.model(img, self._onehot(img.shape[0], d))
+            weit = ops.structure_weit(mask)      # shared by the three maps
+            losses.append(0.5 * ops.structure_loss(map_2, mask, weit) + 0.3 * ops.structure_loss(map_1, mask, weit)
+                          + 0.2 * ops.structure_loss(map_x, mask, weit))
+        return torch.stack(losses)
+
+    def _step_body(self, batches):
+        ops.reset_stream_ids()
+        self.grad.zero_()
+        losses = self.forward_losses(batches)
+        losses.sum().backward()
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            self.grad.mul_(1.0 / self.world)
+        with torch.cuda.device(self.device):
+            check(L.lib().mdv_adamw(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.hyper), self.total, L.stream()),
+                  "mdv_adamw")
+            ops.rng_bump(self.device)
+        return losses.detach()
+
+    def step(self, batches):
+        ops.bump_weight_epoch()
+        return self._step_body(batches)
+
+    def _state_tensors(self):
+        return [self.flat, self.m, self.v, self.hyper, ops.rng_tensor(self.device)] + [b for b in self.model.buffers()]
+
+    def capture(self, example_batches, warmup=2):
+        """Capture the step into one CUDA graph over static input buffers; the training state is restored afterwards.  Weight
+        operand copies are re-derived inside the graph (ops.prep_weight is keyed on the weight epoch, bumped per capture)."""
+        self.static = [(img.clone(), mask.clone(), d) for img, mask, d in example_batches]
+        saved = [t.clone() for t in self._state_tensors()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                ops.bump_weight_epoch()
+                self._step_body(self.static)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        ops.bump_weight_epoch()
+        n0 = L.lib().mdv_launch_count()
+        with torch.cuda.graph(self._graph):
+            self._static_losses = self._step_body(self.static)
+        self.launches_per_step = L.lib().mdv_launch_count() - n0
+        ops.bump_weight_epoch()      # operand copies made inside the capture live in the graph's private pool: never reuse them eagerly
+        with torch.no_grad():
+            for t, s in zip(self._state_tensors(), saved):
+                t.copy_(s)
+        return self
+
+    def step_graph(self, batches=None):
+        if batches is not None:
+            for (s_img, s_mask, _), (img, mask, _) in zip(self.static, batches):
+                s_img.copy_(img, non_blocking=True)
+                s_mask.copy_(mask, non_blocking=True)
+        self._graph.replay()
+        return self._static_losses

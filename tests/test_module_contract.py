@@ -79,6 +79,8 @@ def test_dropin_package_resolves_reference_import_paths():
         mod = importlib.import_module("Models.Transformer.mdvit")
         assert mod.MDViT is MDViT
         assert importlib.import_module("Models.Transformer.base").BASE is BASE
+        from mdvit_b200.transfuse import TransFuse_S_adapt
+        assert importlib.import_module("Models.Hybrid_models.TransFuseFolder.TransFuse").TransFuse_S_adapt is TransFuse_S_adapt
     finally:
         sys.path.remove(os.path.join(root, "dropin"))
         for name in [m for m in sys.modules if m == "Models" or m.startswith("Models.")]:
