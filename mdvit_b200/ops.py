@@ -254,6 +254,10 @@ class bn_groups:
         _BN_GROUPS = self.prev
 
 
+def current_bn_groups():
+    return _BN_GROUPS
+
+
 def bn_fold(weight, bias, running_mean, running_var, conv_bias=None, eps=1e-5):
     """Eval-mode BatchNorm as (scale, shift) for the epilogue of the GEMM that feeds it (gemm_nt(colscale=scale, bias=shift,
     act=...)): the normalised tensor is produced by the GEMM itself, its fp32 pre-activation never reaches HBM."""
@@ -1722,10 +1726,13 @@ class StructureLossFn(torch.autograd.Function):
         with _dev_ctx(pred):
             check(L.lib().mdv_structure_loss_fwd(ptr(pred), ptr(mask), ptr(weit), ptr(sums), ptr(loss), B, HW, L.stream()), "mdv_structure_loss_fwd")
         ctx.save_for_backward(pred, mask, weit, sums)
-        return loss[0]
+        s = sums.view(B, 4)
+        per_sample = (s[:, 1] / s[:, 0] + 1.0 - (s[:, 2] + 1.0) / (s[:, 3] - s[:, 2] + 1.0)).float()
+        ctx.mark_non_differentiable(per_sample)
+        return loss[0], per_sample
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _unused=None):
         pred, mask, weit, sums = ctx.saved_tensors
         B, HW = pred.shape[0], pred[0].numel()
         g = _contig(g.float()).view(1)
@@ -1736,8 +1743,10 @@ class StructureLossFn(torch.autograd.Function):
         return dpred, None, None
 
 
-def structure_loss(pred, mask, weit=None):
-    """Drop-in for multi_train_TransFuse.py:29-38; pass `weit` (structure_weit(mask)) to share it between the three maps."""
+def structure_loss(pred, mask, weit=None, per_sample=False):
+    """Drop-in for multi_train_TransFuse.py:29-38; pass `weit` (structure_weit(mask)) to share it between the three maps.
+    per_sample=True also returns the [B] per-sample terms (wbce + wiou, detached) whose mean the loss is."""
     if weit is None:
         weit = structure_weit(mask)
-    return StructureLossFn.apply(pred, mask, weit)
+    loss, ps = StructureLossFn.apply(pred, mask, weit)
+    return (loss, ps) if per_sample else loss

@@ -458,8 +458,12 @@ class TransFuseTrainer:
     the flat gradient buffer (the loss is a per-sample mean, so the average over ranks is the global-batch gradient).  The whole
     step can be captured into one CUDA graph over static input buffers (capture() / step_graph())."""
 
-    def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, process_group=None, num_domains=4):
+    def __init__(self, model, lr=1e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, process_group=None, num_domains=4,
+                 fuse_datasets=True):
         self.model = model
+        self.fuse_datasets = fuse_datasets      # stack the dataset mini-batches into one pass (TransFuse_S_adapt.forward_multi)
+        self._onehot_cache = {}
+        self._total_loss = None
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.num_domains = num_domains
@@ -493,6 +497,8 @@ class TransFuseTrainer:
 
     def forward_losses(self, batches):
         """batches: [(img [B,3,H,W], mask [B,1,H,W] fp32 or uint8, domain index)] -> per-dataset losses [n]"""
+        if self.fuse_datasets and len(batches) > 1 and len({tuple(b[0].shape) for b in batches}) == 1:
+            return self._forward_losses_fused(batches)
         losses = []
         for img, mask, d in batches:
             mask = mask.float()
@@ -502,11 +508,33 @@ class TransFuseTrainer:
                           + 0.2 * ops.structure_loss(map_x, mask, weit))
         return torch.stack(losses)
 
+    def _forward_losses_fused(self, batches):
+        """All dataset mini-batches in one stacked pass (TransFuse_S_adapt.forward_multi); the summed loss of the G datasets is
+        G x the mean of the per-sample terms over the whole stack, so each map needs one loss launch; the per-dataset values (for
+        logging) are group means of the detached per-sample terms."""
+        G, B = len(batches), batches[0][0].shape[0]
+        x = torch.cat([b[0] for b in batches], dim=0)
+        mask = torch.cat([b[1] for b in batches], dim=0).float()
+        key = (B, tuple(int(b[2]) for b in batches))
+        dl = self._onehot_cache.get(key)
+        if dl is None:
+            dl = self._onehot_cache[key] = torch.cat([self._onehot(B, b[2]) for b in batches], dim=0)
+        map_x, map_1, map_2 = self.model.forward_multi(x, dl, G)
+        weit = ops.structure_weit(mask)
+        total, per = 0.0, 0.0
+        for c, mp in ((0.5, map_2), (0.3, map_1), (0.2, map_x)):
+            l, ps = ops.structure_loss(mp, mask, weit, per_sample=True)
+            total = total + c * l
+            per = per + c * ps
+        self._total_loss = G * total
+        return per.view(G, B).mean(dim=1)
+
     def _step_body(self, batches):
         ops.reset_stream_ids()
         self.grad.zero_()
+        self._total_loss = None
         losses = self.forward_losses(batches)
-        losses.sum().backward()
+        (self._total_loss if self._total_loss is not None else losses.sum()).backward()
         if self.world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
             self.grad.mul_(1.0 / self.world)

@@ -224,10 +224,34 @@ def _cba(x, H, W, conv, bn=None, act=ACT_NONE, residual=None, nchw=False):
     return y, Ho, Wo
 
 
+_BN1_COEF = {}
+
+
 def _bn1(z, bn, H, W):
-    """BatchNorm2d(1) on a single-channel NHWC map [B, H*W, 1]"""
+    """BatchNorm2d(1) on a single-channel NHWC map [B, H*W, 1].  Under ops.bn_groups(G) (the stacked multi-dataset forward) the
+    batch statistics are taken per group of B/G consecutive samples and the running statistics receive the G momentum updates
+    of G consecutive forwards, in group order."""
     B = z.shape[0]
-    return F.batch_norm(z.view(B, 1, H, W), bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps).view(B, H * W, 1)
+    G = ops.current_bn_groups() if bn.training else 1
+    if G == 1:
+        if bn.training:
+            bn.num_batches_tracked.add_(1)      # (nn.BatchNorm2d.forward does this; the functional does not)
+        return F.batch_norm(z.view(B, 1, H, W), bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps).view(B, H * W, 1)
+    zg = z.reshape(G, -1)
+    n = zg.shape[1]
+    mean = zg.mean(dim=1, keepdim=True)
+    var = zg.var(dim=1, unbiased=False, keepdim=True)
+    y = (zg - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
+    mom = bn.momentum
+    key = (G, mom, z.device)
+    coef = _BN1_COEF.get(key)
+    if coef is None:
+        coef = _BN1_COEF[key] = torch.tensor([mom * (1 - mom) ** (G - 1 - g) for g in range(G)], dtype=torch.float32, device=z.device)
+    with torch.no_grad():
+        bn.running_mean.mul_((1 - mom) ** G).add_((coef * mean.flatten()).sum())
+        bn.running_var.mul_((1 - mom) ** G).add_((coef * var.flatten()).sum() * (n / (n - 1)))
+        bn.num_batches_tracked.add_(G)
+    return y.view(B, H * W, 1)
 
 
 def _drop2d(x, p, training):
@@ -483,6 +507,13 @@ class TransFuse_S_adapt(nn.Module):
             x, H, W = m.run(x, H, W)
         B = x.shape[0]
         return ops.ResizeACFn.apply(x, H, W, Ho, Wo).view(B, 1, Ho, Wo)      # one channel: NHWC == NCHW
+
+    def forward_multi(self, imgs, domain_label, groups):
+        """The mini-batches of `groups` datasets stacked along the batch axis in ONE pass (multi_train_TransFuse.py:151-172 runs one
+        forward per dataset): every per-sample kernel runs once on all samples; BatchNorm batch statistics are taken per group of
+        B/groups consecutive samples and the running statistics are updated group by group, exactly as consecutive forwards do."""
+        with ops.bn_groups(groups):
+            return self.forward(imgs, domain_label)
 
     def forward(self, imgs, domain_label, labels=None):
         B, _, Hi, Wi = imgs.shape
