@@ -70,6 +70,16 @@ int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M, int N, in
  * section 7); the transformer blocks' GEMMs, whose outputs are small additive branches, stay bf16. */
 int mdv_gemm_nt_tf32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, void* stream);
 
+/* 3x3 / stride 1 / padding 1 convolution of an NHWC activation as ONE implicit GEMM (no im2col matrix): the A tiles of the K = 9*Cin
+ * reduction are fetched straight from x [B,H,W,Cin] (pixel pitch ldx) by 4-D TMA boxes, whose out-of-range zero fill is the padding:
+ *   out[(b,y,x), n] = epi( sum_{tap=(i,j), c} x[b, y + s(i-1), x + s(j-1), c] . Wm[n, tap*Cin + c] ),   s = flip ? -1 : +1.
+ * x fp32 (x_f32 = 1: TF32 math, Cin % 32 == 0) or bf16 (Cin % 64 == 0); Wm the same type, [N, ldw].  W <= 128 must divide 128 and
+ * H*W must be a multiple of 128 (a 128-row tile = whole image rows), else MDV_ERR_UNSUPPORTED (callers fall back to mdv_im2col3).
+ * Forward of the dense 3x3 convs of TransFuse_S_adapt (torchvision BasicBlock, DoubleConv / Conv, TransFuse.py:574-650) with
+ * Wm = mdv_prep_weight mode 2; with flip = 1, x := dz and Wm = mdv_prep_weight mode 4 it is their input gradient. */
+int mdv_conv3_gemm(const void* x, int x_f32, int ldx, const void* Wm, int ldw, int B, int H, int W, int Cin, int N, int flip,
+                   const MdvGemmEpi* epi, void* stream);
+
 /* C[P,Q] += A[R,P]^T . B[R,Q]  (fp32 atomics; A, B bf16 row-major).  Weight gradients of the above. */
 int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc, void* stream);
 
@@ -252,7 +262,8 @@ int mdv_colsum(const void* x, int x_bf16, int ld, float* out, int M, int C, void
 int mdv_cast_bf16(const float* in, int ld_in, void* out_bf16, int ld_out, long long M, int C, const float* rowscale,
                   int rows_per_scale, float drop_p, const void* rng, uint32_t drop_stream, float* colsum, void* stream);
 int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, int ld_out, long long M, int C, int accumulate, void* stream);
-/* fp32 master weight -> GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2; dst is bf16, or
+/* fp32 master weight -> GEMM operand.  mode 0 copy, 1 transpose, 2 conv3x3 -> im2col order, 3 = transpose of 2, 4 = conv3x3 ->
+ * [Cin, tap*Cout + co] (input-gradient operand of mdv_conv3_gemm); dst is bf16, or
  * fp32 (TF32 GEMM operand) when 8 is added to the mode */
 int mdv_prep_weight(const float* src, void* dst, int R, int Cc, int ld, int mode, int cin, void* stream);
 /* The same for a whole model in one launch: `descs_dev` is a DEVICE array of n descriptors (zero-padded dst regions are

@@ -49,6 +49,9 @@ struct GemmParams {
     int bk;               // elements per k-block: 128 bytes of K per row of a stage
     int nbuf;             // staging buffers per epilogue warp (2 or 4)
     int out_slab, buf_bytes;   // bytes of the output slab (2 KB bf16 / 4 KB fp32) and of one buffer (out [+ 2 KB preact])
+    // NT only, implicit-GEMM 3x3 convolution (mdv_conv3_gemm): A is an NHWC activation read through a 4-D tensor map; k-block kc
+    // belongs to tap kc / conv_cin and channels kc % conv_cin.., and its A tile is the output tile's pixels shifted by that tap
+    int conv_cin, conv_w, conv_hw, conv_flip;
     MdvGemmEpi epi;
 };
 
@@ -156,18 +159,32 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         if (rank == 0) mbar_arrive(&full_bar[s]);
                         continue;
                     }
+                    // implicit 3x3 convolution: the A tile of this k-block = the tile's 128 pixels (whole image rows) moved by the tap
+                    int cv_c = 0, cv_x = 0, cv_y = 0, cv_b = 0;
+                    if (!TN && p.conv_cin) {
+                        const int tap = kc / p.conv_cin;
+                        cv_c = kc - tap * p.conv_cin;
+                        int di = tap / 3 - 1, dj = tap - (tap / 3) * 3 - 1;
+                        if (p.conv_flip) { di = -di; dj = -dj; }
+                        const int p0 = tc.m_tile * TM + (int)rank * BM;
+                        cv_b = p0 / p.conv_hw;
+                        cv_y = (p0 - cv_b * p.conv_hw) / p.conv_w + di;
+                        cv_x = dj;
+                    }
                     if (PAIR) {
                         // the bytes of both CTAs are counted on the leader's barrier (a complete_tx that overtakes the
                         // leader's expect_tx only drives the transaction count negative within the same phase)
                         if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
                         const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
-                        tma_load_2d_pair(sa, &tmA, kc, tc.m_tile * TM + (int)rank * BM, fb);
+                        if (p.conv_cin) tma_load_4d_pair(sa, &tmA, cv_c, cv_x, cv_y, cv_b, fb);
+                        else tma_load_2d_pair(sa, &tmA, kc, tc.m_tile * TM + (int)rank * BM, fb);
                         tma_load_2d_pair(sb, &tmB, kc, tc.n_tile * BN + (int)rank * bn_cta, fb);
                         continue;
                     }
                     mbar_expect_tx(&full_bar[s], stage_bytes);
                     if (!TN) {
-                        tma_load_2d(sa, &tmA, kc, tc.m_tile * BM, &full_bar[s]);
+                        if (p.conv_cin) tma_load_4d(sa, &tmA, cv_c, cv_x, cv_y, cv_b, &full_bar[s]);
+                        else tma_load_2d(sa, &tmA, kc, tc.m_tile * BM, &full_bar[s]);
                         tma_load_2d(sb, &tmB, kc, tc.n_tile * BN, &full_bar[s]);
                     } else {
                         for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, tc.m_tile * BM + c * 64, kc, &full_bar[s]);
@@ -635,11 +652,19 @@ extern "C" int mdv_gemm_force_pair(int mode) {
     return MDV_OK;
 }
 
-static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, int tf32, void* stream) {
+struct ConvGeom {      // implicit 3x3 convolution mode of gemm_nt_impl (mdv_conv3_gemm)
+    int B, H, W, Cin, flip;
+};
+
+static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi, int tf32, void* stream,
+                        const ConvGeom* cv = nullptr) {
     if (!A || !W || !epi || !epi->out || M <= 0 || N <= 0 || K <= 0) return MDV_ERR_ARG;
     if ((N & 3) || (K & (tf32 ? 3 : 7)) || epi->accumulate) return MDV_ERR_ARG;
     GemmParams p = {};
     p.M = M; p.N = N; p.K = K;
+    if (cv) {
+        p.conv_cin = cv->Cin; p.conv_w = cv->W; p.conv_hw = cv->H * cv->W; p.conv_flip = cv->flip;
+    }
     p.epi = *epi;
     p.tf32 = tf32;
     p.bk = tf32 ? 32 : 64;
@@ -662,7 +687,8 @@ static int gemm_nt_impl(const void* A, int lda, const void* W, int ldw, int M, i
     p.has_preact = epi->out_preact != nullptr;
     CUtensorMap ta, tb, tc, tp;
     const int es = tf32 ? 4 : 2;
-    int rc = make_map(&ta, A, es, K, M, lda, p.bk, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = cv ? make_map_nhwc(&ta, A, es, cv->Cin, cv->W, cv->H, cv->B, lda, p.bk, cv->W, BM / cv->W, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map(&ta, A, es, K, M, lda, p.bk, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map(&tb, W, es, K, N, ldw, p.bk, p.pair ? p.BN / 2 : p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -685,6 +711,20 @@ extern "C" int mdv_gemm_nt(const void* A, int lda, const void* W, int ldw, int M
 extern "C" int mdv_gemm_nt_tf32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const MdvGemmEpi* epi,
                                 void* stream) {
     return gemm_nt_impl(A, lda, W, ldw, M, N, K, epi, 1, stream);
+}
+
+// out[(b,y,x), n] = epi( sum_{tap=(i,j), c} x[b, y + s(i-1), x + s(j-1), c] . Wm[n, tap*Cin + c] ),  s = flip ? -1 : +1, zero outside
+// the image: a 3x3 / stride 1 / padding 1 convolution as ONE tcgen05 GEMM with K = 9*Cin whose A tiles are fetched straight from
+// the NHWC activation by 4-D TMA boxes (no im2col matrix).  flip = 1 with x := dz and Wm[ci, tap*Cout + co] = w[co, ci, tap] is the
+// convolution's input gradient.
+extern "C" int mdv_conv3_gemm(const void* x, int x_f32, int ldx, const void* Wm, int ldw, int B, int H, int W, int Cin, int N, int flip,
+                              const MdvGemmEpi* epi, void* stream) {
+    if (!x || !Wm || !epi || B <= 0 || H <= 0 || W <= 0 || Cin <= 0) return MDV_ERR_ARG;
+    const int bk = x_f32 ? 32 : 64;
+    if ((Cin % bk) || W > BM || (BM % W) || ((long long)H * W) % BM) return MDV_ERR_UNSUPPORTED;
+    if ((long long)B * H * W >= 2147483647LL) return MDV_ERR_UNSUPPORTED;
+    ConvGeom cv = {B, H, W, Cin, flip ? 1 : 0};
+    return gemm_nt_impl(x, ldx, Wm, ldw, B * H * W, N, 9 * Cin, epi, x_f32 ? 1 : 0, stream, &cv);
 }
 
 extern "C" int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc,

@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(256) add_f32_kernel(const TI* __restrict__ in,
 //  mode 1: src [R, Cc] row-major                       -> dst [Cc, ld] = src^T (for input gradients)
 //  mode 2: src [R, Cin, 3, 3] (PyTorch conv)           -> dst [R, ld], column (i*3+j)*Cin + ci    (im2col order)
 //  mode 3: src [R, Cin, 3, 3]                          -> dst [9*Cin (pad to rows), ld] transposed of mode 2
+//  mode 4: src [R, Cin, 3, 3]                          -> dst [Cin, ld], column t*R + r            (operand of the implicit-GEMM input gradient)
 //  mode | 8: the same layouts with an fp32 destination (operands of the TF32 GEMMs of the conv trunk)
 template <typename TO>
 __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ src, TO* __restrict__ dst, int R, int Cc,
@@ -389,6 +390,9 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
             dst[(size_t)r * ld + c] = v;
         } else if (mode == 1) {
             dst[(size_t)c * ld + r] = v;
+        } else if (mode == 4) {      // conv [R, Cin, 3, 3] -> [Cin, ld >= 9*R]: dst[ci, t*R + r] (input-gradient operand of mdv_conv3_gemm)
+            const int ci = c / 9, t = c % 9;
+            dst[(size_t)ci * ld + t * R + r] = v;
         } else {
             const int ci = c / 9, t = c % 9;
             const int col = t * cin + ci;
@@ -414,6 +418,8 @@ __global__ void __launch_bounds__(256) prep_weights_batched_kernel(const MdvPrep
             o = (size_t)r * d.ld + c;
         } else if (mode == 1) {
             o = (size_t)c * d.ld + r;
+        } else if (mode == 4) {
+            o = (size_t)(c / 9) * d.ld + (size_t)(c % 9) * d.rows + r;
         } else {
             const int ci = c / 9, t = c % 9;
             const int col = t * d.cin + ci;
@@ -741,7 +747,7 @@ extern "C" int mdv_add_f32(const void* in, int in_bf16, int ld_in, float* out, i
 }
 
 extern "C" int mdv_prep_weight(const float* src, void* dst, int R, int Cc, int ld, int mode, int cin, void* stream) {
-    if (!src || !dst || mode < 0 || (mode & 7) > 3 || mode > 11) return MDV_ERR_ARG;
+    if (!src || !dst || mode < 0 || (mode & 7) > 4 || mode > 12) return MDV_ERR_ARG;
     if (mode & 8)
         mdv_launch(prep_weight_kernel<float>, dim3(grid_for((long long)R * Cc)), dim3(256), 0, (cudaStream_t)stream, src, (float*)dst, R, Cc, ld, mode & 7, cin);
     else

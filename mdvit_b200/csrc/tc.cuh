@@ -81,6 +81,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// 4-D tiled load (implicit-GEMM convolution: (channel, x, y, image) boxes of an NHWC tensor; out-of-range x / y / image coordinates,
+// negative ones included, are zero-filled by the TMA unit = the convolution's zero padding)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
@@ -155,6 +164,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs when the MMAs so far are done
@@ -251,6 +267,22 @@ static inline int make_map(CUtensorMap* m, const void* ptr, int esize, long long
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MDV_OK : MDV_ERR_DRIVER;
+}
+
+// 4-D tensor map over an NHWC activation [B, H, W, C] (pixel pitch `ld` elements): dims (C, W, H, B), box (box_c, box_w, box_h, 1).
+static inline int make_map_nhwc(CUtensorMap* m, const void* ptr, int esize, int C, int W, int H, int B, long long ld, int box_c, int box_w,
+                                int box_h, CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return MDV_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esize) & 15)) return MDV_ERR_ARG;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * esize, (cuuint64_t)ld * esize * W, (cuuint64_t)ld * esize * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? MDV_OK : MDV_ERR_DRIVER;

@@ -13,7 +13,6 @@ inline int grid_for(long long total, int threads = 256) {
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
 }
-inline bool fits_i32(long long v) { return v >= 0 && v < 2147483647LL; }
 
 // ---------------------------------------------------------------------------------- generic k x k im2col / col2im
 // col[(b,yo,xo), c*k*k + i*k + j] = in[b, yo*s - pad + i, xo*s - pad + j, c]   (0 outside the image and in the columns

@@ -114,11 +114,13 @@ def set_weight_mirror(m):
 
 def prep_weight(w, mode, rows, cols, ld=None, cin=0):
     """GEMM operand of fp32 parameter `w`: bf16, or fp32 (TF32 GEMM operand) when 8 is added to the mode
-    (mode & 7: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order)."""
+    (mode & 7: 0 copy [R,ld], 1 transpose [Cc,ld], 2/3 conv3x3 im2col order, 4 conv3x3 -> [Cin, tap*R + r])."""
     R, Cc = rows, cols
     m = mode & 7
     if m == 0 or m == 2:
         out_rows, out_ld = R, (ld or Cc)
+    elif m == 4:      # conv3x3 [R, Cin, 3, 3] -> [Cin, 9 R] (input-gradient operand of mdv_conv3_gemm)
+        out_rows, out_ld = Cc // 9, (ld or 9 * R)
     else:
         out_rows, out_ld = Cc, (ld or R)
     if _mirror is not None:
@@ -1470,14 +1472,36 @@ def conv_geom(H, W, k, stride):
     return (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1, pad
 
 
-def _conv_cols(x, B, H, W, Cin, k, stride, nchw):
-    """fp32 A operand of the conv GEMM: (A [M, ld], ld, kind).  kind 'direct': the map itself (1x1, stride 1); 'k3': im2col in
-    (tap, channel) order (mdv_im2col3); 'gen': generic k x k im2col in the flattened-weight (channel, tap) order."""
+_IMPLICIT_CONV = not bool(int(_os.environ.get("MDV_NO_IMPLICIT_CONV", "0")))      # A/B switch (development)
+
+
+def implicit_conv_ok(H, W, Cin, bf16):
+    """mdv_conv3_gemm's geometry: 128-row tiles are whole image rows, channel chunks fill a 128-byte k-block"""
+    return _IMPLICIT_CONV and W <= 128 and 128 % W == 0 and (H * W) % 128 == 0 and Cin % (64 if bf16 else 32) == 0
+
+
+def conv3_gemm(x, Wm, B, H, W, Cin, N, out, *, flip=False, bias=None):
+    """out [B*H*W, N] = 3x3/stride-1/pad-1 convolution of the NHWC map x as one implicit tcgen05 GEMM (mdv_conv3_gemm)"""
+    e = GemmEpi()
+    e.bias, e.out, e.ldc = ptr(bias), ptr(out), N
+    e.out_bf16 = 1 if out.dtype == BF16 else 0
+    e.rows_per_scale = 1
+    check(L.lib().mdv_conv3_gemm(ptr(x), int(x.dtype == F32), Cin, ptr(Wm), Wm.shape[1], B, H, W, Cin, N, int(flip), ctypes.byref(e),
+                                 L.stream()), "mdv_conv3_gemm")
+    return out
+
+
+def _conv_cols(x, B, H, W, Cin, k, stride, nchw, Cout=0):
+    """fp32 A operand of the conv GEMM: (A [M, ld], ld, kind).  kind 'direct': the map itself (1x1, stride 1); 'k3i': the map
+    itself, read by the implicit-GEMM kernel (3x3, stride 1; no im2col matrix); 'k3': im2col in (tap, channel) order
+    (mdv_im2col3); 'gen': generic k x k im2col in the flattened-weight (channel, tap) order."""
     Ho, Wo, pad = conv_geom(H, W, k, stride)
     M, dev = B * Ho * Wo, x.device
     lib = L.lib()
     if k == 1 and stride == 1 and not nchw and Cin % 8 == 0:
         return x.view(M, Cin), Cin, "direct"
+    if k == 3 and stride == 1 and not nchw and Cout > 1 and Cin % 8 == 0 and implicit_conv_ok(H, W, Cin, False):
+        return x.view(M, Cin), 9 * Cin, "k3i"
     if k == 3 and not nchw and Cin % 8 == 0:
         col = torch.empty((M, 9 * Cin), dtype=F32, device=dev)
         check(lib.mdv_im2col3(ptr(x), 0, ptr(col), 0, B, H, W, Ho, Wo, Cin, stride, 9 * Cin, L.stream()), "mdv_im2col3")
@@ -1492,7 +1516,7 @@ def _conv_cols(x, B, H, W, Cin, k, stride, nchw):
 def _conv_weight_f32(w, kind, ld):
     """fp32 W operand [Cout, ld] matching _conv_cols' column order."""
     Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
-    if kind == "k3":
+    if kind in ("k3", "k3i"):
         return prep_weight(w, 2 | 8, Cout, 9 * Cin, cin=Cin)
     K = Cin * k * k
     if ld == K:
@@ -1520,9 +1544,16 @@ class ConvBnActFn(torch.autograd.Function):
         has_bn = gamma is not None
         lib = L.lib()
         with _dev_ctx(x):
-            A, ld, kind = _conv_cols(x, B, H, W, Cin, k, stride, nchw)
+            A, ld, kind = _conv_cols(x, B, H, W, Cin, k, stride, nchw, Cout)
             Wf = _conv_weight_f32(w, kind, ld)
             z = mean = rstd = None
+
+            def conv_out(**kw):      # fp32 [M, Cout] = conv(x) (+ bias ...)
+                o = torch.empty((M, Cout), dtype=F32, device=dev)
+                if kind == "k3i":
+                    return conv3_gemm(A, Wf, B, H, W, Cin, Cout, o, bias=kw.get("bias"))
+                return gemm_nt(A, Wf, M, Cout, ld, o, tf32=True, **kw)
+
             if Cout == 1:
                 if has_bn or residual is not None or act != ACT_NONE:
                     raise NotImplementedError("single-channel conv: no BN / residual / activation")
@@ -1533,10 +1564,12 @@ class ConvBnActFn(torch.autograd.Function):
                 if act != ACT_NONE and residual is not None:
                     raise NotImplementedError("activation after a residual add needs BN in between")
                 res = _contig(residual).view(M, Cout) if residual is not None else None
+                if kind == "k3i":
+                    raise NotImplementedError("3x3 conv without BatchNorm (not part of TransFuse_S_adapt apart from the 1-channel heads)")
                 y = gemm_nt(A, Wf, M, Cout, ld, torch.empty((M, Cout), dtype=F32, device=dev), bias=cbias, residual=res, act=act, tf32=True)
             else:
                 rm, rv, nb = bufs
-                z = gemm_nt(A, Wf, M, Cout, ld, torch.empty((M, Cout), dtype=F32, device=dev), bias=cbias, tf32=True)
+                z = conv_out(bias=cbias)
                 if residual is None:
                     y, mean, rstd = bn_forward(z, M, Cout, gamma, beta, rm, rv, nb, training, act, False)
                 else:
@@ -1592,8 +1625,12 @@ class ConvBnActFn(torch.autograd.Function):
                 colsum(dz, M, Cout, gb)
                 gw, rw = gtarget(w)
                 if gw is not None:
-                    Ab = cast_bf16(A, M, ld)
-                    if kind == "k3":
+                    if kind == "k3i":      # the im2col matrix exists only here, in bf16, as the weight-gradient GEMM's operand
+                        Ab = torch.empty((M, ld), dtype=BF16, device=dev)
+                        check(lib.mdv_im2col3(ptr(A), 0, ptr(Ab), 1, B, H, W, Ho, Wo, Cin, 1, ld, L.stream()), "mdv_im2col3")
+                    else:
+                        Ab = cast_bf16(A, M, ld)
+                    if kind in ("k3", "k3i"):
                         gwp = gemm_tn(dz, Ab, M, Cout, ld, torch.zeros((Cout, ld), dtype=F32, device=dev))
                         check(lib.mdv_unperm_conv_grad(ptr(gwp), ld, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
                     elif ld == K:
@@ -1605,7 +1642,11 @@ class ConvBnActFn(torch.autograd.Function):
                 if need_dx:
                     if kind == "direct":
                         dx = gemm_nt(dz, prep_weight(w, 1, Cout, Cin), M, Cin, Cout, torch.empty((M, Cin), dtype=F32, device=dev))
-                    elif kind == "k3":
+                    elif kind == "k3i" and implicit_conv_ok(H, W, Cout, True):
+                        # input gradient = the same implicit GEMM over dz with the taps mirrored: dx never exists as a [M, 9 Cin] matrix
+                        dx = conv3_gemm(dz, prep_weight(w, 4, Cout, 9 * Cin), B, H, W, Cout, Cin, torch.empty((M, Cin), dtype=F32, device=dev),
+                                        flip=True)
+                    elif kind in ("k3", "k3i"):
                         dcol = gemm_nt(dz, prep_weight(w, 3, Cout, 9 * Cin, cin=Cin), M, 9 * Cin, Cout, torch.empty((M, ld), dtype=F32, device=dev))
                     else:
                         if K != ld:
@@ -1615,7 +1656,7 @@ class ConvBnActFn(torch.autograd.Function):
                 dx = dcol
             elif need_dx and dx is None:
                 dx = torch.empty((B * H * W, Cin), dtype=F32, device=dev)
-                if kind == "k3":
+                if kind in ("k3", "k3i"):
                     check(lib.mdv_col2im3(ptr(dcol), ptr(dx), B, H, W, Ho, Wo, Cin, stride, ld, L.stream()), "mdv_col2im3")
                 else:
                     check(lib.mdv_col2im_k(ptr(dcol), ptr(dx), B, H, W, Ho, Wo, Cin, k, stride, pad, ld, L.stream()), "mdv_col2im_k")

@@ -32,6 +32,11 @@ def rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
 def tf32_representable(t):
     """round to 10 explicit mantissa bits: products of such operands are exact on the TF32 tensor-core path AND in fp32, so the
     op-level comparison below sees the same pre-activations (no ReLU-mask flips on near-zero values) and isolates the kernels"""
@@ -52,14 +57,30 @@ CONV_CASES = [
     (384, 128, 1, 1, 8, 8, True, False, False, False, True),      # W_x / identity convs
     (128, 128, 1, 1, 8, 8, True, True, True, False, True),        # relu(g1 + x1)
     (64, 128, 1, 1, 8, 12, False, False, True, False, True),      # Residual.conv3 + residual (GEMM epilogue add)
-    (192, 64, 3, 1, 12, 8, True, True, False, False, True),       # DoubleConv first conv, ragged map
+    (192, 64, 3, 1, 12, 8, True, True, False, False, True),       # DoubleConv first conv, ragged map (im2col fallback)
+    (64, 64, 3, 1, 64, 64, True, True, False, False, False),      # implicit GEMM, 2 image rows per 128-row tile
+    (128, 128, 3, 1, 32, 32, True, True, True, False, False),     # implicit GEMM, 4 rows per tile, + identity
+    (256, 256, 3, 1, 16, 16, True, True, False, False, False),    # implicit GEMM, 8 rows per tile (2 tiles per image)
+    (384, 128, 3, 1, 32, 32, True, True, False, False, True),     # up1 / up_c_1_2 DoubleConv
+    (32, 32, 3, 1, 64, 64, True, True, False, False, True),       # Residual.conv2 of up_c_2_1: implicit forward, im2col input gradient
 ]
 
 
+@pytest.mark.parametrize("pair", [-1, 1])
 @pytest.mark.parametrize("case_", CONV_CASES)
-def test_conv_bn_act_fwd_bwd_vs_torch(case_):
-    from mdvit_b200 import ops
+def test_conv_bn_act_fwd_bwd_vs_torch(case_, pair):
+    from mdvit_b200 import _lib as L, ops
     dev = _dev()
+    if pair == 1 and case_[2] != 3:
+        pytest.skip("the forced CTA-pair run covers the 3x3 convolutions")
+    L.lib().mdv_gemm_force_pair(pair)      # 1: every NT GEMM (implicit-conv mode included) as tcgen05 cta_group::2 CTA pairs
+    try:
+        _conv_case(case_, dev, ops)
+    finally:
+        L.lib().mdv_gemm_force_pair(-1)
+
+
+def _conv_case(case_, dev, ops):
     Cin, Cout, k, s, H, W, bn, act, res, nchw, bias = case_
     B = 3
     g = torch.Generator().manual_seed(k * 1000 + Cin + Cout)
@@ -90,7 +111,11 @@ def test_conv_bn_act_fwd_bwd_vs_torch(case_):
         if name == "dbias" and bn:      # exactly zero in exact arithmetic (BatchNorm removes the bias): only round-off to compare
             assert torch.isfinite(a_).all()
             continue
-        assert rel(a_, b_) < BWD_TOL, (name, rel(a_, b_))
+        # L2-relative: with K up to 3456 the two fp32 accumulation orders can still put a BatchNorm output on different sides of
+        # zero (about one ReLU-mask flip per few 1e5 elements), which moves a handful of gradient entries by a whole weight
+        assert rel_l2(a_, b_) < BWD_TOL, (name, rel_l2(a_, b_))
+        big = ((a_ - b_).abs() > 5 * BWD_TOL * b_.abs().max()).float().mean().item()
+        assert big < 2e-3, (name, big)
     if bn:
         assert rel(b0[0], b1[0]) < FWD_TOL and rel(b0[1], b1[1]) < FWD_TOL and int(b0[2]) == 1
 
@@ -329,4 +354,27 @@ def test_transfuse_trainer_eager_and_graph_steps_agree():
     # AdamW's first steps are ~ lr * sign(g): parameters whose true gradient is zero (conv biases in front of a BatchNorm) follow
     # the sign of round-off (fp32 atomics order), so a few elements may differ by up to 2 lr; everything else must agree closely
     diff = (f0 - f1).abs()
-    assert diff.median().item() < 1e-5 and (diff > 2e-4).float().mean().item() < 1e-2, (diff.median().item(), (diff > 2e-4).float().mean().item())
+    assert diff.median().item() < 5e-5 and (diff > 5e-4).float().mean().item() < 2e-2, (diff.median().item(), (diff > 5e-4).float().mean().item())
+
+
+def test_stacked_multi_dataset_forward_matches_consecutive_forwards_on_gpu():
+    """forward_multi (grouped BatchNorm kernels, one pass over the stack) against one forward per dataset, on the real kernels"""
+    from mdvit_b200 import transfuse as T
+    dev = _dev()
+    img, _, dlab = (t.to(dev) for t in case(B=4))
+    outs, bufs = [], []
+    for stacked in (True, False):
+        torch.manual_seed(0)
+        m = T.TransFuse_S_adapt(drop_rate=0.0).to(dev).train()
+        with torch.no_grad():
+            if stacked:
+                maps = m.forward_multi(img, dlab, 2)
+            else:
+                parts = [m(img[:2], dlab[:2]), m(img[2:], dlab[2:])]
+                maps = [torch.cat([a, b]) for a, b in zip(*parts)]
+        outs.append(maps)
+        bufs.append({k: v.clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k})
+    for a, b in zip(*outs):
+        assert rel(a, b) < 1e-2, rel(a, b)
+    for k in bufs[0]:
+        assert rel(bufs[0][k], bufs[1][k]) < 1e-2, k
