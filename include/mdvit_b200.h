@@ -80,6 +80,13 @@ int mdv_gemm_nt_tf32(const float* A, int lda, const float* W, int ldw, int M, in
 int mdv_conv3_gemm(const void* x, int x_f32, int ldx, const void* Wm, int ldw, int B, int H, int W, int Cin, int N, int flip,
                    const MdvGemmEpi* epi, void* stream);
 
+/* Weight gradient of the same convolution, in the column order of mdv_prep_weight mode 2 (apply mdv_unperm_conv_grad):
+ *   dWm[p, tap*Cin + c] += sum_{(b,y,x)} dz[(b,y,x), p] . x[b, y + i - 1, x + j - 1, c]
+ * one TN GEMM whose B tiles are 4-D TMA boxes of x (bf16 NHWC, pixel pitch ldx); dz bf16 [B*H*W, P].  Cin % 64 == 0, W <= 64 must
+ * divide 64, H*W % 64 == 0, else MDV_ERR_UNSUPPORTED. */
+int mdv_conv3_wgrad(const void* dz_bf16, int ldz, const void* x_bf16, int ldx, int B, int H, int W, int Cin, int P, float* dWm, int ldc,
+                    void* stream);
+
 /* C[P,Q] += A[R,P]^T . B[R,Q]  (fp32 atomics; A, B bf16 row-major).  Weight gradients of the above. */
 int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc, void* stream);
 

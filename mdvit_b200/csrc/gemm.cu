@@ -188,7 +188,20 @@ __global__ void __launch_bounds__(32 * (4 + NEPI), 1)
                         tma_load_2d(sb, &tmB, kc, tc.n_tile * BN, &full_bar[s]);
                     } else {
                         for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, tc.m_tile * BM + c * 64, kc, &full_bar[s]);
-                        for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, tc.n_tile * BN + c * 64, kc, &full_bar[s]);
+                        if (p.conv_cin) {
+                            // implicit 3x3 weight gradient: column q of B is (tap, channel) = (q / Cin, q % Cin); the 64 reduction
+                            // rows of this k-block are 64 consecutive pixels (whole image rows) moved by the tap
+                            const int cb = kc / p.conv_hw, cy = (kc - cb * p.conv_hw) / p.conv_w;
+                            for (int c = 0; c < BN / 64; ++c) {
+                                const int q = tc.n_tile * BN + c * 64;
+                                const int tap = q / p.conv_cin;
+                                const int di = tap / 3 - 1, dj = tap - (tap / 3) * 3 - 1;
+                                // (chunks past the last tap: an image index beyond the batch = all zeros)
+                                tma_load_4d(sb + c * 8192, &tmB, q - tap * p.conv_cin, dj, cy + di, tap < 9 ? cb : 0x3fffffff, &full_bar[s]);
+                            }
+                        } else {
+                            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, tc.n_tile * BN + c * 64, kc, &full_bar[s]);
+                        }
                     }
                 }
             }
@@ -727,12 +740,15 @@ extern "C" int mdv_conv3_gemm(const void* x, int x_f32, int ldx, const void* Wm,
     return gemm_nt_impl(x, ldx, Wm, ldw, B * H * W, N, 9 * Cin, epi, x_f32 ? 1 : 0, stream, &cv);
 }
 
-extern "C" int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc,
-                           void* stream) {
+static int gemm_tn_impl(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc, void* stream,
+                        const ConvGeom* cv = nullptr) {
     if (!A || !B || !C || R <= 0 || P <= 0 || Q <= 0) return MDV_ERR_ARG;
     if ((P & 7) || (Q & 7) || (ldc & 3)) return MDV_ERR_ARG;
     GemmParams p = {};
     p.M = P; p.N = Q; p.K = R;
+    if (cv) {
+        p.conv_cin = cv->Cin; p.conv_w = cv->W; p.conv_hw = cv->H * cv->W;
+    }
     p.bk = BK;
     p.BN = pick_bn(Q, 64);
     p.n_tiles = mdv_cdiv(Q, p.BN);
@@ -753,9 +769,27 @@ extern "C" int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R
     CUtensorMap ta, tb, tc;
     int rc = make_map(&ta, A, 2, P, R, lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, B, 2, Q, R, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = cv ? make_map_nhwc(&tb, B, 2, cv->Cin, cv->W, cv->H, cv->B, ldb, 64, cv->W, BK / cv->W, CU_TENSOR_MAP_SWIZZLE_128B)
+            : make_map(&tb, B, 2, Q, R, ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map(&tc, C, 4, Q, P, ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     return launch<true>(ta, tb, tc, tc, p, (cudaStream_t)stream);
+}
+
+extern "C" int mdv_gemm_tn(const void* A, int lda, const void* B, int ldb, int R, int P, int Q, float* C, int ldc,
+                           void* stream) {
+    return gemm_tn_impl(A, lda, B, ldb, R, P, Q, C, ldc, stream);
+}
+
+// dWm[p, tap*Cin + c] += sum_{(b,y,x)} dz[(b,y,x), p] . x[b, y + i - 1, x + j - 1, c]: the weight gradient of the 3x3 / stride 1 /
+// padding 1 convolution in the im2col column order of mdv_prep_weight mode 2 (mdv_unperm_conv_grad turns it into [P, Cin, 3, 3]),
+// as one TN GEMM whose B tiles come straight from the NHWC activation (4-D TMA boxes; no im2col matrix).
+extern "C" int mdv_conv3_wgrad(const void* dz_bf16, int ldz, const void* x_bf16, int ldx, int B, int H, int W, int Cin, int P, float* dWm,
+                               int ldc, void* stream) {
+    if (!dz_bf16 || !x_bf16 || !dWm || B <= 0 || H <= 0 || W <= 0 || Cin <= 0) return MDV_ERR_ARG;
+    if ((Cin % 64) || W > BK || (BK % W) || ((long long)H * W) % BK) return MDV_ERR_UNSUPPORTED;
+    if ((long long)B * H * W >= 2147483647LL) return MDV_ERR_UNSUPPORTED;
+    ConvGeom cv = {B, H, W, Cin, 0};
+    return gemm_tn_impl(dz_bf16, ldz, x_bf16, ldx, B * H * W, P, 9 * Cin, dWm, ldc, stream, &cv);
 }

@@ -18,10 +18,13 @@ inline int grid_for(long long total, int threads = 256) {
 // col[(b,yo,xo), c*k*k + i*k + j] = in[b, yo*s - pad + i, xo*s - pad + j, c]   (0 outside the image and in the columns
 // >= C*k*k up to the pitch ldc).  The column order is that of a flattened nn.Conv2d weight [Cout, Cin, k, k], so the GEMM's
 // W operand is the parameter itself.  `in` is NHWC, or the NCHW input image (in_nchw = 1: resnet.conv1, TransFuse.py:231).
-template <typename TO>
+// KK / CC / LD: kernel size, channels and pitch at compile time (0 = the runtime arguments): the index arithmetic of the generic
+// form (five divisions by runtime integers per element) made the 7x7 stem im2col instruction bound at 4x its HBM time.
+template <typename TO, int KK, int CC, int LD>
 __global__ void __launch_bounds__(256) im2col_k_kernel(const float* __restrict__ in, TO* __restrict__ col, int B, int Hi, int Wi,
-                                                        int Ho, int Wo, int C, int k, int stride, int pad, int ldc, int in_nchw) {
+                                                        int Ho, int Wo, int C_rt, int k_rt, int stride, int pad, int ldc_rt, int in_nchw) {
     MDV_PDL_SYNC();
+    const int C = CC ? CC : C_rt, k = KK ? KK : k_rt, ldc = LD ? LD : ldc_rt;
     const long long total = (long long)B * Ho * Wo * ldc;
     const int kk = k * k, K = C * kk;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -357,10 +360,16 @@ extern "C" int mdv_im2col_k(const float* in, int in_nchw, void* col, int col_bf1
     if (!in || !col || k < 1 || stride < 1 || pad < 0 || ldc < C * k * k) return MDV_ERR_ARG;
     const long long total = (long long)B * Ho * Wo * ldc;
     if (total <= 0) return MDV_ERR_ARG;
+#define MDV_I2C(TO_, K_, C_, L_) mdv_launch((im2col_k_kernel<TO_, K_, C_, L_>), dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, in, (TO_*)col, B, Hi, Wi, Ho, Wo, C, k, stride, pad, ldc, in_nchw)
     if (col_bf16)
-        mdv_launch(im2col_k_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, in, (bf16*)col, B, Hi, Wi, Ho, Wo, C, k, stride, pad, ldc, in_nchw);
+        MDV_I2C(bf16, 0, 0, 0);
+    else if (k == 7 && C == 3 && ldc == 152)
+        MDV_I2C(float, 7, 3, 152);      // resnet.conv1
+    else if (k == 7 && C == 2 && ldc == 104)
+        MDV_I2C(float, 7, 2, 104);      // BiFusion_block.spatial
     else
-        mdv_launch(im2col_k_kernel<float>, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, in, (float*)col, B, Hi, Wi, Ho, Wo, C, k, stride, pad, ldc, in_nchw);
+        MDV_I2C(float, 0, 0, 0);
+#undef MDV_I2C
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

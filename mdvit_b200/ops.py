@@ -1625,12 +1625,21 @@ class ConvBnActFn(torch.autograd.Function):
                 colsum(dz, M, Cout, gb)
                 gw, rw = gtarget(w)
                 if gw is not None:
-                    if kind == "k3i":      # the im2col matrix exists only here, in bf16, as the weight-gradient GEMM's operand
+                    if kind == "k3i" and _IMPLICIT_CONV and Cin % 64 == 0 and W <= 64 and 64 % W == 0 and (H * W) % 64 == 0:
+                        # implicit weight-gradient GEMM: B tiles straight from a bf16 copy of the map
+                        gwp = torch.zeros((Cout, ld), dtype=F32, device=dev)
+                        check(lib.mdv_conv3_wgrad(ptr(dz), Cout, ptr(cast_bf16(A, M, Cin)), Cin, B, H, W, Cin, Cout, ptr(gwp), ld, L.stream()),
+                              "mdv_conv3_wgrad")
+                        check(lib.mdv_unperm_conv_grad(ptr(gwp), ld, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
+                        Ab = None
+                    elif kind == "k3i":      # the im2col matrix exists only here, in bf16, as the weight-gradient GEMM's operand
                         Ab = torch.empty((M, ld), dtype=BF16, device=dev)
                         check(lib.mdv_im2col3(ptr(A), 0, ptr(Ab), 1, B, H, W, Ho, Wo, Cin, 1, ld, L.stream()), "mdv_im2col3")
                     else:
                         Ab = cast_bf16(A, M, ld)
-                    if kind in ("k3", "k3i"):
+                    if Ab is None:
+                        pass
+                    elif kind in ("k3", "k3i"):
                         gwp = gemm_tn(dz, Ab, M, Cout, ld, torch.zeros((Cout, ld), dtype=F32, device=dev))
                         check(lib.mdv_unperm_conv_grad(ptr(gwp), ld, ptr(gw), Cout, Cin, L.stream()), "mdv_unperm_conv_grad")
                     elif ld == K:
