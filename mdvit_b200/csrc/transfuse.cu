@@ -7,6 +7,8 @@ namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// element loops index with 32-bit unsigned arithmetic (64-bit divisions by runtime integers cost ~100 instructions each)
+inline bool fits_u32(long long total) { return total > 0 && total < 4000000000LL; }
 inline int grid_for(long long total, int threads = 256) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)MDV_NUM_SMS * 16;
@@ -25,22 +27,25 @@ __global__ void __launch_bounds__(256) im2col_k_kernel(const float* __restrict__
                                                         int Ho, int Wo, int C_rt, int k_rt, int stride, int pad, int ldc_rt, int in_nchw) {
     MDV_PDL_SYNC();
     const int C = CC ? CC : C_rt, k = KK ? KK : k_rt, ldc = LD ? LD : ldc_rt;
-    const long long total = (long long)B * Ho * Wo * ldc;
     const int kk = k * k, K = C * kk;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(idx % ldc);
-        const long long pix = idx / ldc;
-        float v = 0.f;
-        if (q < K) {
-            const int c = q / kk, t = q % kk;
-            const int xo = (int)(pix % Wo);
-            const int yo = (int)((pix / Wo) % Ho);
-            const int b = (int)(pix / ((long long)Wo * Ho));
-            const int yi = yo * stride - pad + t / k, xi = xo * stride - pad + t % k;
-            if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi)
-                v = in_nchw ? __ldg(in + (((size_t)b * C + c) * Hi + yi) * Wi + xi) : __ldg(in + (((size_t)b * Hi + yi) * Wi + xi) * C + c);
+    const int npix = B * Ho * Wo;
+    const int lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+    // one warp per output pixel (its coordinates are decoded once), lanes over the columns: coalesced stores
+    for (int pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += nwarp) {
+        const int xo = pix % Wo, yo = (pix / Wo) % Ho, b = pix / (Wo * Ho);
+        const int y0 = yo * stride - pad, x0 = xo * stride - pad;
+        TO* dst = col + (size_t)pix * ldc;
+        for (int q = lane; q < ldc; q += 32) {
+            float v = 0.f;
+            if (q < K) {
+                const int c = q / kk, t = q - c * kk;
+                const int i = t / k;
+                const int yi = y0 + i, xi = x0 + (t - i * k);
+                if (yi >= 0 && yi < Hi && xi >= 0 && xi < Wi)
+                    v = in_nchw ? __ldg(in + (((size_t)b * C + c) * Hi + yi) * Wi + xi) : __ldg(in + (((size_t)b * Hi + yi) * Wi + xi) * C + c);
+            }
+            stf(dst + q, v);
         }
-        stf(col + idx, v);
     }
 }
 
@@ -50,12 +55,12 @@ __global__ void __launch_bounds__(256) col2im_k_kernel(const float* __restrict__
     MDV_PDL_SYNC();
     const long long total = (long long)B * Hi * Wi * C;
     const int kk = k * k;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = (int)(idx % C);
-        const long long pix = idx / C;
+        const unsigned pix = idx / C;
         const int x = (int)(pix % Wi);
         const int y = (int)((pix / Wi) % Hi);
-        const int b = (int)(pix / ((long long)Wi * Hi));
+        const int b = (int)(pix / (unsigned)(Wi * Hi));
         float a = 0.f;
         for (int i = 0; i < k; ++i) {
             const int t = y + pad - i;
@@ -82,12 +87,12 @@ __global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const float* __rest
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const long long total = (long long)B * Ho * Wo * c4n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = (int)(idx % c4n) * 4;
-        const long long pix = idx / c4n;
+        const unsigned pix = idx / c4n;
         const int xo = (int)(pix % Wo);
         const int yo = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long long)Wo * Ho));
+        const int b = (int)(pix / (unsigned)(Wo * Ho));
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         int am[4] = {0, 0, 0, 0};
         bool first = true;
@@ -117,12 +122,12 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const float* __rest
     MDV_PDL_SYNC();
     const int c4n = C >> 2;
     const long long total = (long long)B * Hi * Wi * c4n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = (int)(idx % c4n) * 4;
-        const long long pix = idx / c4n;
+        const unsigned pix = idx / c4n;
         const int x = (int)(pix % Wi);
         const int y = (int)((pix / Wi) % Hi);
-        const int b = (int)(pix / ((long long)Wi * Hi));
+        const int b = (int)(pix / (unsigned)(Wi * Hi));
         float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -155,20 +160,20 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) add_act_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                                        long long n4, int act) {
     MDV_PDL_SYNC();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 x = ld4(a + i * 4), y = ld4(b + i * 4);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 x = ld4(a + (size_t)i * 4), y = ld4(b + (size_t)i * 4);
         float4 r = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
         if (act == MDV_ACT_RELU) r = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
-        st4(out + i * 4, r);
+        st4(out + (size_t)i * 4, r);
     }
 }
 // dx = dy * act'(.) evaluated from the activation's OUTPUT y (ReLU: y > 0)
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
                                                        long long n4) {
     MDV_PDL_SYNC();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 d = ld4(dy + i * 4), v = ld4(y + i * 4);
-        st4(dx + i * 4, make_float4(v.x > 0.f ? d.x : 0.f, v.y > 0.f ? d.y : 0.f, v.z > 0.f ? d.z : 0.f, v.w > 0.f ? d.w : 0.f));
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 d = ld4(dy + (size_t)i * 4), v = ld4(y + (size_t)i * 4);
+        st4(dx + (size_t)i * 4, make_float4(v.x > 0.f ? d.x : 0.f, v.y > 0.f ? d.y : 0.f, v.z > 0.f ? d.z : 0.f, v.w > 0.f ? d.w : 0.f));
     }
 }
 
@@ -199,12 +204,12 @@ __global__ void __launch_bounds__(256) resize_ac_fwd_kernel(const float* __restr
     MDV_PDL_SYNC();
     const int cn = C / V;
     const long long total = (long long)B * Ho * Wo * cn;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = (int)(idx % cn) * V;
-        const long long pix = idx / cn;
+        const unsigned pix = idx / cn;
         const int xo = (int)(pix % Wo);
         const int yo = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((long long)Wo * Ho));
+        const int b = (int)(pix / (unsigned)(Wo * Ho));
         int y0, y1, x0, x1;
         float ly, lx;
         ac_src(yo, sy, Hi, y0, y1, ly);
@@ -231,12 +236,12 @@ __global__ void __launch_bounds__(256) resize_ac_bwd_kernel(const float* __restr
     MDV_PDL_SYNC();
     const int cn = C / V;
     const long long total = (long long)B * Hi * Wi * cn;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = (int)(idx % cn) * V;
-        const long long pix = idx / cn;
+        const unsigned pix = idx / cn;
         const int x = (int)(pix % Wi);
         const int y = (int)((pix / Wi) % Hi);
-        const int b = (int)(pix / ((long long)Wi * Hi));
+        const int b = (int)(pix / (unsigned)(Wi * Hi));
         // outputs d with source in (y-1, y+1): d in ((y-1)*r, (y+1)*r), r = (n_out-1)/(n_in-1); widened by one on each side
         int ylo = (int)floorf((float)(y - 1) * ry) - 1, yhi = (int)ceilf((float)(y + 1) * ry) + 1;
         int xlo = (int)floorf((float)(x - 1) * rx) - 1, xhi = (int)ceilf((float)(x + 1) * rx) + 1;
@@ -271,9 +276,9 @@ __global__ void __launch_bounds__(256) resize_ac_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) boxsum_rows_kernel(const float* __restrict__ mask, float* __restrict__ tmp, int B, int H, int W, int R) {
     MDV_PDL_SYNC();
     const long long total = (long long)B * H * W;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int x = (int)(idx % W);
-        const float* row = mask + (idx - x);
+        const float* row = mask + ((size_t)idx - x);
         float s = 0.f;
         const int lo = max(x - R, 0), hi = min(x + R, W - 1);
         for (int u = lo; u <= hi; ++u) s += __ldg(row + u);
@@ -285,10 +290,10 @@ __global__ void __launch_bounds__(256) boxsum_cols_weit_kernel(const float* __re
     MDV_PDL_SYNC();
     const long long total = (long long)B * H * W;
     const float inv = 1.f / (float)((2 * R + 1) * (2 * R + 1));
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int x = (int)(idx % W);
         const int y = (int)((idx / W) % H);
-        const float* img = tmp + (idx - (long long)y * W - x);
+        const float* img = tmp + ((size_t)idx - (size_t)y * W - x);
         float s = 0.f;
         const int lo = max(y - R, 0), hi = min(y + R, H - 1);
         for (int v = lo; v <= hi; ++v) s += __ldg(img + (size_t)v * W + x);
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(256) structure_bwd_kernel(const float* __restr
     MDV_PDL_SYNC();
     const long long total = (long long)B * HW;
     const float g = (gout ? gout[0] : 1.f) * coef / (float)B;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int b = (int)(idx / HW);
         const float S0 = (float)sums[b * 4], I1 = (float)(sums[b * 4 + 2] + 1.0), U1 = (float)(sums[b * 4 + 3] - sums[b * 4 + 2] + 1.0);
         const float z = __ldg(pred + idx), m = __ldg(mask + idx), w = __ldg(weit + idx);
@@ -358,8 +363,8 @@ __global__ void __launch_bounds__(256) structure_bwd_kernel(const float* __restr
 extern "C" int mdv_im2col_k(const float* in, int in_nchw, void* col, int col_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, int k,
                             int stride, int pad, int ldc, void* stream) {
     if (!in || !col || k < 1 || stride < 1 || pad < 0 || ldc < C * k * k) return MDV_ERR_ARG;
-    const long long total = (long long)B * Ho * Wo * ldc;
-    if (total <= 0) return MDV_ERR_ARG;
+    const long long total = (long long)B * Ho * Wo * 32;      // one warp per output pixel
+    if (total <= 0 || (long long)B * Ho * Wo >= 2147483647LL) return MDV_ERR_ARG;
 #define MDV_I2C(TO_, K_, C_, L_) mdv_launch((im2col_k_kernel<TO_, K_, C_, L_>), dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, in, (TO_*)col, B, Hi, Wi, Ho, Wo, C, k, stride, pad, ldc, in_nchw)
     if (col_bf16)
         MDV_I2C(bf16, 0, 0, 0);
@@ -377,6 +382,7 @@ extern "C" int mdv_im2col_k(const float* in, int in_nchw, void* col, int col_bf1
 extern "C" int mdv_col2im_k(const float* dcol, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int k, int stride, int pad,
                             int ldc, void* stream) {
     if (!dcol || !dx || k < 1 || stride < 1 || pad < 0 || ldc < C * k * k) return MDV_ERR_ARG;
+    if (!fits_u32((long long)B * Hi * Wi * C)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(col2im_k_kernel, dim3(grid_for((long long)B * Hi * Wi * C)), dim3(256), 0, (cudaStream_t)stream, dcol, dx, B, Hi, Wi, Ho, Wo, C, k, stride, pad, ldc);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -385,6 +391,7 @@ extern "C" int mdv_col2im_k(const float* dcol, float* dx, int B, int Hi, int Wi,
 extern "C" int mdv_maxpool3s2_fwd(const float* in, float* out, void* tap_u8, int B, int Hi, int Wi, int C, void* stream) {
     if (!in || !out || !tap_u8 || (C & 3)) return MDV_ERR_ARG;
     const int Ho = (Hi - 1) / 2 + 1, Wo = (Wi - 1) / 2 + 1;
+    if (!fits_u32((long long)B * Hi * Wi * C)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(maxpool3s2_fwd_kernel, dim3(grid_for((long long)B * Ho * Wo * (C / 4))), dim3(256), 0, (cudaStream_t)stream, in, out, (unsigned char*)tap_u8, B, Hi, Wi, Ho, Wo, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -393,6 +400,7 @@ extern "C" int mdv_maxpool3s2_fwd(const float* in, float* out, void* tap_u8, int
 extern "C" int mdv_maxpool3s2_bwd(const float* dout, const void* tap_u8, float* din, int B, int Hi, int Wi, int C, void* stream) {
     if (!dout || !din || !tap_u8 || (C & 3)) return MDV_ERR_ARG;
     const int Ho = (Hi - 1) / 2 + 1, Wo = (Wi - 1) / 2 + 1;
+    if (!fits_u32((long long)B * Hi * Wi * C)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(maxpool3s2_bwd_kernel, dim3(grid_for((long long)B * Hi * Wi * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dout, (const unsigned char*)tap_u8, din, B, Hi, Wi, Ho, Wo, C);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -400,6 +408,7 @@ extern "C" int mdv_maxpool3s2_bwd(const float* dout, const void* tap_u8, float* 
 
 extern "C" int mdv_add_act(const float* a, const float* b, float* out, long long n, int act, void* stream) {
     if (!a || !b || !out || n <= 0 || (n & 3) || (act != MDV_ACT_NONE && act != MDV_ACT_RELU)) return MDV_ERR_ARG;
+    if (!fits_u32(n / 4)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(add_act_kernel, dim3(grid_for(n / 4)), dim3(256), 0, (cudaStream_t)stream, a, b, out, n / 4, act);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -407,6 +416,7 @@ extern "C" int mdv_add_act(const float* a, const float* b, float* out, long long
 
 extern "C" int mdv_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream) {
     if (!dy || !y || !dx || n <= 0 || (n & 3)) return MDV_ERR_ARG;
+    if (!fits_u32(n / 4)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(act_bwd_kernel, dim3(grid_for(n / 4)), dim3(256), 0, (cudaStream_t)stream, dy, y, dx, n / 4);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
@@ -414,6 +424,7 @@ extern "C" int mdv_relu_bwd(const float* dy, const float* y, float* dx, long lon
 
 extern "C" int mdv_resize_ac_fwd(const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream) {
     if (!in || !out || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1 || C < 1) return MDV_ERR_ARG;
+    if (!fits_u32((long long)B * Ho * Wo * C)) return MDV_ERR_UNSUPPORTED;
     const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
     if (!(C & 3))
         mdv_launch(resize_ac_fwd_kernel<4>, dim3(grid_for((long long)B * Ho * Wo * (C / 4))), dim3(256), 0, (cudaStream_t)stream, in, out, B, Hi, Wi, Ho, Wo, C, sy, sx);
@@ -425,6 +436,7 @@ extern "C" int mdv_resize_ac_fwd(const float* in, float* out, int B, int Hi, int
 
 extern "C" int mdv_resize_ac_bwd(const float* dout, float* din, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream) {
     if (!dout || !din || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1 || C < 1) return MDV_ERR_ARG;
+    if (!fits_u32((long long)B * Ho * Wo * C)) return MDV_ERR_UNSUPPORTED;
     const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
     const float ry = Hi > 1 ? (float)(Ho - 1) / (float)(Hi - 1) : (float)Ho, rx = Wi > 1 ? (float)(Wo - 1) / (float)(Wi - 1) : (float)Wo;
     if (!(C & 3))
@@ -437,6 +449,7 @@ extern "C" int mdv_resize_ac_bwd(const float* dout, float* din, int B, int Hi, i
 
 extern "C" int mdv_structure_weit(const float* mask, float* weit, float* ws, int B, int H, int W, void* stream) {
     if (!mask || !weit || !ws || B < 1 || H < 1 || W < 1) return MDV_ERR_ARG;
+    if (!fits_u32((long long)B * H * W)) return MDV_ERR_UNSUPPORTED;
     const long long total = (long long)B * H * W;
     mdv_launch(boxsum_rows_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, mask, ws, B, H, W, 15);
     MDV_CHECK_LAUNCH();
@@ -462,6 +475,7 @@ extern "C" int mdv_structure_loss_fwd(const float* pred, const float* mask, cons
 extern "C" int mdv_structure_loss_bwd(const float* pred, const float* mask, const float* weit, const void* sums, const float* gout, float coef,
                                       float* dpred, int B, int HW, int accumulate, void* stream) {
     if (!pred || !mask || !weit || !sums || !dpred || B < 1 || HW < 1) return MDV_ERR_ARG;
+    if (!fits_u32((long long)B * HW)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(structure_bwd_kernel, dim3(grid_for((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, pred, mask, weit, (const double*)sums, gout, coef, dpred, B, HW, accumulate);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
