@@ -249,6 +249,22 @@ int mdv_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* 
  * TransFuse.py:262-264) and its exact transpose (gather form, deterministic) */
 int mdv_resize_ac_fwd(const float* in, float* out, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream);
 int mdv_resize_ac_bwd(const float* dout, float* din, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream);
+/* Gates of BiFusion_block / Attention_block and the concat that follows them, one pass (TransFuse.py:63-73,620):
+ *   out[m, :] = [ g[m, :C1] * pgate[m]  |  x[m, :C2] * vgate[m / rows_per_sample, :C2]  |  bp[m, :C3] ]
+ * pgate [M] (spatial / psi gate) and vgate [B, C2] (squeeze-and-excitation gate) are the values AFTER their sigmoids.  C2 = C3 = 0
+ * (x, vgate, bp NULL) is Attention_block's `x * psi`.  Channel counts % 4 == 0, C2 <= 512.
+ * _bwd: dg = dout1 * pgate, dp[m] = sum_c dout1 g, dx = dout2 * vgate, dv[b, c] = sum_{m in b} dout2 x (written), dbp = dout3. */
+int mdv_gate_cat_fwd(const float* g, const float* pgate, const float* x, const float* vgate, const float* bp, float* out, int M, int C1,
+                     int C2, int C3, int rows_per_sample, void* stream);
+int mdv_gate_cat_bwd(const float* dout, const float* g, const float* pgate, const float* x, const float* vgate, float* dg, float* dp, float* dx,
+                     float* dv, float* dbp, int M, int C1, int C2, int C3, int rows_per_sample, void* stream);
+/* ChannelPool (TransFuse.py:20-22): out[m] = (max_c x[m,c], mean_c x[m,c]); arg_i32 [M] = first maximal channel (torch.max's gradient
+ * routing).  _bwd: dx[m,c] = dout[m,1] / C + (c == arg[m]) dout[m,0]. */
+int mdv_channel_pool_fwd(const float* x, float* out, void* arg_i32, int M, int C, void* stream);
+int mdv_channel_pool_bwd(const float* dout, const void* arg_i32, float* dx, int M, int C, void* stream);
+/* nn.Dropout2d (TransFuse.py:217,226-245) on an NHWC map: out = x * mask(b, c) / (1 - p), mask a function of (rng, drop_stream, b*C + c);
+ * the backward is the same call on the gradient.  C % 4 == 0. */
+int mdv_dropout2d(const float* x, float* out, int M, int C, int rows_per_sample, float p, const void* rng, uint32_t drop_stream, void* stream);
 /* structure_loss (multi_train_TransFuse.py:29-38): weit = 1 + 5 |avg_pool2d(mask, 31, 1, 15) - mask| (ws: B*H*W floats);
  * loss = mean_b( sum(weit*bce)/sum(weit) + 1 - (I+1)/(U-I+1) ), I = sum(sigmoid(pred)*mask*weit), U = sum((sigmoid(pred)+mask)*weit).
  * sums: DEVICE double[4*B] (per sample: sum weit, sum weit*bce, I, U), written by _fwd, read by _bwd;

@@ -270,6 +270,149 @@ __global__ void __launch_bounds__(256) resize_ac_bwd_kernel(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------- gates of BiFusion_block / Attention_block
+// out[m, :] = [ g[m, :] * p[m]  |  x[m, :] * v[b(m), :]  |  bp[m, :] ]      (TransFuse.py:63-73: sigmoid(spatial) * g_in, sigmoid(fc2) * x_in,
+// torch.cat([g, x, bp], 1); Attention_block `x * psi`, TransFuse.py:620, is the first part alone).  p [M] and v [B, C2] are the
+// gates AFTER their sigmoids.  One warp per row, float4 lanes over the concatenated channels.
+__global__ void __launch_bounds__(256) gate_cat_fwd_kernel(const float* __restrict__ g, const float* __restrict__ pg, const float* __restrict__ x,
+                                                            const float* __restrict__ v, const float* __restrict__ bp, float* __restrict__ out,
+                                                            int M, int C1, int C2, int C3, int rows_per_sample) {
+    MDV_PDL_SYNC();
+    const int Ct = C1 + C2 + C3, n4 = Ct >> 2;
+    const int lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += nwarp) {
+        const float pm = __ldg(pg + m);
+        const float* vb = v ? v + (size_t)(m / rows_per_sample) * C2 : nullptr;
+        for (int q = lane; q < n4; q += 32) {
+            const int c = q << 2;
+            float4 r;
+            if (c < C1) {
+                r = ld4(g + (size_t)m * C1 + c);
+                r.x *= pm; r.y *= pm; r.z *= pm; r.w *= pm;
+            } else if (c < C1 + C2) {
+                r = ld4(x + (size_t)m * C2 + (c - C1));
+                const float4 w = ld4(vb + (c - C1));
+                r.x *= w.x; r.y *= w.y; r.z *= w.z; r.w *= w.w;
+            } else {
+                r = ld4(bp + (size_t)m * C3 + (c - C1 - C2));
+            }
+            st4(out + (size_t)m * Ct + c, r);
+        }
+    }
+}
+// dg = dout1 * p;  dp[m] = sum_c dout1 g;  dx = dout2 * v;  dv[b, c] += sum_{m in b} dout2 x;  dbp = dout3.
+// A warp owns a band of consecutive rows of one sample and keeps its dv partial sums in registers (C2 <= 512).
+__global__ void __launch_bounds__(256) gate_cat_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ g, const float* __restrict__ pg,
+                                                            const float* __restrict__ x, const float* __restrict__ v, float* __restrict__ dg,
+                                                            float* __restrict__ dp, float* __restrict__ dx, float* __restrict__ dv,
+                                                            float* __restrict__ dbp, int M, int C1, int C2, int C3, int rows_per_sample, int band) {
+    MDV_PDL_SYNC();
+    const int Ct = C1 + C2 + C3;
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int bands_per_sample = (rows_per_sample + band - 1) / band;
+    const int b = wid / bands_per_sample;
+    const int r0 = b * rows_per_sample + (wid - b * bands_per_sample) * band;
+    if (r0 >= M) return;
+    const int r1 = min(min(r0 + band, (b + 1) * rows_per_sample), M);
+    float4 acc[4];      // dv partial sums of this lane's chunks (C2 / 4 / 32 <= 4)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* vb = v ? v + (size_t)b * C2 : nullptr;
+    for (int m = r0; m < r1; ++m) {
+        const float pm = __ldg(pg + m);
+        const float* d = dout + (size_t)m * Ct;
+        float dot = 0.f;
+        for (int c = lane << 2; c < C1; c += 128) {
+            const float4 dd = ld4(d + c), gg = ld4(g + (size_t)m * C1 + c);
+            dot += dd.x * gg.x + dd.y * gg.y + dd.z * gg.z + dd.w * gg.w;
+            st4(dg + (size_t)m * C1 + c, make_float4(dd.x * pm, dd.y * pm, dd.z * pm, dd.w * pm));
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) dp[m] = dot;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = (lane << 2) + i * 128;
+            if (c < C2) {
+                const float4 dd = ld4(d + C1 + c), xx = ld4(x + (size_t)m * C2 + c), w = ld4(vb + c);
+                acc[i].x += dd.x * xx.x; acc[i].y += dd.y * xx.y; acc[i].z += dd.z * xx.z; acc[i].w += dd.w * xx.w;
+                st4(dx + (size_t)m * C2 + c, make_float4(dd.x * w.x, dd.y * w.y, dd.z * w.z, dd.w * w.w));
+            }
+        }
+        for (int c = lane << 2; c < C3; c += 128) st4(dbp + (size_t)m * C3 + c, ld4(d + C1 + C2 + c));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = (lane << 2) + i * 128;
+        if (c < C2) {
+            atomicAdd(dv + (size_t)b * C2 + c, acc[i].x);
+            atomicAdd(dv + (size_t)b * C2 + c + 1, acc[i].y);
+            atomicAdd(dv + (size_t)b * C2 + c + 2, acc[i].z);
+            atomicAdd(dv + (size_t)b * C2 + c + 3, acc[i].w);
+        }
+    }
+}
+
+// ChannelPool (TransFuse.py:20-22): out[m] = (max_c x[m, c], mean_c x[m, c]); arg[m] = first maximal channel (where torch.max sends
+// the gradient).  One warp per row.
+__global__ void __launch_bounds__(256) channel_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int* __restrict__ arg, int M, int C) {
+    MDV_PDL_SYNC();
+    const int lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += nwarp) {
+        float mx = -INFINITY, sum = 0.f;
+        int am = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float t = __ldg(x + (size_t)m * C + c);
+            sum += t;
+            if (t > mx) { mx = t; am = c; }
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+            if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+        }
+        if (lane == 0) {
+            out[(size_t)m * 2] = mx;
+            out[(size_t)m * 2 + 1] = sum / (float)C;
+            arg[m] = am;
+        }
+    }
+}
+// dx[m, c] = dout[m, 1] / C + (c == arg[m]) dout[m, 0]
+__global__ void __launch_bounds__(256) channel_pool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, float* __restrict__ dx,
+                                                                int M, int C) {
+    MDV_PDL_SYNC();
+    const unsigned total = (unsigned)M * (unsigned)C;
+    const float inv = 1.f / (float)C;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned m = idx / (unsigned)C;
+        const int c = (int)(idx - m * (unsigned)C);
+        dx[idx] = __ldg(dout + (size_t)m * 2 + 1) * inv + (c == __ldg(arg + m) ? __ldg(dout + (size_t)m * 2) : 0.f);
+    }
+}
+
+// nn.Dropout2d on an NHWC map: whole (sample, channel) planes, mask = f(rng, stream, b*C + c) as in the rowdot kernels; the
+// backward is the same call on the gradient.
+__global__ void __launch_bounds__(256) dropout2d_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int C, int rows_per_sample,
+                                                         float p, const unsigned long long* __restrict__ rng, uint32_t stream) {
+    MDV_PDL_SYNC();
+    const uint32_t thr = drop_thresh(p), key = rng_key(rng, stream);
+    const float inv = 1.f / (1.f - p);
+    const int c4n = C >> 2;
+    const unsigned total = (unsigned)M * (unsigned)c4n;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned m = idx / (unsigned)c4n;
+        const int c = (int)(idx - m * (unsigned)c4n) << 2;
+        const unsigned long long e = (unsigned long long)(m / (unsigned)rows_per_sample) * C + c;
+        const uint32_t h0 = drop_hash(key, (uint32_t)(e >> 1)), h1 = drop_hash(key, (uint32_t)(e >> 1) + 1);      // c % 4 == 0: pairs (c, c+1), (c+2, c+3)
+        float4 v = ld4(x + (size_t)m * C + c);
+        v.x *= drop_lo(h0, thr, inv); v.y *= drop_hi(h0, thr, inv); v.z *= drop_lo(h1, thr, inv); v.w *= drop_hi(h1, thr, inv);
+        st4(out + (size_t)m * C + c, v);
+    }
+}
+
 // ---------------------------------------------------------------------------------- structure_loss (multi_train_TransFuse.py:29-38)
 // weit = 1 + 5 |avg_pool2d(mask, 31, stride 1, padding 15) - mask|   (count_include_pad: always / 961).
 // Separable running sums: one block per (sample, row strip); rows first into shared memory, then columns.
@@ -477,6 +620,58 @@ extern "C" int mdv_structure_loss_bwd(const float* pred, const float* mask, cons
     if (!pred || !mask || !weit || !sums || !dpred || B < 1 || HW < 1) return MDV_ERR_ARG;
     if (!fits_u32((long long)B * HW)) return MDV_ERR_UNSUPPORTED;
     mdv_launch(structure_bwd_kernel, dim3(grid_for((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, pred, mask, weit, (const double*)sums, gout, coef, dpred, B, HW, accumulate);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_gate_cat_fwd(const float* g, const float* pgate, const float* x, const float* vgate, const float* bp, float* out, int M,
+                                int C1, int C2, int C3, int rows_per_sample, void* stream) {
+    if (!g || !pgate || !out || M <= 0 || C1 <= 0 || (C1 & 3) || (C2 & 3) || (C3 & 3) || rows_per_sample <= 0) return MDV_ERR_ARG;
+    if ((C2 && (!x || !vgate)) || (C3 && !bp) || C2 > 512) return MDV_ERR_ARG;
+    mdv_launch(gate_cat_fwd_kernel, dim3(grid_for((long long)M * 32)), dim3(256), 0, (cudaStream_t)stream, g, pgate, x, vgate, bp, out, M, C1, C2, C3, rows_per_sample);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_gate_cat_bwd(const float* dout, const float* g, const float* pgate, const float* x, const float* vgate, float* dg, float* dp,
+                                float* dx, float* dv, float* dbp, int M, int C1, int C2, int C3, int rows_per_sample, void* stream) {
+    if (!dout || !g || !pgate || !dg || !dp || M <= 0 || C1 <= 0 || (C1 & 3) || (C2 & 3) || (C3 & 3) || rows_per_sample <= 0) return MDV_ERR_ARG;
+    if ((C2 && (!x || !vgate || !dx || !dv)) || (C3 && !dbp) || C2 > 512 || (M % rows_per_sample)) return MDV_ERR_ARG;
+    if (C2) {
+        cudaError_t e = cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)(M / rows_per_sample) * C2, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // bands of rows per warp: enough warps to fill the machine, long enough to amortise the dv atomics
+    int band = rows_per_sample;
+    while (band > 16 && (long long)(M / rows_per_sample) * ((rows_per_sample + band / 2 - 1) / (band / 2)) <= (long long)MDV_NUM_SMS * 64) band /= 2;
+    const long long warps = (long long)(M / rows_per_sample) * ((rows_per_sample + band - 1) / band);
+    mdv_launch(gate_cat_bwd_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, dout, g, pgate, x, vgate, dg, dp, dx, dv,
+               dbp, M, C1, C2, C3, rows_per_sample, band);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_channel_pool_fwd(const float* x, float* out, void* arg_i32, int M, int C, void* stream) {
+    if (!x || !out || !arg_i32 || M <= 0 || C <= 0) return MDV_ERR_ARG;
+    mdv_launch(channel_pool_fwd_kernel, dim3(grid_for((long long)M * 32)), dim3(256), 0, (cudaStream_t)stream, x, out, (int*)arg_i32, M, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_channel_pool_bwd(const float* dout, const void* arg_i32, float* dx, int M, int C, void* stream) {
+    if (!dout || !dx || !arg_i32 || M <= 0 || C <= 0) return MDV_ERR_ARG;
+    if (!fits_u32((long long)M * C)) return MDV_ERR_UNSUPPORTED;
+    mdv_launch(channel_pool_bwd_kernel, dim3(grid_for((long long)M * C)), dim3(256), 0, (cudaStream_t)stream, dout, (const int*)arg_i32, dx, M, C);
+    MDV_CHECK_LAUNCH();
+    return MDV_OK;
+}
+
+extern "C" int mdv_dropout2d(const float* x, float* out, int M, int C, int rows_per_sample, float p, const void* rng, uint32_t drop_stream,
+                             void* stream) {
+    if (!x || !out || !rng || M <= 0 || C <= 0 || (C & 3) || rows_per_sample <= 0 || !(p > 0.f) || !(p < 1.f)) return MDV_ERR_ARG;
+    if (!fits_u32((long long)M * C)) return MDV_ERR_UNSUPPORTED;
+    mdv_launch(dropout2d_kernel, dim3(grid_for((long long)M * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, out, M, C, rows_per_sample, p,
+               (const unsigned long long*)rng, drop_stream);
     MDV_CHECK_LAUNCH();
     return MDV_OK;
 }

@@ -1800,3 +1800,90 @@ def structure_loss(pred, mask, weit=None, per_sample=False):
         weit = structure_weit(mask)
     loss, ps = StructureLossFn.apply(pred, mask, weit)
     return (loss, ps) if per_sample else loss
+
+
+class GateCatFn(torch.autograd.Function):
+    """[ g * p | x * v | bp ] in one pass: the spatial / channel gates of BiFusion_block and the concat feeding its Residual block
+    (TransFuse.py:63-73); with x = v = bp = None, Attention_block's `x * psi` (TransFuse.py:620).  g [B,N,C1], p [B,N,1] (after its
+    sigmoid), x [B,N,C2], v [B,C2] (after its sigmoid), bp [B,N,C3]."""
+
+    @staticmethod
+    def forward(ctx, g, p, x, v, bp):
+        B, N, C1 = g.shape
+        C2 = x.shape[2] if x is not None else 0
+        C3 = bp.shape[2] if bp is not None else 0
+        g, p = _contig(g), _contig(p)
+        x, v, bp = (_contig(t) if t is not None else None for t in (x, v, bp))
+        out = torch.empty((B, N, C1 + C2 + C3), dtype=F32, device=g.device)
+        with _dev_ctx(g):
+            check(L.lib().mdv_gate_cat_fwd(ptr(g), ptr(p), ptr(x), ptr(v), ptr(bp), ptr(out), B * N, C1, C2, C3, N, L.stream()), "mdv_gate_cat_fwd")
+        ctx.save_for_backward(g, p, x, v)
+        ctx.meta = (B, N, C1, C2, C3)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g, p, x, v = ctx.saved_tensors
+        B, N, C1, C2, C3 = ctx.meta
+        dev = dout.device
+        dout = _contig(dout.float())
+        dg = torch.empty((B, N, C1), dtype=F32, device=dev)
+        dp = torch.empty((B, N, 1), dtype=F32, device=dev)
+        dx = torch.empty((B, N, C2), dtype=F32, device=dev) if C2 else None
+        dv = torch.empty((B, C2), dtype=F32, device=dev) if C2 else None
+        dbp = torch.empty((B, N, C3), dtype=F32, device=dev) if C3 else None
+        with _dev_ctx(dout):
+            check(L.lib().mdv_gate_cat_bwd(ptr(dout), ptr(g), ptr(p), ptr(x), ptr(v), ptr(dg), ptr(dp), ptr(dx), ptr(dv), ptr(dbp), B * N, C1, C2, C3,
+                                           N, L.stream()), "mdv_gate_cat_bwd")
+        return dg, dp, dx, dv, dbp
+
+
+class ChannelPoolFn(torch.autograd.Function):
+    """ChannelPool (TransFuse.py:20-22) on an NHWC map: [B,N,C] -> [B,N,2] = (max over channels, mean over channels)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, N, C = x.shape
+        x = _contig(x)
+        out = torch.empty((B, N, 2), dtype=F32, device=x.device)
+        arg = torch.empty((B, N), dtype=torch.int32, device=x.device)
+        with _dev_ctx(x):
+            check(L.lib().mdv_channel_pool_fwd(ptr(x), ptr(out), ptr(arg), B * N, C, L.stream()), "mdv_channel_pool_fwd")
+        ctx.save_for_backward(arg)
+        ctx.meta = (B, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        B, N, C = ctx.meta
+        dout = _contig(dout.float())
+        dx = torch.empty((B, N, C), dtype=F32, device=dout.device)
+        with _dev_ctx(dout):
+            check(L.lib().mdv_channel_pool_bwd(ptr(dout), ptr(arg), ptr(dx), B * N, C, L.stream()), "mdv_channel_pool_bwd")
+        return dx
+
+
+class Dropout2dFn(torch.autograd.Function):
+    """nn.Dropout2d on an NHWC map (TransFuse.py:217,226-245): whole (sample, channel) planes; the mask is regenerated in backward
+    from the counter-based RNG (rng_tensor: seed, step) and this call's stream id."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        B, N, C = x.shape
+        x = _contig(x)
+        sid = new_stream_id()
+        out = torch.empty_like(x)
+        with _dev_ctx(x):
+            check(L.lib().mdv_dropout2d(ptr(x), ptr(out), B * N, C, N, ctypes.c_float(p), ptr(rng_tensor(x.device)), sid, L.stream()), "mdv_dropout2d")
+        ctx.meta = (B, N, C, float(p), sid)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, N, C, p, sid = ctx.meta
+        dout = _contig(dout.float())
+        dx = torch.empty_like(dout)
+        with _dev_ctx(dout):
+            check(L.lib().mdv_dropout2d(ptr(dout), ptr(dx), B * N, C, N, ctypes.c_float(p), ptr(rng_tensor(dout.device)), sid, L.stream()), "mdv_dropout2d")
+        return dx, None

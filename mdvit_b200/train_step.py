@@ -542,6 +542,9 @@ class TransFuseTrainer:
             check(L.lib().mdv_adamw(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.hyper), self.total, L.stream()),
                   "mdv_adamw")
             ops.rng_bump(self.device)
+            mirror = getattr(self, "mirror", None)
+            if mirror is not None and mirror.table is not None:
+                mirror.refresh()          # GEMM operand copies of the updated weights, one launch
         return losses.detach()
 
     def step(self, batches):
@@ -552,16 +555,20 @@ class TransFuseTrainer:
         return [self.flat, self.m, self.v, self.hyper, ops.rng_tensor(self.device)] + [b for b in self.model.buffers()]
 
     def capture(self, example_batches, warmup=2):
-        """Capture the step into one CUDA graph over static input buffers; the training state is restored afterwards.  Weight
-        operand copies are re-derived inside the graph (ops.prep_weight is keyed on the weight epoch, bumped per capture)."""
+        """Capture the step into one CUDA graph over static input buffers; the training state is restored afterwards."""
         self.static = [(img.clone(), mask.clone(), d) for img, mask, d in example_batches]
         saved = [t.clone() for t in self._state_tensors()]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
+        # the GEMM operand copies of the weights (bf16 / TF32 layouts, ~190 per step) become persistent buffers refreshed by one
+        # launch after AdamW (ops.WeightMirror) instead of one conversion launch each
+        self.mirror = ops.WeightMirror()
+        ops.set_weight_mirror(self.mirror)
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
                 ops.bump_weight_epoch()
                 self._step_body(self.static)
+            self.mirror.freeze(self.device)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
@@ -574,6 +581,7 @@ class TransFuseTrainer:
         with torch.no_grad():
             for t, s in zip(self._state_tensors(), saved):
                 t.copy_(s)
+            self.mirror.refresh()
         return self
 
     def step_graph(self, batches=None):

@@ -188,9 +188,9 @@ def deit_small_patch16_224_adapt(pretrained=False, pretrained_folder=None, num_d
 # (init_weights, Up, Attention_block, DoubleConv, Residual, Conv).  Same class names, constructor signatures, registration
 # order (=> the same state_dict keys and, under one seed, the same initial weights) and forward signatures.  Inside, maps are
 # NHWC fp32 ([B, H*W, C]); every convolution / BatchNorm / pooling / resize is a C-ABI kernel (ops.ConvBnActFn, ops.BnActFn,
-# ops.MaxPool3s2Fn, ops.ResizeACFn); the per-pixel / per-sample gates of BiFusion_block and Attention_block (sigmoid gates,
-# channel max / mean, the squeeze-and-excitation Linears on [B, C], the two single-channel BatchNorms) are torch tensor
-# expressions on those maps.  Each block's `forward` keeps the reference's NCHW signature; `run` is the NHWC form the model
+# ops.MaxPool3s2Fn, ops.ResizeACFn, ops.GateCatFn, ops.ChannelPoolFn, ops.Dropout2dFn); what remains as torch tensor expressions are
+# the small per-pixel / per-sample pieces (the squeeze-and-excitation mean + Linears on [B, C], the two single-channel
+# BatchNorms + sigmoids on [B, H*W, 1]) and the W_g * W_x product / Up-block concatenations.  Each block's `forward` keeps the reference's NCHW signature; `run` is the NHWC form the model
 # chains internally.
 import torch.nn.functional as F
 
@@ -258,14 +258,12 @@ def _drop2d(x, p, training):
     """nn.Dropout2d on an NHWC map: whole (sample, channel) planes"""
     if p <= 0. or not training:
         return x
-    B, _, C = x.shape
-    keep = (torch.rand((B, 1, C), device=x.device) >= p).to(x.dtype) / (1. - p)
-    return x * keep
+    return ops.Dropout2dFn.apply(x, float(p))
 
 
 class ChannelPool(nn.Module):
     def run(self, x):
-        return torch.cat((x.max(dim=2, keepdim=True)[0], x.mean(dim=2, keepdim=True)), dim=2)
+        return ops.ChannelPoolFn.apply(x)
 
     def forward(self, x):
         return torch.cat((torch.max(x, 1)[0].unsqueeze(1), torch.mean(x, 1).unsqueeze(1)), dim=1)
@@ -366,7 +364,7 @@ class Attention_block(nn.Module):
         s, _, _ = _cba(x, H, W, self.W_x[0], self.W_x[1], ACT_RELU, g1)      # relu(g1 + x1)
         p, _, _ = _cba(s, H, W, self.psi[0])
         p = torch.sigmoid(_bn1(p, self.psi[1], H, W))
-        return x * p
+        return ops.GateCatFn.apply(x, p, None, None, None)      # x * psi
 
     def forward(self, g, x):
         gt, H, W = _to_nhwc(g)
@@ -426,15 +424,14 @@ class BiFusion_block(nn.Module):
         W_g, _, _ = self.W_g.run(g, H, W)
         W_x, _, _ = self.W_x.run(x, H, W)
         bp, _, _ = self.W.run(W_g * W_x, H, W)
-        # spatial attention for cnn branch
+        # spatial attention for cnn branch: per-pixel gate sigmoid(BN(conv7x7(ChannelPool(g))))
         s, _, _ = self.spatial.run(self.compress.run(g), H, W)
-        g = torch.sigmoid(s) * g
         # channel attention for transformer branch (the 1x1 convs act on the [B, C] pooled vector)
         v = x.mean(dim=1)
         v = torch.relu(F.linear(v, self.fc1.weight.flatten(1), self.fc1.bias))
         v = torch.sigmoid(F.linear(v, self.fc2.weight.flatten(1), self.fc2.bias))
-        x = v.unsqueeze(1) * x
-        fuse = self.residual.run(torch.cat([g, x, bp], dim=2), H, W)
+        # both gates and torch.cat([g, x, bp], 1) in one kernel
+        fuse = self.residual.run(ops.GateCatFn.apply(g, torch.sigmoid(s), x, v, bp), H, W)
         return _drop2d(fuse, self.drop_rate, self.training)
 
     def forward(self, g, x):

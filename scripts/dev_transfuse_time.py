@@ -86,7 +86,8 @@ def main():
         run_mine()
         print(L.profile_report(40))
     # ---- the same module through stock PyTorch
-    for name, cls in (("ConvBnActFn", W._EmuConv), ("BnActFn", W._EmuBn), ("MaxPool3s2Fn", W._EmuPool), ("ResizeACFn", W._EmuResize)):
+    for name, cls in (("ConvBnActFn", W._EmuConv), ("BnActFn", W._EmuBn), ("MaxPool3s2Fn", W._EmuPool), ("ResizeACFn", W._EmuResize),
+                     ("GateCatFn", W._EmuGateCat), ("ChannelPoolFn", W._EmuChannelPool)):
         setattr(ops, name, cls)
     T.DeiT_adapt.forward = lambda self, imgs, label: W.deit_forward_torch(self, imgs, label)
 

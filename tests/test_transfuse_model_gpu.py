@@ -249,10 +249,11 @@ def trained_once():
         m.train()
     # stock PyTorch, TF32 convolutions / matmuls allowed (its default for cuDNN), same initial state
     m.load_state_dict(init)
-    saved = {n: getattr(ops, n) for n in ("ConvBnActFn", "BnActFn", "MaxPool3s2Fn", "ResizeACFn")}
+    saved = {n: getattr(ops, n) for n in ("ConvBnActFn", "BnActFn", "MaxPool3s2Fn", "ResizeACFn", "GateCatFn", "ChannelPoolFn")}
     fwd = T.DeiT_adapt.forward
     try:
-        for n, c in (("ConvBnActFn", W._EmuConv), ("BnActFn", W._EmuBn), ("MaxPool3s2Fn", W._EmuPool), ("ResizeACFn", W._EmuResize)):
+        for n, c in (("ConvBnActFn", W._EmuConv), ("BnActFn", W._EmuBn), ("MaxPool3s2Fn", W._EmuPool), ("ResizeACFn", W._EmuResize),
+                     ("GateCatFn", W._EmuGateCat), ("ChannelPoolFn", W._EmuChannelPool)):
             setattr(ops, n, c)
         T.DeiT_adapt.forward = lambda self, imgs, label: W.deit_forward_torch(self, imgs, label)
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -378,3 +379,65 @@ def test_stacked_multi_dataset_forward_matches_consecutive_forwards_on_gpu():
         assert rel(a, b) < 1e-2, rel(a, b)
     for k in bufs[0]:
         assert rel(bufs[0][k], bufs[1][k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("shape", [(3, 256, 256, 384, 256), (2, 4096, 64, 64, 64), (5, 100, 128, 0, 0), (2, 64, 32, 512, 8)])
+def test_gate_cat_fwd_bwd_vs_torch(shape):
+    """BiFusion_block's two gates + concat (and Attention_block's x * psi: C2 = C3 = 0) against the torch expression"""
+    from mdvit_b200 import ops
+    from tests.test_transfuse_wiring import _EmuGateCat
+    dev = _dev()
+    B, N, C1, C2, C3 = shape
+    g = torch.randn(B, N, C1, device=dev).requires_grad_(True)
+    p = torch.rand(B, N, 1, device=dev).requires_grad_(True)
+    x = torch.randn(B, N, C2, device=dev).requires_grad_(True) if C2 else None
+    v = torch.rand(B, C2, device=dev).requires_grad_(True) if C2 else None
+    bp = torch.randn(B, N, C3, device=dev).requires_grad_(True) if C3 else None
+    probe = torch.randn(B, N, C1 + C2 + C3, device=dev)
+    res = []
+    for fn in (ops.GateCatFn, _EmuGateCat):
+        for t in (g, p, x, v, bp):
+            if t is not None:
+                t.grad = None
+        y = fn.apply(g, p, x, v, bp)
+        (y * probe).sum().backward()
+        res.append([y.detach()] + [t.grad.clone() for t in (g, p, x, v, bp) if t is not None])
+    for a, b in zip(*res):
+        assert a.shape == b.shape and rel(a, b) < 1e-5, rel(a, b)
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 256), (3, 100, 64), (1, 33, 5)])
+def test_channel_pool_fwd_bwd_vs_torch(shape):
+    from mdvit_b200 import ops
+    from tests.test_transfuse_wiring import _EmuChannelPool
+    dev = _dev()
+    x = torch.randn(*shape, device=dev).requires_grad_(True)
+    probe = torch.randn(shape[0], shape[1], 2, device=dev)
+    res = []
+    for fn in (ops.ChannelPoolFn, _EmuChannelPool):
+        x.grad = None
+        y = fn.apply(x)
+        (y * probe).sum().backward()
+        res.append((y.detach(), x.grad.clone()))
+    assert torch.equal(res[0][0][..., 0], res[1][0][..., 0]) and rel(res[0][0], res[1][0]) < 1e-6
+    assert rel(res[0][1], res[1][1]) < 1e-6
+
+
+def test_dropout2d_drops_whole_planes_and_backward_reuses_the_mask():
+    from mdvit_b200 import ops
+    dev = _dev()
+    ops.manual_seed(11, dev)
+    ops.reset_stream_ids()
+    B, N, C, p = 64, 50, 128, 0.2
+    x = (torch.rand(B, N, C, device=dev) + 0.5).requires_grad_(True)
+    y = ops.Dropout2dFn.apply(x, p)
+    ratio = (y / x.detach())                                   # 0 or 1/(1-p), constant over the N pixels of a (sample, channel) plane
+    assert torch.allclose(ratio, ratio[:, :1, :].expand_as(ratio))
+    plane = ratio[:, 0, :]
+    kept = plane > 0
+    assert torch.allclose(plane[kept], torch.full_like(plane[kept], 1 / (1 - p)), rtol=1e-6)
+    assert abs((~kept).float().mean().item() - p) < 0.02       # 8192 planes: sigma = 0.0044
+    y.sum().backward()
+    assert torch.allclose(x.grad, ratio)                       # same mask in backward
+    y2 = ops.Dropout2dFn.apply(x, p)                           # another call site -> another stream id -> another mask
+    assert not torch.equal(y2 > 0, y > 0)

@@ -66,6 +66,23 @@ class _EmuResize:
         return y.permute(0, 2, 3, 1).reshape(B, -1, C)
 
 
+class _EmuGateCat:
+    @staticmethod
+    def apply(g, p, x, v, bp):
+        parts = [g * p]
+        if x is not None:
+            parts.append(x * v.unsqueeze(1))
+        if bp is not None:
+            parts.append(bp)
+        return torch.cat(parts, dim=2) if len(parts) > 1 else parts[0]
+
+
+class _EmuChannelPool:
+    @staticmethod
+    def apply(x):
+        return torch.cat((x.max(dim=2, keepdim=True)[0], x.mean(dim=2, keepdim=True)), dim=2)
+
+
 def deit_forward_torch(tr, imgs, label):
     """plain-torch DeiT-S-adapt forward over the module's parameters (vision_transformer.py:125-211,322-389; DeiT.py:116-139)"""
     x = F.conv2d(imgs, tr.patch_embed.proj.weight, tr.patch_embed.proj.bias, stride=16).flatten(2).transpose(1, 2) + tr.pos_embed
@@ -90,6 +107,8 @@ def emulated(monkeypatch):
     monkeypatch.setattr(ops, "BnActFn", _EmuBn)
     monkeypatch.setattr(ops, "MaxPool3s2Fn", _EmuPool)
     monkeypatch.setattr(ops, "ResizeACFn", _EmuResize)
+    monkeypatch.setattr(ops, "GateCatFn", _EmuGateCat)
+    monkeypatch.setattr(ops, "ChannelPoolFn", _EmuChannelPool)
     monkeypatch.setattr(T.DeiT_adapt, "forward", lambda self, imgs, label: deit_forward_torch(self, imgs, label))
 
 
