@@ -464,6 +464,7 @@ class TransFuseTrainer:
         self.fuse_datasets = fuse_datasets      # stack the dataset mini-batches into one pass (TransFuse_S_adapt.forward_multi)
         self._onehot_cache = {}
         self._total_loss = None
+        self.last_logits = []      # per dataset: map_2 logits of the last forward (detached)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.num_domains = num_domains
@@ -497,12 +498,14 @@ class TransFuseTrainer:
 
     def forward_losses(self, batches):
         """batches: [(img [B,3,H,W], mask [B,1,H,W] fp32 or uint8, domain index)] -> per-dataset losses [n]"""
+        self.last_logits = []
         if self.fuse_datasets and len(batches) > 1 and len({tuple(b[0].shape) for b in batches}) == 1:
             return self._forward_losses_fused(batches)
         losses = []
         for img, mask, d in batches:
             mask = mask.float()
             map_x, map_1, map_2 = self.model(img, self._onehot(img.shape[0], d))
+            self.last_logits.append(map_2.detach())      # the prediction the trainer scores (multi_train_TransFuse.py:167,175-181)
             weit = ops.structure_weit(mask)      # shared by the three maps
             losses.append(0.5 * ops.structure_loss(map_2, mask, weit) + 0.3 * ops.structure_loss(map_1, mask, weit)
                           + 0.2 * ops.structure_loss(map_x, mask, weit))
@@ -520,6 +523,7 @@ class TransFuseTrainer:
         if dl is None:
             dl = self._onehot_cache[key] = torch.cat([self._onehot(B, b[2]) for b in batches], dim=0)
         map_x, map_1, map_2 = self.model.forward_multi(x, dl, G)
+        self.last_logits = list(map_2.detach().split(B, dim=0))
         weit = ops.structure_weit(mask)
         total, per = 0.0, 0.0
         for c, mp in ((0.5, map_2), (0.3, map_1), (0.2, map_x)):

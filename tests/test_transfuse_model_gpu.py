@@ -441,3 +441,32 @@ def test_dropout2d_drops_whole_planes_and_backward_reuses_the_mask():
     assert torch.allclose(x.grad, ratio)                       # same mask in backward
     y2 = ops.Dropout2dFn.apply(x, p)                           # another call site -> another stream id -> another mask
     assert not torch.equal(y2 > 0, y > 0)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_five_step_trajectory_matches_reference_golden(fused):
+    """5 AdamW steps of the reference's training loop (multi_train_TransFuse.py:145-197; oracle/make_golden_transfuse_traj.py ran the
+    UNMODIFIED reference): per-step per-dataset losses and the hard Dice of the joint prediction.  The loss falls 1.6 -> 0.58 and
+    Dice rises 0.31 -> 0.95 over these steps; at lr 1e-3 the trajectory amplifies operand rounding: the fp32 CPU run with only
+    TF32-rounded conv operands and bf16-rounded conv output gradients ends 3-4 % (loss) / 1.6e-2 (Dice) from the reference
+    (DESIGN.md section 11), which sets the tolerance here (not the 1e-3 Dice bound MDViT's own trajectory test meets)."""
+    from mdvit_b200 import ops, transfuse as T
+    from mdvit_b200.train_step import TransFuseTrainer
+    from oracle.make_golden_transfuse_traj import LR, STEPS, WD, batches
+    dev = _dev()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "transfuse_traj_golden.npz"))
+    torch.manual_seed(0)
+    m = T.TransFuse_S_adapt(drop_rate=0.0).to(dev).train()
+    tr = TransFuseTrainer(m, lr=LR, weight_decay=WD, fuse_datasets=fused)
+    bs = [(i.to(dev), k.to(dev), d) for i, k, d in batches()]
+    losses, dice = [], []
+    for _ in range(STEPS):
+        ls = tr.step(bs)
+        losses.append(ls.cpu().numpy())
+        dice.append([ops.dice_jaccard(ops.seg_counts(lg, b[1]))[0] for lg, b in zip(tr.last_logits, bs)])
+    losses, dice = np.asarray(losses, np.float64), np.asarray(dice, np.float64)
+    print("loss rel err per step", np.abs(losses / g["losses"] - 1).max(axis=1), "dice abs err per step", np.abs(dice - g["dice"]).max(axis=1))
+    np.testing.assert_allclose(losses[0], g["losses"][0], rtol=2e-3)                 # before any update: the forward alone
+    np.testing.assert_allclose(losses, g["losses"], rtol=8e-2)
+    assert np.abs(dice - g["dice"]).max() < 4e-2
+    assert losses[-1].max() < 0.75 * losses[0].min() and dice[-1].min() > 0.9         # it trains
