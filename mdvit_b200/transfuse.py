@@ -169,12 +169,23 @@ class DeiT_adapt(nn.Module):
         return ops.LayerNormOutFn.apply(t, self.norm.weight, self.norm.bias, float(self.norm.eps))
 
 
+def load_pretrain(model, pre_s_dict):
+    """DeiT.py:74-90: copy the entries of `pre_s_dict` whose keys the model has, keep the model's own values for the rest
+    (the reference passes the checkpoint file's top-level dict, so with the published DeiT file — {'model': ...} — nothing
+    matches and the model keeps its initialisation; the behaviour is reproduced as is)."""
+    s_dict = model.state_dict()
+    missing = [k for k in s_dict if k not in pre_s_dict]
+    print('{} keys are not in the pretrain model:'.format(len(missing)), missing)
+    model.load_state_dict({k: (pre_s_dict[k] if k in pre_s_dict else v) for k, v in s_dict.items()})
+    return model
+
+
 def deit_small_patch16_224_adapt(pretrained=False, pretrained_folder=None, num_domains=4, **kwargs):
     """DeiT.py:157-181: DeiT-S (384 wide, depth 8, 6 heads) with pos_embed resampled to a 16 x 16 grid (256 tokens), no head."""
-    if pretrained:
-        raise NotImplementedError("loading the ImageNet checkpoint is the reference's job: load_state_dict() the result here")
     model = DeiT_adapt(patch_size=16, embed_dim=384, depth=8, num_heads=6, mlp_ratio=4, qkv_bias=True,
                        norm_layer=partial(nn.LayerNorm, eps=1e-6), num_domains=num_domains, **kwargs)
+    if pretrained:      # DeiT.py:125-127
+        load_pretrain(model, torch.load(pretrained_folder + '/pretrained/deit_small_patch16_224-cd65a155.pth'))
     pe = model.pos_embed[:, 1:, :].detach().transpose(-1, -2)
     g = int(math.sqrt(pe.shape[2]))
     pe = torch.nn.functional.interpolate(pe.reshape(pe.shape[0], pe.shape[1], g, g), size=(16, 16), mode='bilinear', align_corners=True)
@@ -468,9 +479,7 @@ class TransFuse_S_adapt(nn.Module):
             self.resnet.load_state_dict(torch.load(pretrained_folder + '/pretrained/resnet34-333f7ec4.pth'))
         self.resnet.fc = nn.Identity()
         self.resnet.layer4 = nn.Identity()
-        self.transformer = deit_small_patch16_224_adapt(pretrained=False, pretrained_folder=pretrained_folder, num_domains=num_domains)
-        if pretrained:
-            raise NotImplementedError("load the DeiT checkpoint with load_state_dict() (see deit_small_patch16_224_adapt)")
+        self.transformer = deit_small_patch16_224_adapt(pretrained=pretrained, pretrained_folder=pretrained_folder, num_domains=num_domains)
         self.up1 = Up(in_ch1=384, out_ch=128)
         self.up2 = Up(128, 64)
         self.final_x = nn.Sequential(Conv(256, 64, 1, bn=True, relu=True), Conv(64, 64, 3, bn=True, relu=True),
