@@ -171,3 +171,44 @@ def test_stacked_multi_dataset_forward_equals_consecutive_forwards(emulated):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
     for k in bufs[0]:
         assert torch.allclose(bufs[0][k].float(), bufs[1][k].float(), rtol=1e-4, atol=1e-6), k
+
+
+def test_trainer_stacked_loss_equals_per_dataset_losses(emulated, monkeypatch):
+    """TransFuseTrainer host logic: the stacked schedule back-propagates G x mean(per-sample terms over the whole stack) and reports
+    group means — the same numbers as one forward + three structure losses per dataset (multi_train_TransFuse.py:151-172,191),
+    and the same gradients."""
+    from mdvit_b200.train_step import TransFuseTrainer
+    from oracle.make_golden_transfuse_model import structure_loss_ref
+
+    def weit_ref(mask):
+        return 1 + 5 * torch.abs(F.avg_pool2d(mask, kernel_size=31, stride=1, padding=15) - mask)
+
+    def loss_ref(pred, mask, weit=None, per_sample=False):
+        weit = weit_ref(mask) if weit is None else weit
+        wbce = (weit * F.binary_cross_entropy_with_logits(pred, mask, reduction="none")).sum(dim=(2, 3)) / weit.sum(dim=(2, 3))
+        p = torch.sigmoid(pred)
+        inter, union = ((p * mask) * weit).sum(dim=(2, 3)), ((p + mask) * weit).sum(dim=(2, 3))
+        ps = (wbce + 1 - (inter + 1) / (union - inter + 1)).flatten()
+        return (ps.mean(), ps.detach()) if per_sample else ps.mean()
+
+    monkeypatch.setattr(ops, "structure_weit", weit_ref)
+    monkeypatch.setattr(ops, "structure_loss", loss_ref)
+    img, mask, _ = case(B=4, side=64)
+    assert abs(loss_ref(img[:, :1], mask).item() - structure_loss_ref(img[:, :1], mask).item()) < 1e-6
+    batches = [(img[:2], mask[:2], 1), (img[2:], mask[2:], 3)]
+    res = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        m = T.TransFuse_S_adapt(drop_rate=0.0).train()
+        with torch.no_grad():
+            m.transformer.pos_embed = torch.nn.Parameter(0.02 * torch.randn(1, 16, 384))      # 64 x 64 images: 4 x 4 tokens
+        tr = TransFuseTrainer(m, fuse_datasets=fused)
+        losses = tr.forward_losses(batches)
+        total = tr._total_loss if tr._total_loss is not None else losses.sum()
+        assert (tr._total_loss is not None) == fused
+        total.backward()
+        assert len(tr.last_logits) == 2 and tuple(tr.last_logits[0].shape) == (2, 1, 64, 64)
+        res.append((losses.detach().clone(), total.item(), tr.grad.clone()))
+    (l0, t0, g0), (l1, t1, g1) = res
+    assert torch.allclose(l0, l1, rtol=1e-4) and abs(t0 - t1) < 1e-4 * abs(t1) and abs(t0 - l0.sum().item()) < 1e-4 * abs(t0)
+    assert ((g0 - g1).norm() / g1.norm()).item() < 2e-2      # (fp32 reordering through this ill-conditioned net, see DESIGN.md section 11)
