@@ -248,11 +248,11 @@ def _bn1(z, bn, H, W):
         if bn.training:
             bn.num_batches_tracked.add_(1)      # (nn.BatchNorm2d.forward does this; the functional does not)
         return F.batch_norm(z.view(B, 1, H, W), bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps).view(B, H * W, 1)
-    zg = z.reshape(G, -1)
-    n = zg.shape[1]
-    mean = zg.mean(dim=1, keepdim=True)
-    var = zg.var(dim=1, unbiased=False, keepdim=True)
-    y = (zg - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
+    zg = z.reshape(1, G, -1)      # groups as the channel axis of one batch_norm call (one kernel forward, one backward)
+    n = zg.shape[2]
+    y = F.batch_norm(zg, None, None, bn.weight.expand(G), bn.bias.expand(G), True, 0.0, bn.eps)
+    with torch.no_grad():
+        var, mean = torch.var_mean(zg[0], dim=1, unbiased=False)
     mom = bn.momentum
     key = (G, mom, z.device)
     coef = _BN1_COEF.get(key)
