@@ -433,7 +433,12 @@ def run_transfuse(args):
     if rank == 0:
         sampler.start()
     n0 = lib.mdv_launch_count()
+    ncu_range = bool(int(os.environ.get("MDV_NCU_RANGE", "0")))     # `ncu --profile-from-start off`: capture exactly the timed steps
+    if ncu_range:
+        torch.cuda.profiler.start()
     ms_res, _ = timed(step_resident, args.steps, False)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     n1 = lib.mdv_launch_count()
     ms_e2e, loss_host = timed(step_e2e, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
