@@ -16,89 +16,8 @@ from tests.helpers import fingerprint
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "transfuse_model_golden.npz")
 
 
-def _emu_bn(z, bufs, gamma, beta, training):
-    """nn.BatchNorm2d on NCHW; under ops.bn_groups(G): G consecutive calls on the G batch chunks (what the grouped kernels compute)"""
-    G = ops.current_bn_groups() if training else 1
-    out = torch.cat([F.batch_norm(c, bufs[0], bufs[1], gamma, beta, training, 0.1, 1e-5) for c in z.chunk(G)])
-    if training:
-        bufs[2].add_(G)
-    return out
-
-
-class _EmuConv:
-    @staticmethod
-    def apply(x, w, cbias, gamma, beta, residual, bufs, B, H, W, stride, act, training, nchw):
-        k = w.shape[2]
-        xin = x if nchw else x.view(B, H, W, -1).permute(0, 3, 1, 2)
-        z = F.conv2d(xin, w, cbias, stride, (k - 1) // 2)
-        if gamma is not None:
-            z = _emu_bn(z, bufs, gamma, beta, training)
-        y = z.permute(0, 2, 3, 1).reshape(B, -1, w.shape[0])
-        if gamma is None and act == ops.ACT_RELU:
-            y = torch.relu(y)
-        if residual is not None:
-            y = y + residual
-        if gamma is not None and act == ops.ACT_RELU:
-            y = torch.relu(y)
-        return y
-
-
-class _EmuBn:
-    @staticmethod
-    def apply(x, gamma, beta, bufs, act, training):
-        y = _emu_bn(x.transpose(1, 2).unsqueeze(-1), bufs, gamma, beta, training).squeeze(-1).transpose(1, 2)
-        return torch.relu(y) if act == ops.ACT_RELU else y
-
-
-class _EmuPool:
-    @staticmethod
-    def apply(x, H, W):
-        B, _, C = x.shape
-        y = F.max_pool2d(x.view(B, H, W, C).permute(0, 3, 1, 2), 3, 2, 1)
-        return y.permute(0, 2, 3, 1).reshape(B, -1, C)
-
-
-class _EmuResize:
-    @staticmethod
-    def apply(x, H, W, Ho, Wo):
-        B, _, C = x.shape
-        y = F.interpolate(x.view(B, H, W, C).permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=True)
-        return y.permute(0, 2, 3, 1).reshape(B, -1, C)
-
-
-class _EmuGateCat:
-    @staticmethod
-    def apply(g, p, x, v, bp):
-        parts = [g * p]
-        if x is not None:
-            parts.append(x * v.unsqueeze(1))
-        if bp is not None:
-            parts.append(bp)
-        return torch.cat(parts, dim=2) if len(parts) > 1 else parts[0]
-
-
-class _EmuChannelPool:
-    @staticmethod
-    def apply(x):
-        return torch.cat((x.max(dim=2, keepdim=True)[0], x.mean(dim=2, keepdim=True)), dim=2)
-
-
-def deit_forward_torch(tr, imgs, label):
-    """plain-torch DeiT-S-adapt forward over the module's parameters (vision_transformer.py:125-211,322-389; DeiT.py:116-139)"""
-    x = F.conv2d(imgs, tr.patch_embed.proj.weight, tr.patch_embed.proj.bias, stride=16).flatten(2).transpose(1, 2) + tr.pos_embed
-    for blk in tr.blocks:
-        a = blk.attn
-        B, N, C = x.shape
-        h = F.layer_norm(x, (C,), blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
-        qkv = a.qkv(h).reshape(B, N, 3, a.num_heads, C // a.num_heads).permute(2, 0, 3, 1, 4)
-        att = ((qkv[0] @ qkv[1].transpose(-2, -1)) * a.scale).softmax(dim=-1)
-        o = att @ qkv[2]                                                              # [B, heads, N, 64]
-        gate = a.domain_layer(label).reshape(B, a.num_heads, 1, C // a.num_heads).softmax(dim=1)
-        o = (o * gate).transpose(1, 2).reshape(B, N, C)
-        x = x + a.proj(o)
-        h = F.layer_norm(x, (C,), blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-        x = x + blk.mlp.fc2(F.gelu(blk.mlp.fc1(h)))
-    return F.layer_norm(x, (x.shape[-1],), tr.norm.weight, tr.norm.bias, tr.norm.eps)
+from oracle.transfuse_oracle import (EmuBn as _EmuBn, EmuChannelPool as _EmuChannelPool, EmuConv as _EmuConv,      # noqa: E402,F401
+                                     EmuGateCat as _EmuGateCat, EmuPool as _EmuPool, EmuResize as _EmuResize, deit_forward_torch)
 
 
 @pytest.fixture()
